@@ -1,0 +1,164 @@
+/*
+ * kss_icp_b200.h -- C ABI of the B200-native KSS-ICP registration hot path.
+ *
+ * The reference (vvvwo/KSS-ICP) has no FFI boundary: the path is reached through two
+ * header-only C++ classes (KSS_ICP.hpp, initRegistrationKSS.hpp) plus PCR_QM
+ * (registrationMeasure.hpp) that call PCL 1.8.1 directly.  Each entry point below
+ * replaces the body of one of those methods; the same-named C++ classes in
+ * kss-icp_b200/host/ forward to them.
+ *
+ * Conventions
+ *   - clouds are packed double[n][3] (the flattened vector<vector<double>> of the reference);
+ *     narrowing to float happens on the device with round-to-nearest exactly where the
+ *     reference narrows (KSS_ICP.hpp:328-333, initRegistrationKSS.hpp:231-235, 440-442).
+ *   - every function returns 0 on success, a negative KSS_ERR_* otherwise;
+ *     kss_last_error(ctx) gives the message.  Nothing throws, nothing falls back to the CPU.
+ *   - the caller owns all host buffers; the library owns device memory inside ctx.
+ *   - one host thread per ctx; one ctx per GPU; different ctx may run concurrently.
+ *   - "_device" variants take device pointers on ctx's device and enqueue on ctx's stream.
+ */
+#ifndef KSS_ICP_B200_H
+#define KSS_ICP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KSS_OK               0
+#define KSS_ERR_ARG         -1   /* bad argument (null pointer, n < 1, ...)              */
+#define KSS_ERR_CUDA        -2   /* a CUDA runtime call failed (message in last_error)  */
+#define KSS_ERR_UNSUPPORTED -3   /* size / mode outside what this build implements      */
+#define KSS_ERR_NCCL        -4
+#define KSS_ERR_NOMEM       -5
+
+#define KSS_SMALL_MAX 2048       /* clouds up to this size run on the shared-memory path */
+
+/* sweep score modes: live one is AVE (initRegistrationKSS.hpp:255); the dead siblings
+ * _Error (:406-428) and _Error_Diff (:452-479) stay selectable */
+#define KSS_SCORE_AVE  0
+#define KSS_SCORE_MAX  1
+#define KSS_SCORE_DIFF 2
+
+typedef struct kss_ctx kss_ctx;
+
+/* ICP parameters as set at KSS_ICP.hpp:156-159 (defaults of kss_icp_params_default). */
+typedef struct kss_icp_params {
+    int    max_iterations;        /* setMaximumIterations        (1000, Main_KSS_ICP.cpp:81) */
+    double max_corr_dist;         /* setMaxCorrespondenceDistance (1)     */
+    double transformation_eps;    /* setTransformationEpsilon     (1e-10) */
+    double fitness_eps;           /* setEuclideanFitnessEpsilon   (0.001) */
+} kss_icp_params;
+
+/* optional per-iteration trace of kss_icp (tests): any pointer may be NULL */
+typedef struct kss_icp_trace {
+    int      cap_iters;
+    int32_t* corr_idx;            /* [cap_iters][n_s] target index per source point, -1 = rejected */
+    float*   T_k;                 /* [cap_iters][16] */
+    double*  mse;                 /* [cap_iters]     */
+    float*   src_k;               /* [cap_iters][n_s][3] source cloud before the iteration */
+} kss_icp_trace;
+
+/* result of one registration (KSSICP_Registration + PCR_QM) */
+typedef struct kss_pair_result {
+    double align[8];              /* x_middle_S,y,z ; x_middle,y,z ; scale ; pad (initRegistrationKSS.hpp:38-44) */
+    double judge_fitness;         /* E_d_init (KSS_ICP.hpp:93)  */
+    double final_fitness;         /* resultFitness (KSS_ICP.hpp:130) */
+    double mse, rmse, mae;        /* PCR_QM (registrationMeasure.hpp:83-96) */
+    float  T[16];                 /* icp.getFinalTransformation(), row-major */
+    int    G;                     /* angles per axis (9 at step 8) */
+    int    best_h;                /* flattened (i*G+j)*G+k index of the sweep winner */
+    int    n_minima;              /* |angleList| */
+    int    branch_multi;          /* 1 iff judge_fitness > 0.0005 (KSS_ICP.hpp:99) */
+    int    winner;                /* angleList index chosen (KSS_ICP.hpp:113-116), -1 otherwise */
+    int    used_h;                /* flattened index of the angles finally applied */
+    int    use_list;              /* 1: used angles are index*6.3/step, 0: accumulated loop values */
+    int    judge_iters, final_iters, total_icp_iters, n_icp_runs;
+    int    overflow;              /* internal: hypothesis slots were exhausted and the pair was re-run */
+} kss_pair_result;
+
+/* batch of registrations: arrays are [n_pairs][cap][3] doubles, counts optional (NULL = cap) */
+typedef struct kss_batch {
+    int n_pairs;
+    int cap_s, cap_t;             /* simplified clouds (<= KSS_SMALL_MAX)          */
+    int cap_S, cap_T;             /* full-resolution clouds                        */
+    const double* sim_s;          /* AIVS-simplified source  (pointCloudS, KSS_ICP.hpp:81) */
+    const double* sim_t;          /* AIVS-simplified target  (pointCloudT, KSS_ICP.hpp:75) */
+    const double* full_s;         /* pointSource */
+    const double* full_t;         /* pointTarget */
+    const int* cnt_s; const int* cnt_t; const int* cnt_S; const int* cnt_T;
+    double step;                  /* `accurate` of KSSICP_init (8, Main_KSS_ICP.cpp:80) */
+    kss_icp_params icp;
+    double judge_threshold;       /* 0.0005 (KSS_ICP.hpp:99) */
+} kss_batch;
+
+/* ---- context ------------------------------------------------------------------------ */
+int  kss_ctx_create(int device, kss_ctx** out);
+int  kss_ctx_create_on_stream(int device, void* cuda_stream, kss_ctx** out);
+void kss_ctx_destroy(kss_ctx* ctx);
+const char* kss_last_error(kss_ctx* ctx);
+int  kss_ctx_synchronize(kss_ctx* ctx);
+void kss_icp_params_default(kss_icp_params* p);
+void kss_batch_default(kss_batch* b);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+long long kss_ctx_launch_count(kss_ctx* ctx);
+
+/* ---- single-object entry points ------------------------------------------------------ */
+
+/* replaces initRegistration_KSS::initRegistration_MiddleAlign (initRegistrationKSS.hpp:144-220).
+ * out7 = {x_middle_S,y,z, x_middle,y,z, scale}; src_aligned [n_s][3] optional. */
+int kss_middle_align(kss_ctx* ctx, const double* src, int n_s, const double* tgt, int n_t,
+                     double out7[7], double* src_aligned);
+
+/* the angle grid of initRegistrationKSS.hpp:245 (host arithmetic only): returns G */
+int kss_sweep_angles(double step, double* accum, double* list, int cap);
+
+/* replaces initRegistration_KSS::initRegistration_Rotation() (initRegistrationKSS.hpp:222-296,
+ * 430-450, 481-522).  src_aligned is the cloud MiddleAlign produced.  value [G^3]; best_angle =
+ * accumulated loop values; minima [<=G^3][3] grid indices in loop order (angleList = idx*6.3/step). */
+int kss_rotation_sweep(kss_ctx* ctx, const double* src_aligned, int n_s, const double* tgt, int n_t,
+                       double step, int score_mode, double* value, int* G_out,
+                       double best_angle[3], int best_index[3], int* minima, int* n_minima);
+
+/* replaces initRegistration_Rotation(src) / _Rotation_Angle(src, angle) (initRegistrationKSS.hpp:75-109) */
+int kss_apply_similarity(kss_ctx* ctx, const double* pts, int n, const double align7[7],
+                         const double angles[3], double* out);
+
+/* replaces one pcl::IterativeClosestPoint run as wrapped by shapeRegistration_ICP_Judge /
+ * _AngleList / _ICP (KSS_ICP.hpp:185-274, 323-356): T row-major 4x4, fitness = getFitnessScore(). */
+int kss_icp(kss_ctx* ctx, const double* src, int n_s, const double* tgt, int n_t,
+            const kss_icp_params* prm, float T[16], double* fitness, int* iters, int* converged,
+            kss_icp_trace* trace);
+
+/* replaces the final apply loop at KSS_ICP.hpp:222-230 */
+int kss_apply_transform(kss_ctx* ctx, const float T[16], const double* pts, int n, double* out);
+
+/* replaces PCR_QM::PCR_QM_Start (registrationMeasure.hpp:47-98): out3 = {MSE, RMSE, MAE} */
+int kss_nn_metrics(kss_ctx* ctx, const double* a, int n_a, const double* t, int n_t, double out3[3]);
+
+/* exact 1-NN (replaces pcl::KdTreeFLANN::nearestKSearch, K=1): idx into t, squared distance (float).
+ * Tie rule: lowest target index among fp32-equal distances. */
+int kss_nn_search(kss_ctx* ctx, const double* q, int n_q, const double* t, int n_t,
+                  int32_t* idx, float* d2);
+
+/* ---- batched registration (KSSICP_Registration after simplification + PCR_QM) --------- */
+
+/* host buffers in, host results out (H2D/D2H inside). point_align [n_pairs][cap_S][3] optional. */
+int kss_register_batch(kss_ctx* ctx, const kss_batch* b, kss_pair_result* results, double* point_align);
+
+/* device buffers in (b->* are device pointers), results/point_align are device pointers;
+ * everything is enqueued on ctx's stream; call kss_ctx_synchronize before reading. */
+int kss_register_batch_device(kss_ctx* ctx, const kss_batch* b, kss_pair_result* d_results,
+                              double* d_point_align);
+
+/* one pair, the exact flow of KSSICP_Registration (KSS_ICP.hpp:86-130) */
+int kss_register(kss_ctx* ctx, const double* sim_s, int n_s, const double* sim_t, int n_t,
+                 const double* full_s, int N_s, const double* full_t, int N_t,
+                 double step, int max_iter, kss_pair_result* result, double* point_align);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,601 @@
+// kss_api.cu -- the C ABI (include/kss_icp_b200.h): context, device memory, host<->device
+// copies and the kernel pipelines.  No computation of the path happens on the host; the only
+// host arithmetic is the angle grid and its libm cos/sin tables, which the reference also
+// evaluates on the CPU (initRegistrationKSS.hpp:245, 371-397).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kss_kernels.h"
+#include "kss_large.h"
+
+using namespace kss;
+
+struct kss_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    long long launches = 0;
+    // angle grid cache
+    double step = -1.0;
+    int G = 0;
+    std::vector<double> accum, list;
+    double* d_trig_accum = nullptr;   // [G][2] cos, sin of the accumulated loop values
+    double* d_trig_list = nullptr;    // [G][2] cos, sin of index*6.3/step
+    // grow-only named device buffers
+    struct Buf { void* p = nullptr; size_t cap = 0; };
+    std::map<std::string, Buf> bufs;
+    size_t ws_budget = (size_t)6 << 30;
+    int slots_override = 0;
+};
+
+namespace {
+
+int fail(kss_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            char b_[512];                                                                     \
+            snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                     __FILE__, __LINE__);                                                     \
+            return fail(ctx, KSS_ERR_CUDA, b_);                                               \
+        }                                                                                     \
+    } while (0)
+
+#define KL(call)        \
+    do {                \
+        CU(call);       \
+        ctx->launches++;\
+    } while (0)
+
+template <class T>
+int dev_buf(kss_ctx* ctx, const char* name, size_t count, T** out) {
+    kss_ctx::Buf& b = ctx->bufs[name];
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    if (b.cap < bytes) {
+        if (b.p) { cudaStreamSynchronize(ctx->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&b.p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            char m[256];
+            snprintf(m, sizeof(m), "cudaMalloc(%zu bytes) for '%s' failed: %s", bytes, name, cudaGetErrorString(e));
+            return fail(ctx, KSS_ERR_NOMEM, m);
+        }
+        b.cap = want;
+    }
+    *out = reinterpret_cast<T*>(b.p);
+    return KSS_OK;
+}
+#define BUF(name, count, ptr)                              \
+    do {                                                   \
+        int r_ = dev_buf(ctx, name, (size_t)(count), ptr); \
+        if (r_ != KSS_OK) return r_;                       \
+    } while (0)
+
+__global__ void fill_int_kernel(int* p, int n, int v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+int angle_grid(double step, std::vector<double>& accum, std::vector<double>& list) {
+    accum.clear(); list.clear();
+    if (!(step > 0.0) || 6.3 / step < 1e-3) return 0;
+    int g = 0;
+    for (double a = 0; a < 6.3; a = a + 6.3 / step) {      // initRegistrationKSS.hpp:245
+        accum.push_back(a);
+        list.push_back((double)g * 6.3 / (double)step);    // initRegistrationKSS.hpp:282-284
+        ++g;
+    }
+    return g;
+}
+
+int ensure_trig(kss_ctx* ctx, double step) {
+    if (ctx->step == step && ctx->G > 0) return KSS_OK;
+    int G = angle_grid(step, ctx->accum, ctx->list);
+    if (G < 1 || G > 16) return fail(ctx, KSS_ERR_UNSUPPORTED, "step gives an angle grid outside 1..16 per axis");
+    std::vector<double> ta(2 * G), tl(2 * G);
+    for (int g = 0; g < G; ++g) {
+        ta[2 * g] = std::cos(ctx->accum[g]); ta[2 * g + 1] = std::sin(ctx->accum[g]);
+        tl[2 * g] = std::cos(ctx->list[g]);  tl[2 * g + 1] = std::sin(ctx->list[g]);
+    }
+    BUF("trig_accum", 2 * 16, &ctx->d_trig_accum);
+    BUF("trig_list", 2 * 16, &ctx->d_trig_list);
+    CU(cudaMemcpyAsync(ctx->d_trig_accum, ta.data(), sizeof(double) * 2 * G, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_trig_list, tl.data(), sizeof(double) * 2 * G, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));     // ta/tl are stack-owned
+    ctx->step = step; ctx->G = G;
+    return KSS_OK;
+}
+
+int counts_or_fill(kss_ctx* ctx, const char* name, const int* d_cnt, int P, int cap, const int** out) {
+    if (d_cnt) { *out = d_cnt; return KSS_OK; }
+    int* p;
+    BUF(name, P, &p);
+    fill_int_kernel<<<(P + 255) / 256, 256, 0, ctx->stream>>>(p, P, cap);
+    KL(cudaGetLastError());
+    *out = p;
+    return KSS_OK;
+}
+
+inline int pad32(int n) { return (n + 31) / 32 * 32; }
+
+void icp_fill(IcpArgs& a, const kss_icp_params& prm) {
+    a.max_iter = prm.max_iterations;
+    a.max_dist_sqr = prm.max_corr_dist * prm.max_corr_dist;
+    a.rot_thr = 1.0 - prm.transformation_eps;
+    a.trans_thr = prm.transformation_eps;
+    a.mse_rel = prm.fitness_eps;
+    a.mse_abs = 1e-12;
+}
+
+// The whole KSSICP_Registration flow for pairs [0, P) whose inputs are device resident.
+// All kernels go to ctx->stream, no host synchronisation.
+int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s, const double* sim_t,
+                    const double* full_s, const double* full_t, const int* cnt_s, const int* cnt_t,
+                    const int* cnt_S, const int* cnt_T, int slots, kss_pair_result* d_out, double* d_point_align) {
+    cudaStream_t st = ctx->stream;
+    const int G = ctx->G, H = G * G * G, hpad = H;
+    const int cap_s = b.cap_s, cap_t = b.cap_t, cap_S = b.cap_S, cap_T = b.cap_T;
+    const int cap_tpad = pad32(cap_t), cap_Tpad = pad32(cap_T);
+    const int R = 1 + slots;
+    double *align8, *s_al, *rbuf, *value, *run_fit;
+    unsigned short *s_perm, *t_inv, *S_perm, *T_inv;
+    float4 *t_sorted, *T_sorted;
+    float *t_box, *T_box, *run_T;
+    int *best_h, *minima, *n_minima, *run_iters, *run_conv;
+    BUF("align8", (size_t)P * 8, &align8);
+    BUF("s_al", (size_t)P * cap_s * 3, &s_al);
+    BUF("s_perm", (size_t)P * cap_s, &s_perm);
+    BUF("t_sorted", (size_t)P * cap_tpad, &t_sorted);
+    BUF("t_box", (size_t)P * 6 * MAX_TILES, &t_box);
+    BUF("t_inv", (size_t)P * cap_t, &t_inv);
+    BUF("rbuf", (size_t)P * cap_s * hpad, &rbuf);
+    BUF("value", (size_t)P * hpad, &value);
+    BUF("best_h", (size_t)P, &best_h);
+    BUF("minima", (size_t)P * hpad, &minima);
+    BUF("n_minima", (size_t)P, &n_minima);
+    BUF("run_T", (size_t)P * R * 16, &run_T);
+    BUF("run_fit", (size_t)P * R, &run_fit);
+    BUF("run_iters", (size_t)P * R, &run_iters);
+    BUF("run_conv", (size_t)P * R, &run_conv);
+
+    KL(launch_middle_align(st, P, sim_s, cnt_s, cap_s, sim_t, cnt_t, cap_t, align8, s_al));
+    KL(launch_sort_target(st, P, sim_t, cnt_t, cap_t, t_sorted, t_box, t_inv, cap_tpad));
+    KL(launch_sort_source(st, P, sim_s, cnt_s, cap_s, s_perm));
+    KL(launch_sweep(st, P, s_al, cnt_s, cap_s, s_perm, t_sorted, t_box, cnt_t, cap_tpad, ctx->d_trig_accum, G,
+                    KSS_SCORE_AVE, rbuf, hpad));
+    KL(launch_sweep_finalize(st, P, rbuf, cnt_s, cap_s, hpad, G, KSS_SCORE_AVE, value, best_h, minima, n_minima));
+
+    IcpArgs a{};
+    a.src_f64 = sim_s; a.cnt_s = cnt_s; a.cap_s = cap_s; a.s_perm = s_perm;
+    a.t_sorted = t_sorted; a.t_box = t_box; a.t_inv = t_inv; a.cnt_t = cnt_t; a.cap_t = cap_t; a.cap_tpad = cap_tpad;
+    a.align8 = align8; a.runs_per_pair = R; a.hpad = hpad; a.G = G;
+    a.best_h = best_h; a.minima = minima; a.n_minima = n_minima;
+    a.trig_accum = ctx->d_trig_accum; a.trig_list = ctx->d_trig_list;
+    a.judge_thr = b.judge_threshold;
+    icp_fill(a, b.icp);
+    a.run_T = run_T; a.run_fit = run_fit; a.run_iters = run_iters; a.run_conv = run_conv;
+    a.mode = 0;
+    KL(launch_icp(st, P, 1, a));                           // judge run (KSS_ICP.hpp:93)
+    a.mode = 1;
+    if (slots > 0) KL(launch_icp(st, P, slots, a));        // hypothesis runs (KSS_ICP.hpp:102-118)
+    KL(launch_select(st, P, R, hpad, G, b.judge_threshold, align8, run_fit, run_iters, run_T, best_h, minima,
+                     n_minima, d_out));
+
+    double* pa = d_point_align;
+    if (!pa) BUF("point_align", (size_t)P * cap_S * 3, &pa);
+    KL(launch_final_apply(st, P, full_s, cnt_S, cap_S, align8, d_out, ctx->d_trig_accum, ctx->d_trig_list, G, pa));
+    if (cap_T <= SMALL_MAX && cap_S <= SMALL_MAX) {
+        BUF("S_perm", (size_t)P * cap_S, &S_perm);
+        BUF("T_sorted", (size_t)P * cap_Tpad, &T_sorted);
+        BUF("T_box", (size_t)P * 6 * MAX_TILES, &T_box);
+        BUF("T_inv", (size_t)P * cap_T, &T_inv);
+        KL(launch_sort_target(st, P, full_t, cnt_T, cap_T, T_sorted, T_box, T_inv, cap_Tpad));
+        KL(launch_sort_source(st, P, full_s, cnt_S, cap_S, S_perm));
+        KL(launch_nn_small(st, P, 1, pa, cnt_S, cap_S, S_perm, T_sorted, T_box, cnt_T, cap_Tpad, nullptr, nullptr,
+                           &d_out[0].mse, (int)(sizeof(kss_pair_result) / sizeof(double))));
+    } else {
+        // full-resolution clouds beyond the shared-memory path: uniform-grid NN, pair by pair
+        for (int p = 0; p < P; ++p) {
+            int r = large_metrics_device(ctx->stream, &ctx->launches, pa + (size_t)p * cap_S * 3, cnt_S + p, cap_S,
+                                         full_t + (size_t)p * cap_T * 3, cnt_T + p, cap_T, &d_out[p].mse,
+                                         [&](const char* name, size_t bytes, void** out) {
+                                             unsigned char* q; int rr = dev_buf(ctx, name, bytes, &q); *out = q; return rr; });
+            if (r != KSS_OK) return fail(ctx, r, "large-cloud metrics failed");
+        }
+    }
+    return KSS_OK;
+}
+
+size_t per_pair_ws_bytes(const kss_batch& b, int H, int slots) {
+    size_t v = (size_t)b.cap_s * H * 8 + (size_t)b.cap_s * 30 + (size_t)pad32(b.cap_t) * 18 + (size_t)H * 12 +
+               (size_t)(1 + slots) * 96 + (size_t)b.cap_S * 26 + (size_t)pad32(b.cap_T) * 18 + 8192;
+    return v;
+}
+
+int check_batch(kss_ctx* ctx, const kss_batch* b) {
+    if (!ctx) return KSS_ERR_ARG;
+    if (!b || b->n_pairs < 1 || !b->sim_s || !b->sim_t || !b->full_s || !b->full_t)
+        return fail(ctx, KSS_ERR_ARG, "kss_batch: null pointer or n_pairs < 1");
+    if (b->cap_s < 1 || b->cap_t < 1 || b->cap_S < 1 || b->cap_T < 1) return fail(ctx, KSS_ERR_ARG, "kss_batch: empty cloud");
+    if (b->cap_s > SMALL_MAX || b->cap_t > SMALL_MAX)
+        return fail(ctx, KSS_ERR_UNSUPPORTED, "simplified clouds must have <= 2048 points (reference caps pNumber at 2000)");
+    return KSS_OK;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+void kss_icp_params_default(kss_icp_params* p) {
+    p->max_iterations = 1000; p->max_corr_dist = 1.0; p->transformation_eps = 1e-10; p->fitness_eps = 0.001;
+}
+void kss_batch_default(kss_batch* b) {
+    std::memset(b, 0, sizeof(*b));
+    b->step = 8.0; b->judge_threshold = 0.0005;
+    kss_icp_params_default(&b->icp);
+}
+
+int kss_ctx_create_on_stream(int device, void* cuda_stream, kss_ctx** out) {
+    if (!out) return KSS_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return KSS_ERR_CUDA; }
+    if (device < 0 || device >= ndev) return KSS_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return KSS_ERR_CUDA;
+    kss_ctx* c = new kss_ctx();
+    c->device = device;
+    if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return KSS_ERR_CUDA; }
+        c->own_stream = true;
+    }
+    const char* ws = getenv("KSS_WS_BYTES");
+    if (ws) { long long v = atoll(ws); if (v > (1ll << 26)) c->ws_budget = (size_t)v; }
+    *out = c;
+    return KSS_OK;
+}
+int kss_ctx_create(int device, kss_ctx** out) { return kss_ctx_create_on_stream(device, nullptr, out); }
+
+void kss_ctx_destroy(kss_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->bufs) if (kv.second.p) cudaFree(kv.second.p);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+const char* kss_last_error(kss_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+long long kss_ctx_launch_count(kss_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int kss_ctx_synchronize(kss_ctx* ctx) {
+    if (!ctx) return KSS_ERR_ARG;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KSS_OK;
+}
+
+int kss_sweep_angles(double step, double* accum, double* list, int cap) {
+    std::vector<double> a, l;
+    int g = angle_grid(step, a, l);
+    for (int i = 0; i < g && i < cap; ++i) { if (accum) accum[i] = a[i]; if (list) list[i] = l[i]; }
+    return g;
+}
+
+int kss_middle_align(kss_ctx* ctx, const double* src, int n_s, const double* tgt, int n_t, double out7[7],
+                     double* src_aligned) {
+    if (!ctx) return KSS_ERR_ARG;
+    if (!src || !tgt || !out7 || n_s < 1 || n_t < 1) return fail(ctx, KSS_ERR_ARG, "kss_middle_align: bad argument");
+    if (n_s > SMALL_MAX || n_t > SMALL_MAX) return fail(ctx, KSS_ERR_UNSUPPORTED, "kss_middle_align: > 2048 points");
+    CU(cudaSetDevice(ctx->device));
+    double *d_s, *d_t, *d_a8, *d_al; const int *c_s, *c_t;
+    BUF("one_s", (size_t)n_s * 3, &d_s); BUF("one_t", (size_t)n_t * 3, &d_t);
+    BUF("align8", 8, &d_a8); BUF("s_al", (size_t)n_s * 3, &d_al);
+    CU(cudaMemcpyAsync(d_s, src, sizeof(double) * 3 * n_s, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_t, tgt, sizeof(double) * 3 * n_t, cudaMemcpyHostToDevice, ctx->stream));
+    int r = counts_or_fill(ctx, "cnt_s", nullptr, 1, n_s, &c_s); if (r) return r;
+    r = counts_or_fill(ctx, "cnt_t", nullptr, 1, n_t, &c_t); if (r) return r;
+    KL(launch_middle_align(ctx->stream, 1, d_s, c_s, n_s, d_t, c_t, n_t, d_a8, d_al));
+    double a8[8];
+    CU(cudaMemcpyAsync(a8, d_a8, sizeof(a8), cudaMemcpyDeviceToHost, ctx->stream));
+    if (src_aligned) CU(cudaMemcpyAsync(src_aligned, d_al, sizeof(double) * 3 * n_s, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 7; ++i) out7[i] = a8[i];
+    return KSS_OK;
+}
+
+int kss_rotation_sweep(kss_ctx* ctx, const double* src_aligned, int n_s, const double* tgt, int n_t, double step,
+                       int score_mode, double* value, int* G_out, double best_angle[3], int best_index[3],
+                       int* minima, int* n_minima) {
+    if (!ctx) return KSS_ERR_ARG;
+    if (!src_aligned || !tgt || n_s < 1 || n_t < 1) return fail(ctx, KSS_ERR_ARG, "kss_rotation_sweep: bad argument");
+    if (n_s > SMALL_MAX || n_t > SMALL_MAX) return fail(ctx, KSS_ERR_UNSUPPORTED, "kss_rotation_sweep: > 2048 points");
+    if (score_mode < 0 || score_mode > 2) return fail(ctx, KSS_ERR_ARG, "kss_rotation_sweep: score_mode");
+    CU(cudaSetDevice(ctx->device));
+    int r = ensure_trig(ctx, step); if (r) return r;
+    const int G = ctx->G, H = G * G * G;
+    double *d_s, *d_t, *rbuf, *d_val; const int *c_s, *c_t;
+    unsigned short *s_perm, *t_inv; float4* t_sorted; float* t_box; int *d_best, *d_min, *d_nmin;
+    const int tpad = pad32(n_t);
+    BUF("one_s", (size_t)n_s * 3, &d_s); BUF("one_t", (size_t)n_t * 3, &d_t);
+    BUF("s_perm", n_s, &s_perm); BUF("t_sorted", tpad, &t_sorted); BUF("t_box", 6 * MAX_TILES, &t_box); BUF("t_inv", n_t, &t_inv);
+    BUF("rbuf", (size_t)n_s * H, &rbuf); BUF("value", H, &d_val); BUF("best_h", 1, &d_best);
+    BUF("minima", H, &d_min); BUF("n_minima", 1, &d_nmin);
+    CU(cudaMemcpyAsync(d_s, src_aligned, sizeof(double) * 3 * n_s, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_t, tgt, sizeof(double) * 3 * n_t, cudaMemcpyHostToDevice, ctx->stream));
+    r = counts_or_fill(ctx, "cnt_s", nullptr, 1, n_s, &c_s); if (r) return r;
+    r = counts_or_fill(ctx, "cnt_t", nullptr, 1, n_t, &c_t); if (r) return r;
+    KL(launch_sort_target(ctx->stream, 1, d_t, c_t, n_t, t_sorted, t_box, t_inv, tpad));
+    KL(launch_sort_source(ctx->stream, 1, d_s, c_s, n_s, s_perm));
+    KL(launch_sweep(ctx->stream, 1, d_s, c_s, n_s, s_perm, t_sorted, t_box, c_t, tpad, ctx->d_trig_accum, G, score_mode, rbuf, H));
+    KL(launch_sweep_finalize(ctx->stream, 1, rbuf, c_s, n_s, H, G, score_mode, d_val, d_best, d_min, d_nmin));
+    std::vector<int> hmin(H);
+    int hbest = 0, nmin = 0;
+    if (value) CU(cudaMemcpyAsync(value, d_val, sizeof(double) * H, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&hbest, d_best, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&nmin, d_nmin, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(hmin.data(), d_min, sizeof(int) * H, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (G_out) *G_out = G;
+    const int bi[3] = {hbest / (G * G), (hbest / G) % G, hbest % G};
+    for (int k = 0; k < 3; ++k) {
+        if (best_index) best_index[k] = bi[k];
+        if (best_angle) best_angle[k] = ctx->accum[bi[k]];
+    }
+    if (n_minima) *n_minima = nmin;
+    if (minima)
+        for (int l = 0; l < nmin; ++l) {
+            minima[3 * l] = hmin[l] / (G * G); minima[3 * l + 1] = (hmin[l] / G) % G; minima[3 * l + 2] = hmin[l] % G;
+        }
+    return KSS_OK;
+}
+
+int kss_apply_similarity(kss_ctx* ctx, const double* pts, int n, const double align7[7], const double angles[3],
+                         double* out) {
+    if (!ctx) return KSS_ERR_ARG;
+    if (!pts || !align7 || !angles || !out || n < 1) return fail(ctx, KSS_ERR_ARG, "kss_apply_similarity: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    double *d_p, *d_o, *d_par;
+    BUF("pts_in", (size_t)n * 3, &d_p); BUF("pts_out", (size_t)n * 3, &d_o); BUF("sim_par", 16, &d_par);
+    double par[16] = {0};
+    for (int i = 0; i < 7; ++i) par[i] = align7[i];
+    for (int k = 0; k < 3; ++k) { par[8 + 2 * k] = std::cos(angles[k]); par[9 + 2 * k] = std::sin(angles[k]); }
+    CU(cudaMemcpyAsync(d_p, pts, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_par, par, sizeof(par), cudaMemcpyHostToDevice, ctx->stream));
+    KL(launch_apply_similarity(ctx->stream, d_p, n, d_par, d_par + 8, d_o));
+    CU(cudaMemcpyAsync(out, d_o, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KSS_OK;
+}
+
+int kss_apply_transform(kss_ctx* ctx, const float T[16], const double* pts, int n, double* out) {
+    if (!ctx) return KSS_ERR_ARG;
+    if (!T || !pts || !out || n < 1) return fail(ctx, KSS_ERR_ARG, "kss_apply_transform: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    double *d_p, *d_o; float* d_T;
+    BUF("pts_in", (size_t)n * 3, &d_p); BUF("pts_out", (size_t)n * 3, &d_o); BUF("T16", 16, &d_T);
+    CU(cudaMemcpyAsync(d_p, pts, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_T, T, sizeof(float) * 16, cudaMemcpyHostToDevice, ctx->stream));
+    KL(launch_apply_transform(ctx->stream, d_p, n, d_T, d_o));
+    CU(cudaMemcpyAsync(out, d_o, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KSS_OK;
+}
+
+int kss_icp(kss_ctx* ctx, const double* src, int n_s, const double* tgt, int n_t, const kss_icp_params* prm,
+            float T[16], double* fitness, int* iters, int* converged, kss_icp_trace* trace) {
+    if (!ctx) return KSS_ERR_ARG;
+    if (!src || !tgt || n_s < 1 || n_t < 1) return fail(ctx, KSS_ERR_ARG, "kss_icp: bad argument");
+    kss_icp_params dp; kss_icp_params_default(&dp);
+    if (!prm) prm = &dp;
+    CU(cudaSetDevice(ctx->device));
+    auto alloc = [&](const char* name, size_t bytes, void** out) {
+        unsigned char* q; int rr = dev_buf(ctx, name, bytes, &q); *out = q; return rr; };
+    if (n_s > SMALL_MAX || n_t > SMALL_MAX) {
+        // full-resolution overload shapeRegistration_ICP(int iter) (KSS_ICP.hpp:133-183)
+        if (trace) return fail(ctx, KSS_ERR_UNSUPPORTED, "kss_icp: trace is only available on the <= 2048-point path");
+        int r = large_icp_host(ctx->stream, &ctx->launches, src, n_s, tgt, n_t, prm, T, fitness, iters, converged, alloc);
+        if (r != KSS_OK) return fail(ctx, r, "kss_icp (large path) failed");
+        return KSS_OK;
+    }
+    double *d_s, *d_t, *run_fit; const int *c_s, *c_t;
+    unsigned short *s_perm, *t_inv; float4* t_sorted; float *t_box, *run_T; int *run_iters, *run_conv;
+    const int tpad = pad32(n_t);
+    BUF("one_s", (size_t)n_s * 3, &d_s); BUF("one_t", (size_t)n_t * 3, &d_t);
+    BUF("s_perm", n_s, &s_perm); BUF("t_sorted", tpad, &t_sorted); BUF("t_box", 6 * MAX_TILES, &t_box); BUF("t_inv", n_t, &t_inv);
+    BUF("run_T", 16, &run_T); BUF("run_fit", 1, &run_fit); BUF("run_iters", 1, &run_iters); BUF("run_conv", 1, &run_conv);
+    CU(cudaMemcpyAsync(d_s, src, sizeof(double) * 3 * n_s, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_t, tgt, sizeof(double) * 3 * n_t, cudaMemcpyHostToDevice, ctx->stream));
+    int r = counts_or_fill(ctx, "cnt_s", nullptr, 1, n_s, &c_s); if (r) return r;
+    r = counts_or_fill(ctx, "cnt_t", nullptr, 1, n_t, &c_t); if (r) return r;
+    KL(launch_sort_target(ctx->stream, 1, d_t, c_t, n_t, t_sorted, t_box, t_inv, tpad));
+    KL(launch_sort_source(ctx->stream, 1, d_s, c_s, n_s, s_perm));
+    IcpArgs a{};
+    a.src_f64 = d_s; a.cnt_s = c_s; a.cap_s = n_s; a.s_perm = s_perm;
+    a.t_sorted = t_sorted; a.t_box = t_box; a.t_inv = t_inv; a.cnt_t = c_t; a.cap_t = n_t; a.cap_tpad = tpad;
+    a.mode = 2; a.runs_per_pair = 1; a.judge_thr = -1.0;
+    icp_fill(a, *prm);
+    a.run_T = run_T; a.run_fit = run_fit; a.run_iters = run_iters; a.run_conv = run_conv;
+    int cap = 0;
+    if (trace && trace->cap_iters > 0) {
+        cap = trace->cap_iters; a.trace_cap = cap;
+        if (trace->corr_idx) { BUF("trace_idx", (size_t)cap * n_s, &a.trace_idx); CU(cudaMemsetAsync(a.trace_idx, 0xff, sizeof(int) * (size_t)cap * n_s, ctx->stream)); }
+        if (trace->T_k) { BUF("trace_T", (size_t)cap * 16, &a.trace_T); CU(cudaMemsetAsync(a.trace_T, 0, sizeof(float) * (size_t)cap * 16, ctx->stream)); }
+        if (trace->mse) { BUF("trace_mse", (size_t)cap, &a.trace_mse); CU(cudaMemsetAsync(a.trace_mse, 0, sizeof(double) * (size_t)cap, ctx->stream)); }
+        if (trace->src_k) { BUF("trace_src", (size_t)cap * n_s * 3, &a.trace_src); CU(cudaMemsetAsync(a.trace_src, 0, sizeof(float) * (size_t)cap * n_s * 3, ctx->stream)); }
+    }
+    KL(launch_icp(ctx->stream, 1, 1, a));
+    float hT[16]; double hf = 0; int hi = 0, hc = 0;
+    CU(cudaMemcpyAsync(hT, run_T, sizeof(hT), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&hf, run_fit, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&hi, run_iters, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&hc, run_conv, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (cap > 0) {
+        if (trace->corr_idx) CU(cudaMemcpyAsync(trace->corr_idx, a.trace_idx, sizeof(int) * (size_t)cap * n_s, cudaMemcpyDeviceToHost, ctx->stream));
+        if (trace->T_k) CU(cudaMemcpyAsync(trace->T_k, a.trace_T, sizeof(float) * (size_t)cap * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        if (trace->mse) CU(cudaMemcpyAsync(trace->mse, a.trace_mse, sizeof(double) * (size_t)cap, cudaMemcpyDeviceToHost, ctx->stream));
+        if (trace->src_k) CU(cudaMemcpyAsync(trace->src_k, a.trace_src, sizeof(float) * (size_t)cap * n_s * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (T) std::memcpy(T, hT, sizeof(hT));
+    if (fitness) *fitness = hf;
+    if (iters) *iters = hi;
+    if (converged) *converged = hc;
+    return KSS_OK;
+}
+
+static int nn_common(kss_ctx* ctx, const double* q, int n_q, const double* t, int n_t, int mode, int32_t* idx,
+                     float* d2, double* out3) {
+    CU(cudaSetDevice(ctx->device));
+    auto alloc = [&](const char* name, size_t bytes, void** out) {
+        unsigned char* p; int rr = dev_buf(ctx, name, bytes, &p); *out = p; return rr; };
+    double *d_q, *d_t;
+    BUF("one_s", (size_t)n_q * 3, &d_q); BUF("one_t", (size_t)n_t * 3, &d_t);
+    CU(cudaMemcpyAsync(d_q, q, sizeof(double) * 3 * n_q, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_t, t, sizeof(double) * 3 * n_t, cudaMemcpyHostToDevice, ctx->stream));
+    const int *c_q, *c_t;
+    int r = counts_or_fill(ctx, "cnt_s", nullptr, 1, n_q, &c_q); if (r) return r;
+    r = counts_or_fill(ctx, "cnt_t", nullptr, 1, n_t, &c_t); if (r) return r;
+    int* d_idx = nullptr; float* d_d2 = nullptr; double* d_o3 = nullptr;
+    if (mode == 0) { BUF("nn_idx", n_q, &d_idx); BUF("nn_d2", n_q, &d_d2); }
+    else BUF("nn_out3", 3, &d_o3);
+    if (n_q <= SMALL_MAX && n_t <= SMALL_MAX) {
+        unsigned short *q_perm, *t_inv; float4* t_sorted; float* t_box;
+        const int tpad = pad32(n_t);
+        BUF("s_perm", n_q, &q_perm); BUF("t_sorted", tpad, &t_sorted); BUF("t_box", 6 * MAX_TILES, &t_box); BUF("t_inv", n_t, &t_inv);
+        KL(launch_sort_target(ctx->stream, 1, d_t, c_t, n_t, t_sorted, t_box, t_inv, tpad));
+        KL(launch_sort_source(ctx->stream, 1, d_q, c_q, n_q, q_perm));
+        KL(launch_nn_small(ctx->stream, 1, mode, d_q, c_q, n_q, q_perm, t_sorted, t_box, c_t, tpad, d_idx, d_d2, d_o3, 3));
+    } else if (mode == 0) {
+        r = large_nn_device(ctx->stream, &ctx->launches, d_q, n_q, d_t, n_t, d_idx, d_d2, alloc);
+        if (r != KSS_OK) return fail(ctx, r, "large-cloud NN failed");
+    } else {
+        r = large_metrics_device(ctx->stream, &ctx->launches, d_q, c_q, n_q, d_t, c_t, n_t, d_o3, alloc);
+        if (r != KSS_OK) return fail(ctx, r, "large-cloud metrics failed");
+    }
+    if (mode == 0) {
+        if (idx) CU(cudaMemcpyAsync(idx, d_idx, sizeof(int) * n_q, cudaMemcpyDeviceToHost, ctx->stream));
+        if (d2) CU(cudaMemcpyAsync(d2, d_d2, sizeof(float) * n_q, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        CU(cudaMemcpyAsync(out3, d_o3, sizeof(double) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KSS_OK;
+}
+
+int kss_nn_search(kss_ctx* ctx, const double* q, int n_q, const double* t, int n_t, int32_t* idx, float* d2) {
+    if (!ctx) return KSS_ERR_ARG;
+    if (!q || !t || n_q < 1 || n_t < 1) return fail(ctx, KSS_ERR_ARG, "kss_nn_search: bad argument");
+    return nn_common(ctx, q, n_q, t, n_t, 0, idx, d2, nullptr);
+}
+
+int kss_nn_metrics(kss_ctx* ctx, const double* a, int n_a, const double* t, int n_t, double out3[3]) {
+    if (!ctx) return KSS_ERR_ARG;
+    if (!a || !t || !out3 || n_a < 1 || n_t < 1) return fail(ctx, KSS_ERR_ARG, "kss_nn_metrics: bad argument");
+    return nn_common(ctx, a, n_a, t, n_t, 1, nullptr, nullptr, out3);
+}
+
+int kss_register_batch_device(kss_ctx* ctx, const kss_batch* b, kss_pair_result* d_results, double* d_point_align) {
+    int r = check_batch(ctx, b); if (r) return r;
+    if (!d_results) return fail(ctx, KSS_ERR_ARG, "kss_register_batch_device: null results");
+    CU(cudaSetDevice(ctx->device));
+    r = ensure_trig(ctx, b->step); if (r) return r;
+    const int H = ctx->G * ctx->G * ctx->G;
+    int slots = 32;
+    const char* es = getenv("KSS_HYP_SLOTS");
+    if (es && atoi(es) > 0) slots = atoi(es);
+    if (ctx->slots_override > 0) slots = ctx->slots_override;
+    if (slots > H) slots = H;
+    const size_t per = per_pair_ws_bytes(*b, H, slots);
+    int chunk = (int)std::min<size_t>((size_t)b->n_pairs, std::max<size_t>(1, ctx->ws_budget / per));
+    for (int p0 = 0; p0 < b->n_pairs; p0 += chunk) {
+        const int P = std::min(chunk, b->n_pairs - p0);
+        const int *c_s, *c_t, *c_S, *c_T;
+        r = counts_or_fill(ctx, "cnt_s", b->cnt_s ? b->cnt_s + p0 : nullptr, P, b->cap_s, &c_s); if (r) return r;
+        r = counts_or_fill(ctx, "cnt_t", b->cnt_t ? b->cnt_t + p0 : nullptr, P, b->cap_t, &c_t); if (r) return r;
+        r = counts_or_fill(ctx, "cnt_S", b->cnt_S ? b->cnt_S + p0 : nullptr, P, b->cap_S, &c_S); if (r) return r;
+        r = counts_or_fill(ctx, "cnt_T", b->cnt_T ? b->cnt_T + p0 : nullptr, P, b->cap_T, &c_T); if (r) return r;
+        r = pipeline_device(ctx, P, *b, b->sim_s + (size_t)p0 * b->cap_s * 3, b->sim_t + (size_t)p0 * b->cap_t * 3,
+                            b->full_s + (size_t)p0 * b->cap_S * 3, b->full_t + (size_t)p0 * b->cap_T * 3, c_s, c_t, c_S,
+                            c_T, slots, d_results + p0,
+                            d_point_align ? d_point_align + (size_t)p0 * b->cap_S * 3 : nullptr);
+        if (r) return r;
+    }
+    return KSS_OK;
+}
+
+int kss_register_batch(kss_ctx* ctx, const kss_batch* b, kss_pair_result* results, double* point_align) {
+    int r = check_batch(ctx, b); if (r) return r;
+    if (!results) return fail(ctx, KSS_ERR_ARG, "kss_register_batch: null results");
+    CU(cudaSetDevice(ctx->device));
+    const int P = b->n_pairs;
+    double *d_ss, *d_st, *d_fs, *d_ft, *d_pa = nullptr; kss_pair_result* d_res;
+    int *d_cs = nullptr, *d_ct = nullptr, *d_cS = nullptr, *d_cT = nullptr;
+    BUF("in_sim_s", (size_t)P * b->cap_s * 3, &d_ss); BUF("in_sim_t", (size_t)P * b->cap_t * 3, &d_st);
+    BUF("in_full_s", (size_t)P * b->cap_S * 3, &d_fs); BUF("in_full_t", (size_t)P * b->cap_T * 3, &d_ft);
+    BUF("out_res", (size_t)P, &d_res);
+    if (point_align) BUF("out_pa", (size_t)P * b->cap_S * 3, &d_pa);
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(d_ss, b->sim_s, sizeof(double) * 3 * (size_t)P * b->cap_s, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_st, b->sim_t, sizeof(double) * 3 * (size_t)P * b->cap_t, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_fs, b->full_s, sizeof(double) * 3 * (size_t)P * b->cap_S, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_ft, b->full_t, sizeof(double) * 3 * (size_t)P * b->cap_T, cudaMemcpyHostToDevice, st));
+    kss_batch db = *b;
+    db.sim_s = d_ss; db.sim_t = d_st; db.full_s = d_fs; db.full_t = d_ft;
+    if (b->cnt_s) { BUF("in_cnt_s", P, &d_cs); CU(cudaMemcpyAsync(d_cs, b->cnt_s, sizeof(int) * P, cudaMemcpyHostToDevice, st)); db.cnt_s = d_cs; }
+    if (b->cnt_t) { BUF("in_cnt_t", P, &d_ct); CU(cudaMemcpyAsync(d_ct, b->cnt_t, sizeof(int) * P, cudaMemcpyHostToDevice, st)); db.cnt_t = d_ct; }
+    if (b->cnt_S) { BUF("in_cnt_S", P, &d_cS); CU(cudaMemcpyAsync(d_cS, b->cnt_S, sizeof(int) * P, cudaMemcpyHostToDevice, st)); db.cnt_S = d_cS; }
+    if (b->cnt_T) { BUF("in_cnt_T", P, &d_cT); CU(cudaMemcpyAsync(d_cT, b->cnt_T, sizeof(int) * P, cudaMemcpyHostToDevice, st)); db.cnt_T = d_cT; }
+    r = kss_register_batch_device(ctx, &db, d_res, d_pa); if (r) return r;
+    CU(cudaMemcpyAsync(results, d_res, sizeof(kss_pair_result) * (size_t)P, cudaMemcpyDeviceToHost, st));
+    if (point_align) CU(cudaMemcpyAsync(point_align, d_pa, sizeof(double) * 3 * (size_t)P * b->cap_S, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    // pairs whose local-minimum list exceeded the hypothesis slots: re-run alone with enough slots
+    for (int p = 0; p < P; ++p) {
+        if (!results[p].overflow) continue;
+        kss_batch one = db;
+        one.n_pairs = 1;
+        one.sim_s = d_ss + (size_t)p * b->cap_s * 3; one.sim_t = d_st + (size_t)p * b->cap_t * 3;
+        one.full_s = d_fs + (size_t)p * b->cap_S * 3; one.full_t = d_ft + (size_t)p * b->cap_T * 3;
+        one.cnt_s = db.cnt_s ? db.cnt_s + p : nullptr; one.cnt_t = db.cnt_t ? db.cnt_t + p : nullptr;
+        one.cnt_S = db.cnt_S ? db.cnt_S + p : nullptr; one.cnt_T = db.cnt_T ? db.cnt_T + p : nullptr;
+        ctx->slots_override = results[p].n_minima;
+        r = kss_register_batch_device(ctx, &one, d_res + p, d_pa ? d_pa + (size_t)p * b->cap_S * 3 : nullptr);
+        ctx->slots_override = 0;
+        if (r) return r;
+        CU(cudaMemcpyAsync(results + p, d_res + p, sizeof(kss_pair_result), cudaMemcpyDeviceToHost, st));
+        if (point_align)
+            CU(cudaMemcpyAsync(point_align + (size_t)p * b->cap_S * 3, d_pa + (size_t)p * b->cap_S * 3,
+                               sizeof(double) * 3 * (size_t)b->cap_S, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        results[p].overflow = 1;
+    }
+    return KSS_OK;
+}
+
+int kss_register(kss_ctx* ctx, const double* sim_s, int n_s, const double* sim_t, int n_t, const double* full_s,
+                 int N_s, const double* full_t, int N_t, double step, int max_iter, kss_pair_result* result,
+                 double* point_align) {
+    kss_batch b; kss_batch_default(&b);
+    b.n_pairs = 1; b.cap_s = n_s; b.cap_t = n_t; b.cap_S = N_s; b.cap_T = N_t;
+    b.sim_s = sim_s; b.sim_t = sim_t; b.full_s = full_s; b.full_t = full_t;
+    b.step = step; b.icp.max_iterations = max_iter;
+    return kss_register_batch(ctx, &b, result, point_align);
+}
+
+}  // extern "C"

@@ -1,0 +1,390 @@
+// kss_device.cuh -- device-side building blocks of the KSS-ICP B200 path.
+//
+// Arithmetic contract (DESIGN.md "numerics"): every parity-relevant expression is
+// written with explicit round-to-nearest intrinsics (__fmul_rn/__fadd_rn/__dmul_rn/
+// __dadd_rn) so that no FMA contraction can change a result, independent of -fmad.
+// fmaf() is used only in conservative lower bounds that never reach an output.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+#include "kss_kernels.h"
+
+#define KSS_FULL 0xffffffffu
+
+namespace kss {
+
+constexpr float CULL_SLACK = 1.00001f;       // lower bounds must exceed best*slack before a tile is skipped
+constexpr float PAD_COORD = 1.0e18f;         // coordinate of padding targets (d2 ~ 3e36, finite)
+
+// ---------------------------------------------------------------- ordering helpers
+__device__ __forceinline__ unsigned f2ord(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ float warp_min_f(float v) { return ord2f(__reduce_min_sync(KSS_FULL, f2ord(v))); }
+__device__ __forceinline__ float warp_max_f(float v) { return ord2f(__reduce_max_sync(KSS_FULL, f2ord(v))); }
+
+// ---------------------------------------------------------------- exact distance
+// FLANN L2_Simple<float>: ((dx*dx) + dy*dy) + dz*dz, one rounding per operator
+// (replaces pcl::KdTreeFLANN distance; initRegistrationKSS.hpp:443, registrationMeasure.hpp:79)
+__device__ __forceinline__ float d2_rn(float qx, float qy, float qz, float tx, float ty, float tz) {
+    float dx = __fsub_rn(qx, tx), dy = __fsub_rn(qy, ty), dz = __fsub_rn(qz, tz);
+    float r = __fmul_rn(dx, dx);
+    r = __fadd_rn(r, __fmul_rn(dy, dy));
+    r = __fadd_rn(r, __fmul_rn(dz, dz));
+    return r;
+}
+
+// ---------------------------------------------------------------- target tiles in shared memory
+// tgt : float4 {x, y, z, bits(original index)} in Morton order, padded to a multiple of 32
+// box : SoA [6][MAX_TILES] = minx,miny,minz,maxx,maxy,maxz of each 32-point tile
+struct TileView {
+    const float4* tgt;
+    const float* box;
+    int ntiles;
+};
+
+__device__ __forceinline__ float gap(float lo, float hi, float blo, float bhi) {
+    // distance between intervals [lo,hi] and [blo,bhi] (0 if they overlap)
+    return fmaxf(0.0f, fmaxf(blo - hi, lo - bhi));
+}
+
+__device__ __forceinline__ float boxbox_lb(const float* box, int t, float lx, float ly, float lz,
+                                           float hx, float hy, float hz) {
+    float gx = gap(lx, hx, box[0 * MAX_TILES + t], box[3 * MAX_TILES + t]);
+    float gy = gap(ly, hy, box[1 * MAX_TILES + t], box[4 * MAX_TILES + t]);
+    float gz = gap(lz, hz, box[2 * MAX_TILES + t], box[5 * MAX_TILES + t]);
+    return fmaf(gz, gz, fmaf(gy, gy, gx * gx));
+}
+
+// Exact 1-NN of one query per lane against all tiles, warp-synchronous best-first
+// traversal with conservative culling.  All 32 lanes must be active and should carry
+// spatially coherent queries (Morton-consecutive points).  Result: bit-exact minimum of
+// d2_rn over ALL target points; WITH_INDEX additionally returns the lowest original
+// index among fp32-equal minima (the oracle's tie rule) packed as (d2bits<<32)|orig.
+template <bool WITH_INDEX>
+__device__ __forceinline__ unsigned long long warp_nn(const TileView& tv, float qx, float qy, float qz) {
+    const int lane = threadIdx.x & 31;
+    // warp query box
+    const float lx = warp_min_f(qx), ly = warp_min_f(qy), lz = warp_min_f(qz);
+    const float hx = warp_max_f(qx), hy = warp_max_f(qy), hz = warp_max_f(qz);
+    // each lane owns tiles lane and lane+32 ; lower bounds kept as uint (>=0 floats order as uints)
+    unsigned lbA = 0xffffffffu, lbB = 0xffffffffu;
+    if (lane < tv.ntiles) lbA = __float_as_uint(boxbox_lb(tv.box, lane, lx, ly, lz, hx, hy, hz));
+    if (lane + 32 < tv.ntiles) lbB = __float_as_uint(boxbox_lb(tv.box, lane + 32, lx, ly, lz, hx, hy, hz));
+
+    float best = __int_as_float(0x7f800000);  // +inf
+    unsigned long long bestkey = 0xffffffffffffffffull;
+
+    for (;;) {
+        const unsigned c = min(lbA, lbB);
+        const unsigned m = __reduce_min_sync(KSS_FULL, c);
+        if (m == 0xffffffffu) break;
+        const float B = __uint_as_float(__reduce_max_sync(KSS_FULL, __float_as_uint(best)));
+        if (__uint_as_float(m) > B * CULL_SLACK) break;
+        const unsigned bal = __ballot_sync(KSS_FULL, c == m);
+        const int src = __ffs(bal) - 1;
+        int t = (lbA == m) ? lane : lane + 32;
+        t = __shfl_sync(KSS_FULL, t, src);
+        if (lane == src) { if (lbA == m) lbA = 0xffffffffu; else lbB = 0xffffffffu; }
+        // per-lane point-to-box bound: skip the tile if it cannot improve any lane
+        {
+            float gx = gap(qx, qx, tv.box[0 * MAX_TILES + t], tv.box[3 * MAX_TILES + t]);
+            float gy = gap(qy, qy, tv.box[1 * MAX_TILES + t], tv.box[4 * MAX_TILES + t]);
+            float gz = gap(qz, qz, tv.box[2 * MAX_TILES + t], tv.box[5 * MAX_TILES + t]);
+            float lbp = fmaf(gz, gz, fmaf(gy, gy, gx * gx));
+            if (__ballot_sync(KSS_FULL, lbp <= best * CULL_SLACK) == 0u) continue;
+        }
+        const float4* tp = tv.tgt + t * TILE;
+#pragma unroll 8
+        for (int j = 0; j < TILE; ++j) {
+            const float4 p = tp[j];  // warp-uniform address: one broadcast LDS.128 per 32 distances
+            const float d = d2_rn(qx, qy, qz, p.x, p.y, p.z);
+            if (WITH_INDEX) {
+                const unsigned long long key =
+                    ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_uint(p.w);
+                bestkey = key < bestkey ? key : bestkey;
+            } else {
+                best = fminf(best, d);
+            }
+        }
+        if (WITH_INDEX) best = __uint_as_float((unsigned)(bestkey >> 32));
+    }
+    if (!WITH_INDEX) bestkey = (unsigned long long)__float_as_uint(best) << 32;
+    return bestkey;
+}
+
+// ---------------------------------------------------------------- canonical reductions (CANON256)
+// Order contract shared with the oracle (oracle/kss_oracle.cpp sum_canon): per 256-element
+// chunk, lane l accumulates elements i = l (mod 32) in increasing i starting from +0, then an
+// xor butterfly 16,8,4,2,1; chunk results are reduced by the same rule.  One warp runs one
+// reduction; n <= 8192 here (two levels).  get(i, v) returns false for masked slots.
+template <class Get>
+__device__ __forceinline__ float canon_sum_warp_f32(int n, Get get) {
+    const int lane = threadIdx.x & 31;
+    const int nc = (n + 255) >> 8;
+    float acc = 0.0f;
+    float p = 0.0f;
+    for (int c = 0; c < nc || c == 0; ++c) {
+        p = 0.0f;
+        const int hi = min(n, (c + 1) << 8);
+        for (int i = (c << 8) + lane; i < hi; i += 32) {
+            float v;
+            if (get(i, v)) p = __fadd_rn(p, v);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) p = __fadd_rn(p, __shfl_xor_sync(KSS_FULL, p, off));
+        if (lane == c) acc = __fadd_rn(0.0f, p);
+        if (nc <= 1) return p;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(KSS_FULL, acc, off));
+    return acc;
+}
+
+template <class Get>
+__device__ __forceinline__ double canon_sum_warp_f64(int n, Get get) {
+    const int lane = threadIdx.x & 31;
+    const int nc = (n + 255) >> 8;
+    double acc = 0.0;
+    double p = 0.0;
+    for (int c = 0; c < nc || c == 0; ++c) {
+        p = 0.0;
+        const int hi = min(n, (c + 1) << 8);
+        for (int i = (c << 8) + lane; i < hi; i += 32) {
+            double v;
+            if (get(i, v)) p = __dadd_rn(p, v);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) p = __dadd_rn(p, __shfl_xor_sync(KSS_FULL, p, off));
+        if (lane == c) acc = __dadd_rn(0.0, p);
+        if (nc <= 1) return p;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(KSS_FULL, acc, off));
+    return acc;
+}
+
+// ---------------------------------------------------------------- 3x3 SVD / Kabsch (one thread per problem)
+// Two-sided Jacobi SVD of a real 3x3 in float, the small-fixed-size algorithm behind
+// Eigen::JacobiSVD which pcl::umeyama calls.  Operation order is the
+// contract with the oracle's svd3(); all ops are single-rounded.
+struct Rot2 { float c, s; };
+
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float sqrt_(float a) { return __fsqrt_rn(a); }
+
+__device__ __forceinline__ void rot_left(float* W, int p, int q, Rot2 j) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float x = W[3 * p + k], y = W[3 * q + k];
+        W[3 * p + k] = add_(mul_(j.c, x), mul_(j.s, y));
+        W[3 * q + k] = add_(mul_(-j.s, x), mul_(j.c, y));
+    }
+}
+__device__ __forceinline__ void rot_right(float* W, int p, int q, Rot2 j) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float x = W[3 * k + p], y = W[3 * k + q];
+        W[3 * k + p] = sub_(mul_(j.c, x), mul_(j.s, y));
+        W[3 * k + q] = add_(mul_(j.s, x), mul_(j.c, y));
+    }
+}
+__device__ __forceinline__ Rot2 sym_jacobi(float x, float y, float z) {
+    Rot2 r;
+    float deno = mul_(2.0f, fabsf(y));
+    if (deno < FLT_MIN) { r.c = 1.0f; r.s = 0.0f; return r; }
+    float tau = div_(sub_(x, z), deno);
+    float w = sqrt_(add_(mul_(tau, tau), 1.0f));
+    float t = tau > 0.0f ? div_(1.0f, add_(tau, w)) : div_(1.0f, sub_(tau, w));
+    float sign_t = t > 0.0f ? 1.0f : -1.0f;
+    float n = div_(1.0f, sqrt_(add_(mul_(t, t), 1.0f)));
+    r.s = mul_(mul_(mul_(-sign_t, div_(y, fabsf(y))), fabsf(t)), n);
+    r.c = n;
+    return r;
+}
+
+__device__ inline void svd3(const float* A, float* U, float* s, float* V) {
+    float scale = 0.0f;
+    for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(A[i]));
+    if (!(scale > 0.0f)) scale = 1.0f;
+    float W[9];
+    for (int i = 0; i < 9; ++i) W[i] = div_(A[i], scale);
+    for (int i = 0; i < 9; ++i) { U[i] = (i % 4 == 0) ? 1.0f : 0.0f; V[i] = U[i]; }
+    const float precision = 2.0f * FLT_EPSILON;
+    const float tiny = FLT_MIN;
+    float maxDiag = fmaxf(fabsf(W[0]), fmaxf(fabsf(W[4]), fabsf(W[8])));
+    bool finished = false;
+    int guard = 0;
+    while (!finished && guard++ < 64) {
+        finished = true;
+        for (int p = 1; p < 3; ++p)
+            for (int q = 0; q < p; ++q) {
+                float thr = fmaxf(tiny, mul_(precision, maxDiag));
+                if (fabsf(W[3 * p + q]) > thr || fabsf(W[3 * q + p]) > thr) {
+                    finished = false;
+                    float m00 = W[3 * p + p], m01 = W[3 * p + q], m10 = W[3 * q + p], m11 = W[3 * q + q];
+                    Rot2 r1;
+                    float t = add_(m00, m11), d = sub_(m10, m01);
+                    if (fabsf(d) < tiny) { r1.s = 0.0f; r1.c = 1.0f; }
+                    else {
+                        float u = div_(t, d);
+                        float tmp = sqrt_(add_(1.0f, mul_(u, u)));
+                        r1.s = div_(1.0f, tmp); r1.c = div_(u, tmp);
+                    }
+                    float n00 = add_(mul_(r1.c, m00), mul_(r1.s, m10));
+                    float n01 = add_(mul_(r1.c, m01), mul_(r1.s, m11));
+                    float n11 = add_(mul_(-r1.s, m01), mul_(r1.c, m11));
+                    Rot2 jr = sym_jacobi(n00, n01, n11);
+                    Rot2 jl;
+                    jl.c = sub_(mul_(r1.c, jr.c), mul_(r1.s, -jr.s));
+                    jl.s = add_(mul_(r1.c, -jr.s), mul_(r1.s, jr.c));
+                    rot_left(W, p, q, jl);
+                    Rot2 jlt; jlt.c = jl.c; jlt.s = -jl.s;
+                    rot_right(U, p, q, jlt);
+                    rot_right(W, p, q, jr);
+                    rot_right(V, p, q, jr);
+                    maxDiag = fmaxf(maxDiag, fmaxf(fabsf(W[3 * p + p]), fabsf(W[3 * q + q])));
+                }
+            }
+    }
+    for (int i = 0; i < 3; ++i) {
+        float a = W[4 * i];
+        s[i] = fabsf(a);
+        if (a < 0.0f) for (int k = 0; k < 3; ++k) U[3 * k + i] = -U[3 * k + i];
+    }
+    for (int i = 0; i < 3; ++i) s[i] = mul_(s[i], scale);
+    for (int i = 0; i < 3; ++i) {
+        int pos = i;
+        for (int k = i + 1; k < 3; ++k) if (s[k] > s[pos]) pos = k;
+        if (s[pos] == 0.0f) break;
+        if (pos != i) {
+            float ts = s[i]; s[i] = s[pos]; s[pos] = ts;
+            for (int k = 0; k < 3; ++k) {
+                float tu = U[3 * k + i]; U[3 * k + i] = U[3 * k + pos]; U[3 * k + pos] = tu;
+                float tv = V[3 * k + i]; V[3 * k + i] = V[3 * k + pos]; V[3 * k + pos] = tv;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float det3(const float* m) {
+    float h0 = mul_(m[0], sub_(mul_(m[4], m[8]), mul_(m[5], m[7])));
+    float h1 = mul_(m[1], sub_(mul_(m[3], m[8]), mul_(m[5], m[6])));
+    float h2 = mul_(m[2], sub_(mul_(m[3], m[7]), mul_(m[4], m[6])));
+    return add_(sub_(h0, h1), h2);
+}
+
+// pcl::umeyama tail: sigma, means -> 4x4 row-major rigid transform
+__device__ inline void umeyama_finish(const float* sigma, const float* smean, const float* dmean, float* T) {
+    float U[9], sv[3], V[9];
+    svd3(sigma, U, sv, V);
+    float S[3] = {1.0f, 1.0f, 1.0f};
+    if (det3(sigma) < 0.0f) S[2] = -1.0f;
+    int rank = 0;
+    for (int i = 0; i < 3; ++i)
+        if (!(fabsf(sv[i]) <= mul_(fabsf(sv[0]), 1e-5f))) ++rank;
+    if (rank == 2) {
+        if (mul_(det3(U), det3(V)) > 0.0f) { S[0] = S[1] = S[2] = 1.0f; }
+        else { S[2] = -1.0f; }
+    }
+    for (int i = 0; i < 16; ++i) T[i] = 0.0f;
+    T[15] = 1.0f;
+    for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) {
+            float r = mul_(mul_(U[3 * a + 0], S[0]), V[3 * b + 0]);
+            r = add_(r, mul_(mul_(U[3 * a + 1], S[1]), V[3 * b + 1]));
+            r = add_(r, mul_(mul_(U[3 * a + 2], S[2]), V[3 * b + 2]));
+            T[4 * a + b] = r;
+        }
+        float rs = mul_(T[4 * a + 0], smean[0]);
+        rs = add_(rs, mul_(T[4 * a + 1], smean[1]));
+        rs = add_(rs, mul_(T[4 * a + 2], smean[2]));
+        T[4 * a + 3] = sub_(dmean[a], rs);
+    }
+}
+
+// Matrix4f * (x,y,z,1) : ((m0*x + m1*y) + m2*z) + m3   
+__device__ __forceinline__ void xform_point(const float* T, float x, float y, float z,
+                                            float& ox, float& oy, float& oz) {
+    ox = add_(add_(add_(mul_(T[0], x), mul_(T[1], y)), mul_(T[2], z)), T[3]);
+    oy = add_(add_(add_(mul_(T[4], x), mul_(T[5], y)), mul_(T[6], z)), T[7]);
+    oz = add_(add_(add_(mul_(T[8], x), mul_(T[9], y)), mul_(T[10], z)), T[11]);
+}
+
+__device__ inline void mat4_mul(const float* A, const float* B, float* C) {
+    float R[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            float r = mul_(A[4 * i + 0], B[0 + j]);
+            r = add_(r, mul_(A[4 * i + 1], B[4 + j]));
+            r = add_(r, mul_(A[4 * i + 2], B[8 + j]));
+            r = add_(r, mul_(A[4 * i + 3], B[12 + j]));
+            R[4 * i + j] = r;
+        }
+    for (int i = 0; i < 16; ++i) C[i] = R[i];
+}
+
+// ---------------------------------------------------------------- fp64 similarity pieces
+// initRegistration_Transfer (initRegistrationKSS.hpp:365-404) with host-supplied cos/sin
+__device__ __forceinline__ void rot_x(double c, double s, double& y, double& z) {
+    double ny = __dsub_rn(__dmul_rn(y, c), __dmul_rn(z, s));
+    double nz = __dadd_rn(__dmul_rn(y, s), __dmul_rn(z, c));
+    y = ny; z = nz;
+}
+__device__ __forceinline__ void rot_y(double c, double s, double& x, double& z) {
+    double nx = __dadd_rn(__dmul_rn(z, s), __dmul_rn(x, c));
+    double nz = __dsub_rn(__dmul_rn(z, c), __dmul_rn(x, s));
+    x = nx; z = nz;
+}
+__device__ __forceinline__ void rot_z(double c, double s, double& x, double& y) {
+    double nx = __dsub_rn(__dmul_rn(x, c), __dmul_rn(y, s));
+    double ny = __dadd_rn(__dmul_rn(x, s), __dmul_rn(y, c));
+    x = nx; y = ny;
+}
+// initRegistrationKSS.hpp:77-84 : p + middle ; c + (p - c) * scale
+__device__ __forceinline__ double align_coord(double v, double mid_s, double mid, double scale) {
+    double w = __dadd_rn(v, mid);
+    return __dadd_rn(mid_s, __dmul_rn(__dsub_rn(w, mid_s), scale));
+}
+
+// Morton helpers (ordering only; never affects results)
+__device__ __forceinline__ unsigned spread7(unsigned v) {  // 7 bits -> every third bit
+    unsigned r = 0;
+#pragma unroll
+    for (int b = 0; b < 7; ++b) r |= ((v >> b) & 1u) << (3 * b);
+    return r;
+}
+__device__ __forceinline__ unsigned morton21(float x, float y, float z, const float* lo, const float* inv) {
+    unsigned ix = (unsigned)fminf(fmaxf((x - lo[0]) * inv[0], 0.0f), 127.0f);
+    unsigned iy = (unsigned)fminf(fmaxf((y - lo[1]) * inv[1], 0.0f), 127.0f);
+    unsigned iz = (unsigned)fminf(fmaxf((z - lo[2]) * inv[2], 0.0f), 127.0f);
+    return spread7(ix) | (spread7(iy) << 1) | (spread7(iz) << 2);
+}
+
+// in-place bitonic sort of NP (power of two) uint keys in shared memory, ascending
+template <int NP>
+__device__ __forceinline__ void bitonic_sort_smem(unsigned* keys) {
+    for (int k = 2; k <= NP; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < NP; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned a = keys[i], b = keys[ixj];
+                    bool up = ((i & k) == 0);
+                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+        }
+    __syncthreads();
+}
+
+}  // namespace kss

@@ -1,0 +1,27 @@
+// kss_large.h -- clouds beyond one CTA's shared memory (> 2048 points): hierarchical
+// Morton-tile NN, canonical-order reductions and the full-resolution ICP loop
+// (shapeRegistration_ICP(int iter), KSS_ICP.hpp:133-183; PCR_QM at full resolution).
+#pragma once
+#include <cuda_runtime.h>
+#include <functional>
+#include "../../include/kss_icp_b200.h"
+
+namespace kss {
+
+// named grow-only device allocation supplied by the context
+typedef std::function<int(const char* name, size_t bytes, void** out)> DevAlloc;
+
+// exact 1-NN of n_q double queries (narrowed RN) against n_t targets; device pointers
+int large_nn_device(cudaStream_t st, long long* launches, const double* d_q, int n_q, const double* d_t, int n_t,
+                    int* d_idx, float* d_d2, const DevAlloc& alloc);
+
+// PCR_QM (registrationMeasure.hpp:47-98) for one pair; counts are device ints, caps host ints
+int large_metrics_device(cudaStream_t st, long long* launches, const double* d_q, const int* d_cnt_q, int cap_q,
+                         const double* d_t, const int* d_cnt_t, int cap_t, double* d_out3, const DevAlloc& alloc);
+
+// one full-resolution PCL-ICP run from host clouds
+int large_icp_host(cudaStream_t st, long long* launches, const double* src, int n_s, const double* tgt, int n_t,
+                   const kss_icp_params* prm, float T[16], double* fitness, int* iters, int* converged,
+                   const DevAlloc& alloc);
+
+}  // namespace kss

@@ -1,0 +1,770 @@
+// kss_small.cu -- sm_100a kernels for clouds that fit one CTA's shared memory (<= 2048 points):
+// the sizes the reference actually runs its sweep and ICP on (pNumber <= 2000, KSS_ICP.hpp:57-66).
+//
+//   sort_cloud_kernel      Morton order + 32-point tiles + tile boxes of a target; Morton perm of a source
+//   middle_align_kernel    initRegistration_MiddleAlign            (initRegistrationKSS.hpp:144-220)
+//   sweep_kernel           initRegistration_Rotation() inner loops (initRegistrationKSS.hpp:245-256, 430-450)
+//   sweep_finalize_kernel  serial score sums, argmin, local minima  (initRegistrationKSS.hpp:258-289, 481-522)
+//   icp_small_kernel       one whole PCL-1.8.1 ICP run per CTA      (KSS_ICP.hpp:323-356 + SURVEY.md A.2-A.7)
+//   select_kernel          hypothesis choice                        (KSS_ICP.hpp:99-125)
+//   final_apply_kernel     similarity + final 4x4 on the full cloud (KSS_ICP.hpp:119-124, 222-230)
+//   metrics_small_kernel   PCR_QM                                   (registrationMeasure.hpp:47-98)
+//   nn_small_kernel        bare exact 1-NN (tests, kss_nn_search)
+#include "kss_device.cuh"
+#include "kss_kernels.h"
+
+namespace kss {
+
+// =============================================================== sort_cloud_kernel
+// One CTA per cloud.  mode 0: target -> t_sorted (float4 Morton order, padded), t_box, t_inv
+//                     mode 1: source -> perm only (u16 original index per Morton position)
+// pts_f64 may be the original double cloud (narrowed here with RN, like KSS_ICP.hpp:328-333).
+__global__ void __launch_bounds__(256)
+sort_cloud_kernel(const double* __restrict__ pts, const int* __restrict__ cnt, int cap, int mode,
+                  float4* __restrict__ t_sorted, float* __restrict__ t_box, unsigned short* __restrict__ t_inv,
+                  int cap_pad, unsigned short* __restrict__ perm) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned* keys = reinterpret_cast<unsigned*>(smem_raw);            // [2048]
+    float* cx = reinterpret_cast<float*>(keys + SMALL_MAX);            // [2048] x3
+    float* cy = cx + SMALL_MAX;
+    float* cz = cy + SMALL_MAX;
+    __shared__ unsigned bb[6];
+    __shared__ float lo[3], inv[3];
+
+    const int p = blockIdx.x;
+    const int n = cnt ? cnt[p] : cap;
+    const double* src = pts + (size_t)p * cap * 3;
+    if (threadIdx.x < 3) { bb[threadIdx.x] = 0xffffffffu; bb[3 + threadIdx.x] = 0u; }
+    __syncthreads();
+    unsigned mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float x = (float)src[3 * i], y = (float)src[3 * i + 1], z = (float)src[3 * i + 2];
+        cx[i] = x; cy[i] = y; cz[i] = z;
+        unsigned ox = f2ord(x), oy = f2ord(y), oz = f2ord(z);
+        mn[0] = min(mn[0], ox); mn[1] = min(mn[1], oy); mn[2] = min(mn[2], oz);
+        mx[0] = max(mx[0], ox); mx[1] = max(mx[1], oy); mx[2] = max(mx[2], oz);
+    }
+    for (int a = 0; a < 3; ++a) {
+        unsigned m0 = __reduce_min_sync(KSS_FULL, mn[a]);
+        unsigned m1 = __reduce_max_sync(KSS_FULL, mx[a]);
+        if ((threadIdx.x & 31) == 0) { atomicMin(&bb[a], m0); atomicMax(&bb[3 + a], m1); }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float l = ord2f(bb[threadIdx.x]), h = ord2f(bb[3 + threadIdx.x]);
+        float e = h - l;
+        lo[threadIdx.x] = l;
+        inv[threadIdx.x] = e > 0.0f ? 127.999f / e : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SMALL_MAX; i += blockDim.x)
+        keys[i] = i < n ? ((morton21(cx[i], cy[i], cz[i], lo, inv) << 11) | (unsigned)i) : 0xffffffffu;
+    bitonic_sort_smem<SMALL_MAX>(keys);
+
+    if (mode == 1) {
+        unsigned short* out = perm + (size_t)p * cap;
+        for (int j = threadIdx.x; j < n; j += blockDim.x) out[j] = (unsigned short)(keys[j] & 2047u);
+        return;
+    }
+    const int npad = (n + TILE - 1) / TILE * TILE;
+    float4* ts = t_sorted + (size_t)p * cap_pad;
+    unsigned short* ti = t_inv + (size_t)p * cap;
+    for (int j = threadIdx.x; j < npad; j += blockDim.x) {
+        float4 v;
+        if (j < n) {
+            int o = keys[j] & 2047u;
+            v = make_float4(cx[o], cy[o], cz[o], __int_as_float(o));
+            ti[o] = (unsigned short)j;
+        } else {
+            v = make_float4(PAD_COORD, PAD_COORD, PAD_COORD, __int_as_float(0x7fffffff));
+        }
+        ts[j] = v;
+    }
+    // tile boxes over real points only: one warp per tile
+    float* tb = t_box + (size_t)p * 6 * MAX_TILES;
+    const int ntiles = npad / TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int t = warp; t < ntiles; t += nwarps) {
+        int j = t * TILE + lane;
+        int o = keys[min(j, n - 1)] & 2047u;  // pads replicate the last real point
+        float x = cx[o], y = cy[o], z = cz[o];
+        float v0 = warp_min_f(x), v1 = warp_min_f(y), v2 = warp_min_f(z);
+        float v3 = warp_max_f(x), v4 = warp_max_f(y), v5 = warp_max_f(z);
+        if (lane == 0) {
+            tb[0 * MAX_TILES + t] = v0; tb[1 * MAX_TILES + t] = v1; tb[2 * MAX_TILES + t] = v2;
+            tb[3 * MAX_TILES + t] = v3; tb[4 * MAX_TILES + t] = v4; tb[5 * MAX_TILES + t] = v5;
+        }
+    }
+}
+
+// =============================================================== middle_align_kernel
+// One CTA per pair.  Every sum of the reference is a serial index-order double loop
+// (initRegistrationKSS.hpp:150-207); here each such chain runs on one thread over
+// shared-memory data so the 7 outputs are bit-identical to the serial definition.
+__global__ void __launch_bounds__(256)
+middle_align_kernel(const double* __restrict__ sim_s, const int* __restrict__ cnt_s, int cap_s,
+                    const double* __restrict__ sim_t, const int* __restrict__ cnt_t, int cap_t,
+                    double* __restrict__ align8, double* __restrict__ s_al) {
+    extern __shared__ unsigned char smem_raw[];
+    double* buf = reinterpret_cast<double*>(smem_raw);   // [2048*3]
+    double* len = buf + 3 * SMALL_MAX;                   // [2048]
+    __shared__ double mean[2][3];
+    __shared__ double avg[2];
+
+    const int p = blockIdx.x;
+    for (int which = 0; which < 2; ++which) {            // 0: source, 1: target
+        const int n = which == 0 ? (cnt_s ? cnt_s[p] : cap_s) : (cnt_t ? cnt_t[p] : cap_t);
+        const double* src = which == 0 ? sim_s + (size_t)p * cap_s * 3 : sim_t + (size_t)p * cap_t * 3;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) buf[i] = src[i];
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            double s = 0.0;
+            const double* b = buf + threadIdx.x;
+#pragma unroll 8
+            for (int i = 0; i < n; ++i) s = __dadd_rn(s, b[3 * i]);
+            mean[which][threadIdx.x] = __ddiv_rn(s, (double)n);
+        }
+        __syncthreads();
+        const double mx = mean[which][0], my = mean[which][1], mz = mean[which][2];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            double xl = __dsub_rn(buf[3 * i], mx), yl = __dsub_rn(buf[3 * i + 1], my), zl = __dsub_rn(buf[3 * i + 2], mz);
+            double q = __dadd_rn(__dadd_rn(__dmul_rn(xl, xl), __dmul_rn(yl, yl)), __dmul_rn(zl, zl));
+            len[i] = __dsqrt_rn(q);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+#pragma unroll 8
+            for (int i = 0; i < n; ++i) s = __dadd_rn(s, len[i]);
+            avg[which] = __ddiv_rn(s, (double)n);
+        }
+    }
+    __syncthreads();
+    // align8 = {x_middle_S, y_, z_, x_middle, y_, z_, scale, pad}
+    double* a8 = align8 + (size_t)p * 8;
+    const double scale = __ddiv_rn(avg[1], avg[0]);
+    if (threadIdx.x < 3) {
+        a8[threadIdx.x] = mean[1][threadIdx.x];
+        a8[3 + threadIdx.x] = __dsub_rn(mean[1][threadIdx.x], mean[0][threadIdx.x]);
+    }
+    if (threadIdx.x == 3) { a8[6] = scale; a8[7] = 0.0; }
+    if (s_al) {
+        const int n = cnt_s ? cnt_s[p] : cap_s;
+        const double* src = sim_s + (size_t)p * cap_s * 3;
+        double* dst = s_al + (size_t)p * cap_s * 3;
+        for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) {
+            int a = i % 3;
+            dst[i] = align_coord(src[i], mean[1][a], __dsub_rn(mean[1][a], mean[0][a]), scale);
+        }
+    }
+}
+
+// =============================================================== sweep_kernel
+// grid (G*G, P): CTA (i,j) of pair p applies Rx(i), Ry(j) once per point and loops Rz(k),
+// searching the exact NN of every rotated point (narrowed to float) in the Morton-tiled
+// target.  rbuf[p][orig][h] receives sqrt((double)d2) (score modes AVE/DIFF) or (double)d2
+// (MAX); the serial sums are taken by sweep_finalize_kernel.
+__global__ void __launch_bounds__(256)
+sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int cap_s,
+             const unsigned short* __restrict__ s_perm,
+             const float4* __restrict__ t_sorted, const float* __restrict__ t_box,
+             const int* __restrict__ cnt_t, int cap_tpad,
+             const double* __restrict__ trig_accum /* [G][2] cos,sin */, int G, int score_mode,
+             double* __restrict__ rbuf, int hpad) {
+    extern __shared__ unsigned char smem_raw[];
+    float4* tgt = reinterpret_cast<float4*>(smem_raw);
+    const int p = blockIdx.y;
+    const int n_t = cnt_t[p];
+    const int npad = (n_t + TILE - 1) / TILE * TILE;
+    float* box = reinterpret_cast<float*>(tgt + npad);
+    const float4* gts = t_sorted + (size_t)p * cap_tpad;
+    for (int j = threadIdx.x; j < npad; j += blockDim.x) tgt[j] = gts[j];
+    const float* gtb = t_box + (size_t)p * 6 * MAX_TILES;
+    for (int j = threadIdx.x; j < 6 * MAX_TILES; j += blockDim.x) box[j] = gtb[j];
+    __syncthreads();
+    TileView tv{tgt, box, npad / TILE};
+
+    const int gi = blockIdx.x / G, gj = blockIdx.x % G;
+    const double ci = trig_accum[2 * gi], si = trig_accum[2 * gi + 1];
+    const double cj = trig_accum[2 * gj], sj = trig_accum[2 * gj + 1];
+    const int n_s = cnt_s[p];
+    const unsigned short* perm = s_perm + (size_t)p * cap_s;
+    const double* sa = s_al + (size_t)p * cap_s * 3;
+    double* rb = rbuf + (size_t)p * cap_s * hpad;
+    const int hbase = (gi * G + gj) * G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+
+    for (int base = warp * 32; base < n_s; base += nwarps * 32) {
+        const int jpos = base + lane;
+        const bool valid = jpos < n_s;
+        const int o = perm[valid ? jpos : n_s - 1];
+        double x = sa[3 * o], y = sa[3 * o + 1], z = sa[3 * o + 2];
+        rot_x(ci, si, y, z);
+        rot_y(cj, sj, x, z);
+        double* ro = rb + (size_t)o * hpad + hbase;
+        for (int k = 0; k < G; ++k) {
+            const double ck = trig_accum[2 * k], sk = trig_accum[2 * k + 1];
+            double xx = x, yy = y;
+            rot_z(ck, sk, xx, yy);
+            const float qx = (float)xx, qy = (float)yy, qz = (float)z;   // :440-442 narrowing
+            const unsigned long long key = warp_nn<false>(tv, qx, qy, qz);
+            const float d2 = __uint_as_float((unsigned)(key >> 32));
+            const double r = score_mode == 1 ? (double)d2 : __dsqrt_rn((double)d2);
+            if (valid) ro[k] = r;
+        }
+    }
+}
+
+// =============================================================== sweep_finalize_kernel
+// One CTA per pair.  Thread h sums rbuf[p][0..n_s)[h] serially in index order (the
+// reference's `distanceSum = distanceSum + distance_i`), then argmin (first strict <,
+// errorT = 9999) and the clamped 5x5x5 local-minimum test in (i,j,k) loop order.
+__global__ void __launch_bounds__(1024)
+sweep_finalize_kernel(const double* __restrict__ rbuf, const int* __restrict__ cnt_s, int cap_s, int hpad,
+                      int G, int score_mode,
+                      double* __restrict__ value /* [P][hpad] */, int* __restrict__ best_h /* [P] */,
+                      int* __restrict__ minima /* [P][hpad] */, int* __restrict__ n_minima /* [P] */) {
+    extern __shared__ unsigned char smem_raw[];
+    double* val = reinterpret_cast<double*>(smem_raw);                 // [H]
+    unsigned char* flag = reinterpret_cast<unsigned char*>(val + G * G * G);
+    __shared__ unsigned long long bestkey;
+    const int p = blockIdx.x;
+    const int H = G * G * G;
+    const int n = cnt_s[p];
+    const double* rb = rbuf + (size_t)p * cap_s * hpad;
+    if (threadIdx.x == 0) bestkey = 0xffffffffffffffffull;
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        double sum = 0.0, dmax = -9999.0;
+#pragma unroll 8
+        for (int i = 0; i < n; ++i) {
+            const double r = rb[(size_t)i * hpad + h];
+            if (score_mode == 1) { if (r > dmax) dmax = r; }
+            else { sum = __dadd_rn(sum, r); if (dmax < r) dmax = r; }
+        }
+        double v;
+        if (score_mode == 1) v = dmax;
+        else if (score_mode == 2) v = __dsub_rn(dmax, __ddiv_rn(sum, (double)n));
+        else v = __ddiv_rn(sum, (double)n);
+        val[h] = v;
+        value[(size_t)p * hpad + h] = v;
+    }
+    __syncthreads();
+    // first strict minimum below 9999 in loop order == smallest (value, h) pair
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        const double v = val[h];
+        if (v < 9999.0) {
+            // order-preserving map of a double to uint64
+            unsigned long long u = (unsigned long long)__double_as_longlong(v);
+            u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+            // 64-bit value key cannot also hold h: reduce value first, then index
+            atomicMin(&bestkey, u);
+        }
+    }
+    __syncthreads();
+    __shared__ int besth;
+    if (threadIdx.x == 0) besth = 0x7fffffff;
+    __syncthreads();
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        const double v = val[h];
+        if (v < 9999.0) {
+            unsigned long long u = (unsigned long long)__double_as_longlong(v);
+            u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+            if (u == bestkey) atomicMin(&besth, h);
+        }
+    }
+    // local minima (initRegistration_kernel): reject iff centre > some neighbour
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        const int i = h / (G * G), j = (h / G) % G, k = h % G;
+        const double c = val[h];
+        bool ok = true;
+        for (int ii = max(0, i - 2); ii <= min(G - 1, i + 2) && ok; ++ii)
+            for (int jj = max(0, j - 2); jj <= min(G - 1, j + 2) && ok; ++jj)
+                for (int kk = max(0, k - 2); kk <= min(G - 1, k + 2); ++kk)
+                    if (c > val[(ii * G + jj) * G + kk]) { ok = false; break; }
+        flag[h] = ok ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) best_h[p] = besth == 0x7fffffff ? 0 : besth;
+    if (threadIdx.x < 32) {                                  // ordered compaction by one warp
+        int count = 0;
+        int* out = minima + (size_t)p * hpad;
+        for (int base = 0; base < H; base += 32) {
+            const int h = base + threadIdx.x;
+            const bool f = h < H && flag[h];
+            const unsigned bal = __ballot_sync(KSS_FULL, f);
+            if (f) out[count + __popc(bal & ((1u << threadIdx.x) - 1u))] = h;
+            count += __popc(bal);
+        }
+        if (threadIdx.x == 0) n_minima[p] = count;
+    }
+}
+
+// =============================================================== icp_small_kernel
+// One CTA = one complete PCL-1.8.1 ICP run on a <=2048 x <=2048 pair:
+// correspondences (exact NN, reject d2 > max^2), umeyama (two-pass float, CANON256 sums),
+// in-place float transform, final = T_k * final, DefaultConvergenceCriteria, and the
+// getFitnessScore pass.  No host round trip inside a run.
+//
+// mode 0: judge run      -> angles = accumulated loop values of best_h      (KSS_ICP.hpp:92-93)
+// mode 1: hypothesis l   -> angles = index*6.3/step of minima[l], only if judge fitness > thr
+// mode 2: explicit input -> src_f64 is used as is (kss_icp API, KSS_ICP.hpp:323-356)
+__global__ void __launch_bounds__(256)
+icp_small_kernel(IcpArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    const int p = blockIdx.y;
+    const int slot = blockIdx.x;
+    const int n_s = a.cnt_s ? a.cnt_s[p] : a.cap_s;
+    const int n_t = a.cnt_t[p];
+    const int run = p * a.runs_per_pair + (a.mode == 1 ? 1 + slot : 0);
+
+    double ang_c[3] = {1.0, 1.0, 1.0}, ang_s[3] = {0.0, 0.0, 0.0};
+    if (a.mode == 1) {
+        const bool active = a.judge_thr < 0.0 || a.run_fit[p * a.runs_per_pair] > a.judge_thr;
+        if (!active || slot >= a.n_minima[p] || slot >= a.runs_per_pair - 1) return;
+        const int h = a.minima[(size_t)p * a.hpad + slot];
+        const int idx[3] = {h / (a.G * a.G), (h / a.G) % a.G, h % a.G};
+        for (int k = 0; k < 3; ++k) { ang_c[k] = a.trig_list[2 * idx[k]]; ang_s[k] = a.trig_list[2 * idx[k] + 1]; }
+    } else if (a.mode == 0) {
+        const int h = a.best_h[p];
+        const int idx[3] = {h / (a.G * a.G), (h / a.G) % a.G, h % a.G};
+        for (int k = 0; k < 3; ++k) { ang_c[k] = a.trig_accum[2 * idx[k]]; ang_s[k] = a.trig_accum[2 * idx[k] + 1]; }
+    }
+
+    const int npad = (n_t + TILE - 1) / TILE * TILE;
+    float4* tgt = reinterpret_cast<float4*>(smem_raw);
+    float* box = reinterpret_cast<float*>(tgt + npad);
+    float* cur = box + 6 * MAX_TILES;                 // SoA by ORIGINAL source index: x[n_s] y[n_s] z[n_s]
+    float* d2s = cur + 3 * n_s;                       // [n_s]
+    unsigned short* perm = reinterpret_cast<unsigned short*>(d2s + n_s);   // [n_s] Morton pos -> original
+    unsigned short* mpos = perm + n_s;                // [n_s] matched target position, 0xffff = rejected
+    unsigned short* tinv = mpos + n_s;                // [n_t] original target index -> Morton position
+    __shared__ float red[16];
+    __shared__ double redd;
+    __shared__ float Tk[16], fin[16];
+    __shared__ int kept, done;
+    __shared__ double prev_mse;
+
+    {
+        const float4* gts = a.t_sorted + (size_t)p * a.cap_tpad;
+        for (int j = threadIdx.x; j < npad; j += blockDim.x) tgt[j] = gts[j];
+        const float* gtb = a.t_box + (size_t)p * 6 * MAX_TILES;
+        for (int j = threadIdx.x; j < 6 * MAX_TILES; j += blockDim.x) box[j] = gtb[j];
+        const unsigned short* gp = a.s_perm + (size_t)p * a.cap_s;
+        for (int j = threadIdx.x; j < n_s; j += blockDim.x) perm[j] = gp[j];
+        const unsigned short* gi = a.t_inv + (size_t)p * a.cap_t;
+        for (int j = threadIdx.x; j < n_t; j += blockDim.x) tinv[j] = gi[j];
+    }
+    if (threadIdx.x < 16) fin[threadIdx.x] = (threadIdx.x % 5 == 0) ? 1.0f : 0.0f;
+    if (threadIdx.x == 0) { kept = 0; done = 0; prev_mse = DBL_MAX; }
+    __syncthreads();
+    TileView tv{tgt, box, npad / TILE};
+
+    const double* src = a.src_f64 + (size_t)p * a.cap_s * 3;
+    const double* a8 = a.align8 ? a.align8 + (size_t)p * 8 : nullptr;
+    auto input_point = [&](int o, float& x, float& y, float& z) {
+        double dx = src[3 * o], dy = src[3 * o + 1], dz = src[3 * o + 2];
+        if (a.mode != 2) {                                            // initRegistrationKSS.hpp:75-109
+            dx = align_coord(dx, a8[0], a8[3], a8[6]);
+            dy = align_coord(dy, a8[1], a8[4], a8[6]);
+            dz = align_coord(dz, a8[2], a8[5], a8[6]);
+            rot_x(ang_c[0], ang_s[0], dy, dz);
+            rot_y(ang_c[1], ang_s[1], dx, dz);
+            rot_z(ang_c[2], ang_s[2], dx, dy);
+        }
+        x = (float)dx; y = (float)dy; z = (float)dz;                  // KSS_ICP.hpp:328-333
+    };
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int iters = 0;
+    int converged = 0;
+
+    for (;;) {
+        // ---- (1) lazily apply the previous T_k, then correspondences for Morton-consecutive queries
+        int my_kept = 0;
+        for (int base = warp * 32; base < n_s; base += nwarps * 32) {
+            const int jpos = base + lane;
+            const bool valid = jpos < n_s;
+            const int o = perm[valid ? jpos : n_s - 1];
+            float x, y, z;
+            if (iters == 0) input_point(o, x, y, z);
+            else { xform_point(Tk, cur[o], cur[n_s + o], cur[2 * n_s + o], x, y, z); }
+            __syncwarp();
+            if (valid) { cur[o] = x; cur[n_s + o] = y; cur[2 * n_s + o] = z; }
+            const unsigned long long key = warp_nn<true>(tv, x, y, z);
+            const float d2 = __uint_as_float((unsigned)(key >> 32));
+            const unsigned orig = (unsigned)(key & 0xffffffffu);
+            const bool keep = !((double)d2 > a.max_dist_sqr);        // A.3: skip iff d2 > max_dist^2
+            if (valid) {
+                d2s[o] = d2;
+                mpos[o] = keep ? tinv[orig] : (unsigned short)0xffff;
+                my_kept += keep ? 1 : 0;
+                if (a.trace_idx && iters < a.trace_cap)
+                    a.trace_idx[((size_t)run * a.trace_cap + iters) * a.cap_s + o] = keep ? (int)orig : -1;
+                if (a.trace_src && iters < a.trace_cap) {
+                    float* ts = a.trace_src + (((size_t)run * a.trace_cap + iters) * a.cap_s + o) * 3;
+                    ts[0] = x; ts[1] = y; ts[2] = z;
+                }
+            }
+        }
+        my_kept = __reduce_add_sync(KSS_FULL, my_kept);
+        if (lane == 0 && my_kept) atomicAdd(&kept, my_kept);
+        __syncthreads();
+        const int cnt = kept;
+        if (cnt < 3) { converged = 0; break; }                       // min_number_correspondences_
+        // ---- (2) pass A: sums of kept source / matched target coordinates, and of d2 (double)
+        for (int q = warp; q < 7; q += nwarps) {
+            if (q < 3) {
+                const float* c = cur + q * n_s;
+                float s = canon_sum_warp_f32(n_s, [&](int i, float& v) { if (mpos[i] == 0xffff) return false; v = c[i]; return true; });
+                if (lane == 0) red[q] = s;
+            } else if (q < 6) {
+                const int ax = q - 3;
+                float s = canon_sum_warp_f32(n_s, [&](int i, float& v) {
+                    const unsigned m = mpos[i]; if (m == 0xffff) return false;
+                    const float4 t = tgt[m]; v = ax == 0 ? t.x : (ax == 1 ? t.y : t.z); return true; });
+                if (lane == 0) red[q] = s;
+            } else {
+                double s = canon_sum_warp_f64(n_s, [&](int i, double& v) { if (mpos[i] == 0xffff) return false; v = (double)d2s[i]; return true; });
+                if (lane == 0) redd = s;
+            }
+        }
+        __syncthreads();
+        const float one_over_n = div_(1.0f, (float)cnt);
+        const float sm0 = mul_(red[0], one_over_n), sm1 = mul_(red[1], one_over_n), sm2 = mul_(red[2], one_over_n);
+        const float dm0 = mul_(red[3], one_over_n), dm1 = mul_(red[4], one_over_n), dm2 = mul_(red[5], one_over_n);
+        // ---- (3) pass B: sigma(a,b) = one_over_n * sum (d_a - dmean_a) * (s_b - smean_b)
+        for (int q = warp; q < 9; q += nwarps) {
+            const int ra = q / 3, cb = q % 3;
+            const float dmean = ra == 0 ? dm0 : (ra == 1 ? dm1 : dm2);
+            const float smean = cb == 0 ? sm0 : (cb == 1 ? sm1 : sm2);
+            const float* c = cur + cb * n_s;
+            float s = canon_sum_warp_f32(n_s, [&](int i, float& v) {
+                const unsigned m = mpos[i]; if (m == 0xffff) return false;
+                const float4 t = tgt[m];
+                const float dv = ra == 0 ? t.x : (ra == 1 ? t.y : t.z);
+                v = mul_(sub_(dv, dmean), sub_(c[i], smean)); return true; });
+            if (lane == 0) red[7 + q] = mul_(one_over_n, s);
+        }
+        __syncthreads();
+        // ---- (4) one thread: SVD/Kabsch, accumulate, convergence
+        if (threadIdx.x == 0) {
+            float sigma[9], smean[3] = {sm0, sm1, sm2}, dmean[3] = {dm0, dm1, dm2}, T[16];
+            for (int i = 0; i < 9; ++i) sigma[i] = red[7 + i];
+            umeyama_finish(sigma, smean, dmean, T);
+            float F[16];
+            for (int i = 0; i < 16; ++i) F[i] = fin[i];
+            mat4_mul(T, F, F);
+            for (int i = 0; i < 16; ++i) { Tk[i] = T[i]; fin[i] = F[i]; }
+            const double mse = __ddiv_rn(redd, (double)cnt);
+            if (a.trace_T && iters < a.trace_cap)
+                for (int i = 0; i < 16; ++i) a.trace_T[((size_t)run * a.trace_cap + iters) * 16 + i] = T[i];
+            if (a.trace_mse && iters < a.trace_cap) a.trace_mse[(size_t)run * a.trace_cap + iters] = mse;
+            const int it = iters + 1;
+            int dn = 0;
+            if (it >= a.max_iter) dn = 1;                                            // A.6 (1)
+            else {
+                const double cos_angle = 0.5 * (double)sub_(add_(add_(T[0], T[5]), T[10]), 1.0f);
+                const double tr2 = (double)add_(add_(mul_(T[3], T[3]), mul_(T[7], T[7])), mul_(T[11], T[11]));
+                if (cos_angle >= a.rot_thr && tr2 <= a.trans_thr) dn = 1;           // A.6 (2)
+                else if (fabs(__dsub_rn(mse, prev_mse)) < a.mse_abs) dn = 1;        // A.6 (3) absolute
+                else if (__ddiv_rn(fabs(__dsub_rn(mse, prev_mse)), prev_mse) < a.mse_rel) dn = 1;  // relative
+                else prev_mse = mse;
+            }
+            done = dn; kept = 0;
+        }
+        __syncthreads();
+        ++iters;
+        if (done) { converged = 1; break; }
+    }
+
+    // ---- getFitnessScore: final * ORIGINAL input (one rounding), NN, mean of d2 in double (A.7)
+    __syncthreads();
+    for (int base = warp * 32; base < n_s; base += nwarps * 32) {
+        const int jpos = base + lane;
+        const bool valid = jpos < n_s;
+        const int o = perm[valid ? jpos : n_s - 1];
+        float x, y, z, fx, fy, fz;
+        input_point(o, x, y, z);
+        xform_point(fin, x, y, z, fx, fy, fz);
+        const unsigned long long key = warp_nn<false>(tv, fx, fy, fz);
+        if (valid) d2s[o] = __uint_as_float((unsigned)(key >> 32));
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double s = canon_sum_warp_f64(n_s, [&](int i, double& v) { v = (double)d2s[i]; return true; });
+        if (lane == 0) {
+            a.run_fit[run] = n_s > 0 ? __ddiv_rn(s, (double)n_s) : DBL_MAX;
+            a.run_iters[run] = iters;
+            a.run_conv[run] = converged;
+        }
+    }
+    if (threadIdx.x < 16) a.run_T[(size_t)run * 16 + threadIdx.x] = fin[threadIdx.x];
+}
+
+// =============================================================== select_kernel
+// KSS_ICP.hpp:99-125: multi-hypothesis branch iff judge fitness > 0.0005; winner = first
+// strict minimum with ri >= 0 starting from Q = 9999; else the sweep winner.
+__global__ void select_kernel(int P, int runs_per_pair, int hpad, int G, double judge_thr,
+                              const double* __restrict__ align8,
+                              const double* __restrict__ run_fit, const int* __restrict__ run_iters,
+                              const float* __restrict__ run_T,
+                              const int* __restrict__ best_h, const int* __restrict__ minima,
+                              const int* __restrict__ n_minima,
+                              PairOut* __restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    PairOut& o = out[p];
+    for (int i = 0; i < 8; ++i) o.align[i] = align8[(size_t)p * 8 + i];
+    const double E = run_fit[p * runs_per_pair];
+    o.judge_fitness = E;
+    o.judge_iters = run_iters[p * runs_per_pair];
+    o.n_minima = n_minima[p];
+    o.best_h = best_h[p];
+    o.G = G;
+    int total = o.judge_iters, nruns = 1;
+    int use_run = 0, used_h = best_h[p], winner = -1, multi = 0, overflow = 0;
+    if (E > judge_thr) {
+        multi = 1;
+        double Q = 9999.0;
+        int angleIndex = 0;
+        int L = n_minima[p];
+        if (L > runs_per_pair - 1) { overflow = 1; L = runs_per_pair - 1; }
+        for (int l = 0; l < L; ++l) {
+            const double ri = run_fit[p * runs_per_pair + 1 + l];
+            total += run_iters[p * runs_per_pair + 1 + l]; ++nruns;
+            if (ri < Q && ri >= 0.0) { Q = ri; angleIndex = l; }
+        }
+        winner = angleIndex;
+        use_run = 1 + angleIndex;
+        used_h = minima[(size_t)p * hpad + angleIndex];
+    }
+    // the final ICP (KSS_ICP.hpp:130) repeats the winner's run on identical input: reuse it
+    o.branch_multi = multi; o.winner = winner; o.used_h = used_h; o.use_list = multi;
+    o.final_fitness = run_fit[p * runs_per_pair + use_run];
+    o.final_iters = run_iters[p * runs_per_pair + use_run];
+    o.total_icp_iters = total + o.final_iters;
+    o.n_icp_runs = nruns + 1;
+    o.overflow = overflow;
+    for (int i = 0; i < 16; ++i) o.T[i] = run_T[((size_t)p * runs_per_pair + use_run) * 16 + i];
+}
+
+// =============================================================== final_apply_kernel
+// pointAlign = rt * Rotation_Angle(pointSource) : similarity in double (initRegistrationKSS.hpp:75-109),
+// then float 3x4 coefficients promoted to double, left-to-right sums (KSS_ICP.hpp:224-230).
+__global__ void __launch_bounds__(256)
+final_apply_kernel(const double* __restrict__ full_s, const int* __restrict__ cnt_S, int cap_S,
+                   const double* __restrict__ align8, const PairOut* __restrict__ out,
+                   const double* __restrict__ trig_accum, const double* __restrict__ trig_list, int G,
+                   double* __restrict__ point_align) {
+    const int p = blockIdx.y;
+    const int n = cnt_S ? cnt_S[p] : cap_S;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PairOut& o = out[p];
+    const double* trig = o.use_list ? trig_list : trig_accum;
+    const int h = o.used_h;
+    const int ix[3] = {h / (G * G), (h / G) % G, h % G};
+    const double* a8 = align8 + (size_t)p * 8;
+    const double* src = full_s + ((size_t)p * cap_S + i) * 3;
+    double x = align_coord(src[0], a8[0], a8[3], a8[6]);
+    double y = align_coord(src[1], a8[1], a8[4], a8[6]);
+    double z = align_coord(src[2], a8[2], a8[5], a8[6]);
+    rot_x(trig[2 * ix[0]], trig[2 * ix[0] + 1], y, z);
+    rot_y(trig[2 * ix[1]], trig[2 * ix[1] + 1], x, z);
+    rot_z(trig[2 * ix[2]], trig[2 * ix[2] + 1], x, y);
+    double* dst = point_align + ((size_t)p * cap_S + i) * 3;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        double v = __dmul_rn((double)o.T[4 * r + 0], x);
+        v = __dadd_rn(v, __dmul_rn((double)o.T[4 * r + 1], y));
+        v = __dadd_rn(v, __dmul_rn((double)o.T[4 * r + 2], z));
+        v = __dadd_rn(v, (double)o.T[4 * r + 3]);
+        dst[r] = v;
+    }
+}
+
+// =============================================================== generic point kernels (any n)
+__global__ void __launch_bounds__(256)
+apply_similarity_kernel(const double* __restrict__ pts, int n, const double* __restrict__ a7,
+                        const double* __restrict__ cs /* c0,s0,c1,s1,c2,s2 */, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = align_coord(pts[3 * i], a7[0], a7[3], a7[6]);
+    double y = align_coord(pts[3 * i + 1], a7[1], a7[4], a7[6]);
+    double z = align_coord(pts[3 * i + 2], a7[2], a7[5], a7[6]);
+    rot_x(cs[0], cs[1], y, z);
+    rot_y(cs[2], cs[3], x, z);
+    rot_z(cs[4], cs[5], x, y);
+    out[3 * i] = x; out[3 * i + 1] = y; out[3 * i + 2] = z;
+}
+
+__global__ void __launch_bounds__(256)
+apply_transform_kernel(const double* __restrict__ pts, int n, const float* __restrict__ T, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        double v = __dmul_rn((double)T[4 * r + 0], x);
+        v = __dadd_rn(v, __dmul_rn((double)T[4 * r + 1], y));
+        v = __dadd_rn(v, __dmul_rn((double)T[4 * r + 2], z));
+        v = __dadd_rn(v, (double)T[4 * r + 3]);
+        out[3 * i + r] = v;
+    }
+}
+
+// =============================================================== nn / metrics on the small path
+// One CTA per pair: exact NN of every query (double, narrowed with RN) against the
+// Morton-tiled target.  MODE 0: write idx/d2.  MODE 1: PCR_QM serial double sums
+// (registrationMeasure.hpp:66-88) -> out3 = {MSE, RMSE, MAE}.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+nn_small_kernel(const double* __restrict__ q, const int* __restrict__ cnt_q, int cap_q,
+                const unsigned short* __restrict__ q_perm,
+                const float4* __restrict__ t_sorted, const float* __restrict__ t_box,
+                const int* __restrict__ cnt_t, int cap_tpad,
+                int* __restrict__ idx, float* __restrict__ d2out, double* __restrict__ out3, int out3_stride) {
+    extern __shared__ unsigned char smem_raw[];
+    const int p = blockIdx.x;
+    const int n_q = cnt_q ? cnt_q[p] : cap_q;
+    const int n_t = cnt_t[p];
+    const int npad = (n_t + TILE - 1) / TILE * TILE;
+    float4* tgt = reinterpret_cast<float4*>(smem_raw);
+    float* box = reinterpret_cast<float*>(tgt + npad);
+    float* d2s = box + 6 * MAX_TILES;                  // [n_q]      (MODE 1)
+    const float4* gts = t_sorted + (size_t)p * cap_tpad;
+    for (int j = threadIdx.x; j < npad; j += blockDim.x) tgt[j] = gts[j];
+    const float* gtb = t_box + (size_t)p * 6 * MAX_TILES;
+    for (int j = threadIdx.x; j < 6 * MAX_TILES; j += blockDim.x) box[j] = gtb[j];
+    __syncthreads();
+    TileView tv{tgt, box, npad / TILE};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const double* qs = q + (size_t)p * cap_q * 3;
+    const unsigned short* perm = q_perm + (size_t)p * cap_q;
+    for (int base = warp * 32; base < n_q; base += nwarps * 32) {
+        const int jpos = base + lane;
+        const bool valid = jpos < n_q;
+        const int o = perm[valid ? jpos : n_q - 1];
+        const float x = (float)qs[3 * o], y = (float)qs[3 * o + 1], z = (float)qs[3 * o + 2];
+        const unsigned long long key = warp_nn<MODE == 0>(tv, x, y, z);
+        const float d2 = __uint_as_float((unsigned)(key >> 32));
+        if (valid) {
+            if (MODE == 0) { idx[(size_t)p * cap_q + o] = (int)(key & 0xffffffffu); d2out[(size_t)p * cap_q + o] = d2; }
+            else d2s[o] = d2;
+        }
+    }
+    if (MODE == 1) {
+        __syncthreads();
+        __shared__ double sums[2];
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+#pragma unroll 8
+            for (int i = 0; i < n_q; ++i) s = __dadd_rn(s, (double)d2s[i]);
+            sums[0] = s;
+        }
+        if (threadIdx.x == 32) {
+            double s = 0.0;
+#pragma unroll 4
+            for (int i = 0; i < n_q; ++i) s = __dadd_rn(s, __dsqrt_rn((double)d2s[i]));
+            sums[1] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double mse = __ddiv_rn(sums[0], (double)n_q);
+            out3[(size_t)p * out3_stride + 0] = mse;
+            out3[(size_t)p * out3_stride + 1] = __dsqrt_rn(mse);
+            out3[(size_t)p * out3_stride + 2] = __ddiv_rn(sums[1], (double)n_q);
+        }
+    }
+}
+
+// =============================================================== host-side launchers
+static inline size_t sort_smem() { return SMALL_MAX * sizeof(unsigned) + 3 * SMALL_MAX * sizeof(float); }
+
+cudaError_t launch_sort_target(cudaStream_t st, int P, const double* pts, const int* cnt, int cap,
+                               float4* t_sorted, float* t_box, unsigned short* t_inv, int cap_pad) {
+    sort_cloud_kernel<<<P, 256, sort_smem(), st>>>(pts, cnt, cap, 0, t_sorted, t_box, t_inv, cap_pad, nullptr);
+    return cudaGetLastError();
+}
+cudaError_t launch_sort_source(cudaStream_t st, int P, const double* pts, const int* cnt, int cap,
+                               unsigned short* perm) {
+    sort_cloud_kernel<<<P, 256, sort_smem(), st>>>(pts, cnt, cap, 1, nullptr, nullptr, nullptr, 0, perm);
+    return cudaGetLastError();
+}
+cudaError_t launch_middle_align(cudaStream_t st, int P, const double* sim_s, const int* cnt_s, int cap_s,
+                                const double* sim_t, const int* cnt_t, int cap_t, double* align8, double* s_al) {
+    const size_t smem = 4 * SMALL_MAX * sizeof(double);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(middle_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    middle_align_kernel<<<P, 256, smem, st>>>(sim_s, cnt_s, cap_s, sim_t, cnt_t, cap_t, align8, s_al);
+    return cudaGetLastError();
+}
+cudaError_t launch_sweep(cudaStream_t st, int P, const double* s_al, const int* cnt_s, int cap_s,
+                         const unsigned short* s_perm, const float4* t_sorted, const float* t_box,
+                         const int* cnt_t, int cap_tpad, const double* trig_accum, int G, int score_mode,
+                         double* rbuf, int hpad) {
+    const size_t smem = (size_t)cap_tpad * sizeof(float4) + 6 * MAX_TILES * sizeof(float);
+    static size_t set = 0;
+    if (smem > set) { cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
+    sweep_kernel<<<dim3(G * G, P), 256, smem, st>>>(s_al, cnt_s, cap_s, s_perm, t_sorted, t_box, cnt_t, cap_tpad,
+                                                   trig_accum, G, score_mode, rbuf, hpad);
+    return cudaGetLastError();
+}
+cudaError_t launch_sweep_finalize(cudaStream_t st, int P, const double* rbuf, const int* cnt_s, int cap_s, int hpad,
+                                  int G, int score_mode, double* value, int* best_h, int* minima, int* n_minima) {
+    const int H = G * G * G;
+    const size_t smem = (size_t)H * sizeof(double) + H;
+    int threads = H < 1024 ? (H + 31) / 32 * 32 : 1024;
+    sweep_finalize_kernel<<<P, threads, smem, st>>>(rbuf, cnt_s, cap_s, hpad, G, score_mode, value, best_h, minima, n_minima);
+    return cudaGetLastError();
+}
+size_t icp_smem_bytes(int cap_s, int cap_t, int cap_tpad) {
+    return (size_t)cap_tpad * sizeof(float4) + 6 * MAX_TILES * sizeof(float) + (size_t)cap_s * 4 * sizeof(float) +
+           (size_t)cap_s * 2 * sizeof(unsigned short) + (size_t)cap_t * sizeof(unsigned short) + 16;
+}
+cudaError_t launch_icp(cudaStream_t st, int P, int slots, const IcpArgs& a) {
+    const size_t smem = icp_smem_bytes(a.cap_s, a.cap_t, a.cap_tpad);
+    static size_t set = 0;
+    if (smem > set) { cudaFuncSetAttribute(icp_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
+    icp_small_kernel<<<dim3(slots, P), 256, smem, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_select(cudaStream_t st, int P, int runs_per_pair, int hpad, int G, double judge_thr,
+                          const double* align8, const double* run_fit, const int* run_iters, const float* run_T, const int* best_h,
+                          const int* minima, const int* n_minima, PairOut* out) {
+    select_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, runs_per_pair, hpad, G, judge_thr, align8, run_fit, run_iters, run_T,
+                                                  best_h, minima, n_minima, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_final_apply(cudaStream_t st, int P, const double* full_s, const int* cnt_S, int cap_S,
+                               const double* align8, const PairOut* out, const double* trig_accum,
+                               const double* trig_list, int G, double* point_align) {
+    final_apply_kernel<<<dim3((cap_S + 255) / 256, P), 256, 0, st>>>(full_s, cnt_S, cap_S, align8, out, trig_accum,
+                                                                    trig_list, G, point_align);
+    return cudaGetLastError();
+}
+cudaError_t launch_apply_similarity(cudaStream_t st, const double* pts, int n, const double* a7, const double* cs, double* out) {
+    apply_similarity_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, a7, cs, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_apply_transform(cudaStream_t st, const double* pts, int n, const float* T, double* out) {
+    apply_transform_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, T, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_nn_small(cudaStream_t st, int P, int mode, const double* q, const int* cnt_q, int cap_q,
+                            const unsigned short* q_perm, const float4* t_sorted, const float* t_box,
+                            const int* cnt_t, int cap_tpad, int* idx, float* d2, double* out3, int out3_stride) {
+    const size_t smem = (size_t)cap_tpad * sizeof(float4) + 6 * MAX_TILES * sizeof(float) + (size_t)cap_q * sizeof(float);
+    static size_t set0 = 0, set1 = 0;
+    if (mode == 0) {
+        if (smem > set0) { cudaFuncSetAttribute(nn_small_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set0 = smem; }
+        nn_small_kernel<0><<<P, 256, smem, st>>>(q, cnt_q, cap_q, q_perm, t_sorted, t_box, cnt_t, cap_tpad, idx, d2, out3, out3_stride);
+    } else {
+        if (smem > set1) { cudaFuncSetAttribute(nn_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set1 = smem; }
+        nn_small_kernel<1><<<P, 256, smem, st>>>(q, cnt_q, cap_q, q_perm, t_sorted, t_box, cnt_t, cap_tpad, idx, d2, out3, out3_stride);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace kss
