@@ -105,6 +105,22 @@ void kss_batch_default(kss_batch* b);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 long long kss_ctx_launch_count(kss_ctx* ctx);
 
+/* per-stage device timing of the batched pipeline: CUDA events recorded on ctx's stream around
+ * each stage (bench.py derives the per-kernel roofline from these; off by default) */
+#define KSS_STAGE_PREP            0   /* MiddleAlign + Morton sorts        */
+#define KSS_STAGE_SWEEP           1   /* sweep_kernel                       */
+#define KSS_STAGE_SWEEP_FINALIZE  2
+#define KSS_STAGE_ICP_JUDGE       3
+#define KSS_STAGE_ICP_HYP         4
+#define KSS_STAGE_SELECT_APPLY    5
+#define KSS_STAGE_METRICS         6
+#define KSS_STAGE_LARGE_BUILD     7   /* large path: Morton bucket sort + box pyramid */
+#define KSS_STAGE_LARGE_NN        8   /* large path: hierarchical NN kernel           */
+#define KSS_STAGE_LARGE_REDUCE    9   /* large path: canonical reductions + SVD       */
+#define KSS_STAGE_COUNT          10
+int kss_ctx_set_timing(kss_ctx* ctx, int enable);      /* also resets the accumulators */
+int kss_ctx_stage_ms(kss_ctx* ctx, int stage, double* ms, long long* calls);
+
 /* ---- single-object entry points ------------------------------------------------------ */
 
 /* replaces initRegistration_KSS::initRegistration_MiddleAlign (initRegistrationKSS.hpp:144-220).

@@ -18,6 +18,8 @@ HEADER_PATH = os.path.join(os.path.dirname(_DIR), "include", "kss_icp_b200.h")
 KSS_OK = 0
 SMALL_MAX = 2048
 SCORE_AVE, SCORE_MAX, SCORE_DIFF = 0, 1, 2
+STAGES = ("prep", "sweep", "sweep_finalize", "icp_judge", "icp_hyp", "select_apply", "metrics",
+          "large_build", "large_nn", "large_reduce")
 
 
 class KssError(RuntimeError):
@@ -116,6 +118,14 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.kss_ctx_launch_count(self.h))
+
+    def set_timing(self, enable=True):
+        self._ck(self.lib.kss_ctx_set_timing(self.h, C.c_int(1 if enable else 0)))
+
+    def stage_ms(self, stage):
+        ms = C.c_double(0); calls = C.c_longlong(0)
+        self._ck(self.lib.kss_ctx_stage_ms(self.h, C.c_int(stage), C.byref(ms), C.byref(calls)))
+        return ms.value, calls.value
 
     def synchronize(self):
         self._ck(self.lib.kss_ctx_synchronize(self.h))

@@ -32,6 +32,13 @@ struct kss_ctx {
     std::map<std::string, Buf> bufs;
     size_t ws_budget = (size_t)6 << 30;
     int slots_override = 0;
+    // optional per-stage CUDA-event timing (bench.py roofline): events on the launching stream
+    bool timing = false;
+    struct Span { int stage; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> ev_pool;
+    double stage_ms[KSS_STAGE_COUNT] = {0};
+    long long stage_calls[KSS_STAGE_COUNT] = {0};
 };
 
 namespace {
@@ -57,6 +64,32 @@ int fail(kss_ctx* c, int code, const std::string& msg) {
         CU(call);       \
         ctx->launches++;\
     } while (0)
+
+cudaEvent_t ev_get(kss_ctx* c) {
+    cudaEvent_t e;
+    if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+struct StageTimer {
+    kss_ctx* c; int stage; cudaEvent_t a = nullptr;
+    StageTimer(kss_ctx* ctx, int st) : c(ctx), stage(st) {
+        if (c->timing) { a = ev_get(c); cudaEventRecord(a, c->stream); }
+    }
+    ~StageTimer() {
+        if (a) { cudaEvent_t b = ev_get(c); cudaEventRecord(b, c->stream); c->spans.push_back({stage, a, b}); }
+    }
+};
+void collect_spans(kss_ctx* c) {
+    for (auto& sp : c->spans) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            c->stage_ms[sp.stage] += ms; c->stage_calls[sp.stage] += 1;
+        }
+        c->ev_pool.push_back(sp.a); c->ev_pool.push_back(sp.b);
+    }
+    c->spans.clear();
+}
 
 template <class T>
 int dev_buf(kss_ctx* ctx, const char* name, size_t count, T** out) {
@@ -175,12 +208,21 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
     BUF("run_iters", (size_t)P * R, &run_iters);
     BUF("run_conv", (size_t)P * R, &run_conv);
 
-    KL(launch_middle_align(st, P, sim_s, cnt_s, cap_s, sim_t, cnt_t, cap_t, align8, s_al));
-    KL(launch_sort_target(st, P, sim_t, cnt_t, cap_t, t_sorted, t_box, t_inv, cap_tpad));
-    KL(launch_sort_source(st, P, sim_s, cnt_s, cap_s, s_perm));
-    KL(launch_sweep(st, P, s_al, cnt_s, cap_s, s_perm, t_sorted, t_box, cnt_t, cap_tpad, ctx->d_trig_accum, G,
-                    KSS_SCORE_AVE, rbuf, hpad));
-    KL(launch_sweep_finalize(st, P, rbuf, cnt_s, cap_s, hpad, G, KSS_SCORE_AVE, value, best_h, minima, n_minima));
+    {
+        StageTimer tm(ctx, KSS_STAGE_PREP);
+        KL(launch_middle_align(st, P, sim_s, cnt_s, cap_s, sim_t, cnt_t, cap_t, align8, s_al));
+        KL(launch_sort_target(st, P, sim_t, cnt_t, cap_t, t_sorted, t_box, t_inv, cap_tpad));
+        KL(launch_sort_source(st, P, sim_s, cnt_s, cap_s, s_perm));
+    }
+    {
+        StageTimer tm(ctx, KSS_STAGE_SWEEP);
+        KL(launch_sweep(st, P, s_al, cnt_s, cap_s, s_perm, t_sorted, t_box, cnt_t, cap_tpad, ctx->d_trig_accum, G,
+                        KSS_SCORE_AVE, rbuf, hpad));
+    }
+    {
+        StageTimer tm(ctx, KSS_STAGE_SWEEP_FINALIZE);
+        KL(launch_sweep_finalize(st, P, rbuf, cnt_s, cap_s, hpad, G, KSS_SCORE_AVE, value, best_h, minima, n_minima));
+    }
 
     IcpArgs a{};
     a.src_f64 = sim_s; a.cnt_s = cnt_s; a.cap_s = cap_s; a.s_perm = s_perm;
@@ -192,15 +234,24 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
     icp_fill(a, b.icp);
     a.run_T = run_T; a.run_fit = run_fit; a.run_iters = run_iters; a.run_conv = run_conv;
     a.mode = 0;
-    KL(launch_icp(st, P, 1, a));                           // judge run (KSS_ICP.hpp:93)
+    {
+        StageTimer tm(ctx, KSS_STAGE_ICP_JUDGE);
+        KL(launch_icp(st, P, 1, a));                           // judge run (KSS_ICP.hpp:93)
+    }
     a.mode = 1;
-    if (slots > 0) KL(launch_icp(st, P, slots, a));        // hypothesis runs (KSS_ICP.hpp:102-118)
-    KL(launch_select(st, P, R, hpad, G, b.judge_threshold, align8, run_fit, run_iters, run_T, best_h, minima,
-                     n_minima, d_out));
-
+    if (slots > 0) {
+        StageTimer tm(ctx, KSS_STAGE_ICP_HYP);
+        KL(launch_icp(st, P, slots, a));                       // hypothesis runs (KSS_ICP.hpp:102-118)
+    }
     double* pa = d_point_align;
     if (!pa) BUF("point_align", (size_t)P * cap_S * 3, &pa);
-    KL(launch_final_apply(st, P, full_s, cnt_S, cap_S, align8, d_out, ctx->d_trig_accum, ctx->d_trig_list, G, pa));
+    {
+        StageTimer tm(ctx, KSS_STAGE_SELECT_APPLY);
+        KL(launch_select(st, P, R, hpad, G, b.judge_threshold, align8, run_fit, run_iters, run_T, best_h, minima,
+                         n_minima, d_out));
+        KL(launch_final_apply(st, P, full_s, cnt_S, cap_S, align8, d_out, ctx->d_trig_accum, ctx->d_trig_list, G, pa));
+    }
+    StageTimer tm_metrics(ctx, KSS_STAGE_METRICS);
     if (cap_T <= SMALL_MAX && cap_S <= SMALL_MAX) {
         BUF("S_perm", (size_t)P * cap_S, &S_perm);
         BUF("T_sorted", (size_t)P * cap_Tpad, &T_sorted);
@@ -278,6 +329,8 @@ void kss_ctx_destroy(kss_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    collect_spans(ctx);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto& kv : ctx->bufs) if (kv.second.p) cudaFree(kv.second.p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -287,6 +340,22 @@ long long kss_ctx_launch_count(kss_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int kss_ctx_synchronize(kss_ctx* ctx) {
     if (!ctx) return KSS_ERR_ARG;
     CU(cudaStreamSynchronize(ctx->stream));
+    return KSS_OK;
+}
+
+int kss_ctx_set_timing(kss_ctx* ctx, int enable) {
+    if (!ctx) return KSS_ERR_ARG;
+    collect_spans(ctx);
+    ctx->timing = enable != 0;
+    for (int i = 0; i < KSS_STAGE_COUNT; ++i) { ctx->stage_ms[i] = 0; ctx->stage_calls[i] = 0; }
+    return KSS_OK;
+}
+int kss_ctx_stage_ms(kss_ctx* ctx, int stage, double* ms, long long* calls) {
+    if (!ctx || stage < 0 || stage >= KSS_STAGE_COUNT) return KSS_ERR_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    collect_spans(ctx);
+    if (ms) *ms = ctx->stage_ms[stage];
+    if (calls) *calls = ctx->stage_calls[stage];
     return KSS_OK;
 }
 
