@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-1m", action="store_true", help="skip the 1M-point ICP-iteration roofline leg")
     ap.add_argument("--points-1m", type=int, default=1000000)
+    ap.add_argument("--only-1m", action="store_true", help="debug: run only the 1M-point leg")
     return ap.parse_args()
 
 
@@ -168,6 +169,13 @@ def main():
     stream = torch.cuda.Stream(device=local)
     ctx = pkg.Context(local, stream=stream.cuda_stream)
 
+    if args.only_1m:
+        import bench_large
+        with torch.cuda.stream(stream):
+            r, ex = bench_large.icp_iteration_roofline(pkg, ctx, args, *peaks(), stream=stream)
+        print(json.dumps({"roofline": r, **ex}))
+        return
+
     lo, hi = shard(args.pairs, world, rank)
     P = hi - lo
     b, _ = pkg.synth.modelnet_batch(P, n_full=N_FULL, first=lo)
@@ -243,7 +251,9 @@ def main():
         hbm_peak, which = peaks()
         try:
             import bench_large
-            roofline, extra = bench_large.icp_iteration_roofline(pkg, ctx, args, hbm_peak, which) if not args.no_1m else (None, {})
+            if not args.no_1m and world == 1:
+                with torch.cuda.stream(stream):
+                    roofline, extra = bench_large.icp_iteration_roofline(pkg, ctx, args, hbm_peak, which, stream=stream)
         except ImportError:
             roofline = None
         if world == 1 and not args.no_cpu_baseline:

@@ -148,6 +148,15 @@ int kss_icp(kss_ctx* ctx, const double* src, int n_s, const double* tgt, int n_t
             const kss_icp_params* prm, float T[16], double* fitness, int* iters, int* converged,
             kss_icp_trace* trace);
 
+/* the same ICP on clouds of any size, driven in steps (full-resolution overload
+ * shapeRegistration_ICP(int iter), KSS_ICP.hpp:133-183; bench.py times `iterate`):
+ * begin = H2D + Morton bucket sort + box pyramid; iterate = enqueue `count` iterations
+ * (NN, reductions, SVD, transform; no-ops once converged; fitness_eps < 0 disables the
+ * convergence tests for steady-state timing); end = getFitnessScore pass + results. */
+int kss_icp_large_begin(kss_ctx* ctx, const double* src, int n_s, const double* tgt, int n_t);
+int kss_icp_large_iterate(kss_ctx* ctx, const kss_icp_params* prm, int count);
+int kss_icp_large_end(kss_ctx* ctx, const kss_icp_params* prm, float T[16], double* fitness, int* iters, int* converged);
+
 /* replaces the final apply loop at KSS_ICP.hpp:222-230 */
 int kss_apply_transform(kss_ctx* ctx, const float T[16], const double* pts, int n, double* out);
 

@@ -177,6 +177,20 @@ class Context:
             out["trace"] = keep
         return out
 
+    def icp_large_begin(self, src, tgt):
+        s = _f64(src); t = _f64(tgt)
+        self._ck(self.lib.kss_icp_large_begin(self.h, _p(s), C.c_int(len(s)), _p(t), C.c_int(len(t))))
+
+    def icp_large_iterate(self, count, max_iter=1000, max_corr_dist=1.0, trans_eps=1e-10, fit_eps=1e-3):
+        prm = IcpParams(max_iter, max_corr_dist, trans_eps, fit_eps)
+        self._ck(self.lib.kss_icp_large_iterate(self.h, C.byref(prm), C.c_int(count)))
+
+    def icp_large_end(self, max_iter=1000, max_corr_dist=1.0, trans_eps=1e-10, fit_eps=1e-3):
+        prm = IcpParams(max_iter, max_corr_dist, trans_eps, fit_eps)
+        T = np.empty(16, np.float32); fit = C.c_double(0); it = C.c_int(0); cv = C.c_int(0)
+        self._ck(self.lib.kss_icp_large_end(self.h, C.byref(prm), _p(T), C.byref(fit), C.byref(it), C.byref(cv)))
+        return dict(fitness=fit.value, T=T.reshape(4, 4), iters=it.value, converged=cv.value)
+
     def nn_metrics(self, a, t):
         a = _f64(a); t = _f64(t); out = np.empty(3, np.float64)
         self._ck(self.lib.kss_nn_metrics(self.h, _p(a), C.c_int(len(a)), _p(t), C.c_int(len(t)), _p(out)))

@@ -37,6 +37,9 @@ struct kss_ctx {
     struct Span { int stage; cudaEvent_t a, b; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> ev_pool;
+    LargeIcp large_run;
+    bool large_ready = false;
+    cudaEvent_t open_ev[KSS_STAGE_COUNT] = {nullptr};
     double stage_ms[KSS_STAGE_COUNT] = {0};
     long long stage_calls[KSS_STAGE_COUNT] = {0};
 };
@@ -356,6 +359,54 @@ int kss_ctx_stage_ms(kss_ctx* ctx, int stage, double* ms, long long* calls) {
     collect_spans(ctx);
     if (ms) *ms = ctx->stage_ms[stage];
     if (calls) *calls = ctx->stage_calls[stage];
+    return KSS_OK;
+}
+
+int kss_icp_large_begin(kss_ctx* ctx, const double* src, int n_s, const double* tgt, int n_t) {
+    if (!ctx) return KSS_ERR_ARG;
+    if (!src || !tgt || n_s < 1 || n_t < 1) return fail(ctx, KSS_ERR_ARG, "kss_icp_large_begin: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    double *d_s, *d_t;
+    BUF("lg_in_s", (size_t)n_s * 3, &d_s); BUF("lg_in_t", (size_t)n_t * 3, &d_t);
+    CU(cudaMemcpyAsync(d_s, src, sizeof(double) * 3 * (size_t)n_s, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_t, tgt, sizeof(double) * 3 * (size_t)n_t, cudaMemcpyHostToDevice, ctx->stream));
+    auto alloc = [&](const char* name, size_t bytes, void** out) {
+        unsigned char* q; int rr = dev_buf(ctx, name, bytes, &q); *out = q; return rr; };
+    ctx->large_ready = false;
+    int r;
+    {
+        StageTimer tm(ctx, KSS_STAGE_LARGE_BUILD);
+        r = large_icp_prepare(ctx->stream, &ctx->launches, d_s, n_s, d_t, n_t, alloc, &ctx->large_run);
+    }
+    if (r != KSS_OK) return fail(ctx, r, "kss_icp_large_begin: build failed");
+    ctx->large_run.mark_user = ctx;
+    ctx->large_run.mark = [](void* u, int stage, int begin) {
+        kss_ctx* c = (kss_ctx*)u;
+        if (!c->timing) return;
+        if (begin) { c->open_ev[stage] = ev_get(c); cudaEventRecord(c->open_ev[stage], c->stream); }
+        else if (c->open_ev[stage]) {
+            cudaEvent_t b = ev_get(c); cudaEventRecord(b, c->stream);
+            c->spans.push_back({stage, c->open_ev[stage], b}); c->open_ev[stage] = nullptr;
+        }
+    };
+    ctx->large_ready = true;
+    return KSS_OK;
+}
+int kss_icp_large_iterate(kss_ctx* ctx, const kss_icp_params* prm, int count) {
+    if (!ctx || !prm) return KSS_ERR_ARG;
+    if (!ctx->large_ready) return fail(ctx, KSS_ERR_ARG, "kss_icp_large_iterate: call kss_icp_large_begin first");
+    int r = large_icp_iterations(ctx->stream, &ctx->launches, &ctx->large_run, prm, count);
+    if (r != KSS_OK) return fail(ctx, r, "kss_icp_large_iterate failed");
+    return KSS_OK;
+}
+int kss_icp_large_end(kss_ctx* ctx, const kss_icp_params* prm, float T[16], double* fitness, int* iters, int* converged) {
+    if (!ctx || !prm) return KSS_ERR_ARG;
+    if (!ctx->large_ready) return fail(ctx, KSS_ERR_ARG, "kss_icp_large_end: call kss_icp_large_begin first");
+    kss_icp_params stop = *prm;
+    stop.max_iterations = 0;                       // no further iterations: fitness pass only
+    int r = large_icp_run(ctx->stream, &ctx->launches, &ctx->large_run, &stop, 1);
+    if (r == KSS_OK) r = large_icp_result(ctx->stream, &ctx->large_run, T, fitness, iters, converged);
+    if (r != KSS_OK) return fail(ctx, r, "kss_icp_large_end failed");
     return KSS_OK;
 }
 

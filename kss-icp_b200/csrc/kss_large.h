@@ -19,6 +19,24 @@ int large_nn_device(cudaStream_t st, long long* launches, const double* d_q, int
 int large_metrics_device(cudaStream_t st, long long* launches, const double* d_q, const int* d_cnt_q, int cap_q,
                          const double* d_t, const int* d_cnt_t, int cap_t, double* d_out3, const DevAlloc& alloc);
 
+// a prepared full-resolution ICP run (device buffers owned by the context's allocator)
+struct LargeIcp {
+    alignas(8) unsigned char pyramid[160];
+    int n_s = 0, n_t = 0, nchunks = 0;
+    void *t_orig = nullptr, *inp = nullptr, *cur = nullptr, *state = nullptr;
+    int *perm = nullptr, *idx = nullptr, *partK = nullptr;
+    float *d2 = nullptr, *partA = nullptr, *partB = nullptr;
+    double *partD = nullptr, *out3 = nullptr;
+    // optional stage marks (CUDA-event timing by the context): mark(user, KSS_STAGE_*, begin?1:0)
+    void (*mark)(void* user, int stage, int begin) = nullptr;
+    void* mark_user = nullptr;
+};
+int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, int n_s, const double* d_t, int n_t,
+                      const DevAlloc& alloc, LargeIcp* run);
+int large_icp_iterations(cudaStream_t st, long long* launches, LargeIcp* run, const kss_icp_params* prm, int count);
+int large_icp_run(cudaStream_t st, long long* launches, LargeIcp* run, const kss_icp_params* prm, int poll);
+int large_icp_result(cudaStream_t st, LargeIcp* run, float T[16], double* fitness, int* iters, int* converged);
+
 // one full-resolution PCL-ICP run from host clouds
 int large_icp_host(cudaStream_t st, long long* launches, const double* src, int n_s, const double* tgt, int n_t,
                    const kss_icp_params* prm, float T[16], double* fitness, int* iters, int* converged,
