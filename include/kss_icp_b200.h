@@ -117,7 +117,8 @@ long long kss_ctx_launch_count(kss_ctx* ctx);
 #define KSS_STAGE_LARGE_BUILD     7   /* large path: Morton bucket sort + box pyramid */
 #define KSS_STAGE_LARGE_NN        8   /* large path: hierarchical NN kernel           */
 #define KSS_STAGE_LARGE_REDUCE    9   /* large path: canonical reductions + SVD       */
-#define KSS_STAGE_COUNT          10
+#define KSS_STAGE_CG_BUILD       10   /* candidate grid build (per pair, once)         */
+#define KSS_STAGE_COUNT          11
 int kss_ctx_set_timing(kss_ctx* ctx, int enable);      /* also resets the accumulators */
 int kss_ctx_stage_ms(kss_ctx* ctx, int stage, double* ms, long long* calls);
 

@@ -19,7 +19,7 @@ KSS_OK = 0
 SMALL_MAX = 2048
 SCORE_AVE, SCORE_MAX, SCORE_DIFF = 0, 1, 2
 STAGES = ("prep", "sweep", "sweep_finalize", "icp_judge", "icp_hyp", "select_apply", "metrics",
-          "large_build", "large_nn", "large_reduce")
+          "large_build", "large_nn", "large_reduce", "cg_build")
 
 
 class KssError(RuntimeError):

@@ -30,7 +30,7 @@ struct kss_ctx {
     // grow-only named device buffers
     struct Buf { void* p = nullptr; size_t cap = 0; };
     std::map<std::string, Buf> bufs;
-    size_t ws_budget = (size_t)6 << 30;
+    size_t ws_budget = (size_t)48 << 30;
     int slots_override = 0;
     // optional per-stage CUDA-event timing (bench.py roofline): events on the launching stream
     bool timing = false;
@@ -171,6 +171,18 @@ int counts_or_fill(kss_ctx* ctx, const char* name, const int* d_cnt, int P, int 
 
 inline int pad32(int n) { return (n + 31) / 32 * 32; }
 
+// KSS_NO_CG=1 disables the candidate grid (tile search everywhere): A/B switch for tests and profiling
+bool cg_enabled() { const char* e = getenv("KSS_NO_CG"); return !(e && e[0] == '1'); }
+
+int cg_buffers(kss_ctx* ctx, int P, CgBuffers* cg) {
+    BUF("cg_geom", (size_t)P * 8, &cg->geom);
+    BUF("cg_hdr", (size_t)P * cg_hdr_words_per_pair(), &cg->hdr);
+    BUF("cg_arena", (size_t)P * cg_arena_entries_per_pair(), &cg->arena);
+    BUF("cg_cursor", (size_t)P, &cg->cursor);
+    BUF("cg_ok", (size_t)P, &cg->ok);
+    return KSS_OK;
+}
+
 void icp_fill(IcpArgs& a, const kss_icp_params& prm) {
     a.max_iter = prm.max_iterations;
     a.max_dist_sqr = prm.max_corr_dist * prm.max_corr_dist;
@@ -217,10 +229,19 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
         KL(launch_sort_target(st, P, sim_t, cnt_t, cap_t, t_sorted, t_box, t_inv, cap_tpad));
         KL(launch_sort_source(st, P, sim_s, cnt_s, cap_s, s_perm));
     }
+    CgBuffers cgb{}; const CgBuffers* cg = nullptr;
+    if (cg_enabled()) {
+        StageTimer tm(ctx, KSS_STAGE_CG_BUILD);
+        int r = cg_buffers(ctx, P, &cgb); if (r) return r;
+        int nl = 0;
+        CU(launch_cg_build(st, P, 0, s_al, cnt_s, cap_s, nullptr, nullptr, 0, t_sorted, cnt_t, cap_tpad, cgb, &nl));
+        ctx->launches += nl;
+        cg = &cgb;
+    }
     {
         StageTimer tm(ctx, KSS_STAGE_SWEEP);
         KL(launch_sweep(st, P, s_al, cnt_s, cap_s, s_perm, t_sorted, t_box, cnt_t, cap_tpad, ctx->d_trig_accum, G,
-                        KSS_SCORE_AVE, rbuf, hpad));
+                        KSS_SCORE_AVE, rbuf, hpad, cg));
     }
     {
         StageTimer tm(ctx, KSS_STAGE_SWEEP_FINALIZE);
@@ -234,6 +255,7 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
     a.best_h = best_h; a.minima = minima; a.n_minima = n_minima;
     a.trig_accum = ctx->d_trig_accum; a.trig_list = ctx->d_trig_list;
     a.judge_thr = b.judge_threshold;
+    if (cg) { a.cg_geom = cg->geom; a.cg_hdr = cg->hdr; a.cg_arena = cg->arena; a.cg_ok = cg->ok; }
     icp_fill(a, b.icp);
     a.run_T = run_T; a.run_fit = run_fit; a.run_iters = run_iters; a.run_conv = run_conv;
     a.mode = 0;
@@ -278,7 +300,8 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
 }
 
 size_t per_pair_ws_bytes(const kss_batch& b, int H, int slots) {
-    size_t v = (size_t)b.cap_s * H * 8 + (size_t)b.cap_s * 30 + (size_t)pad32(b.cap_t) * 18 + (size_t)H * 12 +
+    size_t v = (cg_enabled() ? cg_hdr_words_per_pair() * 4 + cg_arena_entries_per_pair() * 2 + 64 : 0) +
+               (size_t)b.cap_s * H * 8 + (size_t)b.cap_s * 30 + (size_t)pad32(b.cap_t) * 18 + (size_t)H * 12 +
                (size_t)(1 + slots) * 96 + (size_t)b.cap_S * 26 + (size_t)pad32(b.cap_T) * 18 + 8192;
     return v;
 }
@@ -462,7 +485,15 @@ int kss_rotation_sweep(kss_ctx* ctx, const double* src_aligned, int n_s, const d
     r = counts_or_fill(ctx, "cnt_t", nullptr, 1, n_t, &c_t); if (r) return r;
     KL(launch_sort_target(ctx->stream, 1, d_t, c_t, n_t, t_sorted, t_box, t_inv, tpad));
     KL(launch_sort_source(ctx->stream, 1, d_s, c_s, n_s, s_perm));
-    KL(launch_sweep(ctx->stream, 1, d_s, c_s, n_s, s_perm, t_sorted, t_box, c_t, tpad, ctx->d_trig_accum, G, score_mode, rbuf, H));
+    CgBuffers cgb{}; const CgBuffers* cg = nullptr;
+    if (cg_enabled()) {
+        r = cg_buffers(ctx, 1, &cgb); if (r) return r;
+        int nl = 0;
+        CU(launch_cg_build(ctx->stream, 1, 0, d_s, c_s, n_s, nullptr, nullptr, 0, t_sorted, c_t, tpad, cgb, &nl));
+        ctx->launches += nl;
+        cg = &cgb;
+    }
+    KL(launch_sweep(ctx->stream, 1, d_s, c_s, n_s, s_perm, t_sorted, t_box, c_t, tpad, ctx->d_trig_accum, G, score_mode, rbuf, H, cg));
     KL(launch_sweep_finalize(ctx->stream, 1, rbuf, c_s, n_s, H, G, score_mode, d_val, d_best, d_min, d_nmin));
     std::vector<int> hmin(H);
     int hbest = 0, nmin = 0;
@@ -549,6 +580,14 @@ int kss_icp(kss_ctx* ctx, const double* src, int n_s, const double* tgt, int n_t
     a.src_f64 = d_s; a.cnt_s = c_s; a.cap_s = n_s; a.s_perm = s_perm;
     a.t_sorted = t_sorted; a.t_box = t_box; a.t_inv = t_inv; a.cnt_t = c_t; a.cap_t = n_t; a.cap_tpad = tpad;
     a.mode = 2; a.runs_per_pair = 1; a.judge_thr = -1.0;
+    CgBuffers cgb{};
+    if (cg_enabled()) {
+        r = cg_buffers(ctx, 1, &cgb); if (r) return r;
+        int nl = 0;
+        CU(launch_cg_build(ctx->stream, 1, 1, d_s, c_s, n_s, d_t, c_t, n_t, t_sorted, c_t, tpad, cgb, &nl));
+        ctx->launches += nl;
+        a.cg_geom = cgb.geom; a.cg_hdr = cgb.hdr; a.cg_arena = cgb.arena; a.cg_ok = cgb.ok;
+    }
     icp_fill(a, *prm);
     a.run_T = run_T; a.run_fit = run_fit; a.run_iters = run_iters; a.run_conv = run_conv;
     int cap = 0;

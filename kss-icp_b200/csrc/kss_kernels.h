@@ -12,6 +12,14 @@ constexpr int MAX_TILES = SMALL_MAX / TILE;  // 64 -> two tiles per lane
 
 typedef kss_pair_result PairOut;
 
+// candidate grid buffers (kss_cg.cuh): per pair 8 floats of geometry, CG_HDR_TOTAL header words,
+// CG_ARENA u16 list entries, an arena cursor and an ok flag
+struct CgBuffers {
+    float* geom; unsigned* hdr; unsigned short* arena; unsigned* cursor; int* ok;
+};
+size_t cg_hdr_words_per_pair();
+size_t cg_arena_entries_per_pair();
+
 struct IcpArgs {
     // source: original (double) simplified cloud, similarity applied in-kernel (mode 0/1) or used as is (mode 2)
     const double* src_f64; const int* cnt_s; int cap_s;
@@ -24,6 +32,8 @@ struct IcpArgs {
     const int* best_h; const int* minima; const int* n_minima;
     const double* trig_accum; const double* trig_list;
     double judge_thr;         // mode 1 runs only if judge fitness > thr (thr < 0: always)
+    // candidate grid of the pair (null: tile search)
+    const float* cg_geom; const unsigned* cg_hdr; const unsigned short* cg_arena; const int* cg_ok;
     // PCL parameters
     int max_iter; double max_dist_sqr, rot_thr, trans_thr, mse_rel, mse_abs;
     // per-run outputs, run = pair * runs_per_pair + (mode==1 ? 1 + slot : 0)
@@ -43,7 +53,10 @@ cudaError_t launch_middle_align(cudaStream_t st, int P, const double* sim_s, con
 cudaError_t launch_sweep(cudaStream_t st, int P, const double* s_al, const int* cnt_s, int cap_s,
                          const unsigned short* s_perm, const float4* t_sorted, const float* t_box,
                          const int* cnt_t, int cap_tpad, const double* trig_accum, int G, int score_mode,
-                         double* rbuf, int hpad);
+                         double* rbuf, int hpad, const CgBuffers* cg);
+cudaError_t launch_cg_build(cudaStream_t st, int P, int geom_mode, const double* a, const int* cnt_a, int cap_a,
+                            const double* b, const int* cnt_b, int cap_b, const float4* t_sorted, const int* cnt_t,
+                            int cap_tpad, const CgBuffers& cg, int* launches);
 cudaError_t launch_sweep_finalize(cudaStream_t st, int P, const double* rbuf, const int* cnt_s, int cap_s, int hpad,
                                   int G, int score_mode, double* value, int* best_h, int* minima, int* n_minima);
 cudaError_t launch_icp(cudaStream_t st, int P, int slots, const IcpArgs& a);

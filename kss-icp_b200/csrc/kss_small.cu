@@ -11,6 +11,7 @@
 //   metrics_small_kernel   PCR_QM                                   (registrationMeasure.hpp:47-98)
 //   nn_small_kernel        bare exact 1-NN (tests, kss_nn_search)
 #include "kss_device.cuh"
+#include "kss_cg.cuh"
 #include "kss_kernels.h"
 
 namespace kss {
@@ -160,6 +161,181 @@ middle_align_kernel(const double* __restrict__ sim_s, const int* __restrict__ cn
     }
 }
 
+
+// =============================================================== cg_geom_kernel
+// mode 0: queries live in the ball |q| <= R about the origin, R = max |p| over the (aligned) source
+//         (every sweep hypothesis is a rotation about the origin)
+// mode 1: explicit ICP input: cube around the bounding box of source and target
+__global__ void __launch_bounds__(256)
+cg_geom_kernel(int mode, const double* __restrict__ a, const int* __restrict__ cnt_a, int cap_a,
+               const double* __restrict__ b, const int* __restrict__ cnt_b, int cap_b,
+               float* __restrict__ geom, unsigned* __restrict__ cursor, int* __restrict__ ok) {
+    __shared__ unsigned bb[6];
+    __shared__ unsigned long long r2max;
+    const int p = blockIdx.x;
+    if (threadIdx.x < 3) { bb[threadIdx.x] = 0xffffffffu; bb[3 + threadIdx.x] = 0u; }
+    if (threadIdx.x == 0) r2max = 0ull;
+    __syncthreads();
+    double r2 = 0.0;
+    unsigned mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+    for (int which = 0; which < (mode == 1 ? 2 : 1); ++which) {
+        const double* pts = which == 0 ? a + (size_t)p * cap_a * 3 : b + (size_t)p * cap_b * 3;
+        const int n = which == 0 ? cnt_a[p] : cnt_b[p];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+            r2 = fmax(r2, x * x + y * y + z * z);
+            const unsigned ox = f2ord((float)x), oy = f2ord((float)y), oz = f2ord((float)z);
+            mn[0] = min(mn[0], ox); mn[1] = min(mn[1], oy); mn[2] = min(mn[2], oz);
+            mx[0] = max(mx[0], ox); mx[1] = max(mx[1], oy); mx[2] = max(mx[2], oz);
+        }
+    }
+    atomicMax(&r2max, (unsigned long long)__double_as_longlong(r2));       // r2 >= 0: bits order as integers
+    for (int k = 0; k < 3; ++k) { atomicMin(&bb[k], mn[k]); atomicMax(&bb[3 + k], mx[k]); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float* g = geom + (size_t)p * 8;
+        if (mode == 0) {
+            const float R = fmaxf((float)(sqrt(__longlong_as_double((long long)r2max)) * 1.0001), 1e-12f);
+            g[0] = g[1] = g[2] = 0.0f; g[3] = R * 1.1f; g[4] = R * 1.1f;   // 10% slack for ICP excursions
+        } else {
+            float half = 0.0f;
+            for (int k = 0; k < 3; ++k) {
+                const float l = ord2f(bb[k]), hgh = ord2f(bb[3 + k]);
+                g[k] = 0.5f * (l + hgh);
+                half = fmaxf(half, 0.5f * (hgh - l));
+            }
+            g[3] = fmaxf(half * 1.1f, 1e-12f);
+            g[4] = __int_as_float(0x7f800000);
+        }
+        g[5] = g[6] = g[7] = 0.0f;
+        cursor[p] = 0u;
+        ok[p] = 1;
+    }
+}
+
+// =============================================================== cg_level_kernel
+// Builds one level of the candidate grid (kss_cg.cuh).  One thread per child cell; the 8 children
+// of a parent sit in adjacent lanes, so parent-list and target reads are broadcasts (4 distinct
+// addresses per warp).  Pass A: p_c = the centre's nearest target, d_c^2.  Pass B: keep p iff
+// d2 <= ((d_c + 2 rho)(1+1e-4))^2 and p_c does not dominate p over the whole cell; remembered as a bit mask (lists <= 64) so pass C only re-reads
+// indices.  Space: one atomicAdd per warp on the pair's arena cursor (list order never matters).
+__global__ void __launch_bounds__(256)
+cg_level_kernel(int level, const float4* __restrict__ t_sorted, const int* __restrict__ cnt_t, int cap_tpad,
+                const float* __restrict__ geom, unsigned* __restrict__ hdr_all,
+                unsigned short* __restrict__ arena_all, unsigned* __restrict__ cursor, int* __restrict__ ok) {
+    const int p = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int ng = cg_ng(level);
+    const int png = ng >> 1;
+    const int ncells = ng * ng * ng;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;        // = parent * 8 + child
+    if (tid - lane >= ncells) return;                              // whole warp out of range
+    const bool live = tid < ncells;
+    const int n_t = cnt_t[p];
+    const float4* __restrict__ tgt = t_sorted + (size_t)p * cap_tpad;
+    unsigned* hdr = hdr_all + (size_t)p * CG_HDR_TOTAL + cg_hdr_base(level);
+    unsigned short* arena = arena_all + (size_t)p * CG_ARENA;
+    const float* gm = geom + (size_t)p * 8;
+    const float R = gm[3], ballR = gm[4];
+    const float h = 2.0f * R / (float)ng;
+    const float rho = h * 0.8660254f * 1.002f;
+    const int child = tid & 7, parent = tid >> 3;
+
+    int ix = 0, iy = 0, iz = 0, m_p = 0;
+    const unsigned short* plist = nullptr;
+    if (live) {
+        if (level == 0) {
+            ix = tid & 3; iy = (tid >> 2) & 3; iz = tid >> 4;
+            m_p = n_t;
+        } else {
+            const int px = parent % png, py = (parent / png) % png, pz = parent / (png * png);
+            ix = 2 * px + (child & 1); iy = 2 * py + ((child >> 1) & 1); iz = 2 * pz + (child >> 2);
+            const unsigned ph = (hdr_all + (size_t)p * CG_HDR_TOTAL + cg_hdr_base(level - 1))[parent];
+            m_p = (int)(ph & CG_CNT_MASK);
+            plist = arena + ((size_t)(ph >> CG_CNT_BITS) << 2);
+            if (m_p == (int)CG_CNT_MASK) { m_p = n_t; plist = nullptr; }      // over-long parent: all points
+        }
+    }
+    const int cell = ix + ng * (iy + ng * iz);
+    const float ox = -R + ((float)ix + 0.5f) * h, oy = -R + ((float)iy + 0.5f) * h, oz = -R + ((float)iz + 0.5f) * h;
+    const float cx = gm[0] + ox, cy = gm[1] + oy, cz = gm[2] + oz;
+    const float rr = ballR + rho;
+    const bool inball = ox * ox + oy * oy + oz * oz <= rr * rr;
+    if (!inball) m_p = 0;                                                  // outside the query ball: empty list
+
+    // ---- pass A: the centre's nearest target p_c and its squared distance
+    float mn = __int_as_float(0x7f800000);
+    int amin = 0;
+    for (int j = 0; j < m_p; ++j) {
+        const int id = plist ? (int)plist[j] : j;
+        const float4 q = __ldg(tgt + id);
+        const float d = d2_rn(cx, cy, cz, q.x, q.y, q.z);
+        if (d < mn) { mn = d; amin = id; }
+    }
+    const float thr = (sqrtf(mn) + 2.0f * rho) * 1.0001f;
+    const float thr2 = thr * thr;
+    // dominance test against p_c: g(x) = |x-p|^2 - |x-p_c|^2 is linear in x, so its minimum over the
+    // cell is g(c) - h * (|dx|+|dy|+|dz|), d = p - p_c.  If that is > 0 (with a margin far above fp32
+    // rounding of any query's two distances) p_c beats p everywhere in the cell: p can never be a
+    // nearest neighbour of a query in this cell, nor tie with one.
+    const float4 pc = __ldg(tgt + amin);
+    const float hh = h * 1.002f * 1.0001f;
+    const float marg0 = 1e-5f * (mn + 4.0f * rho * rho);
+    auto keep_test = [&](const float4& q, float d) -> bool {
+        if (!(d <= thr2)) return false;
+        const float s = fabsf(q.x - pc.x) + fabsf(q.y - pc.y) + fabsf(q.z - pc.z);
+        return !((d - mn) - hh * s > marg0 + 1e-5f * d);
+    };
+    // ---- pass B: count (and remember) the candidates
+    unsigned long long mask = 0ull;
+    int k = 0, first = 0;
+    for (int j = 0; j < m_p; ++j) {
+        const int id = plist ? (int)plist[j] : j;
+        const float4 q = __ldg(tgt + id);
+        if (keep_test(q, d2_rn(cx, cy, cz, q.x, q.y, q.z))) {
+            if (j < 64) mask |= 1ull << j;
+            if (k == 0) first = id;
+            ++k;
+        }
+    }
+    const bool huge = k >= (int)CG_CNT_MASK;
+    const int tot4 = huge ? 0 : ((k + 3) & ~3);
+    // warp exclusive scan of tot4, one atomicAdd per warp
+    int incl = tot4;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(KSS_FULL, incl, o); if (lane >= o) incl += y; }
+    const int wtot = __shfl_sync(KSS_FULL, incl, 31);
+    unsigned base = 0;
+    if (lane == 0 && wtot > 0) base = atomicAdd(&cursor[p], (unsigned)wtot);
+    base = __shfl_sync(KSS_FULL, base, 0);
+    if ((size_t)base + (size_t)wtot > CG_ARENA) {                         // arena exhausted: pair falls back
+        if (lane == 0) atomicExch(&ok[p], 0);
+        if (live) hdr[cell] = 0u;
+        return;
+    }
+    if (!live) return;
+    const unsigned off = base + (unsigned)(incl - tot4);
+    hdr[cell] = huge ? CG_CNT_MASK : (k == 0 ? 0u : (((off >> 2) << CG_CNT_BITS) | (unsigned)k));
+    if (huge || k == 0) return;
+    // ---- pass C: write the list, padded to a multiple of 4 with a valid candidate
+    unsigned short* out = arena + off;
+    int w = 0;
+    if (m_p <= 64) {
+        while (mask) {
+            const int j = __ffsll((long long)mask) - 1;
+            mask &= mask - 1ull;
+            out[w++] = (unsigned short)(plist ? (int)plist[j] : j);
+        }
+    } else {
+        for (int j = 0; j < m_p; ++j) {
+            const int id = plist ? (int)plist[j] : j;
+            const float4 q = __ldg(tgt + id);
+            if (keep_test(q, d2_rn(cx, cy, cz, q.x, q.y, q.z))) out[w++] = (unsigned short)id;
+        }
+    }
+    for (; w < tot4; ++w) out[w] = (unsigned short)first;
+}
+
 // =============================================================== sweep_kernel
 // grid (G*G, P): CTA (i,j) of pair p applies Rx(i), Ry(j) once per point and loops Rz(k),
 // searching the exact NN of every rotated point (narrowed to float) in the Morton-tiled
@@ -171,7 +347,9 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
              const float4* __restrict__ t_sorted, const float* __restrict__ t_box,
              const int* __restrict__ cnt_t, int cap_tpad,
              const double* __restrict__ trig_accum /* [G][2] cos,sin */, int G, int score_mode,
-             double* __restrict__ rbuf, int hpad) {
+             double* __restrict__ rbuf, int hpad,
+             const float* __restrict__ cg_geom, const unsigned* __restrict__ cg_hdr,
+             const unsigned short* __restrict__ cg_arena, const int* __restrict__ cg_ok) {
     extern __shared__ unsigned char smem_raw[];
     float4* tgt = reinterpret_cast<float4*>(smem_raw);
     const int p = blockIdx.y;
@@ -184,6 +362,9 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
     for (int j = threadIdx.x; j < 6 * MAX_TILES; j += blockDim.x) box[j] = gtb[j];
     __syncthreads();
     TileView tv{tgt, box, npad / TILE};
+    const bool use_cg = cg_hdr != nullptr && cg_ok[p] != 0;
+    CgView cg{};
+    if (use_cg) cg = cg_view(cg_geom, cg_hdr, cg_arena, cg_ok, p);
 
     const int gi = blockIdx.x / G, gj = blockIdx.x % G;
     const double ci = trig_accum[2 * gi], si = trig_accum[2 * gi + 1];
@@ -208,7 +389,8 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
             double xx = x, yy = y;
             rot_z(ck, sk, xx, yy);
             const float qx = (float)xx, qy = (float)yy, qz = (float)z;   // :440-442 narrowing
-            const unsigned long long key = warp_nn<false>(tv, qx, qy, qz);
+            const unsigned long long key = use_cg ? cg_query<false>(cg, tgt, n_t, qx, qy, qz)
+                                                  : warp_nn<false>(tv, qx, qy, qz);
             const float d2 = __uint_as_float((unsigned)(key >> 32));
             const double r = score_mode == 1 ? (double)d2 : __dsqrt_rn((double)d2);
             if (valid) ro[k] = r;
@@ -309,7 +491,7 @@ sweep_finalize_kernel(const double* __restrict__ rbuf, const int* __restrict__ c
 // mode 0: judge run      -> angles = accumulated loop values of best_h      (KSS_ICP.hpp:92-93)
 // mode 1: hypothesis l   -> angles = index*6.3/step of minima[l], only if judge fitness > thr
 // mode 2: explicit input -> src_f64 is used as is (kss_icp API, KSS_ICP.hpp:323-356)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 icp_small_kernel(IcpArgs a) {
     extern __shared__ unsigned char smem_raw[];
     const int p = blockIdx.y;
@@ -359,6 +541,9 @@ icp_small_kernel(IcpArgs a) {
     if (threadIdx.x == 0) { kept = 0; done = 0; prev_mse = DBL_MAX; }
     __syncthreads();
     TileView tv{tgt, box, npad / TILE};
+    const bool use_cg = a.cg_hdr != nullptr && a.cg_ok[p] != 0;
+    CgView cg{};
+    if (use_cg) cg = cg_view(a.cg_geom, a.cg_hdr, a.cg_arena, a.cg_ok, p);
 
     const double* src = a.src_f64 + (size_t)p * a.cap_s * 3;
     const double* a8 = a.align8 ? a.align8 + (size_t)p * 8 : nullptr;
@@ -391,7 +576,7 @@ icp_small_kernel(IcpArgs a) {
             else { xform_point(Tk, cur[o], cur[n_s + o], cur[2 * n_s + o], x, y, z); }
             __syncwarp();
             if (valid) { cur[o] = x; cur[n_s + o] = y; cur[2 * n_s + o] = z; }
-            const unsigned long long key = warp_nn<true>(tv, x, y, z);
+            const unsigned long long key = use_cg ? cg_query<true>(cg, tgt, n_t, x, y, z) : warp_nn<true>(tv, x, y, z);
             const float d2 = __uint_as_float((unsigned)(key >> 32));
             const unsigned orig = (unsigned)(key & 0xffffffffu);
             const bool keep = !((double)d2 > a.max_dist_sqr);        // A.3: skip iff d2 > max_dist^2
@@ -487,7 +672,7 @@ icp_small_kernel(IcpArgs a) {
         float x, y, z, fx, fy, fz;
         input_point(o, x, y, z);
         xform_point(fin, x, y, z, fx, fy, fz);
-        const unsigned long long key = warp_nn<false>(tv, fx, fy, fz);
+        const unsigned long long key = use_cg ? cg_query<false>(cg, tgt, n_t, fx, fy, fz) : warp_nn<false>(tv, fx, fy, fz);
         if (valid) d2s[o] = __uint_as_float((unsigned)(key >> 32));
     }
     __syncthreads();
@@ -703,14 +888,34 @@ cudaError_t launch_middle_align(cudaStream_t st, int P, const double* sim_s, con
 cudaError_t launch_sweep(cudaStream_t st, int P, const double* s_al, const int* cnt_s, int cap_s,
                          const unsigned short* s_perm, const float4* t_sorted, const float* t_box,
                          const int* cnt_t, int cap_tpad, const double* trig_accum, int G, int score_mode,
-                         double* rbuf, int hpad) {
+                         double* rbuf, int hpad, const CgBuffers* cg) {
     const size_t smem = (size_t)cap_tpad * sizeof(float4) + 6 * MAX_TILES * sizeof(float);
     static size_t set = 0;
     if (smem > set) { cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
     sweep_kernel<<<dim3(G * G, P), 256, smem, st>>>(s_al, cnt_s, cap_s, s_perm, t_sorted, t_box, cnt_t, cap_tpad,
-                                                   trig_accum, G, score_mode, rbuf, hpad);
+                                                   trig_accum, G, score_mode, rbuf, hpad,
+                                                   cg ? cg->geom : nullptr, cg ? cg->hdr : nullptr,
+                                                   cg ? cg->arena : nullptr, cg ? cg->ok : nullptr);
     return cudaGetLastError();
 }
+// candidate grid: geometry, then one launch per level (a level reads the previous one)
+cudaError_t launch_cg_build(cudaStream_t st, int P, int geom_mode, const double* a, const int* cnt_a, int cap_a,
+                            const double* b, const int* cnt_b, int cap_b, const float4* t_sorted, const int* cnt_t,
+                            int cap_tpad, const CgBuffers& cg, int* launches) {
+    cg_geom_kernel<<<P, 256, 0, st>>>(geom_mode, a, cnt_a, cap_a, b, cnt_b, cap_b, cg.geom, cg.cursor, cg.ok);
+    int n = 1;
+    for (int l = 0; l < CG_LEVELS; ++l) {
+        const int ncells = cg_ng(l) * cg_ng(l) * cg_ng(l);
+        cg_level_kernel<<<dim3((ncells + 255) / 256, P), 256, 0, st>>>(l, t_sorted, cnt_t, cap_tpad, cg.geom, cg.hdr, cg.arena,
+                                                                  cg.cursor, cg.ok);
+        ++n;
+    }
+    if (launches) *launches = n;
+    return cudaGetLastError();
+}
+size_t cg_hdr_words_per_pair() { return CG_HDR_TOTAL; }
+size_t cg_arena_entries_per_pair() { return CG_ARENA; }
+
 cudaError_t launch_sweep_finalize(cudaStream_t st, int P, const double* rbuf, const int* cnt_s, int cap_s, int hpad,
                                   int G, int score_mode, double* value, int* best_h, int* minima, int* n_minima) {
     const int H = G * G * G;
