@@ -523,6 +523,8 @@ icp_small_kernel(IcpArgs a) {
     unsigned short* tinv = mpos + n_s;                // [n_t] original target index -> Morton position
     __shared__ float red[16];
     __shared__ double redd;
+    __shared__ float partF[8 * 16];
+    __shared__ double partD[8];
     __shared__ float Tk[16], fin[16];
     __shared__ int kept, done;
     __shared__ double prev_mse;
@@ -597,41 +599,88 @@ icp_small_kernel(IcpArgs a) {
         __syncthreads();
         const int cnt = kept;
         if (cnt < 3) { converged = 0; break; }                       // min_number_correspondences_
-        // ---- (2) pass A: sums of kept source / matched target coordinates, and of d2 (double)
-        for (int q = warp; q < 7; q += nwarps) {
-            if (q < 3) {
-                const float* c = cur + q * n_s;
-                float s = canon_sum_warp_f32(n_s, [&](int i, float& v) { if (mpos[i] == 0xffff) return false; v = c[i]; return true; });
-                if (lane == 0) red[q] = s;
-            } else if (q < 6) {
-                const int ax = q - 3;
-                float s = canon_sum_warp_f32(n_s, [&](int i, float& v) {
-                    const unsigned m = mpos[i]; if (m == 0xffff) return false;
-                    const float4 t = tgt[m]; v = ax == 0 ? t.x : (ax == 1 ? t.y : t.z); return true; });
-                if (lane == 0) red[q] = s;
-            } else {
-                double s = canon_sum_warp_f64(n_s, [&](int i, double& v) { if (mpos[i] == 0xffff) return false; v = (double)d2s[i]; return true; });
-                if (lane == 0) redd = s;
+        // ---- (2) pass A, level 1: one warp per 256-slot chunk sums kept source xyz, matched target
+        //      xyz (float) and d2 (double) in the CANON256 order (lane-strided, then butterfly)
+        const int nc = (n_s + 255) >> 8;
+        for (int c = warp; c < nc; c += nwarps) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f;
+            double dd = 0.0;
+            const int hi = min(n_s, (c + 1) << 8);
+            for (int i = (c << 8) + lane; i < hi; i += 32) {
+                const unsigned m = mpos[i];
+                if (m == 0xffff) continue;
+                const float4 t = tgt[m];
+                s0 = add_(s0, cur[i]); s1 = add_(s1, cur[n_s + i]); s2 = add_(s2, cur[2 * n_s + i]);
+                t0 = add_(t0, t.x); t1 = add_(t1, t.y); t2 = add_(t2, t.z);
+                dd = __dadd_rn(dd, (double)d2s[i]);
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                s0 = add_(s0, __shfl_xor_sync(KSS_FULL, s0, off)); s1 = add_(s1, __shfl_xor_sync(KSS_FULL, s1, off));
+                s2 = add_(s2, __shfl_xor_sync(KSS_FULL, s2, off)); t0 = add_(t0, __shfl_xor_sync(KSS_FULL, t0, off));
+                t1 = add_(t1, __shfl_xor_sync(KSS_FULL, t1, off)); t2 = add_(t2, __shfl_xor_sync(KSS_FULL, t2, off));
+                dd = __dadd_rn(dd, __shfl_xor_sync(KSS_FULL, dd, off));
+            }
+            if (lane == 0) {
+                float* pf = partF + c * 16;
+                pf[0] = s0; pf[1] = s1; pf[2] = s2; pf[3] = t0; pf[4] = t1; pf[5] = t2;
+                partD[c] = dd;
             }
         }
         __syncthreads();
+        // level 2 (every warp redundantly, identical arithmetic): chunk results by the same rule
+        auto lvl2f = [&](int q) -> float {
+            if (nc == 1) return partF[q];
+            float v = lane < nc ? add_(0.0f, partF[lane * 16 + q]) : 0.0f;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) v = add_(v, __shfl_xor_sync(KSS_FULL, v, off));
+            return v;
+        };
         const float one_over_n = div_(1.0f, (float)cnt);
-        const float sm0 = mul_(red[0], one_over_n), sm1 = mul_(red[1], one_over_n), sm2 = mul_(red[2], one_over_n);
-        const float dm0 = mul_(red[3], one_over_n), dm1 = mul_(red[4], one_over_n), dm2 = mul_(red[5], one_over_n);
-        // ---- (3) pass B: sigma(a,b) = one_over_n * sum (d_a - dmean_a) * (s_b - smean_b)
-        for (int q = warp; q < 9; q += nwarps) {
-            const int ra = q / 3, cb = q % 3;
-            const float dmean = ra == 0 ? dm0 : (ra == 1 ? dm1 : dm2);
-            const float smean = cb == 0 ? sm0 : (cb == 1 ? sm1 : sm2);
-            const float* c = cur + cb * n_s;
-            float s = canon_sum_warp_f32(n_s, [&](int i, float& v) {
-                const unsigned m = mpos[i]; if (m == 0xffff) return false;
+        const float sm0 = mul_(lvl2f(0), one_over_n), sm1 = mul_(lvl2f(1), one_over_n), sm2 = mul_(lvl2f(2), one_over_n);
+        const float dm0 = mul_(lvl2f(3), one_over_n), dm1 = mul_(lvl2f(4), one_over_n), dm2 = mul_(lvl2f(5), one_over_n);
+        double dsum;
+        if (nc == 1) dsum = partD[0];
+        else {
+            dsum = lane < nc ? __dadd_rn(0.0, partD[lane]) : 0.0;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) dsum = __dadd_rn(dsum, __shfl_xor_sync(KSS_FULL, dsum, off));
+        }
+        __syncthreads();                                   // partF is reused by pass B
+        // ---- (3) pass B, level 1: sigma(a,b) partials = sum (d_a - dmean_a) * (s_b - smean_b)
+        for (int c = warp; c < nc; c += nwarps) {
+            float v[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int hi = min(n_s, (c + 1) << 8);
+            for (int i = (c << 8) + lane; i < hi; i += 32) {
+                const unsigned m = mpos[i];
+                if (m == 0xffff) continue;
                 const float4 t = tgt[m];
-                const float dv = ra == 0 ? t.x : (ra == 1 ? t.y : t.z);
-                v = mul_(sub_(dv, dmean), sub_(c[i], smean)); return true; });
-            if (lane == 0) red[7 + q] = mul_(one_over_n, s);
+                const float sx = sub_(cur[i], sm0), sy = sub_(cur[n_s + i], sm1), sz = sub_(cur[2 * n_s + i], sm2);
+                const float dx = sub_(t.x, dm0), dy = sub_(t.y, dm1), dz = sub_(t.z, dm2);
+                v[0] = add_(v[0], mul_(dx, sx)); v[1] = add_(v[1], mul_(dx, sy)); v[2] = add_(v[2], mul_(dx, sz));
+                v[3] = add_(v[3], mul_(dy, sx)); v[4] = add_(v[4], mul_(dy, sy)); v[5] = add_(v[5], mul_(dy, sz));
+                v[6] = add_(v[6], mul_(dz, sx)); v[7] = add_(v[7], mul_(dz, sy)); v[8] = add_(v[8], mul_(dz, sz));
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+                for (int q = 0; q < 9; ++q) v[q] = add_(v[q], __shfl_xor_sync(KSS_FULL, v[q], off));
+            if (lane == 0)
+#pragma unroll
+                for (int q = 0; q < 9; ++q) partF[c * 16 + q] = v[q];
         }
         __syncthreads();
+        if (warp == 0) {
+            float sg[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) sg[q] = mul_(one_over_n, lvl2f(q));
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) red[7 + q] = sg[q];
+                redd = dsum;
+            }
+        }
+        __syncwarp();
         // ---- (4) one thread: SVD/Kabsch, accumulate, convergence
         if (threadIdx.x == 0) {
             float sigma[9], smean[3] = {sm0, sm1, sm2}, dmean[3] = {dm0, dm1, dm2}, T[16];
