@@ -254,4 +254,4 @@ def exported_symbols():
     return sorted(set(re.findall(r"\b(kss_[a-z0-9_]+)\s*\(", txt)))
 
 
-from . import synth  # noqa: E402,F401  (synthetic clouds for tests and bench)
+from . import synth, dist  # noqa: E402,F401  (synthetic clouds; multi-GPU host logic)

@@ -119,7 +119,7 @@ __device__ __forceinline__ unsigned long long warp_nn(const TileView& tv, float 
 }
 
 // ---------------------------------------------------------------- canonical reductions (CANON256)
-// Order contract shared with the oracle (oracle/kss_oracle.cpp sum_canon): per 256-element
+// Order contract (DESIGN.md "reduction order contract", also implemented by the CPU checker): per 256-element
 // chunk, lane l accumulates elements i = l (mod 32) in increasing i starting from +0, then an
 // xor butterfly 16,8,4,2,1; chunk results are reduced by the same rule.  One warp runs one
 // reduction; n <= 8192 here (two levels).  get(i, v) returns false for masked slots.

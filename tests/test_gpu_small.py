@@ -218,3 +218,24 @@ def test_bad_arguments(ctx, pkg):
         ctx.rotation_sweep(np.zeros((3000, 3)), np.zeros((10, 3)))
     with pytest.raises(pkg.KssError):
         ctx.middle_align(np.zeros((0, 3)), np.zeros((10, 3)))
+
+
+@pytest.mark.parametrize("model", ["Bunny", "Horse", "Dog"])
+def test_golden_fixtures_from_reference_data(ctx, pkg, model):
+    """the reference's own shipped pairs (data/registration/*.wlop|.gird, decimated; see
+    tests/golden/make_golden.py) against the committed golden vectors: no oracle at run time"""
+    import os
+    gd = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gd, "golden_oracle.npz")); fx = np.load(os.path.join(gd, "fixtures_pairs.npz"))
+    s = fx[model + "_src"].astype(np.float64); t = fx[model + "_tgt"].astype(np.float64)
+    a7, al = ctx.middle_align(s, t)
+    assert np.array_equal(a7, g[model + "_align7"])
+    sw = ctx.rotation_sweep(al, t, 8.0)
+    assert np.array_equal(sw["value"], g[model + "_value"])
+    assert np.array_equal(sw["minima"], g[model + "_minima"])
+    r = ctx.register(s, t, s, t)
+    assert int(r["winner"]) == int(g[model + "_canon_winner"])
+    assert np.array_equal(np.asarray(r["T"]).reshape(4, 4), g[model + "_canon_T"])
+    assert float(r["final_fitness"]) == float(g[model + "_canon_final_fitness"])
+    assert float(r["rmse"]) == float(g[model + "_canon_rmse"]) and float(r["mae"]) == float(g[model + "_canon_mae"])
+    assert int(r["total_icp_iters"]) == int(g[model + "_canon_total_icp_iters"])
