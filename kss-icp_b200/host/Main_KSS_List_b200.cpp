@@ -1,0 +1,71 @@
+// Main_KSS_List_b200.cpp -- batch driver: the loop body of the reference's Main_KSS_List.cpp:133-166
+// (load pair, KSSICP_init, KSSICP_Registration, PCR_QM, record the time) for a list of pairs, but handing the
+// whole list to ONE kss_register_batch call so the GPU sees every pair at once.  The reference file itself is
+// an empty translation unit as shipped (its body is inside a comment and its list is empty), so it cannot be
+// "driven unchanged"; this is the equivalent driver.
+//
+// usage: Main_KSS_List_b200 <list.txt> [step=8] [iter=1000]     list.txt: one "<source.ply> <target.ply>" per line
+#include <chrono>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "KSS_ICP.hpp"
+#include "registrationMeasure.hpp"
+
+static std::vector<std::vector<double>> Load_PLY(const std::string& f) {
+	CPLYLoader l;
+	std::vector<char> p(f.begin(), f.end()); p.push_back(0);
+	l.LoadModel(p.data());
+	return l.points;
+}
+
+int main(int argc, char** argv) {
+	if (argc < 2) { std::cerr << "usage: " << argv[0] << " <list.txt> [step] [iter]\n"; return 2; }
+	const double step = argc > 2 ? std::atof(argv[2]) : 8.0;
+	const int iter = argc > 3 ? std::atoi(argv[3]) : 1000;
+	std::ifstream lf(argv[1]);
+	std::string line;
+	std::vector<kss_host::Cloud> S, T, simS, simT;
+	while (std::getline(lf, line)) {
+		std::istringstream ls(line);
+		std::string a, b;
+		if (!(ls >> a >> b)) continue;
+		kss_host::Cloud s = Load_PLY(a), t = Load_PLY(b);
+		if (s.empty() || t.empty()) { std::cerr << "skip " << line << "\n"; continue; }
+		int pNumber = (int)std::min(s.size(), t.size()) / 2;                     // KSS_ICP.hpp:57-66
+		if (pNumber > 2000) pNumber = 2000;
+		pointPipeline pp; AIVS_Simplification_Pro as;
+		pp.pointPipeline_init_point_withoutUniform(t); as.AIVS_Pro_init(pp.br, "target"); simT.push_back(as.AIVS_simplification(pNumber));
+		pp.pointPipeline_init_point_withoutUniform(s); as.AIVS_Pro_init(pp.br, "source"); simS.push_back(as.AIVS_simplification(pNumber));
+		S.push_back(s); T.push_back(t);
+	}
+	const int P = (int)S.size();
+	if (P == 0) { std::cerr << "no pairs\n"; return 1; }
+	size_t cs = 0, ct = 0, cS = 0, cT = 0;
+	for (int p = 0; p < P; ++p) { cs = std::max(cs, simS[p].size()); ct = std::max(ct, simT[p].size()); cS = std::max(cS, S[p].size()); cT = std::max(cT, T[p].size()); }
+	std::vector<double> bs(P * cs * 3), bt(P * ct * 3), bS(P * cS * 3), bT(P * cT * 3);
+	std::vector<int> ns(P), nt(P), nS(P), nT(P);
+	auto put = [](std::vector<double>& dst, size_t cap, int p, const kss_host::Cloud& c) {
+		for (size_t i = 0; i < c.size(); ++i) for (int a = 0; a < 3; ++a) dst[((size_t)p * cap + i) * 3 + a] = c[i][a];
+	};
+	for (int p = 0; p < P; ++p) {
+		put(bs, cs, p, simS[p]); put(bt, ct, p, simT[p]); put(bS, cS, p, S[p]); put(bT, cT, p, T[p]);
+		ns[p] = (int)simS[p].size(); nt[p] = (int)simT[p].size(); nS[p] = (int)S[p].size(); nT[p] = (int)T[p].size();
+	}
+	kss_batch b;
+	kss_batch_default(&b);
+	b.n_pairs = P; b.cap_s = (int)cs; b.cap_t = (int)ct; b.cap_S = (int)cS; b.cap_T = (int)cT;
+	b.sim_s = bs.data(); b.sim_t = bt.data(); b.full_s = bS.data(); b.full_t = bT.data();
+	b.cnt_s = ns.data(); b.cnt_t = nt.data(); b.cnt_S = nS.data(); b.cnt_T = nT.data();
+	b.step = step; b.icp.max_iterations = iter;
+	std::vector<kss_pair_result> res(P);
+	auto t0 = std::chrono::steady_clock::now();
+	if (!kss_host::ok(kss_register_batch(kss_host::ctx(), &b, res.data(), nullptr), "kss_register_batch")) return 1;
+	const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	for (int p = 0; p < P; ++p)
+		std::cout << "pair " << p << " MSE: " << res[p].mse << " RMSE: " << res[p].rmse << " MAE: " << res[p].mae
+		          << " fitness: " << res[p].final_fitness << " hypotheses: " << res[p].n_minima << " winner: " << res[p].winner << "\n";
+	std::cout << P << " registrations in " << sec << " s (" << P / sec << " registrations/s, host buffers in and out)\n";
+	return 0;
+}

@@ -1,0 +1,71 @@
+"""The reference's UNMODIFIED Main_KSS_ICP.cpp (compiled by kss-icp_b200/host/Makefile against this repo's
+same-named KSS_ICP.hpp / initRegistrationKSS.hpp / registrationMeasure.hpp) and the batch driver, run as
+real executables on the GPU and checked against the Python binding of the same C ABI."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "kss-icp_b200", "host", "build")
+
+
+def _write_ply(path, pts):
+    with open(path, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+                "element face 0\nproperty list uchar int vertex_indices\nend_header\n" % len(pts))
+        for p in pts:
+            f.write("%.9g %.9g %.9g\n" % (np.float32(p[0]), np.float32(p[1]), np.float32(p[2])))
+
+
+def _stride(c, n):
+    N = len(c)
+    return c if n >= N else c[(np.arange(n) * N) // n]
+
+
+def _expected(ctx, s, t):
+    pn = min(min(len(s), len(t)) // 2, 2000)
+    return ctx.register(_stride(s, pn), _stride(t, pn), s, t)
+
+
+def test_unmodified_reference_main(ctx, pkg, tmp_path):
+    exe = os.path.join(BIN, "Main_KSS_ICP")
+    if not os.path.exists(exe):
+        pytest.skip("Main_KSS_ICP was not built (reference tree absent at build time)")
+    p = pkg.synth.modelnet_pair(61, n_full=1500)
+    d = tmp_path / "E:" / "chen_database" / "_Registration" / "_MiddleResult"     # Main_KSS_ICP.cpp:67-71
+    d.mkdir(parents=True)
+    _write_ply(d / "centuarPart.ply", p["full_s"]); _write_ply(d / "centuar.ply", p["full_t"])
+    out = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    m = re.search(r"Registration Measure:MSE: (\S+) RMSE: (\S+) MAE: (\S+)", out.stdout)
+    assert m, out.stdout[-2000:]
+    exp = _expected(ctx, p["full_s"], p["full_t"])
+    got = [float(x) for x in m.groups()]
+    assert np.allclose(got, [exp["mse"], exp["rmse"], exp["mae"]], rtol=2e-5)       # 6 significant digits printed
+    xyz = (d / "Registration.xyz").read_text().split()
+    assert int(xyz[0]) == 1500 and len(xyz) == 1 + 3 * 1500                        # save_PointCloud (Main_KSS_ICP.cpp:49-59)
+
+
+def test_batch_driver(ctx, pkg, tmp_path):
+    exe = os.path.join(BIN, "Main_KSS_List_b200")
+    if not os.path.exists(exe):
+        pytest.skip("batch driver not built")
+    lines, exp = [], []
+    for i, n in enumerate((700, 1100, 400)):
+        p = pkg.synth.modelnet_pair(70 + i, n_full=n)
+        a, b = tmp_path / ("s%d.ply" % i), tmp_path / ("t%d.ply" % i)
+        _write_ply(a, p["full_s"]); _write_ply(b, p["full_t"])
+        lines.append("%s %s" % (a, b))
+        exp.append(_expected(ctx, p["full_s"], p["full_t"]))
+    (tmp_path / "list.txt").write_text("\n".join(lines) + "\n")
+    out = subprocess.run([exe, str(tmp_path / "list.txt")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rows = re.findall(r"pair (\d+) MSE: (\S+) RMSE: (\S+) MAE: (\S+) fitness: (\S+) hypotheses: (\d+) winner: (-?\d+)", out.stdout)
+    assert len(rows) == 3
+    for r, e in zip(rows, exp):
+        assert np.allclose([float(r[1]), float(r[2]), float(r[3])], [e["mse"], e["rmse"], e["mae"]], rtol=2e-5)
+        assert int(r[5]) == int(e["n_minima"]) and int(r[6]) == int(e["winner"])
