@@ -13,6 +13,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
 #include <vector>
 
 #include "kss_device.cuh"
@@ -180,6 +183,265 @@ lg_up_box_kernel(const float* __restrict__ cbox, int ccnt, int cpad, int pcnt, i
     }
 }
 
+// ------------------------------------------------------------------ large candidate grid (LCG)
+// The idea of kss_cg.cuh carried to clouds of any size: a DENSE grid over the target's bounding box
+// (power-of-two cells per axis, anisotropic, ~32 cells per target point, <= 2^26) whose every cell lists
+// ALL targets that can be the nearest neighbour of ANY query inside it (sphere rule + dominance rule,
+// same rigorous margins).  Built coarse-to-fine from a single root cell; a cell is handled by a group
+// of GS threads (256 / 32 / 1) chosen per level from the mean parent-list length.  Queries then cost
+// one header read plus a handful of candidate distances per THREAD (no warp cooperation); queries
+// outside the box fall back to the box pyramid for their whole warp.
+struct LcgGeom {
+    float lo[3], h[3], inv_h[3];     // finest level: cell = floor((q - lo) * inv_h)
+    int bits[3];                     // finest level: 2^bits cells per axis
+    int levels;                      // level 0 = root ... levels-1 = finest
+};
+struct LcgView {
+    const unsigned long long* hdr;   // finest level headers: far flag | count << 40 | offset
+    const float4* arena4;            // finest-level lists: the candidate points themselves, .w = bits(original index)
+    const unsigned* arena;           // u32 lists of unrefined far cells inherited from coarser levels
+    const float4* tgt;               // targets by original index (for the u32 lists)
+    LcgGeom g;
+    int ok;
+};
+__host__ __device__ inline int lcg_bits(const LcgGeom& g, int level, int a) {
+    const int L = g.levels - 1;
+    const int b = g.bits[a] - (L - level);
+    return b > 0 ? b : 0;
+}
+
+struct LcgLevelArgs {
+    int level;
+    int bits[3], pbits[3];           // this level / parent level bits per axis
+    float lo[3], h[3];               // this level: cell sizes
+    const float4* tgt; int n_t;
+    const unsigned long long* hdr_prev; unsigned long long* hdr_cur;
+    unsigned* arena; unsigned long long* cursor; unsigned long long cap;   // scratch region of this level: cursor[0] < cap
+    unsigned long long cap_persist;                                       // persistent region: cursor[1] < cap_persist
+    int persist_all;                                                      // finest level: everything is persistent ...
+    float4* arena4;                                                       // ... and stored as float4 {x,y,z,bits(orig)} here (offsets in float4 units)
+    int* ok;
+};
+
+// header: bit 63 = "far" (centre more than 3 half-diagonals from every target; a far cell with a short list is
+// not refined, its descendants inherit the header), bit 62 = list is u32 indices (else float4 points),
+// bits 61:36 = count, bits 35:0 = offset (multiple of 4) into the respective arena.
+// Lists are padded to a multiple of 4 entries with a repeated valid candidate.
+constexpr unsigned long long LCG_FAR = 1ull << 63;
+constexpr unsigned long long LCG_IDX = 1ull << 62;     // list holds u32 indices in `arena` (all intermediate levels)
+__host__ __device__ inline int lcg_count(unsigned long long h) { return (int)((h >> 36) & 0x3ffffffull); }
+__host__ __device__ inline unsigned long long lcg_offset(unsigned long long h) { return h & 0xfffffffffull; }
+__host__ __device__ inline unsigned long long lcg_make(bool far, bool idx, unsigned long long cnt, unsigned long long off) {
+    return (far ? LCG_FAR : 0ull) | (idx ? LCG_IDX : 0ull) | (cnt << 36) | off;
+}
+
+template <int GS>
+__global__ void __launch_bounds__(256)
+lcg_level_kernel(LcgLevelArgs a) {
+    __shared__ unsigned long long s_key[8];
+    __shared__ unsigned s_cnt[8];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long cell = gtid / GS;
+    const int r = (int)(gtid % GS);
+    const long long ncells = 1ll << (a.bits[0] + a.bits[1] + a.bits[2]);
+    if (GS == 1) { if (gtid - lane >= ncells) return; }
+    else if (cell >= ncells) return;                                  // group-uniform (GS is 32 or 256 = block)
+    const bool live = cell < ncells;
+    const int ix = (int)(cell & ((1ll << a.bits[0]) - 1));
+    const int iy = (int)((cell >> a.bits[0]) & ((1ll << a.bits[1]) - 1));
+    const int iz = (int)(cell >> (a.bits[0] + a.bits[1]));
+    int m_p = 0;
+    unsigned long long ph = 0ull;
+    const unsigned* plist = nullptr;
+    if (live) {
+        if (a.level == 0) m_p = a.n_t;
+        else {
+            const long long parent = (long long)(ix >> (a.bits[0] - a.pbits[0])) +
+                                     ((long long)(iy >> (a.bits[1] - a.pbits[1])) << a.pbits[0]) +
+                                     ((long long)(iz >> (a.bits[2] - a.pbits[2])) << (a.pbits[0] + a.pbits[1]));
+            ph = a.hdr_prev[parent];
+            m_p = lcg_count(ph);
+            plist = a.arena + lcg_offset(ph);
+        }
+    }
+    // far parents whose list is already short are not refined: the child inherits the header (the parent's list
+    // is a valid superset for every query inside the child).  This is empty space away from the surface.
+    // (finest level only: level L-1 stays in its scratch region, which nothing overwrites afterwards)
+    const bool inherit = live && a.persist_all && a.level > 0 && (ph & LCG_FAR) && m_p <= 64;
+    if (inherit) m_p = 0;
+    const float cx = a.lo[0] + ((float)ix + 0.5f) * a.h[0], cy = a.lo[1] + ((float)iy + 0.5f) * a.h[1],
+                cz = a.lo[2] + ((float)iz + 0.5f) * a.h[2];
+    const float rho = 0.5f * sqrtf(a.h[0] * a.h[0] + a.h[1] * a.h[1] + a.h[2] * a.h[2]) * 1.002f;
+    auto cand = [&](int j) -> unsigned { return plist ? plist[j] : (unsigned)j; };
+
+    // ---- pass A: nearest target of the centre
+    unsigned long long key = 0xffffffffffffffffull;
+    for (int j = r; j < m_p; j += GS) {
+        const unsigned id = cand(j);
+        const float4 q = __ldg(a.tgt + id);
+        const unsigned long long k2 = ((unsigned long long)__float_as_uint(d2_rn(cx, cy, cz, q.x, q.y, q.z)) << 32) | id;
+        key = k2 < key ? k2 : key;
+    }
+    if (GS >= 32) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(KSS_FULL, key, off); key = o < key ? o : key; }
+    }
+    if (GS == 256) {
+        if (lane == 0) s_key[threadIdx.x >> 5] = key;
+        __syncthreads();
+        key = s_key[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) key = s_key[w] < key ? s_key[w] : key;
+    }
+    const float mn = __uint_as_float((unsigned)(key >> 32));
+    const unsigned amin = m_p > 0 ? (unsigned)(key & 0xffffffffu) : 0u;
+    const float4 pc = __ldg(a.tgt + amin);
+    const float thr = (sqrtf(mn) + 2.0f * rho) * 1.0001f, thr2 = thr * thr;
+    const float sx = a.h[0] * 1.002f * 1.0001f, sy = a.h[1] * 1.002f * 1.0001f, sz = a.h[2] * 1.002f * 1.0001f;
+    const float marg0 = 1e-5f * (mn + 4.0f * rho * rho);
+    auto keep_test = [&](const float4& q, float d) -> bool {       // sphere rule and dominance rule (see kss_cg.cuh)
+        if (!(d <= thr2)) return false;
+        const float s = sx * fabsf(q.x - pc.x) + sy * fabsf(q.y - pc.y) + sz * fabsf(q.z - pc.z);
+        return !((d - mn) - s > marg0 + 1e-5f * d);
+    };
+    // ---- pass B: count
+    unsigned long long mask = 0ull;
+    unsigned k = 0;
+    for (int j = r, jj = 0; j < m_p; j += GS, ++jj) {
+        const float4 q = __ldg(a.tgt + cand(j));
+        if (keep_test(q, d2_rn(cx, cy, cz, q.x, q.y, q.z))) { if (jj < 64) mask |= 1ull << jj; ++k; }
+    }
+    // ---- allocate (lists padded to x4).  Lists of far cells are inherited by descendants of any depth, so they
+    //      go to the persistent region (cursor[1]); all other lists of an intermediate level go to this level's
+    //      ping-pong scratch region (cursor[0]).  One atomicAdd per warp and region.
+    const bool far = m_p > 0 && sqrtf(mn) > 3.0f * rho;
+    unsigned long long base = 0;
+    unsigned pre = 0, ktot = k;
+    bool persist;
+    if (GS == 1) {
+        persist = a.persist_all != 0;
+        const unsigned mine = (k + 3u) & ~3u;
+        unsigned inc0 = persist ? 0u : mine, inc1 = persist ? mine : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y0 = __shfl_up_sync(KSS_FULL, inc0, o), y1 = __shfl_up_sync(KSS_FULL, inc1, o);
+            if (lane >= o) { inc0 += y0; inc1 += y1; }
+        }
+        const unsigned t0 = __shfl_sync(KSS_FULL, inc0, 31), t1 = __shfl_sync(KSS_FULL, inc1, 31);
+        unsigned long long b0 = 0, b1 = 0;
+        if (lane == 0) { if (t0) b0 = atomicAdd(a.cursor, (unsigned long long)t0); if (t1) b1 = atomicAdd(a.cursor + 1, (unsigned long long)t1); }
+        b0 = __shfl_sync(KSS_FULL, b0, 0); b1 = __shfl_sync(KSS_FULL, b1, 0);
+        if (b0 + t0 > a.cap || b1 + t1 > a.cap_persist) { atomicExch(a.ok, 0); if (live) a.hdr_cur[cell] = 0ull; return; }
+        base = persist ? b1 : b0;
+        pre = (persist ? inc1 : inc0) - mine;
+    } else {
+        unsigned incl = k;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(KSS_FULL, incl, o); if (lane >= o) incl += y; }
+        unsigned tot = __shfl_sync(KSS_FULL, incl, 31);
+        pre = incl - k;
+        if (GS == 256) {
+            if (lane == 31) s_cnt[threadIdx.x >> 5] = incl;
+            __syncthreads();
+            unsigned before = 0; tot = 0;
+            for (int w = 0; w < 8; ++w) { if (w < (int)(threadIdx.x >> 5)) before += s_cnt[w]; tot += s_cnt[w]; }
+            pre += before;
+            persist = a.persist_all != 0;
+            if (threadIdx.x == 0) s_base = tot ? atomicAdd(a.cursor + (persist ? 1 : 0), (unsigned long long)((tot + 3u) & ~3u)) : 0ull;
+            __syncthreads();
+            base = s_base;
+        } else {
+            persist = a.persist_all != 0;
+            if (lane == 0 && tot) base = atomicAdd(a.cursor + (persist ? 1 : 0), (unsigned long long)((tot + 3u) & ~3u));
+            base = __shfl_sync(KSS_FULL, base, 0);
+        }
+        ktot = tot;
+        if (base + ((tot + 3u) & ~3u) > (persist ? a.cap_persist : a.cap)) { atomicExch(a.ok, 0); if (live && r == 0) a.hdr_cur[cell] = 0ull; return; }
+    }
+    if (!live) return;
+    if (inherit) { a.hdr_cur[cell] = ph; return; }
+    if (r == 0) a.hdr_cur[cell] = lcg_make(far, a.arena4 == nullptr, ktot, GS == 1 ? base + pre : base);
+    // ---- pass C: write (intermediate levels: u32 indices; finest level: the points themselves, so that a
+    //      query's candidates are contiguous 16-byte records instead of one 32-byte sector per gather)
+    unsigned* out = a.arena + base + pre;
+    float4* out4 = a.arena4 ? a.arena4 + base + pre : nullptr;
+    unsigned w = 0;
+    auto emit = [&](unsigned id) {
+        if (out4) { float4 q = __ldg(a.tgt + id); q.w = __uint_as_float(id); out4[w] = q; } else out[w] = id;
+        ++w;
+    };
+    if ((m_p + GS - 1) / GS <= 64) {
+        while (mask) {
+            const int jj = __ffsll((long long)mask) - 1;
+            mask &= mask - 1ull;
+            emit(cand(r + GS * jj));
+        }
+    } else {
+        for (int j = r; j < m_p; j += GS) {
+            const unsigned id = cand(j);
+            const float4 q = __ldg(a.tgt + id);
+            if (keep_test(q, d2_rn(cx, cy, cz, q.x, q.y, q.z))) emit(id);
+        }
+    }
+    // padding to x4 (the centre's nearest target is always a member of the list)
+    if (GS == 1) { for (const unsigned e = (k + 3u) & ~3u; w < e;) emit(amin); }
+    else if (r == 0) {
+        for (unsigned t = ktot; t < ((ktot + 3u) & ~3u); ++t) {
+            if (a.arena4) { float4 q = __ldg(a.tgt + amin); q.w = __uint_as_float(amin); a.arena4[base + t] = q; }
+            else a.arena[base + t] = amin;
+        }
+    }
+}
+
+// exact 1-NN through the large candidate grid (per thread); returns 0 on success, 1 if the query is outside the
+// box, 2 for an empty header, 3 for an unrefined far cell with a long list (the caller then uses the box pyramid)
+template <bool IDX>
+__device__ __forceinline__ int lcg_query(const LcgView& v, float qx, float qy, float qz,
+                                          unsigned long long& keyout) {
+    const float fx = (qx - v.g.lo[0]) * v.g.inv_h[0], fy = (qy - v.g.lo[1]) * v.g.inv_h[1], fz = (qz - v.g.lo[2]) * v.g.inv_h[2];
+    const float nx = (float)(1 << v.g.bits[0]), ny = (float)(1 << v.g.bits[1]), nz = (float)(1 << v.g.bits[2]);
+    if (!(fx >= 0.0f && fy >= 0.0f && fz >= 0.0f && fx < nx && fy < ny && fz < nz)) return 1;
+    const size_t cell = (size_t)(int)fx + ((size_t)(int)fy << v.g.bits[0]) + ((size_t)(int)fz << (v.g.bits[0] + v.g.bits[1]));
+    const unsigned long long h = __ldg(v.hdr + cell);
+    const int cnt = lcg_count(h);
+    if (cnt == 0) return 2;
+    if (cnt > 1024) return 3;
+    float best = __int_as_float(0x7f800000);
+    unsigned long long bestkey = 0xffffffffffffffffull;
+    if (h & LCG_IDX) {           // inherited list of an unrefined far cell: u32 indices (never on the steady-state path)
+        const unsigned* ip = v.arena + lcg_offset(h);
+        for (int j = 0; j < cnt; ++j) {
+            const unsigned id = __ldg(ip + j);
+            const float4 p = __ldg(v.tgt + id);
+            const float d = d2_rn(qx, qy, qz, p.x, p.y, p.z);
+            if (IDX) { const unsigned long long k0 = ((unsigned long long)__float_as_uint(d) << 32) | id; bestkey = k0 < bestkey ? k0 : bestkey; }
+            else best = fminf(best, d);
+        }
+        keyout = IDX ? bestkey : ((unsigned long long)__float_as_uint(best) << 32);
+        return 0;
+    }
+    const float4* lp = v.arena4 + lcg_offset(h);
+    const int n4 = (cnt + 3) >> 2;
+    for (int j = 0; j < n4; ++j) {
+        const float4 p0 = __ldg(lp + 4 * j), p1 = __ldg(lp + 4 * j + 1), p2 = __ldg(lp + 4 * j + 2), p3 = __ldg(lp + 4 * j + 3);
+        const float d0 = d2_rn(qx, qy, qz, p0.x, p0.y, p0.z), d1 = d2_rn(qx, qy, qz, p1.x, p1.y, p1.z);
+        const float d2 = d2_rn(qx, qy, qz, p2.x, p2.y, p2.z), d3 = d2_rn(qx, qy, qz, p3.x, p3.y, p3.z);
+        if (IDX) {                                                       // .w = original index
+            const unsigned long long k0 = ((unsigned long long)__float_as_uint(d0) << 32) | __float_as_uint(p0.w);
+            const unsigned long long k1 = ((unsigned long long)__float_as_uint(d1) << 32) | __float_as_uint(p1.w);
+            const unsigned long long k2 = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(p2.w);
+            const unsigned long long k3 = ((unsigned long long)__float_as_uint(d3) << 32) | __float_as_uint(p3.w);
+            const unsigned long long m01 = k0 < k1 ? k0 : k1, m23 = k2 < k3 ? k2 : k3;
+            const unsigned long long m = m01 < m23 ? m01 : m23;
+            bestkey = m < bestkey ? m : bestkey;
+        } else best = fminf(best, fminf(fminf(d0, d1), fminf(d2, d3)));
+    }
+    keyout = IDX ? bestkey : ((unsigned long long)__float_as_uint(best) << 32);
+    return 0;
+}
+
 // ------------------------------------------------------------------ warp-cooperative pyramid NN
 struct NNState {
     float qx, qy, qz;
@@ -273,6 +535,7 @@ struct LgState {
     double prev_mse, mse, fitness;
     int iters, done, converged, kept, apply_T;
     unsigned ticketA, ticketB, ticketF;
+    unsigned miss[5];            // queries not served by the candidate grid, by reason (diagnostics)
 };
 
 // NN kernel.  MODE 0: plain queries from q4 (float4 by original index) -> idx/d2 by original index
@@ -280,8 +543,9 @@ struct LgState {
 //             MODE 2: fitness pass: query = st->fin * inp (original input), d2 only
 template <int MODE>
 __global__ void __launch_bounds__(LG_WARPS * 32)
-lg_nn_kernel(Pyramid py, const int* __restrict__ perm, int n_q, float4* __restrict__ cur,
-             const float4* __restrict__ inp, int* __restrict__ idx, float* __restrict__ d2out,
+lg_nn_kernel(Pyramid py, LcgView lcg, const float4* __restrict__ t_orig, const int* __restrict__ perm, int n_q,
+             float4* __restrict__ cur, const float4* __restrict__ inp, int* __restrict__ idx, float* __restrict__ d2out,
+             int2* __restrict__ corr /* MODE 1: {target index or -1, d2 bits} in one 8-byte record */,
              LgState* __restrict__ st, double max_dist_sqr) {
     __shared__ float4 slots[LG_WARPS][TILE];
     __shared__ float T[16];
@@ -309,13 +573,21 @@ lg_nn_kernel(Pyramid py, const int* __restrict__ perm, int n_q, float4* __restri
             if (valid) cur[o] = make_float4(x, y, z, p.w);
         }
     }
-    const unsigned long long key = (MODE == 2) ? lg_warp_nn<false>(py, x, y, z, slots[warp])
-                                               : lg_warp_nn<true>(py, x, y, z, slots[warp]);
+    unsigned long long key = 0ull;
+    int code = 4;
+    if (lcg.ok) code = (MODE == 2) ? lcg_query<false>(lcg, x, y, z, key) : lcg_query<true>(lcg, x, y, z, key);
+    const bool hit = code == 0;
+    if (MODE == 1 && !hit && valid) atomicAdd(&st->miss[code], 1u);
+    if (__any_sync(KSS_FULL, !hit)) {            // some query left the grid's box: exact pyramid search for the warp
+        const unsigned long long k2 = (MODE == 2) ? lg_warp_nn<false>(py, x, y, z, slots[warp])
+                                                  : lg_warp_nn<true>(py, x, y, z, slots[warp]);
+        if (!hit) key = k2;
+    }
     if (!valid) return;
     const float d2 = __uint_as_float((unsigned)(key >> 32));
-    d2out[o] = d2;
+    if (MODE == 1) corr[o] = make_int2(((double)d2 > max_dist_sqr) ? -1 : (int)(key & 0xffffffffu), __float_as_int(d2));   // A.3
+    else d2out[o] = d2;
     if (MODE == 0) idx[o] = (int)(key & 0xffffffffu);
-    if (MODE == 1) idx[o] = ((double)d2 > max_dist_sqr) ? -1 : (int)(key & 0xffffffffu);   // A.3
 }
 
 // ------------------------------------------------------------------ canonical reductions, large n
@@ -323,19 +595,36 @@ lg_nn_kernel(Pyramid py, const int* __restrict__ perm, int n_q, float4* __restri
 // upper levels: the last CTA to finish reduces the chunk partials by the same rule (<= 2 more levels)
 template <int NQ>
 __device__ __forceinline__ void lg_finish_f32(const float* __restrict__ part, int nchunks, float* out /* [NQ] smem */) {
-    // called by one full CTA (256 threads = 8 warps); part is [nchunks][NQ]
+    // called by one full CTA (256 threads = 8 warps); part is [nchunks][NQ].  Level 2: one warp per 256 partials,
+    // all NQ quantities at once, the lane's 8 rows loaded up front (the accumulation order is unchanged).
     __shared__ float lvl2[256 * 16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int n2 = (nchunks + 255) >> 8;             // level-2 chunks (<= 256 supported -> n <= 16.7 M)
-    for (int q = 0; q < NQ; ++q) {
-        for (int c = warp; c < n2; c += nwarps) {
-            float p = 0.0f;
-            const int hi = min(nchunks, (c + 1) << 8);
-            for (int i = (c << 8) + lane; i < hi; i += 32) p = __fadd_rn(p, part[(size_t)i * NQ + q]);
+    for (int c = warp; c < n2; c += nwarps) {
+        float v[8][NQ];
+        bool have[8];
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) p = __fadd_rn(p, __shfl_xor_sync(KSS_FULL, p, off));
-            if (lane == 0) lvl2[c * 16 + q] = p;
+        for (int u = 0; u < 8; ++u) {
+            const int i = (c << 8) + lane + 32 * u;
+            have[u] = i < nchunks;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) v[u][q] = have[u] ? part[(size_t)i * NQ + q] : 0.0f;
         }
+        float p[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) p[q] = 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (have[u])
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) p[q] = __fadd_rn(p[q], v[u][q]);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) p[q] = __fadd_rn(p[q], __shfl_xor_sync(KSS_FULL, p[q], off));
+        if (lane == 0)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) lvl2[c * 16 + q] = p[q];
     }
     __syncthreads();
     if (warp == 0) {
@@ -360,9 +649,13 @@ __device__ __forceinline__ double lg_finish_f64(const double* __restrict__ part,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int n2 = (nchunks + 255) >> 8;
     for (int c = warp; c < n2; c += nwarps) {
+        double v[8];
+        bool have[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = (c << 8) + lane + 32 * u; have[u] = i < nchunks; v[u] = have[u] ? part[i] : 0.0; }
         double p = 0.0;
-        const int hi = min(nchunks, (c + 1) << 8);
-        for (int i = (c << 8) + lane; i < hi; i += 32) p = __dadd_rn(p, part[i]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (have[u]) p = __dadd_rn(p, v[u]);
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) p = __dadd_rn(p, __shfl_xor_sync(KSS_FULL, p, off));
         if (lane == 0) lvl2d[c] = p;
@@ -400,8 +693,8 @@ __device__ __forceinline__ bool lg_last_block(unsigned* ticket) {
 
 // pass A: per chunk sums of kept source xyz, matched target xyz (float), d2 (double), kept count
 __global__ void __launch_bounds__(256)
-lg_passA_kernel(const float4* __restrict__ cur, const float4* __restrict__ t_orig, const int* __restrict__ idx,
-                const float* __restrict__ d2, int n, int nchunks, float* __restrict__ partA /* [nchunks][6] */,
+lg_passA_kernel(const float4* __restrict__ cur, const float4* __restrict__ t_orig, const int2* __restrict__ corr,
+                int n, int nchunks, float* __restrict__ partA /* [nchunks][6] */,
                 double* __restrict__ partD, int* __restrict__ partK, LgState* __restrict__ st) {
     if (st->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -410,15 +703,26 @@ lg_passA_kernel(const float4* __restrict__ cur, const float4* __restrict__ t_ori
         float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         double dsum = 0.0;
         int k = 0;
-        const int hi = min(n, (c + 1) << 8);
-        for (int i = (c << 8) + lane; i < hi; i += 32) {
-            const int m = idx[i];
-            if (m < 0) continue;
-            const float4 s = cur[i];
-            const float4 t = t_orig[m];
-            a[0] = __fadd_rn(a[0], s.x); a[1] = __fadd_rn(a[1], s.y); a[2] = __fadd_rn(a[2], s.z);
-            a[3] = __fadd_rn(a[3], t.x); a[4] = __fadd_rn(a[4], t.y); a[5] = __fadd_rn(a[5], t.z);
-            dsum = __dadd_rn(dsum, (double)d2[i]);
+        const int i0 = (c << 8) + lane;
+        // all loads of the lane's 8 slots are issued before the (ordered) accumulation
+        int m[8]; float4 sv[8], tv[8]; float dv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + 32 * u;
+            m[u] = -1;
+            if (i < n) { const int2 cr = corr[i]; m[u] = cr.x; dv[u] = __int_as_float(cr.y); }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + 32 * u;
+            if (m[u] >= 0) { sv[u] = cur[i]; tv[u] = __ldg(t_orig + m[u]); }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (m[u] < 0) continue;
+            a[0] = __fadd_rn(a[0], sv[u].x); a[1] = __fadd_rn(a[1], sv[u].y); a[2] = __fadd_rn(a[2], sv[u].z);
+            a[3] = __fadd_rn(a[3], tv[u].x); a[4] = __fadd_rn(a[4], tv[u].y); a[5] = __fadd_rn(a[5], tv[u].z);
+            dsum = __dadd_rn(dsum, (double)dv[u]);
             ++k;
         }
 #pragma unroll
@@ -462,7 +766,7 @@ lg_passA_kernel(const float4* __restrict__ cur, const float4* __restrict__ t_ori
 
 // pass B: sigma partials, then (last CTA) umeyama + accumulate + convergence
 __global__ void __launch_bounds__(256)
-lg_passB_kernel(const float4* __restrict__ cur, const float4* __restrict__ t_orig, const int* __restrict__ idx,
+lg_passB_kernel(const float4* __restrict__ cur, const float4* __restrict__ t_orig, const int2* __restrict__ corr,
                 int n, int nchunks, float* __restrict__ partB /* [nchunks][9] */, LgState* __restrict__ st,
                 int max_iter, double rot_thr, double trans_thr, double mse_rel, double mse_abs) {
     if (st->done) return;
@@ -473,12 +777,19 @@ lg_passB_kernel(const float4* __restrict__ cur, const float4* __restrict__ t_ori
         const float sm0 = st->smean[0], sm1 = st->smean[1], sm2 = st->smean[2];
         const float dm0 = st->dmean[0], dm1 = st->dmean[1], dm2 = st->dmean[2];
         float a[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        const int hi = min(n, (c + 1) << 8);
-        for (int i = (c << 8) + lane; i < hi; i += 32) {
-            const int m = idx[i];
-            if (m < 0) continue;
-            const float4 s = cur[i];
-            const float4 t = t_orig[m];
+        const int i0 = (c << 8) + lane;
+        int m[8]; float4 sv[8], tv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = i0 + 32 * u; m[u] = i < n ? corr[i].x : -1; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + 32 * u;
+            if (m[u] >= 0) { sv[u] = cur[i]; tv[u] = __ldg(t_orig + m[u]); }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (m[u] < 0) continue;
+            const float4 s = sv[u], t = tv[u];
             const float sx = sub_(s.x, sm0), sy = sub_(s.y, sm1), sz = sub_(s.z, sm2);
             const float dx = sub_(t.x, dm0), dy = sub_(t.y, dm1), dz = sub_(t.z, dm2);
             a[0] = add_(a[0], mul_(dx, sx)); a[1] = add_(a[1], mul_(dx, sy)); a[2] = add_(a[2], mul_(dx, sz));
@@ -564,6 +875,7 @@ __global__ void lg_state_init_kernel(LgState* st) {
     if (threadIdx.x == 0) {
         st->prev_mse = DBL_MAX; st->mse = 0; st->fitness = 0; st->iters = 0; st->done = 0; st->converged = 0;
         st->kept = 0; st->apply_T = 0; st->ticketA = st->ticketB = st->ticketF = 0u; st->one_over_n = 0.f;
+        for (int i = 0; i < 5; ++i) st->miss[i] = 0u;
     }
 }
 
@@ -641,6 +953,117 @@ int build_pyramid(Ctx& c, const double* d_t, int n_t, Pyramid* py, float4** t_or
     return c.ok() ? KSS_OK : c.err;
 }
 
+bool lcg_enabled() { const char* e = getenv("KSS_NO_LCG"); return !(e && e[0] == '1'); }
+
+// large candidate grid over the target's bounding box (device bbox from order_cloud's "<tag>_bb")
+int build_lcg(Ctx& c, const float4* t_orig, int n_t, LcgView* view) {
+    memset(view, 0, sizeof(*view));
+    if (!lcg_enabled()) return KSS_OK;
+    unsigned* bb = c.get<unsigned>("lg_t_bb", 8);
+    if (c.err) return c.err;
+    unsigned hb[6];
+    if (cudaMemcpyAsync(hb, bb, sizeof(hb), cudaMemcpyDeviceToHost, c.st) != cudaSuccess) return KSS_ERR_CUDA;
+    if (cudaStreamSynchronize(c.st) != cudaSuccess) return KSS_ERR_CUDA;
+    auto o2f = [](unsigned u) { unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; memcpy(&f, &v, 4); return f; };
+    float lo[3], ext[3], emax = 0.f;
+    for (int a = 0; a < 3; ++a) { lo[a] = o2f(hb[a]); ext[a] = o2f(hb[3 + a]) - lo[a]; emax = std::max(emax, ext[a]); }
+    if (!(emax > 0.f)) return KSS_OK;                                   // degenerate cloud: pyramid only
+    const float margin = 0.02f * emax + 1e-6f;
+    double vol = 1.0;
+    for (int a = 0; a < 3; ++a) { lo[a] -= margin; ext[a] += 2.f * margin; vol *= std::max(ext[a], 1e-3f * emax); }
+    const double cells_target = std::min(67108864.0, std::max(4096.0, 32.0 * (double)n_t));
+    const double h = std::cbrt(vol / cells_target);
+    LcgGeom g;
+    int L = 0;
+    for (int a = 0; a < 3; ++a) {
+        int b = (int)std::lround(std::log2(std::max(ext[a], 1e-3f * emax) / h));
+        b = std::min(10, std::max(0, b));
+        g.bits[a] = b; L = std::max(L, b);
+        g.lo[a] = lo[a]; g.h[a] = ext[a] / (float)(1 << b); g.inv_h[a] = (float)(1 << b) / ext[a];
+    }
+    g.levels = L + 1;
+    size_t hdr_total = 0;
+    std::vector<size_t> hdr_off(g.levels);
+    for (int l = 0; l < g.levels; ++l) {
+        hdr_off[l] = hdr_total;
+        hdr_total += (size_t)1 << (lcg_bits(g, l, 0) + lcg_bits(g, l, 1) + lcg_bits(g, l, 2));
+    }
+    const size_t finest = (size_t)1 << (g.bits[0] + g.bits[1] + g.bits[2]);
+    // list storage: two ping-pong scratch regions for the intermediate levels (a level only reads its
+    // parent level) and one region for the finest level, which is the only one queries use
+    const unsigned long long cap_s = 112ull * (unsigned long long)n_t + 65536ull;
+    const unsigned long long cap_f = 4ull * finest + 32ull * (unsigned long long)n_t + 65536ull;
+    unsigned long long* hdr = c.get<unsigned long long>("lcg_hdr", hdr_total);
+    // u32 arena: [scratch A | scratch B | persistent far lists of intermediate levels]; float4 arena: finest level
+    const unsigned long long cap_p = 1024ull;
+    unsigned* arena = c.get<unsigned>("lcg_arena", 2 * cap_s + cap_p);
+    float4* arena4 = c.get<float4>("lcg_arena4", cap_f);
+    unsigned long long* cursor = c.get<unsigned long long>("lcg_cursor", 2);
+    int* ok = c.get<int>("lcg_ok", 2);
+    if (c.err) { c.err = 0; return KSS_OK; }                             // not enough memory: pyramid only
+    const int one = 1;
+    cudaMemcpyAsync(ok, &one, sizeof(int), cudaMemcpyHostToDevice, c.st);
+    unsigned long long prev_cursor = 0, pers_prev = 0, pers_last = 0;
+    double mean_parent = (double)n_t;
+    for (int l = 0; l < g.levels; ++l) {
+        LcgLevelArgs a;
+        a.level = l;
+        for (int k = 0; k < 3; ++k) {
+            a.bits[k] = lcg_bits(g, l, k); a.pbits[k] = l ? lcg_bits(g, l - 1, k) : 0;
+            a.lo[k] = g.lo[k]; a.h[k] = ext[k] / (float)(1 << a.bits[k]);
+        }
+        a.tgt = t_orig; a.n_t = n_t;
+        a.hdr_prev = l ? hdr + hdr_off[l - 1] : nullptr; a.hdr_cur = hdr + hdr_off[l];
+        const bool last = l == g.levels - 1;
+        const unsigned long long region = (unsigned long long)(l & 1) * cap_s;
+        a.arena = arena; a.cursor = cursor; a.cap = region + cap_s; a.persist_all = last ? 1 : 0;
+        a.cap_persist = last ? cap_f : 2 * cap_s + cap_p; a.arena4 = last ? arena4 : nullptr;
+        a.ok = ok;
+        if (l == 0 || last) {      // persistent cursor: u32 region for far lists of intermediate levels, 0-based float4 arena for the finest
+            const unsigned long long pf = last ? 0ull : 2 * cap_s;
+            if (last) { cudaMemcpyAsync(&pers_last, cursor + 1, sizeof(pers_last), cudaMemcpyDeviceToHost, c.st); cudaStreamSynchronize(c.st); }
+            cudaMemcpyAsync(cursor + 1, &pf, sizeof(pf), cudaMemcpyHostToDevice, c.st); cudaStreamSynchronize(c.st);
+            if (last) pers_prev = 0;
+        }
+        cudaMemcpyAsync(cursor, &region, sizeof(region), cudaMemcpyHostToDevice, c.st);   // `region` lives until the sync below
+        prev_cursor = region;
+        const long long ncells = 1ll << (a.bits[0] + a.bits[1] + a.bits[2]);
+        if (mean_parent > 1024.0 && ncells <= (1 << 20)) lcg_level_kernel<256><<<(unsigned)ncells, 256, 0, c.st>>>(a);
+        else if (mean_parent > 40.0) lcg_level_kernel<32><<<(unsigned)((ncells * 32 + 255) / 256), 256, 0, c.st>>>(a);
+        else lcg_level_kernel<1><<<(unsigned)((ncells + 255) / 256), 256, 0, c.st>>>(a);
+        c.launched();
+        unsigned long long cur2[2] = {0, 0};
+        if (cudaMemcpyAsync(cur2, cursor, sizeof(cur2), cudaMemcpyDeviceToHost, c.st) != cudaSuccess) return KSS_ERR_CUDA;
+        if (cudaStreamSynchronize(c.st) != cudaSuccess) return KSS_ERR_CUDA;
+        const unsigned long long pers_now = last ? cur2[1] : cur2[1] - 2 * cap_s;
+        const unsigned long long cur = cur2[0] + (pers_now - pers_prev);       // entries written by this level (both regions)
+        pers_prev = pers_now;
+        const int gs_used = (mean_parent > 1024.0 && ncells <= (1 << 20)) ? 256 : (mean_parent > 40.0 ? 32 : 1);
+        mean_parent = (double)(cur - prev_cursor) / (double)ncells;
+        if (getenv("KSS_LCG_VERBOSE")) {
+            static double t_prev = 0; struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+            const double t_now = ts.tv_sec + 1e-9 * ts.tv_nsec;
+            fprintf(stderr, "[lcg] level %d GS %d bits %d,%d,%d cells %lld entries %llu mean %.2f  (+%.3f ms)\n", l, gs_used, a.bits[0], a.bits[1],
+                    a.bits[2], ncells, cur - prev_cursor, mean_parent, l ? (t_now - t_prev) * 1e3 : 0.0);
+            t_prev = t_now;
+        }
+        prev_cursor = cur;
+    }
+    int hok = 0;
+    if (cudaMemcpyAsync(&hok, ok, sizeof(int), cudaMemcpyDeviceToHost, c.st) != cudaSuccess) return KSS_ERR_CUDA;
+    if (cudaStreamSynchronize(c.st) != cudaSuccess) return KSS_ERR_CUDA;
+    view->hdr = hdr + hdr_off[g.levels - 1];
+    view->arena4 = arena4;
+    view->arena = arena;
+    view->tgt = t_orig;
+    view->g = g;
+    view->ok = hok;
+    if (getenv("KSS_LCG_VERBOSE"))
+        fprintf(stderr, "[lcg] n_t=%d bits=%d,%d,%d levels=%d cells=%zu caps %llu/%llu finest mean list %.2f ok=%d\n", n_t,
+                g.bits[0], g.bits[1], g.bits[2], g.levels, finest, cap_s, cap_f, mean_parent, hok);
+    return c.ok() ? KSS_OK : c.err;
+}
+
 inline int nn_grid(int n_q) { return (n_q + LG_WARPS * 32 - 1) / (LG_WARPS * 32); }
 
 }  // namespace
@@ -649,14 +1072,18 @@ int large_nn_device(cudaStream_t st, long long* launches, const double* d_q, int
                     int* d_idx, float* d_d2, const DevAlloc& alloc) {
     Ctx c{st, launches, alloc};
     Pyramid py;
-    int r = build_pyramid(c, d_t, n_t, &py, nullptr);
+    float4* t_orig = nullptr;
+    int r = build_pyramid(c, d_t, n_t, &py, &t_orig);
+    if (r) return r;
+    LcgView lcg;
+    r = build_lcg(c, t_orig, n_t, &lcg);
     if (r) return r;
     float4* q4 = c.get<float4>("lg_q4", n_q);
     int* perm = c.get<int>("lg_perm", n_q);
     if (c.err) return c.err;
     r = order_cloud(c, "lg_q", d_q, n_q, q4, nullptr, 0, perm);
     if (r) return r;
-    lg_nn_kernel<0><<<nn_grid(n_q), LG_WARPS * 32, 0, st>>>(py, perm, n_q, q4, nullptr, d_idx, d_d2, nullptr, 0.0);
+    lg_nn_kernel<0><<<nn_grid(n_q), LG_WARPS * 32, 0, st>>>(py, lcg, t_orig, perm, n_q, q4, nullptr, d_idx, d_d2, nullptr, nullptr, 0.0);
     c.launched();
     return c.ok() ? KSS_OK : c.err;
 }
@@ -708,10 +1135,15 @@ int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, i
     float4* t_orig = nullptr;
     int r = build_pyramid(c, d_t, n_t, &py, &t_orig);
     if (r) return r;
+    LcgView lcg;
+    r = build_lcg(c, t_orig, n_t, &lcg);
+    if (r) return r;
+    static_assert(sizeof(LcgView) <= sizeof(run->lcg), "LargeIcp::lcg too small");
+    memcpy(run->lcg, &lcg, sizeof(lcg));
     float4* inp = c.get<float4>("lg_inp", n_s);
     float4* cur = c.get<float4>("lg_cur", n_s);
     int* perm = c.get<int>("lg_perm", n_s);
-    int* idx = c.get<int>("lg_idx", n_s);
+    int* idx = c.get<int>("lg_corr", (size_t)n_s * 2);      // int2 {index, d2 bits} per source point
     float* d2 = c.get<float>("lg_d2", n_s);
     const int nchunks = (n_s + 255) / 256;
     float* pA = c.get<float>("lg_partA", (size_t)nchunks * 6);
@@ -737,18 +1169,19 @@ int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, i
 // enqueue `count` ICP iterations (each = NN + pass A + pass B); kernels are no-ops once the run is done
 int large_icp_iterations(cudaStream_t st, long long* launches, LargeIcp* run, const kss_icp_params* prm, int count) {
     Pyramid py; memcpy(&py, run->pyramid, sizeof(py));
+    LcgView lcg; memcpy(&lcg, run->lcg, sizeof(lcg));
     LgState* state = (LgState*)run->state;
     const double max2 = prm->max_corr_dist * prm->max_corr_dist;
     const int n = run->n_s, nch = run->nchunks;
     const double mse_abs = prm->fitness_eps < 0.0 ? -1.0 : 1e-12;   // fitness_eps < 0: never converge (steady-state timing)
     for (int k = 0; k < count; ++k) {
         if (run->mark) run->mark(run->mark_user, KSS_STAGE_LARGE_NN, 1);
-        lg_nn_kernel<1><<<nn_grid(n), LG_WARPS * 32, 0, st>>>(py, run->perm, n, (float4*)run->cur, nullptr, run->idx,
-                                                              run->d2, state, max2);
+        lg_nn_kernel<1><<<nn_grid(n), LG_WARPS * 32, 0, st>>>(py, lcg, (const float4*)run->t_orig, run->perm, n, (float4*)run->cur, nullptr, nullptr,
+                                                              nullptr, (int2*)run->idx, state, max2);
         if (run->mark) { run->mark(run->mark_user, KSS_STAGE_LARGE_NN, 0); run->mark(run->mark_user, KSS_STAGE_LARGE_REDUCE, 1); }
-        lg_passA_kernel<<<(nch + 7) / 8, 256, 0, st>>>((const float4*)run->cur, (const float4*)run->t_orig, run->idx,
-                                                       run->d2, n, nch, run->partA, run->partD, run->partK, state);
-        lg_passB_kernel<<<(nch + 7) / 8, 256, 0, st>>>((const float4*)run->cur, (const float4*)run->t_orig, run->idx, n,
+        lg_passA_kernel<<<(nch + 7) / 8, 256, 0, st>>>((const float4*)run->cur, (const float4*)run->t_orig, (const int2*)run->idx,
+                                                       n, nch, run->partA, run->partD, run->partK, state);
+        lg_passB_kernel<<<(nch + 7) / 8, 256, 0, st>>>((const float4*)run->cur, (const float4*)run->t_orig, (const int2*)run->idx, n,
                                                        nch, run->partB, state, prm->max_iterations,
                                                        1.0 - prm->transformation_eps, prm->transformation_eps,
                                                        prm->fitness_eps, mse_abs);
@@ -772,8 +1205,9 @@ int large_icp_run(cudaStream_t st, long long* launches, LargeIcp* run, const kss
     }
     // getFitnessScore: final * ORIGINAL input, NN, mean d2 in double (A.7)
     Pyramid py; memcpy(&py, run->pyramid, sizeof(py));
-    lg_nn_kernel<2><<<nn_grid(run->n_s), LG_WARPS * 32, 0, st>>>(py, run->perm, run->n_s, nullptr, (const float4*)run->inp,
-                                                               nullptr, run->d2, state, 0.0);
+    LcgView lcg; memcpy(&lcg, run->lcg, sizeof(lcg));
+    lg_nn_kernel<2><<<nn_grid(run->n_s), LG_WARPS * 32, 0, st>>>(py, lcg, (const float4*)run->t_orig, run->perm, run->n_s, nullptr, (const float4*)run->inp,
+                                                               nullptr, run->d2, nullptr, state, 0.0);
     lg_passF_kernel<<<(run->nchunks + 7) / 8, 256, 0, st>>>(run->d2, run->n_s, run->nchunks, run->partD, nullptr,
                                                             &state->ticketF, run->out3);
     *launches += 2;
@@ -786,6 +1220,8 @@ int large_icp_result(cudaStream_t st, LargeIcp* run, float T[16], double* fitnes
     if (cudaMemcpyAsync(&h, run->state, sizeof(LgState), cudaMemcpyDeviceToHost, st) != cudaSuccess) return KSS_ERR_CUDA;
     if (cudaMemcpyAsync(o3, run->out3, sizeof(o3), cudaMemcpyDeviceToHost, st) != cudaSuccess) return KSS_ERR_CUDA;
     if (cudaStreamSynchronize(st) != cudaSuccess) return KSS_ERR_CUDA;
+    if (getenv("KSS_LCG_VERBOSE"))
+        fprintf(stderr, "[lcg] grid misses over the run: outside box %u, empty %u, far/long %u, grid off %u (iterations %d)\n", h.miss[1], h.miss[2], h.miss[3], h.miss[4], h.iters);
     if (T) for (int i = 0; i < 16; ++i) T[i] = h.fin[i];
     if (fitness) *fitness = o3[0];
     if (iters) *iters = h.iters;

@@ -22,6 +22,7 @@ int large_metrics_device(cudaStream_t st, long long* launches, const double* d_q
 // a prepared full-resolution ICP run (device buffers owned by the context's allocator)
 struct LargeIcp {
     alignas(8) unsigned char pyramid[160];
+    alignas(8) unsigned char lcg[160];
     int n_s = 0, n_t = 0, nchunks = 0;
     void *t_orig = nullptr, *inp = nullptr, *cur = nullptr, *state = nullptr;
     int *perm = nullptr, *idx = nullptr, *partK = nullptr;
