@@ -19,8 +19,10 @@ def icp_iteration_roofline(pkg, ctx, args, hbm_peak, which, stream=None):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % dev)     # > 126 MB L2
     never = dict(max_iter=1 << 30, fit_eps=-1.0, trans_eps=-1.0)                  # steady state: no convergence exit
 
+    ctx.icp_large_begin(p["full_s"], p["full_t"])          # first call also pays cudaMalloc of the work buffers
+    ctx.synchronize()
     ctx.set_timing(True)
-    ctx.icp_large_begin(p["full_s"], p["full_t"])
+    ctx.icp_large_begin(p["full_s"], p["full_t"])          # timed: H2D (pageable) + Morton bucket sort + box pyramid + candidate grid
     ctx.synchronize()
     build_ms = ctx.stage_ms(7)[0]
     ctx.icp_large_iterate(30, **never)                                            # warm-up, reaches the fixed point

@@ -258,15 +258,10 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
     if (cg) { a.cg_geom = cg->geom; a.cg_hdr = cg->hdr; a.cg_arena = cg->arena; a.cg_ok = cg->ok; }
     icp_fill(a, b.icp);
     a.run_T = run_T; a.run_fit = run_fit; a.run_iters = run_iters; a.run_conv = run_conv;
-    a.mode = 0;
+    a.mode = 3;                                                // judge (KSS_ICP.hpp:93) + hypothesis runs (:102-118), one launch
     {
-        StageTimer tm(ctx, KSS_STAGE_ICP_JUDGE);
-        KL(launch_icp(st, P, 1, a));                           // judge run (KSS_ICP.hpp:93)
-    }
-    a.mode = 1;
-    if (slots > 0) {
         StageTimer tm(ctx, KSS_STAGE_ICP_HYP);
-        KL(launch_icp(st, P, slots, a));                       // hypothesis runs (KSS_ICP.hpp:102-118)
+        KL(launch_icp(st, P, 1 + slots, a));
     }
     double* pa = d_point_align;
     if (!pa) BUF("point_align", (size_t)P * cap_S * 3, &pa);

@@ -21,7 +21,7 @@
 
 namespace kss {
 
-constexpr int CG_LEVELS = 5;                  // 4, 8, 16, 32, 64 cells per axis
+constexpr int CG_LEVELS = 4;                  // 4, 8, 16, 32 cells per axis
 constexpr int CG_NG0 = 4;
 constexpr int CG_NG = CG_NG0 << (CG_LEVELS - 1);
 constexpr int CG_CNT_BITS = 11;               // header = (offset/4 << 11) | count ; count 2047 = "search everything"

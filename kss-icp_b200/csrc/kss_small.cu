@@ -248,7 +248,8 @@ cg_level_kernel(int level, const float4* __restrict__ t_sorted, const int* __res
             ix = tid & 3; iy = (tid >> 2) & 3; iz = tid >> 4;
             m_p = n_t;
         } else {
-            const int px = parent % png, py = (parent / png) % png, pz = parent / (png * png);
+            const int lp = level + 1, pm = png - 1;                      // png = 2 << level is a power of two
+            const int px = parent & pm, py = (parent >> lp) & pm, pz = parent >> (2 * lp);
             ix = 2 * px + (child & 1); iy = 2 * py + ((child >> 1) & 1); iz = 2 * pz + (child >> 2);
             const unsigned ph = (hdr_all + (size_t)p * CG_HDR_TOTAL + cg_hdr_base(level - 1))[parent];
             m_p = (int)(ph & CG_CNT_MASK);
@@ -498,16 +499,20 @@ icp_small_kernel(IcpArgs a) {
     const int slot = blockIdx.x;
     const int n_s = a.cnt_s ? a.cnt_s[p] : a.cap_s;
     const int n_t = a.cnt_t[p];
-    const int run = p * a.runs_per_pair + (a.mode == 1 ? 1 + slot : 0);
+    // mode 3 = one launch for everything: slot 0 is the judge run, slots >= 1 the hypothesis runs (not gated on
+    // the judge's fitness -- the two are independent; select_kernel ignores them when the judge passes)
+    const int mode = a.mode == 3 ? (slot == 0 ? 0 : 1) : a.mode;
+    const int hslot = a.mode == 3 ? slot - 1 : slot;
+    const int run = p * a.runs_per_pair + (mode == 1 ? 1 + hslot : 0);
 
     double ang_c[3] = {1.0, 1.0, 1.0}, ang_s[3] = {0.0, 0.0, 0.0};
-    if (a.mode == 1) {
-        const bool active = a.judge_thr < 0.0 || a.run_fit[p * a.runs_per_pair] > a.judge_thr;
-        if (!active || slot >= a.n_minima[p] || slot >= a.runs_per_pair - 1) return;
-        const int h = a.minima[(size_t)p * a.hpad + slot];
+    if (mode == 1) {
+        const bool active = a.mode == 3 || a.judge_thr < 0.0 || a.run_fit[p * a.runs_per_pair] > a.judge_thr;
+        if (!active || hslot >= a.n_minima[p] || hslot >= a.runs_per_pair - 1) return;
+        const int h = a.minima[(size_t)p * a.hpad + hslot];
         const int idx[3] = {h / (a.G * a.G), (h / a.G) % a.G, h % a.G};
         for (int k = 0; k < 3; ++k) { ang_c[k] = a.trig_list[2 * idx[k]]; ang_s[k] = a.trig_list[2 * idx[k] + 1]; }
-    } else if (a.mode == 0) {
+    } else if (mode == 0) {
         const int h = a.best_h[p];
         const int idx[3] = {h / (a.G * a.G), (h / a.G) % a.G, h % a.G};
         for (int k = 0; k < 3; ++k) { ang_c[k] = a.trig_accum[2 * idx[k]]; ang_s[k] = a.trig_accum[2 * idx[k] + 1]; }
@@ -551,7 +556,7 @@ icp_small_kernel(IcpArgs a) {
     const double* a8 = a.align8 ? a.align8 + (size_t)p * 8 : nullptr;
     auto input_point = [&](int o, float& x, float& y, float& z) {
         double dx = src[3 * o], dy = src[3 * o + 1], dz = src[3 * o + 2];
-        if (a.mode != 2) {                                            // initRegistrationKSS.hpp:75-109
+        if (mode != 2) {                                              // initRegistrationKSS.hpp:75-109
             dx = align_coord(dx, a8[0], a8[3], a8[6]);
             dy = align_coord(dy, a8[1], a8[4], a8[6]);
             dz = align_coord(dz, a8[2], a8[5], a8[6]);
