@@ -218,6 +218,9 @@ struct LcgLevelArgs {
     const unsigned long long* hdr_prev; unsigned long long* hdr_cur;
     unsigned* arena; unsigned long long* cursor; unsigned long long cap;   // scratch region of this level: cursor[0] < cap
     unsigned long long cap_persist;                                       // persistent region: cursor[1] < cap_persist
+    int from_all;                                                         // first built level: the parent list is every target
+    const unsigned* worklist; unsigned nwork;                             // GS=1 pass 2: cells to build (compacted)
+    unsigned* worklist_out; unsigned* worklist_long; unsigned* nwork_out; // GS=1 pass 1: cells that do not inherit (short / long parent lists)
     int persist_all;                                                      // finest level: everything is persistent ...
     float4* arena4;                                                       // ... and stored as float4 {x,y,z,bits(orig)} here (offsets in float4 units)
     int* ok;
@@ -243,12 +246,13 @@ lcg_level_kernel(LcgLevelArgs a) {
     __shared__ unsigned long long s_base;
     const int lane = threadIdx.x & 31;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long cell = gtid / GS;
+    long long cell = gtid / GS;
     const int r = (int)(gtid % GS);
-    const long long ncells = 1ll << (a.bits[0] + a.bits[1] + a.bits[2]);
+    const long long ncells = a.worklist ? (long long)a.nwork : 1ll << (a.bits[0] + a.bits[1] + a.bits[2]);
     if (GS == 1) { if (gtid - lane >= ncells) return; }
     else if (cell >= ncells) return;                                  // group-uniform (GS is 32 or 256 = block)
     const bool live = cell < ncells;
+    if (a.worklist) cell = live ? (long long)a.worklist[cell] : 0;    // compacted pass: the cells that need building
     const int ix = (int)(cell & ((1ll << a.bits[0]) - 1));
     const int iy = (int)((cell >> a.bits[0]) & ((1ll << a.bits[1]) - 1));
     const int iz = (int)(cell >> (a.bits[0] + a.bits[1]));
@@ -256,7 +260,7 @@ lcg_level_kernel(LcgLevelArgs a) {
     unsigned long long ph = 0ull;
     const unsigned* plist = nullptr;
     if (live) {
-        if (a.level == 0) m_p = a.n_t;
+        if (a.from_all) m_p = a.n_t;
         else {
             const long long parent = (long long)(ix >> (a.bits[0] - a.pbits[0])) +
                                      ((long long)(iy >> (a.bits[1] - a.pbits[1])) << a.pbits[0]) +
@@ -269,7 +273,22 @@ lcg_level_kernel(LcgLevelArgs a) {
     // far parents whose list is already short are not refined: the child inherits the header (the parent's list
     // is a valid superset for every query inside the child).  This is empty space away from the surface.
     // (finest level only: level L-1 stays in its scratch region, which nothing overwrites afterwards)
-    const bool inherit = live && a.persist_all && a.level > 0 && (ph & LCG_FAR) && m_p <= 64;
+    const bool inherit = live && a.persist_all && !a.from_all && (ph & LCG_FAR) && m_p <= 128;
+    if (GS == 1 && a.worklist_out) {
+        // pass 1 of the finest level: write inherited headers, compact everything else into the work list so
+        // that pass 2 runs with dense warps (almost all cells of the finest level inherit)
+        if (inherit) a.hdr_cur[cell] = ph;
+        const bool want = live && !inherit;
+        const bool lng = want && m_p > 48;                            // long parent lists get a warp per cell
+        const unsigned ns = __ballot_sync(KSS_FULL, want && !lng), nl = __ballot_sync(KSS_FULL, lng);
+        unsigned bs = 0, bl = 0;
+        if (lane == 0) { if (ns) bs = atomicAdd(a.nwork_out, (unsigned)__popc(ns)); if (nl) bl = atomicAdd(a.nwork_out + 1, (unsigned)__popc(nl)); }
+        bs = __shfl_sync(KSS_FULL, bs, 0); bl = __shfl_sync(KSS_FULL, bl, 0);
+        const unsigned below = (1u << lane) - 1u;
+        if (want && !lng) a.worklist_out[bs + __popc(ns & below)] = (unsigned)cell;
+        if (lng) a.worklist_long[bl + __popc(nl & below)] = (unsigned)cell;
+        return;
+    }
     if (inherit) m_p = 0;
     const float cx = a.lo[0] + ((float)ix + 0.5f) * a.h[0], cy = a.lo[1] + ((float)iy + 0.5f) * a.h[1],
                 cz = a.lo[2] + ((float)iz + 0.5f) * a.h[2];
@@ -995,18 +1014,23 @@ int build_lcg(Ctx& c, const float4* t_orig, int n_t, LcgView* view) {
     const unsigned long long cap_f = 4ull * finest + 32ull * (unsigned long long)n_t + 65536ull;
     unsigned long long* hdr = c.get<unsigned long long>("lcg_hdr", hdr_total);
     // u32 arena: [scratch A | scratch B | persistent far lists of intermediate levels]; float4 arena: finest level
-    const unsigned long long cap_p = 1024ull;
-    unsigned* arena = c.get<unsigned>("lcg_arena", 2 * cap_s + cap_p);
+    unsigned* arena = c.get<unsigned>("lcg_arena", 2 * cap_s);
     float4* arena4 = c.get<float4>("lcg_arena4", cap_f);
     unsigned long long* cursor = c.get<unsigned long long>("lcg_cursor", 2);
     int* ok = c.get<int>("lcg_ok", 2);
     if (c.err) { c.err = 0; return KSS_OK; }                             // not enough memory: pyramid only
     const int one = 1;
     cudaMemcpyAsync(ok, &one, sizeof(int), cudaMemcpyHostToDevice, c.st);
-    unsigned long long prev_cursor = 0, pers_prev = 0, pers_last = 0;
+    unsigned long long prev_cursor = 0;
     double mean_parent = (double)n_t;
-    for (int l = 0; l < g.levels; ++l) {
+    // the hierarchy starts at the last level with <= 256 cells, built directly from all targets (one block per cell)
+    int l_start = 0;
+    for (int l = 0; l < g.levels; ++l)
+        if ((lcg_bits(g, l, 0) + lcg_bits(g, l, 1) + lcg_bits(g, l, 2)) <= 8) l_start = l;
+    unsigned* worklist = nullptr; unsigned* nwork = nullptr;
+    for (int l = l_start; l < g.levels; ++l) {
         LcgLevelArgs a;
+        memset(&a, 0, sizeof(a));
         a.level = l;
         for (int k = 0; k < 3; ++k) {
             a.bits[k] = lcg_bits(g, l, k); a.pbits[k] = l ? lcg_bits(g, l - 1, k) : 0;
@@ -1014,37 +1038,54 @@ int build_lcg(Ctx& c, const float4* t_orig, int n_t, LcgView* view) {
         }
         a.tgt = t_orig; a.n_t = n_t;
         a.hdr_prev = l ? hdr + hdr_off[l - 1] : nullptr; a.hdr_cur = hdr + hdr_off[l];
+        a.from_all = l == l_start ? 1 : 0;
         const bool last = l == g.levels - 1;
         const unsigned long long region = (unsigned long long)(l & 1) * cap_s;
         a.arena = arena; a.cursor = cursor; a.cap = region + cap_s; a.persist_all = last ? 1 : 0;
-        a.cap_persist = last ? cap_f : 2 * cap_s + cap_p; a.arena4 = last ? arena4 : nullptr;
+        a.cap_persist = cap_f; a.arena4 = last ? arena4 : nullptr;
         a.ok = ok;
-        if (l == 0 || last) {      // persistent cursor: u32 region for far lists of intermediate levels, 0-based float4 arena for the finest
-            const unsigned long long pf = last ? 0ull : 2 * cap_s;
-            if (last) { cudaMemcpyAsync(&pers_last, cursor + 1, sizeof(pers_last), cudaMemcpyDeviceToHost, c.st); cudaStreamSynchronize(c.st); }
-            cudaMemcpyAsync(cursor + 1, &pf, sizeof(pf), cudaMemcpyHostToDevice, c.st); cudaStreamSynchronize(c.st);
-            if (last) pers_prev = 0;
-        }
-        cudaMemcpyAsync(cursor, &region, sizeof(region), cudaMemcpyHostToDevice, c.st);   // `region` lives until the sync below
+        const unsigned long long init2[2] = {region, 0ull};                 // scratch cursor, float4-arena cursor
+        cudaMemcpyAsync(cursor, init2, sizeof(init2), cudaMemcpyHostToDevice, c.st);
+        if (cudaStreamSynchronize(c.st) != cudaSuccess) return KSS_ERR_CUDA;
         prev_cursor = region;
         const long long ncells = 1ll << (a.bits[0] + a.bits[1] + a.bits[2]);
-        if (mean_parent > 1024.0 && ncells <= (1 << 20)) lcg_level_kernel<256><<<(unsigned)ncells, 256, 0, c.st>>>(a);
-        else if (mean_parent > 40.0) lcg_level_kernel<32><<<(unsigned)((ncells * 32 + 255) / 256), 256, 0, c.st>>>(a);
-        else lcg_level_kernel<1><<<(unsigned)((ncells + 255) / 256), 256, 0, c.st>>>(a);
+        const int gs_used = (a.from_all || (mean_parent > 1024.0 && ncells <= (1 << 20))) ? 256 : (mean_parent > 40.0 ? 32 : 1);
+        if (gs_used == 256) lcg_level_kernel<256><<<(unsigned)ncells, 256, 0, c.st>>>(a);
+        else if (gs_used == 32) lcg_level_kernel<32><<<(unsigned)((ncells * 32 + 255) / 256), 256, 0, c.st>>>(a);
+        else if (!last) lcg_level_kernel<1><<<(unsigned)((ncells + 255) / 256), 256, 0, c.st>>>(a);
+        else {
+            // finest level, two passes: (1) inherit or enqueue, (2) build the enqueued cells with dense warps
+            if (!worklist) { worklist = c.get<unsigned>("lcg_work", (size_t)ncells * 2); nwork = c.get<unsigned>("lcg_nwork", 2); }
+            if (c.err) { c.err = 0; return KSS_OK; }
+            cudaMemsetAsync(nwork, 0, 8, c.st);
+            LcgLevelArgs p1 = a; p1.worklist_out = worklist; p1.worklist_long = worklist + ncells; p1.nwork_out = nwork;
+            lcg_level_kernel<1><<<(unsigned)((ncells + 255) / 256), 256, 0, c.st>>>(p1);
+            unsigned hn[2] = {0, 0};
+            if (cudaMemcpyAsync(hn, nwork, sizeof(hn), cudaMemcpyDeviceToHost, c.st) != cudaSuccess) return KSS_ERR_CUDA;
+            if (cudaStreamSynchronize(c.st) != cudaSuccess) return KSS_ERR_CUDA;
+            if (getenv("KSS_LCG_VERBOSE"))
+                fprintf(stderr, "[lcg] finest level: %u short + %u long of %lld cells are built, the rest inherit\n", hn[0], hn[1], ncells);
+            if (hn[0]) {
+                LcgLevelArgs p2 = a; p2.worklist = worklist; p2.nwork = hn[0];
+                lcg_level_kernel<1><<<(hn[0] + 255) / 256, 256, 0, c.st>>>(p2);
+            }
+            if (hn[1]) {
+                LcgLevelArgs p3 = a; p3.worklist = worklist + ncells; p3.nwork = hn[1];
+                lcg_level_kernel<32><<<(unsigned)(((unsigned long long)hn[1] * 32 + 255) / 256), 256, 0, c.st>>>(p3);
+            }
+            c.launched(2);
+        }
         c.launched();
         unsigned long long cur2[2] = {0, 0};
         if (cudaMemcpyAsync(cur2, cursor, sizeof(cur2), cudaMemcpyDeviceToHost, c.st) != cudaSuccess) return KSS_ERR_CUDA;
         if (cudaStreamSynchronize(c.st) != cudaSuccess) return KSS_ERR_CUDA;
-        const unsigned long long pers_now = last ? cur2[1] : cur2[1] - 2 * cap_s;
-        const unsigned long long cur = cur2[0] + (pers_now - pers_prev);       // entries written by this level (both regions)
-        pers_prev = pers_now;
-        const int gs_used = (mean_parent > 1024.0 && ncells <= (1 << 20)) ? 256 : (mean_parent > 40.0 ? 32 : 1);
+        const unsigned long long cur = last ? cur2[1] + region : cur2[0];
         mean_parent = (double)(cur - prev_cursor) / (double)ncells;
         if (getenv("KSS_LCG_VERBOSE")) {
             static double t_prev = 0; struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
             const double t_now = ts.tv_sec + 1e-9 * ts.tv_nsec;
             fprintf(stderr, "[lcg] level %d GS %d bits %d,%d,%d cells %lld entries %llu mean %.2f  (+%.3f ms)\n", l, gs_used, a.bits[0], a.bits[1],
-                    a.bits[2], ncells, cur - prev_cursor, mean_parent, l ? (t_now - t_prev) * 1e3 : 0.0);
+                    a.bits[2], ncells, cur - prev_cursor, mean_parent, l > l_start ? (t_now - t_prev) * 1e3 : 0.0);
             t_prev = t_now;
         }
         prev_cursor = cur;
