@@ -295,19 +295,37 @@ lcg_level_kernel(LcgLevelArgs a) {
     const float rho = 0.5f * sqrtf(a.h[0] * a.h[0] + a.h[1] * a.h[1] + a.h[2] * a.h[2]) * 1.002f;
     auto cand = [&](int j) -> unsigned { return plist ? plist[j] : (unsigned)j; };
 
-    // ---- pass A: nearest target of the centre
-    unsigned long long key = 0xffffffffffffffffull;
+    // ---- pass A: nearest target of the centre (GS = 1: the four nearest, used as dominance competitors)
+    unsigned long long key = 0xffffffffffffffffull, k1 = ~0ull, k2 = ~0ull, k3 = ~0ull;
     for (int j = r; j < m_p; j += GS) {
         const unsigned id = cand(j);
         const float4 q = __ldg(a.tgt + id);
-        const unsigned long long k2 = ((unsigned long long)__float_as_uint(d2_rn(cx, cy, cz, q.x, q.y, q.z)) << 32) | id;
-        key = k2 < key ? k2 : key;
+        const unsigned long long kk = ((unsigned long long)__float_as_uint(d2_rn(cx, cy, cz, q.x, q.y, q.z)) << 32) | id;
+        if (GS <= 32) {
+            if (kk < k3) {
+                if (kk < key) { k3 = k2; k2 = k1; k1 = key; key = kk; }
+                else if (kk < k1) { k3 = k2; k2 = k1; k1 = kk; }
+                else if (kk < k2) { k3 = k2; k2 = kk; }
+                else k3 = kk;
+            }
+        } else key = kk < key ? kk : key;
     }
-    if (GS >= 32) {
+    if (GS == 32) {
+        // merge the lanes' sorted top-4 lists into the warp's top-4: four rounds of "global minimum, pop it at its owner"
+        unsigned long long g[4];
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(KSS_FULL, key, off); key = o < key ? o : key; }
+        for (int t = 0; t < 4; ++t) {
+            unsigned long long m = key;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(KSS_FULL, m, off); m = o < m ? o : m; }
+            g[t] = m;
+            if (key == m && m != ~0ull) { key = k1; k1 = k2; k2 = k3; k3 = ~0ull; }   // keys are unique (they carry the index)
+        }
+        key = g[0]; k1 = g[1]; k2 = g[2]; k3 = g[3];
     }
     if (GS == 256) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(KSS_FULL, key, off); key = o < key ? o : key; }
         if (lane == 0) s_key[threadIdx.x >> 5] = key;
         __syncthreads();
         key = s_key[0];
@@ -316,14 +334,26 @@ lcg_level_kernel(LcgLevelArgs a) {
     }
     const float mn = __uint_as_float((unsigned)(key >> 32));
     const unsigned amin = m_p > 0 ? (unsigned)(key & 0xffffffffu) : 0u;
-    const float4 pc = __ldg(a.tgt + amin);
     const float thr = (sqrtf(mn) + 2.0f * rho) * 1.0001f, thr2 = thr * thr;
     const float sx = a.h[0] * 1.002f * 1.0001f, sy = a.h[1] * 1.002f * 1.0001f, sz = a.h[2] * 1.002f * 1.0001f;
-    const float marg0 = 1e-5f * (mn + 4.0f * rho * rho);
+    const float rr4 = 4.0f * rho * rho;
+    constexpr int NC = GS <= 32 ? 4 : 1;
+    const unsigned long long ck[4] = {key, k1, k2, k3};
+    float4 cp[NC]; float cd[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const bool have = m_p > 0 && ck[c] != ~0ull;
+        cp[c] = __ldg(a.tgt + (have ? (unsigned)(ck[c] & 0xffffffffu) : 0u));
+        cd[c] = have ? __uint_as_float((unsigned)(ck[c] >> 32)) : __int_as_float(0x7f800000);   // +inf: never dominates
+    }
     auto keep_test = [&](const float4& q, float d) -> bool {       // sphere rule and dominance rule (see kss_cg.cuh)
         if (!(d <= thr2)) return false;
-        const float s = sx * fabsf(q.x - pc.x) + sy * fabsf(q.y - pc.y) + sz * fabsf(q.z - pc.z);
-        return !((d - mn) - s > marg0 + 1e-5f * d);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const float s = sx * fabsf(q.x - cp[c].x) + sy * fabsf(q.y - cp[c].y) + sz * fabsf(q.z - cp[c].z);
+            if ((d - cd[c]) - s > 1e-5f * (d + cd[c] + rr4)) return false;
+        }
+        return true;
     };
     // ---- pass B: count
     unsigned long long mask = 0ull;

@@ -264,28 +264,44 @@ cg_level_kernel(int level, const float4* __restrict__ t_sorted, const int* __res
     const bool inball = ox * ox + oy * oy + oz * oz <= rr * rr;
     if (!inball) m_p = 0;                                                  // outside the query ball: empty list
 
-    // ---- pass A: the centre's nearest target p_c and its squared distance
-    float mn = __int_as_float(0x7f800000);
-    int amin = 0;
+    // ---- pass A: the four targets nearest to the centre (ascending keys d2bits<<32 | id); the first is p_c
+    unsigned long long k0 = ~0ull, k1 = ~0ull, k2 = ~0ull, k3 = ~0ull;
     for (int j = 0; j < m_p; ++j) {
         const int id = plist ? (int)plist[j] : j;
         const float4 q = __ldg(tgt + id);
-        const float d = d2_rn(cx, cy, cz, q.x, q.y, q.z);
-        if (d < mn) { mn = d; amin = id; }
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d2_rn(cx, cy, cz, q.x, q.y, q.z)) << 32) | (unsigned)id;
+        if (key < k3) {
+            if (key < k0) { k3 = k2; k2 = k1; k1 = k0; k0 = key; }
+            else if (key < k1) { k3 = k2; k2 = k1; k1 = key; }
+            else if (key < k2) { k3 = k2; k2 = key; }
+            else k3 = key;
+        }
     }
+    const float mn = __uint_as_float((unsigned)(k0 >> 32));
     const float thr = (sqrtf(mn) + 2.0f * rho) * 1.0001f;
     const float thr2 = thr * thr;
-    // dominance test against p_c: g(x) = |x-p|^2 - |x-p_c|^2 is linear in x, so its minimum over the
-    // cell is g(c) - h * (|dx|+|dy|+|dz|), d = p - p_c.  If that is > 0 (with a margin far above fp32
-    // rounding of any query's two distances) p_c beats p everywhere in the cell: p can never be a
-    // nearest neighbour of a query in this cell, nor tie with one.
-    const float4 pc = __ldg(tgt + amin);
+    // dominance test against a competitor p': g(x) = |x-p|^2 - |x-p'|^2 is linear in x, so its minimum over the
+    // cell is g(c) - h * (|dx|+|dy|+|dz|), d = p - p'.  If that is > 0 (with a margin far above fp32 rounding of
+    // any query's two distances) p' beats p everywhere in the cell: p can never be a nearest neighbour of a query
+    // in this cell, nor tie with one.  Competitors: the (up to) four targets nearest to the centre.
+    const unsigned long long ck[4] = {k0, k1, k2, k3};
+    float4 cp[4]; float cd[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const bool have = ck[c] != ~0ull;
+        cp[c] = __ldg(tgt + (have ? (unsigned)(ck[c] & 0xffffffffu) : 0u));
+        cd[c] = have ? __uint_as_float((unsigned)(ck[c] >> 32)) : __int_as_float(0x7f800000);   // +inf: never dominates
+    }
     const float hh = h * 1.002f * 1.0001f;
-    const float marg0 = 1e-5f * (mn + 4.0f * rho * rho);
+    const float rr4 = 4.0f * rho * rho;
     auto keep_test = [&](const float4& q, float d) -> bool {
         if (!(d <= thr2)) return false;
-        const float s = fabsf(q.x - pc.x) + fabsf(q.y - pc.y) + fabsf(q.z - pc.z);
-        return !((d - mn) - hh * s > marg0 + 1e-5f * d);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float s = fabsf(q.x - cp[c].x) + fabsf(q.y - cp[c].y) + fabsf(q.z - cp[c].z);
+            if ((d - cd[c]) - hh * s > 1e-5f * (d + cd[c] + rr4)) return false;
+        }
+        return true;
     };
     // ---- pass B: count (and remember) the candidates
     unsigned long long mask = 0ull;
