@@ -7,7 +7,20 @@ Algorithmic bytes: fp32 12 B/point, 4 B index, 4 B d2
   transform    : 12 N_s + 12 N_s
   iteration    : 76 N_s + 12 N_t  (= 88 MB at N_s = N_t = 1e6)
 """
+import json
+import os
+
 import numpy as np
+
+
+def _ncu_traffic():
+    """DRAM bytes per launch of the NN kernel from the committed ncu capture (profiles/), or None"""
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+    try:
+        k = json.load(open(p))["lg_nn_kernel<1>"]
+        return float(k["dram_bytes_read"] + k["dram_bytes_write"])
+    except Exception:
+        return None
 
 
 def icp_iteration_roofline(pkg, ctx, args, hbm_peak, which, stream=None):
@@ -64,7 +77,8 @@ def icp_iteration_roofline(pkg, ctx, args, hbm_peak, which, stream=None):
     cold_ms = float(np.median(cold))
     roofline = {"bound": "hbm", "kernel": "lg_nn_kernel<1> (1M-point correspondence search + fused transform)",
                 "achieved": nn_bytes / (nn_cold * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": nn_bytes / (nn_cold * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                "frac": nn_bytes / (nn_cold * 1e-3) / 1e9 / hbm_peak, "traffic": _ncu_traffic(),
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture summarised in profiles/r01_full_large_path_1m.md",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % which,
                 "algorithmic_bytes_per_launch": nn_bytes, "ms_per_launch": nn_cold,
                 "timing": "CUDA events on the launching stream around every launch, L2 flushed (256 MB write) before each iteration, 40 launches"}
