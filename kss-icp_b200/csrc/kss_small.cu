@@ -356,7 +356,7 @@ cg_level_kernel(int level, const float4* __restrict__ t_sorted, const int* __res
 // =============================================================== sweep_kernel
 // grid (G*G, P): CTA (i,j) of pair p applies Rx(i), Ry(j) once per point and loops Rz(k),
 // searching the exact NN of every rotated point (narrowed to float) in the Morton-tiled
-// target.  rbuf[p][orig][h] receives sqrt((double)d2) (score modes AVE/DIFF) or (double)d2
+// target.  rbuf[p][orig][h] receives (double)sqrtf(d2) (score modes AVE/DIFF) or (double)d2
 // (MAX); the serial sums are taken by sweep_finalize_kernel.
 __global__ void __launch_bounds__(256)
 sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int cap_s,
@@ -409,7 +409,7 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
             const unsigned long long key = use_cg ? cg_query<false>(cg, tgt, n_t, qx, qy, qz)
                                                   : warp_nn<false>(tv, qx, qy, qz);
             const float d2 = __uint_as_float((unsigned)(key >> 32));
-            const double r = score_mode == 1 ? (double)d2 : __dsqrt_rn((double)d2);
+            const double r = score_mode == 1 ? (double)d2 : (double)__fsqrt_rn(d2);   // float sqrt, then widened (:444)
             if (valid) ro[k] = r;
         }
     }

@@ -403,6 +403,249 @@ int icp_estimate(const float* cur, int n_s, const float* tgt, const NNIndex& nn,
 
 }  // namespace
 
+
+/* =========================================================== AIVS simplification
+ * Restates, with its quirks, the pre-processing that feeds the hot path:
+ *   pointPipeline_Border                      pointPipeline.hpp:105-158
+ *   BallRegion_EstimateBoxScale / _AchieveXYZ ballRegionCompute.hpp:1194-1214, 690-758
+ *   BallRegion_ReturnBoxCenter_Center         ballRegionCompute.hpp:1150-1172   (forgets the y wrap, B10)
+ *   BallRegion_BoxInput                       ballRegionCompute.hpp:632-688     (1-based boxes)
+ *   BallRegion_ReturnNeiborBox_Box            ballRegionCompute.hpp:975-1040    (forgets the x wrap, B10)
+ *   AIVS_initBoxIndexNumber                   Method_AIVS_SimPro.hpp:587-643    (8 colours)
+ *   AIVS_BoxSimplification_Points             Method_AIVS_SimPro.hpp:776-794    (quota, +1 if frac > 0.2)
+ *   AIVS_Voroni_OpenMP_KNN                    Method_AIVS_SimPro.hpp:222-376    (per-box farthest point sampling)
+ *   AIVS_AccurateCut_Optimization             Method_AIVS_SimPro.hpp:848-957    (greedy closest-pair trim, stale lists)
+ * kd-tree searches of the reference are exact, so they are replaced by plain scans; their only tie-dependent
+ * use is the K=3 list of the trim step, ordered here by (d2, index).  Distances are float d2 on float-narrowed
+ * coordinates, sqrt in float (float argument -> float overload), as in the reference. */
+namespace {
+
+struct Aivs {
+    int n; const double* P;
+    int nx, ny, nz; double unit; double mn[3];
+    std::vector<std::vector<int>> boxes;
+    std::vector<double> creal;       /* [boxes][3] */
+    std::vector<int> center;         /* position inside the box list of the point nearest the (quirky) centre */
+    int nbox() const { return (int)boxes.size(); }
+};
+
+int aivs_box_scale(int n) {
+    if (n < 10000) return 10;
+    if (n < 50000) return 20;
+    if (n < 100000) return 30;
+    if (n < 500000) return 40;
+    if (n < 1000000) return 50;
+    return (int)std::pow((double)n / 8.0, 1.0 / 3.0);
+}
+
+void aivs_center(const Aivs& a, int boxIndex, double c[3]) {
+    int z_num = boxIndex / (a.nx * a.ny) + 1;
+    int leveZ = boxIndex % (a.nx * a.ny);
+    int y_num = leveZ / a.nx + 1;
+    int x_num = leveZ % a.nx;
+    if (x_num == 0) { x_num = a.nx; y_num = y_num - 1; }
+    c[0] = (a.mn[0] + (x_num - 1) * a.unit + a.mn[0] + x_num * a.unit) / 2;
+    c[1] = (a.mn[1] + (y_num - 1) * a.unit + a.mn[1] + y_num * a.unit) / 2;
+    c[2] = (a.mn[2] + (z_num - 1) * a.unit + a.mn[2] + z_num * a.unit) / 2;
+}
+
+std::vector<int> aivs_neighbours(const Aivs& a, int boxIndex) {
+    int z_num = boxIndex / (a.nx * a.ny) + 1;
+    int leveZ = boxIndex % (a.nx * a.ny);
+    int y_num = leveZ / a.nx + 1;
+    int x_num = leveZ % a.nx;                                     /* no wrap fix here (B10) */
+    std::vector<int> xs, ys, zs, out;
+    if (x_num > 1) xs.push_back(x_num - 1);
+    xs.push_back(x_num);
+    if (x_num < a.nx) xs.push_back(x_num + 1);
+    if (y_num > 1) ys.push_back(y_num - 1);
+    ys.push_back(y_num);
+    if (y_num < a.ny) ys.push_back(y_num + 1);
+    if (z_num > 1) zs.push_back(z_num - 1);
+    zs.push_back(z_num);
+    if (z_num < a.nz) zs.push_back(z_num + 1);
+    for (int xi : xs) for (int yj : ys) for (int zk : zs) {
+        if (xi == x_num && yj == y_num && zk == z_num) continue;
+        int idx = xi + (yj - 1) * a.nx + (zk - 1) * a.nx * a.ny;
+        if (idx < a.nbox()) out.push_back(idx);
+    }
+    return out;
+}
+
+}  // namespace
+
+extern "C" int okss_aivs_simplify(const double* pts, int n, int pointNum, double* out, int32_t* out_idx) {
+    if (n < 1) return 0;
+    Aivs a; a.n = n; a.P = pts;
+    /* pointPipeline_Border: first index of each strict extreme */
+    int imin[3] = {0, 0, 0}, imax[3] = {0, 0, 0};
+    double vmin[3] = {pts[0], pts[1], pts[2]}, vmax[3] = {pts[0], pts[1], pts[2]};
+    for (int i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d) {
+            double v = pts[3 * i + d];
+            if (v < vmin[d]) { vmin[d] = v; imin[d] = i; }
+            if (v > vmax[d]) { vmax[d] = v; imax[d] = i; }
+        }
+    const int boxNum = aivs_box_scale(n);
+    for (int d = 0; d < 3; ++d) a.mn[d] = pts[3 * imin[d] + d];
+    double dis[3];
+    for (int d = 0; d < 3; ++d) dis[d] = std::fabs(pts[3 * imax[d] + d] - a.mn[d]);
+    double large = dis[0];
+    if (large < dis[1]) large = dis[1];
+    if (large < dis[2]) large = dis[2];
+    a.unit = large / double(boxNum);
+    int num[3];
+    for (int d = 0; d < 3; ++d) {
+        double nd = dis[d] / a.unit;
+        num[d] = (int)nd;
+        if (nd > (double)num[d]) num[d]++;
+    }
+    a.nx = num[0]; a.ny = num[1]; a.nz = num[2];
+    a.boxes.assign((size_t)a.nx * a.ny * a.nz + 1, std::vector<int>());
+    a.creal.resize(3 * a.boxes.size());
+    for (int b = 0; b < a.nbox(); ++b) aivs_center(a, b, &a.creal[3 * b]);
+    /* BallRegion_BoxInput */
+    std::vector<double> cmin(a.boxes.size(), 9999);
+    a.center.assign(a.boxes.size(), -1);
+    for (int i = 0; i < n; ++i) {
+        int id[3];
+        for (int d = 0; d < 3; ++d) {
+            double v = (pts[3 * i + d] - a.mn[d]) / a.unit;
+            id[d] = (int)v;
+            if (id[d] < v || id[d] == 0) id[d]++;
+        }
+        int b = id[0] + a.nx * (id[1] - 1) + (a.nx * a.ny * (id[2] - 1));
+        if (b < 0 || b >= a.nbox()) continue;                         /* the reference only prints "Hello!" (UB) */
+        const double* c = &a.creal[3 * b];
+        double dm = std::sqrt((c[0] - pts[3 * i]) * (c[0] - pts[3 * i]) + (c[1] - pts[3 * i + 1]) * (c[1] - pts[3 * i + 1]) +
+                              (c[2] - pts[3 * i + 2]) * (c[2] - pts[3 * i + 2]));
+        a.boxes[b].push_back(i);
+        if (cmin[b] > dm) { cmin[b] = dm; a.center[b] = (int)a.boxes[b].size() - 1; }
+    }
+    /* AIVS_initBoxIndexNumber: colours in x-outer, y, z-inner loop order */
+    std::vector<int> colour[8];
+    for (int i = 1; i <= a.nx; ++i)
+        for (int j = 1; j <= a.ny; ++j)
+            for (int k = 1; k <= a.nz; ++k) {
+                int b = i + a.nx * (j - 1) + (a.nx * a.ny * (k - 1));
+                if (a.boxes[b].empty()) continue;
+                int c;
+                if (i % 2 == 1 && j % 2 == 1 && k % 2 == 1) c = 0;
+                else if (i % 2 == 0 && j % 2 == 1 && k % 2 == 1) c = 1;
+                else if (i % 2 == 0 && j % 2 == 0 && k % 2 == 1) c = 2;
+                else if (i % 2 == 1 && j % 2 == 0 && k % 2 == 1) c = 3;
+                else if (i % 2 == 1 && j % 2 == 1 && k % 2 == 0) c = 4;
+                else if (i % 2 == 0 && j % 2 == 1 && k % 2 == 0) c = 5;
+                else if (i % 2 == 0 && j % 2 == 0 && k % 2 == 0) c = 6;
+                else c = 7;
+                colour[c].push_back(b);
+            }
+    /* quotas */
+    const double rate = (double)pointNum / (double)n;
+    std::vector<int> quota(a.boxes.size(), 0);
+    for (int b = 0; b < a.nbox(); ++b) {
+        double sb = (double)a.boxes[b].size() * rate;
+        int t = (int)sb;
+        quota[b] = (sb - t > 0.2) ? t + 1 : t;
+    }
+    std::vector<int> labelG(n, 1);
+    std::vector<std::vector<int>> simiT(a.boxes.size());
+    for (int b = 0; b < a.nbox(); ++b) simiT[b].assign(a.boxes[b].size(), -1);
+    const double radius = a.unit * 3.0 / 4.0;
+    std::vector<float> pf;
+    for (int c = 0; c < 8; ++c)
+        for (int b : colour[c]) {
+            const int simNum = quota[b];
+            if (simNum == 0) continue;
+            const double* pc = &a.creal[3 * b];
+            std::vector<int> pointTemp = a.boxes[b];
+            std::vector<int> labelTemp(pointTemp.size(), 1);
+            bool addJ = true;
+            for (int nb : aivs_neighbours(a, b))
+                for (int pt : a.boxes[nb]) {
+                    const double* q = pts + 3 * pt;
+                    if (q[0] <= pc[0] + radius && q[0] >= pc[0] - radius && q[1] <= pc[1] + radius && q[1] >= pc[1] - radius &&
+                        q[2] <= pc[2] + radius && q[2] >= pc[2] - radius && labelG[pt] == 0) {
+                        pointTemp.push_back(pt); labelTemp.push_back(2); addJ = false;
+                    }
+                }
+            if (addJ && a.center[b] >= 0 && a.center[b] < (int)pointTemp.size()) labelTemp[a.center[b]] = 0;
+            const int m = (int)pointTemp.size();
+            pf.resize(3 * (size_t)m);
+            for (int k = 0; k < m; ++k) for (int d = 0; d < 3; ++d) pf[3 * k + d] = (float)pts[3 * pointTemp[k] + d];
+            int sampled = 0;
+            std::vector<double> mind(m, -1);
+            for (int k = 0; k < m; ++k) {
+                if (labelTemp[k] == 0) {
+                    mind[k] = 0; simiT[b][sampled] = pointTemp[k]; labelG[pointTemp[k]] = 0; sampled++;
+                } else if (labelTemp[k] == 2) {
+                    mind[k] = 0;
+                } else {
+                    double minTemp = 9999;
+                    float best = std::numeric_limits<float>::infinity();
+                    for (int l = 0; l < m; ++l)
+                        if (labelTemp[l] == 0 || labelTemp[l] == 2) best = std::min(best, dist2f(&pf[3 * k], &pf[3 * l]));
+                    if (best != std::numeric_limits<float>::infinity()) minTemp = (double)std::sqrt(best);
+                    mind[k] = minTemp;
+                }
+            }
+            while (sampled < simNum) {
+                int sel = -1; double mx = 0;
+                for (int k = 0; k < m; ++k) if (labelTemp[k] == 1 && mind[k] > mx) { sel = k; mx = mind[k]; }
+                if (sel == -1) break;
+                mind[sel] = 0; labelG[pointTemp[sel]] = 0; simiT[b][sampled] = pointTemp[sel]; sampled++;
+                for (int k = 0; k < m; ++k)
+                    if (labelTemp[k] == 1) {
+                        double d = (double)std::sqrt(dist2f(&pf[3 * sel], &pf[3 * k]));
+                        if (d < mind[k]) mind[k] = d;
+                    }
+            }
+        }
+    /* AIVS_AccurateCut_Optimization */
+    std::vector<int> sample;
+    for (int b = 0; b < a.nbox(); ++b)
+        for (int v : simiT[b]) { if (v == -1) break; sample.push_back(v); }
+    const int S = (int)sample.size();
+    int dTiff = S - pointNum;
+    std::vector<char> keep(S, 1);
+    if (dTiff > 0 && S >= 3) {
+        std::vector<float> sf(3 * (size_t)S);
+        for (int i = 0; i < S; ++i) for (int d = 0; d < 3; ++d) sf[3 * i + d] = (float)pts[3 * sample[i] + d];
+        std::vector<int> nidx(3 * (size_t)S);
+        std::vector<float> ndis(3 * (size_t)S);
+        for (int i = 0; i < S; ++i) {                                   /* K = 3, ascending (d2, index) */
+            float bd[3] = {INFINITY, INFINITY, INFINITY}; int bi[3] = {-1, -1, -1};
+            for (int j = 0; j < S; ++j) {
+                float d = dist2f(&sf[3 * i], &sf[3 * j]);
+                int jj = j;
+                for (int r = 0; r < 3; ++r)
+                    if (better(d, jj, bd[r], bi[r] < 0 ? INT32_MAX : bi[r])) { std::swap(d, bd[r]); std::swap(jj, bi[r]); }
+            }
+            for (int r = 0; r < 3; ++r) { nidx[3 * i + r] = bi[r]; ndis[3 * i + r] = std::sqrt(bd[r]); }
+        }
+        while (dTiff > 0) {
+            double mn = 9999; int b1 = -1, b2 = -1;
+            for (int i = 0; i < S; ++i) {
+                int b2t = nidx[3 * i + 1];
+                double dt = ndis[3 * i + 1];
+                if (dt < mn && keep[i] && keep[b2t]) { mn = dt; b1 = i; b2 = b2t; }
+            }
+            if (mn == 9999 || b1 == -1 || b2 == -1) break;
+            int del = b1;
+            if ((double)ndis[3 * b1 + 2] > (double)ndis[3 * b2 + 2]) del = b2;
+            keep[del] = 0; dTiff--;
+        }
+    }
+    int m = 0;
+    for (int i = 0; i < S; ++i)
+        if (keep[i]) {
+            if (out) for (int d = 0; d < 3; ++d) out[3 * m + d] = pts[3 * sample[i] + d];
+            if (out_idx) out_idx[m] = sample[i];
+            ++m;
+        }
+    return m;
+}
+
 /* ===================================================================== API */
 
 extern "C" {
@@ -493,7 +736,10 @@ static double score_cloud(const std::vector<double>& pts, int n_s, const NNIndex
             double di = bd;
             if (di > dmax) dmax = di;
         } else {
-            double di = std::sqrt((double)bd);
+            /* `sqrt(pointNKNSquaredDistance[0])` has a float argument: with <math.h> + `using namespace std`
+             * overload resolution picks float sqrt(float) (MSVC and GCC alike); the result is widened afterwards
+             * (initRegistrationKSS.hpp:444, 468) */
+            double di = (double)std::sqrt(bd);
             sum = sum + di;
             if (dmax < di) dmax = di;
         }

@@ -158,6 +158,12 @@ int okss_icp_iteration(const float* src, int n_s, const float* tgt, int n_t,
                        int32_t* idx, float* d2, float T_k[16], double* mse,
                        float* src_out /* transformed, or NULL */);
 
+/* AIVS simplification + BallRegion voxel grid (the step before the hot path):
+ * pointPipeline_init_point_withoutUniform + AIVS_Pro_init + AIVS_simplification(pointNum)
+ * (KSS_ICP.hpp:71-81).  out [<= n][3], out_idx original indices (either may be NULL); returns the count,
+ * which can be below pointNum (B9). */
+int okss_aivs_simplify(const double* pts, int n, int pointNum, double* out, int32_t* out_idx);
+
 /* canonical sums exposed for tests */
 float  okss_canon_sum_f32(const float* v, int n);
 double okss_canon_sum_f64(const double* v, int n);

@@ -179,6 +179,14 @@ def svd3(A):
     return U.reshape(3, 3), s, V.reshape(3, 3)
 
 
+def aivs_simplify(pts, point_num):
+    """AIVS_simplification(pointNum) on the BallRegion of `pts`: returns (points [m,3], original indices [m])"""
+    pts = _f64(pts)
+    out = np.empty_like(pts); idx = np.empty(len(pts), np.int32)
+    m = lib().okss_aivs_simplify(_p(pts), C.c_int(len(pts)), C.c_int(point_num), _p(out), _p(idx))
+    return out[:m].copy(), idx[:m].copy()
+
+
 def canon_sum_f32(v):
     v = _f32(v); return float(lib().okss_canon_sum_f32(_p(v), C.c_int(len(v))))
 
