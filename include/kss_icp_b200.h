@@ -118,7 +118,8 @@ long long kss_ctx_launch_count(kss_ctx* ctx);
 #define KSS_STAGE_LARGE_NN        8   /* large path: hierarchical NN kernel           */
 #define KSS_STAGE_LARGE_REDUCE    9   /* large path: canonical reductions + SVD       */
 #define KSS_STAGE_CG_BUILD       10   /* candidate grid build (per pair, once)         */
-#define KSS_STAGE_COUNT          11
+#define KSS_STAGE_AIVS           11   /* AIVS simplification of raw clouds             */
+#define KSS_STAGE_COUNT          12
 int kss_ctx_set_timing(kss_ctx* ctx, int enable);      /* also resets the accumulators */
 int kss_ctx_stage_ms(kss_ctx* ctx, int stage, double* ms, long long* calls);
 
@@ -169,7 +170,31 @@ int kss_nn_metrics(kss_ctx* ctx, const double* a, int n_a, const double* t, int 
 int kss_nn_search(kss_ctx* ctx, const double* q, int n_q, const double* t, int n_t,
                   int32_t* idx, float* d2);
 
-/* ---- batched registration (KSSICP_Registration after simplification + PCR_QM) --------- */
+/* ---- AIVS simplification (the step in front of the path) --------------- */
+
+/* replaces pointPipeline_init_point_withoutUniform + AIVS_Pro_init + AIVS_simplification(pointNum)
+ * (pointPipeline.hpp:62-103, Method_AIVS_SimPro.hpp:66-123, called at KSS_ICP.hpp:72-82): out [out_cap][3]
+ * receives the simplified cloud (out_cap >= point_num suffices), *out_n its size, out_idx (optional) the
+ * position of every kept point in `pts`.  n >= 1; clouds with zero extent are KSS_ERR_UNSUPPORTED. */
+int kss_aivs_simplify(kss_ctx* ctx, const double* pts, int n, int point_num, double* out, int out_cap,
+                      int* out_n, int32_t* out_idx);
+
+/* many clouds at once: pts [n_clouds][cap][3], cnt (optional) their sizes, point_num_each (optional,
+ * else point_num for all); out [n_clouds][out_cap][3], out_cnt [n_clouds], out_idx optional */
+int kss_aivs_simplify_batch(kss_ctx* ctx, int n_clouds, const double* pts, const int* cnt, int cap,
+                            const int* point_num_each, int point_num, double* out, int out_cap,
+                            int* out_cnt, int32_t* out_idx);
+/* the same on device pointers, enqueued on ctx's stream; kss_aivs_status() afterwards synchronizes
+ * and reports a cloud the simplification could not handle */
+int kss_aivs_simplify_batch_device(kss_ctx* ctx, int n_clouds, const double* d_pts, const int* d_cnt, int cap,
+                                   const int* d_point_num, int point_num, double* d_out, int out_cap,
+                                   int* d_out_cnt, int32_t* d_out_idx);
+int kss_aivs_status(kss_ctx* ctx);
+
+/* ---- batched registration (KSSICP_Registration + PCR_QM) -------------------------------- */
+/* kss_batch.sim_s == sim_t == NULL selects the whole of KSSICP_Registration (KSS_ICP.hpp:70-130): the
+ * library computes pNumber = min(|S|,|T|)/2 (<= 2000) per pair and simplifies both clouds with AIVS on the
+ * device; cap_s / cap_t / cnt_s / cnt_t are ignored.  Otherwise the given simplified clouds are used. */
 
 /* host buffers in, host results out (H2D/D2H inside). point_align [n_pairs][cap_S][3] optional. */
 int kss_register_batch(kss_ctx* ctx, const kss_batch* b, kss_pair_result* results, double* point_align);

@@ -19,7 +19,7 @@ KSS_OK = 0
 SMALL_MAX = 2048
 SCORE_AVE, SCORE_MAX, SCORE_DIFF = 0, 1, 2
 STAGES = ("prep", "sweep", "sweep_finalize", "icp_judge", "icp_hyp", "select_apply", "metrics",
-          "large_build", "large_nn", "large_reduce", "cg_build")
+          "large_build", "large_nn", "large_reduce", "cg_build", "aivs")
 
 
 class KssError(RuntimeError):
@@ -217,19 +217,51 @@ class Context:
 
     def register_batch(self, sim_s, sim_t, full_s, full_t, step=8.0, max_iter=1000, counts=None,
                        want_points=False, judge_threshold=0.0005, results=None):
-        """host arrays [P, cap, 3] float64 (numpy; pinned memory makes the copies asynchronous)"""
-        ss = _f64(sim_s); st = _f64(sim_t); fs = _f64(full_s); ft = _f64(full_t)
-        P = ss.shape[0]
+        """host arrays [P, cap, 3] float64 (numpy; pinned memory makes the copies asynchronous).
+        sim_s = sim_t = None: the library simplifies full_s / full_t itself (AIVS, pNumber rule)."""
+        fs = _f64(full_s); ft = _f64(full_t)
+        raw = sim_s is None
+        ss = None if raw else _f64(sim_s); st = None if raw else _f64(sim_t)
+        P = fs.shape[0]
         cn = [None] * 4
         if counts is not None:
             cn = [np.ascontiguousarray(c, np.int32) if c is not None else None for c in counts]
-        b = self._batch(P, (ss.shape[1], st.shape[1], fs.shape[1], ft.shape[1]),
-                        (_p(ss).value, _p(st).value, _p(fs).value, _p(ft).value),
+        b = self._batch(P, (0 if raw else ss.shape[1], 0 if raw else st.shape[1], fs.shape[1], ft.shape[1]),
+                        (None if raw else _p(ss).value, None if raw else _p(st).value, _p(fs).value, _p(ft).value),
                         tuple((_p(c).value if c is not None else None) for c in cn), step, max_iter, judge_threshold)
         res = results if results is not None else np.zeros(P, RESULT_DTYPE)
         pa = np.empty_like(fs) if want_points else None
         self._ck(self.lib.kss_register_batch(self.h, C.byref(b), _p(res), _p(pa)))
         return (res, pa) if want_points else res
+
+    def aivs_simplify_batch(self, pts, point_num, counts=None, want_index=True):
+        """pts [P, cap, 3] float64; point_num int or [P] ints -> (out [P, out_cap, 3], out_cnt [P], out_idx [P, out_cap])"""
+        pts = _f64(pts); P, cap = pts.shape[0], pts.shape[1]
+        each = None if np.isscalar(point_num) else np.ascontiguousarray(point_num, np.int32)
+        out_cap = int(point_num if each is None else each.max())
+        out_cap = max(out_cap, 3)
+        cn = None if counts is None else np.ascontiguousarray(counts, np.int32)
+        out = np.zeros((P, out_cap, 3), np.float64); ocnt = np.zeros(P, np.int32)
+        oidx = np.full((P, out_cap), -1, np.int32) if want_index else None
+        self._ck(self.lib.kss_aivs_simplify_batch(self.h, C.c_int(P), _p(pts), _p(cn), C.c_int(cap), _p(each),
+                                                  C.c_int(0 if each is not None else int(point_num)), _p(out),
+                                                  C.c_int(out_cap), _p(ocnt), _p(oidx)))
+        return out, ocnt, oidx
+
+    def aivs_simplify(self, pts, point_num):
+        """AIVS_simplification(point_num) of one cloud: (points [m, 3], positions in pts [m])"""
+        out, cnt, idx = self.aivs_simplify_batch(_f64(pts)[None], int(point_num))
+        return out[0, :cnt[0]].copy(), idx[0, :cnt[0]].copy()
+
+    def aivs_simplify_batch_device(self, P, d_pts, cap, point_num, d_out, out_cap, d_out_cnt, d_cnt=None, d_point_num=None,
+                                   d_out_idx=None):
+        self._ck(self.lib.kss_aivs_simplify_batch_device(self.h, C.c_int(P), C.c_void_p(d_pts), C.c_void_p(d_cnt or 0),
+                                                         C.c_int(cap), C.c_void_p(d_point_num or 0), C.c_int(point_num),
+                                                         C.c_void_p(d_out), C.c_int(out_cap), C.c_void_p(d_out_cnt),
+                                                         C.c_void_p(d_out_idx or 0)))
+
+    def aivs_status(self):
+        self._ck(self.lib.kss_aivs_status(self.h))
 
     def register_batch_device(self, P, caps, dev_ptrs, d_results, d_point_align=None, dev_counts=(None,) * 4,
                               step=8.0, max_iter=1000, judge_threshold=0.0005):

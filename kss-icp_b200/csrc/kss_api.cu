@@ -12,6 +12,7 @@
 
 #include "kss_kernels.h"
 #include "kss_large.h"
+#include "kss_aivs.h"
 
 using namespace kss;
 
@@ -32,6 +33,7 @@ struct kss_ctx {
     std::map<std::string, Buf> bufs;
     size_t ws_budget = (size_t)48 << 30;
     int slots_override = 0;
+    int* aivs_bad = nullptr;          // device flag written by the last raw-cloud batch (kss_aivs.h)
     // optional per-stage CUDA-event timing (bench.py roofline): events on the launching stream
     bool timing = false;
     struct Span { int stage; cudaEvent_t a, b; };
@@ -303,9 +305,14 @@ size_t per_pair_ws_bytes(const kss_batch& b, int H, int slots) {
 
 int check_batch(kss_ctx* ctx, const kss_batch* b) {
     if (!ctx) return KSS_ERR_ARG;
-    if (!b || b->n_pairs < 1 || !b->sim_s || !b->sim_t || !b->full_s || !b->full_t)
+    if (!b || b->n_pairs < 1 || !b->full_s || !b->full_t || (!b->sim_s) != (!b->sim_t))
         return fail(ctx, KSS_ERR_ARG, "kss_batch: null pointer or n_pairs < 1");
-    if (b->cap_s < 1 || b->cap_t < 1 || b->cap_S < 1 || b->cap_T < 1) return fail(ctx, KSS_ERR_ARG, "kss_batch: empty cloud");
+    if (b->cap_S < 1 || b->cap_T < 1) return fail(ctx, KSS_ERR_ARG, "kss_batch: empty cloud");
+    if (!b->sim_s) {                                   // raw clouds: the library runs AIVS itself
+        if (b->cap_S < 4 || b->cap_T < 4) return fail(ctx, KSS_ERR_ARG, "kss_batch: raw clouds need at least 4 points");
+        return KSS_OK;
+    }
+    if (b->cap_s < 1 || b->cap_t < 1) return fail(ctx, KSS_ERR_ARG, "kss_batch: empty cloud");
     if (b->cap_s > SMALL_MAX || b->cap_t > SMALL_MAX)
         return fail(ctx, KSS_ERR_UNSUPPORTED, "simplified clouds must have <= 2048 points (reference caps pNumber at 2000)");
     return KSS_OK;
@@ -664,10 +671,14 @@ int kss_nn_metrics(kss_ctx* ctx, const double* a, int n_a, const double* t, int 
     return nn_common(ctx, a, n_a, t, n_t, 1, nullptr, nullptr, out3);
 }
 
-int kss_register_batch_device(kss_ctx* ctx, const kss_batch* b, kss_pair_result* d_results, double* d_point_align) {
-    int r = check_batch(ctx, b); if (r) return r;
+int kss_register_batch_device(kss_ctx* ctx, const kss_batch* b_in, kss_pair_result* d_results, double* d_point_align) {
+    int r = check_batch(ctx, b_in); if (r) return r;
     if (!d_results) return fail(ctx, KSS_ERR_ARG, "kss_register_batch_device: null results");
     CU(cudaSetDevice(ctx->device));
+    kss_batch bb = *b_in;
+    const kss_batch* b = &bb;
+    const bool raw = !bb.sim_s;
+    if (raw) bb.cap_s = bb.cap_t = std::min(2000, std::min(bb.cap_S, bb.cap_T) / 2);     // pNumber, KSS_ICP.hpp:53-67
     r = ensure_trig(ctx, b->step); if (r) return r;
     const int H = ctx->G * ctx->G * ctx->G;
     int slots = 32;
@@ -675,56 +686,93 @@ int kss_register_batch_device(kss_ctx* ctx, const kss_batch* b, kss_pair_result*
     if (es && atoi(es) > 0) slots = atoi(es);
     if (ctx->slots_override > 0) slots = ctx->slots_override;
     if (slots > H) slots = H;
-    const size_t per = per_pair_ws_bytes(*b, H, slots);
+    const size_t per = per_pair_ws_bytes(*b, H, slots) + (raw ? (size_t)(b->cap_S + b->cap_T) * 64 + 65536 : 0);
     int chunk = (int)std::min<size_t>((size_t)b->n_pairs, std::max<size_t>(1, ctx->ws_budget / per));
+    auto alloc = [&](const char* name, size_t bytes, void** out) {
+        unsigned char* q; int rr = dev_buf(ctx, name, bytes, &q); *out = q; return rr; };
     for (int p0 = 0; p0 < b->n_pairs; p0 += chunk) {
         const int P = std::min(chunk, b->n_pairs - p0);
         const int *c_s, *c_t, *c_S, *c_T;
-        r = counts_or_fill(ctx, "cnt_s", b->cnt_s ? b->cnt_s + p0 : nullptr, P, b->cap_s, &c_s); if (r) return r;
-        r = counts_or_fill(ctx, "cnt_t", b->cnt_t ? b->cnt_t + p0 : nullptr, P, b->cap_t, &c_t); if (r) return r;
         r = counts_or_fill(ctx, "cnt_S", b->cnt_S ? b->cnt_S + p0 : nullptr, P, b->cap_S, &c_S); if (r) return r;
         r = counts_or_fill(ctx, "cnt_T", b->cnt_T ? b->cnt_T + p0 : nullptr, P, b->cap_T, &c_T); if (r) return r;
-        r = pipeline_device(ctx, P, *b, b->sim_s + (size_t)p0 * b->cap_s * 3, b->sim_t + (size_t)p0 * b->cap_t * 3,
-                            b->full_s + (size_t)p0 * b->cap_S * 3, b->full_t + (size_t)p0 * b->cap_T * 3, c_s, c_t, c_S,
-                            c_T, slots, d_results + p0,
+        const double* full_s = b->full_s + (size_t)p0 * b->cap_S * 3;
+        const double* full_t = b->full_t + (size_t)p0 * b->cap_T * 3;
+        const double *sim_s, *sim_t;
+        if (raw) {
+            // KSSICP_Registration's first half (KSS_ICP.hpp:72-84): AIVS_simplification(pNumber) of target and source
+            StageTimer tm(ctx, KSS_STAGE_AIVS);
+            double *d_ss, *d_st; int *d_pn, *d_cs, *d_ct, *d_bad;
+            BUF("aivs_sim_s", (size_t)P * b->cap_s * 3, &d_ss); BUF("aivs_sim_t", (size_t)P * b->cap_t * 3, &d_st);
+            BUF("aivs_pn", P, &d_pn); BUF("aivs_cnt_s", P, &d_cs); BUF("aivs_cnt_t", P, &d_ct);
+            BUF("aivs_bad", 1, &d_bad);
+            if (p0 == 0) CU(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+            r = aivs_pnumber_device(ctx->stream, &ctx->launches, P, c_S, b->cap_S, c_T, b->cap_T, d_pn);
+            if (!r) r = aivs_simplify_device(ctx->stream, &ctx->launches, P, full_t, c_T, b->cap_T, d_pn, 0, d_st, b->cap_t, d_ct,
+                                             nullptr, d_bad, alloc, "t");
+            if (!r) r = aivs_simplify_device(ctx->stream, &ctx->launches, P, full_s, c_S, b->cap_S, d_pn, 0, d_ss, b->cap_s, d_cs,
+                                             nullptr, d_bad, alloc, "s");
+            if (r) return fail(ctx, r, "AIVS simplification failed to launch");
+            sim_s = d_ss; sim_t = d_st; c_s = d_cs; c_t = d_ct;
+            ctx->aivs_bad = d_bad;
+        } else {
+            r = counts_or_fill(ctx, "cnt_s", b->cnt_s ? b->cnt_s + p0 : nullptr, P, b->cap_s, &c_s); if (r) return r;
+            r = counts_or_fill(ctx, "cnt_t", b->cnt_t ? b->cnt_t + p0 : nullptr, P, b->cap_t, &c_t); if (r) return r;
+            sim_s = b->sim_s + (size_t)p0 * b->cap_s * 3; sim_t = b->sim_t + (size_t)p0 * b->cap_t * 3;
+        }
+        r = pipeline_device(ctx, P, *b, sim_s, sim_t, full_s, full_t, c_s, c_t, c_S, c_T, slots, d_results + p0,
                             d_point_align ? d_point_align + (size_t)p0 * b->cap_S * 3 : nullptr);
         if (r) return r;
     }
     return KSS_OK;
 }
 
+namespace {
+int aivs_status(kss_ctx* ctx, int bad) {
+    if (bad == 1) return fail(ctx, KSS_ERR_UNSUPPORTED, "AIVS: a cloud has zero extent or needs more boxes than its point count allows");
+    if (bad == 2) return fail(ctx, KSS_ERR_UNSUPPORTED, "AIVS: more than 16384 samples before the trim step");
+    if (bad == 3) return fail(ctx, KSS_ERR_UNSUPPORTED, "AIVS: output capacity too small");
+    return KSS_OK;
+}
+}  // namespace
+
 int kss_register_batch(kss_ctx* ctx, const kss_batch* b, kss_pair_result* results, double* point_align) {
     int r = check_batch(ctx, b); if (r) return r;
     if (!results) return fail(ctx, KSS_ERR_ARG, "kss_register_batch: null results");
     CU(cudaSetDevice(ctx->device));
     const int P = b->n_pairs;
-    double *d_ss, *d_st, *d_fs, *d_ft, *d_pa = nullptr; kss_pair_result* d_res;
+    const bool raw = !b->sim_s;
+    double *d_ss = nullptr, *d_st = nullptr, *d_fs, *d_ft, *d_pa = nullptr; kss_pair_result* d_res;
     int *d_cs = nullptr, *d_ct = nullptr, *d_cS = nullptr, *d_cT = nullptr;
-    BUF("in_sim_s", (size_t)P * b->cap_s * 3, &d_ss); BUF("in_sim_t", (size_t)P * b->cap_t * 3, &d_st);
+    if (!raw) { BUF("in_sim_s", (size_t)P * b->cap_s * 3, &d_ss); BUF("in_sim_t", (size_t)P * b->cap_t * 3, &d_st); }
     BUF("in_full_s", (size_t)P * b->cap_S * 3, &d_fs); BUF("in_full_t", (size_t)P * b->cap_T * 3, &d_ft);
     BUF("out_res", (size_t)P, &d_res);
     if (point_align) BUF("out_pa", (size_t)P * b->cap_S * 3, &d_pa);
     cudaStream_t st = ctx->stream;
-    CU(cudaMemcpyAsync(d_ss, b->sim_s, sizeof(double) * 3 * (size_t)P * b->cap_s, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_st, b->sim_t, sizeof(double) * 3 * (size_t)P * b->cap_t, cudaMemcpyHostToDevice, st));
+    if (!raw) {
+        CU(cudaMemcpyAsync(d_ss, b->sim_s, sizeof(double) * 3 * (size_t)P * b->cap_s, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_st, b->sim_t, sizeof(double) * 3 * (size_t)P * b->cap_t, cudaMemcpyHostToDevice, st));
+    }
     CU(cudaMemcpyAsync(d_fs, b->full_s, sizeof(double) * 3 * (size_t)P * b->cap_S, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_ft, b->full_t, sizeof(double) * 3 * (size_t)P * b->cap_T, cudaMemcpyHostToDevice, st));
     kss_batch db = *b;
     db.sim_s = d_ss; db.sim_t = d_st; db.full_s = d_fs; db.full_t = d_ft;
-    if (b->cnt_s) { BUF("in_cnt_s", P, &d_cs); CU(cudaMemcpyAsync(d_cs, b->cnt_s, sizeof(int) * P, cudaMemcpyHostToDevice, st)); db.cnt_s = d_cs; }
-    if (b->cnt_t) { BUF("in_cnt_t", P, &d_ct); CU(cudaMemcpyAsync(d_ct, b->cnt_t, sizeof(int) * P, cudaMemcpyHostToDevice, st)); db.cnt_t = d_ct; }
+    if (!raw && b->cnt_s) { BUF("in_cnt_s", P, &d_cs); CU(cudaMemcpyAsync(d_cs, b->cnt_s, sizeof(int) * P, cudaMemcpyHostToDevice, st)); db.cnt_s = d_cs; }
+    if (!raw && b->cnt_t) { BUF("in_cnt_t", P, &d_ct); CU(cudaMemcpyAsync(d_ct, b->cnt_t, sizeof(int) * P, cudaMemcpyHostToDevice, st)); db.cnt_t = d_ct; }
     if (b->cnt_S) { BUF("in_cnt_S", P, &d_cS); CU(cudaMemcpyAsync(d_cS, b->cnt_S, sizeof(int) * P, cudaMemcpyHostToDevice, st)); db.cnt_S = d_cS; }
     if (b->cnt_T) { BUF("in_cnt_T", P, &d_cT); CU(cudaMemcpyAsync(d_cT, b->cnt_T, sizeof(int) * P, cudaMemcpyHostToDevice, st)); db.cnt_T = d_cT; }
     r = kss_register_batch_device(ctx, &db, d_res, d_pa); if (r) return r;
+    int bad = 0;
+    if (raw) CU(cudaMemcpyAsync(&bad, ctx->aivs_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(results, d_res, sizeof(kss_pair_result) * (size_t)P, cudaMemcpyDeviceToHost, st));
     if (point_align) CU(cudaMemcpyAsync(point_align, d_pa, sizeof(double) * 3 * (size_t)P * b->cap_S, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (bad) return aivs_status(ctx, bad);
     // pairs whose local-minimum list exceeded the hypothesis slots: re-run alone with enough slots
     for (int p = 0; p < P; ++p) {
         if (!results[p].overflow) continue;
         kss_batch one = db;
         one.n_pairs = 1;
-        one.sim_s = d_ss + (size_t)p * b->cap_s * 3; one.sim_t = d_st + (size_t)p * b->cap_t * 3;
+        if (!raw) { one.sim_s = d_ss + (size_t)p * b->cap_s * 3; one.sim_t = d_st + (size_t)p * b->cap_t * 3; }
         one.full_s = d_fs + (size_t)p * b->cap_S * 3; one.full_t = d_ft + (size_t)p * b->cap_T * 3;
         one.cnt_s = db.cnt_s ? db.cnt_s + p : nullptr; one.cnt_t = db.cnt_t ? db.cnt_t + p : nullptr;
         one.cnt_S = db.cnt_S ? db.cnt_S + p : nullptr; one.cnt_T = db.cnt_T ? db.cnt_T + p : nullptr;
@@ -740,6 +788,64 @@ int kss_register_batch(kss_ctx* ctx, const kss_batch* b, kss_pair_result* result
         results[p].overflow = 1;
     }
     return KSS_OK;
+}
+
+int kss_aivs_simplify_batch_device(kss_ctx* ctx, int n_clouds, const double* d_pts, const int* d_cnt, int cap,
+                                   const int* d_point_num, int point_num, double* d_out, int out_cap, int* d_out_cnt,
+                                   int32_t* d_out_idx) {
+    if (!ctx) return KSS_ERR_ARG;
+    if (n_clouds < 1 || !d_pts || cap < 1 || !d_out || !d_out_cnt || out_cap < 1 || (!d_point_num && point_num < 1))
+        return fail(ctx, KSS_ERR_ARG, "kss_aivs_simplify_batch_device: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    auto alloc = [&](const char* name, size_t bytes, void** out) {
+        unsigned char* q; int rr = dev_buf(ctx, name, bytes, &q); *out = q; return rr; };
+    int* d_bad;
+    BUF("aivs_bad", 1, &d_bad);
+    CU(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+    ctx->aivs_bad = d_bad;
+    StageTimer tm(ctx, KSS_STAGE_AIVS);
+    int r = aivs_simplify_device(ctx->stream, &ctx->launches, n_clouds, d_pts, d_cnt, cap, d_point_num, point_num, d_out,
+                                 out_cap, d_out_cnt, d_out_idx, d_bad, alloc, "u");
+    if (r) return fail(ctx, r, "AIVS simplification failed to launch");
+    return KSS_OK;
+}
+
+int kss_aivs_status(kss_ctx* ctx) {
+    if (!ctx) return KSS_ERR_ARG;
+    if (!ctx->aivs_bad) return KSS_OK;
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, ctx->aivs_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return aivs_status(ctx, bad);
+}
+
+int kss_aivs_simplify_batch(kss_ctx* ctx, int n_clouds, const double* pts, const int* cnt, int cap, const int* point_num_each,
+                            int point_num, double* out, int out_cap, int* out_cnt, int32_t* out_idx) {
+    if (!ctx) return KSS_ERR_ARG;
+    if (n_clouds < 1 || !pts || cap < 1 || !out || !out_cnt || out_cap < 1 || (!point_num_each && point_num < 1))
+        return fail(ctx, KSS_ERR_ARG, "kss_aivs_simplify_batch: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t P = (size_t)n_clouds;
+    double *d_pts, *d_out; int *d_cnt = nullptr, *d_pn = nullptr, *d_ocnt, *d_oidx = nullptr;
+    BUF("aivs_in", P * cap * 3, &d_pts); BUF("aivs_out", P * out_cap * 3, &d_out); BUF("aivs_ocnt", P, &d_ocnt);
+    if (out_idx) BUF("aivs_oidx", P * out_cap, &d_oidx);
+    CU(cudaMemcpyAsync(d_pts, pts, sizeof(double) * 3 * P * cap, cudaMemcpyHostToDevice, st));
+    if (cnt) { BUF("aivs_icnt", P, &d_cnt); CU(cudaMemcpyAsync(d_cnt, cnt, sizeof(int) * P, cudaMemcpyHostToDevice, st)); }
+    if (point_num_each) { BUF("aivs_ipn", P, &d_pn); CU(cudaMemcpyAsync(d_pn, point_num_each, sizeof(int) * P, cudaMemcpyHostToDevice, st)); }
+    int r = kss_aivs_simplify_batch_device(ctx, n_clouds, d_pts, d_cnt, cap, d_pn, point_num, d_out, out_cap, d_ocnt, d_oidx);
+    if (r) return r;
+    CU(cudaMemcpyAsync(out, d_out, sizeof(double) * 3 * P * out_cap, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_cnt, d_ocnt, sizeof(int) * P, cudaMemcpyDeviceToHost, st));
+    if (out_idx) CU(cudaMemcpyAsync(out_idx, d_oidx, sizeof(int) * P * out_cap, cudaMemcpyDeviceToHost, st));
+    return kss_aivs_status(ctx);
+}
+
+int kss_aivs_simplify(kss_ctx* ctx, const double* pts, int n, int point_num, double* out, int out_cap, int* out_n,
+                      int32_t* out_idx) {
+    if (!ctx) return KSS_ERR_ARG;
+    if (!out_n) return fail(ctx, KSS_ERR_ARG, "kss_aivs_simplify: null out_n");
+    return kss_aivs_simplify_batch(ctx, 1, pts, nullptr, n, nullptr, point_num, out, out_cap, out_n, out_idx);
 }
 
 int kss_register(kss_ctx* ctx, const double* sim_s, int n_s, const double* sim_t, int n_t, const double* full_s,
