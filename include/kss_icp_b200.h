@@ -174,7 +174,8 @@ int kss_nn_search(kss_ctx* ctx, const double* q, int n_q, const double* t, int n
 
 /* replaces pointPipeline_init_point_withoutUniform + AIVS_Pro_init + AIVS_simplification(pointNum)
  * (pointPipeline.hpp:62-103, Method_AIVS_SimPro.hpp:66-123, called at KSS_ICP.hpp:72-82): out [out_cap][3]
- * receives the simplified cloud (out_cap >= point_num suffices), *out_n its size, out_idx (optional) the
+ * receives the simplified cloud (out_cap >= n always suffices; point_num does unless the trim step ends
+ * early, which is reported as KSS_ERR_UNSUPPORTED), *out_n its size, out_idx (optional) the
  * position of every kept point in `pts`.  n >= 1; clouds with zero extent are KSS_ERR_UNSUPPORTED. */
 int kss_aivs_simplify(kss_ctx* ctx, const double* pts, int n, int point_num, double* out, int out_cap,
                       int* out_n, int32_t* out_idx);

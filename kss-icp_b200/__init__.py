@@ -238,8 +238,7 @@ class Context:
         """pts [P, cap, 3] float64; point_num int or [P] ints -> (out [P, out_cap, 3], out_cnt [P], out_idx [P, out_cap])"""
         pts = _f64(pts); P, cap = pts.shape[0], pts.shape[1]
         each = None if np.isscalar(point_num) else np.ascontiguousarray(point_num, np.int32)
-        out_cap = int(point_num if each is None else each.max())
-        out_cap = max(out_cap, 3)
+        out_cap = cap               # the greedy trim may stop early (stale neighbour lists): up to all samples can stay
         cn = None if counts is None else np.ascontiguousarray(counts, np.int32)
         out = np.zeros((P, out_cap, 3), np.float64); ocnt = np.zeros(P, np.int32)
         oidx = np.full((P, out_cap), -1, np.int32) if want_index else None

@@ -678,7 +678,11 @@ int kss_register_batch_device(kss_ctx* ctx, const kss_batch* b_in, kss_pair_resu
     kss_batch bb = *b_in;
     const kss_batch* b = &bb;
     const bool raw = !bb.sim_s;
-    if (raw) bb.cap_s = bb.cap_t = std::min(2000, std::min(bb.cap_S, bb.cap_T) / 2);     // pNumber, KSS_ICP.hpp:53-67
+    if (raw) {   // pNumber (KSS_ICP.hpp:53-67) plus room for a trim step that stops early on its stale neighbour lists
+        const int pn = std::min(2000, std::min(bb.cap_S, bb.cap_T) / 2);
+        bb.cap_s = std::min(std::min(pn + 48, SMALL_MAX), bb.cap_S);
+        bb.cap_t = std::min(std::min(pn + 48, SMALL_MAX), bb.cap_T);
+    }
     r = ensure_trig(ctx, b->step); if (r) return r;
     const int H = ctx->G * ctx->G * ctx->G;
     int slots = 32;

@@ -1008,9 +1008,22 @@ int okss_register_batch(int n_pairs,
         for (;;) {
             int p = next.fetch_add(1);
             if (p >= n_pairs) break;
-            okss_register(sim_s + (size_t)p * 3 * n_s, n_s, sim_t + (size_t)p * 3 * n_t, n_t,
-                          full_s + (size_t)p * 3 * N_s, N_s, full_t + (size_t)p * 3 * N_t, N_t,
-                          step, max_iter, sum_order, nn_method, res + p, nullptr);
+            const double* fs = full_s + (size_t)p * 3 * N_s;
+            const double* ft = full_t + (size_t)p * 3 * N_t;
+            if (sim_s && sim_t) {
+                okss_register(sim_s + (size_t)p * 3 * n_s, n_s, sim_t + (size_t)p * 3 * n_t, n_t, fs, N_s, ft, N_t,
+                              step, max_iter, sum_order, nn_method, res + p, nullptr);
+            } else {
+                /* the whole of KSSICP_init + KSSICP_Registration (KSS_ICP.hpp:53-130): pNumber rule, then AIVS of
+                 * the target and of the source */
+                int pn = (N_s > N_t ? N_t : N_s) / 2;
+                if (pn > 2000) pn = 2000;
+                std::vector<double> st((size_t)3 * N_t), ss((size_t)3 * N_s);
+                const int mt = okss_aivs_simplify(ft, N_t, pn, st.data(), nullptr);
+                const int ms = okss_aivs_simplify(fs, N_s, pn, ss.data(), nullptr);
+                okss_register(ss.data(), ms, st.data(), mt, fs, N_s, ft, N_t, step, max_iter, sum_order, nn_method,
+                              res + p, nullptr);
+            }
         }
     };
     std::vector<std::thread> pool;

@@ -144,7 +144,9 @@ void okss_register(const double* sim_s, int n_s, const double* sim_t, int n_t,
                    okss_pair_result* res, double* point_align);
 
 /* batch of equally-shaped pairs, std::thread pool over pairs (threads<=0: all cores).
- * Arrays are concatenated per pair. Returns the number of threads used. */
+ * Arrays are concatenated per pair. Returns the number of threads used.
+ * sim_s == sim_t == NULL: every pair is simplified first (pNumber rule + okss_aivs_simplify), i.e. the whole of
+ * KSSICP_init + KSSICP_Registration (KSS_ICP.hpp:53-130). */
 int okss_register_batch(int n_pairs,
                         const double* sim_s, int n_s, const double* sim_t, int n_t,
                         const double* full_s, int N_s, const double* full_t, int N_t,

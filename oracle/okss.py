@@ -220,11 +220,15 @@ def register(sim_s, sim_t, full_s, full_t, step=8.0, max_iter=1000,
 
 def register_batch(sim_s, sim_t, full_s, full_t, step=8.0, max_iter=1000,
                    sum_order=SUM_CANON256, method=NN_KDTREE, threads=0):
-    """arrays shaped [P, n, 3]; returns (list of result dicts, threads used)"""
-    ss = _f64(sim_s); st = _f64(sim_t); fs = _f64(full_s); ft = _f64(full_t)
-    P = ss.shape[0]
+    """arrays shaped [P, n, 3]; returns (list of result dicts, threads used).
+    sim_s = sim_t = None: raw clouds, AIVS-simplified per pair inside (KSSICP_init + KSSICP_Registration)."""
+    fs = _f64(full_s); ft = _f64(full_t)
+    raw = sim_s is None
+    ss = None if raw else _f64(sim_s); st = None if raw else _f64(sim_t)
+    P = fs.shape[0]
     res = (PairResult * P)()
-    used = lib().okss_register_batch(C.c_int(P), _p(ss), C.c_int(ss.shape[1]), _p(st), C.c_int(st.shape[1]),
+    used = lib().okss_register_batch(C.c_int(P), _p(ss), C.c_int(0 if raw else ss.shape[1]), _p(st),
+                                     C.c_int(0 if raw else st.shape[1]),
                                      _p(fs), C.c_int(fs.shape[1]), _p(ft), C.c_int(ft.shape[1]),
                                      C.c_double(step), C.c_int(max_iter), C.c_int(sum_order),
                                      C.c_int(method), C.c_int(threads), res)
