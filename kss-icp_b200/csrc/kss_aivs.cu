@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include "kss_device.cuh"
 #include "kss_aivs.h"
@@ -237,19 +238,12 @@ __device__ __forceinline__ int aivs_colour(int i, int j, int k) {
     return 7;
 }
 
-__global__ void __launch_bounds__(128)
-aivs_fps_kernel(int colour, const double* __restrict__ pts, int cap, const AivsGrid* __restrict__ grids, int bcap,
-                const int* __restrict__ box_start, const int* __restrict__ members, const int* __restrict__ center_pos,
-                const int* __restrict__ quota, unsigned char* __restrict__ selected /* labelG == 0 */,
-                double* __restrict__ mind, int* __restrict__ sel, int* __restrict__ sel_cnt) {
-    const int p = blockIdx.y;
-    const AivsGrid g = grids[p];
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < 1 || b >= g.nbox) return;
-    // true (i,j,k) of the box, as the colouring loop enumerates them (Method_AIVS_SimPro.hpp:598-602)
-    const int b0 = b - 1;
-    const int i = b0 % g.nx + 1, j = (b0 / g.nx) % g.ny + 1, k = b0 / (g.nx * g.ny) + 1;
-    if (aivs_colour(i, j, k) != colour) return;
+// one box of AIVS_Voroni_OpenMP_KNN, run by one thread
+__device__ void aivs_fps_box(int p, int b, const AivsGrid& g, const double* __restrict__ pts, int cap, int bcap,
+                             const int* __restrict__ box_start, const int* __restrict__ members,
+                             const int* __restrict__ center_pos, const int* __restrict__ quota,
+                             unsigned char* __restrict__ selected /* labelG == 0 */, double* __restrict__ mind,
+                             int* __restrict__ sel, int* __restrict__ sel_cnt) {
     const int* st = box_start + (size_t)p * (bcap + 1);
     const int s = st[b], m = st[b + 1] - s;
     const int simNum = quota[(size_t)p * bcap + b];
@@ -329,6 +323,35 @@ aivs_fps_kernel(int colour, const double* __restrict__ pts, int cap, const AivsG
         }
     }
     sel_cnt[(size_t)p * bcap + b] = sampled;
+}
+
+// Same-colour boxes never see each other's points -- except the boxes whose index is a multiple of nx * ny: the
+// reference's centre decode misplaces their centre (B10), so their seed cube can reach same-colour boxes, including
+// each other.  In the reference's loop order they are the last boxes of their colour, in ascending index.  So a colour
+// is two phases: 2c = all other boxes, one thread each; 2c + 1 = the misplaced ones, one after the other.
+__global__ void __launch_bounds__(128)
+aivs_fps_kernel(int phase, const double* __restrict__ pts, int cap, const AivsGrid* __restrict__ grids, int bcap,
+                const int* __restrict__ box_start, const int* __restrict__ members, const int* __restrict__ center_pos,
+                const int* __restrict__ quota, unsigned char* __restrict__ selected, double* __restrict__ mind,
+                int* __restrict__ sel, int* __restrict__ sel_cnt) {
+    const int p = blockIdx.y;
+    const AivsGrid g = grids[p];
+    const int colour = phase >> 1;
+    if (phase & 1) {
+        if (blockIdx.x != 0 || threadIdx.x != 0) return;
+        for (int k = 1; k <= g.nz; ++k) {
+            const int b = g.nx * g.ny * k;
+            if (b >= g.nbox || aivs_colour(g.nx, g.ny, k) != colour) continue;
+            aivs_fps_box(p, b, g, pts, cap, bcap, box_start, members, center_pos, quota, selected, mind, sel, sel_cnt);
+        }
+        return;
+    }
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < 1 || b >= g.nbox || (b % (g.nx * g.ny)) == 0) return;
+    // true (i,j,k) of the box, as the colouring loop enumerates them (Method_AIVS_SimPro.hpp:598-602)
+    const int b0 = b - 1;
+    if (aivs_colour(b0 % g.nx + 1, (b0 / g.nx) % g.ny + 1, b0 / (g.nx * g.ny) + 1) != colour) return;
+    aivs_fps_box(p, b, g, pts, cap, bcap, box_start, members, center_pos, quota, selected, mind, sel, sel_cnt);
 }
 
 // ---------------------------------------------------------------- 4. samples in box order, K = 3 lists, greedy trim
@@ -464,6 +487,402 @@ aivs_cut_kernel(const double* __restrict__ pts, int cap, AivsGrid* __restrict__ 
     }
 }
 
+// ================================================================ clouds of at most 2048 points: one CTA per cloud
+// The whole simplification in one launch, everything in shared memory: float copies of the points, the box
+// membership as one bitonic sort of (box << 11 | index) keys, farthest point sampling with GL lanes per box (same
+// colour boxes in parallel, a barrier between colours), the K = 3 lists and the sorted greedy trim.  Same arithmetic
+// and the same selection rules as the general kernels above (the min-distance array is kept in float: every value
+// is a float square root or 9999, so comparisons are unchanged).
+constexpr int AS_THREADS = 256;
+constexpr int AS_SB = 1336;                   // >= 11^3 + 2 boxes (10 per axis, 11 when the division rounds up)
+constexpr int AS_MAX = 2048;
+
+__device__ __forceinline__ int as_block_excl_scan(int* a, int L, int* wsum) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (L + AS_THREADS - 1) / AS_THREADS;
+    const int lo = min(L, tid * per), hi = min(L, lo + per);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += a[i];
+    int x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(KSS_FULL, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    int base = x - sum, total = 0;
+#pragma unroll
+    for (int w = 0; w < AS_THREADS / 32; ++w) { const int v = wsum[w]; if (w < warp) base += v; total += v; }
+    for (int i = lo; i < hi; ++i) { const int v = a[i]; a[i] = base; base += v; }
+    __syncthreads();
+    return total;
+}
+
+template <typename K>
+__device__ __forceinline__ void as_bitonic(K* keys, int np) {
+    for (int k = 2; k <= np; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < np; i += AS_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const K a = keys[i], b = keys[ixj];
+                    if ((a > b) == ((i & k) == 0)) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+        }
+    __syncthreads();
+}
+
+struct AsLayout {               // byte offsets into dynamic shared memory
+    int xf, yf, zf, sample, a_base;
+    int mkey, md, start, selc, sel, centre, quota, clist, lab;       // before the samples are gathered
+    int key64, d2s, keep;                                            // after (aliases the block above)
+    int total;
+};
+__host__ __device__ inline AsLayout as_layout(int cap) {
+    AsLayout L;
+    const int capA = (cap + 7) & ~7;
+    int np = 1; while (np < cap) np <<= 1;
+    int o = 0;
+    L.xf = o; o += 4 * capA; L.yf = o; o += 4 * capA; L.zf = o; o += 4 * capA;
+    L.sample = o; o += 2 * capA;
+    o = (o + 15) & ~15; L.a_base = o;
+    L.mkey = o; o += 4 * np; L.md = o; o += 4 * capA; L.start = o; o += 4 * AS_SB; L.selc = o; o += 4 * AS_SB;
+    L.sel = o; o += 2 * capA; L.centre = o; o += 2 * AS_SB; L.quota = o; o += 2 * AS_SB; L.clist = o; o += 2 * AS_SB;
+    L.lab = o; o += capA;
+    const int pre_end = o;
+    o = L.a_base;
+    L.key64 = o; o += 8 * np; L.d2s = o; o += 4 * capA; L.keep = o; o += capA;
+    L.total = (pre_end > o ? pre_end : o) + 16;
+    return L;
+}
+
+template <int GL>
+__global__ void __launch_bounds__(AS_THREADS, 2)
+aivs_small_kernel(const double* __restrict__ pts, const int* __restrict__ cnt, int cap, const int* __restrict__ point_num,
+                  int point_num_all, double* __restrict__ out, int out_cap, int* __restrict__ out_cnt,
+                  int* __restrict__ out_idx, int* __restrict__ bad) {
+    extern __shared__ __align__(16) unsigned char as_smem[];
+    __shared__ AivsGrid g_s;
+    __shared__ double red[6][AS_THREADS / 32];
+    __shared__ int wsum[AS_THREADS / 32];
+    __shared__ int ccount[16], coff[17], ccur[16];   // colour * 2 + (misplaced-centre box ? 1 : 0), see aivs_fps_kernel
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = min(cnt ? cnt[p] : cap, cap);
+    const int pn = point_num ? point_num[p] : point_num_all;
+    const double* P = pts + (size_t)p * cap * 3;
+    const AsLayout L = as_layout(cap);
+    float* xf = reinterpret_cast<float*>(as_smem + L.xf);
+    float* yf = reinterpret_cast<float*>(as_smem + L.yf);
+    float* zf = reinterpret_cast<float*>(as_smem + L.zf);
+    unsigned short* sample = reinterpret_cast<unsigned short*>(as_smem + L.sample);
+    unsigned* mkey = reinterpret_cast<unsigned*>(as_smem + L.mkey);
+    float* md = reinterpret_cast<float*>(as_smem + L.md);
+    int* start = reinterpret_cast<int*>(as_smem + L.start);
+    int* selc = reinterpret_cast<int*>(as_smem + L.selc);
+    unsigned short* sel = reinterpret_cast<unsigned short*>(as_smem + L.sel);
+    unsigned short* centre = reinterpret_cast<unsigned short*>(as_smem + L.centre);
+    unsigned short* quota = reinterpret_cast<unsigned short*>(as_smem + L.quota);
+    unsigned short* clist = reinterpret_cast<unsigned short*>(as_smem + L.clist);
+    unsigned char* lab = as_smem + L.lab;
+    unsigned long long* key64 = reinterpret_cast<unsigned long long*>(as_smem + L.key64);
+    float* d2s = reinterpret_cast<float*>(as_smem + L.d2s);
+    unsigned char* keep = as_smem + L.keep;
+    if (n < 1) { if (tid == 0) { out_cnt[p] = 0; atomicExch(bad, 1); } return; }
+
+    // ---- border (pointPipeline_Border) + float copies
+    {
+        double lmin[3] = {INFINITY, INFINITY, INFINITY}, lmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i = tid; i < n; i += AS_THREADS) {
+            const double q0 = P[3 * i], q1 = P[3 * i + 1], q2 = P[3 * i + 2];
+            xf[i] = (float)q0; yf[i] = (float)q1; zf[i] = (float)q2;
+            lmin[0] = fmin(lmin[0], q0); lmax[0] = fmax(lmax[0], q0);
+            lmin[1] = fmin(lmin[1], q1); lmax[1] = fmax(lmax[1], q1);
+            lmin[2] = fmin(lmin[2], q2); lmax[2] = fmax(lmax[2], q2);
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                lmin[d] = fmin(lmin[d], __shfl_xor_sync(KSS_FULL, lmin[d], o));
+                lmax[d] = fmax(lmax[d], __shfl_xor_sync(KSS_FULL, lmax[d], o));
+            }
+        if (lane == 0) for (int d = 0; d < 3; ++d) { red[d][warp] = lmin[d]; red[3 + d][warp] = lmax[d]; }
+        for (int i = tid; i < AS_SB; i += AS_THREADS) { start[i] = 0; selc[i] = 0; }
+        for (int i = tid; i < n; i += AS_THREADS) lab[i] = 0;
+        if (tid < 16) { ccount[tid] = 0; ccur[tid] = 0; }
+        __syncthreads();
+        if (tid == 0) {
+            AivsGrid g;
+            double dis[3];
+            for (int d = 0; d < 3; ++d) {
+                double a = red[d][0], b = red[3 + d][0];
+                for (int w = 1; w < AS_THREADS / 32; ++w) { a = fmin(a, red[d][w]); b = fmax(b, red[3 + d][w]); }
+                g.mn[d] = a; dis[d] = fabs(__dsub_rn(b, a));
+            }
+            g.n = n; g.point_num = pn;
+            const int boxNum = aivs_box_scale(n);
+            double large = dis[0];
+            if (large < dis[1]) large = dis[1];
+            if (large < dis[2]) large = dis[2];
+            g.unit = __ddiv_rn(large, (double)boxNum);
+            int num[3];
+            for (int d = 0; d < 3; ++d) {
+                const double nd = __ddiv_rn(dis[d], g.unit);
+                num[d] = (int)nd;
+                if (nd > (double)num[d]) num[d]++;
+            }
+            g.nx = num[0]; g.ny = num[1]; g.nz = num[2];
+            const long long nb = (long long)g.nx * g.ny * g.nz + 1;
+            g.nbox = (int)nb; g.n_samples = 0; g.pad = 0;
+            if (!(large > 0.0) || nb > AS_SB - 2 || g.nx < 1 || g.ny < 1 || g.nz < 1) { g.nbox = 0; atomicExch(bad, 1); out_cnt[p] = 0; }
+            g_s = g;
+        }
+        __syncthreads();
+    }
+    const AivsGrid g = g_s;
+    if (g.nbox == 0) return;
+    const int nbox = g.nbox;
+    int NP = 1; while (NP < n) NP <<= 1;
+
+    // ---- BallRegion_BoxInput: membership = sort of (box, index) keys; box starts = scan of the counts
+    for (int i = tid; i < NP; i += AS_THREADS) {
+        unsigned key = 0xffffffffu;
+        if (i < n) {
+            int b = aivs_box_of(g, P + 3 * (size_t)i);
+            if (b < 0 || b >= nbox) b = nbox; else atomicAdd(&start[b], 1);
+            key = ((unsigned)b << 11) | (unsigned)i;
+        }
+        mkey[i] = key;
+    }
+    as_bitonic(mkey, NP);
+    as_block_excl_scan(start, nbox + 1, wsum);
+
+    // ---- per box: centre-nearest member, quota, colour census
+    for (int b = 1 + tid; b < nbox; b += AS_THREADS) {
+        const int s = start[b], m = start[b + 1] - s;
+        if (m == 0) { quota[b] = 0; continue; }
+        double c[3];
+        aivs_center(g, b, c);
+        double best = 9999.0; int bi = -1;
+        for (int i = 0; i < m; ++i) {
+            const double* q = P + 3 * (size_t)(mkey[s + i] & 2047u);
+            const double dx = __dsub_rn(c[0], q[0]), dy = __dsub_rn(c[1], q[1]), dz = __dsub_rn(c[2], q[2]);
+            const double dm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+            if (best > dm) { best = dm; bi = i; }
+        }
+        centre[b] = bi < 0 ? 0xffffu : (unsigned short)bi;
+        const double rate = __ddiv_rn((double)pn, (double)n);
+        const double sb = __dmul_rn((double)m, rate);
+        const int t = (int)sb;
+        const int qv = (__dsub_rn(sb, (double)t) > 0.2) ? t + 1 : t;
+        quota[b] = (unsigned short)min(qv, 65535);
+        if (qv > 0) {
+            const int b0 = b - 1;
+            atomicAdd(&ccount[aivs_colour(b0 % g.nx + 1, (b0 / g.nx) % g.ny + 1, b0 / (g.nx * g.ny) + 1) * 2 +
+                              ((b % (g.nx * g.ny)) == 0 ? 1 : 0)], 1);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { int o = 0; for (int c = 0; c < 16; ++c) { coff[c] = o; o += ccount[c]; } coff[16] = o; }
+    __syncthreads();
+    for (int b = 1 + tid; b < nbox; b += AS_THREADS) {
+        if (start[b + 1] == start[b] || quota[b] == 0) continue;
+        const int b0 = b - 1;
+        const int c = aivs_colour(b0 % g.nx + 1, (b0 / g.nx) % g.ny + 1, b0 / (g.nx * g.ny) + 1) * 2 +
+                      ((b % (g.nx * g.ny)) == 0 ? 1 : 0);
+        clist[coff[c] + atomicAdd(&ccur[c], 1)] = (unsigned short)b;
+    }
+    __syncthreads();
+
+    // ---- AIVS_Voroni_OpenMP_KNN: colour by colour, GL lanes per box
+    {
+        const int grp = tid / GL, gl = tid % GL, ngrp = AS_THREADS / GL;
+        const unsigned gmask = GL == 32 ? 0xffffffffu : (((1u << GL) - 1u) << ((lane / GL) * GL));
+        const double radius = __ddiv_rn(__dmul_rn(g.unit, 3.0), 4.0);
+        for (int col = 0; col < 16; ++col) {
+            // even phase: the colour's boxes in parallel; odd phase: its misplaced-centre boxes (index multiple of
+            // nx * ny, see aivs_fps_kernel) one after the other in ascending index, by group 0
+            const bool serial = col & 1;
+            const int nb_col = serial ? g.nz : ccount[col];
+            for (int gi = serial ? (grp == 0 ? 0 : nb_col) : grp; gi < nb_col; gi += serial ? 1 : ngrp) {
+                int b;
+                if (serial) {
+                    b = g.nx * g.ny * (gi + 1);
+                    if (b >= nbox || aivs_colour(g.nx, g.ny, gi + 1) != (col >> 1) || start[b + 1] == start[b] || quota[b] == 0) continue;
+                } else {
+                    b = clist[coff[col] + gi];
+                }
+                const int s = start[b], m = start[b + 1] - s, simNum = quota[b];
+                double pc[3];
+                aivs_center(g, b, pc);
+                const double lo0 = __dsub_rn(pc[0], radius), hi0 = __dadd_rn(pc[0], radius);
+                const double lo1 = __dsub_rn(pc[1], radius), hi1 = __dadd_rn(pc[1], radius);
+                const double lo2 = __dsub_rn(pc[2], radius), hi2 = __dadd_rn(pc[2], radius);
+                const int z_num = b / (g.nx * g.ny) + 1;
+                const int leveZ = b % (g.nx * g.ny);
+                const int y_num = leveZ / g.nx + 1;
+                const int x_num = leveZ % g.nx;                              // no wrap fix (B10)
+                for (int t = gl; t < m; t += GL) md[s + t] = INFINITY;
+                bool any_seed = false;
+                for (int xi = x_num - 1; xi <= x_num + 1; ++xi) {
+                    if ((xi < x_num && !(x_num > 1)) || (xi > x_num && !(x_num < g.nx))) continue;
+                    for (int yj = y_num - 1; yj <= y_num + 1; ++yj) {
+                        if ((yj < y_num && !(y_num > 1)) || (yj > y_num && !(y_num < g.ny))) continue;
+                        for (int zk = z_num - 1; zk <= z_num + 1; ++zk) {
+                            if ((zk < z_num && !(z_num > 1)) || (zk > z_num && !(z_num < g.nz))) continue;
+                            if (xi == x_num && yj == y_num && zk == z_num) continue;
+                            const int nb = xi + (yj - 1) * g.nx + (zk - 1) * g.nx * g.ny;
+                            if (nb >= nbox || nb < 0) continue;
+                            const int ns = start[nb], nm = start[nb + 1] - ns;
+                            for (int l0 = 0; l0 < nm; l0 += GL) {
+                                const int l = l0 + gl;
+                                bool ok = false; int pt = 0;
+                                if (l < nm) {
+                                    pt = (int)(mkey[ns + l] & 2047u);
+                                    if (lab[pt]) {
+                                        const double* q = P + 3 * (size_t)pt;
+                                        const double q0 = q[0], q1 = q[1], q2 = q[2];
+                                        ok = q0 <= hi0 && q0 >= lo0 && q1 <= hi1 && q1 >= lo1 && q2 <= hi2 && q2 >= lo2;
+                                    }
+                                }
+                                unsigned bal = __ballot_sync(gmask, ok) & gmask;
+                                while (bal) {
+                                    const int src = __ffs(bal) - 1; bal &= bal - 1;
+                                    const int spt = __shfl_sync(gmask, pt, src);
+                                    const float sx = xf[spt], sy = yf[spt], sz = zf[spt];
+                                    for (int t = gl; t < m; t += GL) {
+                                        const int w = (int)(mkey[s + t] & 2047u);
+                                        const float d = __fsqrt_rn(d2_rn(xf[w], yf[w], zf[w], sx, sy, sz));
+                                        if (d < md[s + t]) md[s + t] = d;
+                                    }
+                                    any_seed = true;
+                                }
+                            }
+                        }
+                    }
+                }
+                for (int t = gl; t < m; t += GL) if (md[s + t] == INFINITY) md[s + t] = 9999.0f;
+                int sampled = 0;
+                if (!any_seed) {
+                    const int ci = centre[b];
+                    if (ci != 0xffff && ci < m) {
+                        const int cpt = (int)(mkey[s + ci] & 2047u);
+                        const float sx = xf[cpt], sy = yf[cpt], sz = zf[cpt];
+                        for (int t = gl; t < m; t += GL) {
+                            const int w = (int)(mkey[s + t] & 2047u);
+                            md[s + t] = t == ci ? 0.0f : __fsqrt_rn(d2_rn(xf[w], yf[w], zf[w], sx, sy, sz));
+                        }
+                        if (gl == 0) { sel[s] = (unsigned short)cpt; lab[cpt] = 1; }
+                        sampled = 1;
+                    }
+                }
+                while (sampled < simNum) {
+                    float bv = 0.0f; int bt = -1;
+                    for (int t = gl; t < m; t += GL) { const float v = md[s + t]; if (v > bv) { bv = v; bt = t; } }
+#pragma unroll
+                    for (int o = GL / 2; o >= 1; o >>= 1) {
+                        const float ov = __shfl_xor_sync(gmask, bv, o);
+                        const int ot = __shfl_xor_sync(gmask, bt, o);
+                        if (ov > bv || (ov == bv && ot < bt)) { bv = ov; bt = ot; }
+                    }
+                    if (bt < 0) break;
+                    const int ppt = (int)(mkey[s + bt] & 2047u);
+                    if (gl == 0) { lab[ppt] = 1; sel[s + sampled] = (unsigned short)ppt; }
+                    ++sampled;
+                    const float sx = xf[ppt], sy = yf[ppt], sz = zf[ppt];
+                    for (int t = gl; t < m; t += GL) {
+                        const int w = (int)(mkey[s + t] & 2047u);
+                        const float d = __fsqrt_rn(d2_rn(sx, sy, sz, xf[w], yf[w], zf[w]));
+                        if (d < md[s + t]) md[s + t] = d;
+                    }
+                }
+                if (gl == 0) selc[b] = sampled;
+                __syncwarp(gmask);
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- samples in box order
+    const int S = as_block_excl_scan(selc, nbox + 1, wsum);
+    for (int b = 1 + tid; b < nbox; b += AS_THREADS) {
+        const int dst = selc[b], c = selc[b + 1] - dst, src = start[b];
+        for (int r = 0; r < c; ++r) sample[dst + r] = sel[src + r];
+    }
+    __syncthreads();
+
+    // ---- AIVS_AccurateCut_Optimization
+    int dT = S - pn;
+    const bool trim = dT > 0 && S >= 3;
+    if (trim) {
+        int NP2 = 1; while (NP2 < S) NP2 <<= 1;
+        for (int i0 = 0; i0 < S; i0 += AS_THREADS) {
+            const int i = i0 + tid;
+            const int me = i < S ? sample[i] : sample[0];
+            const float x = xf[me], y = yf[me], z = zf[me];
+            // ascending (d2, position): j grows, so a later candidate replaces an entry only when strictly nearer
+            float e0 = INFINITY, e1 = INFINITY, e2 = INFINITY; int j1 = 0;
+            int j0 = 0;
+            for (int j = 0; j < S; ++j) {
+                const int o = sample[j];
+                const float d = d2_rn(x, y, z, xf[o], yf[o], zf[o]);
+                if (d < e2) {
+                    if (d < e0) { e2 = e1; e1 = e0; j1 = j0; e0 = d; j0 = j; }
+                    else if (d < e1) { e2 = e1; e1 = d; j1 = j; }
+                    else e2 = d;
+                }
+            }
+            __syncwarp();
+            if (i < S) {
+                const float d1 = __fsqrt_rn(e1);
+                key64[i] = ((unsigned long long)__float_as_uint(d1) << 32) | ((unsigned long long)i << 16) | (unsigned long long)j1;
+                d2s[i] = __fsqrt_rn(e2);
+                keep[i] = 1;
+            }
+        }
+        for (int i = S + tid; i < NP2; i += AS_THREADS) key64[i] = ~0ull;
+        as_bitonic(key64, NP2);
+        if (tid == 0) {
+            for (int pos = 0; pos < S && dT > 0; ++pos) {
+                const unsigned long long key = key64[pos];
+                if (!((double)__uint_as_float((unsigned)(key >> 32)) < 9999.0)) break;
+                const int b1 = (int)((key >> 16) & 0xffffu), b2 = (int)(key & 0xffffu);
+                if (!keep[b1] || !keep[b2]) continue;
+                keep[((double)d2s[b1] > (double)d2s[b2]) ? b2 : b1] = 0;
+                --dT;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- ordered output
+    {
+        const int per = (S + AS_THREADS - 1) / AS_THREADS;
+        const int lo = min(S, tid * per), hi = min(S, lo + per);
+        int c = 0;
+        for (int i = lo; i < hi; ++i) c += (!trim || keep[i]) ? 1 : 0;
+        int x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(KSS_FULL, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        int pos = x - c, total = 0;
+        for (int w = 0; w < AS_THREADS / 32; ++w) { if (w < warp) pos += wsum[w]; total += wsum[w]; }
+        for (int i = lo; i < hi; ++i)
+            if (!trim || keep[i]) {
+                if (pos < out_cap) {
+                    const int me = sample[i];
+                    const double* q = P + 3 * (size_t)me;
+                    double* o = out + ((size_t)p * out_cap + pos) * 3;
+                    o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
+                    if (out_idx) out_idx[(size_t)p * out_cap + pos] = me;
+                }
+                ++pos;
+            }
+        if (tid == 0) { out_cnt[p] = min(total, out_cap); if (total > out_cap) atomicExch(bad, 3); }
+    }
+}
+
 // pNumber = min(|S|, |T|) / 2 capped at 2000 (KSS_ICP.hpp:53-67)
 __global__ void aivs_pnumber_kernel(int P, const int* cnt_S, int cap_S, const int* cnt_T, int cap_T, int* pn) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -485,6 +904,19 @@ int aivs_box_cap(int cap) {
 int aivs_simplify_device(cudaStream_t st, long long* launches, int P, const double* d_pts, const int* d_cnt, int cap,
                          const int* d_point_num, int point_num_all, double* d_out, int out_cap, int* d_out_cnt,
                          int* d_out_idx, int* d_bad, const DevAlloc& alloc, const char* tag) {
+    if (cap <= AS_MAX && !getenv("KSS_AIVS_GENERAL")) {
+        const AsLayout L = as_layout(cap);
+        static int smem_small = 0;
+        if (L.total > smem_small) {
+            if (cudaFuncSetAttribute(aivs_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total) != cudaSuccess)
+                return KSS_ERR_CUDA;
+            smem_small = L.total;
+        }
+        aivs_small_kernel<8><<<P, AS_THREADS, L.total, st>>>(d_pts, d_cnt, cap, d_point_num, point_num_all, d_out, out_cap,
+                                                             d_out_cnt, d_out_idx, d_bad);
+        *launches += 1;
+        return cudaGetLastError() == cudaSuccess ? KSS_OK : KSS_ERR_CUDA;
+    }
     const int bcap = aivs_box_cap(cap);
     auto get = [&](const char* name, size_t bytes, void** out) {
         char nm[64]; snprintf(nm, sizeof(nm), "aivs_%s_%s", tag, name);
@@ -520,7 +952,7 @@ int aivs_simplify_device(cudaStream_t st, long long* launches, int P, const doub
     aivs_scan_kernel<<<P, 1024, 0, st>>>(grids, bcap, box_cnt, box_start, cursor);
     aivs_fill_kernel<<<gp, 256, 0, st>>>(cap, grids, bcap, box_of, cursor, members);
     aivs_box_kernel<<<gb, 256, 0, st>>>(d_pts, cap, grids, bcap, box_start, members, center_pos, quota);
-    for (int c = 0; c < 8; ++c)
+    for (int c = 0; c < 16; ++c)
         aivs_fps_kernel<<<dim3((bcap + 127) / 128, P), 128, 0, st>>>(c, d_pts, cap, grids, bcap, box_start, members, center_pos,
                                                                   quota, selected, mind, sel, sel_cnt);
     aivs_scan_kernel<<<P, 1024, 0, st>>>(grids, bcap, sel_cnt, sel_start, nullptr);
@@ -535,7 +967,7 @@ int aivs_simplify_device(cudaStream_t st, long long* launches, int P, const doub
     }
     aivs_cut_kernel<<<P, 512, smem, st>>>(d_pts, cap, grids, bcap, sel_start, sample, key1, dis2, np2, d_out, out_cap, d_out_cnt,
                                           d_out_idx, d_bad);
-    *launches += 17;
+    *launches += 25;
     return cudaGetLastError() == cudaSuccess ? KSS_OK : KSS_ERR_CUDA;
 }
 

@@ -145,3 +145,48 @@ def test_register_raw_ragged_counts(ctx, okss, pkg):
         for k in ("final_fitness", "judge_fitness", "rmse", "mse", "mae", "winner", "n_minima"):
             assert raw[p][k] == one[k], (p, k)
         assert np.array_equal(raw[p]["T"], one["T"])
+
+
+def test_aivs_general_kernels_match_single_cta_kernel(ctx, okss, pkg, monkeypatch):
+    """clouds <= 2048 points normally take the one-CTA-per-cloud kernel; KSS_AIVS_GENERAL=1 forces the multi-kernel
+    path used for large clouds: both must keep the same points"""
+    P, cap = 5, 1500
+    rng = np.random.default_rng(19)
+    pts = np.zeros((P, cap, 3)); cnt = np.zeros(P, np.int32)
+    for p in range(P):
+        n = int(rng.integers(100, cap + 1))
+        pts[p, :n] = _shape_cloud(pkg, 300 + p, n)[0]; cnt[p] = n
+    a = ctx.aivs_simplify_batch(pts, 600, counts=cnt)
+    monkeypatch.setenv("KSS_AIVS_GENERAL", "1")
+    b = ctx.aivs_simplify_batch(pts, 600, counts=cnt)
+    monkeypatch.delenv("KSS_AIVS_GENERAL")
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    for p in range(P):
+        assert np.array_equal(a[2][p, :a[1][p]], okss.aivs_simplify(pts[p, :cnt[p]], 600)[1])
+
+
+def test_aivs_many_random_shapes(ctx, okss, pkg):
+    """96 clouds with random anisotropy and sizes: any dependence on the order in which same-colour boxes are
+    processed (misplaced centres of the boxes at the end of an x/y row) would show up here"""
+    P, cap = 96, 2048
+    rng = np.random.default_rng(20)
+    pts = np.zeros((P, cap, 3)); cnt = np.zeros(P, np.int32); pn = np.zeros(P, np.int32)
+    for p in range(P):
+        n = int(rng.integers(300, cap + 1))
+        kind = p % 4
+        if kind == 0:
+            c = _shape_cloud(pkg, 500 + p, n)[0]
+        elif kind == 1:
+            c = rng.uniform(-1, 1, (n, 3))
+        elif kind == 2:
+            c = rng.normal(size=(n, 3)); c /= np.linalg.norm(c, axis=1, keepdims=True)
+        else:
+            c = rng.normal(size=(n, 3))
+        c = c * rng.uniform(0.05, 1.0, 3) * rng.choice([1.0, 1.0, 0.02], 3)
+        pts[p, :n] = c; cnt[p] = n; pn[p] = int(n * rng.uniform(0.2, 0.6))
+    out, ocnt, oidx = ctx.aivs_simplify_batch(pts, pn, counts=cnt)
+    for p in range(P):
+        o_idx = okss.aivs_simplify(pts[p, :cnt[p]], int(pn[p]))[1]
+        assert ocnt[p] == len(o_idx), p
+        assert np.array_equal(oidx[p, :ocnt[p]], o_idx), p
