@@ -496,6 +496,9 @@ aivs_cut_kernel(const double* __restrict__ pts, int cap, AivsGrid* __restrict__ 
 constexpr int AS_THREADS = 256;
 constexpr int AS_SB = 1336;                   // >= 11^3 + 2 boxes (10 per axis, 11 when the division rounds up)
 constexpr int AS_MAX = 2048;
+#ifndef AS_GL
+#define AS_GL 16                             // lanes per box in the sampling phases
+#endif
 
 __device__ __forceinline__ int as_block_excl_scan(int* a, int L, int* wsum) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -533,9 +536,9 @@ __device__ __forceinline__ void as_bitonic(K* keys, int np) {
 }
 
 struct AsLayout {               // byte offsets into dynamic shared memory
-    int xf, yf, zf, sample, a_base;
-    int mkey, md, start, selc, sel, centre, quota, clist, lab;       // before the samples are gathered
-    int key64, d2s, keep;                                            // after (aliases the block above)
+    int xf, yf, zf, sample;
+    int mkey, start, centre, quota, clist, md, sel, lab, selc;       // while the boxes are sampled
+    int key64, d2s, keep, sbox;                                      // for the trim (aliases everything above but selc)
     int total;
 };
 __host__ __device__ inline AsLayout as_layout(int cap) {
@@ -545,19 +548,27 @@ __host__ __device__ inline AsLayout as_layout(int cap) {
     int o = 0;
     L.xf = o; o += 4 * capA; L.yf = o; o += 4 * capA; L.zf = o; o += 4 * capA;
     L.sample = o; o += 2 * capA;
-    o = (o + 15) & ~15; L.a_base = o;
-    L.mkey = o; o += 4 * np; L.md = o; o += 4 * capA; L.start = o; o += 4 * AS_SB; L.selc = o; o += 4 * AS_SB;
-    L.sel = o; o += 2 * capA; L.centre = o; o += 2 * AS_SB; L.quota = o; o += 2 * AS_SB; L.clist = o; o += 2 * AS_SB;
-    L.lab = o; o += capA;
-    const int pre_end = o;
-    o = L.a_base;
+    o = (o + 15) & ~15;
+    const int a_base = o;
+    L.mkey = o; o += 4 * np; L.start = o; o += 4 * AS_SB; L.centre = o; o += 2 * AS_SB; L.quota = o; o += 2 * AS_SB;
+    L.clist = o; o += 2 * AS_SB;
+    L.md = o; o += 4 * capA; L.sel = o; o += 2 * capA; L.lab = o; o += capA;
+    L.selc = o; o += 4 * AS_SB;
+    int end = o;
+    o = a_base;
     L.key64 = o; o += 8 * np; L.d2s = o; o += 4 * capA; L.keep = o; o += capA;
-    L.total = (pre_end > o ? pre_end : o) + 16;
+    // sample -> box table: written while `sel` is read and `selc` is live, read while key64/d2s/keep are written:
+    // inside the dead `md` block when it lies behind the trim arrays, else appended
+    L.sbox = (o > L.md ? o : L.md);
+    L.sbox = (L.sbox + 7) & ~7;
+    if (L.sbox + 2 * capA > L.sel) { L.sbox = (end + 7) & ~7; end = L.sbox + 2 * capA; }
+    if (o > L.selc) { /* trim arrays would reach selc: move selc behind them */ L.selc = (end + 7) & ~7; end = L.selc + 4 * AS_SB; }
+    L.total = end + 16;
     return L;
 }
 
 template <int GL>
-__global__ void __launch_bounds__(AS_THREADS, 2)
+__global__ void __launch_bounds__(AS_THREADS, 3)
 aivs_small_kernel(const double* __restrict__ pts, const int* __restrict__ cnt, int cap, const int* __restrict__ point_num,
                   int point_num_all, double* __restrict__ out, int out_cap, int* __restrict__ out_cnt,
                   int* __restrict__ out_idx, int* __restrict__ bad) {
@@ -581,6 +592,7 @@ aivs_small_kernel(const double* __restrict__ pts, const int* __restrict__ cnt, i
     int* selc = reinterpret_cast<int*>(as_smem + L.selc);
     unsigned short* sel = reinterpret_cast<unsigned short*>(as_smem + L.sel);
     unsigned short* centre = reinterpret_cast<unsigned short*>(as_smem + L.centre);
+    unsigned short* sbox = reinterpret_cast<unsigned short*>(as_smem + L.sbox);
     unsigned short* quota = reinterpret_cast<unsigned short*>(as_smem + L.quota);
     unsigned short* clist = reinterpret_cast<unsigned short*>(as_smem + L.clist);
     unsigned char* lab = as_smem + L.lab;
@@ -718,6 +730,7 @@ aivs_small_kernel(const double* __restrict__ pts, const int* __restrict__ cnt, i
                 const double lo0 = __dsub_rn(pc[0], radius), hi0 = __dadd_rn(pc[0], radius);
                 const double lo1 = __dsub_rn(pc[1], radius), hi1 = __dadd_rn(pc[1], radius);
                 const double lo2 = __dsub_rn(pc[2], radius), hi2 = __dadd_rn(pc[2], radius);
+                const float lf0 = (float)lo0, hf0 = (float)hi0, lf1 = (float)lo1, hf1 = (float)hi1, lf2 = (float)lo2, hf2 = (float)hi2;
                 const int z_num = b / (g.nx * g.ny) + 1;
                 const int leveZ = b % (g.nx * g.ny);
                 const int y_num = leveZ / g.nx + 1;
@@ -740,9 +753,16 @@ aivs_small_kernel(const double* __restrict__ pts, const int* __restrict__ cnt, i
                                 if (l < nm) {
                                     pt = (int)(mkey[ns + l] & 2047u);
                                     if (lab[pt]) {
-                                        const double* q = P + 3 * (size_t)pt;
-                                        const double q0 = q[0], q1 = q[1], q2 = q[2];
-                                        ok = q0 <= hi0 && q0 >= lo0 && q1 <= hi1 && q1 >= lo1 && q2 <= hi2 && q2 >= lo2;
+                                        // rounding to float is monotonic: a float coordinate strictly inside (outside)
+                                        // the float-rounded bounds decides the double comparison; only equality needs it
+                                        const float a0 = xf[pt], a1 = yf[pt], a2 = zf[pt];
+                                        if (a0 > hf0 || a0 < lf0 || a1 > hf1 || a1 < lf1 || a2 > hf2 || a2 < lf2) ok = false;
+                                        else if (a0 < hf0 && a0 > lf0 && a1 < hf1 && a1 > lf1 && a2 < hf2 && a2 > lf2) ok = true;
+                                        else {
+                                            const double* q = P + 3 * (size_t)pt;
+                                            const double q0 = q[0], q1 = q[1], q2 = q[2];
+                                            ok = q0 <= hi0 && q0 >= lo0 && q1 <= hi1 && q1 >= lo1 && q2 <= hi2 && q2 >= lo2;
+                                        }
                                     }
                                 }
                                 unsigned bal = __ballot_sync(gmask, ok) & gmask;
@@ -807,7 +827,7 @@ aivs_small_kernel(const double* __restrict__ pts, const int* __restrict__ cnt, i
     const int S = as_block_excl_scan(selc, nbox + 1, wsum);
     for (int b = 1 + tid; b < nbox; b += AS_THREADS) {
         const int dst = selc[b], c = selc[b + 1] - dst, src = start[b];
-        for (int r = 0; r < c; ++r) sample[dst + r] = sel[src + r];
+        for (int r = 0; r < c; ++r) { sample[dst + r] = sel[src + r]; sbox[dst + r] = (unsigned short)b; }
     }
     __syncthreads();
 
@@ -816,29 +836,57 @@ aivs_small_kernel(const double* __restrict__ pts, const int* __restrict__ cnt, i
     const bool trim = dT > 0 && S >= 3;
     if (trim) {
         int NP2 = 1; while (NP2 < S) NP2 <<= 1;
+        // K = 3 nearest samples in ascending (d2, position).  Candidates are visited in ascending position, so a later
+        // one replaces an entry only when strictly nearer.  First the samples of the 27 boxes around the sample's own
+        // box (ascending box index = ascending position); a sample outside that block is at least one box width away
+        // along some axis, so when the third distance found is below that (minus the float narrowing of the
+        // coordinates, `lim2`), the three are the global answer; otherwise all samples are scanned.
+        float lim2 = 0.0f;
+        {
+            double amax = 0.0;
+            for (int d = 0; d < 3; ++d) amax = fmax(amax, fmax(fabs(g.mn[d]), fabs(g.mn[d] + g.unit * (double)(d == 0 ? g.nx : d == 1 ? g.ny : g.nz))));
+            const double lim = g.unit * 0.999 - amax * 1.0e-6;
+            if (lim > 0.0) lim2 = (float)(lim * lim * 0.999);
+        }
         for (int i0 = 0; i0 < S; i0 += AS_THREADS) {
             const int i = i0 + tid;
-            const int me = i < S ? sample[i] : sample[0];
+            if (i >= S) break;
+            const int me = sample[i];
             const float x = xf[me], y = yf[me], z = zf[me];
-            // ascending (d2, position): j grows, so a later candidate replaces an entry only when strictly nearer
-            float e0 = INFINITY, e1 = INFINITY, e2 = INFINITY; int j1 = 0;
-            int j0 = 0;
-            for (int j = 0; j < S; ++j) {
-                const int o = sample[j];
-                const float d = d2_rn(x, y, z, xf[o], yf[o], zf[o]);
-                if (d < e2) {
-                    if (d < e0) { e2 = e1; e1 = e0; j1 = j0; e0 = d; j0 = j; }
-                    else if (d < e1) { e2 = e1; e1 = d; j1 = j; }
-                    else e2 = d;
+            float e0 = INFINITY, e1 = INFINITY, e2 = INFINITY; int j1 = 0, j0 = 0;
+            const int b0 = (int)sbox[i] - 1;
+            const int bi = b0 % g.nx + 1, bj = (b0 / g.nx) % g.ny + 1, bk = b0 / (g.nx * g.ny) + 1;
+            for (int nk = max(1, bk - 1); nk <= min(g.nz, bk + 1); ++nk)
+                for (int nj = max(1, bj - 1); nj <= min(g.ny, bj + 1); ++nj) {
+                    const int ilo = max(1, bi - 1), ihi = min(g.nx, bi + 1);
+                    const int row = g.nx * (nj - 1) + g.nx * g.ny * (nk - 1);
+                    const int jlo = selc[row + ilo], jhi = selc[row + ihi + 1];        // consecutive boxes = one run of samples
+                    for (int j = jlo; j < jhi; ++j) {
+                        const int o = sample[j];
+                        const float d = d2_rn(x, y, z, xf[o], yf[o], zf[o]);
+                        if (d < e2) {
+                            if (d < e0) { e2 = e1; e1 = e0; j1 = j0; e0 = d; j0 = j; }
+                            else if (d < e1) { e2 = e1; e1 = d; j1 = j; }
+                            else e2 = d;
+                        }
+                    }
+                }
+            if (!(e2 < lim2)) {
+                e0 = INFINITY; e1 = INFINITY; e2 = INFINITY; j1 = 0; j0 = 0;
+                for (int j = 0; j < S; ++j) {
+                    const int o = sample[j];
+                    const float d = d2_rn(x, y, z, xf[o], yf[o], zf[o]);
+                    if (d < e2) {
+                        if (d < e0) { e2 = e1; e1 = e0; j1 = j0; e0 = d; j0 = j; }
+                        else if (d < e1) { e2 = e1; e1 = d; j1 = j; }
+                        else e2 = d;
+                    }
                 }
             }
-            __syncwarp();
-            if (i < S) {
-                const float d1 = __fsqrt_rn(e1);
-                key64[i] = ((unsigned long long)__float_as_uint(d1) << 32) | ((unsigned long long)i << 16) | (unsigned long long)j1;
-                d2s[i] = __fsqrt_rn(e2);
-                keep[i] = 1;
-            }
+            const float d1 = __fsqrt_rn(e1);
+            key64[i] = ((unsigned long long)__float_as_uint(d1) << 32) | ((unsigned long long)i << 16) | (unsigned long long)j1;
+            d2s[i] = __fsqrt_rn(e2);
+            keep[i] = 1;
         }
         for (int i = S + tid; i < NP2; i += AS_THREADS) key64[i] = ~0ull;
         as_bitonic(key64, NP2);
@@ -906,14 +954,12 @@ int aivs_simplify_device(cudaStream_t st, long long* launches, int P, const doub
                          int* d_out_idx, int* d_bad, const DevAlloc& alloc, const char* tag) {
     if (cap <= AS_MAX && !getenv("KSS_AIVS_GENERAL")) {
         const AsLayout L = as_layout(cap);
-        static int smem_small = 0;
-        if (L.total > smem_small) {
-            if (cudaFuncSetAttribute(aivs_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total) != cudaSuccess)
-                return KSS_ERR_CUDA;
-            smem_small = L.total;
-        }
-        aivs_small_kernel<8><<<P, AS_THREADS, L.total, st>>>(d_pts, d_cnt, cap, d_point_num, point_num_all, d_out, out_cap,
-                                                             d_out_cnt, d_out_idx, d_bad);
+        const char* e = getenv("KSS_AIVS_GL");
+        const int gl = e ? atoi(e) : AS_GL;
+        auto kern = gl == 4 ? aivs_small_kernel<4> : gl == 8 ? aivs_small_kernel<8> : gl == 32 ? aivs_small_kernel<32> : aivs_small_kernel<16>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total) != cudaSuccess) return KSS_ERR_CUDA;
+        kern<<<P, AS_THREADS, L.total, st>>>(d_pts, d_cnt, cap, d_point_num, point_num_all, d_out, out_cap, d_out_cnt, d_out_idx,
+                                             d_bad);
         *launches += 1;
         return cudaGetLastError() == cudaSuccess ? KSS_OK : KSS_ERR_CUDA;
     }
