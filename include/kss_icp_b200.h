@@ -205,7 +205,8 @@ int kss_register_batch(kss_ctx* ctx, const kss_batch* b, kss_pair_result* result
 int kss_register_batch_device(kss_ctx* ctx, const kss_batch* b, kss_pair_result* d_results,
                               double* d_point_align);
 
-/* one pair, the exact flow of KSSICP_Registration (KSS_ICP.hpp:86-130) */
+/* one pair, the exact flow of KSSICP_Registration (KSS_ICP.hpp:86-130); sim_s = sim_t = NULL: raw clouds,
+ * simplified by the library first (KSS_ICP.hpp:53-82), n_s / n_t ignored */
 int kss_register(kss_ctx* ctx, const double* sim_s, int n_s, const double* sim_t, int n_t,
                  const double* full_s, int N_s, const double* full_t, int N_t,
                  double step, int max_iter, kss_pair_result* result, double* point_align);

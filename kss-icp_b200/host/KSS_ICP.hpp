@@ -1,9 +1,8 @@
 // KSS_ICP.hpp -- B200 drop-in for the reference header of the same name (PS_AIS_Simplification/KSS_ICP.hpp:38-393).
 // Same class KSSICP, same public methods and the public member pointAlign; every pcl::IterativeClosestPoint
 // run, the similarity applies and the final 4x4 apply go through the C ABI (include/kss_icp_b200.h).
-// The simplification step before the path (pointPipeline + AIVS_Simplification_Pro, KSS_ICP.hpp:71-81) is NOT
-// part of this replacement: the lines below call whatever pointPipeline.hpp / Method_AIVS_SimPro.hpp are on
-// the include path -- the reference's own in its tree, the stand-ins of this directory otherwise.
+// The simplification step before the path (pointPipeline + AIVS_Simplification_Pro, KSS_ICP.hpp:71-81) goes through
+// the headers of the same names in this directory, which forward to kss_aivs_simplify: the same points are kept.
 #pragma once
 #include <cfloat>
 #include <fstream>

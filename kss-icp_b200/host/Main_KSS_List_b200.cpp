@@ -26,38 +26,32 @@ int main(int argc, char** argv) {
 	const int iter = argc > 3 ? std::atoi(argv[3]) : 1000;
 	std::ifstream lf(argv[1]);
 	std::string line;
-	std::vector<kss_host::Cloud> S, T, simS, simT;
+	std::vector<kss_host::Cloud> S, T;
 	while (std::getline(lf, line)) {
 		std::istringstream ls(line);
 		std::string a, b;
 		if (!(ls >> a >> b)) continue;
 		kss_host::Cloud s = Load_PLY(a), t = Load_PLY(b);
 		if (s.empty() || t.empty()) { std::cerr << "skip " << line << "\n"; continue; }
-		int pNumber = (int)std::min(s.size(), t.size()) / 2;                     // KSS_ICP.hpp:57-66
-		if (pNumber > 2000) pNumber = 2000;
-		pointPipeline pp; AIVS_Simplification_Pro as;
-		pp.pointPipeline_init_point_withoutUniform(t); as.AIVS_Pro_init(pp.br, "target"); simT.push_back(as.AIVS_simplification(pNumber));
-		pp.pointPipeline_init_point_withoutUniform(s); as.AIVS_Pro_init(pp.br, "source"); simS.push_back(as.AIVS_simplification(pNumber));
 		S.push_back(s); T.push_back(t);
 	}
 	const int P = (int)S.size();
 	if (P == 0) { std::cerr << "no pairs\n"; return 1; }
-	size_t cs = 0, ct = 0, cS = 0, cT = 0;
-	for (int p = 0; p < P; ++p) { cs = std::max(cs, simS[p].size()); ct = std::max(ct, simT[p].size()); cS = std::max(cS, S[p].size()); cT = std::max(cT, T[p].size()); }
-	std::vector<double> bs(P * cs * 3), bt(P * ct * 3), bS(P * cS * 3), bT(P * cT * 3);
-	std::vector<int> ns(P), nt(P), nS(P), nT(P);
+	// raw clouds: sim_s = sim_t = NULL makes the library run the pNumber rule and both AIVS simplifications
+	// (KSS_ICP.hpp:53-82) on the device, in the same batch
+	size_t cS = 0, cT = 0;
+	for (int p = 0; p < P; ++p) { cS = std::max(cS, S[p].size()); cT = std::max(cT, T[p].size()); }
+	std::vector<double> bS(P * cS * 3), bT(P * cT * 3);
+	std::vector<int> nS(P), nT(P);
 	auto put = [](std::vector<double>& dst, size_t cap, int p, const kss_host::Cloud& c) {
 		for (size_t i = 0; i < c.size(); ++i) for (int a = 0; a < 3; ++a) dst[((size_t)p * cap + i) * 3 + a] = c[i][a];
 	};
-	for (int p = 0; p < P; ++p) {
-		put(bs, cs, p, simS[p]); put(bt, ct, p, simT[p]); put(bS, cS, p, S[p]); put(bT, cT, p, T[p]);
-		ns[p] = (int)simS[p].size(); nt[p] = (int)simT[p].size(); nS[p] = (int)S[p].size(); nT[p] = (int)T[p].size();
-	}
+	for (int p = 0; p < P; ++p) { put(bS, cS, p, S[p]); put(bT, cT, p, T[p]); nS[p] = (int)S[p].size(); nT[p] = (int)T[p].size(); }
 	kss_batch b;
 	kss_batch_default(&b);
-	b.n_pairs = P; b.cap_s = (int)cs; b.cap_t = (int)ct; b.cap_S = (int)cS; b.cap_T = (int)cT;
-	b.sim_s = bs.data(); b.sim_t = bt.data(); b.full_s = bS.data(); b.full_t = bT.data();
-	b.cnt_s = ns.data(); b.cnt_t = nt.data(); b.cnt_S = nS.data(); b.cnt_T = nT.data();
+	b.n_pairs = P; b.cap_S = (int)cS; b.cap_T = (int)cT;
+	b.full_s = bS.data(); b.full_t = bT.data();
+	b.cnt_S = nS.data(); b.cnt_T = nT.data();
 	b.step = step; b.icp.max_iterations = iter;
 	std::vector<kss_pair_result> res(P);
 	auto t0 = std::chrono::steady_clock::now();

@@ -1,8 +1,8 @@
-// pointPipeline.hpp -- STAND-IN for the reference's pre-processing front end (pointPipeline.hpp:88-101 +
-// ballRegionCompute.hpp).  The voxel-grid / AIVS simplification runs BEFORE the registration hot path and is
-// outside this round's scope; this header only keeps the call surface KSS_ICP.hpp uses
-// (`pointPipeline::pointPipeline_init_point_withoutUniform(cloud)` and the `br` member handed to AIVS).
-// In the reference's own tree, keep its pointPipeline.hpp instead.
+// pointPipeline.hpp -- B200 drop-in for the part of the reference's front end KSS-ICP uses:
+// pointPipeline::pointPipeline_init_point_withoutUniform(cloud) (pointPipeline.hpp:88-101) and the `br` member it
+// hands to AIVS_Pro_init.  The border scan and the BallRegion box grid (ballRegionCompute.hpp) are rebuilt on the GPU
+// inside kss_aivs_simplify, so `br` only carries the cloud.  Loading, normal estimation and the other pointPipeline
+// entry points are outside the registration path (out of scope).
 #pragma once
 #include <vector>
 

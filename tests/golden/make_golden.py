@@ -8,7 +8,8 @@
    (PS_AIS_Simplification/data/registration/<Model>.{wlop,gird}, known rotation in transfer.txt),
    decimated by a fixed stride so the file stays small, float32.
 2. golden_oracle.npz   -- what the CPU oracle (oracle/kss_oracle.cpp) computes on those inputs:
-   MiddleAlign, the 9x9x9 sweep grid, minima, judge / final ICP, metrics.  The oracle is the only
+   MiddleAlign, the 9x9x9 sweep grid, minima, judge / final ICP, metrics, the AIVS index lists and the
+   registration of the AIVS-simplified clouds.  The oracle is the only
    CPU restatement available (the reference needs PCL 1.8.1 / FLANN / Eigen and cannot run here),
    so these vectors pin the ORACLE against regressions and pin the GPU path against the oracle;
    the link to the reference itself is the known-answer rotation of transfer.txt checked in
@@ -55,6 +56,13 @@ def main():
             gold[name + "_canon_" + k] = np.asarray(reg[k])
             gold[name + "_serial_" + k] = np.asarray(ser[k])
         gold[name + "_axis_angle"] = np.array([{"x": 0, "y": 1, "z": 2}[axis], ang])
+        # AIVS simplification of both clouds with the pNumber rule, and the registration behind it
+        pn = min(len(s), len(t)) // 2
+        sim_s, idx_s = okss.aivs_simplify(s, pn); sim_t, idx_t = okss.aivs_simplify(t, pn)
+        raw = okss.register(sim_s, sim_t, s, t, step=8.0, max_iter=1000, sum_order=okss.SUM_CANON256, method=okss.NN_KDTREE)
+        gold[name + "_aivs_src_idx"] = idx_s; gold[name + "_aivs_tgt_idx"] = idx_t
+        for k in ("winner", "n_minima", "final_fitness", "T", "mse", "rmse", "mae"):
+            gold[name + "_raw_" + k] = np.asarray(raw[k])
     np.savez_compressed(os.path.join(out, "fixtures_pairs.npz"), **pairs)
     np.savez_compressed(os.path.join(out, "golden_oracle.npz"), **gold)
     print("wrote", {k: v.shape for k, v in pairs.items()})

@@ -190,3 +190,23 @@ def test_aivs_many_random_shapes(ctx, okss, pkg):
         o_idx = okss.aivs_simplify(pts[p, :cnt[p]], int(pn[p]))[1]
         assert ocnt[p] == len(o_idx), p
         assert np.array_equal(oidx[p, :ocnt[p]], o_idx), p
+
+
+@pytest.mark.parametrize("model", ["Bunny", "Horse", "Dog"])
+def test_aivs_golden_fixtures_from_reference_data(ctx, model):
+    """the reference's own shipped clouds (decimated fixtures) against the committed golden vectors: AIVS index lists
+    and the raw-cloud registration behind them, no oracle at run time"""
+    import os
+    gd = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gd, "golden_oracle.npz")); fx = np.load(os.path.join(gd, "fixtures_pairs.npz"))
+    s = fx[model + "_src"].astype(np.float64); t = fx[model + "_tgt"].astype(np.float64)
+    pn = min(len(s), len(t)) // 2
+    assert np.array_equal(ctx.aivs_simplify(s, pn)[1], g[model + "_aivs_src_idx"])
+    assert np.array_equal(ctx.aivs_simplify(t, pn)[1], g[model + "_aivs_tgt_idx"])
+    cap = max(len(s), len(t))
+    fs = np.zeros((1, cap, 3)); ft = np.zeros((1, cap, 3)); fs[0, :len(s)] = s; ft[0, :len(t)] = t
+    r = ctx.register_batch(None, None, fs, ft, counts=(None, None, np.array([len(s)], np.int32), np.array([len(t)], np.int32)))[0]
+    assert int(r["winner"]) == int(g[model + "_raw_winner"]) and int(r["n_minima"]) == int(g[model + "_raw_n_minima"])
+    assert np.array_equal(r["T"].reshape(4, 4), g[model + "_raw_T"])
+    for k in ("final_fitness", "mse", "rmse", "mae"):
+        assert float(r[k]) == float(g[model + "_raw_" + k]), k

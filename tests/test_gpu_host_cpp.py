@@ -21,17 +21,13 @@ def _write_ply(path, pts):
             f.write("%.9g %.9g %.9g\n" % (np.float32(p[0]), np.float32(p[1]), np.float32(p[2])))
 
 
-def _stride(c, n):
-    N = len(c)
-    return c if n >= N else c[(np.arange(n) * N) // n]
-
-
-def _expected(ctx, s, t):
+def _expected(ctx, okss, s, t):
+    """KSSICP_init + KSSICP_Registration + PCR_QM with the oracle's AIVS in front of the C ABI's registration"""
     pn = min(min(len(s), len(t)) // 2, 2000)
-    return ctx.register(_stride(s, pn), _stride(t, pn), s, t)
+    return ctx.register(okss.aivs_simplify(s, pn)[0], okss.aivs_simplify(t, pn)[0], s, t)
 
 
-def test_unmodified_reference_main(ctx, pkg, tmp_path):
+def test_unmodified_reference_main(ctx, okss, pkg, tmp_path):
     exe = os.path.join(BIN, "Main_KSS_ICP")
     if not os.path.exists(exe):
         pytest.skip("Main_KSS_ICP was not built (reference tree absent at build time)")
@@ -43,14 +39,14 @@ def test_unmodified_reference_main(ctx, pkg, tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     m = re.search(r"Registration Measure:MSE: (\S+) RMSE: (\S+) MAE: (\S+)", out.stdout)
     assert m, out.stdout[-2000:]
-    exp = _expected(ctx, p["full_s"], p["full_t"])
+    exp = _expected(ctx, okss, p["full_s"], p["full_t"])
     got = [float(x) for x in m.groups()]
     assert np.allclose(got, [exp["mse"], exp["rmse"], exp["mae"]], rtol=2e-5)       # 6 significant digits printed
     xyz = (d / "Registration.xyz").read_text().split()
     assert int(xyz[0]) == 1500 and len(xyz) == 1 + 3 * 1500                        # save_PointCloud (Main_KSS_ICP.cpp:49-59)
 
 
-def test_batch_driver(ctx, pkg, tmp_path):
+def test_batch_driver(ctx, okss, pkg, tmp_path):
     exe = os.path.join(BIN, "Main_KSS_List_b200")
     if not os.path.exists(exe):
         pytest.skip("batch driver not built")
@@ -60,7 +56,7 @@ def test_batch_driver(ctx, pkg, tmp_path):
         a, b = tmp_path / ("s%d.ply" % i), tmp_path / ("t%d.ply" % i)
         _write_ply(a, p["full_s"]); _write_ply(b, p["full_t"])
         lines.append("%s %s" % (a, b))
-        exp.append(_expected(ctx, p["full_s"], p["full_t"]))
+        exp.append(_expected(ctx, okss, p["full_s"], p["full_t"]))
     (tmp_path / "list.txt").write_text("\n".join(lines) + "\n")
     out = subprocess.run([exe, str(tmp_path / "list.txt")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]

@@ -176,3 +176,53 @@ def test_pcr_qm_definition(okss):
         mse += float(x); mae += float(np.sqrt(np.float64(x)))
     m = okss.nn_metrics(a, t)
     assert m[0] == mse / 300 and m[1] == np.sqrt(mse / 300) and m[2] == mae / 300
+
+
+# ------------------------------------------------------------------ AIVS simplification
+@pytest.mark.parametrize("model", ["Bunny", "Horse", "Dog"])
+def test_aivs_matches_golden(okss, gold, model):
+    g, fx = gold
+    s = fx[model + "_src"].astype(np.float64); t = fx[model + "_tgt"].astype(np.float64)
+    pn = min(len(s), len(t)) // 2
+    out, idx = okss.aivs_simplify(s, pn)
+    assert np.array_equal(idx, g[model + "_aivs_src_idx"])
+    assert np.array_equal(out, s[idx])
+    assert np.array_equal(okss.aivs_simplify(t, pn)[1], g[model + "_aivs_tgt_idx"])
+
+
+def test_aivs_properties(okss):
+    """exact target size after the trim, no point twice, an even spread: the largest hole of the simplified cloud
+    stays within a small multiple of the mean sample spacing (what farthest point sampling is for)"""
+    rng = np.random.default_rng(3)
+    u = rng.normal(size=(4000, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    u[:2000] *= 1.0 + 0.05 * rng.random((2000, 1))              # uneven density
+    out, idx = okss.aivs_simplify(u, 1000)
+    assert len(idx) == 1000 and len(np.unique(idx)) == 1000
+    assert np.array_equal(out, u[idx])
+    d = np.sqrt(((u[:, None, :] - out[None, :, :]) ** 2).sum(-1)).min(1)
+    spacing = np.sqrt(4 * np.pi / 1000)
+    assert d.max() < 1.5 * spacing
+    # pointNum above what the quotas give: no trim, fewer points (SURVEY B12)
+    few, fidx = okss.aivs_simplify(u, 20)
+    assert len(fidx) <= 20
+
+
+def test_aivs_box_scale_rule(okss):
+    """EstimateBoxScale (ballRegionCompute.hpp:1194-1214): 10 boxes along the longest axis below 1e4 points -> a cloud
+    on a 10-cell lattice with one point per cell and pointNum = n keeps every point"""
+    g = np.stack(np.meshgrid(np.arange(10.0), np.arange(10.0), np.arange(10.0)), -1).reshape(-1, 3) + 0.5
+    g = np.concatenate([g, [[0.0, 0.0, 0.0], [10.0, 10.0, 10.0]]])
+    out, idx = okss.aivs_simplify(g, len(g))
+    assert len(idx) == len(g) and len(np.unique(idx)) == len(g)
+
+
+def test_raw_batch_equals_simplify_then_register(okss):
+    rng = np.random.default_rng(4)
+    P, n = 2, 600
+    fs = rng.normal(size=(P, n, 3)); ft = fs[:, ::-1, :] * 1.3 + 0.2
+    res, _ = okss.register_batch(None, None, fs, ft, threads=2)
+    for p in range(P):
+        a = okss.aivs_simplify(fs[p], n // 2)[0]; b = okss.aivs_simplify(ft[p], n // 2)[0]
+        one = okss.register(a, b, fs[p], ft[p])
+        assert res[p]["final_fitness"] == one["final_fitness"] and res[p]["rmse"] == one["rmse"]
+        assert np.array_equal(res[p]["T"], one["T"])
