@@ -211,6 +211,9 @@ int kss_register(kss_ctx* ctx, const double* sim_s, int n_s, const double* sim_t
                  const double* full_s, int N_s, const double* full_t, int N_t,
                  double step, int max_iter, kss_pair_result* result, double* point_align);
 
+/* diagnostics for tools/: copies a range of a named internal device buffer to the host (names are internal) */
+int kss_debug_read(kss_ctx* ctx, const char* name, size_t offset, size_t bytes, void* dst);
+
 #ifdef __cplusplus
 }
 #endif

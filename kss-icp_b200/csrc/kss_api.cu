@@ -182,6 +182,8 @@ int cg_buffers(kss_ctx* ctx, int P, CgBuffers* cg) {
     BUF("cg_arena", (size_t)P * cg_arena_entries_per_pair(), &cg->arena);
     BUF("cg_cursor", (size_t)P, &cg->cursor);
     BUF("cg_ok", (size_t)P, &cg->ok);
+    BUF("cg_wl", (size_t)P * cg_worklist_entries_per_pair(), &cg->wl);
+    BUF("cg_wl_cnt", (size_t)P, &cg->wl_cnt);
     return KSS_OK;
 }
 
@@ -297,7 +299,7 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
 }
 
 size_t per_pair_ws_bytes(const kss_batch& b, int H, int slots) {
-    size_t v = (cg_enabled() ? cg_hdr_words_per_pair() * 4 + cg_arena_entries_per_pair() * 2 + 64 : 0) +
+    size_t v = (cg_enabled() ? cg_hdr_words_per_pair() * 4 + cg_arena_entries_per_pair() * 2 + cg_worklist_entries_per_pair() * 2 + 64 : 0) +
                (size_t)b.cap_s * H * 8 + (size_t)b.cap_s * 30 + (size_t)pad32(b.cap_t) * 18 + (size_t)H * 12 +
                (size_t)(1 + slots) * 96 + (size_t)b.cap_S * 26 + (size_t)pad32(b.cap_T) * 18 + 8192;
     return v;
@@ -811,6 +813,16 @@ int kss_aivs_simplify_batch_device(kss_ctx* ctx, int n_clouds, const double* d_p
     int r = aivs_simplify_device(ctx->stream, &ctx->launches, n_clouds, d_pts, d_cnt, cap, d_point_num, point_num, d_out,
                                  out_cap, d_out_cnt, d_out_idx, d_bad, alloc, "u");
     if (r) return fail(ctx, r, "AIVS simplification failed to launch");
+    return KSS_OK;
+}
+
+// diagnostics: copy part of a named internal device buffer to the host (tools/ only; names are not a stable interface)
+int kss_debug_read(kss_ctx* ctx, const char* name, size_t offset, size_t bytes, void* dst) {
+    if (!ctx || !name || !dst) return KSS_ERR_ARG;
+    auto it = ctx->bufs.find(name);
+    if (it == ctx->bufs.end() || !it->second.p || offset + bytes > it->second.cap) return fail(ctx, KSS_ERR_ARG, "kss_debug_read: no such buffer / range");
+    CU(cudaMemcpyAsync(dst, (const unsigned char*)it->second.p + offset, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return KSS_OK;
 }
 

@@ -27,6 +27,13 @@ constexpr int CG_NG = CG_NG0 << (CG_LEVELS - 1);
 constexpr int CG_CNT_BITS = 11;               // header = (offset/4 << 11) | count ; count 2047 = "search everything"
 constexpr unsigned CG_CNT_MASK = (1u << CG_CNT_BITS) - 1u;
 constexpr size_t CG_ARENA = (size_t)3 << 19;  // 1.5 M u16 entries per pair (all levels); overflow -> tile search
+// Sparse fifth level: a finest-level cell whose list has >= CG_REFINE_MIN entries is cut into its 8 octants, each with
+// its own (shorter) list.  Its header then carries count CG_REFINED and the offset of 8 child headers in the arena.
+constexpr unsigned CG_REFINED = CG_CNT_MASK - 1u;
+constexpr int CG_WL_CAP = 12288;              // refined cells per pair at most (the rest simply keep their list)
+#ifndef CG_REFINE_MIN
+#define CG_REFINE_MIN 7
+#endif
 __host__ __device__ constexpr int cg_ng(int l) { return CG_NG0 << l; }
 __host__ __device__ constexpr size_t cg_hdr_base(int l) {     // start of level l in the per-pair header array
     size_t b = 0;
@@ -58,9 +65,16 @@ __device__ __forceinline__ unsigned long long cg_query(const CgView& g, const fl
     unsigned cnt = CG_CNT_MASK, off = 0;
     if (fx >= 0.0f && fy >= 0.0f && fz >= 0.0f && fx < ngf && fy < ngf && fz < ngf) {
         const int cell = (int)fx + CG_NG * ((int)fy + CG_NG * (int)fz);
-        const unsigned h = g.hdr[cell];
+        unsigned h = g.hdr[cell];
         cnt = h & CG_CNT_MASK;
         off = (h >> CG_CNT_BITS) << 2;
+        if (cnt == CG_REFINED) {
+            const int oct = ((fx - (float)(int)fx) >= 0.5f ? 1 : 0) | ((fy - (float)(int)fy) >= 0.5f ? 2 : 0) |
+                            ((fz - (float)(int)fz) >= 0.5f ? 4 : 0);
+            h = __ldg(reinterpret_cast<const unsigned*>(g.list + off) + oct);
+            cnt = h & CG_CNT_MASK;
+            off = (h >> CG_CNT_BITS) << 2;
+        }
     }
     float best = __int_as_float(0x7f800000);
     unsigned long long bestkey = 0xffffffffffffffffull;

@@ -16,9 +16,11 @@ typedef kss_pair_result PairOut;
 // CG_ARENA u16 list entries, an arena cursor and an ok flag
 struct CgBuffers {
     float* geom; unsigned* hdr; unsigned short* arena; unsigned* cursor; int* ok;
+    unsigned short* wl; unsigned* wl_cnt;      // finest-level cells to refine (kss_cg.cuh), per pair CG_WL_CAP entries
 };
 size_t cg_hdr_words_per_pair();
 size_t cg_arena_entries_per_pair();
+size_t cg_worklist_entries_per_pair();
 
 struct IcpArgs {
     // source: original (double) simplified cloud, similarity applied in-kernel (mode 0/1) or used as is (mode 2)

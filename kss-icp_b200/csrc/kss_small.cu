@@ -169,7 +169,7 @@ middle_align_kernel(const double* __restrict__ sim_s, const int* __restrict__ cn
 __global__ void __launch_bounds__(256)
 cg_geom_kernel(int mode, const double* __restrict__ a, const int* __restrict__ cnt_a, int cap_a,
                const double* __restrict__ b, const int* __restrict__ cnt_b, int cap_b,
-               float* __restrict__ geom, unsigned* __restrict__ cursor, int* __restrict__ ok) {
+               float* __restrict__ geom, unsigned* __restrict__ cursor, int* __restrict__ ok, unsigned* __restrict__ wl_cnt) {
     __shared__ unsigned bb[6];
     __shared__ unsigned long long r2max;
     const int p = blockIdx.x;
@@ -210,6 +210,7 @@ cg_geom_kernel(int mode, const double* __restrict__ a, const int* __restrict__ c
         g[5] = g[6] = g[7] = 0.0f;
         cursor[p] = 0u;
         ok[p] = 1;
+        wl_cnt[p] = 0u;
     }
 }
 
@@ -219,32 +220,43 @@ cg_geom_kernel(int mode, const double* __restrict__ a, const int* __restrict__ c
 // addresses per warp).  Pass A: p_c = the centre's nearest target, d_c^2.  Pass B: keep p iff
 // d2 <= ((d_c + 2 rho)(1+1e-4))^2 and p_c does not dominate p over the whole cell; remembered as a bit mask (lists <= 64) so pass C only re-reads
 // indices.  Space: one atomicAdd per warp on the pair's arena cursor (list order never matters).
+// SPARSE: the fifth, sparse level -- one thread per octant of every worklisted finest-level cell.
+template <bool SPARSE>
 __global__ void __launch_bounds__(256)
 cg_level_kernel(int level, const float4* __restrict__ t_sorted, const int* __restrict__ cnt_t, int cap_tpad,
                 const float* __restrict__ geom, unsigned* __restrict__ hdr_all,
-                unsigned short* __restrict__ arena_all, unsigned* __restrict__ cursor, int* __restrict__ ok) {
+                unsigned short* __restrict__ arena_all, unsigned* __restrict__ cursor, int* __restrict__ ok,
+                unsigned short* __restrict__ wl_all, unsigned* __restrict__ wl_cnt) {
     const int p = blockIdx.y;
     const int lane = threadIdx.x & 31;
-    const int ng = cg_ng(level);
+    const int ng = SPARSE ? 2 * CG_NG : cg_ng(level);
     const int png = ng >> 1;
-    const int ncells = ng * ng * ng;
+    const int ncells = SPARSE ? 8 * (int)min(wl_cnt[p], (unsigned)CG_WL_CAP) : ng * ng * ng;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;        // = parent * 8 + child
     if (tid - lane >= ncells) return;                              // whole warp out of range
     const bool live = tid < ncells;
     const int n_t = cnt_t[p];
     const float4* __restrict__ tgt = t_sorted + (size_t)p * cap_tpad;
-    unsigned* hdr = hdr_all + (size_t)p * CG_HDR_TOTAL + cg_hdr_base(level);
+    unsigned* hdr = hdr_all + (size_t)p * CG_HDR_TOTAL + cg_hdr_base(SPARSE ? CG_LEVELS - 1 : level);
     unsigned short* arena = arena_all + (size_t)p * CG_ARENA;
     const float* gm = geom + (size_t)p * 8;
     const float R = gm[3], ballR = gm[4];
     const float h = 2.0f * R / (float)ng;
     const float rho = h * 0.8660254f * 1.002f;
-    const int child = tid & 7, parent = tid >> 3;
+    const int child = tid & 7;
+    int parent = tid >> 3;
 
     int ix = 0, iy = 0, iz = 0, m_p = 0;
     const unsigned short* plist = nullptr;
     if (live) {
-        if (level == 0) {
+        if (SPARSE) {
+            parent = wl_all[(size_t)p * CG_WL_CAP + parent];                 // a cell of the finest dense level
+            const int px = parent & (CG_NG - 1), py = (parent / CG_NG) & (CG_NG - 1), pz = parent / (CG_NG * CG_NG);
+            ix = 2 * px + (child & 1); iy = 2 * py + ((child >> 1) & 1); iz = 2 * pz + (child >> 2);
+            const unsigned ph = hdr[parent];
+            m_p = (int)(ph & CG_CNT_MASK);
+            plist = arena + ((size_t)(ph >> CG_CNT_BITS) << 2);
+        } else if (level == 0) {
             ix = tid & 3; iy = (tid >> 2) & 3; iz = tid >> 4;
             m_p = n_t;
         } else {
@@ -315,24 +327,38 @@ cg_level_kernel(int level, const float4* __restrict__ t_sorted, const int* __res
             ++k;
         }
     }
-    const bool huge = k >= (int)CG_CNT_MASK;
+    const bool huge = k >= (int)CG_REFINED;
     const int tot4 = huge ? 0 : ((k + 3) & ~3);
-    // warp exclusive scan of tot4, one atomicAdd per warp
-    int incl = tot4;
+    // warp exclusive scan of the space needed, one atomicAdd per warp; a refined cell also needs 8 child headers
+    // (16 entries), reserved by its octant 0
+    const int need = tot4 + ((SPARSE && live && child == 0) ? 16 : 0);
+    int incl = need;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(KSS_FULL, incl, o); if (lane >= o) incl += y; }
     const int wtot = __shfl_sync(KSS_FULL, incl, 31);
     unsigned base = 0;
     if (lane == 0 && wtot > 0) base = atomicAdd(&cursor[p], (unsigned)wtot);
     base = __shfl_sync(KSS_FULL, base, 0);
-    if ((size_t)base + (size_t)wtot > CG_ARENA) {                         // arena exhausted: pair falls back
-        if (lane == 0) atomicExch(&ok[p], 0);
+    unsigned off = base + (unsigned)(incl - need);
+    const unsigned blk = __shfl_sync(KSS_FULL, off, lane & ~7);           // the child-header block of this thread's parent
+    if ((size_t)base + (size_t)wtot > CG_ARENA) {
+        if (SPARSE) return;                                               // no room: the cells keep their unrefined lists
+        if (lane == 0) atomicExch(&ok[p], 0);                             // arena exhausted: pair falls back
         if (live) hdr[cell] = 0u;
         return;
     }
     if (!live) return;
-    const unsigned off = base + (unsigned)(incl - tot4);
-    hdr[cell] = huge ? CG_CNT_MASK : (k == 0 ? 0u : (((off >> 2) << CG_CNT_BITS) | (unsigned)k));
+    if (SPARSE) {
+        if (child == 0) off += 16u;
+        reinterpret_cast<unsigned*>(arena + blk)[child] = huge ? CG_CNT_MASK : (k == 0 ? 0u : (((off >> 2) << CG_CNT_BITS) | (unsigned)k));
+        if (child == 0) hdr[parent] = ((blk >> 2) << CG_CNT_BITS) | CG_REFINED;
+    } else {
+        hdr[cell] = huge ? CG_CNT_MASK : (k == 0 ? 0u : (((off >> 2) << CG_CNT_BITS) | (unsigned)k));
+        if (level == CG_LEVELS - 1 && wl_all != nullptr && !huge && k >= CG_REFINE_MIN) {
+            const unsigned slot = atomicAdd(&wl_cnt[p], 1u);
+            if (slot < (unsigned)CG_WL_CAP) wl_all[(size_t)p * CG_WL_CAP + slot] = (unsigned short)cell;
+        }
+    }
     if (huge || k == 0) return;
     // ---- pass C: write the list, padded to a multiple of 4 with a valid candidate
     unsigned short* out = arena + off;
@@ -972,12 +998,19 @@ cudaError_t launch_sweep(cudaStream_t st, int P, const double* s_al, const int* 
 cudaError_t launch_cg_build(cudaStream_t st, int P, int geom_mode, const double* a, const int* cnt_a, int cap_a,
                             const double* b, const int* cnt_b, int cap_b, const float4* t_sorted, const int* cnt_t,
                             int cap_tpad, const CgBuffers& cg, int* launches) {
-    cg_geom_kernel<<<P, 256, 0, st>>>(geom_mode, a, cnt_a, cap_a, b, cnt_b, cap_b, cg.geom, cg.cursor, cg.ok);
+    cg_geom_kernel<<<P, 256, 0, st>>>(geom_mode, a, cnt_a, cap_a, b, cnt_b, cap_b, cg.geom, cg.cursor, cg.ok, cg.wl_cnt);
     int n = 1;
+    const char* e = getenv("KSS_CG_NO_REFINE");
+    const bool refine = !(e && e[0] == '1');
     for (int l = 0; l < CG_LEVELS; ++l) {
         const int ncells = cg_ng(l) * cg_ng(l) * cg_ng(l);
-        cg_level_kernel<<<dim3((ncells + 255) / 256, P), 256, 0, st>>>(l, t_sorted, cnt_t, cap_tpad, cg.geom, cg.hdr, cg.arena,
-                                                                  cg.cursor, cg.ok);
+        cg_level_kernel<false><<<dim3((ncells + 255) / 256, P), 256, 0, st>>>(l, t_sorted, cnt_t, cap_tpad, cg.geom, cg.hdr, cg.arena,
+                                                                         cg.cursor, cg.ok, refine ? cg.wl : nullptr, cg.wl_cnt);
+        ++n;
+    }
+    if (refine) {
+        cg_level_kernel<true><<<dim3((8 * CG_WL_CAP + 255) / 256, P), 256, 0, st>>>(CG_LEVELS, t_sorted, cnt_t, cap_tpad, cg.geom, cg.hdr,
+                                                                               cg.arena, cg.cursor, cg.ok, cg.wl, cg.wl_cnt);
         ++n;
     }
     if (launches) *launches = n;
@@ -985,6 +1018,7 @@ cudaError_t launch_cg_build(cudaStream_t st, int P, int geom_mode, const double*
 }
 size_t cg_hdr_words_per_pair() { return CG_HDR_TOTAL; }
 size_t cg_arena_entries_per_pair() { return CG_ARENA; }
+size_t cg_worklist_entries_per_pair() { return CG_WL_CAP; }
 
 cudaError_t launch_sweep_finalize(cudaStream_t st, int P, const double* rbuf, const int* cnt_s, int cap_s, int hpad,
                                   int G, int score_mode, double* value, int* best_h, int* minima, int* n_minima) {
