@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "libkss_icp_b200.so")
+LIB_PATH = os.environ.get("KSS_ICP_B200_LIB") or os.path.join(_DIR, "libkss_icp_b200.so")   # override: A/B builds in tools/
 HEADER_PATH = os.path.join(os.path.dirname(_DIR), "include", "kss_icp_b200.h")
 
 KSS_OK = 0

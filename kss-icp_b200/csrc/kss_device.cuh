@@ -181,20 +181,24 @@ __device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b)
 __device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float sqrt_(float a) { return __fsqrt_rn(a); }
 
-__device__ __forceinline__ void rot_left(float* W, int p, int q, Rot2 j) {
+// All indices below are compile-time constants so that W, U, V stay in registers: the SVD runs on ONE thread between
+// two barriers of the ICP loop, and local-memory round trips in its dependency chain were a third of the loop time.
+template <int P, int Q>
+__device__ __forceinline__ void rot_left(float (&W)[9], Rot2 j) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float x = W[3 * p + k], y = W[3 * q + k];
-        W[3 * p + k] = add_(mul_(j.c, x), mul_(j.s, y));
-        W[3 * q + k] = add_(mul_(-j.s, x), mul_(j.c, y));
+        float x = W[3 * P + k], y = W[3 * Q + k];
+        W[3 * P + k] = add_(mul_(j.c, x), mul_(j.s, y));
+        W[3 * Q + k] = add_(mul_(-j.s, x), mul_(j.c, y));
     }
 }
-__device__ __forceinline__ void rot_right(float* W, int p, int q, Rot2 j) {
+template <int P, int Q>
+__device__ __forceinline__ void rot_right(float (&W)[9], Rot2 j) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float x = W[3 * k + p], y = W[3 * k + q];
-        W[3 * k + p] = sub_(mul_(j.c, x), mul_(j.s, y));
-        W[3 * k + q] = add_(mul_(j.s, x), mul_(j.c, y));
+        float x = W[3 * k + P], y = W[3 * k + Q];
+        W[3 * k + P] = sub_(mul_(j.c, x), mul_(j.s, y));
+        W[3 * k + Q] = add_(mul_(j.s, x), mul_(j.c, y));
     }
 }
 __device__ __forceinline__ Rot2 sym_jacobi(float x, float y, float z) {
@@ -211,71 +215,95 @@ __device__ __forceinline__ Rot2 sym_jacobi(float x, float y, float z) {
     return r;
 }
 
-__device__ inline void svd3(const float* A, float* U, float* s, float* V) {
+// one two-sided Jacobi step on the (P,Q) block; returns false when the block is already diagonal enough
+template <int P, int Q>
+__device__ __forceinline__ bool svd3_step(float (&W)[9], float (&U)[9], float (&V)[9], float& maxDiag) {
+    const float precision = 2.0f * FLT_EPSILON;
+    const float tiny = FLT_MIN;
+    const float thr = fmaxf(tiny, mul_(precision, maxDiag));
+    if (!(fabsf(W[3 * P + Q]) > thr || fabsf(W[3 * Q + P]) > thr)) return false;
+    const float m00 = W[3 * P + P], m01 = W[3 * P + Q], m10 = W[3 * Q + P], m11 = W[3 * Q + Q];
+    Rot2 r1;
+    const float t = add_(m00, m11), d = sub_(m10, m01);
+    if (fabsf(d) < tiny) { r1.s = 0.0f; r1.c = 1.0f; }
+    else {
+        const float u = div_(t, d);
+        const float tmp = sqrt_(add_(1.0f, mul_(u, u)));
+        r1.s = div_(1.0f, tmp); r1.c = div_(u, tmp);
+    }
+    const float n00 = add_(mul_(r1.c, m00), mul_(r1.s, m10));
+    const float n01 = add_(mul_(r1.c, m01), mul_(r1.s, m11));
+    const float n11 = add_(mul_(-r1.s, m01), mul_(r1.c, m11));
+    const Rot2 jr = sym_jacobi(n00, n01, n11);
+    Rot2 jl;
+    jl.c = sub_(mul_(r1.c, jr.c), mul_(r1.s, -jr.s));
+    jl.s = add_(mul_(r1.c, -jr.s), mul_(r1.s, jr.c));
+    rot_left<P, Q>(W, jl);
+    Rot2 jlt; jlt.c = jl.c; jlt.s = -jl.s;
+    rot_right<P, Q>(U, jlt);
+    rot_right<P, Q>(W, jr);
+    rot_right<P, Q>(V, jr);
+    maxDiag = fmaxf(maxDiag, fmaxf(fabsf(W[3 * P + P]), fabsf(W[3 * Q + Q])));
+    return true;
+}
+
+template <int I, int J>
+__device__ __forceinline__ void svd3_swap(float (&s)[3], float (&U)[9], float (&V)[9]) {
+    const float ts = s[I]; s[I] = s[J]; s[J] = ts;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float tu = U[3 * k + I]; U[3 * k + I] = U[3 * k + J]; U[3 * k + J] = tu;
+        const float tv = V[3 * k + I]; V[3 * k + I] = V[3 * k + J]; V[3 * k + J] = tv;
+    }
+}
+
+__device__ __forceinline__ void svd3(const float (&A)[9], float (&U)[9], float (&s)[3], float (&V)[9]) {
     float scale = 0.0f;
+#pragma unroll
     for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(A[i]));
     if (!(scale > 0.0f)) scale = 1.0f;
     float W[9];
+#pragma unroll
     for (int i = 0; i < 9; ++i) W[i] = div_(A[i], scale);
+#pragma unroll
     for (int i = 0; i < 9; ++i) { U[i] = (i % 4 == 0) ? 1.0f : 0.0f; V[i] = U[i]; }
-    const float precision = 2.0f * FLT_EPSILON;
-    const float tiny = FLT_MIN;
     float maxDiag = fmaxf(fabsf(W[0]), fmaxf(fabsf(W[4]), fabsf(W[8])));
     bool finished = false;
     int guard = 0;
     while (!finished && guard++ < 64) {
-        finished = true;
-        for (int p = 1; p < 3; ++p)
-            for (int q = 0; q < p; ++q) {
-                float thr = fmaxf(tiny, mul_(precision, maxDiag));
-                if (fabsf(W[3 * p + q]) > thr || fabsf(W[3 * q + p]) > thr) {
-                    finished = false;
-                    float m00 = W[3 * p + p], m01 = W[3 * p + q], m10 = W[3 * q + p], m11 = W[3 * q + q];
-                    Rot2 r1;
-                    float t = add_(m00, m11), d = sub_(m10, m01);
-                    if (fabsf(d) < tiny) { r1.s = 0.0f; r1.c = 1.0f; }
-                    else {
-                        float u = div_(t, d);
-                        float tmp = sqrt_(add_(1.0f, mul_(u, u)));
-                        r1.s = div_(1.0f, tmp); r1.c = div_(u, tmp);
-                    }
-                    float n00 = add_(mul_(r1.c, m00), mul_(r1.s, m10));
-                    float n01 = add_(mul_(r1.c, m01), mul_(r1.s, m11));
-                    float n11 = add_(mul_(-r1.s, m01), mul_(r1.c, m11));
-                    Rot2 jr = sym_jacobi(n00, n01, n11);
-                    Rot2 jl;
-                    jl.c = sub_(mul_(r1.c, jr.c), mul_(r1.s, -jr.s));
-                    jl.s = add_(mul_(r1.c, -jr.s), mul_(r1.s, jr.c));
-                    rot_left(W, p, q, jl);
-                    Rot2 jlt; jlt.c = jl.c; jlt.s = -jl.s;
-                    rot_right(U, p, q, jlt);
-                    rot_right(W, p, q, jr);
-                    rot_right(V, p, q, jr);
-                    maxDiag = fmaxf(maxDiag, fmaxf(fabsf(W[3 * p + p]), fabsf(W[3 * q + q])));
-                }
-            }
+        // sweep order (p,q) = (1,0), (2,0), (2,1)
+        const bool a = svd3_step<1, 0>(W, U, V, maxDiag);
+        const bool b = svd3_step<2, 0>(W, U, V, maxDiag);
+        const bool c = svd3_step<2, 1>(W, U, V, maxDiag);
+        finished = !(a || b || c);
     }
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
-        float a = W[4 * i];
+        const float a = W[4 * i];
         s[i] = fabsf(a);
-        if (a < 0.0f) for (int k = 0; k < 3; ++k) U[3 * k + i] = -U[3 * k + i];
-    }
-    for (int i = 0; i < 3; ++i) s[i] = mul_(s[i], scale);
-    for (int i = 0; i < 3; ++i) {
-        int pos = i;
-        for (int k = i + 1; k < 3; ++k) if (s[k] > s[pos]) pos = k;
-        if (s[pos] == 0.0f) break;
-        if (pos != i) {
-            float ts = s[i]; s[i] = s[pos]; s[pos] = ts;
-            for (int k = 0; k < 3; ++k) {
-                float tu = U[3 * k + i]; U[3 * k + i] = U[3 * k + pos]; U[3 * k + pos] = tu;
-                float tv = V[3 * k + i]; V[3 * k + i] = V[3 * k + pos]; V[3 * k + pos] = tv;
-            }
+        if (a < 0.0f) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) U[3 * k + i] = -U[3 * k + i];
         }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s[i] = mul_(s[i], scale);
+    // selection sort, descending: position of the first strict maximum of the tail; stop at a zero maximum
+    {
+        const int pos = (s[2] > (s[1] > s[0] ? s[1] : s[0])) ? 2 : (s[1] > s[0] ? 1 : 0);
+        const float m = pos == 2 ? s[2] : (pos == 1 ? s[1] : s[0]);
+        if (m == 0.0f) return;
+        if (pos == 1) svd3_swap<0, 1>(s, U, V);
+        else if (pos == 2) svd3_swap<0, 2>(s, U, V);
+    }
+    {
+        const bool two = s[2] > s[1];
+        if ((two ? s[2] : s[1]) == 0.0f) return;
+        if (two) svd3_swap<1, 2>(s, U, V);
     }
 }
 
-__device__ __forceinline__ float det3(const float* m) {
+__device__ __forceinline__ float det3(const float (&m)[9]) {
     float h0 = mul_(m[0], sub_(mul_(m[4], m[8]), mul_(m[5], m[7])));
     float h1 = mul_(m[1], sub_(mul_(m[3], m[8]), mul_(m[5], m[6])));
     float h2 = mul_(m[2], sub_(mul_(m[3], m[7]), mul_(m[4], m[6])));
@@ -283,21 +311,25 @@ __device__ __forceinline__ float det3(const float* m) {
 }
 
 // pcl::umeyama tail: sigma, means -> 4x4 row-major rigid transform
-__device__ inline void umeyama_finish(const float* sigma, const float* smean, const float* dmean, float* T) {
+__device__ __forceinline__ void umeyama_finish(const float (&sigma)[9], const float (&smean)[3], const float (&dmean)[3], float (&T)[16]) {
     float U[9], sv[3], V[9];
     svd3(sigma, U, sv, V);
     float S[3] = {1.0f, 1.0f, 1.0f};
     if (det3(sigma) < 0.0f) S[2] = -1.0f;
     int rank = 0;
+#pragma unroll
     for (int i = 0; i < 3; ++i)
         if (!(fabsf(sv[i]) <= mul_(fabsf(sv[0]), 1e-5f))) ++rank;
     if (rank == 2) {
         if (mul_(det3(U), det3(V)) > 0.0f) { S[0] = S[1] = S[2] = 1.0f; }
         else { S[2] = -1.0f; }
     }
+#pragma unroll
     for (int i = 0; i < 16; ++i) T[i] = 0.0f;
     T[15] = 1.0f;
+#pragma unroll
     for (int a = 0; a < 3; ++a) {
+#pragma unroll
         for (int b = 0; b < 3; ++b) {
             float r = mul_(mul_(U[3 * a + 0], S[0]), V[3 * b + 0]);
             r = add_(r, mul_(mul_(U[3 * a + 1], S[1]), V[3 * b + 1]));
@@ -319,9 +351,11 @@ __device__ __forceinline__ void xform_point(const float* T, float x, float y, fl
     oz = add_(add_(add_(mul_(T[8], x), mul_(T[9], y)), mul_(T[10], z)), T[11]);
 }
 
-__device__ inline void mat4_mul(const float* A, const float* B, float* C) {
+__device__ __forceinline__ void mat4_mul(const float (&A)[16], const float (&B)[16], float (&C)[16]) {
     float R[16];
+#pragma unroll
     for (int i = 0; i < 4; ++i)
+#pragma unroll
         for (int j = 0; j < 4; ++j) {
             float r = mul_(A[4 * i + 0], B[0 + j]);
             r = add_(r, mul_(A[4 * i + 1], B[4 + j]));
@@ -329,6 +363,7 @@ __device__ inline void mat4_mul(const float* A, const float* B, float* C) {
             r = add_(r, mul_(A[4 * i + 3], B[12 + j]));
             R[4 * i + j] = r;
         }
+#pragma unroll
     for (int i = 0; i < 16; ++i) C[i] = R[i];
 }
 

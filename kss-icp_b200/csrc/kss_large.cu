@@ -862,11 +862,15 @@ lg_passB_kernel(const float4* __restrict__ cur, const float4* __restrict__ t_ori
     if (threadIdx.x == 0) {
         if (!enough) { st->done = 1; st->converged = 0; return; }      // min_number_correspondences_
         float sigma[9], T[16], F[16], sm[3], dm[3];
+#pragma unroll
         for (int i = 0; i < 9; ++i) sigma[i] = mul_(st->one_over_n, tot[i]);
+#pragma unroll
         for (int i = 0; i < 3; ++i) { sm[i] = st->smean[i]; dm[i] = st->dmean[i]; }
         umeyama_finish(sigma, sm, dm, T);
+#pragma unroll
         for (int i = 0; i < 16; ++i) F[i] = st->fin[i];
         mat4_mul(T, F, F);
+#pragma unroll
         for (int i = 0; i < 16; ++i) { st->Tk[i] = T[i]; st->fin[i] = F[i]; }
         st->apply_T = 1;
         const int it = st->iters + 1;

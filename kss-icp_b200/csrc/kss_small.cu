@@ -534,7 +534,10 @@ sweep_finalize_kernel(const double* __restrict__ rbuf, const int* __restrict__ c
 // mode 0: judge run      -> angles = accumulated loop values of best_h      (KSS_ICP.hpp:92-93)
 // mode 1: hypothesis l   -> angles = index*6.3/step of minima[l], only if judge fitness > thr
 // mode 2: explicit input -> src_f64 is used as is (kss_icp API, KSS_ICP.hpp:323-356)
-__global__ void __launch_bounds__(256, 4)
+#ifndef ICP_MIN_CTAS
+#define ICP_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(256, ICP_MIN_CTAS)
 icp_small_kernel(IcpArgs a) {
     extern __shared__ unsigned char smem_raw[];
     const int p = blockIdx.y;
@@ -731,11 +734,14 @@ icp_small_kernel(IcpArgs a) {
         // ---- (4) one thread: SVD/Kabsch, accumulate, convergence
         if (threadIdx.x == 0) {
             float sigma[9], smean[3] = {sm0, sm1, sm2}, dmean[3] = {dm0, dm1, dm2}, T[16];
+#pragma unroll
             for (int i = 0; i < 9; ++i) sigma[i] = red[7 + i];
             umeyama_finish(sigma, smean, dmean, T);
             float F[16];
+#pragma unroll
             for (int i = 0; i < 16; ++i) F[i] = fin[i];
             mat4_mul(T, F, F);
+#pragma unroll
             for (int i = 0; i < 16; ++i) { Tk[i] = T[i]; fin[i] = F[i]; }
             const double mse = __ddiv_rn(redd, (double)cnt);
             if (a.trace_T && iters < a.trace_cap)
