@@ -238,7 +238,7 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
         StageTimer tm(ctx, KSS_STAGE_CG_BUILD);
         int r = cg_buffers(ctx, P, &cgb); if (r) return r;
         int nl = 0;
-        CU(launch_cg_build(st, P, 0, s_al, cnt_s, cap_s, nullptr, nullptr, 0, t_sorted, cnt_t, cap_tpad, cgb, &nl));
+        CU(launch_cg_build(st, P, 0, s_al, cnt_s, cap_s, nullptr, nullptr, 0, t_sorted, t_inv, cap_t, cnt_t, cap_tpad, cgb, &nl));
         ctx->launches += nl;
         cg = &cgb;
     }
@@ -493,7 +493,7 @@ int kss_rotation_sweep(kss_ctx* ctx, const double* src_aligned, int n_s, const d
     if (cg_enabled()) {
         r = cg_buffers(ctx, 1, &cgb); if (r) return r;
         int nl = 0;
-        CU(launch_cg_build(ctx->stream, 1, 0, d_s, c_s, n_s, nullptr, nullptr, 0, t_sorted, c_t, tpad, cgb, &nl));
+        CU(launch_cg_build(ctx->stream, 1, 0, d_s, c_s, n_s, nullptr, nullptr, 0, t_sorted, t_inv, n_t, c_t, tpad, cgb, &nl));
         ctx->launches += nl;
         cg = &cgb;
     }
@@ -588,7 +588,7 @@ int kss_icp(kss_ctx* ctx, const double* src, int n_s, const double* tgt, int n_t
     if (cg_enabled()) {
         r = cg_buffers(ctx, 1, &cgb); if (r) return r;
         int nl = 0;
-        CU(launch_cg_build(ctx->stream, 1, 1, d_s, c_s, n_s, d_t, c_t, n_t, t_sorted, c_t, tpad, cgb, &nl));
+        CU(launch_cg_build(ctx->stream, 1, 1, d_s, c_s, n_s, d_t, c_t, n_t, t_sorted, t_inv, n_t, c_t, tpad, cgb, &nl));
         ctx->launches += nl;
         a.cg_geom = cgb.geom; a.cg_hdr = cgb.hdr; a.cg_arena = cgb.arena; a.cg_ok = cgb.ok;
     }

@@ -77,6 +77,7 @@ __device__ __forceinline__ unsigned long long cg_query(const CgView& g, const fl
         }
     }
     float best = __int_as_float(0x7f800000);
+    unsigned bi = 0u;
     unsigned long long bestkey = 0xffffffffffffffffull;
     if (cnt == 0u || cnt == CG_CNT_MASK) {
         // outside the cube, an empty header or an over-long list: plain scan of every target (rare)
@@ -98,15 +99,81 @@ __device__ __forceinline__ unsigned long long cg_query(const CgView& g, const fl
             for (int k = 0; k < 4; ++k) {
                 const float4 p = tgt[id[k]];
                 const float d = d2_rn(qx, qy, qz, p.x, p.y, p.z);
+                // lists are ascending in original index (cg_level_kernel): the first of equal distances wins
+                if (IDX) { if (d < best) { best = d; bi = id[k]; } }
+                else best = fminf(best, d);
+            }
+        }
+        if (IDX) bestkey = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)__float_as_uint(tgt[bi].w);
+    }
+    if (!IDX) bestkey = (unsigned long long)__float_as_uint(best) << 32;
+    return bestkey;
+}
+
+// U independent queries of one thread at once: the three dependent global reads of a query (cell header, octant
+// header of a refined cell, first list word) are issued for all U queries before any is consumed, so their
+// latencies overlap instead of adding up.  Same arithmetic and result as cg_query for every query.
+template <int U, bool IDX>
+__device__ __forceinline__ void cg_query_batch(const CgView& g, const float4* __restrict__ tgt, int n_t,
+                                               const float (&qx)[U], const float (&qy)[U], const float (&qz)[U],
+                                               unsigned long long (&out)[U]) {
+    const float ngf = (float)CG_NG;
+    unsigned h[U]; int oct[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const float fx = (qx[u] - g.lox) * g.inv_h, fy = (qy[u] - g.loy) * g.inv_h, fz = (qz[u] - g.loz) * g.inv_h;
+        h[u] = CG_CNT_MASK;                                   // outside the cube: scan everything
+        oct[u] = ((fx - (float)(int)fx) >= 0.5f ? 1 : 0) | ((fy - (float)(int)fy) >= 0.5f ? 2 : 0) |
+                 ((fz - (float)(int)fz) >= 0.5f ? 4 : 0);
+        if (fx >= 0.0f && fy >= 0.0f && fz >= 0.0f && fx < ngf && fy < ngf && fz < ngf)
+            h[u] = g.hdr[(int)fx + CG_NG * ((int)fy + CG_NG * (int)fz)];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if ((h[u] & CG_CNT_MASK) == CG_REFINED)
+            h[u] = __ldg(reinterpret_cast<const unsigned*>(g.list + ((h[u] >> CG_CNT_BITS) << 2)) + oct[u]);
+    uint2 w0[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const unsigned cnt = h[u] & CG_CNT_MASK;
+        w0[u] = make_uint2(0u, 0u);
+        if (cnt != 0u && cnt != CG_CNT_MASK) w0[u] = __ldg(reinterpret_cast<const uint2*>(g.list + ((h[u] >> CG_CNT_BITS) << 2)));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const unsigned cnt = h[u] & CG_CNT_MASK, off = (h[u] >> CG_CNT_BITS) << 2;
+        float best = __int_as_float(0x7f800000);
+        unsigned bi = 0u;
+        unsigned long long bestkey = 0xffffffffffffffffull;
+        if (cnt == 0u || cnt == CG_CNT_MASK) {
+            for (int j = 0; j < n_t; ++j) {
+                const float4 p = tgt[j];
+                const float d = d2_rn(qx[u], qy[u], qz[u], p.x, p.y, p.z);
                 if (IDX) {
                     const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_uint(p.w);
                     bestkey = key < bestkey ? key : bestkey;
                 } else best = fminf(best, d);
             }
+        } else {
+            const uint2* lp = reinterpret_cast<const uint2*>(g.list + off);
+            const unsigned n4 = (cnt + 3u) >> 2;
+            uint2 w = w0[u];
+            for (unsigned j = 0; j < n4; ++j) {
+                const unsigned id[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
+                if (j + 1 < n4) w = __ldg(lp + j + 1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 p = tgt[id[k]];
+                    const float d = d2_rn(qx[u], qy[u], qz[u], p.x, p.y, p.z);
+                    if (IDX) { if (d < best) { best = d; bi = id[k]; } }      // ascending original index: first wins
+                    else best = fminf(best, d);
+                }
+            }
+            if (IDX) bestkey = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)__float_as_uint(tgt[bi].w);
         }
+        if (!IDX) bestkey = (unsigned long long)__float_as_uint(best) << 32;
+        out[u] = bestkey;
     }
-    if (!IDX) bestkey = (unsigned long long)__float_as_uint(best) << 32;
-    return bestkey;
 }
 
 __device__ __forceinline__ CgView cg_view(const float* __restrict__ geom, const unsigned* __restrict__ hdr_all,

@@ -57,7 +57,8 @@ cudaError_t launch_sweep(cudaStream_t st, int P, const double* s_al, const int* 
                          const int* cnt_t, int cap_tpad, const double* trig_accum, int G, int score_mode,
                          double* rbuf, int hpad, const CgBuffers* cg);
 cudaError_t launch_cg_build(cudaStream_t st, int P, int geom_mode, const double* a, const int* cnt_a, int cap_a,
-                            const double* b, const int* cnt_b, int cap_b, const float4* t_sorted, const int* cnt_t,
+                            const double* b, const int* cnt_b, int cap_b, const float4* t_sorted,
+                            const unsigned short* t_inv, int cap_t, const int* cnt_t,
                             int cap_tpad, const CgBuffers& cg, int* launches);
 cudaError_t launch_sweep_finalize(cudaStream_t st, int P, const double* rbuf, const int* cnt_s, int cap_s, int hpad,
                                   int G, int score_mode, double* value, int* best_h, int* minima, int* n_minima);

@@ -223,7 +223,8 @@ cg_geom_kernel(int mode, const double* __restrict__ a, const int* __restrict__ c
 // SPARSE: the fifth, sparse level -- one thread per octant of every worklisted finest-level cell.
 template <bool SPARSE>
 __global__ void __launch_bounds__(256)
-cg_level_kernel(int level, const float4* __restrict__ t_sorted, const int* __restrict__ cnt_t, int cap_tpad,
+cg_level_kernel(int level, const float4* __restrict__ t_sorted, const unsigned short* __restrict__ t_inv_all, int cap_t,
+                const int* __restrict__ cnt_t, int cap_tpad,
                 const float* __restrict__ geom, unsigned* __restrict__ hdr_all,
                 unsigned short* __restrict__ arena_all, unsigned* __restrict__ cursor, int* __restrict__ ok,
                 unsigned short* __restrict__ wl_all, unsigned* __restrict__ wl_cnt) {
@@ -237,6 +238,10 @@ cg_level_kernel(int level, const float4* __restrict__ t_sorted, const int* __res
     const bool live = tid < ncells;
     const int n_t = cnt_t[p];
     const float4* __restrict__ tgt = t_sorted + (size_t)p * cap_tpad;
+    // level 0 enumerates the targets in ORIGINAL index order (t_inv: original index -> Morton position) and every
+    // level keeps its parent's order, so all lists are ascending in original index: a query can resolve equal
+    // distances by "first one wins" (kss_cg.cuh)
+    const unsigned short* __restrict__ tinv = t_inv_all + (size_t)p * cap_t;
     unsigned* hdr = hdr_all + (size_t)p * CG_HDR_TOTAL + cg_hdr_base(SPARSE ? CG_LEVELS - 1 : level);
     unsigned short* arena = arena_all + (size_t)p * CG_ARENA;
     const float* gm = geom + (size_t)p * 8;
@@ -279,7 +284,7 @@ cg_level_kernel(int level, const float4* __restrict__ t_sorted, const int* __res
     // ---- pass A: the four targets nearest to the centre (ascending keys d2bits<<32 | id); the first is p_c
     unsigned long long k0 = ~0ull, k1 = ~0ull, k2 = ~0ull, k3 = ~0ull;
     for (int j = 0; j < m_p; ++j) {
-        const int id = plist ? (int)plist[j] : j;
+        const int id = plist ? (int)plist[j] : (int)tinv[j];
         const float4 q = __ldg(tgt + id);
         const unsigned long long key = ((unsigned long long)__float_as_uint(d2_rn(cx, cy, cz, q.x, q.y, q.z)) << 32) | (unsigned)id;
         if (key < k3) {
@@ -319,7 +324,7 @@ cg_level_kernel(int level, const float4* __restrict__ t_sorted, const int* __res
     unsigned long long mask = 0ull;
     int k = 0, first = 0;
     for (int j = 0; j < m_p; ++j) {
-        const int id = plist ? (int)plist[j] : j;
+        const int id = plist ? (int)plist[j] : (int)tinv[j];
         const float4 q = __ldg(tgt + id);
         if (keep_test(q, d2_rn(cx, cy, cz, q.x, q.y, q.z))) {
             if (j < 64) mask |= 1ull << j;
@@ -367,11 +372,11 @@ cg_level_kernel(int level, const float4* __restrict__ t_sorted, const int* __res
         while (mask) {
             const int j = __ffsll((long long)mask) - 1;
             mask &= mask - 1ull;
-            out[w++] = (unsigned short)(plist ? (int)plist[j] : j);
+            out[w++] = (unsigned short)(plist ? (int)plist[j] : (int)tinv[j]);
         }
     } else {
         for (int j = 0; j < m_p; ++j) {
-            const int id = plist ? (int)plist[j] : j;
+            const int id = plist ? (int)plist[j] : (int)tinv[j];
             const float4 q = __ldg(tgt + id);
             if (keep_test(q, d2_rn(cx, cy, cz, q.x, q.y, q.z))) out[w++] = (unsigned short)id;
         }
@@ -427,16 +432,39 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
         rot_x(ci, si, y, z);
         rot_y(cj, sj, x, z);
         double* ro = rb + (size_t)o * hpad + hbase;
-        for (int k = 0; k < G; ++k) {
-            const double ck = trig_accum[2 * k], sk = trig_accum[2 * k + 1];
-            double xx = x, yy = y;
-            rot_z(ck, sk, xx, yy);
-            const float qx = (float)xx, qy = (float)yy, qz = (float)z;   // :440-442 narrowing
-            const unsigned long long key = use_cg ? cg_query<false>(cg, tgt, n_t, qx, qy, qz)
-                                                  : warp_nn<false>(tv, qx, qy, qz);
-            const float d2 = __uint_as_float((unsigned)(key >> 32));
-            const double r = score_mode == 1 ? (double)d2 : (double)__fsqrt_rn(d2);   // float sqrt, then widened (:444)
-            if (valid) ro[k] = r;
+        if (use_cg) {
+            // three z-rotations per batch: their grid look-ups overlap (cg_query_batch)
+            constexpr int U = 3;
+            for (int k0 = 0; k0 < G; k0 += U) {
+                float qx[U], qy[U], qz[U];
+                unsigned long long key[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int k = min(k0 + u, G - 1);
+                    const double ck = trig_accum[2 * k], sk = trig_accum[2 * k + 1];
+                    double xx = x, yy = y;
+                    rot_z(ck, sk, xx, yy);
+                    qx[u] = (float)xx; qy[u] = (float)yy; qz[u] = (float)z;   // :440-442 narrowing
+                }
+                cg_query_batch<U, false>(cg, tgt, n_t, qx, qy, qz, key);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float d2 = __uint_as_float((unsigned)(key[u] >> 32));
+                    const double r = score_mode == 1 ? (double)d2 : (double)__fsqrt_rn(d2);   // float sqrt, then widened (:444)
+                    if (valid && k0 + u < G) ro[k0 + u] = r;
+                }
+            }
+        } else {
+            for (int k = 0; k < G; ++k) {
+                const double ck = trig_accum[2 * k], sk = trig_accum[2 * k + 1];
+                double xx = x, yy = y;
+                rot_z(ck, sk, xx, yy);
+                const float qx = (float)xx, qy = (float)yy, qz = (float)z;   // :440-442 narrowing
+                const unsigned long long key = warp_nn<false>(tv, qx, qy, qz);
+                const float d2 = __uint_as_float((unsigned)(key >> 32));
+                const double r = score_mode == 1 ? (double)d2 : (double)__fsqrt_rn(d2);
+                if (valid) ro[k] = r;
+            }
         }
     }
 }
@@ -534,6 +562,9 @@ sweep_finalize_kernel(const double* __restrict__ rbuf, const int* __restrict__ c
 // mode 0: judge run      -> angles = accumulated loop values of best_h      (KSS_ICP.hpp:92-93)
 // mode 1: hypothesis l   -> angles = index*6.3/step of minima[l], only if judge fitness > thr
 // mode 2: explicit input -> src_f64 is used as is (kss_icp API, KSS_ICP.hpp:323-356)
+#ifndef ICP_U
+#define ICP_U 1
+#endif
 #ifndef ICP_MIN_CTAS
 #define ICP_MIN_CTAS 4
 #endif
@@ -619,16 +650,7 @@ icp_small_kernel(IcpArgs a) {
     for (;;) {
         // ---- (1) lazily apply the previous T_k, then correspondences for Morton-consecutive queries
         int my_kept = 0;
-        for (int base = warp * 32; base < n_s; base += nwarps * 32) {
-            const int jpos = base + lane;
-            const bool valid = jpos < n_s;
-            const int o = perm[valid ? jpos : n_s - 1];
-            float x, y, z;
-            if (iters == 0) input_point(o, x, y, z);
-            else { xform_point(Tk, cur[o], cur[n_s + o], cur[2 * n_s + o], x, y, z); }
-            __syncwarp();
-            if (valid) { cur[o] = x; cur[n_s + o] = y; cur[2 * n_s + o] = z; }
-            const unsigned long long key = use_cg ? cg_query<true>(cg, tgt, n_t, x, y, z) : warp_nn<true>(tv, x, y, z);
+        auto record = [&](bool valid, int o, float x, float y, float z, unsigned long long key) {
             const float d2 = __uint_as_float((unsigned)(key >> 32));
             const unsigned orig = (unsigned)(key & 0xffffffffu);
             const bool keep = !((double)d2 > a.max_dist_sqr);        // A.3: skip iff d2 > max_dist^2
@@ -642,6 +664,41 @@ icp_small_kernel(IcpArgs a) {
                     float* ts = a.trace_src + (((size_t)run * a.trace_cap + iters) * a.cap_s + o) * 3;
                     ts[0] = x; ts[1] = y; ts[2] = z;
                 }
+            }
+        };
+        if (use_cg) {
+            // four queries per thread at once: their grid look-ups overlap (cg_query_batch)
+            constexpr int U = ICP_U;
+            for (int base0 = warp * 32; base0 < n_s; base0 += U * nwarps * 32) {
+                float x[U], y[U], z[U]; int o[U]; bool valid[U];
+                unsigned long long key[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int jpos = base0 + u * nwarps * 32 + lane;
+                    valid[u] = jpos < n_s;
+                    o[u] = perm[valid[u] ? jpos : n_s - 1];
+                    if (iters == 0) input_point(o[u], x[u], y[u], z[u]);
+                    else { xform_point(Tk, cur[o[u]], cur[n_s + o[u]], cur[2 * n_s + o[u]], x[u], y[u], z[u]); }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (valid[u]) { cur[o[u]] = x[u]; cur[n_s + o[u]] = y[u]; cur[2 * n_s + o[u]] = z[u]; }
+                cg_query_batch<U, true>(cg, tgt, n_t, x, y, z, key);
+#pragma unroll
+                for (int u = 0; u < U; ++u) record(valid[u], o[u], x[u], y[u], z[u], key[u]);
+            }
+        } else {
+            for (int base = warp * 32; base < n_s; base += nwarps * 32) {
+                const int jpos = base + lane;
+                const bool valid = jpos < n_s;
+                const int o = perm[valid ? jpos : n_s - 1];
+                float x, y, z;
+                if (iters == 0) input_point(o, x, y, z);
+                else { xform_point(Tk, cur[o], cur[n_s + o], cur[2 * n_s + o], x, y, z); }
+                __syncwarp();
+                if (valid) { cur[o] = x; cur[n_s + o] = y; cur[2 * n_s + o] = z; }
+                record(valid, o, x, y, z, warp_nn<true>(tv, x, y, z));
             }
         }
         my_kept = __reduce_add_sync(KSS_FULL, my_kept);
@@ -1002,7 +1059,8 @@ cudaError_t launch_sweep(cudaStream_t st, int P, const double* s_al, const int* 
 }
 // candidate grid: geometry, then one launch per level (a level reads the previous one)
 cudaError_t launch_cg_build(cudaStream_t st, int P, int geom_mode, const double* a, const int* cnt_a, int cap_a,
-                            const double* b, const int* cnt_b, int cap_b, const float4* t_sorted, const int* cnt_t,
+                            const double* b, const int* cnt_b, int cap_b, const float4* t_sorted,
+                            const unsigned short* t_inv, int cap_t, const int* cnt_t,
                             int cap_tpad, const CgBuffers& cg, int* launches) {
     cg_geom_kernel<<<P, 256, 0, st>>>(geom_mode, a, cnt_a, cap_a, b, cnt_b, cap_b, cg.geom, cg.cursor, cg.ok, cg.wl_cnt);
     int n = 1;
@@ -1010,13 +1068,13 @@ cudaError_t launch_cg_build(cudaStream_t st, int P, int geom_mode, const double*
     const bool refine = !(e && e[0] == '1');
     for (int l = 0; l < CG_LEVELS; ++l) {
         const int ncells = cg_ng(l) * cg_ng(l) * cg_ng(l);
-        cg_level_kernel<false><<<dim3((ncells + 255) / 256, P), 256, 0, st>>>(l, t_sorted, cnt_t, cap_tpad, cg.geom, cg.hdr, cg.arena,
-                                                                         cg.cursor, cg.ok, refine ? cg.wl : nullptr, cg.wl_cnt);
+        cg_level_kernel<false><<<dim3((ncells + 255) / 256, P), 256, 0, st>>>(l, t_sorted, t_inv, cap_t, cnt_t, cap_tpad, cg.geom, cg.hdr,
+                                                                         cg.arena, cg.cursor, cg.ok, refine ? cg.wl : nullptr, cg.wl_cnt);
         ++n;
     }
     if (refine) {
-        cg_level_kernel<true><<<dim3((8 * CG_WL_CAP + 255) / 256, P), 256, 0, st>>>(CG_LEVELS, t_sorted, cnt_t, cap_tpad, cg.geom, cg.hdr,
-                                                                               cg.arena, cg.cursor, cg.ok, cg.wl, cg.wl_cnt);
+        cg_level_kernel<true><<<dim3((8 * CG_WL_CAP + 255) / 256, P), 256, 0, st>>>(CG_LEVELS, t_sorted, t_inv, cap_t, cnt_t, cap_tpad, cg.geom,
+                                                                               cg.hdr, cg.arena, cg.cursor, cg.ok, cg.wl, cg.wl_cnt);
         ++n;
     }
     if (launches) *launches = n;

@@ -239,3 +239,19 @@ def test_golden_fixtures_from_reference_data(ctx, pkg, model):
     assert float(r["final_fitness"]) == float(g[model + "_canon_final_fitness"])
     assert float(r["rmse"]) == float(g[model + "_canon_rmse"]) and float(r["mae"]) == float(g[model + "_canon_mae"])
     assert int(r["total_icp_iters"]) == int(g[model + "_canon_total_icp_iters"])
+
+
+def test_icp_correspondence_ties_through_the_candidate_grid(ctx, okss):
+    """duplicated target points and a lattice target give fp32-equal distances inside the ICP loop: the candidate
+    grid's lists are ascending in original index, so the first (lowest index) of equal distances must win"""
+    rng = np.random.default_rng(77)
+    g = np.stack(np.meshgrid(np.arange(9.0), np.arange(9.0), np.arange(9.0)), -1).reshape(-1, 3) / 8.0 - 0.5
+    t = np.concatenate([g, g[100:300], rng.uniform(-0.5, 0.5, (100, 3))]).astype(np.float32).astype(np.float64)
+    perm = rng.permutation(len(t)); t = t[perm]
+    s = np.concatenate([g + 1.0 / 16.0, g[::3]]).astype(np.float32).astype(np.float64)      # cell centres: 8-way ties
+    o = okss.icp(s, t, sum_order=okss.SUM_CANON256, method=okss.NN_BRUTE, trace_iters=6)
+    r = ctx.icp(s, t, trace_iters=6)
+    k = min(o["iters"], 6)
+    assert r["iters"] == o["iters"] and k >= 1
+    assert np.array_equal(r["trace"]["corr_idx"][:k], o["trace"]["corr_idx"][:k])
+    assert np.array_equal(r["T"], o["T"]) and r["fitness"] == o["fitness"]
