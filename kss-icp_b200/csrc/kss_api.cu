@@ -184,6 +184,8 @@ int cg_buffers(kss_ctx* ctx, int P, CgBuffers* cg) {
     BUF("cg_ok", (size_t)P, &cg->ok);
     BUF("cg_wl", (size_t)P * cg_worklist_entries_per_pair(), &cg->wl);
     BUF("cg_wl_cnt", (size_t)P, &cg->wl_cnt);
+    BUF("cg_wl2", (size_t)P * cg_worklist2_entries_per_pair(), &cg->wl2);
+    BUF("cg_wl2_cnt", (size_t)P, &cg->wl2_cnt);
     return KSS_OK;
 }
 
@@ -259,6 +261,11 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
     a.best_h = best_h; a.minima = minima; a.n_minima = n_minima;
     a.trig_accum = ctx->d_trig_accum; a.trig_list = ctx->d_trig_list;
     a.judge_thr = b.judge_threshold;
+    if (getenv("KSS_ICP_PHASES")) {       // diagnostics for tools/: 8 per-phase cycle counters, read with kss_debug_read
+        unsigned long long* pc; BUF("icp_phase", 16, &pc);
+        CU(cudaMemsetAsync(pc, 0, 128, st));
+        a.phase_cycles = pc;
+    }
     if (cg) { a.cg_geom = cg->geom; a.cg_hdr = cg->hdr; a.cg_arena = cg->arena; a.cg_ok = cg->ok; }
     icp_fill(a, b.icp);
     a.run_T = run_T; a.run_fit = run_fit; a.run_iters = run_iters; a.run_conv = run_conv;
@@ -299,7 +306,7 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
 }
 
 size_t per_pair_ws_bytes(const kss_batch& b, int H, int slots) {
-    size_t v = (cg_enabled() ? cg_hdr_words_per_pair() * 4 + cg_arena_entries_per_pair() * 2 + cg_worklist_entries_per_pair() * 2 + 64 : 0) +
+    size_t v = (cg_enabled() ? cg_hdr_words_per_pair() * 8 + cg_arena_entries_per_pair() * 2 + cg_worklist_entries_per_pair() * 2 + cg_worklist2_entries_per_pair() * 16 + 64 : 0) +
                (size_t)b.cap_s * H * 8 + (size_t)b.cap_s * 30 + (size_t)pad32(b.cap_t) * 18 + (size_t)H * 12 +
                (size_t)(1 + slots) * 96 + (size_t)b.cap_S * 26 + (size_t)pad32(b.cap_T) * 18 + 8192;
     return v;

@@ -15,12 +15,13 @@ typedef kss_pair_result PairOut;
 // candidate grid buffers (kss_cg.cuh): per pair 8 floats of geometry, CG_HDR_TOTAL header words,
 // CG_ARENA u16 list entries, an arena cursor and an ok flag
 struct CgBuffers {
-    float* geom; unsigned* hdr; unsigned short* arena; unsigned* cursor; int* ok;
-    unsigned short* wl; unsigned* wl_cnt;      // finest-level cells to refine (kss_cg.cuh), per pair CG_WL_CAP entries
+    float* geom; unsigned long long* hdr; unsigned short* arena; unsigned* cursor; int* ok;
+    unsigned short* wl; unsigned* wl_cnt; uint4* wl2; unsigned* wl2_cnt;      // finest-level cells to refine (kss_cg.cuh), per pair CG_WL_CAP entries
 };
 size_t cg_hdr_words_per_pair();
 size_t cg_arena_entries_per_pair();
 size_t cg_worklist_entries_per_pair();
+size_t cg_worklist2_entries_per_pair();
 
 struct IcpArgs {
     // source: original (double) simplified cloud, similarity applied in-kernel (mode 0/1) or used as is (mode 2)
@@ -35,12 +36,13 @@ struct IcpArgs {
     const double* trig_accum; const double* trig_list;
     double judge_thr;         // mode 1 runs only if judge fitness > thr (thr < 0: always)
     // candidate grid of the pair (null: tile search)
-    const float* cg_geom; const unsigned* cg_hdr; const unsigned short* cg_arena; const int* cg_ok;
+    const float* cg_geom; const unsigned long long* cg_hdr; const unsigned short* cg_arena; const int* cg_ok;
     // PCL parameters
     int max_iter; double max_dist_sqr, rot_thr, trans_thr, mse_rel, mse_abs;
     // per-run outputs, run = pair * runs_per_pair + (mode==1 ? 1 + slot : 0)
     float* run_T; double* run_fit; int* run_iters; int* run_conv;
     // optional trace
+    unsigned long long* phase_cycles;      // diagnostics (tools/): per-phase clock64 sums of thread 0, or null
     int trace_cap; int32_t* trace_idx; float* trace_T; double* trace_mse; float* trace_src;
 };
 

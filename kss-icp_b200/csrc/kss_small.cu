@@ -169,7 +169,8 @@ middle_align_kernel(const double* __restrict__ sim_s, const int* __restrict__ cn
 __global__ void __launch_bounds__(256)
 cg_geom_kernel(int mode, const double* __restrict__ a, const int* __restrict__ cnt_a, int cap_a,
                const double* __restrict__ b, const int* __restrict__ cnt_b, int cap_b,
-               float* __restrict__ geom, unsigned* __restrict__ cursor, int* __restrict__ ok, unsigned* __restrict__ wl_cnt) {
+               float* __restrict__ geom, unsigned* __restrict__ cursor, int* __restrict__ ok, unsigned* __restrict__ wl_cnt,
+               unsigned* __restrict__ wl2_cnt) {
     __shared__ unsigned bb[6];
     __shared__ unsigned long long r2max;
     const int p = blockIdx.x;
@@ -211,104 +212,66 @@ cg_geom_kernel(int mode, const double* __restrict__ a, const int* __restrict__ c
         cursor[p] = 0u;
         ok[p] = 1;
         wl_cnt[p] = 0u;
+        wl2_cnt[p] = 0u;
     }
 }
 
-// =============================================================== cg_level_kernel
-// Builds one level of the candidate grid (kss_cg.cuh).  One thread per child cell; the 8 children
-// of a parent sit in adjacent lanes, so parent-list and target reads are broadcasts (4 distinct
-// addresses per warp).  Pass A: p_c = the centre's nearest target, d_c^2.  Pass B: keep p iff
-// d2 <= ((d_c + 2 rho)(1+1e-4))^2 and p_c does not dominate p over the whole cell; remembered as a bit mask (lists <= 64) so pass C only re-reads
-// indices.  Space: one atomicAdd per warp on the pair's arena cursor (list order never matters).
-// SPARSE: the fifth, sparse level -- one thread per octant of every worklisted finest-level cell.
-template <bool SPARSE>
+// =============================================================== cg_level0_kernel
+// Level 0 of the candidate grid: 64 cells, each filtering ALL targets.  One warp per cell, lanes stride over the
+// targets in original-index order; the same passes as cg_level_kernel (four nearest to the centre, sphere rule +
+// dominance), the kept ones compacted in order with ballots.  Lists of this level always go to the arena.
 __global__ void __launch_bounds__(256)
-cg_level_kernel(int level, const float4* __restrict__ t_sorted, const unsigned short* __restrict__ t_inv_all, int cap_t,
-                const int* __restrict__ cnt_t, int cap_tpad,
-                const float* __restrict__ geom, unsigned* __restrict__ hdr_all,
-                unsigned short* __restrict__ arena_all, unsigned* __restrict__ cursor, int* __restrict__ ok,
-                unsigned short* __restrict__ wl_all, unsigned* __restrict__ wl_cnt) {
+cg_level0_kernel(const float4* __restrict__ t_sorted, const unsigned short* __restrict__ t_inv_all, int cap_t,
+                 const int* __restrict__ cnt_t, int cap_tpad, const float* __restrict__ geom,
+                 cg_hdr_t* __restrict__ hdr_all, unsigned short* __restrict__ arena_all, unsigned* __restrict__ cursor,
+                 int* __restrict__ ok) {
     const int p = blockIdx.y;
     const int lane = threadIdx.x & 31;
-    const int ng = SPARSE ? 2 * CG_NG : cg_ng(level);
-    const int png = ng >> 1;
-    const int ncells = SPARSE ? 8 * (int)min(wl_cnt[p], (unsigned)CG_WL_CAP) : ng * ng * ng;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;        // = parent * 8 + child
-    if (tid - lane >= ncells) return;                              // whole warp out of range
-    const bool live = tid < ncells;
+    const int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int ng = CG_NG0;
+    if (cell >= ng * ng * ng) return;
     const int n_t = cnt_t[p];
     const float4* __restrict__ tgt = t_sorted + (size_t)p * cap_tpad;
-    // level 0 enumerates the targets in ORIGINAL index order (t_inv: original index -> Morton position) and every
-    // level keeps its parent's order, so all lists are ascending in original index: a query can resolve equal
-    // distances by "first one wins" (kss_cg.cuh)
     const unsigned short* __restrict__ tinv = t_inv_all + (size_t)p * cap_t;
-    unsigned* hdr = hdr_all + (size_t)p * CG_HDR_TOTAL + cg_hdr_base(SPARSE ? CG_LEVELS - 1 : level);
+    cg_hdr_t* hdr = hdr_all + (size_t)p * CG_HDR_TOTAL;
     unsigned short* arena = arena_all + (size_t)p * CG_ARENA;
     const float* gm = geom + (size_t)p * 8;
     const float R = gm[3], ballR = gm[4];
     const float h = 2.0f * R / (float)ng;
     const float rho = h * 0.8660254f * 1.002f;
-    const int child = tid & 7;
-    int parent = tid >> 3;
-
-    int ix = 0, iy = 0, iz = 0, m_p = 0;
-    const unsigned short* plist = nullptr;
-    if (live) {
-        if (SPARSE) {
-            parent = wl_all[(size_t)p * CG_WL_CAP + parent];                 // a cell of the finest dense level
-            const int px = parent & (CG_NG - 1), py = (parent / CG_NG) & (CG_NG - 1), pz = parent / (CG_NG * CG_NG);
-            ix = 2 * px + (child & 1); iy = 2 * py + ((child >> 1) & 1); iz = 2 * pz + (child >> 2);
-            const unsigned ph = hdr[parent];
-            m_p = (int)(ph & CG_CNT_MASK);
-            plist = arena + ((size_t)(ph >> CG_CNT_BITS) << 2);
-        } else if (level == 0) {
-            ix = tid & 3; iy = (tid >> 2) & 3; iz = tid >> 4;
-            m_p = n_t;
-        } else {
-            const int lp = level + 1, pm = png - 1;                      // png = 2 << level is a power of two
-            const int px = parent & pm, py = (parent >> lp) & pm, pz = parent >> (2 * lp);
-            ix = 2 * px + (child & 1); iy = 2 * py + ((child >> 1) & 1); iz = 2 * pz + (child >> 2);
-            const unsigned ph = (hdr_all + (size_t)p * CG_HDR_TOTAL + cg_hdr_base(level - 1))[parent];
-            m_p = (int)(ph & CG_CNT_MASK);
-            plist = arena + ((size_t)(ph >> CG_CNT_BITS) << 2);
-            if (m_p == (int)CG_CNT_MASK) { m_p = n_t; plist = nullptr; }      // over-long parent: all points
-        }
-    }
-    const int cell = ix + ng * (iy + ng * iz);
+    const int ix = cell & 3, iy = (cell >> 2) & 3, iz = cell >> 4;
     const float ox = -R + ((float)ix + 0.5f) * h, oy = -R + ((float)iy + 0.5f) * h, oz = -R + ((float)iz + 0.5f) * h;
     const float cx = gm[0] + ox, cy = gm[1] + oy, cz = gm[2] + oz;
     const float rr = ballR + rho;
-    const bool inball = ox * ox + oy * oy + oz * oz <= rr * rr;
-    if (!inball) m_p = 0;                                                  // outside the query ball: empty list
-
-    // ---- pass A: the four targets nearest to the centre (ascending keys d2bits<<32 | id); the first is p_c
-    unsigned long long k0 = ~0ull, k1 = ~0ull, k2 = ~0ull, k3 = ~0ull;
-    for (int j = 0; j < m_p; ++j) {
-        const int id = plist ? (int)plist[j] : (int)tinv[j];
+    if (!(ox * ox + oy * oy + oz * oz <= rr * rr)) { if (lane == 0) hdr[cell] = 0ull; return; }
+    // pass A: per-lane four nearest, then four rounds of warp arg-min
+    const float INF = __int_as_float(0x7f800000);
+    float e0 = INF, e1 = INF, e2 = INF, e3 = INF;
+    int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+    for (int j = lane; j < n_t; j += 32) {
+        const int id = (int)tinv[j];
         const float4 q = __ldg(tgt + id);
-        const unsigned long long key = ((unsigned long long)__float_as_uint(d2_rn(cx, cy, cz, q.x, q.y, q.z)) << 32) | (unsigned)id;
-        if (key < k3) {
-            if (key < k0) { k3 = k2; k2 = k1; k1 = k0; k0 = key; }
-            else if (key < k1) { k3 = k2; k2 = k1; k1 = key; }
-            else if (key < k2) { k3 = k2; k2 = key; }
-            else k3 = key;
+        const float d = d2_rn(cx, cy, cz, q.x, q.y, q.z);
+        if (d < e3) {
+            if (d < e0) { e3 = e2; i3 = i2; e2 = e1; i2 = i1; e1 = e0; i1 = i0; e0 = d; i0 = id; }
+            else if (d < e1) { e3 = e2; i3 = i2; e2 = e1; i2 = i1; e1 = d; i1 = id; }
+            else if (d < e2) { e3 = e2; i3 = i2; e2 = d; i2 = id; }
+            else { e3 = d; i3 = id; }
         }
     }
-    const float mn = __uint_as_float((unsigned)(k0 >> 32));
-    const float thr = (sqrtf(mn) + 2.0f * rho) * 1.0001f;
-    const float thr2 = thr * thr;
-    // dominance test against a competitor p': g(x) = |x-p|^2 - |x-p'|^2 is linear in x, so its minimum over the
-    // cell is g(c) - h * (|dx|+|dy|+|dz|), d = p - p'.  If that is > 0 (with a margin far above fp32 rounding of
-    // any query's two distances) p' beats p everywhere in the cell: p can never be a nearest neighbour of a query
-    // in this cell, nor tie with one.  Competitors: the (up to) four targets nearest to the centre.
-    const unsigned long long ck[4] = {k0, k1, k2, k3};
     float4 cp[4]; float cd[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const bool have = ck[c] != ~0ull;
-        cp[c] = __ldg(tgt + (have ? (unsigned)(ck[c] & 0xffffffffu) : 0u));
-        cd[c] = have ? __uint_as_float((unsigned)(ck[c] >> 32)) : __int_as_float(0x7f800000);   // +inf: never dominates
+        const unsigned m = __reduce_min_sync(KSS_FULL, __float_as_uint(e0));          // d2 >= 0: bits order as integers
+        const unsigned bal = __ballot_sync(KSS_FULL, __float_as_uint(e0) == m);
+        const int src = __ffs(bal) - 1;
+        const int id = __shfl_sync(KSS_FULL, i0, src);
+        cd[c] = (id >= 0) ? __uint_as_float(m) : INF;
+        cp[c] = __ldg(tgt + (id >= 0 ? id : 0));
+        if (lane == src) { e0 = e1; i0 = i1; e1 = e2; i1 = i2; e2 = e3; i2 = i3; e3 = INF; i3 = -1; }
     }
+    const float thr = (sqrtf(cd[0]) + 2.0f * rho) * 1.0001f;
+    const float thr2 = thr * thr;
     const float hh = h * 1.002f * 1.0001f;
     const float rr4 = 4.0f * rho * rho;
     auto keep_test = [&](const float4& q, float d) -> bool {
@@ -320,23 +283,187 @@ cg_level_kernel(int level, const float4* __restrict__ t_sorted, const unsigned s
         }
         return true;
     };
-    // ---- pass B: count (and remember) the candidates
+    // pass B: count; pass C: ordered write
+    int k = 0;
+    for (int j0 = 0; j0 < n_t; j0 += 32) {
+        const int j = j0 + lane;
+        bool keep = false;
+        if (j < n_t) { const float4 q = __ldg(tgt + (int)tinv[j]); keep = keep_test(q, d2_rn(cx, cy, cz, q.x, q.y, q.z)); }
+        k += __popc(__ballot_sync(KSS_FULL, keep));
+    }
+    if (k == 0) { if (lane == 0) hdr[cell] = 0ull; return; }
+    if (k > CG_EXT_MAX) { if (lane == 0) hdr[cell] = (cg_hdr_t)CG_TAG_HUGE << 60; return; }
+    const int tot4 = (k + 3) & ~3;
+    unsigned off = 0;
+    if (lane == 0) off = atomicAdd(&cursor[p], (unsigned)tot4);
+    off = __shfl_sync(KSS_FULL, off, 0);
+    if ((size_t)off + (size_t)tot4 > CG_ARENA) { if (lane == 0) { atomicExch(&ok[p], 0); hdr[cell] = 0ull; } return; }
+    unsigned short* out = arena + off;
+    int w = 0, first = 0;
+    for (int j0 = 0; j0 < n_t; j0 += 32) {
+        const int j = j0 + lane;
+        bool keep = false; int id = 0;
+        if (j < n_t) { id = (int)tinv[j]; const float4 q = __ldg(tgt + id); keep = keep_test(q, d2_rn(cx, cy, cz, q.x, q.y, q.z)); }
+        const unsigned bal = __ballot_sync(KSS_FULL, keep);
+        if (keep) out[w + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)id;
+        if (w == 0 && bal) first = __shfl_sync(KSS_FULL, id, __ffs(bal) - 1);
+        w += __popc(bal);
+    }
+    if (lane < tot4 - k) out[k + lane] = (unsigned short)first;
+    if (lane == 0) hdr[cell] = ((cg_hdr_t)CG_TAG_EXT << 60) | ((cg_hdr_t)(unsigned)k << 32) | (cg_hdr_t)(off >> 2);
+}
+
+// =============================================================== cg_level_kernel
+// Builds one level of the candidate grid (kss_cg.cuh).  One thread per child cell; the 8 children
+// of a parent sit in adjacent lanes, so parent-list and target reads are broadcasts (4 distinct
+// addresses per warp).  Pass A: the four targets nearest to the centre (the first is p_c, d_c^2).  Pass B: keep p iff
+// d2 <= ((d_c + 2 rho)(1+1e-4))^2 and none of the four dominates p over the whole cell; remembered as a bit mask
+// (lists <= 64) so pass C only re-reads indices.  Lists of up to CG_INLINE_MAX entries go into the 64-bit header,
+// longer ones into the pair's arena (one atomicAdd per warp on its cursor).
+// SPARSE 1: one thread per octant of every worklisted 32^3 cell (64^3 resolution); SPARSE 2: the same once more for the
+// worklisted octants (128^3 resolution), whose headers live in the arena.
+#ifndef CG_NCOMP
+#define CG_NCOMP 4
+#endif
+template <int SPARSE>
+__device__ __forceinline__ void cg_build_cell(int tid, int ncells, int level, const float4* __restrict__ t_sorted,
+                                              const unsigned short* __restrict__ t_inv_all, int cap_t,
+                                              const int* __restrict__ cnt_t, int cap_tpad,
+                                              const float* __restrict__ geom, cg_hdr_t* __restrict__ hdr_all,
+                                              unsigned short* __restrict__ arena_all, unsigned* __restrict__ cursor, int* __restrict__ ok,
+                                              unsigned short* __restrict__ wl_all, unsigned* __restrict__ wl_cnt,
+                                              uint4* __restrict__ wl2_all, unsigned* __restrict__ wl2_cnt) {
+    const int p = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int ng = SPARSE == 2 ? 4 * CG_NG : (SPARSE == 1 ? 2 * CG_NG : cg_ng(level));
+    const int png = ng >> 1;
+    const bool live = tid < ncells;
+    const int n_t = cnt_t[p];
+    const float4* __restrict__ tgt = t_sorted + (size_t)p * cap_tpad;
+    // level 0 enumerates the targets in ORIGINAL index order (t_inv: original index -> Morton position) and every
+    // level keeps its parent's order, so all lists are ascending in original index: a query can resolve equal
+    // distances by "first one wins" (kss_cg.cuh)
+    const unsigned short* __restrict__ tinv = t_inv_all + (size_t)p * cap_t;
+    cg_hdr_t* hdr = hdr_all + (size_t)p * CG_HDR_TOTAL + cg_hdr_base(SPARSE ? CG_LEVELS - 1 : level);
+    unsigned short* arena = arena_all + (size_t)p * CG_ARENA;
+    const float* gm = geom + (size_t)p * 8;
+    const float R = gm[3], ballR = gm[4];
+    const float h = 2.0f * R / (float)ng;
+    const float rho = h * 0.8660254f * 1.002f;
+    const int child = tid & 7;
+    int parent = tid >> 3;
+
+    // the parent's list: inline in its header, in the arena, or "all targets" (level 0 / over-long parent)
+    int ix = 0, iy = 0, iz = 0, m_p = 0;
+    cg_hdr_t ph = 0ull;
+    const unsigned short* plist = nullptr;
+    bool p_inline = false;
+    if (live) {
+        bool from_parent = true;
+        if (SPARSE == 2) {
+            const uint4 e = wl2_all[(size_t)p * CG_WL2_CAP + parent];        // an octant of a refined cell
+            parent = (int)e.x;                                               // arena offset of its header
+            ix = 2 * (int)(e.y & 0xffffu) + (child & 1); iy = 2 * (int)(e.y >> 16) + ((child >> 1) & 1); iz = 2 * (int)e.z + (child >> 2);
+            ph = *reinterpret_cast<const cg_hdr_t*>(arena + parent);
+        } else if (SPARSE == 1) {
+            parent = wl_all[(size_t)p * CG_WL_CAP + parent];                 // a cell of the finest dense level
+            const int px = parent & (CG_NG - 1), py = (parent / CG_NG) & (CG_NG - 1), pz = parent / (CG_NG * CG_NG);
+            ix = 2 * px + (child & 1); iy = 2 * py + ((child >> 1) & 1); iz = 2 * pz + (child >> 2);
+            ph = hdr[parent];
+        } else if (level == 0) {
+            ix = tid & 3; iy = (tid >> 2) & 3; iz = tid >> 4;
+            m_p = n_t; from_parent = false;
+        } else {
+            const int lp = level + 1, pm = png - 1;                      // png = 2 << level is a power of two
+            const int px = parent & pm, py = (parent >> lp) & pm, pz = parent >> (2 * lp);
+            ix = 2 * px + (child & 1); iy = 2 * py + ((child >> 1) & 1); iz = 2 * pz + (child >> 2);
+            ph = (hdr_all + (size_t)p * CG_HDR_TOTAL + cg_hdr_base(level - 1))[parent];
+        }
+        if (from_parent) {
+            const unsigned tag = cg_tag(ph);
+            if (tag >= 1u && tag <= (unsigned)CG_INLINE_MAX) { m_p = (int)tag; p_inline = true; }
+            else if (tag == CG_TAG_EXT) { m_p = (int)cg_ext_count(ph); plist = arena + cg_offset(ph); }
+            else if (tag == CG_TAG_HUGE) m_p = n_t;                        // over-long parent: all points
+            else m_p = 0;                                                  // empty parent (outside the query ball)
+        }
+    }
+    auto cand = [&](int j) -> int {
+        return p_inline ? (int)cg_inline_id(ph, j) : (plist ? (int)plist[j] : (int)tinv[j]);
+    };
+    const int cell = ix + ng * (iy + ng * iz);
+    // A parent list that already fits a header costs a query the same five branch-free evaluations however much a
+    // child would shorten it: the children of such a cell just copy its header.  (cand(child) is a subset of
+    // cand(parent), so the parent's list is valid everywhere inside it.)
+    // (The lane still takes part in the warp-wide allocation scan below, with nothing to allocate.)
+    const bool copy = !SPARSE && p_inline;
+    if (copy) m_p = 0;
+    const float ox = -R + ((float)ix + 0.5f) * h, oy = -R + ((float)iy + 0.5f) * h, oz = -R + ((float)iz + 0.5f) * h;
+    const float cx = gm[0] + ox, cy = gm[1] + oy, cz = gm[2] + oz;
+    const float rr = ballR + rho;
+    const bool inball = ox * ox + oy * oy + oz * oz <= rr * rr;
+    if (!inball) m_p = 0;                                                  // outside the query ball: empty list
+
+    // ---- pass A: the four targets nearest to the centre; ties do not matter here (any target is a valid competitor)
+    float e0 = __int_as_float(0x7f800000), e1 = e0, e2 = e0, e3 = e0;
+    int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+    for (int j = 0; j < m_p; ++j) {
+        const int id = cand(j);
+        const float4 q = __ldg(tgt + id);
+        const float d = d2_rn(cx, cy, cz, q.x, q.y, q.z);
+        if (d < e3) {
+            if (d < e0) { e3 = e2; i3 = i2; e2 = e1; i2 = i1; e1 = e0; i1 = i0; e0 = d; i0 = id; }
+            else if (d < e1) { e3 = e2; i3 = i2; e2 = e1; i2 = i1; e1 = d; i1 = id; }
+            else if (d < e2) { e3 = e2; i3 = i2; e2 = d; i2 = id; }
+            else { e3 = d; i3 = id; }
+        }
+    }
+    const float mn = e0;
+    const float thr = (sqrtf(mn) + 2.0f * rho) * 1.0001f;
+    const float thr2 = thr * thr;
+    // dominance test against a competitor p': g(x) = |x-p|^2 - |x-p'|^2 is linear in x, so its minimum over the
+    // cell is g(c) - h * (|dx|+|dy|+|dz|), d = p - p'.  If that is > 0 (with a margin far above fp32 rounding of
+    // any query's two distances) p' beats p everywhere in the cell: p can never be a nearest neighbour of a query
+    // in this cell, nor tie with one.  Competitors: the (up to) four targets nearest to the centre.
+    const int ci[4] = {i0, i1, i2, i3};
+    const float ce[4] = {e0, e1, e2, e3};
+    float4 cp[4]; float cd[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const bool have = ci[c] >= 0;
+        cp[c] = __ldg(tgt + (have ? ci[c] : 0));
+        cd[c] = have ? ce[c] : __int_as_float(0x7f800000);                 // +inf: never dominates
+    }
+    const float hh = h * 1.002f * 1.0001f;
+    const float rr4 = 4.0f * rho * rho;
+    auto keep_test = [&](const float4& q, float d) -> bool {
+        if (!(d <= thr2)) return false;
+#pragma unroll
+        for (int c = 0; c < CG_NCOMP; ++c) {
+            const float s = fabsf(q.x - cp[c].x) + fabsf(q.y - cp[c].y) + fabsf(q.z - cp[c].z);
+            if ((d - cd[c]) - hh * s > 1e-5f * (d + cd[c] + rr4)) return false;
+        }
+        return true;
+    };
+    // ---- pass B: count (and remember) the candidates; the first CG_INLINE_MAX of them are packed on the way
     unsigned long long mask = 0ull;
+    cg_hdr_t packed = 0ull;
     int k = 0, first = 0;
     for (int j = 0; j < m_p; ++j) {
-        const int id = plist ? (int)plist[j] : (int)tinv[j];
+        const int id = cand(j);
         const float4 q = __ldg(tgt + id);
         if (keep_test(q, d2_rn(cx, cy, cz, q.x, q.y, q.z))) {
             if (j < 64) mask |= 1ull << j;
             if (k == 0) first = id;
+            if (k < CG_INLINE_MAX) packed |= (cg_hdr_t)(unsigned)id << (11 * k);
             ++k;
         }
     }
-    const bool huge = k >= (int)CG_REFINED;
-    const int tot4 = huge ? 0 : ((k + 3) & ~3);
-    // warp exclusive scan of the space needed, one atomicAdd per warp; a refined cell also needs 8 child headers
-    // (16 entries), reserved by its octant 0
-    const int need = tot4 + ((SPARSE && live && child == 0) ? 16 : 0);
+    const bool huge = k > CG_EXT_MAX;
+    const bool ext = k > CG_INLINE_MAX && !huge;
+    const int tot4 = ext ? ((k + 3) & ~3) : 0;
+    // warp exclusive scan of the arena space needed, one atomicAdd per warp; a refined cell also needs 8 child headers
+    // (64 bytes = 32 entries), reserved by its octant 0
+    const int need = tot4 + ((SPARSE && live && child == 0) ? 32 : 0);
     int incl = need;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(KSS_FULL, incl, o); if (lane >= o) incl += y; }
@@ -349,39 +476,72 @@ cg_level_kernel(int level, const float4* __restrict__ t_sorted, const unsigned s
     if ((size_t)base + (size_t)wtot > CG_ARENA) {
         if (SPARSE) return;                                               // no room: the cells keep their unrefined lists
         if (lane == 0) atomicExch(&ok[p], 0);                             // arena exhausted: pair falls back
-        if (live) hdr[cell] = 0u;
+        if (live) hdr[cell] = 0ull;
         return;
     }
     if (!live) return;
+    if (SPARSE && child == 0) off += 32u;
+    cg_hdr_t me;
+    if (huge) me = (cg_hdr_t)CG_TAG_HUGE << 60;
+    else if (ext) me = ((cg_hdr_t)CG_TAG_EXT << 60) | ((cg_hdr_t)(unsigned)k << 32) | (cg_hdr_t)(off >> 2);
+    else me = ((cg_hdr_t)(unsigned)k << 60) | packed;                     // k = 0: empty
+    if (copy) me = ph;
     if (SPARSE) {
-        if (child == 0) off += 16u;
-        reinterpret_cast<unsigned*>(arena + blk)[child] = huge ? CG_CNT_MASK : (k == 0 ? 0u : (((off >> 2) << CG_CNT_BITS) | (unsigned)k));
-        if (child == 0) hdr[parent] = ((blk >> 2) << CG_CNT_BITS) | CG_REFINED;
+        reinterpret_cast<cg_hdr_t*>(arena + blk)[child] = me;
+        if (child == 0) {
+            const cg_hdr_t mark = ((cg_hdr_t)CG_TAG_REFINED << 60) | (cg_hdr_t)(blk >> 2);
+            if (SPARSE == 2) *reinterpret_cast<cg_hdr_t*>(arena + parent) = mark; else hdr[parent] = mark;
+        }
+        if (SPARSE == 1 && wl2_all != nullptr && !huge && k >= CG_REFINE_MIN) {
+            const unsigned slot = atomicAdd(&wl2_cnt[p], 1u);
+            if (slot < (unsigned)CG_WL2_CAP)
+                wl2_all[(size_t)p * CG_WL2_CAP + slot] = make_uint4(blk + 4u * (unsigned)child, (unsigned)ix | ((unsigned)iy << 16), (unsigned)iz, 0u);
+        }
     } else {
-        hdr[cell] = huge ? CG_CNT_MASK : (k == 0 ? 0u : (((off >> 2) << CG_CNT_BITS) | (unsigned)k));
+        hdr[cell] = me;
         if (level == CG_LEVELS - 1 && wl_all != nullptr && !huge && k >= CG_REFINE_MIN) {
             const unsigned slot = atomicAdd(&wl_cnt[p], 1u);
             if (slot < (unsigned)CG_WL_CAP) wl_all[(size_t)p * CG_WL_CAP + slot] = (unsigned short)cell;
         }
     }
-    if (huge || k == 0) return;
-    // ---- pass C: write the list, padded to a multiple of 4 with a valid candidate
+    if (!ext) return;
+    // ---- pass C: write the external list, padded to a multiple of 4 with a valid candidate
     unsigned short* out = arena + off;
     int w = 0;
     if (m_p <= 64) {
         while (mask) {
             const int j = __ffsll((long long)mask) - 1;
             mask &= mask - 1ull;
-            out[w++] = (unsigned short)(plist ? (int)plist[j] : (int)tinv[j]);
+            out[w++] = (unsigned short)cand(j);
         }
     } else {
         for (int j = 0; j < m_p; ++j) {
-            const int id = plist ? (int)plist[j] : (int)tinv[j];
+            const int id = cand(j);
             const float4 q = __ldg(tgt + id);
             if (keep_test(q, d2_rn(cx, cy, cz, q.x, q.y, q.z))) out[w++] = (unsigned short)id;
         }
     }
     for (; w < tot4; ++w) out[w] = (unsigned short)first;
+}
+
+// dense levels: one pass over ng^3 cells (the grid covers them exactly); sparse levels: a fixed, small grid per pair
+// loops over the worklist (its length is only known on the device)
+template <int SPARSE>
+__global__ void __launch_bounds__(256)
+cg_level_kernel(int level, const float4* __restrict__ t_sorted, const unsigned short* __restrict__ t_inv_all, int cap_t,
+                const int* __restrict__ cnt_t, int cap_tpad,
+                const float* __restrict__ geom, cg_hdr_t* __restrict__ hdr_all,
+                unsigned short* __restrict__ arena_all, unsigned* __restrict__ cursor, int* __restrict__ ok,
+                unsigned short* __restrict__ wl_all, unsigned* __restrict__ wl_cnt,
+                uint4* __restrict__ wl2_all, unsigned* __restrict__ wl2_cnt) {
+    const int p = blockIdx.y;
+    const int ng = cg_ng(level);
+    const int ncells = SPARSE == 2 ? 8 * (int)min(wl2_cnt[p], (unsigned)CG_WL2_CAP)
+                     : (SPARSE == 1 ? 8 * (int)min(wl_cnt[p], (unsigned)CG_WL_CAP) : ng * ng * ng);
+    const int lane = threadIdx.x & 31;
+    for (int tid = blockIdx.x * blockDim.x + threadIdx.x; tid - lane < ncells; tid += gridDim.x * blockDim.x)
+        cg_build_cell<SPARSE>(tid, ncells, level, t_sorted, t_inv_all, cap_t, cnt_t, cap_tpad, geom, hdr_all, arena_all, cursor, ok,
+                              wl_all, wl_cnt, wl2_all, wl2_cnt);
 }
 
 // =============================================================== sweep_kernel
@@ -396,7 +556,7 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
              const int* __restrict__ cnt_t, int cap_tpad,
              const double* __restrict__ trig_accum /* [G][2] cos,sin */, int G, int score_mode,
              double* __restrict__ rbuf, int hpad,
-             const float* __restrict__ cg_geom, const unsigned* __restrict__ cg_hdr,
+             const float* __restrict__ cg_geom, const cg_hdr_t* __restrict__ cg_hdr,
              const unsigned short* __restrict__ cg_arena, const int* __restrict__ cg_ok) {
     extern __shared__ unsigned char smem_raw[];
     float4* tgt = reinterpret_cast<float4*>(smem_raw);
@@ -568,8 +728,24 @@ sweep_finalize_kernel(const double* __restrict__ rbuf, const int* __restrict__ c
 #ifndef ICP_MIN_CTAS
 #define ICP_MIN_CTAS 4
 #endif
+// diagnostics (-DKSS_ICP_PHASE_TIMING): thread 0 adds the cycles since its previous tick to phase_cycles[ph]
+#ifdef KSS_ICP_PHASE_TIMING
+#define ICP_TICK(ph)                                                                                   \
+    do {                                                                                               \
+        if (a.phase_cycles != nullptr && threadIdx.x == 0) {                                           \
+            const long long now_ = clock64();                                                          \
+            atomicAdd(&a.phase_cycles[ph], (unsigned long long)(now_ - tick_));                        \
+            tick_ = now_;                                                                              \
+        }                                                                                              \
+    } while (0)
+#else
+#define ICP_TICK(ph) do { } while (0)
+#endif
 __global__ void __launch_bounds__(256, ICP_MIN_CTAS)
 icp_small_kernel(IcpArgs a) {
+#ifdef KSS_ICP_PHASE_TIMING
+    long long tick_ = a.phase_cycles != nullptr ? clock64() : 0;
+#endif
     extern __shared__ unsigned char smem_raw[];
     const int p = blockIdx.y;
     const int slot = blockIdx.x;
@@ -623,6 +799,7 @@ icp_small_kernel(IcpArgs a) {
     if (threadIdx.x < 16) fin[threadIdx.x] = (threadIdx.x % 5 == 0) ? 1.0f : 0.0f;
     if (threadIdx.x == 0) { kept = 0; done = 0; prev_mse = DBL_MAX; }
     __syncthreads();
+        ICP_TICK(0);
     TileView tv{tgt, box, npad / TILE};
     const bool use_cg = a.cg_hdr != nullptr && a.cg_ok[p] != 0;
     CgView cg{};
@@ -704,6 +881,7 @@ icp_small_kernel(IcpArgs a) {
         my_kept = __reduce_add_sync(KSS_FULL, my_kept);
         if (lane == 0 && my_kept) atomicAdd(&kept, my_kept);
         __syncthreads();
+        ICP_TICK(1);
         const int cnt = kept;
         if (cnt < 3) { converged = 0; break; }                       // min_number_correspondences_
         // ---- (2) pass A, level 1: one warp per 256-slot chunk sums kept source xyz, matched target
@@ -735,6 +913,7 @@ icp_small_kernel(IcpArgs a) {
             }
         }
         __syncthreads();
+        ICP_TICK(2);
         // level 2 (every warp redundantly, identical arithmetic): chunk results by the same rule
         auto lvl2f = [&](int q) -> float {
             if (nc == 1) return partF[q];
@@ -754,6 +933,7 @@ icp_small_kernel(IcpArgs a) {
             for (int off = 16; off >= 1; off >>= 1) dsum = __dadd_rn(dsum, __shfl_xor_sync(KSS_FULL, dsum, off));
         }
         __syncthreads();                                   // partF is reused by pass B
+        ICP_TICK(3);
         // ---- (3) pass B, level 1: sigma(a,b) partials = sum (d_a - dmean_a) * (s_b - smean_b)
         for (int c = warp; c < nc; c += nwarps) {
             float v[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -777,6 +957,7 @@ icp_small_kernel(IcpArgs a) {
                 for (int q = 0; q < 9; ++q) partF[c * 16 + q] = v[q];
         }
         __syncthreads();
+        ICP_TICK(4);
         if (warp == 0) {
             float sg[9];
 #pragma unroll
@@ -788,16 +969,19 @@ icp_small_kernel(IcpArgs a) {
             }
         }
         __syncwarp();
+        ICP_TICK(11);
         // ---- (4) one thread: SVD/Kabsch, accumulate, convergence
         if (threadIdx.x == 0) {
             float sigma[9], smean[3] = {sm0, sm1, sm2}, dmean[3] = {dm0, dm1, dm2}, T[16];
 #pragma unroll
             for (int i = 0; i < 9; ++i) sigma[i] = red[7 + i];
             umeyama_finish(sigma, smean, dmean, T);
+            ICP_TICK(8);
             float F[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) F[i] = fin[i];
             mat4_mul(T, F, F);
+            ICP_TICK(9);
 #pragma unroll
             for (int i = 0; i < 16; ++i) { Tk[i] = T[i]; fin[i] = F[i]; }
             const double mse = __ddiv_rn(redd, (double)cnt);
@@ -815,15 +999,18 @@ icp_small_kernel(IcpArgs a) {
                 else if (__ddiv_rn(fabs(__dsub_rn(mse, prev_mse)), prev_mse) < a.mse_rel) dn = 1;  // relative
                 else prev_mse = mse;
             }
+            ICP_TICK(10);
             done = dn; kept = 0;
         }
         __syncthreads();
+        ICP_TICK(5);
         ++iters;
         if (done) { converged = 1; break; }
     }
 
     // ---- getFitnessScore: final * ORIGINAL input (one rounding), NN, mean of d2 in double (A.7)
     __syncthreads();
+        ICP_TICK(6);
     for (int base = warp * 32; base < n_s; base += nwarps * 32) {
         const int jpos = base + lane;
         const bool valid = jpos < n_s;
@@ -835,6 +1022,7 @@ icp_small_kernel(IcpArgs a) {
         if (valid) d2s[o] = __uint_as_float((unsigned)(key >> 32));
     }
     __syncthreads();
+        ICP_TICK(7);
     if (warp == 0) {
         double s = canon_sum_warp_f64(n_s, [&](int i, double& v) { v = (double)d2s[i]; return true; });
         if (lane == 0) {
@@ -1062,20 +1250,28 @@ cudaError_t launch_cg_build(cudaStream_t st, int P, int geom_mode, const double*
                             const double* b, const int* cnt_b, int cap_b, const float4* t_sorted,
                             const unsigned short* t_inv, int cap_t, const int* cnt_t,
                             int cap_tpad, const CgBuffers& cg, int* launches) {
-    cg_geom_kernel<<<P, 256, 0, st>>>(geom_mode, a, cnt_a, cap_a, b, cnt_b, cap_b, cg.geom, cg.cursor, cg.ok, cg.wl_cnt);
+    cg_geom_kernel<<<P, 256, 0, st>>>(geom_mode, a, cnt_a, cap_a, b, cnt_b, cap_b, cg.geom, cg.cursor, cg.ok, cg.wl_cnt, cg.wl2_cnt);
     int n = 1;
     const char* e = getenv("KSS_CG_NO_REFINE");
     const bool refine = !(e && e[0] == '1');
-    for (int l = 0; l < CG_LEVELS; ++l) {
+    cg_level0_kernel<<<dim3((CG_NG0 * CG_NG0 * CG_NG0 + 7) / 8, P), 256, 0, st>>>(t_sorted, t_inv, cap_t, cnt_t, cap_tpad, cg.geom, cg.hdr,
+                                                                             cg.arena, cg.cursor, cg.ok);
+    ++n;
+    for (int l = 1; l < CG_LEVELS; ++l) {
         const int ncells = cg_ng(l) * cg_ng(l) * cg_ng(l);
-        cg_level_kernel<false><<<dim3((ncells + 255) / 256, P), 256, 0, st>>>(l, t_sorted, t_inv, cap_t, cnt_t, cap_tpad, cg.geom, cg.hdr,
-                                                                         cg.arena, cg.cursor, cg.ok, refine ? cg.wl : nullptr, cg.wl_cnt);
+        cg_level_kernel<0><<<dim3((ncells + 255) / 256, P), 256, 0, st>>>(l, t_sorted, t_inv, cap_t, cnt_t, cap_tpad, cg.geom, cg.hdr,
+                                                                     cg.arena, cg.cursor, cg.ok, refine ? cg.wl : nullptr, cg.wl_cnt,
+                                                                     nullptr, cg.wl2_cnt);
         ++n;
     }
     if (refine) {
-        cg_level_kernel<true><<<dim3((8 * CG_WL_CAP + 255) / 256, P), 256, 0, st>>>(CG_LEVELS, t_sorted, t_inv, cap_t, cnt_t, cap_tpad, cg.geom,
-                                                                               cg.hdr, cg.arena, cg.cursor, cg.ok, cg.wl, cg.wl_cnt);
-        ++n;
+        cg_level_kernel<1><<<dim3(48, P), 256, 0, st>>>(CG_LEVELS, t_sorted, t_inv, cap_t, cnt_t, cap_tpad, cg.geom,
+                                                                            cg.hdr, cg.arena, cg.cursor, cg.ok, cg.wl, cg.wl_cnt,
+                                                                            cg.wl2, cg.wl2_cnt);
+        cg_level_kernel<2><<<dim3(8, P), 256, 0, st>>>(CG_LEVELS + 1, t_sorted, t_inv, cap_t, cnt_t, cap_tpad,
+                                                                             cg.geom, cg.hdr, cg.arena, cg.cursor, cg.ok, cg.wl,
+                                                                             cg.wl_cnt, cg.wl2, cg.wl2_cnt);
+        n += 2;
     }
     if (launches) *launches = n;
     return cudaGetLastError();
@@ -1083,6 +1279,7 @@ cudaError_t launch_cg_build(cudaStream_t st, int P, int geom_mode, const double*
 size_t cg_hdr_words_per_pair() { return CG_HDR_TOTAL; }
 size_t cg_arena_entries_per_pair() { return CG_ARENA; }
 size_t cg_worklist_entries_per_pair() { return CG_WL_CAP; }
+size_t cg_worklist2_entries_per_pair() { return CG_WL2_CAP; }
 
 cudaError_t launch_sweep_finalize(cudaStream_t st, int P, const double* rbuf, const int* cnt_s, int cap_s, int hpad,
                                   int G, int score_mode, double* value, int* best_h, int* minima, int* n_minima) {

@@ -22,15 +22,15 @@ geom = rd("cg_geom", 0, P * 8, np.float32).reshape(P, 8)
 cap_s = 1072
 acc, lst = pkg.sweep_angles(8.0)
 allw = []; allc = []
+kinds = np.zeros(6, np.int64)     # inline, ext, huge, empty, (refined->) counted by the child
+refq = 0; totq = 0
 for p in range(P):
-    hdr = rd("cg_hdr", (p * tot + base) * 4, NG ** 3, np.uint32)
-    cnt = (hdr & 2047).astype(np.int64)
+    hdr = rd("cg_hdr", (p * tot + base) * 8, NG ** 3, np.uint64)
     arena = rd("cg_arena", p * (3 << 19) * 2, 3 << 19, np.uint16)
-    a32 = arena.view(np.uint32)
+    a64 = arena.view(np.uint64)
     wl = rd("cg_wl_cnt", p * 4, 1, np.uint32)[0]; cur = rd("cg_cursor", p * 4, 1, np.uint32)[0]
     if p == 0: print("pair 0: refined cells %d, arena used %d of %d" % (wl, cur, 3 << 19))
     s_al = rd("s_al", p * cap_s * 3 * 8, cap_s * 3, np.float64).reshape(cap_s, 3)
-    n = int(res[p]["align"][7]) if False else None
     cs = rd("aivs_cnt_s", p * 4, 1, np.int32)[0]
     s = s_al[:cs]
     lo = geom[p, :3] - geom[p, 3]; inv = NG / (2 * geom[p, 3])
@@ -46,18 +46,25 @@ for p in range(P):
         ok = ((f >= 0) & (f < NG)).all(1)
         cell = f[:, 0] + NG * (f[:, 1] + NG * f[:, 2])
         cc = np.clip(cell, 0, NG ** 3 - 1)
-        k = cnt[cc].copy()
-        ref = k == 2046
+        h = hdr[cc].copy()
+        tag = (h >> np.uint64(60)).astype(np.int64)
+        ref = tag == 15
         fr = (q - lo) * inv - f
         octv = (fr[:, 0] >= 0.5) * 1 + (fr[:, 1] >= 0.5) * 2 + (fr[:, 2] >= 0.5) * 4
-        off32 = ((hdr[cc] >> 11).astype(np.int64) << 2) // 2          # u16 offset -> u32 index
-        ch = a32[np.where(ref, off32 + octv, 0)]
-        k = np.where(ref, (ch & 2047).astype(np.int64), k)
+        off64 = ((h & np.uint64(0xffffffff)).astype(np.int64) << 2) // 4      # u16 offset -> u64 index
+        ch = a64[np.where(ref, off64 + octv, 0)]
+        h = np.where(ref, ch, h)
+        tag = (h >> np.uint64(60)).astype(np.int64)
+        k = np.where((tag >= 1) & (tag <= 5), tag, np.where(tag == 14, ((h >> np.uint64(32)) & np.uint64(0xfffffff)).astype(np.int64), np.where(tag == 13, 9999, 0)))
+        kinds[0] += ((tag >= 1) & (tag <= 5) & ok).sum(); kinds[1] += ((tag == 14) & ok).sum(); kinds[2] += ((tag == 13) & ok).sum()
+        kinds[3] += ((tag == 0) | ~ok).sum()
+        refq += (ref & ok).sum(); totq += len(q)
         w.append(np.where(ok, k, -1))
     w = np.concatenate(w)
-    allw.append(w); allc.append(cnt)
+    allw.append(w); allc.append(np.zeros(1))
+print("queries: inline %.2f%%, external %.2f%%, huge %.3f%%, empty/outside %.3f%%; through a refined cell %.1f%%" % tuple(
+    [100.0 * kinds[i] / totq for i in range(4)] + [100.0 * refq / totq]))
 w = np.concatenate(allw); c = np.concatenate(allc)
-print("cells: mean cnt %.2f, nonzero %.1f%%, >4: %.1f%%, >8: %.1f%%, >16: %.1f%%" % (c.mean(), 100 * (c > 0).mean(), 100 * (c > 4).mean(), 100 * (c > 8).mean(), 100 * (c > 16).mean()))
 print("queries: outside/empty %.2f%%, mean cnt %.2f, mean padded %.2f" % (100 * (w <= 0).mean(), w[w > 0].mean(), (((w[w > 0] + 3) // 4) * 4).mean()))
 print("query cnt percentiles 50/75/90/99/max:", np.percentile(w[w > 0], [50, 75, 90, 99, 100]))
 print("query hist:", np.bincount(np.minimum(w[w > 0], 40))[:41])

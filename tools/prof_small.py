@@ -20,3 +20,12 @@ for it in range(reps):
     ctx.synchronize(); t1 = time.perf_counter()
     print("register %d pairs: %.3f ms" % (P, 1e3 * (t1 - t0)))
 print({pkg.STAGES[i]: round(ctx.stage_ms(i)[0] / reps, 3) for i in range(len(pkg.STAGES))})
+if os.environ.get("KSS_ICP_PHASES"):
+    import ctypes as C
+    a = np.zeros(16, np.uint64)
+    ctx.lib.kss_debug_read.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_void_p]
+    assert ctx.lib.kss_debug_read(ctx.h, b"icp_phase", 0, 128, a.ctypes.data_as(C.c_void_p)) == 0
+    names = ["setup", "nn", "passA", "lvl2", "passB", "serial-tail+barrier", "post-loop", "fitness", "umeyama", "matmul", "convergence", "sigma-lvl2", "-", "-", "-", "-"]
+    tot = float(a.sum())
+    print("icp phases (thread-0 cycles, last call): " + ", ".join("%s %.1f%%" % (n, 100 * v / tot) for n, v in zip(names, a)))
+    print("total Mcycles %.1f" % (tot / 1e6))
