@@ -208,7 +208,7 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
     const int cap_s = b.cap_s, cap_t = b.cap_t, cap_S = b.cap_S, cap_T = b.cap_T;
     const int cap_tpad = pad32(cap_t), cap_Tpad = pad32(cap_T);
     const int R = 1 + slots;
-    double *align8, *s_al, *rbuf, *value, *run_fit;
+    double *align8, *s_al, *value, *run_fit; float* rbuf;
     unsigned short *s_perm, *t_inv, *S_perm, *T_inv;
     float4 *t_sorted, *T_sorted;
     float *t_box, *T_box, *run_T;
@@ -307,7 +307,7 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
 
 size_t per_pair_ws_bytes(const kss_batch& b, int H, int slots) {
     size_t v = (cg_enabled() ? cg_hdr_words_per_pair() * 8 + cg_arena_entries_per_pair() * 2 + cg_worklist_entries_per_pair() * 2 + cg_worklist2_entries_per_pair() * 16 + 64 : 0) +
-               (size_t)b.cap_s * H * 8 + (size_t)b.cap_s * 30 + (size_t)pad32(b.cap_t) * 18 + (size_t)H * 12 +
+               (size_t)b.cap_s * H * 4 + (size_t)b.cap_s * 30 + (size_t)pad32(b.cap_t) * 18 + (size_t)H * 12 +
                (size_t)(1 + slots) * 96 + (size_t)b.cap_S * 26 + (size_t)pad32(b.cap_T) * 18 + 8192;
     return v;
 }
@@ -483,7 +483,7 @@ int kss_rotation_sweep(kss_ctx* ctx, const double* src_aligned, int n_s, const d
     CU(cudaSetDevice(ctx->device));
     int r = ensure_trig(ctx, step); if (r) return r;
     const int G = ctx->G, H = G * G * G;
-    double *d_s, *d_t, *rbuf, *d_val; const int *c_s, *c_t;
+    double *d_s, *d_t, *d_val; float* rbuf; const int *c_s, *c_t;
     unsigned short *s_perm, *t_inv; float4* t_sorted; float* t_box; int *d_best, *d_min, *d_nmin;
     const int tpad = pad32(n_t);
     BUF("one_s", (size_t)n_s * 3, &d_s); BUF("one_t", (size_t)n_t * 3, &d_t);

@@ -57,12 +57,12 @@ cudaError_t launch_middle_align(cudaStream_t st, int P, const double* sim_s, con
 cudaError_t launch_sweep(cudaStream_t st, int P, const double* s_al, const int* cnt_s, int cap_s,
                          const unsigned short* s_perm, const float4* t_sorted, const float* t_box,
                          const int* cnt_t, int cap_tpad, const double* trig_accum, int G, int score_mode,
-                         double* rbuf, int hpad, const CgBuffers* cg);
+                         float* rbuf, int hpad, const CgBuffers* cg);
 cudaError_t launch_cg_build(cudaStream_t st, int P, int geom_mode, const double* a, const int* cnt_a, int cap_a,
                             const double* b, const int* cnt_b, int cap_b, const float4* t_sorted,
                             const unsigned short* t_inv, int cap_t, const int* cnt_t,
                             int cap_tpad, const CgBuffers& cg, int* launches);
-cudaError_t launch_sweep_finalize(cudaStream_t st, int P, const double* rbuf, const int* cnt_s, int cap_s, int hpad,
+cudaError_t launch_sweep_finalize(cudaStream_t st, int P, const float* rbuf, const int* cnt_s, int cap_s, int hpad,
                                   int G, int score_mode, double* value, int* best_h, int* minima, int* n_minima);
 cudaError_t launch_icp(cudaStream_t st, int P, int slots, const IcpArgs& a);
 cudaError_t launch_select(cudaStream_t st, int P, int runs_per_pair, int hpad, int G, double judge_thr,

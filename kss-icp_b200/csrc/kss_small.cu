@@ -547,7 +547,7 @@ cg_level_kernel(int level, const float4* __restrict__ t_sorted, const unsigned s
 // =============================================================== sweep_kernel
 // grid (G*G, P): CTA (i,j) of pair p applies Rx(i), Ry(j) once per point and loops Rz(k),
 // searching the exact NN of every rotated point (narrowed to float) in the Morton-tiled
-// target.  rbuf[p][orig][h] receives (double)sqrtf(d2) (score modes AVE/DIFF) or (double)d2
+// target.  rbuf[p][orig][h] receives sqrtf(d2) as a float (widened exactly later) (score modes AVE/DIFF) or (double)d2
 // (MAX); the serial sums are taken by sweep_finalize_kernel.
 __global__ void __launch_bounds__(256)
 sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int cap_s,
@@ -555,7 +555,7 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
              const float4* __restrict__ t_sorted, const float* __restrict__ t_box,
              const int* __restrict__ cnt_t, int cap_tpad,
              const double* __restrict__ trig_accum /* [G][2] cos,sin */, int G, int score_mode,
-             double* __restrict__ rbuf, int hpad,
+             float* __restrict__ rbuf, int hpad,
              const float* __restrict__ cg_geom, const cg_hdr_t* __restrict__ cg_hdr,
              const unsigned short* __restrict__ cg_arena, const int* __restrict__ cg_ok) {
     extern __shared__ unsigned char smem_raw[];
@@ -580,7 +580,7 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
     const int n_s = cnt_s[p];
     const unsigned short* perm = s_perm + (size_t)p * cap_s;
     const double* sa = s_al + (size_t)p * cap_s * 3;
-    double* rb = rbuf + (size_t)p * cap_s * hpad;
+    float* rb = rbuf + (size_t)p * cap_s * hpad;
     const int hbase = (gi * G + gj) * G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
@@ -591,7 +591,7 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
         double x = sa[3 * o], y = sa[3 * o + 1], z = sa[3 * o + 2];
         rot_x(ci, si, y, z);
         rot_y(cj, sj, x, z);
-        double* ro = rb + (size_t)o * hpad + hbase;
+        float* ro = rb + (size_t)o * hpad + hbase;
         if (use_cg) {
             // three z-rotations per batch: their grid look-ups overlap (cg_query_batch)
             constexpr int U = 3;
@@ -610,7 +610,8 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const float d2 = __uint_as_float((unsigned)(key[u] >> 32));
-                    const double r = score_mode == 1 ? (double)d2 : (double)__fsqrt_rn(d2);   // float sqrt, then widened (:444)
+                    // float sqrt (:444); the reference widens it to double before summing: sweep_finalize_kernel does
+                    const float r = score_mode == 1 ? d2 : __fsqrt_rn(d2);
                     if (valid && k0 + u < G) ro[k0 + u] = r;
                 }
             }
@@ -622,7 +623,7 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
                 const float qx = (float)xx, qy = (float)yy, qz = (float)z;   // :440-442 narrowing
                 const unsigned long long key = warp_nn<false>(tv, qx, qy, qz);
                 const float d2 = __uint_as_float((unsigned)(key >> 32));
-                const double r = score_mode == 1 ? (double)d2 : (double)__fsqrt_rn(d2);
+                const float r = score_mode == 1 ? d2 : __fsqrt_rn(d2);
                 if (valid) ro[k] = r;
             }
         }
@@ -634,7 +635,7 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
 // reference's `distanceSum = distanceSum + distance_i`), then argmin (first strict <,
 // errorT = 9999) and the clamped 5x5x5 local-minimum test in (i,j,k) loop order.
 __global__ void __launch_bounds__(1024)
-sweep_finalize_kernel(const double* __restrict__ rbuf, const int* __restrict__ cnt_s, int cap_s, int hpad,
+sweep_finalize_kernel(const float* __restrict__ rbuf, const int* __restrict__ cnt_s, int cap_s, int hpad,
                       int G, int score_mode,
                       double* __restrict__ value /* [P][hpad] */, int* __restrict__ best_h /* [P] */,
                       int* __restrict__ minima /* [P][hpad] */, int* __restrict__ n_minima /* [P] */) {
@@ -645,13 +646,25 @@ sweep_finalize_kernel(const double* __restrict__ rbuf, const int* __restrict__ c
     const int p = blockIdx.x;
     const int H = G * G * G;
     const int n = cnt_s[p];
-    const double* rb = rbuf + (size_t)p * cap_s * hpad;
+    const float* rb = rbuf + (size_t)p * cap_s * hpad;
     if (threadIdx.x == 0) bestkey = 0xffffffffffffffffull;
     for (int h = threadIdx.x; h < H; h += blockDim.x) {
         double sum = 0.0, dmax = -9999.0;
-#pragma unroll 8
-        for (int i = 0; i < n; ++i) {
-            const double r = rb[(size_t)i * hpad + h];
+        // 16 independent loads in flight per thread, then the strictly ordered adds
+        int i = 0;
+        for (; i + 16 <= n; i += 16) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = __ldg(rb + (size_t)(i + u) * hpad + h);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const double r = (double)v[u];
+                if (score_mode == 1) { if (r > dmax) dmax = r; }
+                else { sum = __dadd_rn(sum, r); if (dmax < r) dmax = r; }
+            }
+        }
+        for (; i < n; ++i) {
+            const double r = (double)rb[(size_t)i * hpad + h];
             if (score_mode == 1) { if (r > dmax) dmax = r; }
             else { sum = __dadd_rn(sum, r); if (dmax < r) dmax = r; }
         }
@@ -1235,7 +1248,7 @@ cudaError_t launch_middle_align(cudaStream_t st, int P, const double* sim_s, con
 cudaError_t launch_sweep(cudaStream_t st, int P, const double* s_al, const int* cnt_s, int cap_s,
                          const unsigned short* s_perm, const float4* t_sorted, const float* t_box,
                          const int* cnt_t, int cap_tpad, const double* trig_accum, int G, int score_mode,
-                         double* rbuf, int hpad, const CgBuffers* cg) {
+                         float* rbuf, int hpad, const CgBuffers* cg) {
     const size_t smem = (size_t)cap_tpad * sizeof(float4) + 6 * MAX_TILES * sizeof(float);
     static size_t set = 0;
     if (smem > set) { cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
@@ -1281,7 +1294,7 @@ size_t cg_arena_entries_per_pair() { return CG_ARENA; }
 size_t cg_worklist_entries_per_pair() { return CG_WL_CAP; }
 size_t cg_worklist2_entries_per_pair() { return CG_WL2_CAP; }
 
-cudaError_t launch_sweep_finalize(cudaStream_t st, int P, const double* rbuf, const int* cnt_s, int cap_s, int hpad,
+cudaError_t launch_sweep_finalize(cudaStream_t st, int P, const float* rbuf, const int* cnt_s, int cap_s, int hpad,
                                   int G, int score_mode, double* value, int* best_h, int* minima, int* n_minima) {
     const int H = G * G * G;
     const size_t smem = (size_t)H * sizeof(double) + H;
