@@ -34,6 +34,13 @@ struct kss_ctx {
     size_t ws_budget = (size_t)48 << 30;
     int slots_override = 0;
     int* aivs_bad = nullptr;          // device flag written by the last raw-cloud batch (kss_aivs.h)
+    // batch lanes: chunks of a batch alternate between a few internal streams, so that one chunk's copies and the
+    // thin tail of its ICP launch overlap the next chunk's kernels; every lane has its own set of named buffers
+    static constexpr int MAX_LANES = 4;
+    cudaStream_t lane_stream[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t lane_done[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr;
+    std::string buf_suffix;           // appended to buffer names while a lane is active
     // optional per-stage CUDA-event timing (bench.py roofline): events on the launching stream
     bool timing = false;
     struct Span { int stage; cudaEvent_t a, b; };
@@ -98,11 +105,11 @@ void collect_spans(kss_ctx* c) {
 
 template <class T>
 int dev_buf(kss_ctx* ctx, const char* name, size_t count, T** out) {
-    kss_ctx::Buf& b = ctx->bufs[name];
+    kss_ctx::Buf& b = ctx->bufs[ctx->buf_suffix.empty() ? std::string(name) : std::string(name) + ctx->buf_suffix];
     size_t bytes = count * sizeof(T);
     if (bytes == 0) bytes = 16;
     if (b.cap < bytes) {
-        if (b.p) { cudaStreamSynchronize(ctx->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+        if (b.p) { cudaDeviceSynchronize(); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
         size_t want = bytes + bytes / 8;
         cudaError_t e = cudaMalloc(&b.p, want);
         if (e != cudaSuccess) {
@@ -365,10 +372,15 @@ int kss_ctx_create(int device, kss_ctx** out) { return kss_ctx_create_on_stream(
 void kss_ctx_destroy(kss_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
     collect_spans(ctx);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto& kv : ctx->bufs) if (kv.second.p) cudaFree(kv.second.p);
+    for (int l = 0; l < kss_ctx::MAX_LANES; ++l) {
+        if (ctx->lane_stream[l]) cudaStreamDestroy(ctx->lane_stream[l]);
+        if (ctx->lane_done[l]) cudaEventDestroy(ctx->lane_done[l]);
+    }
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -680,73 +692,159 @@ int kss_nn_metrics(kss_ctx* ctx, const double* a, int n_a, const double* t, int 
     return nn_common(ctx, a, n_a, t, n_t, 1, nullptr, nullptr, out3);
 }
 
-int kss_register_batch_device(kss_ctx* ctx, const kss_batch* b_in, kss_pair_result* d_results, double* d_point_align) {
-    int r = check_batch(ctx, b_in); if (r) return r;
-    if (!d_results) return fail(ctx, KSS_ERR_ARG, "kss_register_batch_device: null results");
-    CU(cudaSetDevice(ctx->device));
-    kss_batch bb = *b_in;
-    const kss_batch* b = &bb;
-    const bool raw = !bb.sim_s;
-    if (raw) {   // pNumber (KSS_ICP.hpp:53-67) plus room for a trim step that stops early on its stale neighbour lists
-        const int pn = std::min(2000, std::min(bb.cap_S, bb.cap_T) / 2);
-        bb.cap_s = std::min(std::min(pn + 48, SMALL_MAX), bb.cap_S);
-        bb.cap_t = std::min(std::min(pn + 48, SMALL_MAX), bb.cap_T);
-    }
-    r = ensure_trig(ctx, b->step); if (r) return r;
-    const int H = ctx->G * ctx->G * ctx->G;
-    int slots = 32;
-    const char* es = getenv("KSS_HYP_SLOTS");
-    if (es && atoi(es) > 0) slots = atoi(es);
-    if (ctx->slots_override > 0) slots = ctx->slots_override;
-    if (slots > H) slots = H;
-    const size_t per = per_pair_ws_bytes(*b, H, slots) + (raw ? (size_t)(b->cap_S + b->cap_T) * 64 + 65536 : 0);
-    int chunk = (int)std::min<size_t>((size_t)b->n_pairs, std::max<size_t>(1, ctx->ws_budget / per));
-    auto alloc = [&](const char* name, size_t bytes, void** out) {
-        unsigned char* q; int rr = dev_buf(ctx, name, bytes, &q); *out = q; return rr; };
-    for (int p0 = 0; p0 < b->n_pairs; p0 += chunk) {
-        const int P = std::min(chunk, b->n_pairs - p0);
-        const int *c_s, *c_t, *c_S, *c_T;
-        r = counts_or_fill(ctx, "cnt_S", b->cnt_S ? b->cnt_S + p0 : nullptr, P, b->cap_S, &c_S); if (r) return r;
-        r = counts_or_fill(ctx, "cnt_T", b->cnt_T ? b->cnt_T + p0 : nullptr, P, b->cap_T, &c_T); if (r) return r;
-        const double* full_s = b->full_s + (size_t)p0 * b->cap_S * 3;
-        const double* full_t = b->full_t + (size_t)p0 * b->cap_T * 3;
-        const double *sim_s, *sim_t;
-        if (raw) {
-            // KSSICP_Registration's first half (KSS_ICP.hpp:72-84): AIVS_simplification(pNumber) of target and source
-            StageTimer tm(ctx, KSS_STAGE_AIVS);
-            double *d_ss, *d_st; int *d_pn, *d_cs, *d_ct, *d_bad;
-            BUF("aivs_sim_s", (size_t)P * b->cap_s * 3, &d_ss); BUF("aivs_sim_t", (size_t)P * b->cap_t * 3, &d_st);
-            BUF("aivs_pn", P, &d_pn); BUF("aivs_cnt_s", P, &d_cs); BUF("aivs_cnt_t", P, &d_ct);
-            BUF("aivs_bad", 1, &d_bad);
-            if (p0 == 0) CU(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
-            r = aivs_pnumber_device(ctx->stream, &ctx->launches, P, c_S, b->cap_S, c_T, b->cap_T, d_pn);
-            if (!r) r = aivs_simplify_device(ctx->stream, &ctx->launches, P, full_t, c_T, b->cap_T, d_pn, 0, d_st, b->cap_t, d_ct,
-                                             nullptr, d_bad, alloc, "t");
-            if (!r) r = aivs_simplify_device(ctx->stream, &ctx->launches, P, full_s, c_S, b->cap_S, d_pn, 0, d_ss, b->cap_s, d_cs,
-                                             nullptr, d_bad, alloc, "s");
-            if (r) return fail(ctx, r, "AIVS simplification failed to launch");
-            sim_s = d_ss; sim_t = d_st; c_s = d_cs; c_t = d_ct;
-            ctx->aivs_bad = d_bad;
-        } else {
-            r = counts_or_fill(ctx, "cnt_s", b->cnt_s ? b->cnt_s + p0 : nullptr, P, b->cap_s, &c_s); if (r) return r;
-            r = counts_or_fill(ctx, "cnt_t", b->cnt_t ? b->cnt_t + p0 : nullptr, P, b->cap_t, &c_t); if (r) return r;
-            sim_s = b->sim_s + (size_t)p0 * b->cap_s * 3; sim_t = b->sim_t + (size_t)p0 * b->cap_t * 3;
-        }
-        r = pipeline_device(ctx, P, *b, sim_s, sim_t, full_s, full_t, c_s, c_t, c_S, c_T, slots, d_results + p0,
-                            d_point_align ? d_point_align + (size_t)p0 * b->cap_S * 3 : nullptr);
-        if (r) return r;
-    }
-    return KSS_OK;
-}
-
 namespace {
+
 int aivs_status(kss_ctx* ctx, int bad) {
     if (bad == 1) return fail(ctx, KSS_ERR_UNSUPPORTED, "AIVS: a cloud has zero extent or needs more boxes than its point count allows");
     if (bad == 2) return fail(ctx, KSS_ERR_UNSUPPORTED, "AIVS: more than 16384 samples before the trim step");
     if (bad == 3) return fail(ctx, KSS_ERR_UNSUPPORTED, "AIVS: output capacity too small");
     return KSS_OK;
 }
+
+int ensure_lanes(kss_ctx* ctx, int n) {
+    for (int l = 0; l < n; ++l) {
+        if (!ctx->lane_stream[l]) CU(cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
+        if (!ctx->lane_done[l]) CU(cudaEventCreateWithFlags(&ctx->lane_done[l], cudaEventDisableTiming));
+    }
+    if (!ctx->fork_ev) CU(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+    return KSS_OK;
+}
+
+// The batch in chunks; `host` = b's clouds/counts and results/point_align are host memory (copied per chunk on the
+// chunk's lane), else device memory.  Everything is ordered after the work already on ctx->stream, and ctx->stream
+// waits for all lanes at the end.
+int batch_core(kss_ctx* ctx, const kss_batch* b_in, bool host, kss_pair_result* results, double* point_align) {
+    kss_batch bb = *b_in;
+    const bool raw = !bb.sim_s;
+    if (raw) {   // pNumber (KSS_ICP.hpp:53-67) plus room for a trim step that stops early on its stale neighbour lists
+        const int pn = std::min(2000, std::min(bb.cap_S, bb.cap_T) / 2);
+        bb.cap_s = std::min(std::min(pn + 48, SMALL_MAX), bb.cap_S);
+        bb.cap_t = std::min(std::min(pn + 48, SMALL_MAX), bb.cap_T);
+    }
+    int r = ensure_trig(ctx, bb.step); if (r) return r;
+    const int H = ctx->G * ctx->G * ctx->G;
+    int slots = 32;
+    const char* es = getenv("KSS_HYP_SLOTS");
+    if (es && atoi(es) > 0) slots = atoi(es);
+    if (ctx->slots_override > 0) slots = ctx->slots_override;
+    if (slots > H) slots = H;
+    int lanes = 2;
+    const char* el = getenv("KSS_LANES");
+    if (el && atoi(el) > 0) lanes = std::min(atoi(el), (int)kss_ctx::MAX_LANES);
+    const size_t per = per_pair_ws_bytes(bb, H, slots) + (raw ? (size_t)(bb.cap_S + bb.cap_T) * 64 + 65536 : 0) +
+                       (host ? (size_t)(bb.cap_S + bb.cap_T + bb.cap_s + bb.cap_t) * 24 : 0);
+    const int NP = bb.n_pairs;
+    int chunk = (int)std::min<size_t>((size_t)NP, std::max<size_t>(1, ctx->ws_budget / (per * (size_t)lanes)));
+    // two chunks per lane when the batch is big enough for every chunk to give each SM a pair; equal chunk sizes
+    if (lanes > 1) {
+        // measured on B200 (2,468 / 1,234 / 617 / 309 pairs): two chunks hide one chunk's thin ICP tail behind the other's
+        // kernels (+8 % at 309-617 pairs, neutral at 2,468); with host buffers four chunks also hide most of the copies
+        int want = NP >= 296 ? 2 : 1;
+        if (host && NP >= 4 * 296) want = 4;
+        const char* em = getenv("KSS_CHUNKS");
+        if (em && atoi(em) > 0) want = atoi(em);
+        int nchunks = std::max((NP + chunk - 1) / chunk, want);
+        if (nchunks < 1) nchunks = 1;
+        chunk = (NP + nchunks - 1) / nchunks;
+    }
+    if (chunk >= NP) lanes = 1;
+    r = ensure_lanes(ctx, lanes); if (r) return r;
+    cudaStream_t main_st = ctx->stream;
+    int* d_bad = nullptr;
+    if (raw) { BUF("aivs_bad", 1, &d_bad); CU(cudaMemsetAsync(d_bad, 0, sizeof(int), main_st)); ctx->aivs_bad = d_bad; }
+    CU(cudaEventRecord(ctx->fork_ev, main_st));
+    for (int l = 0; l < lanes; ++l) CU(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->fork_ev, 0));
+    auto alloc = [&](const char* name, size_t bytes, void** out) {
+        unsigned char* q; int rr = dev_buf(ctx, name, bytes, &q); *out = q; return rr; };
+    int rc = KSS_OK, ci = 0;
+    for (int p0 = 0; p0 < NP && rc == KSS_OK; p0 += chunk, ++ci) {
+        const int P = std::min(chunk, NP - p0);
+        const int lane = ci % lanes;
+        cudaStream_t st = ctx->lane_stream[lane];
+        ctx->stream = st;
+        ctx->buf_suffix = "#" + std::to_string(lane);
+        rc = [&]() -> int {
+            const double *full_s, *full_t, *sim_s = nullptr, *sim_t = nullptr;
+            const int *c_s = nullptr, *c_t = nullptr, *c_S = nullptr, *c_T = nullptr;
+            kss_pair_result* d_res = results ? results + p0 : nullptr;
+            double* d_pa = point_align ? point_align + (size_t)p0 * bb.cap_S * 3 : nullptr;
+            if (host) {
+                double *d_fs, *d_ft;
+                BUF("in_full_s", (size_t)P * bb.cap_S * 3, &d_fs); BUF("in_full_t", (size_t)P * bb.cap_T * 3, &d_ft);
+                CU(cudaMemcpyAsync(d_ft, bb.full_t + (size_t)p0 * bb.cap_T * 3, sizeof(double) * 3 * (size_t)P * bb.cap_T, cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync(d_fs, bb.full_s + (size_t)p0 * bb.cap_S * 3, sizeof(double) * 3 * (size_t)P * bb.cap_S, cudaMemcpyHostToDevice, st));
+                full_s = d_fs; full_t = d_ft;
+                if (!raw) {
+                    double *d_ss, *d_st;
+                    BUF("in_sim_s", (size_t)P * bb.cap_s * 3, &d_ss); BUF("in_sim_t", (size_t)P * bb.cap_t * 3, &d_st);
+                    CU(cudaMemcpyAsync(d_ss, bb.sim_s + (size_t)p0 * bb.cap_s * 3, sizeof(double) * 3 * (size_t)P * bb.cap_s, cudaMemcpyHostToDevice, st));
+                    CU(cudaMemcpyAsync(d_st, bb.sim_t + (size_t)p0 * bb.cap_t * 3, sizeof(double) * 3 * (size_t)P * bb.cap_t, cudaMemcpyHostToDevice, st));
+                    sim_s = d_ss; sim_t = d_st;
+                }
+                auto up = [&](const char* name, const int* h, const int** out) -> int {
+                    if (!h) return KSS_OK;
+                    int* d; BUF(name, P, &d);
+                    CU(cudaMemcpyAsync(d, h + p0, sizeof(int) * P, cudaMemcpyHostToDevice, st));
+                    *out = d; return KSS_OK;
+                };
+                int q;
+                if (!raw) { q = up("in_cnt_s", bb.cnt_s, &c_s); if (q) return q; q = up("in_cnt_t", bb.cnt_t, &c_t); if (q) return q; }
+                q = up("in_cnt_S", bb.cnt_S, &c_S); if (q) return q;
+                q = up("in_cnt_T", bb.cnt_T, &c_T); if (q) return q;
+                BUF("out_res", (size_t)P, &d_res);
+                if (point_align) BUF("out_pa", (size_t)P * bb.cap_S * 3, &d_pa);
+            } else {
+                full_s = bb.full_s + (size_t)p0 * bb.cap_S * 3; full_t = bb.full_t + (size_t)p0 * bb.cap_T * 3;
+                if (!raw) { sim_s = bb.sim_s + (size_t)p0 * bb.cap_s * 3; sim_t = bb.sim_t + (size_t)p0 * bb.cap_t * 3; }
+                if (!raw && bb.cnt_s) c_s = bb.cnt_s + p0;
+                if (!raw && bb.cnt_t) c_t = bb.cnt_t + p0;
+                if (bb.cnt_S) c_S = bb.cnt_S + p0;
+                if (bb.cnt_T) c_T = bb.cnt_T + p0;
+            }
+            int q = counts_or_fill(ctx, "cnt_S", c_S, P, bb.cap_S, &c_S); if (q) return q;
+            q = counts_or_fill(ctx, "cnt_T", c_T, P, bb.cap_T, &c_T); if (q) return q;
+            if (raw) {
+                // KSSICP_Registration's first half (KSS_ICP.hpp:72-84): AIVS_simplification(pNumber) of target and source
+                StageTimer tm(ctx, KSS_STAGE_AIVS);
+                double *d_ss, *d_st; int *d_pn, *d_cs, *d_ct;
+                BUF("aivs_sim_s", (size_t)P * bb.cap_s * 3, &d_ss); BUF("aivs_sim_t", (size_t)P * bb.cap_t * 3, &d_st);
+                BUF("aivs_pn", P, &d_pn); BUF("aivs_cnt_s", P, &d_cs); BUF("aivs_cnt_t", P, &d_ct);
+                q = aivs_pnumber_device(st, &ctx->launches, P, c_S, bb.cap_S, c_T, bb.cap_T, d_pn);
+                if (!q) q = aivs_simplify_device(st, &ctx->launches, P, full_t, c_T, bb.cap_T, d_pn, 0, d_st, bb.cap_t, d_ct, nullptr, d_bad, alloc, "t");
+                if (!q) q = aivs_simplify_device(st, &ctx->launches, P, full_s, c_S, bb.cap_S, d_pn, 0, d_ss, bb.cap_s, d_cs, nullptr, d_bad, alloc, "s");
+                if (q) return fail(ctx, q, "AIVS simplification failed to launch");
+                sim_s = d_ss; sim_t = d_st; c_s = d_cs; c_t = d_ct;
+            } else {
+                q = counts_or_fill(ctx, "cnt_s", c_s, P, bb.cap_s, &c_s); if (q) return q;
+                q = counts_or_fill(ctx, "cnt_t", c_t, P, bb.cap_t, &c_t); if (q) return q;
+            }
+            q = pipeline_device(ctx, P, bb, sim_s, sim_t, full_s, full_t, c_s, c_t, c_S, c_T, slots, d_res, d_pa);
+            if (q) return q;
+            if (host) {
+                CU(cudaMemcpyAsync(results + p0, d_res, sizeof(kss_pair_result) * (size_t)P, cudaMemcpyDeviceToHost, st));
+                if (point_align)
+                    CU(cudaMemcpyAsync(point_align + (size_t)p0 * bb.cap_S * 3, d_pa, sizeof(double) * 3 * (size_t)P * bb.cap_S, cudaMemcpyDeviceToHost, st));
+            }
+            return KSS_OK;
+        }();
+    }
+    ctx->stream = main_st;
+    ctx->buf_suffix.clear();
+    for (int l = 0; l < lanes; ++l) {
+        if (cudaEventRecord(ctx->lane_done[l], ctx->lane_stream[l]) != cudaSuccess ||
+            cudaStreamWaitEvent(main_st, ctx->lane_done[l], 0) != cudaSuccess) { if (rc == KSS_OK) rc = fail(ctx, KSS_ERR_CUDA, "lane join failed"); }
+    }
+    return rc;
+}
+
 }  // namespace
+
+int kss_register_batch_device(kss_ctx* ctx, const kss_batch* b, kss_pair_result* d_results, double* d_point_align) {
+    int r = check_batch(ctx, b); if (r) return r;
+    if (!d_results) return fail(ctx, KSS_ERR_ARG, "kss_register_batch_device: null results");
+    CU(cudaSetDevice(ctx->device));
+    return batch_core(ctx, b, false, d_results, d_point_align);
+}
 
 int kss_register_batch(kss_ctx* ctx, const kss_batch* b, kss_pair_result* results, double* point_align) {
     int r = check_batch(ctx, b); if (r) return r;
@@ -754,49 +852,25 @@ int kss_register_batch(kss_ctx* ctx, const kss_batch* b, kss_pair_result* result
     CU(cudaSetDevice(ctx->device));
     const int P = b->n_pairs;
     const bool raw = !b->sim_s;
-    double *d_ss = nullptr, *d_st = nullptr, *d_fs, *d_ft, *d_pa = nullptr; kss_pair_result* d_res;
-    int *d_cs = nullptr, *d_ct = nullptr, *d_cS = nullptr, *d_cT = nullptr;
-    if (!raw) { BUF("in_sim_s", (size_t)P * b->cap_s * 3, &d_ss); BUF("in_sim_t", (size_t)P * b->cap_t * 3, &d_st); }
-    BUF("in_full_s", (size_t)P * b->cap_S * 3, &d_fs); BUF("in_full_t", (size_t)P * b->cap_T * 3, &d_ft);
-    BUF("out_res", (size_t)P, &d_res);
-    if (point_align) BUF("out_pa", (size_t)P * b->cap_S * 3, &d_pa);
+    r = batch_core(ctx, b, true, results, point_align); if (r) return r;
     cudaStream_t st = ctx->stream;
-    if (!raw) {
-        CU(cudaMemcpyAsync(d_ss, b->sim_s, sizeof(double) * 3 * (size_t)P * b->cap_s, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(d_st, b->sim_t, sizeof(double) * 3 * (size_t)P * b->cap_t, cudaMemcpyHostToDevice, st));
-    }
-    CU(cudaMemcpyAsync(d_fs, b->full_s, sizeof(double) * 3 * (size_t)P * b->cap_S, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_ft, b->full_t, sizeof(double) * 3 * (size_t)P * b->cap_T, cudaMemcpyHostToDevice, st));
-    kss_batch db = *b;
-    db.sim_s = d_ss; db.sim_t = d_st; db.full_s = d_fs; db.full_t = d_ft;
-    if (!raw && b->cnt_s) { BUF("in_cnt_s", P, &d_cs); CU(cudaMemcpyAsync(d_cs, b->cnt_s, sizeof(int) * P, cudaMemcpyHostToDevice, st)); db.cnt_s = d_cs; }
-    if (!raw && b->cnt_t) { BUF("in_cnt_t", P, &d_ct); CU(cudaMemcpyAsync(d_ct, b->cnt_t, sizeof(int) * P, cudaMemcpyHostToDevice, st)); db.cnt_t = d_ct; }
-    if (b->cnt_S) { BUF("in_cnt_S", P, &d_cS); CU(cudaMemcpyAsync(d_cS, b->cnt_S, sizeof(int) * P, cudaMemcpyHostToDevice, st)); db.cnt_S = d_cS; }
-    if (b->cnt_T) { BUF("in_cnt_T", P, &d_cT); CU(cudaMemcpyAsync(d_cT, b->cnt_T, sizeof(int) * P, cudaMemcpyHostToDevice, st)); db.cnt_T = d_cT; }
-    r = kss_register_batch_device(ctx, &db, d_res, d_pa); if (r) return r;
     int bad = 0;
     if (raw) CU(cudaMemcpyAsync(&bad, ctx->aivs_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(results, d_res, sizeof(kss_pair_result) * (size_t)P, cudaMemcpyDeviceToHost, st));
-    if (point_align) CU(cudaMemcpyAsync(point_align, d_pa, sizeof(double) * 3 * (size_t)P * b->cap_S, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (bad) return aivs_status(ctx, bad);
     // pairs whose local-minimum list exceeded the hypothesis slots: re-run alone with enough slots
     for (int p = 0; p < P; ++p) {
         if (!results[p].overflow) continue;
-        kss_batch one = db;
+        kss_batch one = *b;
         one.n_pairs = 1;
-        if (!raw) { one.sim_s = d_ss + (size_t)p * b->cap_s * 3; one.sim_t = d_st + (size_t)p * b->cap_t * 3; }
-        one.full_s = d_fs + (size_t)p * b->cap_S * 3; one.full_t = d_ft + (size_t)p * b->cap_T * 3;
-        one.cnt_s = db.cnt_s ? db.cnt_s + p : nullptr; one.cnt_t = db.cnt_t ? db.cnt_t + p : nullptr;
-        one.cnt_S = db.cnt_S ? db.cnt_S + p : nullptr; one.cnt_T = db.cnt_T ? db.cnt_T + p : nullptr;
+        if (!raw) { one.sim_s = b->sim_s + (size_t)p * b->cap_s * 3; one.sim_t = b->sim_t + (size_t)p * b->cap_t * 3; }
+        one.full_s = b->full_s + (size_t)p * b->cap_S * 3; one.full_t = b->full_t + (size_t)p * b->cap_T * 3;
+        one.cnt_s = b->cnt_s ? b->cnt_s + p : nullptr; one.cnt_t = b->cnt_t ? b->cnt_t + p : nullptr;
+        one.cnt_S = b->cnt_S ? b->cnt_S + p : nullptr; one.cnt_T = b->cnt_T ? b->cnt_T + p : nullptr;
         ctx->slots_override = results[p].n_minima;
-        r = kss_register_batch_device(ctx, &one, d_res + p, d_pa ? d_pa + (size_t)p * b->cap_S * 3 : nullptr);
+        r = batch_core(ctx, &one, true, results + p, point_align ? point_align + (size_t)p * b->cap_S * 3 : nullptr);
         ctx->slots_override = 0;
         if (r) return r;
-        CU(cudaMemcpyAsync(results + p, d_res + p, sizeof(kss_pair_result), cudaMemcpyDeviceToHost, st));
-        if (point_align)
-            CU(cudaMemcpyAsync(point_align + (size_t)p * b->cap_S * 3, d_pa + (size_t)p * b->cap_S * 3,
-                               sizeof(double) * 3 * (size_t)b->cap_S, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         results[p].overflow = 1;
     }
@@ -827,6 +901,7 @@ int kss_aivs_simplify_batch_device(kss_ctx* ctx, int n_clouds, const double* d_p
 int kss_debug_read(kss_ctx* ctx, const char* name, size_t offset, size_t bytes, void* dst) {
     if (!ctx || !name || !dst) return KSS_ERR_ARG;
     auto it = ctx->bufs.find(name);
+    if (it == ctx->bufs.end()) it = ctx->bufs.find(std::string(name) + "#0");       // batch buffers live per lane
     if (it == ctx->bufs.end() || !it->second.p || offset + bytes > it->second.cap) return fail(ctx, KSS_ERR_ARG, "kss_debug_read: no such buffer / range");
     CU(cudaMemcpyAsync(dst, (const unsigned char*)it->second.p + offset, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
