@@ -524,6 +524,176 @@ __device__ __forceinline__ void cg_build_cell(int tid, int ncells, int level, co
     for (; w < tot4; ++w) out[w] = (unsigned short)first;
 }
 
+// =============================================================== cg_level_coop_kernel
+// Dense levels 1..3 with EIGHT LANES PER CELL: the parent lists of these levels are long (tens to hundreds of entries)
+// and, with one thread per cell, a warp mixed cells outside the query ball, short and long lists (11 of 32 lanes
+// active in ncu).  Here a warp holds four sibling cells -- same parent, same list, same trip count -- and the eight
+// lanes of a cell stride over the list.  Same rules and the same (ascending original index) output order as
+// cg_build_cell: kept candidates are remembered as per-lane bit masks and written with ballot-ordered positions.
+// Collectives inside the per-cell loops use the cell's own 8-lane mask (trip counts differ between the four cells).
+__global__ void __launch_bounds__(256)
+cg_level_coop_kernel(int level, const float4* __restrict__ t_sorted, const unsigned short* __restrict__ t_inv_all, int cap_t,
+                     const int* __restrict__ cnt_t, int cap_tpad,
+                     const float* __restrict__ geom, cg_hdr_t* __restrict__ hdr_all,
+                     unsigned short* __restrict__ arena_all, unsigned* __restrict__ cursor, int* __restrict__ ok,
+                     unsigned short* __restrict__ wl_all, unsigned* __restrict__ wl_cnt) {
+    const int p = blockIdx.y;
+    const int lane = threadIdx.x & 31, sub = lane & 7, gsh = lane & 24;
+    const unsigned gmask = 0xffu << gsh;
+    const int ng = cg_ng(level), png = ng >> 1;
+    const int ncells = ng * ng * ng;
+    const int tid = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;     // = parent * 8 + child
+    if (tid - (lane >> 3) >= ncells) return;                           // whole warp out of range (ncells is a multiple of 4)
+    const bool live = tid < ncells;
+    const int n_t = cnt_t[p];
+    const float4* __restrict__ tgt = t_sorted + (size_t)p * cap_tpad;
+    const unsigned short* __restrict__ tinv = t_inv_all + (size_t)p * cap_t;
+    cg_hdr_t* hdr = hdr_all + (size_t)p * CG_HDR_TOTAL + cg_hdr_base(level);
+    unsigned short* arena = arena_all + (size_t)p * CG_ARENA;
+    const float* gm = geom + (size_t)p * 8;
+    const float R = gm[3], ballR = gm[4];
+    const float h = 2.0f * R / (float)ng;
+    const float rho = h * 0.8660254f * 1.002f;
+    const int child = tid & 7, parent = tid >> 3;
+    const int lp = level + 1, pm = png - 1;                            // png = 2 << level is a power of two
+    const int px = parent & pm, py = (parent >> lp) & pm, pz = parent >> (2 * lp);
+    const int ix = 2 * px + (child & 1), iy = 2 * py + ((child >> 1) & 1), iz = 2 * pz + (child >> 2);
+    const int cell = ix + ng * (iy + ng * iz);
+    cg_hdr_t ph = 0ull;
+    int m_p = 0;
+    const unsigned short* plist = nullptr;
+    bool p_inline = false;
+    if (live) {
+        ph = (hdr_all + (size_t)p * CG_HDR_TOTAL + cg_hdr_base(level - 1))[parent];
+        const unsigned tag = cg_tag(ph);
+        if (tag >= 1u && tag <= (unsigned)CG_INLINE_MAX) { m_p = (int)tag; p_inline = true; }
+        else if (tag == CG_TAG_EXT) { m_p = (int)cg_ext_count(ph); plist = arena + cg_offset(ph); }
+        else if (tag == CG_TAG_HUGE) m_p = n_t;
+    }
+    auto cand = [&](int j) -> int {
+        return p_inline ? (int)cg_inline_id(ph, j) : (plist ? (int)plist[j] : (int)tinv[j]);
+    };
+    const bool copy = p_inline;                                        // a list that fits a header is not refined (see cg_build_cell)
+    if (copy) m_p = 0;
+    const float ox = -R + ((float)ix + 0.5f) * h, oy = -R + ((float)iy + 0.5f) * h, oz = -R + ((float)iz + 0.5f) * h;
+    const float cx = gm[0] + ox, cy = gm[1] + oy, cz = gm[2] + oz;
+    const float rr = ballR + rho;
+    if (!(ox * ox + oy * oy + oz * oz <= rr * rr)) m_p = 0;             // outside the query ball: empty list
+    const float INF = __int_as_float(0x7f800000);
+
+    // ---- pass A: per-lane four nearest to the centre, merged over the cell's eight lanes
+    float e0 = INF, e1 = INF, e2 = INF, e3 = INF;
+    int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+    for (int j = sub; j < m_p; j += 8) {
+        const int id = cand(j);
+        const float4 q = __ldg(tgt + id);
+        const float d = d2_rn(cx, cy, cz, q.x, q.y, q.z);
+        if (d < e3) {
+            if (d < e0) { e3 = e2; i3 = i2; e2 = e1; i2 = i1; e1 = e0; i1 = i0; e0 = d; i0 = id; }
+            else if (d < e1) { e3 = e2; i3 = i2; e2 = e1; i2 = i1; e1 = d; i1 = id; }
+            else if (d < e2) { e3 = e2; i3 = i2; e2 = d; i2 = id; }
+            else { e3 = d; i3 = id; }
+        }
+    }
+    float4 cp[4]; float cd[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float m = e0;
+        m = fminf(m, __shfl_xor_sync(gmask, m, 1));
+        m = fminf(m, __shfl_xor_sync(gmask, m, 2));
+        m = fminf(m, __shfl_xor_sync(gmask, m, 4));
+        const unsigned bal = __ballot_sync(gmask, e0 == m);
+        const int src = __ffs(bal) - 1;                                 // bal != 0: the minimum is somebody's e0
+        const int id = __shfl_sync(gmask, i0, src);
+        cd[c] = id >= 0 ? m : INF;                                      // +inf: never dominates
+        cp[c] = __ldg(tgt + (id >= 0 ? id : 0));
+        if (lane == src) { e0 = e1; i0 = i1; e1 = e2; i1 = i2; e2 = e3; i2 = i3; e3 = INF; i3 = -1; }
+    }
+    const float thr = (sqrtf(cd[0]) + 2.0f * rho) * 1.0001f;
+    const float thr2 = thr * thr;
+    const float hh = h * 1.002f * 1.0001f;
+    const float rr4 = 4.0f * rho * rho;
+    auto keep_test = [&](const float4& q, float d) -> bool {
+        if (!(d <= thr2)) return false;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float s = fabsf(q.x - cp[c].x) + fabsf(q.y - cp[c].y) + fabsf(q.z - cp[c].z);
+            if ((d - cd[c]) - hh * s > 1e-5f * (d + cd[c] + rr4)) return false;
+        }
+        return true;
+    };
+    // ---- pass B: this lane's kept candidates as a bit mask (bit jj <-> list position jj * 8 + sub; lists beyond
+    //      512 entries re-run the test in pass C), the cell's count by ballots
+    unsigned long long mask = 0ull;
+    int k = 0;
+    for (int j0 = 0, jj = 0; j0 < m_p; j0 += 8, ++jj) {
+        const int j = j0 + sub;
+        bool keep = false;
+        if (j < m_p) { const float4 q = __ldg(tgt + cand(j)); keep = keep_test(q, d2_rn(cx, cy, cz, q.x, q.y, q.z)); }
+        if (keep && jj < 64) mask |= 1ull << jj;
+        k += __popc(__ballot_sync(gmask, keep));
+    }
+    const bool huge = k > CG_EXT_MAX;
+    const bool ext = k > CG_INLINE_MAX && !huge;
+    const int tot4 = ext ? ((k + 3) & ~3) : 0;
+    // arena space: the cells' leaders take part in a warp scan, one atomicAdd per warp
+    const int need = (sub == 0 && live) ? tot4 : 0;
+    int incl = need;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(KSS_FULL, incl, o); if (lane >= o) incl += y; }
+    const int wtot = __shfl_sync(KSS_FULL, incl, 31);
+    unsigned base = 0;
+    if (lane == 0 && wtot > 0) base = atomicAdd(&cursor[p], (unsigned)wtot);
+    base = __shfl_sync(KSS_FULL, base, 0);
+    const unsigned off = __shfl_sync(KSS_FULL, base + (unsigned)(incl - need), gsh);      // the leader's offset
+    if ((size_t)base + (size_t)wtot > CG_ARENA) {
+        if (lane == 0) atomicExch(&ok[p], 0);                             // arena exhausted: pair falls back
+        if (live && sub == 0) hdr[cell] = 0ull;
+        return;
+    }
+    // ---- pass C: ordered positions from ballots; inline lists are OR-ed together over the lanes
+    cg_hdr_t packed = 0ull;
+    int first = 0;
+    if (!huge && k > 0) {
+        unsigned short* out = arena + off;
+        int w = 0;
+        for (int j0 = 0, jj = 0; j0 < m_p; j0 += 8, ++jj) {
+            const int j = j0 + sub;
+            bool keep = false; int id = 0;
+            if (j < m_p) {
+                id = cand(j);
+                if (jj < 64) keep = (mask >> jj) & 1ull;
+                else { const float4 q = __ldg(tgt + id); keep = keep_test(q, d2_rn(cx, cy, cz, q.x, q.y, q.z)); }
+            }
+            const unsigned bal = __ballot_sync(gmask, keep) >> gsh;
+            const int pos = w + __popc(bal & ((1u << sub) - 1u));
+            if (keep) {
+                if (ext) out[pos] = (unsigned short)id;
+                else packed |= (cg_hdr_t)(unsigned)id << (11 * pos);
+            }
+            if (w == 0 && bal) first = __shfl_sync(gmask, id, gsh + __ffs(bal) - 1);
+            w += __popc(bal);
+        }
+        if (ext) { if (sub < tot4 - k) out[k + sub] = (unsigned short)first; }
+        else {
+            packed |= __shfl_xor_sync(gmask, packed, 1);
+            packed |= __shfl_xor_sync(gmask, packed, 2);
+            packed |= __shfl_xor_sync(gmask, packed, 4);
+        }
+    }
+    if (!live || sub != 0) return;
+    cg_hdr_t me;
+    if (huge) me = (cg_hdr_t)CG_TAG_HUGE << 60;
+    else if (ext) me = ((cg_hdr_t)CG_TAG_EXT << 60) | ((cg_hdr_t)(unsigned)k << 32) | (cg_hdr_t)(off >> 2);
+    else me = ((cg_hdr_t)(unsigned)k << 60) | packed;                     // k = 0: empty
+    if (copy) me = ph;
+    hdr[cell] = me;
+    if (level == CG_LEVELS - 1 && wl_all != nullptr && !huge && !copy && k >= CG_REFINE_MIN) {
+        const unsigned slot = atomicAdd(&wl_cnt[p], 1u);
+        if (slot < (unsigned)CG_WL_CAP) wl_all[(size_t)p * CG_WL_CAP + slot] = (unsigned short)cell;
+    }
+}
+
 // dense levels: one pass over ng^3 cells (the grid covers them exactly); sparse levels: a fixed, small grid per pair
 // loops over the worklist (its length is only known on the device)
 template <int SPARSE>
@@ -1272,9 +1442,17 @@ cudaError_t launch_cg_build(cudaStream_t st, int P, int geom_mode, const double*
     ++n;
     for (int l = 1; l < CG_LEVELS; ++l) {
         const int ncells = cg_ng(l) * cg_ng(l) * cg_ng(l);
-        cg_level_kernel<0><<<dim3((ncells + 255) / 256, P), 256, 0, st>>>(l, t_sorted, t_inv, cap_t, cnt_t, cap_tpad, cg.geom, cg.hdr,
-                                                                     cg.arena, cg.cursor, cg.ok, refine ? cg.wl : nullptr, cg.wl_cnt,
-                                                                     nullptr, cg.wl2_cnt);
+        int coop_levels = 0x6;                                      // levels 1 and 2: long parent lists
+        const char* ec = getenv("KSS_CG_COOP_LEVELS");
+        if (ec) coop_levels = atoi(ec);
+        if (!((coop_levels >> l) & 1))
+            cg_level_kernel<0><<<dim3((ncells + 255) / 256, P), 256, 0, st>>>(l, t_sorted, t_inv, cap_t, cnt_t, cap_tpad, cg.geom, cg.hdr,
+                                                                         cg.arena, cg.cursor, cg.ok, refine ? cg.wl : nullptr, cg.wl_cnt,
+                                                                         nullptr, cg.wl2_cnt);
+        else
+            cg_level_coop_kernel<<<dim3((ncells * 8 + 255) / 256, P), 256, 0, st>>>(l, t_sorted, t_inv, cap_t, cnt_t, cap_tpad, cg.geom,
+                                                                               cg.hdr, cg.arena, cg.cursor, cg.ok,
+                                                                               refine ? cg.wl : nullptr, cg.wl_cnt);
         ++n;
     }
     if (refine) {
