@@ -274,12 +274,18 @@ cg_level0_kernel(const float4* __restrict__ t_sorted, const unsigned short* __re
     const float thr2 = thr * thr;
     const float hh = h * 1.002f * 1.0001f;
     const float rr4 = 4.0f * rho * rho;
+    // dominated by competitor c  <=>  (d - cd) - hh * s > 1e-5 * (d + cd + rr4), rearranged so that the per-competitor
+    // part ca[c] = cd (1 + 1e-5) + 1e-5 * rr4 is computed once
+    float ca[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ca[c] = cd[c] * (1.0f + 1e-5f) + 1e-5f * rr4;
     auto keep_test = [&](const float4& q, float d) -> bool {
         if (!(d <= thr2)) return false;
+        const float dl = d * (1.0f - 1e-5f);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const float s = fabsf(q.x - cp[c].x) + fabsf(q.y - cp[c].y) + fabsf(q.z - cp[c].z);
-            if ((d - cd[c]) - hh * s > 1e-5f * (d + cd[c] + rr4)) return false;
+            if ((dl - ca[c]) - hh * s > 0.0f) return false;
         }
         return true;
     };
@@ -387,16 +393,16 @@ __device__ __forceinline__ void cg_build_cell(int tid, int ncells, int level, co
             else m_p = 0;                                                  // empty parent (outside the query ball)
         }
     }
-    auto cand = [&](int j) -> int {
-        return p_inline ? (int)cg_inline_id(ph, j) : (plist ? (int)plist[j] : (int)tinv[j]);
-    };
+    // (a parent with an inline list is never iterated: dense levels copy its header, sparse levels only refine
+    // external lists)
+    auto cand = [&](int j) -> int { return plist ? (int)plist[j] : (int)tinv[j]; };
     const int cell = ix + ng * (iy + ng * iz);
     // A parent list that already fits a header costs a query the same five branch-free evaluations however much a
     // child would shorten it: the children of such a cell just copy its header.  (cand(child) is a subset of
     // cand(parent), so the parent's list is valid everywhere inside it.)
     // (The lane still takes part in the warp-wide allocation scan below, with nothing to allocate.)
     const bool copy = !SPARSE && p_inline;
-    if (copy) m_p = 0;
+    if (p_inline) m_p = 0;
     const float ox = -R + ((float)ix + 0.5f) * h, oy = -R + ((float)iy + 0.5f) * h, oz = -R + ((float)iz + 0.5f) * h;
     const float cx = gm[0] + ox, cy = gm[1] + oy, cz = gm[2] + oz;
     const float rr = ballR + rho;
@@ -435,12 +441,18 @@ __device__ __forceinline__ void cg_build_cell(int tid, int ncells, int level, co
     }
     const float hh = h * 1.002f * 1.0001f;
     const float rr4 = 4.0f * rho * rho;
+    // dominated by competitor c  <=>  (d - cd) - hh * s > 1e-5 * (d + cd + rr4), rearranged so that the per-competitor
+    // part ca[c] = cd (1 + 1e-5) + 1e-5 * rr4 is computed once
+    float ca[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ca[c] = cd[c] * (1.0f + 1e-5f) + 1e-5f * rr4;
     auto keep_test = [&](const float4& q, float d) -> bool {
         if (!(d <= thr2)) return false;
+        const float dl = d * (1.0f - 1e-5f);
 #pragma unroll
-        for (int c = 0; c < CG_NCOMP; ++c) {
+        for (int c = 0; c < 4; ++c) {
             const float s = fabsf(q.x - cp[c].x) + fabsf(q.y - cp[c].y) + fabsf(q.z - cp[c].z);
-            if ((d - cd[c]) - hh * s > 1e-5f * (d + cd[c] + rr4)) return false;
+            if ((dl - ca[c]) - hh * s > 0.0f) return false;
         }
         return true;
     };
@@ -570,9 +582,9 @@ cg_level_coop_kernel(int level, const float4* __restrict__ t_sorted, const unsig
         else if (tag == CG_TAG_EXT) { m_p = (int)cg_ext_count(ph); plist = arena + cg_offset(ph); }
         else if (tag == CG_TAG_HUGE) m_p = n_t;
     }
-    auto cand = [&](int j) -> int {
-        return p_inline ? (int)cg_inline_id(ph, j) : (plist ? (int)plist[j] : (int)tinv[j]);
-    };
+    // (a parent with an inline list is never iterated: dense levels copy its header, sparse levels only refine
+    // external lists)
+    auto cand = [&](int j) -> int { return plist ? (int)plist[j] : (int)tinv[j]; };
     const bool copy = p_inline;                                        // a list that fits a header is not refined (see cg_build_cell)
     if (copy) m_p = 0;
     const float ox = -R + ((float)ix + 0.5f) * h, oy = -R + ((float)iy + 0.5f) * h, oz = -R + ((float)iz + 0.5f) * h;
@@ -613,12 +625,18 @@ cg_level_coop_kernel(int level, const float4* __restrict__ t_sorted, const unsig
     const float thr2 = thr * thr;
     const float hh = h * 1.002f * 1.0001f;
     const float rr4 = 4.0f * rho * rho;
+    // dominated by competitor c  <=>  (d - cd) - hh * s > 1e-5 * (d + cd + rr4), rearranged so that the per-competitor
+    // part ca[c] = cd (1 + 1e-5) + 1e-5 * rr4 is computed once
+    float ca[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ca[c] = cd[c] * (1.0f + 1e-5f) + 1e-5f * rr4;
     auto keep_test = [&](const float4& q, float d) -> bool {
         if (!(d <= thr2)) return false;
+        const float dl = d * (1.0f - 1e-5f);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const float s = fabsf(q.x - cp[c].x) + fabsf(q.y - cp[c].y) + fabsf(q.z - cp[c].z);
-            if ((d - cd[c]) - hh * s > 1e-5f * (d + cd[c] + rr4)) return false;
+            if ((dl - ca[c]) - hh * s > 0.0f) return false;
         }
         return true;
     };
