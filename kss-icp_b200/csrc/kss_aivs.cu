@@ -715,6 +715,7 @@ aivs_small_kernel(const double* __restrict__ pts, const int* __restrict__ cnt, i
             // even phase: the colour's boxes in parallel; odd phase: its misplaced-centre boxes (index multiple of
             // nx * ny, see aivs_fps_kernel) one after the other in ascending index, by group 0
             const bool serial = col & 1;
+            if (ccount[col] == 0) continue;                              // nothing of this kind: skip the barrier too (uniform)
             const int nb_col = serial ? g.nz : ccount[col];
             for (int gi = serial ? (grp == 0 ? 0 : nb_col) : grp; gi < nb_col; gi += serial ? 1 : ngrp) {
                 int b;

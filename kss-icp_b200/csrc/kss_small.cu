@@ -737,7 +737,13 @@ cg_level_kernel(int level, const float4* __restrict__ t_sorted, const unsigned s
 // searching the exact NN of every rotated point (narrowed to float) in the Morton-tiled
 // target.  rbuf[p][orig][h] receives sqrtf(d2) as a float (widened exactly later) (score modes AVE/DIFF) or (double)d2
 // (MAX); the serial sums are taken by sweep_finalize_kernel.
-__global__ void __launch_bounds__(256)
+#ifndef SWEEP_U
+#define SWEEP_U 3
+#endif
+#ifndef SWEEP_MIN_CTAS
+#define SWEEP_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(256, SWEEP_MIN_CTAS)
 sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int cap_s,
              const unsigned short* __restrict__ s_perm,
              const float4* __restrict__ t_sorted, const float* __restrict__ t_box,
@@ -782,7 +788,7 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
         float* ro = rb + (size_t)o * hpad + hbase;
         if (use_cg) {
             // three z-rotations per batch: their grid look-ups overlap (cg_query_batch)
-            constexpr int U = 3;
+            constexpr int U = SWEEP_U;
             for (int k0 = 0; k0 < G; k0 += U) {
                 float qx[U], qy[U], qz[U];
                 unsigned long long key[U];
