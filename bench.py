@@ -211,7 +211,6 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ctx.set_timing(True)
     l0 = ctx.launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
@@ -222,8 +221,19 @@ def main():
     barrier()
     ms_dev = e0.elapsed_time(e1) / args.steps
     launches = ctx.launch_count() - l0
-    stages = {pkg.STAGES[i]: ctx.stage_ms(i)[0] / args.steps for i in range(len(pkg.STAGES))}
+    # per-stage device times: one extra, untimed step on a single lane (in the timed steps the chunks of the batch
+    # run on two internal streams and their stages overlap, so their spans would not add up to the step)
+    prev_lanes = os.environ.get("KSS_LANES")
+    os.environ["KSS_LANES"] = "1"
+    ctx.set_timing(True)
+    step_device()
+    barrier()
+    stages = {pkg.STAGES[i]: ctx.stage_ms(i)[0] for i in range(len(pkg.STAGES))}
     ctx.set_timing(False)
+    if prev_lanes is None:
+        del os.environ["KSS_LANES"]
+    else:
+        os.environ["KSS_LANES"] = prev_lanes
 
     # ---- e2e: host pinned buffers in, host results out, copies inside the timed region
     for _ in range(min(args.warmup, 2)):
@@ -281,7 +291,7 @@ def main():
                 "e2e": {"value": args.pairs / (ms_e2e / 1000.0), "unit": "registrations/s",
                         "h2d_bytes_per_step": h2d * world if world > 1 else h2d,
                         "d2h_bytes_per_step": d2h * world if world > 1 else d2h, "ms_per_step": ms_e2e},
-                "gpu_launches": launches, "clocks": clocks, "stage_ms_per_step_rank0": stages,
+                "gpu_launches": launches, "clocks": clocks, "stage_ms_single_lane_rank0": stages,
                 "roofline": roofline, "cpu_baseline": cpu_baseline}
         line.update(extra)
         r0 = res_np[0]
