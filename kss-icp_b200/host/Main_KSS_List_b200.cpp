@@ -4,7 +4,9 @@
 // an empty translation unit as shipped (its body is inside a comment and its list is empty), so it cannot be
 // "driven unchanged"; this is the equivalent driver.
 //
-// usage: Main_KSS_List_b200 <list.txt> [step=8] [iter=1000]     list.txt: one "<source.ply> <target.ply>" per line
+// usage: Main_KSS_List_b200 <list.txt> [step=8] [iter=1000] [out_dir]
+//   list.txt: one "<source> <target>" per line; .ply (ASCII) or the count-prefixed .xyz/.wlop/.gird text format;
+//   out_dir: write <k>Align.xyz per pair like Main_KSS_List.cpp:138-141
 #include <chrono>
 #include <fstream>
 #include <iostream>
@@ -12,8 +14,11 @@
 
 #include "KSS_ICP.hpp"
 #include "registrationMeasure.hpp"
+#include "xyzIO.hpp"
 
 static std::vector<std::vector<double>> Load_PLY(const std::string& f) {
+	if (!kss_has_suffix(f, ".ply")) return Load_XYZ(f);          // .xyz / .txt / .wlop / .gird
+
 	CPLYLoader l;
 	std::vector<char> p(f.begin(), f.end()); p.push_back(0);
 	l.LoadModel(p.data());
@@ -54,9 +59,16 @@ int main(int argc, char** argv) {
 	b.cnt_S = nS.data(); b.cnt_T = nT.data();
 	b.step = step; b.icp.max_iterations = iter;
 	std::vector<kss_pair_result> res(P);
+	const std::string out_dir = argc > 4 ? argv[4] : "";
+	std::vector<double> aligned(out_dir.empty() ? 0 : (size_t)P * cS * 3);
 	auto t0 = std::chrono::steady_clock::now();
-	if (!kss_host::ok(kss_register_batch(kss_host::ctx(), &b, res.data(), nullptr), "kss_register_batch")) return 1;
+	if (!kss_host::ok(kss_register_batch(kss_host::ctx(), &b, res.data(), out_dir.empty() ? nullptr : aligned.data()), "kss_register_batch")) return 1;
 	const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	for (int p = 0; p < P && !out_dir.empty(); ++p) {                     // Main_KSS_List.cpp:138-141: the aligned source per pair
+		kss_host::Cloud c(S[p].size(), std::vector<double>(3));
+		for (size_t i = 0; i < c.size(); ++i) for (int a = 0; a < 3; ++a) c[i][a] = aligned[((size_t)p * cS + i) * 3 + a];
+		Save_XYZ(c, out_dir + "/" + std::to_string(p) + "Align.xyz");
+	}
 	for (int p = 0; p < P; ++p)
 		std::cout << "pair " << p << " MSE: " << res[p].mse << " RMSE: " << res[p].rmse << " MAE: " << res[p].mae
 		          << " fitness: " << res[p].final_fitness << " hypotheses: " << res[p].n_minima << " winner: " << res[p].winner << "\n";

@@ -65,3 +65,33 @@ def test_batch_driver(ctx, okss, pkg, tmp_path):
     for r, e in zip(rows, exp):
         assert np.allclose([float(r[1]), float(r[2]), float(r[3])], [e["mse"], e["rmse"], e["mae"]], rtol=2e-5)
         assert int(r[5]) == int(e["n_minima"]) and int(r[6]) == int(e["winner"])
+
+
+def test_batch_driver_xyz_formats_and_aligned_output(ctx, okss, pkg, tmp_path):
+    """the count-prefixed text format of the reference (.xyz as written by save_PointCloud, .wlop / .gird as shipped
+    under data/registration): read by the batch driver, aligned clouds written back in the same format"""
+    exe = os.path.join(BIN, "Main_KSS_List_b200")
+    if not os.path.exists(exe):
+        pytest.skip("batch driver not built")
+    p = pkg.synth.modelnet_pair(81, n_full=900)
+    def write(path, pts, count_line=True):
+        with open(path, "w") as f:
+            if count_line:
+                f.write("%d\n" % len(pts))
+            for q in pts:
+                f.write("%.9g %.9g %.9g\n" % (np.float32(q[0]), np.float32(q[1]), np.float32(q[2])))
+            f.write("\n")
+    write(tmp_path / "a.wlop", p["full_s"]); write(tmp_path / "a.gird", p["full_t"])
+    write(tmp_path / "b.xyz", p["full_s"], count_line=False); write(tmp_path / "b.txt", p["full_t"], count_line=False)
+    (tmp_path / "list.txt").write_text("%s %s\n%s %s\n" % (tmp_path / "a.wlop", tmp_path / "a.gird", tmp_path / "b.xyz", tmp_path / "b.txt"))
+    out_dir = tmp_path / "out"; out_dir.mkdir()
+    out = subprocess.run([exe, str(tmp_path / "list.txt"), "8", "1000", str(out_dir)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rows = re.findall(r"pair (\d+) MSE: (\S+) RMSE: (\S+) MAE: (\S+)", out.stdout)
+    assert len(rows) == 2 and rows[0][1:] == rows[1][1:]                 # same clouds through both flavours
+    exp, pa = ctx.register_batch(None, None, p["full_s"][None], p["full_t"][None], want_points=True)
+    assert np.allclose([float(x) for x in rows[0][1:]], [exp[0]["mse"], exp[0]["rmse"], exp[0]["mae"]], rtol=2e-5)
+    txt = (out_dir / "0Align.xyz").read_text().split()
+    assert int(txt[0]) == 900 and len(txt) == 1 + 3 * 900
+    got = np.array([float(x) for x in txt[1:]]).reshape(900, 3)
+    assert np.allclose(got, pa[0], rtol=1e-5, atol=1e-6)                 # default ostream precision: 6 significant digits
