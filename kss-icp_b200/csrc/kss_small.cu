@@ -741,7 +741,7 @@ cg_level_kernel(int level, const float4* __restrict__ t_sorted, const unsigned s
 #define SWEEP_U 3
 #endif
 #ifndef SWEEP_MIN_CTAS
-#define SWEEP_MIN_CTAS 1
+#define SWEEP_MIN_CTAS 4
 #endif
 __global__ void __launch_bounds__(256, SWEEP_MIN_CTAS)
 sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int cap_s,

@@ -55,6 +55,14 @@ for p in range(P):
         ch = a64[np.where(ref, off64 + octv, 0)]
         h = np.where(ref, ch, h)
         tag = (h >> np.uint64(60)).astype(np.int64)
+        ref2 = tag == 15                                                      # second sparse level (128^3)
+        fr2 = fr * 2 - np.floor(fr * 2)
+        oct2 = (fr2[:, 0] >= 0.5) * 1 + (fr2[:, 1] >= 0.5) * 2 + (fr2[:, 2] >= 0.5) * 4
+        off64 = ((h & np.uint64(0xffffffff)).astype(np.int64) << 2) // 4
+        ch = a64[np.where(ref2, off64 + oct2, 0)]
+        h = np.where(ref2, ch, h)
+        tag = (h >> np.uint64(60)).astype(np.int64)
+        ref2q = globals().get("ref2q", 0) + int((ref2 & ok).sum()); globals()["ref2q"] = ref2q
         k = np.where((tag >= 1) & (tag <= 5), tag, np.where(tag == 14, ((h >> np.uint64(32)) & np.uint64(0xfffffff)).astype(np.int64), np.where(tag == 13, 9999, 0)))
         kinds[0] += ((tag >= 1) & (tag <= 5) & ok).sum(); kinds[1] += ((tag == 14) & ok).sum(); kinds[2] += ((tag == 13) & ok).sum()
         kinds[3] += ((tag == 0) | ~ok).sum()
@@ -62,8 +70,8 @@ for p in range(P):
         w.append(np.where(ok, k, -1))
     w = np.concatenate(w)
     allw.append(w); allc.append(np.zeros(1))
-print("queries: inline %.2f%%, external %.2f%%, huge %.3f%%, empty/outside %.3f%%; through a refined cell %.1f%%" % tuple(
-    [100.0 * kinds[i] / totq for i in range(4)] + [100.0 * refq / totq]))
+print("queries: inline %.2f%%, external %.2f%%, huge %.3f%%, empty/outside %.3f%%; through a refined cell %.1f%%, through two %.1f%%" % tuple(
+    [100.0 * kinds[i] / totq for i in range(4)] + [100.0 * refq / totq, 100.0 * globals().get("ref2q", 0) / totq]))
 w = np.concatenate(allw); c = np.concatenate(allc)
 print("queries: outside/empty %.2f%%, mean cnt %.2f, mean padded %.2f" % (100 * (w <= 0).mean(), w[w > 0].mean(), (((w[w > 0] + 3) // 4) * 4).mean()))
 print("query cnt percentiles 50/75/90/99/max:", np.percentile(w[w > 0], [50, 75, 90, 99, 100]))
