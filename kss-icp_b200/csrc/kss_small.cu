@@ -331,6 +331,9 @@ cg_level0_kernel(const float4* __restrict__ t_sorted, const unsigned short* __re
 #ifndef CG_NCOMP
 #define CG_NCOMP 4
 #endif
+#ifndef CG_REFINE_MIN2
+#define CG_REFINE_MIN2 CG_REFINE_MIN       // octants (64^3) with at least this many candidates are cut once more
+#endif
 template <int SPARSE>
 __device__ __forceinline__ void cg_build_cell(int tid, int ncells, int level, const float4* __restrict__ t_sorted,
                                               const unsigned short* __restrict__ t_inv_all, int cap_t,
@@ -504,7 +507,7 @@ __device__ __forceinline__ void cg_build_cell(int tid, int ncells, int level, co
             const cg_hdr_t mark = ((cg_hdr_t)CG_TAG_REFINED << 60) | (cg_hdr_t)(blk >> 2);
             if (SPARSE == 2) *reinterpret_cast<cg_hdr_t*>(arena + parent) = mark; else hdr[parent] = mark;
         }
-        if (SPARSE == 1 && wl2_all != nullptr && !huge && k >= CG_REFINE_MIN) {
+        if (SPARSE == 1 && wl2_all != nullptr && !huge && k >= CG_REFINE_MIN2) {
             const unsigned slot = atomicAdd(&wl2_cnt[p], 1u);
             if (slot < (unsigned)CG_WL2_CAP)
                 wl2_all[(size_t)p * CG_WL2_CAP + slot] = make_uint4(blk + 4u * (unsigned)child, (unsigned)ix | ((unsigned)iy << 16), (unsigned)iz, 0u);
