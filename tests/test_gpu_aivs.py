@@ -210,3 +210,19 @@ def test_aivs_golden_fixtures_from_reference_data(ctx, model):
     assert np.array_equal(r["T"].reshape(4, 4), g[model + "_raw_T"])
     for k in ("final_fitness", "mse", "rmse", "mae"):
         assert float(r[k]) == float(g[model + "_raw_" + k]), k
+
+
+def test_register_raw_large_clouds(ctx, okss, pkg):
+    """raw clouds beyond the shared-memory path (20k points, pNumber capped at 2000): the any-size AIVS kernels, then
+    the same registration; final metrics through the large-cloud NN"""
+    n = 20000
+    pr = pkg.synth.modelnet_pair(5, n_full=n)
+    fs, ft = pr["full_s"], pr["full_t"]
+    raw = ctx.register_batch(None, None, fs[None], ft[None])[0]
+    ss = okss.aivs_simplify(fs, 2000)[0]; st = okss.aivs_simplify(ft, 2000)[0]
+    one = ctx.register(ss, st, fs, ft)
+    for k in ("final_fitness", "judge_fitness", "winner", "n_minima", "total_icp_iters"):
+        assert raw[k] == one[k], k
+    assert np.array_equal(raw["T"], one["T"])
+    for k in ("mse", "rmse", "mae"):
+        assert abs(raw[k] - one[k]) <= 1e-12 * max(1.0, abs(one[k])), k
