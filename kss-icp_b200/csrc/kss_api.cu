@@ -190,9 +190,9 @@ int cg_buffers(kss_ctx* ctx, int P, CgBuffers* cg) {
     BUF("cg_cursor", (size_t)P, &cg->cursor);
     BUF("cg_ok", (size_t)P, &cg->ok);
     BUF("cg_wl", (size_t)P * cg_worklist_entries_per_pair(), &cg->wl);
-    BUF("cg_wl_cnt", (size_t)P, &cg->wl_cnt);
+    BUF("cg_wl_cnt", (size_t)P * 2, &cg->wl_cnt);
     BUF("cg_wl2", (size_t)P * cg_worklist2_entries_per_pair(), &cg->wl2);
-    BUF("cg_wl2_cnt", (size_t)P, &cg->wl2_cnt);
+    BUF("cg_wl2_cnt", (size_t)P * 2, &cg->wl2_cnt);
     return KSS_OK;
 }
 

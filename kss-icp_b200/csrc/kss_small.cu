@@ -211,8 +211,8 @@ cg_geom_kernel(int mode, const double* __restrict__ a, const int* __restrict__ c
         g[5] = g[6] = g[7] = 0.0f;
         cursor[p] = 0u;
         ok[p] = 1;
-        wl_cnt[p] = 0u;
-        wl2_cnt[p] = 0u;
+        wl_cnt[2 * p] = wl_cnt[2 * p + 1] = 0u;
+        wl2_cnt[2 * p] = wl2_cnt[2 * p + 1] = 0u;
     }
 }
 
@@ -328,6 +328,24 @@ cg_level0_kernel(const float4* __restrict__ t_sorted, const unsigned short* __re
 // longer ones into the pair's arena (one atomicAdd per warp on its cursor).
 // SPARSE 1: one thread per octant of every worklisted 32^3 cell (64^3 resolution); SPARSE 2: the same once more for the
 // worklisted octants (128^3 resolution), whose headers live in the arena.
+// Two-ended work lists: cells with short lists are pushed from the front, cells with long lists from the back, so that
+// the warps of the refinement kernels hold parents of similar list length (the 8 siblings of a parent loop over its
+// list; a warp holds 4 parents).  cnt[2p] = front count, cnt[2p + 1] = back count.
+constexpr int CG_WL_SPLIT = 9;                // lists with >= this many entries go to the back
+__device__ __forceinline__ int cg_wl_push(unsigned* cnt2, int cap, int k) {
+    const bool back = k >= CG_WL_SPLIT;
+    const unsigned slot = atomicAdd(&cnt2[back ? 1 : 0], 1u);
+    const unsigned lim = back ? (unsigned)(cap * 3 / 8) : (unsigned)(cap * 5 / 8);
+    if (slot >= lim) return -1;
+    return back ? cap - 1 - (int)slot : (int)slot;
+}
+__device__ __forceinline__ int cg_wl_count(const unsigned* cnt2, int cap) {
+    return (int)min(cnt2[0], (unsigned)(cap * 5 / 8)) + (int)min(cnt2[1], (unsigned)(cap * 3 / 8));
+}
+__device__ __forceinline__ int cg_wl_index(const unsigned* cnt2, int cap, int t) {     // t-th item -> position in the array
+    const int nf = (int)min(cnt2[0], (unsigned)(cap * 5 / 8));
+    return t < nf ? t : cap - 1 - (t - nf);
+}
 #ifndef CG_NCOMP
 #define CG_NCOMP 4
 #endif
@@ -370,12 +388,12 @@ __device__ __forceinline__ void cg_build_cell(int tid, int ncells, int level, co
     if (live) {
         bool from_parent = true;
         if (SPARSE == 2) {
-            const uint4 e = wl2_all[(size_t)p * CG_WL2_CAP + parent];        // an octant of a refined cell
+            const uint4 e = wl2_all[(size_t)p * CG_WL2_CAP + cg_wl_index(wl2_cnt + 2 * p, CG_WL2_CAP, parent)];   // an octant of a refined cell
             parent = (int)e.x;                                               // arena offset of its header
             ix = 2 * (int)(e.y & 0xffffu) + (child & 1); iy = 2 * (int)(e.y >> 16) + ((child >> 1) & 1); iz = 2 * (int)e.z + (child >> 2);
             ph = *reinterpret_cast<const cg_hdr_t*>(arena + parent);
         } else if (SPARSE == 1) {
-            parent = wl_all[(size_t)p * CG_WL_CAP + parent];                 // a cell of the finest dense level
+            parent = wl_all[(size_t)p * CG_WL_CAP + cg_wl_index(wl_cnt + 2 * p, CG_WL_CAP, parent)];   // a cell of the finest dense level
             const int px = parent & (CG_NG - 1), py = (parent / CG_NG) & (CG_NG - 1), pz = parent / (CG_NG * CG_NG);
             ix = 2 * px + (child & 1); iy = 2 * py + ((child >> 1) & 1); iz = 2 * pz + (child >> 2);
             ph = hdr[parent];
@@ -508,15 +526,15 @@ __device__ __forceinline__ void cg_build_cell(int tid, int ncells, int level, co
             if (SPARSE == 2) *reinterpret_cast<cg_hdr_t*>(arena + parent) = mark; else hdr[parent] = mark;
         }
         if (SPARSE == 1 && wl2_all != nullptr && !huge && k >= CG_REFINE_MIN2) {
-            const unsigned slot = atomicAdd(&wl2_cnt[p], 1u);
-            if (slot < (unsigned)CG_WL2_CAP)
+            const int slot = cg_wl_push(wl2_cnt + 2 * p, CG_WL2_CAP, k);
+            if (slot >= 0)
                 wl2_all[(size_t)p * CG_WL2_CAP + slot] = make_uint4(blk + 4u * (unsigned)child, (unsigned)ix | ((unsigned)iy << 16), (unsigned)iz, 0u);
         }
     } else {
         hdr[cell] = me;
         if (level == CG_LEVELS - 1 && wl_all != nullptr && !huge && k >= CG_REFINE_MIN) {
-            const unsigned slot = atomicAdd(&wl_cnt[p], 1u);
-            if (slot < (unsigned)CG_WL_CAP) wl_all[(size_t)p * CG_WL_CAP + slot] = (unsigned short)cell;
+            const int slot = cg_wl_push(wl_cnt + 2 * p, CG_WL_CAP, k);
+            if (slot >= 0) wl_all[(size_t)p * CG_WL_CAP + slot] = (unsigned short)cell;
         }
     }
     if (!ext) return;
@@ -710,8 +728,8 @@ cg_level_coop_kernel(int level, const float4* __restrict__ t_sorted, const unsig
     if (copy) me = ph;
     hdr[cell] = me;
     if (level == CG_LEVELS - 1 && wl_all != nullptr && !huge && !copy && k >= CG_REFINE_MIN) {
-        const unsigned slot = atomicAdd(&wl_cnt[p], 1u);
-        if (slot < (unsigned)CG_WL_CAP) wl_all[(size_t)p * CG_WL_CAP + slot] = (unsigned short)cell;
+        const int slot = cg_wl_push(wl_cnt + 2 * p, CG_WL_CAP, k);
+        if (slot >= 0) wl_all[(size_t)p * CG_WL_CAP + slot] = (unsigned short)cell;
     }
 }
 
@@ -727,8 +745,8 @@ cg_level_kernel(int level, const float4* __restrict__ t_sorted, const unsigned s
                 uint4* __restrict__ wl2_all, unsigned* __restrict__ wl2_cnt) {
     const int p = blockIdx.y;
     const int ng = cg_ng(level);
-    const int ncells = SPARSE == 2 ? 8 * (int)min(wl2_cnt[p], (unsigned)CG_WL2_CAP)
-                     : (SPARSE == 1 ? 8 * (int)min(wl_cnt[p], (unsigned)CG_WL_CAP) : ng * ng * ng);
+    const int ncells = SPARSE == 2 ? 8 * cg_wl_count(wl2_cnt + 2 * p, CG_WL2_CAP)
+                     : (SPARSE == 1 ? 8 * cg_wl_count(wl_cnt + 2 * p, CG_WL_CAP) : ng * ng * ng);
     const int lane = threadIdx.x & 31;
     for (int tid = blockIdx.x * blockDim.x + threadIdx.x; tid - lane < ncells; tid += gridDim.x * blockDim.x)
         cg_build_cell<SPARSE>(tid, ncells, level, t_sorted, t_inv_all, cap_t, cnt_t, cap_tpad, geom, hdr_all, arena_all, cursor, ok,
