@@ -88,9 +88,11 @@ __device__ __forceinline__ unsigned long long cg_scan(const CgView& g, const flo
     unsigned bi = 0u;
     if (tag >= 1u && tag <= (unsigned)CG_INLINE_MAX) {
         // branch-free: slots past the count re-evaluate entry 0 (same distance, never strictly smaller)
+        const unsigned id0 = cg_inline_id(h, 0);
+        cg_eval<IDX>(tgt, id0, qx, qy, qz, best, bi);
 #pragma unroll
-        for (int k = 0; k < CG_INLINE_MAX; ++k)
-            cg_eval<IDX>(tgt, cg_inline_id(h, (unsigned)k < tag ? k : 0), qx, qy, qz, best, bi);
+        for (int k = 1; k < CG_INLINE_MAX; ++k)                          // constant shifts, one select per slot
+            cg_eval<IDX>(tgt, (unsigned)k < tag ? cg_inline_id(h, k) : id0, qx, qy, qz, best, bi);
     } else if (tag == CG_TAG_EXT) {
         const uint2* lp = reinterpret_cast<const uint2*>(g.list + cg_offset(h));
         const unsigned n4 = (cg_ext_count(h) + 3u) >> 2;

@@ -255,3 +255,18 @@ def test_icp_correspondence_ties_through_the_candidate_grid(ctx, okss):
     assert r["iters"] == o["iters"] and k >= 1
     assert np.array_equal(r["trace"]["corr_idx"][:k], o["trace"]["corr_idx"][:k])
     assert np.array_equal(r["T"], o["T"]) and r["fitness"] == o["fitness"]
+
+
+@pytest.mark.parametrize("env", [{"KSS_NO_CG": "1"}, {"KSS_CG_NO_REFINE": "1"}, {"KSS_CG_COOP_LEVELS": "0"},
+                                 {"KSS_CG_COOP_LEVELS": "14"}, {"KSS_LANES": "1"}, {"KSS_CHUNKS": "5"}])
+def test_engine_switches_do_not_change_results(ctx, pkg, monkeypatch, env):
+    """three NN engines, one result: the tile search, the candidate grid without / with its sparse levels, either
+    build kernel for the dense levels, and any split of the batch over lanes and chunks give identical registrations"""
+    P = 10
+    b, _ = pkg.synth.modelnet_batch(P, n_full=700, first=200)
+    ref = ctx.register_batch(None, None, b["full_s"], b["full_t"])
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = ctx.register_batch(None, None, b["full_s"], b["full_t"])
+    for name in ref.dtype.names:
+        assert np.array_equal(ref[name], got[name]), name
