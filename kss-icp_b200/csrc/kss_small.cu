@@ -969,6 +969,8 @@ sweep_finalize_kernel(const float* __restrict__ rbuf, const int* __restrict__ cn
 #else
 #define ICP_TICK(ph) do { } while (0)
 #endif
+// TRACE: the per-iteration records of kss_icp's trace argument (tests); compiled out of the batched launches
+template <bool TRACE>
 __global__ void __launch_bounds__(256, ICP_MIN_CTAS)
 icp_small_kernel(IcpArgs a) {
 #ifdef KSS_ICP_PHASE_TIMING
@@ -1063,9 +1065,9 @@ icp_small_kernel(IcpArgs a) {
                 d2s[o] = d2;
                 mpos[o] = keep ? tinv[orig] : (unsigned short)0xffff;
                 my_kept += keep ? 1 : 0;
-                if (a.trace_idx && iters < a.trace_cap)
+                if (TRACE && a.trace_idx && iters < a.trace_cap)
                     a.trace_idx[((size_t)run * a.trace_cap + iters) * a.cap_s + o] = keep ? (int)orig : -1;
-                if (a.trace_src && iters < a.trace_cap) {
+                if (TRACE && a.trace_src && iters < a.trace_cap) {
                     float* ts = a.trace_src + (((size_t)run * a.trace_cap + iters) * a.cap_s + o) * 3;
                     ts[0] = x; ts[1] = y; ts[2] = z;
                 }
@@ -1213,9 +1215,9 @@ icp_small_kernel(IcpArgs a) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) { Tk[i] = T[i]; fin[i] = F[i]; }
             const double mse = __ddiv_rn(redd, (double)cnt);
-            if (a.trace_T && iters < a.trace_cap)
+            if (TRACE && a.trace_T && iters < a.trace_cap)
                 for (int i = 0; i < 16; ++i) a.trace_T[((size_t)run * a.trace_cap + iters) * 16 + i] = T[i];
-            if (a.trace_mse && iters < a.trace_cap) a.trace_mse[(size_t)run * a.trace_cap + iters] = mse;
+            if (TRACE && a.trace_mse && iters < a.trace_cap) a.trace_mse[(size_t)run * a.trace_cap + iters] = mse;
             const int it = iters + 1;
             int dn = 0;
             if (it >= a.max_iter) dn = 1;                                            // A.6 (1)
@@ -1531,9 +1533,15 @@ size_t icp_smem_bytes(int cap_s, int cap_t, int cap_tpad) {
 }
 cudaError_t launch_icp(cudaStream_t st, int P, int slots, const IcpArgs& a) {
     const size_t smem = icp_smem_bytes(a.cap_s, a.cap_t, a.cap_tpad);
-    static size_t set = 0;
-    if (smem > set) { cudaFuncSetAttribute(icp_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
-    icp_small_kernel<<<dim3(slots, P), 256, smem, st>>>(a);
+    static size_t set0 = 0, set1 = 0;
+    const bool trace = a.trace_cap > 0 && (a.trace_idx || a.trace_T || a.trace_mse || a.trace_src);
+    if (trace) {
+        if (smem > set1) { cudaFuncSetAttribute(icp_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set1 = smem; }
+        icp_small_kernel<true><<<dim3(slots, P), 256, smem, st>>>(a);
+    } else {
+        if (smem > set0) { cudaFuncSetAttribute(icp_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set0 = smem; }
+        icp_small_kernel<false><<<dim3(slots, P), 256, smem, st>>>(a);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_select(cudaStream_t st, int P, int runs_per_pair, int hpad, int G, double judge_thr,
