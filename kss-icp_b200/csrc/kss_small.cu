@@ -252,11 +252,12 @@ cg_level0_kernel(const float4* __restrict__ t_sorted, const unsigned short* __re
         const int id = (int)tinv[j];
         const float4 q = __ldg(tgt + id);
         const float d = d2_rn(cx, cy, cz, q.x, q.y, q.z);
-        if (d < e3) {
-            if (d < e0) { e3 = e2; i3 = i2; e2 = e1; i2 = i1; e1 = e0; i1 = i0; e0 = d; i0 = id; }
-            else if (d < e1) { e3 = e2; i3 = i2; e2 = e1; i2 = i1; e1 = d; i1 = id; }
-            else if (d < e2) { e3 = e2; i3 = i2; e2 = d; i2 = id; }
-            else { e3 = d; i3 = id; }
+        {   // sorted insert into (e0 <= e1 <= e2 <= e3) with selects only
+            const bool p0 = d < e0, p1 = d < e1, p2 = d < e2, p3 = d < e3;
+            e3 = p2 ? e2 : (p3 ? d : e3); i3 = p2 ? i2 : (p3 ? id : i3);
+            e2 = p1 ? e1 : (p2 ? d : e2); i2 = p1 ? i1 : (p2 ? id : i2);
+            e1 = p0 ? e0 : (p1 ? d : e1); i1 = p0 ? i0 : (p1 ? id : i1);
+            e0 = p0 ? d : e0; i0 = p0 ? id : i0;
         }
     }
     float4 cp[4]; float cd[4];
@@ -438,11 +439,12 @@ __device__ __forceinline__ void cg_build_cell(int tid, int ncells, int level, co
         const int id = cand(j);
         const float4 q = __ldg(tgt + id);
         const float d = d2_rn(cx, cy, cz, q.x, q.y, q.z);
-        if (d < e3) {
-            if (d < e0) { e3 = e2; i3 = i2; e2 = e1; i2 = i1; e1 = e0; i1 = i0; e0 = d; i0 = id; }
-            else if (d < e1) { e3 = e2; i3 = i2; e2 = e1; i2 = i1; e1 = d; i1 = id; }
-            else if (d < e2) { e3 = e2; i3 = i2; e2 = d; i2 = id; }
-            else { e3 = d; i3 = id; }
+        {   // sorted insert into (e0 <= e1 <= e2 <= e3) with selects only
+            const bool p0 = d < e0, p1 = d < e1, p2 = d < e2, p3 = d < e3;
+            e3 = p2 ? e2 : (p3 ? d : e3); i3 = p2 ? i2 : (p3 ? id : i3);
+            e2 = p1 ? e1 : (p2 ? d : e2); i2 = p1 ? i1 : (p2 ? id : i2);
+            e1 = p0 ? e0 : (p1 ? d : e1); i1 = p0 ? i0 : (p1 ? id : i1);
+            e0 = p0 ? d : e0; i0 = p0 ? id : i0;
         }
     }
     const float mn = e0;
@@ -623,11 +625,12 @@ cg_level_coop_kernel(int level, const float4* __restrict__ t_sorted, const unsig
         const int id = cand(j);
         const float4 q = __ldg(tgt + id);
         const float d = d2_rn(cx, cy, cz, q.x, q.y, q.z);
-        if (d < e3) {
-            if (d < e0) { e3 = e2; i3 = i2; e2 = e1; i2 = i1; e1 = e0; i1 = i0; e0 = d; i0 = id; }
-            else if (d < e1) { e3 = e2; i3 = i2; e2 = e1; i2 = i1; e1 = d; i1 = id; }
-            else if (d < e2) { e3 = e2; i3 = i2; e2 = d; i2 = id; }
-            else { e3 = d; i3 = id; }
+        {   // sorted insert into (e0 <= e1 <= e2 <= e3) with selects only
+            const bool p0 = d < e0, p1 = d < e1, p2 = d < e2, p3 = d < e3;
+            e3 = p2 ? e2 : (p3 ? d : e3); i3 = p2 ? i2 : (p3 ? id : i3);
+            e2 = p1 ? e1 : (p2 ? d : e2); i2 = p1 ? i1 : (p2 ? id : i2);
+            e1 = p0 ? e0 : (p1 ? d : e1); i1 = p0 ? i0 : (p1 ? id : i1);
+            e0 = p0 ? d : e0; i0 = p0 ? id : i0;
         }
     }
     float4 cp[4]; float cd[4];
