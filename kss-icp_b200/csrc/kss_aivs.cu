@@ -865,10 +865,13 @@ aivs_small_kernel(const double* __restrict__ pts, const int* __restrict__ cnt, i
                     for (int j = jlo; j < jhi; ++j) {
                         const int o = sample[j];
                         const float d = d2_rn(x, y, z, xf[o], yf[o], zf[o]);
-                        if (d < e2) {
-                            if (d < e0) { e2 = e1; e1 = e0; j1 = j0; e0 = d; j0 = j; }
-                            else if (d < e1) { e2 = e1; e1 = d; j1 = j; }
-                            else e2 = d;
+                        {   // sorted insert with selects only (branches here diverge on almost every candidate)
+                            const bool p0 = d < e0, p1 = d < e1, p2 = d < e2;
+                            e2 = p1 ? e1 : (p2 ? d : e2);
+                            j1 = p0 ? j0 : (p1 ? j : j1);
+                            e1 = p0 ? e0 : (p1 ? d : e1);
+                            j0 = p0 ? j : j0;
+                            e0 = p0 ? d : e0;
                         }
                     }
                 }
