@@ -95,3 +95,21 @@ def test_batch_driver_xyz_formats_and_aligned_output(ctx, okss, pkg, tmp_path):
     assert int(txt[0]) == 900 and len(txt) == 1 + 3 * 900
     got = np.array([float(x) for x in txt[1:]]).reshape(900, 3)
     assert np.allclose(got, pa[0], rtol=1e-5, atol=1e-6)                 # default ostream precision: 6 significant digits
+
+
+def test_released_command_line(ctx, okss, pkg, tmp_path):
+    """EXE/Readme.txt: `KSS-ICP.exe PointSource.ply PointTarget.ply`, result written as .xyz"""
+    exe = os.path.join(BIN, "KSS_ICP_cli")
+    if not os.path.exists(exe):
+        pytest.skip("KSS_ICP_cli not built")
+    p = pkg.synth.modelnet_pair(91, n_full=800)
+    _write_ply(tmp_path / "s.ply", p["full_s"]); _write_ply(tmp_path / "t.ply", p["full_t"])
+    out = subprocess.run([exe, str(tmp_path / "s.ply"), str(tmp_path / "t.ply"), str(tmp_path / "r.xyz")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    m = re.search(r"Registration Measure:MSE: (\S+) RMSE: (\S+) MAE: (\S+)", out.stdout)
+    assert m, out.stdout[-2000:]
+    exp = _expected(ctx, okss, p["full_s"], p["full_t"])
+    assert np.allclose([float(x) for x in m.groups()], [exp["mse"], exp["rmse"], exp["mae"]], rtol=2e-5)
+    xyz = (tmp_path / "r.xyz").read_text().split()
+    assert int(xyz[0]) == 800 and len(xyz) == 1 + 3 * 800
