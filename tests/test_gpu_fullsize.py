@@ -45,17 +45,17 @@ def test_c4_one_million_points_round_trip(ctx):
     rng = np.random.default_rng(7)
     u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
     t = (u * (1.0 + 0.15 * np.sin(4 * u[:, :1]) * np.cos(3 * u[:, 1:2]))).astype(np.float32).astype(np.float64)
-    a = 0.01
+    a = 0.001                                  # motion of ~0.3 point spacings (spacing ~ 3.5e-3): most points match at once
     R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
-    s = (t @ R.T + np.array([0.002, -0.001, 0.0015])).astype(np.float32).astype(np.float64)
+    s = (t @ R.T + np.array([2e-4, -1e-4, 1.5e-4])).astype(np.float32).astype(np.float64)
     ctx.icp_large_begin(s, t)
     ctx.icp_large_iterate(40)
     r = ctx.icp_large_end()
     assert r["converged"] == 1 and r["iters"] <= 40
-    assert r["fitness"] < 1e-9
+    assert r["fitness"] < 1e-10, r
     assert _rot_angle(np.asarray(r["T"], np.float64).reshape(4, 4)[:3, :3], R.T) < 1e-5
     moved = ctx.apply_transform(np.asarray(r["T"], np.float32).reshape(4, 4), s)
     sel = rng.choice(n, 200000, replace=False)
     idx, d2 = ctx.nn_search(moved[sel], t)
     assert (idx == sel).mean() > 0.999                                       # exact duplicates aside
-    assert float(d2.max()) < 1e-8
+    assert float(np.median(d2)) < 1e-12 and float(d2.max()) < 1e-8
