@@ -741,8 +741,11 @@ cg_level_coop_kernel(int level, const float4* __restrict__ t_sorted, const unsig
 
 // dense levels: one pass over ng^3 cells (the grid covers them exactly); sparse levels: a fixed, small grid per pair
 // loops over the worklist (its length is only known on the device)
+#ifndef CG_MIN_CTAS
+#define CG_MIN_CTAS 1
+#endif
 template <int SPARSE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, CG_MIN_CTAS)
 cg_level_kernel(int level, const float4* __restrict__ t_sorted, const unsigned short* __restrict__ t_inv_all, int cap_t,
                 const int* __restrict__ cnt_t, int cap_tpad,
                 const float* __restrict__ geom, cg_hdr_t* __restrict__ hdr_all,
