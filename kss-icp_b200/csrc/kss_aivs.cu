@@ -656,18 +656,31 @@ aivs_small_kernel(const double* __restrict__ pts, const int* __restrict__ cnt, i
     const int nbox = g.nbox;
     int NP = 1; while (NP < n) NP <<= 1;
 
-    // ---- BallRegion_BoxInput: membership = sort of (box, index) keys; box starts = scan of the counts
-    for (int i = tid; i < NP; i += AS_THREADS) {
-        unsigned key = 0xffffffffu;
-        if (i < n) {
-            int b = aivs_box_of(g, P + 3 * (size_t)i);
-            if (b < 0 || b >= nbox) b = nbox; else atomicAdd(&start[b], 1);
-            key = ((unsigned)b << 11) | (unsigned)i;
-        }
-        mkey[i] = key;
+    // ---- BallRegion_BoxInput: counting sort by box (counts -> scan -> scatter), then every box's short list is put
+    //      into ascending index order (the order push_back gives) by one thread; mkey[pos] = point index
+    for (int i = tid; i < n; i += AS_THREADS) {
+        int b = aivs_box_of(g, P + 3 * (size_t)i);
+        if (b < 0 || b >= nbox) b = nbox; else atomicAdd(&start[b], 1);
+        sel[i] = (unsigned short)b;                               // sel is free until the sampling starts
     }
-    as_bitonic(mkey, NP);
+    __syncthreads();
     as_block_excl_scan(start, nbox + 1, wsum);
+    for (int i = tid; i < n; i += AS_THREADS) {
+        const int b = sel[i];
+        if (b < nbox) mkey[start[b] + atomicAdd(&selc[b], 1)] = (unsigned)i;      // selc: zeroed above, zeroed again below
+    }
+    __syncthreads();
+    for (int b = 1 + tid; b < nbox; b += AS_THREADS) {
+        const int s0 = start[b], m = start[b + 1] - s0;
+        selc[b] = 0;
+        for (int i = 1; i < m; ++i) {                              // insertion sort (lists hold a few points)
+            const unsigned v = mkey[s0 + i];
+            int j = i - 1;
+            while (j >= 0 && mkey[s0 + j] > v) { mkey[s0 + j + 1] = mkey[s0 + j]; --j; }
+            mkey[s0 + j + 1] = v;
+        }
+    }
+    __syncthreads();
 
     // ---- per box: centre-nearest member, quota, colour census
     for (int b = 1 + tid; b < nbox; b += AS_THREADS) {
