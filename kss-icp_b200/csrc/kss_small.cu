@@ -742,7 +742,7 @@ cg_level_coop_kernel(int level, const float4* __restrict__ t_sorted, const unsig
 // dense levels: one pass over ng^3 cells (the grid covers them exactly); sparse levels: a fixed, small grid per pair
 // loops over the worklist (its length is only known on the device)
 #ifndef CG_MIN_CTAS
-#define CG_MIN_CTAS 1
+#define CG_MIN_CTAS 4
 #endif
 template <int SPARSE>
 __global__ void __launch_bounds__(256, CG_MIN_CTAS)
