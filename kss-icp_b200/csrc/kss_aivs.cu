@@ -489,7 +489,7 @@ aivs_cut_kernel(const double* __restrict__ pts, int cap, AivsGrid* __restrict__ 
 
 // ================================================================ clouds of at most 2048 points: one CTA per cloud
 // The whole simplification in one launch, everything in shared memory: float copies of the points, the box
-// membership as one bitonic sort of (box << 11 | index) keys, farthest point sampling with GL lanes per box (same
+// membership as a counting sort by box followed by per-box insertion sorts (ascending index), farthest point sampling with GL lanes per box (same
 // colour boxes in parallel, a barrier between colours), the K = 3 lists and the sorted greedy trim.  Same arithmetic
 // and the same selection rules as the general kernels above (the min-distance array is kept in float: every value
 // is a float square root or 9999, so comparisons are unchanged).
