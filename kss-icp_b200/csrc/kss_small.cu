@@ -418,7 +418,8 @@ __device__ __forceinline__ void cg_build_cell(int tid, int ncells, int level, co
     }
     // (a parent with an inline list is never iterated: dense levels copy its header, sparse levels only refine
     // external lists)
-    auto cand = [&](int j) -> int { return plist ? (int)plist[j] : (int)tinv[j]; };
+    const unsigned short* __restrict__ csrc = plist ? plist : tinv;      // level 0 / over-long parent: all targets, original order
+    auto cand = [&](int j) -> int { return (int)csrc[j]; };
     const int cell = ix + ng * (iy + ng * iz);
     // A parent list that already fits a header costs a query the same five branch-free evaluations however much a
     // child would shorten it: the children of such a cell just copy its header.  (cand(child) is a subset of
@@ -609,7 +610,8 @@ cg_level_coop_kernel(int level, const float4* __restrict__ t_sorted, const unsig
     }
     // (a parent with an inline list is never iterated: dense levels copy its header, sparse levels only refine
     // external lists)
-    auto cand = [&](int j) -> int { return plist ? (int)plist[j] : (int)tinv[j]; };
+    const unsigned short* __restrict__ csrc = plist ? plist : tinv;      // level 0 / over-long parent: all targets, original order
+    auto cand = [&](int j) -> int { return (int)csrc[j]; };
     const bool copy = p_inline;                                        // a list that fits a header is not refined (see cg_build_cell)
     if (copy) m_p = 0;
     const float ox = -R + ((float)ix + 0.5f) * h, oy = -R + ((float)iy + 0.5f) * h, oz = -R + ((float)iz + 0.5f) * h;
