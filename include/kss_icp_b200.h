@@ -76,7 +76,11 @@ typedef struct kss_pair_result {
     int    used_h;                /* flattened index of the angles finally applied */
     int    use_list;              /* 1: used angles are index*6.3/step, 0: accumulated loop values */
     int    judge_iters, final_iters, total_icp_iters, n_icp_runs;
-    int    overflow;              /* internal: hypothesis slots were exhausted and the pair was re-run */
+    int    overflow;              /* informational: the pair had more local minima than hypothesis slots, so some
+                                     slots ran several hypotheses one after the other (same results either way) */
+    int    final_converged;       /* icp.hasConverged() of the final run (KSS_ICP.hpp:217): 0 iff it stopped with
+                                     fewer than 3 correspondences */
+    int    reserved_[2];
 } kss_pair_result;
 
 /* batch of registrations: arrays are [n_pairs][cap][3] doubles, counts optional (NULL = cap) */
@@ -104,6 +108,10 @@ void kss_icp_params_default(kss_icp_params* p);
 void kss_batch_default(kss_batch* b);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 long long kss_ctx_launch_count(kss_ctx* ctx);
+/* hypothesis ICP runs per pair that get their own CTA in the batched launch (default 32, 1..729); pairs with more
+ * local minima (KSS_ICP.hpp:102-118) are handled inside the same launch: a slot then runs several hypotheses in
+ * turn.  Results do not depend on the value. */
+int kss_ctx_set_hyp_slots(kss_ctx* ctx, int slots);
 
 /* per-stage device timing of the batched pipeline: CUDA events recorded on ctx's stream around
  * each stage (bench.py derives the per-kernel roofline from these; off by default) */

@@ -42,7 +42,7 @@ class PairResult(C.Structure):
                 ("G", C.c_int), ("best_h", C.c_int), ("n_minima", C.c_int), ("branch_multi", C.c_int),
                 ("winner", C.c_int), ("used_h", C.c_int), ("use_list", C.c_int), ("judge_iters", C.c_int),
                 ("final_iters", C.c_int), ("total_icp_iters", C.c_int), ("n_icp_runs", C.c_int),
-                ("overflow", C.c_int)]
+                ("overflow", C.c_int), ("final_converged", C.c_int), ("reserved_", C.c_int * 2)]
 
 
 class Batch(C.Structure):
@@ -56,7 +56,8 @@ RESULT_DTYPE = np.dtype([("align", "f8", 8), ("judge_fitness", "f8"), ("final_fi
                          ("rmse", "f8"), ("mae", "f8"), ("T", "f4", 16), ("G", "i4"), ("best_h", "i4"),
                          ("n_minima", "i4"), ("branch_multi", "i4"), ("winner", "i4"), ("used_h", "i4"),
                          ("use_list", "i4"), ("judge_iters", "i4"), ("final_iters", "i4"),
-                         ("total_icp_iters", "i4"), ("n_icp_runs", "i4"), ("overflow", "i4")], align=True)
+                         ("total_icp_iters", "i4"), ("n_icp_runs", "i4"), ("overflow", "i4"),
+                         ("final_converged", "i4"), ("reserved_", "i4", 2)], align=True)
 assert RESULT_DTYPE.itemsize == C.sizeof(PairResult), (RESULT_DTYPE.itemsize, C.sizeof(PairResult))
 
 _lib = None
@@ -118,6 +119,9 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.kss_ctx_launch_count(self.h))
+
+    def set_hyp_slots(self, slots):
+        self._ck(self.lib.kss_ctx_set_hyp_slots(self.h, C.c_int(int(slots))))
 
     def set_timing(self, enable=True):
         self._ck(self.lib.kss_ctx_set_timing(self.h, C.c_int(1 if enable else 0)))

@@ -1023,11 +1023,7 @@ int aivs_simplify_device(cudaStream_t st, long long* launches, int P, const doub
     aivs_k3_kernel<<<dim3((smax + 255) / 256, P), 256, 0, st>>>(d_pts, cap, grids, bcap, sel_start, sample, key1, dis2);
     int np2 = 1; while (np2 < smax) np2 <<= 1;
     const size_t smem = (size_t)np2 * (8 + 4 + 1);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        if (cudaFuncSetAttribute(aivs_cut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return KSS_ERR_CUDA;
-        smem_set = smem;
-    }
+    if (cudaFuncSetAttribute(aivs_cut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return KSS_ERR_CUDA;
     aivs_cut_kernel<<<P, 512, smem, st>>>(d_pts, cap, grids, bcap, sel_start, sample, key1, dis2, np2, d_out, out_cap, d_out_cnt,
                                           d_out_idx, d_bad);
     *launches += 25;

@@ -32,7 +32,7 @@ struct kss_ctx {
     struct Buf { void* p = nullptr; size_t cap = 0; };
     std::map<std::string, Buf> bufs;
     size_t ws_budget = (size_t)48 << 30;
-    int slots_override = 0;
+    int hyp_slots = 32;               // hypothesis CTAs per pair in the batched ICP launch (kss_ctx_set_hyp_slots)
     int* aivs_bad = nullptr;          // device flag written by the last raw-cloud batch (kss_aivs.h)
     // batch lanes: chunks of a batch alternate between a few internal streams, so that one chunk's copies and the
     // thin tail of its ICP launch overlap the next chunk's kernels; every lane has its own set of named buffers
@@ -219,7 +219,7 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
     unsigned short *s_perm, *t_inv, *S_perm, *T_inv;
     float4 *t_sorted, *T_sorted;
     float *t_box, *T_box, *run_T;
-    int *best_h, *minima, *n_minima, *run_iters, *run_conv;
+    int *best_h, *minima, *n_minima, *run_iters, *run_conv, *run_hyp, *run_tot;
     BUF("align8", (size_t)P * 8, &align8);
     BUF("s_al", (size_t)P * cap_s * 3, &s_al);
     BUF("s_perm", (size_t)P * cap_s, &s_perm);
@@ -235,6 +235,8 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
     BUF("run_fit", (size_t)P * R, &run_fit);
     BUF("run_iters", (size_t)P * R, &run_iters);
     BUF("run_conv", (size_t)P * R, &run_conv);
+    BUF("run_hyp", (size_t)P * R, &run_hyp);
+    BUF("run_tot", (size_t)P * R * 2, &run_tot);
 
     {
         StageTimer tm(ctx, KSS_STAGE_PREP);
@@ -276,6 +278,7 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
     if (cg) { a.cg_geom = cg->geom; a.cg_hdr = cg->hdr; a.cg_arena = cg->arena; a.cg_ok = cg->ok; }
     icp_fill(a, b.icp);
     a.run_T = run_T; a.run_fit = run_fit; a.run_iters = run_iters; a.run_conv = run_conv;
+    a.run_hyp = run_hyp; a.run_tot = run_tot;
     a.mode = 3;                                                // judge (KSS_ICP.hpp:93) + hypothesis runs (:102-118), one launch
     {
         StageTimer tm(ctx, KSS_STAGE_ICP_HYP);
@@ -285,8 +288,8 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
     if (!pa) BUF("point_align", (size_t)P * cap_S * 3, &pa);
     {
         StageTimer tm(ctx, KSS_STAGE_SELECT_APPLY);
-        KL(launch_select(st, P, R, hpad, G, b.judge_threshold, align8, run_fit, run_iters, run_T, best_h, minima,
-                         n_minima, d_out));
+        KL(launch_select(st, P, R, hpad, G, b.judge_threshold, align8, run_fit, run_iters, run_T, run_conv, run_hyp,
+                         run_tot, best_h, minima, n_minima, d_out));
         KL(launch_final_apply(st, P, full_s, cnt_S, cap_S, align8, d_out, ctx->d_trig_accum, ctx->d_trig_list, G, pa));
     }
     StageTimer tm_metrics(ctx, KSS_STAGE_METRICS);
@@ -386,6 +389,12 @@ void kss_ctx_destroy(kss_ctx* ctx) {
 }
 const char* kss_last_error(kss_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 long long kss_ctx_launch_count(kss_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int kss_ctx_set_hyp_slots(kss_ctx* ctx, int slots) {
+    if (!ctx) return KSS_ERR_ARG;
+    if (slots < 1 || slots > 729) return fail(ctx, KSS_ERR_ARG, "kss_ctx_set_hyp_slots: 1..729");
+    ctx->hyp_slots = slots;
+    return KSS_OK;
+}
 int kss_ctx_synchronize(kss_ctx* ctx) {
     if (!ctx) return KSS_ERR_ARG;
     CU(cudaStreamSynchronize(ctx->stream));
@@ -723,10 +732,9 @@ int batch_core(kss_ctx* ctx, const kss_batch* b_in, bool host, kss_pair_result* 
     }
     int r = ensure_trig(ctx, bb.step); if (r) return r;
     const int H = ctx->G * ctx->G * ctx->G;
-    int slots = 32;
-    const char* es = getenv("KSS_HYP_SLOTS");
+    int slots = ctx->hyp_slots;
+    const char* es = getenv("KSS_HYP_SLOTS");                        // A/B switch for tests
     if (es && atoi(es) > 0) slots = atoi(es);
-    if (ctx->slots_override > 0) slots = ctx->slots_override;
     if (slots > H) slots = H;
     int lanes = 2;
     const char* el = getenv("KSS_LANES");
@@ -858,22 +866,6 @@ int kss_register_batch(kss_ctx* ctx, const kss_batch* b, kss_pair_result* result
     if (raw) CU(cudaMemcpyAsync(&bad, ctx->aivs_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (bad) return aivs_status(ctx, bad);
-    // pairs whose local-minimum list exceeded the hypothesis slots: re-run alone with enough slots
-    for (int p = 0; p < P; ++p) {
-        if (!results[p].overflow) continue;
-        kss_batch one = *b;
-        one.n_pairs = 1;
-        if (!raw) { one.sim_s = b->sim_s + (size_t)p * b->cap_s * 3; one.sim_t = b->sim_t + (size_t)p * b->cap_t * 3; }
-        one.full_s = b->full_s + (size_t)p * b->cap_S * 3; one.full_t = b->full_t + (size_t)p * b->cap_T * 3;
-        one.cnt_s = b->cnt_s ? b->cnt_s + p : nullptr; one.cnt_t = b->cnt_t ? b->cnt_t + p : nullptr;
-        one.cnt_S = b->cnt_S ? b->cnt_S + p : nullptr; one.cnt_T = b->cnt_T ? b->cnt_T + p : nullptr;
-        ctx->slots_override = results[p].n_minima;
-        r = batch_core(ctx, &one, true, results + p, point_align ? point_align + (size_t)p * b->cap_S * 3 : nullptr);
-        ctx->slots_override = 0;
-        if (r) return r;
-        CU(cudaStreamSynchronize(st));
-        results[p].overflow = 1;
-    }
     return KSS_OK;
 }
 

@@ -41,6 +41,9 @@ struct IcpArgs {
     int max_iter; double max_dist_sqr, rot_thr, trans_thr, mse_rel, mse_abs;
     // per-run outputs, run = pair * runs_per_pair + (mode==1 ? 1 + slot : 0)
     float* run_T; double* run_fit; int* run_iters; int* run_conv;
+    // hypothesis slots that serve several hypotheses (more local minima than slots): run_hyp = 2 * l + qualifies of the
+    // run the slot ended up holding, run_tot = {sum of iterations, number of runs} of the slot (both may be null)
+    int* run_hyp; int* run_tot;
     // optional trace
     unsigned long long* phase_cycles;      // diagnostics (tools/): per-phase clock64 sums of thread 0, or null
     int trace_cap; int32_t* trace_idx; float* trace_T; double* trace_mse; float* trace_src;
@@ -67,6 +70,7 @@ cudaError_t launch_sweep_finalize(cudaStream_t st, int P, const float* rbuf, con
 cudaError_t launch_icp(cudaStream_t st, int P, int slots, const IcpArgs& a);
 cudaError_t launch_select(cudaStream_t st, int P, int runs_per_pair, int hpad, int G, double judge_thr,
                           const double* align8, const double* run_fit, const int* run_iters, const float* run_T,
+                          const int* run_conv, const int* run_hyp, const int* run_tot,
                           const int* best_h, const int* minima, const int* n_minima, PairOut* out);
 cudaError_t launch_final_apply(cudaStream_t st, int P, const double* full_s, const int* cnt_S, int cap_S,
                                const double* align8, const PairOut* out, const double* trig_accum,

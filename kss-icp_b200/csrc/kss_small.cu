@@ -997,14 +997,17 @@ icp_small_kernel(IcpArgs a) {
     const int mode = a.mode == 3 ? (slot == 0 ? 0 : 1) : a.mode;
     const int hslot = a.mode == 3 ? slot - 1 : slot;
     const int run = p * a.runs_per_pair + (mode == 1 ? 1 + hslot : 0);
+    // A pair with more local minima than hypothesis slots: the CTA of slot s runs the hypotheses s, s + slots,
+    // s + 2 slots, ... one after the other and keeps the lexicographic minimum (fitness, l) among those with
+    // 0 <= fitness < 9999 -- exactly what the serial scan `ri < Q && ri >= 0`, Q = 9999 (KSS_ICP.hpp:100-116) keeps.
+    const int nslots = a.runs_per_pair - 1;
+    const int n_hyp = mode == 1 ? a.n_minima[p] : 0;
+    int hs = hslot;                                   // hypothesis (angleList index) of the current run
 
     double ang_c[3] = {1.0, 1.0, 1.0}, ang_s[3] = {0.0, 0.0, 0.0};
     if (mode == 1) {
         const bool active = a.mode == 3 || a.judge_thr < 0.0 || a.run_fit[p * a.runs_per_pair] > a.judge_thr;
-        if (!active || hslot >= a.n_minima[p] || hslot >= a.runs_per_pair - 1) return;
-        const int h = a.minima[(size_t)p * a.hpad + hslot];
-        const int idx[3] = {h / (a.G * a.G), (h / a.G) % a.G, h % a.G};
-        for (int k = 0; k < 3; ++k) { ang_c[k] = a.trig_list[2 * idx[k]]; ang_s[k] = a.trig_list[2 * idx[k] + 1]; }
+        if (!active || hslot >= n_hyp || hslot >= nslots) return;
     } else if (mode == 0) {
         const int h = a.best_h[p];
         const int idx[3] = {h / (a.G * a.G), (h / a.G) % a.G, h % a.G};
@@ -1037,8 +1040,6 @@ icp_small_kernel(IcpArgs a) {
         const unsigned short* gi = a.t_inv + (size_t)p * a.cap_t;
         for (int j = threadIdx.x; j < n_t; j += blockDim.x) tinv[j] = gi[j];
     }
-    if (threadIdx.x < 16) fin[threadIdx.x] = (threadIdx.x % 5 == 0) ? 1.0f : 0.0f;
-    if (threadIdx.x == 0) { kept = 0; done = 0; prev_mse = DBL_MAX; }
     __syncthreads();
         ICP_TICK(0);
     TileView tv{tgt, box, npad / TILE};
@@ -1062,6 +1063,18 @@ icp_small_kernel(IcpArgs a) {
     };
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    double best_fit = 0.0;                            // thread 0: best qualifying run of this CTA so far
+    int have_best = 0, stored = 0, tot_iters = 0, tot_runs = 0;
+  for (;;) {                                          // ---- runs of this CTA (one, unless the pair overflows the slots)
+    if (mode == 1) {
+        const int h = a.minima[(size_t)p * a.hpad + hs];
+        const int idx[3] = {h / (a.G * a.G), (h / a.G) % a.G, h % a.G};
+        for (int k = 0; k < 3; ++k) { ang_c[k] = a.trig_list[2 * idx[k]]; ang_s[k] = a.trig_list[2 * idx[k] + 1]; }
+    }
+    __syncthreads();                                  // the previous run's readers of fin / d2s are done
+    if (threadIdx.x < 16) fin[threadIdx.x] = (threadIdx.x % 5 == 0) ? 1.0f : 0.0f;
+    if (threadIdx.x == 0) { kept = 0; done = 0; prev_mse = DBL_MAX; }
+    __syncthreads();
     int iters = 0;
     int converged = 0;
 
@@ -1266,13 +1279,30 @@ icp_small_kernel(IcpArgs a) {
         ICP_TICK(7);
     if (warp == 0) {
         double s = canon_sum_warp_f64(n_s, [&](int i, double& v) { v = (double)d2s[i]; return true; });
+        int take = 0;
         if (lane == 0) {
-            a.run_fit[run] = n_s > 0 ? __ddiv_rn(s, (double)n_s) : DBL_MAX;
-            a.run_iters[run] = iters;
-            a.run_conv[run] = converged;
+            const double fit = n_s > 0 ? __ddiv_rn(s, (double)n_s) : DBL_MAX;
+            const int qual = (fit >= 0.0 && fit < 9999.0) ? 1 : 0;
+            tot_iters += iters; ++tot_runs;
+            // the first run is always stored (it is what the reference uses when nothing qualifies: angleIndex = 0);
+            // later runs (increasing l) replace it only by a strictly smaller qualifying fitness
+            take = !stored || (qual && (!have_best || fit < best_fit));
+            if (take) {
+                a.run_fit[run] = fit;
+                a.run_iters[run] = iters;
+                a.run_conv[run] = converged;
+                if (a.run_hyp) a.run_hyp[run] = hs * 2 + qual;
+                stored = 1;
+                if (qual) { have_best = 1; best_fit = fit; }
+            }
         }
+        take = __shfl_sync(KSS_FULL, take, 0);
+        if (take && lane < 16) a.run_T[(size_t)run * 16 + lane] = fin[lane];
     }
-    if (threadIdx.x < 16) a.run_T[(size_t)run * 16 + threadIdx.x] = fin[threadIdx.x];
+    hs += nslots;
+    if (mode != 1 || hs >= n_hyp) break;
+  }
+    if (threadIdx.x == 0 && a.run_tot) { a.run_tot[2 * run] = tot_iters; a.run_tot[2 * run + 1] = tot_runs; }
 }
 
 // =============================================================== select_kernel
@@ -1281,7 +1311,8 @@ icp_small_kernel(IcpArgs a) {
 __global__ void select_kernel(int P, int runs_per_pair, int hpad, int G, double judge_thr,
                               const double* __restrict__ align8,
                               const double* __restrict__ run_fit, const int* __restrict__ run_iters,
-                              const float* __restrict__ run_T,
+                              const float* __restrict__ run_T, const int* __restrict__ run_conv,
+                              const int* __restrict__ run_hyp, const int* __restrict__ run_tot,
                               const int* __restrict__ best_h, const int* __restrict__ minima,
                               const int* __restrict__ n_minima,
                               PairOut* __restrict__ out) {
@@ -1299,23 +1330,30 @@ __global__ void select_kernel(int P, int runs_per_pair, int hpad, int G, double 
     int use_run = 0, used_h = best_h[p], winner = -1, multi = 0, overflow = 0;
     if (E > judge_thr) {
         multi = 1;
+        // slot s holds the lexicographic minimum (fitness, l) of the hypotheses l = s, s + slots, ... that pass
+        // `ri >= 0 && ri < 9999` (or, when none does, its first run); the minimum over the slots is the l the serial
+        // scan `if (ri < Q && ri >= 0) { Q = ri; angleIndex = l; }` ends with (first strict minimum in l order)
         double Q = 9999.0;
-        int angleIndex = 0;
+        int angleIndex = 0, slot_of = 0, have = 0;
         int L = n_minima[p];
-        if (L > runs_per_pair - 1) { overflow = 1; L = runs_per_pair - 1; }
-        for (int l = 0; l < L; ++l) {
-            const double ri = run_fit[p * runs_per_pair + 1 + l];
-            total += run_iters[p * runs_per_pair + 1 + l]; ++nruns;
-            if (ri < Q && ri >= 0.0) { Q = ri; angleIndex = l; }
+        int S = L;
+        if (L > runs_per_pair - 1) { overflow = 1; S = runs_per_pair - 1; }
+        for (int sidx = 0; sidx < S; ++sidx) {
+            const int rr = p * runs_per_pair + 1 + sidx;
+            const double ri = run_fit[rr];
+            const int hv = run_hyp[rr], l = hv >> 1;
+            total += run_tot[2 * rr]; nruns += run_tot[2 * rr + 1];
+            if ((hv & 1) && (!have || ri < Q || (ri == Q && l < angleIndex))) { Q = ri; angleIndex = l; slot_of = sidx; have = 1; }
         }
         winner = angleIndex;
-        use_run = 1 + angleIndex;
+        use_run = 1 + slot_of;
         used_h = minima[(size_t)p * hpad + angleIndex];
     }
     // the final ICP (KSS_ICP.hpp:130) repeats the winner's run on identical input: reuse it
     o.branch_multi = multi; o.winner = winner; o.used_h = used_h; o.use_list = multi;
     o.final_fitness = run_fit[p * runs_per_pair + use_run];
     o.final_iters = run_iters[p * runs_per_pair + use_run];
+    o.final_converged = run_conv[p * runs_per_pair + use_run];
     o.total_icp_iters = total + o.final_iters;
     o.n_icp_runs = nruns + 1;
     o.overflow = overflow;
@@ -1468,8 +1506,8 @@ cudaError_t launch_sort_source(cudaStream_t st, int P, const double* pts, const 
 cudaError_t launch_middle_align(cudaStream_t st, int P, const double* sim_s, const int* cnt_s, int cap_s,
                                 const double* sim_t, const int* cnt_t, int cap_t, double* align8, double* s_al) {
     const size_t smem = 4 * SMALL_MAX * sizeof(double);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(middle_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    // the opt-in is per device: set on every launch (one ctx per GPU, several ctxs per process)
+    cudaFuncSetAttribute(middle_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     middle_align_kernel<<<P, 256, smem, st>>>(sim_s, cnt_s, cap_s, sim_t, cnt_t, cap_t, align8, s_al);
     return cudaGetLastError();
 }
@@ -1478,8 +1516,7 @@ cudaError_t launch_sweep(cudaStream_t st, int P, const double* s_al, const int* 
                          const int* cnt_t, int cap_tpad, const double* trig_accum, int G, int score_mode,
                          float* rbuf, int hpad, const CgBuffers* cg) {
     const size_t smem = (size_t)cap_tpad * sizeof(float4) + 6 * MAX_TILES * sizeof(float);
-    static size_t set = 0;
-    if (smem > set) { cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = smem; }
+    cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     sweep_kernel<<<dim3(G * G, P), 256, smem, st>>>(s_al, cnt_s, cap_s, s_perm, t_sorted, t_box, cnt_t, cap_tpad,
                                                    trig_accum, G, score_mode, rbuf, hpad,
                                                    cg ? cg->geom : nullptr, cg ? cg->hdr : nullptr,
@@ -1544,22 +1581,22 @@ size_t icp_smem_bytes(int cap_s, int cap_t, int cap_tpad) {
 }
 cudaError_t launch_icp(cudaStream_t st, int P, int slots, const IcpArgs& a) {
     const size_t smem = icp_smem_bytes(a.cap_s, a.cap_t, a.cap_tpad);
-    static size_t set0 = 0, set1 = 0;
     const bool trace = a.trace_cap > 0 && (a.trace_idx || a.trace_T || a.trace_mse || a.trace_src);
     if (trace) {
-        if (smem > set1) { cudaFuncSetAttribute(icp_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set1 = smem; }
+        cudaFuncSetAttribute(icp_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         icp_small_kernel<true><<<dim3(slots, P), 256, smem, st>>>(a);
     } else {
-        if (smem > set0) { cudaFuncSetAttribute(icp_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set0 = smem; }
+        cudaFuncSetAttribute(icp_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         icp_small_kernel<false><<<dim3(slots, P), 256, smem, st>>>(a);
     }
     return cudaGetLastError();
 }
 cudaError_t launch_select(cudaStream_t st, int P, int runs_per_pair, int hpad, int G, double judge_thr,
-                          const double* align8, const double* run_fit, const int* run_iters, const float* run_T, const int* best_h,
+                          const double* align8, const double* run_fit, const int* run_iters, const float* run_T,
+                          const int* run_conv, const int* run_hyp, const int* run_tot, const int* best_h,
                           const int* minima, const int* n_minima, PairOut* out) {
     select_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, runs_per_pair, hpad, G, judge_thr, align8, run_fit, run_iters, run_T,
-                                                  best_h, minima, n_minima, out);
+                                                  run_conv, run_hyp, run_tot, best_h, minima, n_minima, out);
     return cudaGetLastError();
 }
 cudaError_t launch_final_apply(cudaStream_t st, int P, const double* full_s, const int* cnt_S, int cap_S,
@@ -1581,12 +1618,11 @@ cudaError_t launch_nn_small(cudaStream_t st, int P, int mode, const double* q, c
                             const unsigned short* q_perm, const float4* t_sorted, const float* t_box,
                             const int* cnt_t, int cap_tpad, int* idx, float* d2, double* out3, int out3_stride) {
     const size_t smem = (size_t)cap_tpad * sizeof(float4) + 6 * MAX_TILES * sizeof(float) + (size_t)cap_q * sizeof(float);
-    static size_t set0 = 0, set1 = 0;
     if (mode == 0) {
-        if (smem > set0) { cudaFuncSetAttribute(nn_small_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set0 = smem; }
+        cudaFuncSetAttribute(nn_small_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         nn_small_kernel<0><<<P, 256, smem, st>>>(q, cnt_q, cap_q, q_perm, t_sorted, t_box, cnt_t, cap_tpad, idx, d2, out3, out3_stride);
     } else {
-        if (smem > set1) { cudaFuncSetAttribute(nn_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set1 = smem; }
+        cudaFuncSetAttribute(nn_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         nn_small_kernel<1><<<P, 256, smem, st>>>(q, cnt_q, cap_q, q_perm, t_sorted, t_box, cnt_t, cap_tpad, idx, d2, out3, out3_stride);
     }
     return cudaGetLastError();

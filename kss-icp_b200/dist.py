@@ -28,10 +28,24 @@ def select_winner(fitness):
     return idx
 
 
+def angle_list(step):
+    """angleList values per axis index: index * 6.3 / step for the G loop values of `for (a = 0; a < 6.3; a += 6.3 / step)`
+    (initRegistrationKSS.hpp:245, 282-284); the same double arithmetic as kss_sweep_angles"""
+    out, a, g = [], 0.0, 0
+    while a < 6.3:
+        out.append(float(g) * 6.3 / float(step))
+        a = a + 6.3 / float(step)
+        g += 1
+    return np.array(out, np.float64)
+
+
 def register_hypothesis_sharded(backend, sim_s, sim_t, full_s, full_t, rank=0, world=1, allreduce_min=None,
                                 step=8.0, max_iter=1000, list_angles=None):
-    """KSSICP_Registration (KSS_ICP.hpp:86-130) + PCR_QM with the hypothesis ICP runs sharded over ranks.
+    """list_angles: per-axis angleList table (default: the one `step` defines).
+    KSSICP_Registration (KSS_ICP.hpp:86-130) + PCR_QM with the hypothesis ICP runs sharded over ranks.
     allreduce_min(np.ndarray[float64]) -> np.ndarray reduces element-wise MIN over all ranks in place."""
+    if list_angles is None:
+        list_angles = angle_list(step)
     a7, al = backend.middle_align(sim_s, sim_t)
     sw = backend.rotation_sweep(al, sim_t, step)
     src0 = backend.apply_similarity(sim_s, a7, sw["best_angle"])

@@ -74,7 +74,7 @@ public:
 		const int G = res.G;
 		cout << "i:" << res.best_h / (G * G) << " j:" << (res.best_h / G) % G << " k:" << res.best_h % G << " (grid indices)" << endl;
 		if (res.branch_multi) cout << "kernel" << res.winner << ":" << res.final_fitness << " (best of " << res.n_minima << ")" << endl;
-		std::cout << "has converged: " << 1 << std::endl;
+		std::cout << "has converged: " << res.final_converged << std::endl;
 		std::cout << "score: " << res.final_fitness << std::endl;
 		for (int r = 0; r < 4; r++) std::cout << res.T[4 * r] << " " << res.T[4 * r + 1] << " " << res.T[4 * r + 2] << " " << res.T[4 * r + 3] << std::endl;
 
@@ -167,12 +167,14 @@ private:
 		kss_icp_params prm;
 		kss_icp_params_default(&prm);
 		prm.max_iterations = iter;
-		int iters = 0, conv = 0;
-		return kss_host::ok(kss_icp(kss_host::ctx(), s.data(), (int)ps.size(), t.data(), (int)pt.size(), &prm, T, fit, &iters, &conv, nullptr), "kss_icp");
+		int iters = 0;
+		lastConverged = 0;
+		return kss_host::ok(kss_icp(kss_host::ctx(), s.data(), (int)ps.size(), t.data(), (int)pt.size(), &prm, T, fit, &iters, &lastConverged, nullptr), "kss_icp");
 	}
+	int lastConverged = 0;                                    // icp.hasConverged() of the last run_icp
 
 	void print_icp(double fit, const float T[16]) {
-		std::cout << "has converged: " << 1 << std::endl;
+		std::cout << "has converged: " << lastConverged << std::endl;
 		std::cout << "score: " << fit << std::endl;
 		for (int r = 0; r < 4; r++) std::cout << T[4 * r] << " " << T[4 * r + 1] << " " << T[4 * r + 2] << " " << T[4 * r + 3] << std::endl;
 	}

@@ -126,12 +126,19 @@ def test_icp_free_running_bit_exact(ctx, okss, pkg, index, n_full, hyp):
     assert g["fitness"] == o["fitness"]
     # reduction order of the reference's Eigen sums is unknown: the serial order agrees to fp32 rounding
     s = okss.icp(src, tgt, sum_order=okss.SUM_SERIAL, method=okss.NN_KDTREE)
+    R1, R2 = s["T"][:3, :3].astype(np.float64), g["T"][:3, :3].astype(np.float64)
+    ang = np.arccos(np.clip((np.trace(R1.T @ R2) - 1) / 2, -1, 1))
+    dt = np.abs(s["T"][:3, 3] - g["T"][:3, 3]).max()
     if s["iters"] == o["iters"]:
-        R1, R2 = s["T"][:3, :3].astype(np.float64), g["T"][:3, :3].astype(np.float64)
-        ang = np.arccos(np.clip((np.trace(R1.T @ R2) - 1) / 2, -1, 1))
         assert ang < 1e-4                               # north_star: rotation error < 1e-4 rad
-        assert np.abs(s["T"][:3, 3] - g["T"][:3, 3]).max() < 1e-4
+        assert dt < 1e-4
         assert abs(s["fitness"] - g["fitness"]) < 1e-4 * s["fitness"] + 1e-9   # fp32 tolerance, stated
+    else:
+        # the two summation orders crossed PCL's relative-MSE stop (1e-3) on different iterations: the results then
+        # differ by one ICP update at the stopping threshold -- bounded by that threshold, not by fp32 rounding
+        assert abs(s["iters"] - o["iters"]) <= 2
+        assert ang < 2e-3 and dt < 2e-3
+        assert abs(s["fitness"] - g["fitness"]) < 1e-2 * s["fitness"] + 1e-9
 
 
 def test_icp_rejection_and_too_few(ctx, okss):
@@ -202,15 +209,35 @@ def test_register_ragged_counts(ctx, okss, pkg):
         _check_pair(res[p], o)
 
 
-def test_register_hypothesis_slot_overflow(ctx, okss, pkg, monkeypatch):
-    """more local minima than hypothesis slots: the pair is re-run with enough slots, same answer"""
-    monkeypatch.setenv("KSS_HYP_SLOTS", "2")
-    p = pkg.synth.modelnet_pair(21, n_full=512)
-    r = ctx.register(p["sim_s"], p["sim_t"], p["full_s"], p["full_t"])
-    o = okss.register(p["sim_s"], p["sim_t"], p["full_s"], p["full_t"], sum_order=okss.SUM_CANON256)
-    if o["branch_multi"] and o["n_minima"] > 2:
-        assert int(r["overflow"]) == 1
-    _check_pair(r, o)
+@pytest.mark.parametrize("slots", [1, 2, 5])
+def test_register_hypothesis_slot_overflow(ctx, okss, pkg, slots):
+    """more local minima than hypothesis slots: a slot's CTA then runs several hypotheses in turn inside the same
+    launch (KSS_ICP.hpp:102-118 keeps the first strict minimum, which is the lexicographic minimum (fitness, l)) --
+    same answer through the host-buffer entry AND the device entry, which the bench's headline `value` is timed on"""
+    import torch
+    P = 8
+    b, _ = pkg.synth.modelnet_batch(P, n_full=512, first=20)
+    ora = [okss.register(b["sim_s"][p], b["sim_t"][p], b["full_s"][p], b["full_t"][p], sum_order=okss.SUM_CANON256,
+                         method=okss.NN_KDTREE) for p in range(P)]
+    assert sum(1 for o in ora if o["branch_multi"] and o["n_minima"] > slots) >= 2      # the case is really exercised
+    ctx.set_hyp_slots(slots)
+    try:
+        res = ctx.register_batch(b["sim_s"], b["sim_t"], b["full_s"], b["full_t"])
+        dev = {k: torch.from_numpy(np.ascontiguousarray(b[k])).cuda() for k in ("sim_s", "sim_t", "full_s", "full_t")}
+        d_res = torch.zeros(P * pkg.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        caps = (b["sim_s"].shape[1], b["sim_t"].shape[1], b["full_s"].shape[1], b["full_t"].shape[1])
+        ctx.register_batch_device(P, caps, tuple(dev[k].data_ptr() for k in ("sim_s", "sim_t", "full_s", "full_t")),
+                                  d_res.data_ptr())
+        ctx.synchronize()
+        res_d = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=pkg.RESULT_DTYPE)
+    finally:
+        ctx.set_hyp_slots(32)
+    for p in range(P):
+        _check_pair(res[p], ora[p])
+        _check_pair(res_d[p], ora[p])
+        assert int(res[p]["overflow"]) == int(ora[p]["branch_multi"] and ora[p]["n_minima"] > slots)
+        assert int(res[p]["final_converged"]) == 1
 
 
 def test_bad_arguments(ctx, pkg):
