@@ -1000,18 +1000,20 @@ icp_small_kernel(IcpArgs a) {
     // A pair with more local minima than hypothesis slots: the CTA of slot s runs the hypotheses s, s + slots,
     // s + 2 slots, ... one after the other and keeps the lexicographic minimum (fitness, l) among those with
     // 0 <= fitness < 9999 -- exactly what the serial scan `ri < Q && ri >= 0`, Q = 9999 (KSS_ICP.hpp:100-116) keeps.
-    const int nslots = a.runs_per_pair - 1;
-    const int n_hyp = mode == 1 ? a.n_minima[p] : 0;
     int hs = hslot;                                   // hypothesis (angleList index) of the current run
 
-    double ang_c[3] = {1.0, 1.0, 1.0}, ang_s[3] = {0.0, 0.0, 0.0};
+    __shared__ double ang_c[3], ang_s[3];             // cos / sin of the run's start rotation (shared: register cap)
+    if (threadIdx.x < 3) { ang_c[threadIdx.x] = 1.0; ang_s[threadIdx.x] = 0.0; }
+    __syncthreads();
     if (mode == 1) {
         const bool active = a.mode == 3 || a.judge_thr < 0.0 || a.run_fit[p * a.runs_per_pair] > a.judge_thr;
-        if (!active || hslot >= n_hyp || hslot >= nslots) return;
+        if (!active || hslot >= a.n_minima[p] || hslot >= a.runs_per_pair - 1) return;
     } else if (mode == 0) {
-        const int h = a.best_h[p];
-        const int idx[3] = {h / (a.G * a.G), (h / a.G) % a.G, h % a.G};
-        for (int k = 0; k < 3; ++k) { ang_c[k] = a.trig_accum[2 * idx[k]]; ang_s[k] = a.trig_accum[2 * idx[k] + 1]; }
+        if (threadIdx.x < 3) {
+            const int h = a.best_h[p], k = threadIdx.x;
+            const int id = k == 0 ? h / (a.G * a.G) : k == 1 ? (h / a.G) % a.G : h % a.G;
+            ang_c[k] = a.trig_accum[2 * id]; ang_s[k] = a.trig_accum[2 * id + 1];
+        }
     }
 
     const int npad = (n_t + TILE - 1) / TILE * TILE;
@@ -1063,15 +1065,17 @@ icp_small_kernel(IcpArgs a) {
     };
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    double best_fit = 0.0;                            // thread 0: best qualifying run of this CTA so far
-    int have_best = 0, stored = 0, tot_iters = 0, tot_runs = 0;
+    // thread 0's bookkeeping over the runs of this CTA lives in shared memory (the kernel sits at its register cap)
+    __shared__ double best_fit;                       // best qualifying run so far
+    __shared__ int have_best, stored, tot_iters, tot_runs;
+    if (threadIdx.x == 0) { best_fit = 0.0; have_best = 0; stored = 0; tot_iters = 0; tot_runs = 0; }
   for (;;) {                                          // ---- runs of this CTA (one, unless the pair overflows the slots)
-    if (mode == 1) {
-        const int h = a.minima[(size_t)p * a.hpad + hs];
-        const int idx[3] = {h / (a.G * a.G), (h / a.G) % a.G, h % a.G};
-        for (int k = 0; k < 3; ++k) { ang_c[k] = a.trig_list[2 * idx[k]]; ang_s[k] = a.trig_list[2 * idx[k] + 1]; }
+    __syncthreads();                                  // the previous run's readers of fin / d2s / the angles are done
+    if (mode == 1 && threadIdx.x < 3) {
+        const int h = a.minima[(size_t)p * a.hpad + hs], k = threadIdx.x;
+        const int id = k == 0 ? h / (a.G * a.G) : k == 1 ? (h / a.G) % a.G : h % a.G;
+        ang_c[k] = a.trig_list[2 * id]; ang_s[k] = a.trig_list[2 * id + 1];
     }
-    __syncthreads();                                  // the previous run's readers of fin / d2s are done
     if (threadIdx.x < 16) fin[threadIdx.x] = (threadIdx.x % 5 == 0) ? 1.0f : 0.0f;
     if (threadIdx.x == 0) { kept = 0; done = 0; prev_mse = DBL_MAX; }
     __syncthreads();
@@ -1299,8 +1303,9 @@ icp_small_kernel(IcpArgs a) {
         take = __shfl_sync(KSS_FULL, take, 0);
         if (take && lane < 16) a.run_T[(size_t)run * 16 + lane] = fin[lane];
     }
-    hs += nslots;
-    if (mode != 1 || hs >= n_hyp) break;
+    if (mode != 1) break;
+    hs += a.runs_per_pair - 1;
+    if (hs >= a.n_minima[p]) break;
   }
     if (threadIdx.x == 0 && a.run_tot) { a.run_tot[2 * run] = tot_iters; a.run_tot[2 * run + 1] = tot_runs; }
 }
@@ -1354,6 +1359,7 @@ __global__ void select_kernel(int P, int runs_per_pair, int hpad, int G, double 
     o.final_fitness = run_fit[p * runs_per_pair + use_run];
     o.final_iters = run_iters[p * runs_per_pair + use_run];
     o.final_converged = run_conv[p * runs_per_pair + use_run];
+    o.reserved_[0] = 0; o.reserved_[1] = 0;
     o.total_icp_iters = total + o.final_iters;
     o.n_icp_runs = nruns + 1;
     o.overflow = overflow;
