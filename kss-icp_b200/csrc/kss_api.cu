@@ -209,7 +209,8 @@ void icp_fill(IcpArgs& a, const kss_icp_params& prm) {
 // All kernels go to ctx->stream, no host synchronisation.
 int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s, const double* sim_t,
                     const double* full_s, const double* full_t, const int* cnt_s, const int* cnt_t,
-                    const int* cnt_S, const int* cnt_T, int slots, kss_pair_result* d_out, double* d_point_align) {
+                    const int* cnt_S, const int* cnt_T, const int* h_cnt_S, const int* h_cnt_T, int slots,
+                    kss_pair_result* d_out, double* d_point_align) {
     cudaStream_t st = ctx->stream;
     const int G = ctx->G, H = G * G * G, hpad = H;
     const int cap_s = b.cap_s, cap_t = b.cap_t, cap_S = b.cap_S, cap_T = b.cap_T;
@@ -303,10 +304,11 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
         KL(launch_nn_small(st, P, 1, pa, cnt_S, cap_S, S_perm, T_sorted, T_box, cnt_T, cap_Tpad, nullptr, nullptr,
                            &d_out[0].mse, (int)(sizeof(kss_pair_result) / sizeof(double))));
     } else {
-        // full-resolution clouds beyond the shared-memory path: uniform-grid NN, pair by pair
+        // full-resolution clouds beyond the shared-memory path: block-grid NN, pair by pair (every launch is enqueued
+        // without a host synchronisation; h_cnt_* are the per-pair sizes on the host, null = capacity)
         for (int p = 0; p < P; ++p) {
-            int r = large_metrics_device(ctx->stream, &ctx->launches, pa + (size_t)p * cap_S * 3, cnt_S + p, cap_S,
-                                         full_t + (size_t)p * cap_T * 3, cnt_T + p, cap_T, &d_out[p].mse,
+            int r = large_metrics_device(ctx->stream, &ctx->launches, pa + (size_t)p * cap_S * 3, h_cnt_S ? h_cnt_S[p] : cap_S,
+                                         full_t + (size_t)p * cap_T * 3, h_cnt_T ? h_cnt_T[p] : cap_T, &d_out[p].mse,
                                          [&](const char* name, size_t bytes, void** out) {
                                              unsigned char* q; int rr = dev_buf(ctx, name, bytes, &q); *out = q; return rr; });
             if (r != KSS_OK) return fail(ctx, r, "large-cloud metrics failed");
@@ -422,16 +424,16 @@ int kss_icp_large_begin(kss_ctx* ctx, const double* src, int n_s, const double* 
     if (!src || !tgt || n_s < 1 || n_t < 1) return fail(ctx, KSS_ERR_ARG, "kss_icp_large_begin: bad argument");
     CU(cudaSetDevice(ctx->device));
     double *d_s, *d_t;
-    BUF("lg_in_s", (size_t)n_s * 3, &d_s); BUF("lg_in_t", (size_t)n_t * 3, &d_t);
+    ctx->large_ready = false;
+    BUF("run:lg_in_s", (size_t)n_s * 3, &d_s); BUF("run:lg_in_t", (size_t)n_t * 3, &d_t);
     CU(cudaMemcpyAsync(d_s, src, sizeof(double) * 3 * (size_t)n_s, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(d_t, tgt, sizeof(double) * 3 * (size_t)n_t, cudaMemcpyHostToDevice, ctx->stream));
     auto alloc = [&](const char* name, size_t bytes, void** out) {
         unsigned char* q; int rr = dev_buf(ctx, name, bytes, &q); *out = q; return rr; };
-    ctx->large_ready = false;
     int r;
     {
         StageTimer tm(ctx, KSS_STAGE_LARGE_BUILD);
-        r = large_icp_prepare(ctx->stream, &ctx->launches, d_s, n_s, d_t, n_t, alloc, &ctx->large_run);
+        r = large_icp_prepare(ctx->stream, &ctx->launches, d_s, n_s, d_t, n_t, alloc, &ctx->large_run, "run:");
     }
     if (r != KSS_OK) return fail(ctx, r, "kss_icp_large_begin: build failed");
     ctx->large_run.mark_user = ctx;
@@ -676,7 +678,7 @@ static int nn_common(kss_ctx* ctx, const double* q, int n_q, const double* t, in
         r = large_nn_device(ctx->stream, &ctx->launches, d_q, n_q, d_t, n_t, d_idx, d_d2, alloc);
         if (r != KSS_OK) return fail(ctx, r, "large-cloud NN failed");
     } else {
-        r = large_metrics_device(ctx->stream, &ctx->launches, d_q, c_q, n_q, d_t, c_t, n_t, d_o3, alloc);
+        r = large_metrics_device(ctx->stream, &ctx->launches, d_q, n_q, d_t, n_t, d_o3, alloc);
         if (r != KSS_OK) return fail(ctx, r, "large-cloud metrics failed");
     }
     if (mode == 0) {
@@ -826,7 +828,21 @@ int batch_core(kss_ctx* ctx, const kss_batch* b_in, bool host, kss_pair_result* 
                 q = counts_or_fill(ctx, "cnt_s", c_s, P, bb.cap_s, &c_s); if (q) return q;
                 q = counts_or_fill(ctx, "cnt_t", c_t, P, bb.cap_t, &c_t); if (q) return q;
             }
-            q = pipeline_device(ctx, P, bb, sim_s, sim_t, full_s, full_t, c_s, c_t, c_S, c_T, slots, d_res, d_pa);
+            // sizes of ragged full-resolution clouds are needed on the host when they take the large path
+            const int *hS = nullptr, *hT = nullptr;
+            std::vector<int> hostS, hostT;
+            if (bb.cap_S > SMALL_MAX || bb.cap_T > SMALL_MAX) {
+                if (host) { hS = bb.cnt_S ? bb.cnt_S + p0 : nullptr; hT = bb.cnt_T ? bb.cnt_T + p0 : nullptr; }
+                else {
+                    if (bb.cnt_S) { hostS.resize(P); CU(cudaMemcpyAsync(hostS.data(), bb.cnt_S + p0, sizeof(int) * P, cudaMemcpyDeviceToHost, st)); hS = hostS.data(); }
+                    if (bb.cnt_T) { hostT.resize(P); CU(cudaMemcpyAsync(hostT.data(), bb.cnt_T + p0, sizeof(int) * P, cudaMemcpyDeviceToHost, st)); hT = hostT.data(); }
+                    if (hS || hT) CU(cudaStreamSynchronize(st));
+                }
+                for (int i = 0; i < P; ++i)
+                    if ((hS && (hS[i] < 1 || hS[i] > bb.cap_S)) || (hT && (hT[i] < 1 || hT[i] > bb.cap_T)))
+                        return fail(ctx, KSS_ERR_ARG, "kss_batch: a full-resolution count is outside 1..capacity");
+            }
+            q = pipeline_device(ctx, P, bb, sim_s, sim_t, full_s, full_t, c_s, c_t, c_S, c_T, hS, hT, slots, d_res, d_pa);
             if (q) return q;
             if (host) {
                 CU(cudaMemcpyAsync(results + p0, d_res, sizeof(kss_pair_result) * (size_t)P, cudaMemcpyDeviceToHost, st));

@@ -2,20 +2,25 @@
 //
 // Replaces pcl::KdTreeFLANN + the PCL ICP loop at full resolution (shapeRegistration_ICP(int),
 // KSS_ICP.hpp:133-183; PCR_QM, registrationMeasure.hpp:47-98) with
-//   build : Morton-cell bucket sort of the target (histogram + scan + atomic scatter) and a 32-ary
-//           box pyramid over 32-point tiles (order never affects results: the NN is exact and ties
-//           go to the lowest ORIGINAL index)
-//   nn    : warp-cooperative best-first descent of the pyramid, one query per lane,
-//           32 Morton-consecutive queries per warp; tiles are staged through shared memory and
-//           scanned with broadcast LDS.128
-//   reduce: CANON256 sums by ORIGINAL source index (one warp per 256-element chunk, last CTA
-//           finishes the upper levels), umeyama/SVD on one thread, device-side convergence
+//   build : (all on the device, no host synchronisation) bounding box, a 256-sample nearest-neighbour probe that
+//           sets the cell size h to ~2 point spacings, a uniform grid of fine cells grouped into 4x4x4 BLOCKS,
+//           targets counting-sorted by (Morton block, fine cell), one 64-entry offset table per occupied block,
+//           and a 32-ary box pyramid over 32-point tiles of the sorted array (exact fallback for far queries)
+//   nn    : one CTA = 512 consecutive queries of the Morton-sorted source.  The CTA finds the blocks its queries can
+//           touch, stages their points and offset tables in shared memory with cp.async.bulk (TMA 1-D bulk copies
+//           completing on an mbarrier), then every thread searches 2x2x2 fine cells around its query (4x4x4 if the
+//           first stage cannot prove exactness) from shared memory.  A search is accepted only when the best distance
+//           is below the distance to the unsearched region, so the result is the exact minimum over ALL targets
+//           (ties: lowest ORIGINAL index); anything else falls back to the box pyramid.
+//   reduce: CANON256 sums by ORIGINAL source index over 32-byte per-point records the NN kernel scatters
+//           (one warp per 256-element chunk, last CTA finishes the upper levels), umeyama/SVD on one thread,
+//           device-side convergence
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <ctime>
 #include <vector>
 
 #include "kss_device.cuh"
@@ -24,19 +29,41 @@
 namespace kss {
 
 constexpr int LG_MAX_LEVELS = 4;     // 32^4 tiles * 32 points = 33.5 M points
-constexpr int LG_WARPS = 8;          // warps per CTA in the NN kernel
+constexpr int LG_SAMPLES = 256;      // nearest-neighbour probe of the build
 
 struct Pyramid {
-    const float4* tp;                // Morton-cell ordered targets {x,y,z,bits(orig)}, padded to x32
+    const float4* tp;                // (Morton block, fine cell) ordered targets {x,y,z,bits(orig)}, padded to x32
     int nlev;                        // number of box levels (level 0 = tiles)
     int cnt[LG_MAX_LEVELS];          // boxes per level
     int pad[LG_MAX_LEVELS];          // allocated boxes per level (multiple of 32)
     const float* box[LG_MAX_LEVELS]; // SoA [6][pad[l]]
 };
 
+// geometry of the block grid; written by lg_geom_kernel, read by everything after it
+struct LgGeom {
+    float lo[3];                     // bounding-box corner
+    float h, inv_h;                  // fine cell size (cubic)
+    int nf[3];                       // fine cells per axis
+    int nb[3];                       // blocks per axis (4 fine cells each)
+    int bbits[3];                    // ceil(log2(nb))
+    int nbp;                         // 1 << (sum of bbits): entries of the Morton-compact block table
+    int pad_[2];
+};
+constexpr unsigned LG_EMPTY = 0xffffffffu;
+
+struct LgGridView {
+    const LgGeom* geom;
+    const unsigned* blk_rank;        // [nbp] block code -> rank among occupied blocks, or LG_EMPTY
+    const unsigned* fine_start;      // [n_occ * 64 + 68] absolute start offset of every fine cell (ends with n_t)
+    const float4* tp;                // sorted targets
+    const float4* t_orig;            // targets by original index
+    int n_t;
+};
+
 // ------------------------------------------------------------------ build kernels
-__global__ void lg_init_bbox_kernel(unsigned* bb) {
+__global__ void lg_init_bbox_kernel(unsigned* bb, float* sample_d2) {
     if (threadIdx.x < 3) { bb[threadIdx.x] = 0xffffffffu; bb[3 + threadIdx.x] = 0u; }
+    if (sample_d2) for (int i = threadIdx.x; i < LG_SAMPLES; i += blockDim.x) sample_d2[i] = __int_as_float(0x7f800000);
 }
 
 // double[n][3] -> float4 {x,y,z,bits(i)} with RN narrowing (KSS_ICP.hpp:137-152), plus bounding box
@@ -56,96 +83,213 @@ lg_convert_bbox_kernel(const double* __restrict__ pts, int n, float4* __restrict
     }
 }
 
-__device__ __forceinline__ unsigned lg_cell(float4 p, const unsigned* bb, int bits) {
-    const float cells = (float)(1 << bits) - 0.001f;
-    unsigned code = 0;
-    const float v[3] = {p.x, p.y, p.z};
-    unsigned q[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const float lo = ord2f(bb[a]), hi = ord2f(bb[3 + a]);
-        const float e = hi - lo;
-        const float s = e > 0.0f ? cells / e : 0.0f;
-        q[a] = (unsigned)fminf(fmaxf((v[a] - lo) * s, 0.0f), cells);
+// ---- target grid
+// nearest-neighbour probe: LG_SAMPLES evenly strided targets against all targets (brute force, tiles of 1024 targets in
+// shared memory, thread = sample); sample_d2[s] = smallest POSITIVE squared distance (coincident points do not count)
+__global__ void __launch_bounds__(LG_SAMPLES)
+lg_probe_kernel(const float4* __restrict__ p4, int n, float* __restrict__ sample_d2) {
+    __shared__ float4 tile[1024];
+    const int s = threadIdx.x;
+    const int si = (int)(((long long)s * n) / LG_SAMPLES);
+    const float4 q = p4[si < n ? si : n - 1];
+    const int base = blockIdx.x * 1024;
+    for (int j = threadIdx.x; j < 1024; j += LG_SAMPLES) {
+        const int i = base + j;
+        tile[j] = i < n ? p4[i] : make_float4(PAD_COORD, PAD_COORD, PAD_COORD, 0.0f);
     }
-    for (int b = 0; b < bits; ++b)
-        code |= (((q[0] >> b) & 1u) << (3 * b)) | (((q[1] >> b) & 1u) << (3 * b + 1)) | (((q[2] >> b) & 1u) << (3 * b + 2));
+    __syncthreads();
+    float best = __int_as_float(0x7f800000);
+#pragma unroll 8
+    for (int j = 0; j < 1024; ++j) {
+        const float4 p = tile[j];
+        const float d = d2_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+        best = (d > 0.0f && d < best) ? d : best;
+    }
+    if (best < __int_as_float(0x7f800000)) atomicMin(reinterpret_cast<unsigned*>(sample_d2) + s, __float_as_uint(best));   // positive floats order as uints
+}
+
+__host__ __device__ inline int lg_ceil_log2(int v) { int b = 0; while ((1 << b) < v) ++b; return b; }
+
+// h = hc * 2 * median positive NN distance of the probe (2 * E[d_nn] is the point spacing of a uniformly sampled
+// surface; hc = 1.3 gives ~4 points per occupied fine cell on noisy scan data), enlarged until the Morton-compact block table fits max_bits bits
+__global__ void __launch_bounds__(LG_SAMPLES)
+lg_geom_kernel(const unsigned* __restrict__ bb, const float* __restrict__ sample_d2, int n, float hc, int max_bits,
+               LgGeom* __restrict__ g) {
+    __shared__ unsigned keys[LG_SAMPLES];
+    keys[threadIdx.x] = __float_as_uint(sample_d2[threadIdx.x]);        // +inf (no positive neighbour) sorts last
+    bitonic_sort_smem<LG_SAMPLES>(keys);
+    if (threadIdx.x != 0) return;
+    int valid = 0;
+    while (valid < LG_SAMPLES && keys[valid] < 0x7f800000u) ++valid;
+    float lo[3], ext[3], emax = 0.0f;
+    for (int a = 0; a < 3; ++a) { lo[a] = ord2f(bb[a]); ext[a] = ord2f(bb[3 + a]) - lo[a]; emax = fmaxf(emax, ext[a]); }
+    float h = emax > 0.0f ? emax * 0.015625f : 1.0f;
+    if (valid > 0) h = hc * 2.0f * sqrtf(__uint_as_float(keys[valid >> 1]));
+    if (!(h > 0.0f) || !(h < 3.0e38f)) h = emax > 0.0f ? emax : 1.0f;
+    if (emax > 0.0f) h = fmaxf(h, emax * (1.0f / 4000.0f));             // at most ~4000 fine cells (1000 blocks) per axis
+    int nf[3], nb[3], bbits[3];
+    for (int it = 0; it < 200; ++it) {
+        int tot = 0;
+        for (int a = 0; a < 3; ++a) {
+            nf[a] = (int)(ext[a] / h) + 1;
+            nb[a] = (nf[a] + 3) >> 2;
+            bbits[a] = lg_ceil_log2(nb[a]);
+            tot += bbits[a];
+        }
+        if (tot <= max_bits) break;
+        h *= 1.26f;
+    }
+    for (int a = 0; a < 3; ++a) { g->lo[a] = lo[a]; g->nf[a] = nf[a]; g->nb[a] = nb[a]; g->bbits[a] = bbits[a]; }
+    g->h = h; g->inv_h = 1.0f / h;
+    g->nbp = 1 << (bbits[0] + bbits[1] + bbits[2]);
+    g->pad_[0] = n; g->pad_[1] = 0;
+}
+
+// fine cell of a coordinate (the ONE definition used for binning; queries add slack for its rounding)
+__device__ __forceinline__ int lg_fine(float v, float lo, float inv_h, int nf) {
+    const float f = (v - lo) * inv_h;
+    int c = (int)fminf(fmaxf(f, 0.0f), 2.0e9f);
+    return c < nf ? c : nf - 1;
+}
+// Morton-compact block code: bit k of an axis is interleaved only while k < bbits[axis]
+__device__ __forceinline__ unsigned lg_block_code(int bx, int by, int bz, const int* bbits) {
+    unsigned code = 0; int sh = 0;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        if (k < bbits[0]) { code |= (unsigned)((bx >> k) & 1) << sh; ++sh; }
+        if (k < bbits[1]) { code |= (unsigned)((by >> k) & 1) << sh; ++sh; }
+        if (k < bbits[2]) { code |= (unsigned)((bz >> k) & 1) << sh; ++sh; }
+    }
     return code;
 }
 
 __global__ void __launch_bounds__(256)
-lg_hist_kernel(const float4* __restrict__ p4, int n, const unsigned* __restrict__ bb, int bits,
-               unsigned* __restrict__ cellid, unsigned* __restrict__ hist) {
+lg_bin_kernel(const float4* __restrict__ p4, int n, const LgGeom* __restrict__ gp, unsigned* __restrict__ pkey,
+              unsigned* __restrict__ blk_cnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const unsigned c = lg_cell(p4[i], bb, bits);
-    cellid[i] = c;
-    atomicAdd(&hist[c], 1u);
+    const LgGeom g = *gp;
+    const float4 p = p4[i];
+    const int ix = lg_fine(p.x, g.lo[0], g.inv_h, g.nf[0]), iy = lg_fine(p.y, g.lo[1], g.inv_h, g.nf[1]),
+              iz = lg_fine(p.z, g.lo[2], g.inv_h, g.nf[2]);
+    const unsigned b = lg_block_code(ix >> 2, iy >> 2, iz >> 2, g.bbits);
+    const unsigned f = (unsigned)(((iz & 3) << 4) | ((iy & 3) << 2) | (ix & 3));
+    pkey[i] = (b << 6) | f;
+    atomicAdd(&blk_cnt[b], 1u);
 }
 
-// exclusive scan of m counters: (1) per-1024 block scan + block totals, (2) scan of totals, (3) add
+// one 64-bit scan gives both the rank among occupied blocks (high word) and the point base (low word)
 __global__ void __launch_bounds__(1024)
-lg_scan1_kernel(unsigned* __restrict__ data, int m, unsigned* __restrict__ totals) {
-    __shared__ unsigned ws[32];
+lg_bscan1_kernel(const unsigned* __restrict__ blk_cnt, const LgGeom* __restrict__ gp, unsigned long long* __restrict__ scan,
+                 unsigned long long* __restrict__ totals) {
+    __shared__ unsigned long long ws[32];
+    const int m = gp->nbp;
+    if (blockIdx.x * 1024 >= m) return;
     const int i = blockIdx.x * 1024 + threadIdx.x;
-    const unsigned v = i < m ? data[i] : 0u;
-    unsigned x = v;
+    const unsigned c = i < m ? blk_cnt[i] : 0u;
+    const unsigned long long v = c ? ((1ull << 32) | c) : 0ull;
+    unsigned long long x = v;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(KSS_FULL, x, o); if (lane >= o) x += y; }
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(KSS_FULL, x, o); if (lane >= o) x += y; }
     if (lane == 31) ws[warp] = x;
     __syncthreads();
     if (warp == 0) {
-        unsigned w = ws[lane];
-        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(KSS_FULL, w, o); if (lane >= o) w += y; }
+        unsigned long long w = ws[lane];
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(KSS_FULL, w, o); if (lane >= o) w += y; }
         ws[lane] = w;
     }
     __syncthreads();
-    const unsigned incl = x + (warp ? ws[warp - 1] : 0u);
-    if (i < m) data[i] = incl - v;
+    const unsigned long long incl = x + (warp ? ws[warp - 1] : 0ull);
+    if (i < m) scan[i] = incl - v;
     if (threadIdx.x == 1023) totals[blockIdx.x] = incl;
 }
 __global__ void __launch_bounds__(1024)
-lg_scan2_kernel(unsigned* __restrict__ totals, int nb) {          // nb <= 4096 block totals, one CTA
-    __shared__ unsigned ws[32];
-    __shared__ unsigned carry;
-    if (threadIdx.x == 0) carry = 0u;
+lg_bscan2_kernel(unsigned long long* __restrict__ totals, const LgGeom* __restrict__ gp, int* __restrict__ n_occ) {
+    __shared__ unsigned long long ws[32];
+    __shared__ unsigned long long carry;
+    const int nb = (gp->nbp + 1023) >> 10;
+    if (threadIdx.x == 0) carry = 0ull;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int base = 0; base < nb; base += 1024) {
         const int i = base + threadIdx.x;
-        const unsigned v = i < nb ? totals[i] : 0u;
-        unsigned x = v;
-        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(KSS_FULL, x, o); if (lane >= o) x += y; }
+        const unsigned long long v = i < nb ? totals[i] : 0ull;
+        unsigned long long x = v;
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(KSS_FULL, x, o); if (lane >= o) x += y; }
         if (lane == 31) ws[warp] = x;
         __syncthreads();
         if (warp == 0) {
-            unsigned w = ws[lane];
-            for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(KSS_FULL, w, o); if (lane >= o) w += y; }
+            unsigned long long w = ws[lane];
+            for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(KSS_FULL, w, o); if (lane >= o) w += y; }
             ws[lane] = w;
         }
         __syncthreads();
-        const unsigned incl = x + (warp ? ws[warp - 1] : 0u) + carry;
+        const unsigned long long incl = x + (warp ? ws[warp - 1] : 0ull) + carry;
         if (i < nb) totals[i] = incl - v;
         __syncthreads();
         if (threadIdx.x == 1023) carry = incl;
         __syncthreads();
     }
+    if (threadIdx.x == 0) *n_occ = (int)(carry >> 32);
 }
 __global__ void __launch_bounds__(1024)
-lg_scan3_kernel(unsigned* __restrict__ data, int m, const unsigned* __restrict__ totals) {
+lg_bscan3_kernel(const unsigned* __restrict__ blk_cnt, const unsigned long long* __restrict__ scan,
+                 const unsigned long long* __restrict__ totals, const LgGeom* __restrict__ gp,
+                 unsigned* __restrict__ blk_rank, unsigned* __restrict__ blk_base) {
+    const int m = gp->nbp;
     const int i = blockIdx.x * 1024 + threadIdx.x;
-    if (i < m) data[i] += totals[blockIdx.x];
+    if (i >= m) return;
+    const unsigned c = blk_cnt[i];
+    if (!c) { blk_rank[i] = LG_EMPTY; return; }
+    const unsigned long long e = scan[i] + totals[blockIdx.x];
+    const unsigned r = (unsigned)(e >> 32);
+    blk_rank[i] = r;
+    blk_base[r] = (unsigned)(e & 0xffffffffull);
 }
 
-// mode 0: scatter target points ; mode 1: scatter original indices (query order)
+// zero the counters of the occupied blocks (their number is only known on the device): grid-stride
 __global__ void __launch_bounds__(256)
-lg_scatter_kernel(const float4* __restrict__ p4, int n, const unsigned* __restrict__ cellid,
-                  unsigned* __restrict__ offs, float4* __restrict__ tp, int* __restrict__ perm) {
+lg_zero_fine_kernel(const int* __restrict__ n_occ, uint4* __restrict__ fine_cnt4) {
+    const long long total = (long long)*n_occ * 16;           // uint4 per block row = 64 counters / 4
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        fine_cnt4[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+__global__ void __launch_bounds__(256)
+lg_fine_hist_kernel(const unsigned* __restrict__ pkey, int n, const unsigned* __restrict__ blk_rank, unsigned* __restrict__ fine_cnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const unsigned pos = atomicAdd(&offs[cellid[i]], 1u);
-    if (tp) tp[pos] = p4[i];
-    if (perm) perm[pos] = i;
+    const unsigned k = pkey[i];
+    atomicAdd(&fine_cnt[(size_t)blk_rank[k >> 6] * 64 + (k & 63u)], 1u);
+}
+// one warp per occupied block: offsets of its 64 fine cells (absolute), counters reset to serve as scatter cursors
+__global__ void __launch_bounds__(256)
+lg_fine_scan_kernel(const int* __restrict__ n_occ, const unsigned* __restrict__ blk_base, unsigned* __restrict__ fine_cnt,
+                    unsigned* __restrict__ fine_start, int n) {
+    const int lane = threadIdx.x & 31;
+    const int nocc = *n_occ;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int r = wid; r < nocc; r += nw) {
+        uint2* c2 = reinterpret_cast<uint2*>(fine_cnt + (size_t)r * 64) + lane;
+        const uint2 c = *c2;
+        unsigned s = c.x + c.y, x = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(KSS_FULL, x, o); if (lane >= o) x += y; }
+        const unsigned st = blk_base[r] + (x - s);
+        reinterpret_cast<uint2*>(fine_start + (size_t)r * 64)[lane] = make_uint2(st, st + c.x);
+        *c2 = make_uint2(0u, 0u);
+    }
+    if (wid == 0)                                                   // sentinel + padding for the 272-byte table copies
+        for (int j = lane; j < 68; j += 32) fine_start[(size_t)nocc * 64 + j] = (unsigned)n;
+}
+__global__ void __launch_bounds__(256)
+lg_grid_scatter_kernel(const float4* __restrict__ p4, int n, const unsigned* __restrict__ pkey, const unsigned* __restrict__ blk_rank,
+                       const unsigned* __restrict__ fine_start, unsigned* __restrict__ fine_cnt, float4* __restrict__ tp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned k = pkey[i];
+    const size_t c = (size_t)blk_rank[k >> 6] * 64 + (k & 63u);
+    const unsigned pos = fine_start[c] + atomicAdd(&fine_cnt[c], 1u);
+    tp[pos] = p4[i];
 }
 
 __global__ void lg_pad_kernel(float4* tp, int n, int npad) {
@@ -183,315 +327,7 @@ lg_up_box_kernel(const float* __restrict__ cbox, int ccnt, int cpad, int pcnt, i
     }
 }
 
-// ------------------------------------------------------------------ large candidate grid (LCG)
-// The idea of kss_cg.cuh carried to clouds of any size: a DENSE grid over the target's bounding box
-// (power-of-two cells per axis, anisotropic, ~32 cells per target point, <= 2^26) whose every cell lists
-// ALL targets that can be the nearest neighbour of ANY query inside it (sphere rule + dominance rule,
-// same rigorous margins).  Built coarse-to-fine from a single root cell; a cell is handled by a group
-// of GS threads (256 / 32 / 1) chosen per level from the mean parent-list length.  Queries then cost
-// one header read plus a handful of candidate distances per THREAD (no warp cooperation); queries
-// outside the box fall back to the box pyramid for their whole warp.
-struct LcgGeom {
-    float lo[3], h[3], inv_h[3];     // finest level: cell = floor((q - lo) * inv_h)
-    int bits[3];                     // finest level: 2^bits cells per axis
-    int levels;                      // level 0 = root ... levels-1 = finest
-};
-struct LcgView {
-    const unsigned long long* hdr;   // finest level headers: far flag | count << 40 | offset
-    const float4* arena4;            // finest-level lists: the candidate points themselves, .w = bits(original index)
-    const unsigned* arena;           // u32 lists of unrefined far cells inherited from coarser levels
-    const float4* tgt;               // targets by original index (for the u32 lists)
-    LcgGeom g;
-    int ok;
-};
-__host__ __device__ inline int lcg_bits(const LcgGeom& g, int level, int a) {
-    const int L = g.levels - 1;
-    const int b = g.bits[a] - (L - level);
-    return b > 0 ? b : 0;
-}
-
-struct LcgLevelArgs {
-    int level;
-    int bits[3], pbits[3];           // this level / parent level bits per axis
-    float lo[3], h[3];               // this level: cell sizes
-    const float4* tgt; int n_t;
-    const unsigned long long* hdr_prev; unsigned long long* hdr_cur;
-    unsigned* arena; unsigned long long* cursor; unsigned long long cap;   // scratch region of this level: cursor[0] < cap
-    unsigned long long cap_persist;                                       // persistent region: cursor[1] < cap_persist
-    int from_all;                                                         // first built level: the parent list is every target
-    const unsigned* worklist; unsigned nwork;                             // GS=1 pass 2: cells to build (compacted)
-    unsigned* worklist_out; unsigned* worklist_long; unsigned* nwork_out; // GS=1 pass 1: cells that do not inherit (short / long parent lists)
-    int persist_all;                                                      // finest level: everything is persistent ...
-    float4* arena4;                                                       // ... and stored as float4 {x,y,z,bits(orig)} here (offsets in float4 units)
-    int* ok;
-};
-
-// header: bit 63 = "far" (centre more than 3 half-diagonals from every target; a far cell with a short list is
-// not refined, its descendants inherit the header), bit 62 = list is u32 indices (else float4 points),
-// bits 61:36 = count, bits 35:0 = offset (multiple of 4) into the respective arena.
-// Lists are padded to a multiple of 4 entries with a repeated valid candidate.
-constexpr unsigned long long LCG_FAR = 1ull << 63;
-constexpr unsigned long long LCG_IDX = 1ull << 62;     // list holds u32 indices in `arena` (all intermediate levels)
-__host__ __device__ inline int lcg_count(unsigned long long h) { return (int)((h >> 36) & 0x3ffffffull); }
-__host__ __device__ inline unsigned long long lcg_offset(unsigned long long h) { return h & 0xfffffffffull; }
-__host__ __device__ inline unsigned long long lcg_make(bool far, bool idx, unsigned long long cnt, unsigned long long off) {
-    return (far ? LCG_FAR : 0ull) | (idx ? LCG_IDX : 0ull) | (cnt << 36) | off;
-}
-
-template <int GS>
-__global__ void __launch_bounds__(256)
-lcg_level_kernel(LcgLevelArgs a) {
-    __shared__ unsigned long long s_key[8];
-    __shared__ unsigned s_cnt[8];
-    __shared__ unsigned long long s_base;
-    const int lane = threadIdx.x & 31;
-    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long cell = gtid / GS;
-    const int r = (int)(gtid % GS);
-    const long long ncells = a.worklist ? (long long)a.nwork : 1ll << (a.bits[0] + a.bits[1] + a.bits[2]);
-    if (GS == 1) { if (gtid - lane >= ncells) return; }
-    else if (cell >= ncells) return;                                  // group-uniform (GS is 32 or 256 = block)
-    const bool live = cell < ncells;
-    if (a.worklist) cell = live ? (long long)a.worklist[cell] : 0;    // compacted pass: the cells that need building
-    const int ix = (int)(cell & ((1ll << a.bits[0]) - 1));
-    const int iy = (int)((cell >> a.bits[0]) & ((1ll << a.bits[1]) - 1));
-    const int iz = (int)(cell >> (a.bits[0] + a.bits[1]));
-    int m_p = 0;
-    unsigned long long ph = 0ull;
-    const unsigned* plist = nullptr;
-    if (live) {
-        if (a.from_all) m_p = a.n_t;
-        else {
-            const long long parent = (long long)(ix >> (a.bits[0] - a.pbits[0])) +
-                                     ((long long)(iy >> (a.bits[1] - a.pbits[1])) << a.pbits[0]) +
-                                     ((long long)(iz >> (a.bits[2] - a.pbits[2])) << (a.pbits[0] + a.pbits[1]));
-            ph = a.hdr_prev[parent];
-            m_p = lcg_count(ph);
-            plist = a.arena + lcg_offset(ph);
-        }
-    }
-    // far parents whose list is already short are not refined: the child inherits the header (the parent's list
-    // is a valid superset for every query inside the child).  This is empty space away from the surface.
-    // (finest level only: level L-1 stays in its scratch region, which nothing overwrites afterwards)
-    const bool inherit = live && a.persist_all && !a.from_all && (ph & LCG_FAR) && m_p <= 128;
-    if (GS == 1 && a.worklist_out) {
-        // pass 1 of the finest level: write inherited headers, compact everything else into the work list so
-        // that pass 2 runs with dense warps (almost all cells of the finest level inherit)
-        if (inherit) a.hdr_cur[cell] = ph;
-        const bool want = live && !inherit;
-        const bool lng = want && m_p > 48;                            // long parent lists get a warp per cell
-        const unsigned ns = __ballot_sync(KSS_FULL, want && !lng), nl = __ballot_sync(KSS_FULL, lng);
-        unsigned bs = 0, bl = 0;
-        if (lane == 0) { if (ns) bs = atomicAdd(a.nwork_out, (unsigned)__popc(ns)); if (nl) bl = atomicAdd(a.nwork_out + 1, (unsigned)__popc(nl)); }
-        bs = __shfl_sync(KSS_FULL, bs, 0); bl = __shfl_sync(KSS_FULL, bl, 0);
-        const unsigned below = (1u << lane) - 1u;
-        if (want && !lng) a.worklist_out[bs + __popc(ns & below)] = (unsigned)cell;
-        if (lng) a.worklist_long[bl + __popc(nl & below)] = (unsigned)cell;
-        return;
-    }
-    if (inherit) m_p = 0;
-    const float cx = a.lo[0] + ((float)ix + 0.5f) * a.h[0], cy = a.lo[1] + ((float)iy + 0.5f) * a.h[1],
-                cz = a.lo[2] + ((float)iz + 0.5f) * a.h[2];
-    const float rho = 0.5f * sqrtf(a.h[0] * a.h[0] + a.h[1] * a.h[1] + a.h[2] * a.h[2]) * 1.002f;
-    auto cand = [&](int j) -> unsigned { return plist ? plist[j] : (unsigned)j; };
-
-    // ---- pass A: nearest target of the centre (GS = 1: the four nearest, used as dominance competitors)
-    unsigned long long key = 0xffffffffffffffffull, k1 = ~0ull, k2 = ~0ull, k3 = ~0ull;
-    for (int j = r; j < m_p; j += GS) {
-        const unsigned id = cand(j);
-        const float4 q = __ldg(a.tgt + id);
-        const unsigned long long kk = ((unsigned long long)__float_as_uint(d2_rn(cx, cy, cz, q.x, q.y, q.z)) << 32) | id;
-        if (GS <= 32) {
-            if (kk < k3) {
-                if (kk < key) { k3 = k2; k2 = k1; k1 = key; key = kk; }
-                else if (kk < k1) { k3 = k2; k2 = k1; k1 = kk; }
-                else if (kk < k2) { k3 = k2; k2 = kk; }
-                else k3 = kk;
-            }
-        } else key = kk < key ? kk : key;
-    }
-    if (GS == 32) {
-        // merge the lanes' sorted top-4 lists into the warp's top-4: four rounds of "global minimum, pop it at its owner"
-        unsigned long long g[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            unsigned long long m = key;
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(KSS_FULL, m, off); m = o < m ? o : m; }
-            g[t] = m;
-            if (key == m && m != ~0ull) { key = k1; k1 = k2; k2 = k3; k3 = ~0ull; }   // keys are unique (they carry the index)
-        }
-        key = g[0]; k1 = g[1]; k2 = g[2]; k3 = g[3];
-    }
-    if (GS == 256) {
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(KSS_FULL, key, off); key = o < key ? o : key; }
-        if (lane == 0) s_key[threadIdx.x >> 5] = key;
-        __syncthreads();
-        key = s_key[0];
-#pragma unroll
-        for (int w = 1; w < 8; ++w) key = s_key[w] < key ? s_key[w] : key;
-    }
-    const float mn = __uint_as_float((unsigned)(key >> 32));
-    const unsigned amin = m_p > 0 ? (unsigned)(key & 0xffffffffu) : 0u;
-    const float thr = (sqrtf(mn) + 2.0f * rho) * 1.0001f, thr2 = thr * thr;
-    const float sx = a.h[0] * 1.002f * 1.0001f, sy = a.h[1] * 1.002f * 1.0001f, sz = a.h[2] * 1.002f * 1.0001f;
-    const float rr4 = 4.0f * rho * rho;
-    constexpr int NC = GS <= 32 ? 4 : 1;
-    const unsigned long long ck[4] = {key, k1, k2, k3};
-    float4 cp[NC]; float cd[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        const bool have = m_p > 0 && ck[c] != ~0ull;
-        cp[c] = __ldg(a.tgt + (have ? (unsigned)(ck[c] & 0xffffffffu) : 0u));
-        cd[c] = have ? __uint_as_float((unsigned)(ck[c] >> 32)) : __int_as_float(0x7f800000);   // +inf: never dominates
-    }
-    auto keep_test = [&](const float4& q, float d) -> bool {       // sphere rule and dominance rule (see kss_cg.cuh)
-        if (!(d <= thr2)) return false;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const float s = sx * fabsf(q.x - cp[c].x) + sy * fabsf(q.y - cp[c].y) + sz * fabsf(q.z - cp[c].z);
-            if ((d - cd[c]) - s > 1e-5f * (d + cd[c] + rr4)) return false;
-        }
-        return true;
-    };
-    // ---- pass B: count
-    unsigned long long mask = 0ull;
-    unsigned k = 0;
-    for (int j = r, jj = 0; j < m_p; j += GS, ++jj) {
-        const float4 q = __ldg(a.tgt + cand(j));
-        if (keep_test(q, d2_rn(cx, cy, cz, q.x, q.y, q.z))) { if (jj < 64) mask |= 1ull << jj; ++k; }
-    }
-    // ---- allocate (lists padded to x4).  Lists of far cells are inherited by descendants of any depth, so they
-    //      go to the persistent region (cursor[1]); all other lists of an intermediate level go to this level's
-    //      ping-pong scratch region (cursor[0]).  One atomicAdd per warp and region.
-    const bool far = m_p > 0 && sqrtf(mn) > 3.0f * rho;
-    unsigned long long base = 0;
-    unsigned pre = 0, ktot = k;
-    bool persist;
-    if (GS == 1) {
-        persist = a.persist_all != 0;
-        const unsigned mine = (k + 3u) & ~3u;
-        unsigned inc0 = persist ? 0u : mine, inc1 = persist ? mine : 0u;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned y0 = __shfl_up_sync(KSS_FULL, inc0, o), y1 = __shfl_up_sync(KSS_FULL, inc1, o);
-            if (lane >= o) { inc0 += y0; inc1 += y1; }
-        }
-        const unsigned t0 = __shfl_sync(KSS_FULL, inc0, 31), t1 = __shfl_sync(KSS_FULL, inc1, 31);
-        unsigned long long b0 = 0, b1 = 0;
-        if (lane == 0) { if (t0) b0 = atomicAdd(a.cursor, (unsigned long long)t0); if (t1) b1 = atomicAdd(a.cursor + 1, (unsigned long long)t1); }
-        b0 = __shfl_sync(KSS_FULL, b0, 0); b1 = __shfl_sync(KSS_FULL, b1, 0);
-        if (b0 + t0 > a.cap || b1 + t1 > a.cap_persist) { atomicExch(a.ok, 0); if (live) a.hdr_cur[cell] = 0ull; return; }
-        base = persist ? b1 : b0;
-        pre = (persist ? inc1 : inc0) - mine;
-    } else {
-        unsigned incl = k;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(KSS_FULL, incl, o); if (lane >= o) incl += y; }
-        unsigned tot = __shfl_sync(KSS_FULL, incl, 31);
-        pre = incl - k;
-        if (GS == 256) {
-            if (lane == 31) s_cnt[threadIdx.x >> 5] = incl;
-            __syncthreads();
-            unsigned before = 0; tot = 0;
-            for (int w = 0; w < 8; ++w) { if (w < (int)(threadIdx.x >> 5)) before += s_cnt[w]; tot += s_cnt[w]; }
-            pre += before;
-            persist = a.persist_all != 0;
-            if (threadIdx.x == 0) s_base = tot ? atomicAdd(a.cursor + (persist ? 1 : 0), (unsigned long long)((tot + 3u) & ~3u)) : 0ull;
-            __syncthreads();
-            base = s_base;
-        } else {
-            persist = a.persist_all != 0;
-            if (lane == 0 && tot) base = atomicAdd(a.cursor + (persist ? 1 : 0), (unsigned long long)((tot + 3u) & ~3u));
-            base = __shfl_sync(KSS_FULL, base, 0);
-        }
-        ktot = tot;
-        if (base + ((tot + 3u) & ~3u) > (persist ? a.cap_persist : a.cap)) { atomicExch(a.ok, 0); if (live && r == 0) a.hdr_cur[cell] = 0ull; return; }
-    }
-    if (!live) return;
-    if (inherit) { a.hdr_cur[cell] = ph; return; }
-    if (r == 0) a.hdr_cur[cell] = lcg_make(far, a.arena4 == nullptr, ktot, GS == 1 ? base + pre : base);
-    // ---- pass C: write (intermediate levels: u32 indices; finest level: the points themselves, so that a
-    //      query's candidates are contiguous 16-byte records instead of one 32-byte sector per gather)
-    unsigned* out = a.arena + base + pre;
-    float4* out4 = a.arena4 ? a.arena4 + base + pre : nullptr;
-    unsigned w = 0;
-    auto emit = [&](unsigned id) {
-        if (out4) { float4 q = __ldg(a.tgt + id); q.w = __uint_as_float(id); out4[w] = q; } else out[w] = id;
-        ++w;
-    };
-    if ((m_p + GS - 1) / GS <= 64) {
-        while (mask) {
-            const int jj = __ffsll((long long)mask) - 1;
-            mask &= mask - 1ull;
-            emit(cand(r + GS * jj));
-        }
-    } else {
-        for (int j = r; j < m_p; j += GS) {
-            const unsigned id = cand(j);
-            const float4 q = __ldg(a.tgt + id);
-            if (keep_test(q, d2_rn(cx, cy, cz, q.x, q.y, q.z))) emit(id);
-        }
-    }
-    // padding to x4 (the centre's nearest target is always a member of the list)
-    if (GS == 1) { for (const unsigned e = (k + 3u) & ~3u; w < e;) emit(amin); }
-    else if (r == 0) {
-        for (unsigned t = ktot; t < ((ktot + 3u) & ~3u); ++t) {
-            if (a.arena4) { float4 q = __ldg(a.tgt + amin); q.w = __uint_as_float(amin); a.arena4[base + t] = q; }
-            else a.arena[base + t] = amin;
-        }
-    }
-}
-
-// exact 1-NN through the large candidate grid (per thread); returns 0 on success, 1 if the query is outside the
-// box, 2 for an empty header, 3 for an unrefined far cell with a long list (the caller then uses the box pyramid)
-template <bool IDX>
-__device__ __forceinline__ int lcg_query(const LcgView& v, float qx, float qy, float qz,
-                                          unsigned long long& keyout) {
-    const float fx = (qx - v.g.lo[0]) * v.g.inv_h[0], fy = (qy - v.g.lo[1]) * v.g.inv_h[1], fz = (qz - v.g.lo[2]) * v.g.inv_h[2];
-    const float nx = (float)(1 << v.g.bits[0]), ny = (float)(1 << v.g.bits[1]), nz = (float)(1 << v.g.bits[2]);
-    if (!(fx >= 0.0f && fy >= 0.0f && fz >= 0.0f && fx < nx && fy < ny && fz < nz)) return 1;
-    const size_t cell = (size_t)(int)fx + ((size_t)(int)fy << v.g.bits[0]) + ((size_t)(int)fz << (v.g.bits[0] + v.g.bits[1]));
-    const unsigned long long h = __ldg(v.hdr + cell);
-    const int cnt = lcg_count(h);
-    if (cnt == 0) return 2;
-    if (cnt > 1024) return 3;
-    float best = __int_as_float(0x7f800000);
-    unsigned long long bestkey = 0xffffffffffffffffull;
-    if (h & LCG_IDX) {           // inherited list of an unrefined far cell: u32 indices (never on the steady-state path)
-        const unsigned* ip = v.arena + lcg_offset(h);
-        for (int j = 0; j < cnt; ++j) {
-            const unsigned id = __ldg(ip + j);
-            const float4 p = __ldg(v.tgt + id);
-            const float d = d2_rn(qx, qy, qz, p.x, p.y, p.z);
-            if (IDX) { const unsigned long long k0 = ((unsigned long long)__float_as_uint(d) << 32) | id; bestkey = k0 < bestkey ? k0 : bestkey; }
-            else best = fminf(best, d);
-        }
-        keyout = IDX ? bestkey : ((unsigned long long)__float_as_uint(best) << 32);
-        return 0;
-    }
-    const float4* lp = v.arena4 + lcg_offset(h);
-    const int n4 = (cnt + 3) >> 2;
-    for (int j = 0; j < n4; ++j) {
-        const float4 p0 = __ldg(lp + 4 * j), p1 = __ldg(lp + 4 * j + 1), p2 = __ldg(lp + 4 * j + 2), p3 = __ldg(lp + 4 * j + 3);
-        const float d0 = d2_rn(qx, qy, qz, p0.x, p0.y, p0.z), d1 = d2_rn(qx, qy, qz, p1.x, p1.y, p1.z);
-        const float d2 = d2_rn(qx, qy, qz, p2.x, p2.y, p2.z), d3 = d2_rn(qx, qy, qz, p3.x, p3.y, p3.z);
-        if (IDX) {                                                       // .w = original index
-            const unsigned long long k0 = ((unsigned long long)__float_as_uint(d0) << 32) | __float_as_uint(p0.w);
-            const unsigned long long k1 = ((unsigned long long)__float_as_uint(d1) << 32) | __float_as_uint(p1.w);
-            const unsigned long long k2 = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(p2.w);
-            const unsigned long long k3 = ((unsigned long long)__float_as_uint(d3) << 32) | __float_as_uint(p3.w);
-            const unsigned long long m01 = k0 < k1 ? k0 : k1, m23 = k2 < k3 ? k2 : k3;
-            const unsigned long long m = m01 < m23 ? m01 : m23;
-            bestkey = m < bestkey ? m : bestkey;
-        } else best = fminf(best, fminf(fminf(d0, d1), fminf(d2, d3)));
-    }
-    keyout = IDX ? bestkey : ((unsigned long long)__float_as_uint(best) << 32);
-    return 0;
-}
-
-// ------------------------------------------------------------------ warp-cooperative pyramid NN
+// ------------------------------------------------------------------ warp-cooperative pyramid NN (exact fallback)
 struct NNState {
     float qx, qy, qz;
     float lx, ly, lz, hx, hy, hz;    // warp query box
@@ -500,7 +336,6 @@ struct NNState {
     float4* slot;                    // this warp's 32-point staging tile in shared memory
 };
 
-template <bool IDX>
 __device__ __forceinline__ void lg_scan_tile(const Pyramid& py, int t, NNState& s) {
     const int lane = threadIdx.x & 31;
     {   // per-lane point-to-box bound: skip if no lane can improve
@@ -518,21 +353,17 @@ __device__ __forceinline__ void lg_scan_tile(const Pyramid& py, int t, NNState& 
     for (int j = 0; j < TILE; ++j) {
         const float4 p = s.slot[j];
         const float d = d2_rn(s.qx, s.qy, s.qz, p.x, p.y, p.z);
-        if (IDX) {
-            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_uint(p.w);
-            s.bestkey = key < s.bestkey ? key : s.bestkey;
-        } else {
-            s.best = fminf(s.best, d);
-        }
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_uint(p.w);
+        s.bestkey = key < s.bestkey ? key : s.bestkey;
     }
-    if (IDX) s.best = __uint_as_float((unsigned)(s.bestkey >> 32));
+    s.best = __uint_as_float((unsigned)(s.bestkey >> 32));
 }
 
-// visit the children (level L-1 boxes, or tiles when L == 1 ... ) of node `node` at level L
-template <int L, bool IDX>
+// visit the children (level L-1 boxes, or the tile when L == 0) of node `node` at level L
+template <int L>
 __device__ __forceinline__ void lg_descend(const Pyramid& py, int node, NNState& s) {
     if constexpr (L == 0) {
-        lg_scan_tile<IDX>(py, node, s);
+        lg_scan_tile(py, node, s);
     } else {
         const int lane = threadIdx.x & 31;
         const int c = node * 32 + lane;
@@ -552,12 +383,12 @@ __device__ __forceinline__ void lg_descend(const Pyramid& py, int node, NNState&
             if (__uint_as_float(m) > B * CULL_SLACK) break;
             const int src = __ffs(__ballot_sync(KSS_FULL, lb == m)) - 1;
             if (lane == src) lb = 0xffffffffu;
-            lg_descend<L - 1, IDX>(py, node * 32 + src, s);
+            lg_descend<L - 1>(py, node * 32 + src, s);
         }
     }
 }
 
-template <bool IDX>
+// all 32 lanes carry a query (idle lanes repeat a neighbour's); returns (d2 bits << 32) | original index
 __device__ __forceinline__ unsigned long long lg_warp_nn(const Pyramid& py, float qx, float qy, float qz, float4* slot) {
     NNState s;
     s.qx = qx; s.qy = qy; s.qz = qz;
@@ -567,12 +398,11 @@ __device__ __forceinline__ unsigned long long lg_warp_nn(const Pyramid& py, floa
     s.bestkey = 0xffffffffffffffffull;
     s.slot = slot;
     switch (py.nlev) {      // virtual root above the top level
-        case 1: lg_descend<1, IDX>(py, 0, s); break;
-        case 2: lg_descend<2, IDX>(py, 0, s); break;
-        case 3: lg_descend<3, IDX>(py, 0, s); break;
-        default: lg_descend<4, IDX>(py, 0, s); break;
+        case 1: lg_descend<1>(py, 0, s); break;
+        case 2: lg_descend<2>(py, 0, s); break;
+        case 3: lg_descend<3>(py, 0, s); break;
+        default: lg_descend<4>(py, 0, s); break;
     }
-    if (!IDX) s.bestkey = (unsigned long long)__float_as_uint(s.best) << 32;
     return s.bestkey;
 }
 
@@ -584,59 +414,555 @@ struct LgState {
     double prev_mse, mse, fitness;
     int iters, done, converged, kept, apply_T;
     unsigned ticketA, ticketB, ticketF;
-    unsigned miss[5];            // queries not served by the candidate grid, by reason (diagnostics)
+    unsigned miss[5];            // diagnostics: [1] second-stage searches, [2] pyramid fallbacks, [3] passes on global tables, [4] CTAs split in two passes
 };
 
-// NN kernel.  MODE 0: plain queries from q4 (float4 by original index) -> idx/d2 by original index
-//             MODE 1: ICP iteration: lazily apply st->Tk to cur (in place), correspondences with rejection
-//             MODE 2: fitness pass: query = st->fin * inp (original input), d2 only
-template <int MODE>
-__global__ void __launch_bounds__(LG_WARPS * 32)
-lg_nn_kernel(Pyramid py, LcgView lcg, const float4* __restrict__ t_orig, const int* __restrict__ perm, int n_q,
-             float4* __restrict__ cur, const float4* __restrict__ inp, int* __restrict__ idx, float* __restrict__ d2out,
-             int2* __restrict__ corr /* MODE 1: {target index or -1, d2 bits} in one 8-byte record */,
-             LgState* __restrict__ st, double max_dist_sqr) {
-    __shared__ float4 slots[LG_WARPS][TILE];
-    __shared__ float T[16];
-    if (MODE != 0) {
-        if (st->done && MODE == 1) return;
-        if (threadIdx.x < 16) T[threadIdx.x] = MODE == 1 ? st->Tk[threadIdx.x] : st->fin[threadIdx.x];
-        __syncthreads();
+// ------------------------------------------------------------------ staged grid search
+constexpr int NN_THREADS = 256;
+constexpr int NN_QPT = 2;                       // queries per thread
+constexpr int NN_QPC = NN_THREADS * NN_QPT;     // queries per CTA
+constexpr int NN_MAXBOX = 2048;                 // blocks in the bounding box of a pass's queries (bitmap of touched blocks)
+constexpr int NN_MAXREG = 128;                  // blocks actually touched (the region)
+#ifndef KSS_NN_MAXOCC
+#define KSS_NN_MAXOCC 48
+#define KSS_NN_PTS_CAP 2048
+#define KSS_NN_CTAS 3
+#endif
+constexpr int NN_MAXOCC = KSS_NN_MAXOCC;        // occupied blocks staged
+constexpr int NN_PTS_CAP = KSS_NN_PTS_CAP;      // staged points (40 KB)
+__device__ unsigned lg_dbg[8];
+__device__ unsigned lg_dbg2[4];                 // diagnostics: third stage {no bound, cube too large, failed, resolved}
+__device__ unsigned long long lg_cnt[4];        // -DKSS_LG_COUNT: first-stage candidates {evaluated, lane slots, queries}                  // diagnostics: why passes could not stage (KSS_LG_VERBOSE)
+constexpr int NN_TAB_STRIDE = 68;               // u32 per staged table: 65 used, copied as 272 bytes
+constexpr int NN_RNG_STRIDE = 9;                // per-thread list of candidate ranges: 8 + sentinel (odd stride: no bank conflicts)
+constexpr size_t NN_SMEM = (size_t)NN_PTS_CAP * sizeof(float4) + (size_t)NN_MAXOCC * NN_TAB_STRIDE * sizeof(unsigned) +
+                           (size_t)NN_QPC * sizeof(float4) + (size_t)NN_THREADS * NN_RNG_STRIDE * sizeof(unsigned);
+static_assert(NN_PTS_CAP < 65536 && NN_MAXOCC < 128, "ranges are packed as two u16, slots as int8");
+static_assert(NN_MAXREG % 32 == 0 && 8 * TILE * sizeof(float4) <= NN_PTS_CAP * sizeof(float4), "pyramid tiles reuse the point area");
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "KSS_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra KSS_MBAR_DONE;\n"
+        "bra KSS_MBAR_WAIT;\n"
+        "KSS_MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (sizes / addresses multiples of 16)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// block accessors: table of 65 absolute offsets + a pointer such that pts[absolute offset] is the candidate
+struct SmemAcc {
+    const float4* pts; const unsigned* tab; const signed char* slot; const int* delta;
+    int bx0, by0, bz0, rx, ry;
+    __device__ __forceinline__ bool block(int bx, int by, int bz, const unsigned*& t, const float4*& p) const {
+        const int s = slot[((bz - bz0) * ry + (by - by0)) * rx + (bx - bx0)];
+        if (s < 0) return false;
+        t = tab + s * NN_TAB_STRIDE;
+        p = pts + delta[s];
+        return true;
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int base = (blockIdx.x * LG_WARPS + warp) * 32;
-    if (base >= n_q) return;
-    const int j = min(base + lane, n_q - 1);
-    const bool valid = base + lane < n_q;
-    const int o = perm[j];
-    float x, y, z;
-    if (MODE == 2) {
-        const float4 p = inp[o];
-        xform_point(T, p.x, p.y, p.z, x, y, z);
-    } else {
-        const float4 p = cur[o];
-        x = p.x; y = p.y; z = p.z;
-        if (MODE == 1 && st->apply_T) {
-            xform_point(T, p.x, p.y, p.z, x, y, z);     // transformCloud of the previous iteration (A.5)
-            __syncwarp();
-            if (valid) cur[o] = make_float4(x, y, z, p.w);
+};
+struct GlobAcc {
+    const unsigned* blk_rank; const unsigned* fine_start; const float4* tp; const int* bbits;
+    __device__ __forceinline__ bool block(int bx, int by, int bz, const unsigned*& t, const float4*& p) const {
+        const unsigned r = __ldg(blk_rank + lg_block_code(bx, by, bz, bbits));
+        if (r == LG_EMPTY) return false;
+        t = fine_start + (size_t)r * 64;
+        p = tp;
+        return true;
+    }
+};
+
+struct Best { float d; unsigned idx; };          // smallest d2_rn so far, lowest original index among equals
+
+// all targets of the fine cells [x0..x1] x [y0..y1] x [z0..z1] (inside the grid)
+template <class Acc>
+__device__ __forceinline__ void lg_scan_cells(const Acc& acc, int x0, int x1, int y0, int y1, int z0, int z1,
+                                              float qx, float qy, float qz, Best& b) {
+    for (int iz = z0; iz <= z1; ++iz)
+        for (int iy = y0; iy <= y1; ++iy) {
+            const int f = ((iz & 3) << 4) | ((iy & 3) << 2);
+            for (int ix = x0; ix <= x1;) {
+                const int bx = ix >> 2;
+                const int xe = min(x1, (bx << 2) | 3);            // cells of one block along x are contiguous
+                const unsigned* t; const float4* p;
+                if (acc.block(bx, iy >> 2, iz >> 2, t, p)) {
+                    const unsigned s = t[f + (ix & 3)], e = t[f + (xe & 3) + 1];
+                    for (unsigned j = s; j < e; ++j) {
+                        const float4 c = p[j];
+                        const float d = d2_rn(qx, qy, qz, c.x, c.y, c.z);
+                        const unsigned id = __float_as_uint(c.w);
+                        const bool take = d < b.d || (d == b.d && id < b.idx);
+                        b.d = take ? d : b.d;
+                        b.idx = take ? id : b.idx;
+                    }
+                }
+                ix = xe + 1;
+            }
+        }
+}
+
+// the query's position in cell units: nearest cell corner c and the distance m to it (max over the axes)
+struct QCell { int cx, cy, cz; float dx, dy, dz, m; bool inside; };      // d* = signed offset from the corner, in cells
+__device__ __forceinline__ QCell lg_qcell(const LgGeom& g, float x, float y, float z) {
+    QCell q;
+    const float fx = (x - g.lo[0]) * g.inv_h, fy = (y - g.lo[1]) * g.inv_h, fz = (z - g.lo[2]) * g.inv_h;
+    // more than 8 cells outside the grid nothing can be found by either stage: clamping there only keeps the ints sane
+    const float cxf = floorf(fminf(fmaxf(fx, -8.0f), (float)g.nf[0] + 8.0f) + 0.5f);
+    const float cyf = floorf(fminf(fmaxf(fy, -8.0f), (float)g.nf[1] + 8.0f) + 0.5f);
+    const float czf = floorf(fminf(fmaxf(fz, -8.0f), (float)g.nf[2] + 8.0f) + 0.5f);
+    q.cx = (int)cxf; q.cy = (int)cyf; q.cz = (int)czf;
+    q.dx = fx - cxf; q.dy = fy - cyf; q.dz = fz - czf;
+    q.m = fmaxf(fabsf(q.dx), fmaxf(fabsf(q.dy), fabsf(q.dz)));
+    // the 4x4x4 neighbourhood [c-2, c+1] meets the grid?  (m > 0.5 only for clamped, far-away queries)
+    q.inside = q.cx + 1 >= 0 && q.cx - 2 < g.nf[0] && q.cy + 1 >= 0 && q.cy - 2 < g.nf[1] && q.cz + 1 >= 0 && q.cz - 2 < g.nf[2] &&
+               q.m <= 0.75f;
+    return q;
+}
+// the cells one query reads: offsets from the nearest corner, each in -2 .. 1, plus "bounded" (exact without proof)
+__device__ __forceinline__ int lg_box_pack(int x0, int x1, int y0, int y1, int z0, int z1, bool bounded) {
+    return (x0 + 2) | ((x1 + 2) << 2) | ((y0 + 2) << 4) | ((y1 + 2) << 6) | ((z0 + 2) << 8) | ((z1 + 2) << 10) | (bounded ? 1 << 12 : 0);
+}
+__device__ __forceinline__ int lg_box_get(int b, int i) { return ((b >> (2 * i)) & 3) - 2; }
+__device__ __forceinline__ bool lg_box_bounded(int b) { return (b >> 12) & 1; }
+
+// Every target outside the cells [c - reach, c + reach - 1]^3 is farther than (reach - m) cells from the query, up to the
+// rounding of the binning (< 1e-4 cells, covered by the 0.002 slack), so a best distance below that bound is the exact
+// nearest neighbour over ALL targets.
+__device__ __forceinline__ bool lg_proven(const LgGeom& g, const QCell& q, int reach, float best) {
+    const float r = g.h * ((float)reach - 0.002f - q.m);
+    return best <= r * r * 0.9999f;
+}
+
+// NN kernel.  MODE 0: plain queries (sorted, w = original index) -> idx/d2 by original index
+//             MODE 1: ICP iteration: apply st->Tk to the sorted source in place, correspondences with rejection,
+//                     one 32-byte record {source xyz, d2 | target xyz, index or -1} per point by ORIGINAL index
+//             MODE 2: fitness pass: query = st->fin * input, d2 by original index
+// One CTA = NN_QPC consecutive queries.  A pass = region of blocks around the pass's queries -> TMA bulk copies of the
+// blocks' points and offset tables into shared memory -> 2x2x2 search per thread -> warp-cooperative 4x4x4 search of the
+// few queries the first stage could not prove.  A CTA whose region does not fit runs two passes over its halves; a pass
+// that still does not fit reads the grid from global memory.  What neither stage proves goes to the box pyramid.
+template <int MODE>
+__global__ void __launch_bounds__(NN_THREADS, KSS_NN_CTAS)
+lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s, const float4* __restrict__ inp_s,
+             int* __restrict__ idx_out, float* __restrict__ d2out, float4* __restrict__ rec, int* __restrict__ prev_s,
+             LgState* __restrict__ st, double max_dist_sqr) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    float4* s_pts = reinterpret_cast<float4*>(dyn_smem);
+    unsigned* s_tab = reinterpret_cast<unsigned*>(s_pts + NN_PTS_CAP);
+    float4* s_lq = reinterpret_cast<float4*>(s_tab + NN_MAXOCC * NN_TAB_STRIDE);      // queries the first stage left over
+    unsigned* s_rng = reinterpret_cast<unsigned*>(s_lq + NN_QPC);                     // per-thread candidate ranges of the first stage
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ LgGeom g;
+    __shared__ float T[16];
+    __shared__ int s_lo[3], s_hi[3];
+    __shared__ signed char s_slot[NN_MAXBOX];    // box-local block index -> staged slot or -1 (touched blocks only)
+    __shared__ unsigned s_mark[NN_MAXBOX / 32];  // touched blocks of the box
+    __shared__ short s_list[NN_MAXREG];          // the touched blocks, compacted
+    __shared__ int s_delta[NN_MAXOCC];
+    __shared__ unsigned short s_pyr[2 * NN_QPC]; // s_lq entries past the second stage | past the third (pyramid)
+    __shared__ float s_lub[NN_QPC];              // their bound (the previous match's distance), +inf if none
+    __shared__ int s_path;                       // 0 staged, 1 global tables, 2 nothing in reach
+    __shared__ unsigned s_p0[NN_MAXREG], s_cnt[NN_MAXREG], s_rank[NN_MAXREG];
+    __shared__ int s_nleft, s_npyr, s_n2, s_nglob, s_nreg;
+
+    if (MODE == 1 && st->done) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < (int)(sizeof(LgGeom) / 4)) reinterpret_cast<int*>(&g)[tid] = reinterpret_cast<const int*>(gv.geom)[tid];
+    if (MODE != 0 && tid < 16) T[tid] = MODE == 1 ? st->Tk[tid] : st->fin[tid];
+    if (tid == 0) { s_nleft = 0; s_npyr = 0; s_n2 = 0; s_nglob = 0; mbar_init(&s_bar, 1); }
+    __syncthreads();
+
+    // ---- this thread's queries (coalesced), the pending transform, their position in the grid
+    const int base = blockIdx.x * NN_QPC;
+    float qx[NN_QPT], qy[NN_QPT], qz[NN_QPT]; unsigned qo[NN_QPT]; bool valid[NN_QPT]; QCell qc[NN_QPT];
+    int box[NN_QPT];                             // cells to read, relative to the nearest corner (lg_box_pack)
+    Best ub[NN_QPT];                             // MODE 1: the previous iteration's match is a target like any other --
+                                                 // its distance bounds the search before a single cell is read
+    unsigned long long key[NN_QPT];
+    int left_at[NN_QPT];
+    const bool applyT = MODE == 1 && st->apply_T;
+#pragma unroll
+    for (int k = 0; k < NN_QPT; ++k) {
+        const int pos = base + k * NN_THREADS + tid;
+        valid[k] = pos < n_q;
+        qx[k] = qy[k] = qz[k] = 0.0f; qo[k] = 0u;
+        qc[k].inside = false; qc[k].cx = qc[k].cy = qc[k].cz = 0; qc[k].m = 1.0f;
+        key[k] = 0xffffffffffffffffull; left_at[k] = -1;
+        ub[k].d = __int_as_float(0x7f800000); ub[k].idx = 0xffffffffu; box[k] = 0;
+        if (valid[k]) {
+            const int pv = (MODE == 1 && prev_s) ? prev_s[pos] : -1;
+            float4 tprev = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pv >= 0) tprev = __ldg(gv.t_orig + pv);
+            const float4 p = MODE == 2 ? inp_s[pos] : cur_s[pos];
+            qo[k] = __float_as_uint(p.w);
+            if (MODE == 2 || applyT) {
+                xform_point(T, p.x, p.y, p.z, qx[k], qy[k], qz[k]);      // transformCloud of the previous iteration (A.5) / final * input (A.7)
+                if (MODE == 1) cur_s[pos] = make_float4(qx[k], qy[k], qz[k], p.w);
+            } else { qx[k] = p.x; qy[k] = p.y; qz[k] = p.z; }
+            qc[k] = lg_qcell(g, qx[k], qy[k], qz[k]);
+            if (pv >= 0) { ub[k].d = d2_rn(qx[k], qy[k], qz[k], tprev.x, tprev.y, tprev.z); ub[k].idx = (unsigned)pv; }
+            // the cells a search has to read.  With a bound: the cells meeting the cube q +- sqrt(bound) -- every target that
+            // can beat or tie the bound lies inside (0.003 cells of slack for the rounding of the binning), so scanning them
+            // is exact without any further proof.  Without (or when the cube leaves the 4x4x4 cells around the nearest corner,
+            // which is all a pass stages): the 2x2x2 cells around the corner, to be proven by lg_proven.
+            box[k] = lg_box_pack(-1, 0, -1, 0, -1, 0, false);
+            if (pv >= 0 && qc[k].inside) {
+                const float rc = sqrtf(ub[k].d) * g.inv_h * 1.00001f + 0.003f;
+                const float fx = (float)qc[k].cx + qc[k].dx, fy = (float)qc[k].cy + qc[k].dy, fz = (float)qc[k].cz + qc[k].dz;
+                const int x0 = (int)floorf(fx - rc) - qc[k].cx, x1 = (int)floorf(fx + rc) - qc[k].cx;
+                const int y0 = (int)floorf(fy - rc) - qc[k].cy, y1 = (int)floorf(fy + rc) - qc[k].cy;
+                const int z0 = (int)floorf(fz - rc) - qc[k].cz, z1 = (int)floorf(fz + rc) - qc[k].cz;
+                // at most 4 rows of at most 4 cells: at most 8 ranges (a row crosses at most one block boundary)
+                if (x0 >= -2 && x1 <= 1 && y0 >= -2 && y1 <= 1 && z0 >= -2 && z1 <= 1 && (y1 - y0 + 1) * (z1 - z0 + 1) <= 4)
+                    box[k] = lg_box_pack(x0, x1, y0, y1, z0, z1, true);
+            }
         }
     }
-    unsigned long long key = 0ull;
-    int code = 4;
-    if (lcg.ok) code = (MODE == 2) ? lcg_query<false>(lcg, x, y, z, key) : lcg_query<true>(lcg, x, y, z, key);
-    const bool hit = code == 0;
-    if (MODE == 1 && !hit && valid) atomicAdd(&st->miss[code], 1u);
-    if (__any_sync(KSS_FULL, !hit)) {            // some query left the grid's box: exact pyramid search for the warp
-        const unsigned long long k2 = (MODE == 2) ? lg_warp_nn<false>(py, x, y, z, slots[warp])
-                                                  : lg_warp_nn<true>(py, x, y, z, slots[warp]);
-        if (!hit) key = k2;
+
+    int npass = 1;
+    unsigned phase = 0u;
+    for (int pass = 0; pass < npass; ++pass) {
+        // ---- (1) region of blocks around the pass's queries
+        if (tid < 3) { s_lo[tid] = INT_MAX; s_hi[tid] = INT_MIN; }
+        if (tid < NN_MAXBOX / 32) s_mark[tid] = 0u;
+        __syncthreads();
+        int lo3[3] = {INT_MAX, INT_MAX, INT_MAX}, hi3[3] = {INT_MIN, INT_MIN, INT_MIN};
+        // the cells query k reads along axis a (0 = low end, 1 = high end), clamped to the grid; unbounded queries may
+        // need the second stage: 4x4x4 cells
+        auto cell_end = [&](int k, int a, int hi) {
+            const int c = a == 0 ? qc[k].cx : a == 1 ? qc[k].cy : qc[k].cz;
+            const int o = lg_box_bounded(box[k]) ? lg_box_get(box[k], 2 * a + hi) : (hi ? 1 : -2);
+            return hi ? min(c + o, g.nf[a] - 1) : max(c + o, 0);
+        };
+#pragma unroll
+        for (int k = 0; k < NN_QPT; ++k) {
+            if (!(valid[k] && qc[k].inside && (npass == 1 || k == pass))) continue;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { lo3[a] = min(lo3[a], cell_end(k, a, 0)); hi3[a] = max(hi3[a], cell_end(k, a, 1)); }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int l = __reduce_min_sync(KSS_FULL, lo3[a]), h = __reduce_max_sync(KSS_FULL, hi3[a]);
+            if (lane == 0 && l <= h) { atomicMin(&s_lo[a], l); atomicMax(&s_hi[a], h); }
+        }
+        __syncthreads();
+        const bool any = s_lo[0] <= s_hi[0];
+        const int bx0 = any ? s_lo[0] >> 2 : 0, by0 = any ? s_lo[1] >> 2 : 0, bz0 = any ? s_lo[2] >> 2 : 0;
+        const int rx = any ? (s_hi[0] >> 2) - bx0 + 1 : 0, ry = any ? (s_hi[1] >> 2) - by0 + 1 : 0, rz = any ? (s_hi[2] >> 2) - bz0 + 1 : 0;
+        const long long nbox_ll = (long long)rx * ry * rz;
+        const bool boxed = any && nbox_ll <= NN_MAXBOX;
+        // the blocks the pass's queries can touch: bitmap over the box, then a compact list -- a Z-order range of queries
+        // is not a box, its union of blocks is what gets staged
+        if (boxed) {
+#pragma unroll
+            for (int k = 0; k < NN_QPT; ++k) {
+                if (!(valid[k] && qc[k].inside && (npass == 1 || k == pass))) continue;
+                const int xb = cell_end(k, 0, 1) >> 2, yb = cell_end(k, 1, 1) >> 2, zb = cell_end(k, 2, 1) >> 2;
+                for (int bz = cell_end(k, 2, 0) >> 2; bz <= zb; ++bz)
+                    for (int by = cell_end(k, 1, 0) >> 2; by <= yb; ++by)
+                        for (int bx = cell_end(k, 0, 0) >> 2; bx <= xb; ++bx) {
+                            const int li = ((bz - bz0) * ry + (by - by0)) * rx + (bx - bx0);
+                            if (!((s_mark[li >> 5] >> (li & 31)) & 1u)) atomicOr(&s_mark[li >> 5], 1u << (li & 31));
+                        }
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            static_assert(NN_MAXBOX == 2048, "two bitmap words per lane");
+            unsigned w0 = s_mark[2 * lane], w1 = s_mark[2 * lane + 1];
+            const unsigned c = (unsigned)(__popc(w0) + __popc(w1));
+            unsigned x = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(KSS_FULL, x, o); if (lane >= o) x += y; }
+            const unsigned total = __shfl_sync(KSS_FULL, x, 31);
+            unsigned e = x - c;
+            const int nr0 = (boxed && total <= (unsigned)NN_MAXREG) ? (int)total : 0;
+            if (nr0) {
+                while (w0) { const int b = __ffs(w0) - 1; w0 &= w0 - 1u; s_list[e++] = (short)(64 * lane + b); }
+                while (w1) { const int b = __ffs(w1) - 1; w1 &= w1 - 1u; s_list[e++] = (short)(64 * lane + 32 + b); }
+            }
+            if (lane == 0) s_nreg = nr0;
+        }
+        __syncthreads();
+        const int nreg = s_nreg;
+        if (tid < nreg) {                                        // ranks and point ranges of the touched blocks, one thread each
+            const int li = s_list[tid];
+            const unsigned r = __ldg(gv.blk_rank + lg_block_code(bx0 + li % rx, by0 + (li / rx) % ry, bz0 + li / (rx * ry), g.bbits));
+            unsigned q0 = 0u, cnt = 0u;
+            if (r != LG_EMPTY) { q0 = __ldg(gv.fine_start + (size_t)r * 64); cnt = __ldg(gv.fine_start + (size_t)r * 64 + 64) - q0; }
+            s_rank[tid] = r; s_p0[tid] = q0; s_cnt[tid] = cnt;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // slots and shared-memory offsets (prefix sums, EPL consecutive entries per lane), then the TMA bulk copies
+            constexpr int EPL = NN_MAXREG / 32;
+            unsigned cn[EPL], p0[EPL], rk[EPL], ps = 0u, os = 0u;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                const int en = lane * EPL + j;
+                cn[j] = en < nreg ? s_cnt[en] : 0u; p0[j] = en < nreg ? s_p0[en] : 0u; rk[j] = en < nreg ? s_rank[en] : LG_EMPTY;
+                ps += cn[j]; os += cn[j] ? 1u : 0u;
+            }
+            unsigned px = ps, ox = os;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned yp = __shfl_up_sync(KSS_FULL, px, o), yo = __shfl_up_sync(KSS_FULL, ox, o);
+                if (lane >= o) { px += yp; ox += yo; }
+            }
+            const unsigned tp_total = __shfl_sync(KSS_FULL, px, 31), nocc = __shfl_sync(KSS_FULL, ox, 31);
+            int path = 0;
+            if (!any) path = 2;
+            else if (nreg == 0 || tp_total > (unsigned)NN_PTS_CAP || nocc > (unsigned)NN_MAXOCC) {
+                path = 1;
+                if (lane == 0 && npass > 1) {
+                    atomicAdd(&lg_dbg[!boxed ? 0 : nreg == 0 ? 1 : tp_total > (unsigned)NN_PTS_CAP ? 2 : 3], 1u);
+                    atomicAdd(&lg_dbg[4], tp_total); atomicAdd(&lg_dbg[5], nocc); atomicAdd(&lg_dbg[6], (unsigned)nreg); atomicAdd(&lg_dbg[7], (unsigned)min(nbox_ll, 100000ll));
+                }
+            }
+            if (path == 0 && tp_total > 0u) {
+                if (lane == 0) mbar_arrive_expect_tx(&s_bar, tp_total * 16u + nocc * (unsigned)(NN_TAB_STRIDE * 4));
+                __syncwarp();
+                unsigned poff = px - ps, slot = ox - os;
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) {
+                    const int en = lane * EPL + j;
+                    if (en < nreg) s_slot[s_list[en]] = cn[j] ? (signed char)slot : (signed char)-1;
+                    if (cn[j]) {
+                        s_delta[slot] = (int)poff - (int)p0[j];
+                        // TMA bulk copies: the block's points (contiguous in the sorted array) and its offset table
+                        bulk_g2s(s_pts + poff, gv.tp + p0[j], cn[j] * 16u, &s_bar);
+                        bulk_g2s(s_tab + slot * NN_TAB_STRIDE, gv.fine_start + (size_t)rk[j] * 64, NN_TAB_STRIDE * 4, &s_bar);
+                        poff += cn[j]; ++slot;
+                    }
+                }
+            } else if (path == 0) path = 2;                     // the region holds no target at all
+            if (lane == 0) s_path = path;
+        }
+        __syncthreads();
+        const int path = s_path;
+        if (path == 1 && npass == 1 && NN_QPT > 1) { npass = NN_QPT; pass = -1; continue; }     // retry in halves (CTA-uniform)
+        if (path == 0) { mbar_wait(&s_bar, phase & 1u); ++phase; }
+        if (path == 1 && tid == 0) ++s_nglob;
+
+        // ---- (2) first stage, one thread per query: the 2x2x2 cells around the nearest cell corner.  Cells farther from
+        //      the query than the bound it already holds are skipped (their targets are strictly farther); the ranges of
+        //      the rest go to a per-thread list and ONE flat loop walks them, so that a warp iterates max-over-lanes of the
+        //      candidate TOTALS instead of the sum over cells of per-cell maxima
+        SmemAcc sacc{s_pts, s_tab, s_slot, s_delta, bx0, by0, bz0, rx, ry};
+        GlobAcc gacc{gv.blk_rank, gv.fine_start, gv.tp, g.bbits};
+        unsigned* rng = s_rng + tid * NN_RNG_STRIDE;
+#pragma unroll
+        for (int k = 0; k < NN_QPT; ++k) {
+            const bool mine = valid[k] && (npass == 1 || k == pass);
+            const bool search = mine && qc[k].inside && path != 2;
+            const bool staged4 = search && !lg_box_bounded(box[k]);                 // its 4x4x4 cells are part of the region
+            Best b = ub[k];
+            if (path == 0) {
+                unsigned total = 0u; int nr = 0;
+                bool overflow = false;                                               // more ranges than the list holds: not proven
+                if (search) {
+                    const float h2 = g.h * g.h;
+                    const float fx = (float)qc[k].cx + qc[k].dx, fy = (float)qc[k].cy + qc[k].dy, fz = (float)qc[k].cz + qc[k].dz;
+                    const int bxl = qc[k].cx + lg_box_get(box[k], 0), bxh = qc[k].cx + lg_box_get(box[k], 1);
+                    const int byl = max(qc[k].cy + lg_box_get(box[k], 2), 0), byh = min(qc[k].cy + lg_box_get(box[k], 3), g.nf[1] - 1);
+                    const int bzl = max(qc[k].cz + lg_box_get(box[k], 4), 0), bzh = min(qc[k].cz + lg_box_get(box[k], 5), g.nf[2] - 1);
+                    // gap of the query to a cell along one axis, in cells, 0.002 short (rounding of the binning): a lower
+                    // bound of the distance to everything in the cell
+                    auto gap1 = [](float f, int i) { return fmaxf(fmaxf((float)i - f, f - (float)(i + 1)) - 0.002f, 0.0f); };
+                    for (int iz = bzl; iz <= bzh; ++iz) {
+                        const float gz = gap1(fz, iz);
+                        for (int iy = byl; iy <= byh; ++iy) {
+                            const float gy = gap1(fy, iy);
+                            const float lb = (gy * gy + gz * gz) * h2;
+                            if (lb > b.d) continue;                                      // everything in this row is strictly farther
+                            int xa = bxl, xb = bxh;
+                            while (xa < xb && lb + gap1(fx, xa) * gap1(fx, xa) * h2 > b.d) ++xa;
+                            while (xb > xa && lb + gap1(fx, xb) * gap1(fx, xb) * h2 > b.d) --xb;
+                            xa = max(xa, 0); xb = min(xb, g.nf[0] - 1);
+                            const int f = ((iz & 3) << 4) | ((iy & 3) << 2);
+                            for (int ix = xa; ix <= xb;) {
+                                const int bx = ix >> 2, xe = min(xb, (bx << 2) | 3);
+                                const int sl = s_slot[(((iz >> 2) - bz0) * ry + ((iy >> 2) - by0)) * rx + (bx - bx0)];
+                                if (sl >= 0) {
+                                    const unsigned* t = s_tab + sl * NN_TAB_STRIDE;
+                                    const unsigned st0 = t[f + (ix & 3)], en = t[f + (xe & 3) + 1];
+                                    if (en > st0 && nr < NN_RNG_STRIDE - 1) { rng[nr++] = (st0 + (unsigned)s_delta[sl]) | ((en + (unsigned)s_delta[sl]) << 16); total += en - st0; }
+                                    else if (en > st0) overflow = true;
+                                }
+                                ix = xe + 1;
+                            }
+                        }
+                    }
+                }
+                rng[nr] = 0u;
+                const unsigned maxtot = __reduce_max_sync(KSS_FULL, total);
+#ifdef KSS_LG_COUNT
+                { const unsigned sum = __reduce_add_sync(KSS_FULL, total); if (lane == 0) { atomicAdd(&lg_cnt[0], (unsigned long long)sum); atomicAdd(&lg_cnt[1], (unsigned long long)maxtot * 32u); atomicAdd(&lg_cnt[2], 32ull); } }
+#endif
+                unsigned cur = rng[0], j = cur & 0xffffu, e = cur >> 16; int r = 0;
+                unsigned long long bk = ((unsigned long long)__float_as_uint(b.d) << 32) | b.idx;
+                for (unsigned it = 0; it < maxtot; ++it) {
+                    if (it < total) {
+                        if (j == e) { ++r; cur = rng[r]; j = cur & 0xffffu; e = cur >> 16; }
+                        const float4 c = s_pts[j]; ++j;
+                        const unsigned long long ck = ((unsigned long long)__float_as_uint(d2_rn(qx[k], qy[k], qz[k], c.x, c.y, c.z)) << 32) | __float_as_uint(c.w);
+                        bk = ck < bk ? ck : bk;                                         // d2 >= 0: float bits order as integers; ties -> lowest index
+                    }
+                }
+                b.d = __uint_as_float((unsigned)(bk >> 32)); b.idx = (unsigned)bk;
+                if (overflow) box[k] &= ~(1 << 12), b.d = __int_as_float(0x7f800000);   // (the second stage starts afresh)
+            } else if (search) {
+                const int x0 = max(qc[k].cx - 1, 0), x1 = min(qc[k].cx, g.nf[0] - 1);
+                const int y0 = max(qc[k].cy - 1, 0), y1 = min(qc[k].cy, g.nf[1] - 1);
+                const int z0 = max(qc[k].cz - 1, 0), z1 = min(qc[k].cz, g.nf[2] - 1);
+                lg_scan_cells(gacc, x0, x1, y0, y1, z0, z1, qx[k], qy[k], qz[k], b);
+            }
+            if (!mine) continue;
+            const bool ok = search && ((path == 0 && lg_box_bounded(box[k])) || lg_proven(g, qc[k], 1, b.d));
+            if (ok) key[k] = ((unsigned long long)__float_as_uint(b.d) << 32) | b.idx;
+            else {
+                left_at[k] = atomicAdd(&s_nleft, 1);
+                s_lq[left_at[k]] = make_float4(qx[k], qy[k], qz[k], __int_as_float(staged4 ? 1 : 0));
+                s_lub[left_at[k]] = ub[k].d;
+            }
+        }
+        __syncthreads();
+        // ---- (3) second stage, one WARP per left-over query of this pass: lane = one (y, z) row of half the 4x4x4 cells
+        const int nleft = s_nleft;
+        const int first = (npass == 1 || pass == 0) ? 0 : s_n2;                   // entries queued by this pass
+        for (int li = first + warp; li < nleft; li += NN_THREADS / 32) {
+            const float4 q = s_lq[li];
+            bool ok = false;
+            unsigned long long kk = 0xffffffffffffffffull;
+            if (__float_as_int(q.w) == 1) {
+                const QCell c = lg_qcell(g, q.x, q.y, q.z);
+                const int iy = c.cy - 2 + (lane & 3), iz = c.cz - 2 + ((lane >> 2) & 3);
+                const int xa = c.cx - 2 + 2 * (lane >> 4);
+                Best b; b.d = __int_as_float(0x7f800000); b.idx = 0xffffffffu;
+                if (iy >= 0 && iy < g.nf[1] && iz >= 0 && iz < g.nf[2]) {
+                    const int x0 = max(xa, 0), x1 = min(xa + 1, g.nf[0] - 1);
+                    if (path == 0) lg_scan_cells(sacc, x0, x1, iy, iy, iz, iz, q.x, q.y, q.z, b);
+                    else lg_scan_cells(gacc, x0, x1, iy, iy, iz, iz, q.x, q.y, q.z, b);
+                }
+                kk = ((unsigned long long)__float_as_uint(b.d) << 32) | b.idx;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(KSS_FULL, kk, off); kk = o < kk ? o : kk; }
+                ok = lg_proven(g, c, 2, __uint_as_float((unsigned)(kk >> 32)));
+            }
+            if (lane == 0) {
+                if (ok) { s_lq[li].x = __uint_as_float((unsigned)(kk >> 32)); s_lq[li].y = __uint_as_float((unsigned)kk); s_lq[li].w = __int_as_float(2); }
+                else s_pyr[atomicAdd(&s_npyr, 1)] = (unsigned short)li;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_n2 = nleft;
+        // (the next pass's first barrier orders this write and the reuse of the staging area)
     }
-    if (!valid) return;
-    const float d2 = __uint_as_float((unsigned)(key >> 32));
-    if (MODE == 1) corr[o] = make_int2(((double)d2 > max_dist_sqr) ? -1 : (int)(key & 0xffffffffu), __float_as_int(d2));   // A.3
-    else d2out[o] = d2;
-    if (MODE == 0) idx[o] = (int)(key & 0xffffffffu);
+
+    // ---- (4) left-overs that carry a bound (the previous match): one WARP per query reads, from the grid in global memory,
+    //      the cells meeting the cube q +- sqrt(bound), lane = (y, z) row -- exact without proof, like the bounded first
+    //      stage, for isolated points whose neighbour is many cells away.  What has no bound, or a cube of more than
+    //      17 x 17 rows, is left to the box pyramid.
+    {
+        const int n3 = s_npyr;
+        __syncthreads();
+        if (tid == 0) s_npyr = 0;
+        __syncthreads();
+        GlobAcc gacc{gv.blk_rank, gv.fine_start, gv.tp, g.bbits};
+        for (int e3 = warp; e3 < n3; e3 += NN_THREADS / 32) {
+            const int li = s_pyr[e3];
+            const float4 q = s_lq[li];
+            const float ubd = s_lub[li];
+            const float rc = sqrtf(ubd) * g.inv_h * 1.00001f + 0.003f;
+            bool done3 = false;
+            if (rc <= 8.0f) {
+                const float fx = (q.x - g.lo[0]) * g.inv_h, fy = (q.y - g.lo[1]) * g.inv_h, fz = (q.z - g.lo[2]) * g.inv_h;
+                // (a query with a bound this small is within 8 cells of a target, hence of the grid: no overflow)
+                const int xl = max((int)floorf(fx - rc), 0), xh = min((int)floorf(fx + rc), g.nf[0] - 1);
+                const int yl = max((int)floorf(fy - rc), 0), yh = min((int)floorf(fy + rc), g.nf[1] - 1);
+                const int zl = max((int)floorf(fz - rc), 0), zh = min((int)floorf(fz + rc), g.nf[2] - 1);
+                const int ny = yh - yl + 1, nrows = ny * (zh - zl + 1);
+                auto gap1 = [](float f, int i) { return fmaxf(fmaxf((float)i - f, f - (float)(i + 1)) - 0.002f, 0.0f); };
+                const float h2 = g.h * g.h;
+                Best b; b.d = __int_as_float(0x7f800000); b.idx = 0xffffffffu;
+                for (int rw = lane; rw < nrows; rw += 32) {
+                    const int iy = yl + rw % ny, iz = zl + rw / ny;
+                    const float gy = gap1(fy, iy), gz = gap1(fz, iz);
+                    const float lb = (gy * gy + gz * gz) * h2;
+                    if (lb > ubd) continue;
+                    int xa = xl, xb = xh;
+                    while (xa < xb && lb + gap1(fx, xa) * gap1(fx, xa) * h2 > ubd) ++xa;
+                    while (xb > xa && lb + gap1(fx, xb) * gap1(fx, xb) * h2 > ubd) --xb;
+                    lg_scan_cells(gacc, xa, xb, iy, iy, iz, iz, q.x, q.y, q.z, b);
+                }
+                unsigned long long kk = ((unsigned long long)__float_as_uint(b.d) << 32) | b.idx;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(KSS_FULL, kk, off); kk = o < kk ? o : kk; }
+                done3 = nrows > 0 && (unsigned)(kk >> 32) <= __float_as_uint(ubd);       // (the previous match itself is in the cube)
+                if (done3 && lane == 0) { s_lq[li].x = __uint_as_float((unsigned)(kk >> 32)); s_lq[li].y = __uint_as_float((unsigned)kk); s_lq[li].w = __int_as_float(2); }
+            }
+            if (!done3 && lane == 0) s_pyr[NN_QPC + atomicAdd(&s_npyr, 1)] = (unsigned short)li;
+            if (lane == 0) atomicAdd(&lg_dbg2[done3 ? 3 : !(ubd < 3.0e38f) ? 0 : rc > 8.0f ? 1 : 2], 1u);
+        }
+        __syncthreads();
+    }
+    // ---- (5) whatever is left: the box pyramid, 32 queries per warp
+    const int npyr = s_npyr;
+    if (npyr > 0) {
+        float4* slots = s_pts + warp * TILE;                     // the staged points are no longer needed
+        for (int b0 = warp * 32; b0 < npyr; b0 += NN_THREADS) {
+            const int li = s_pyr[NN_QPC + min(b0 + lane, npyr - 1)];      // idle lanes repeat the last query
+            const float4 q = s_lq[li];
+            const unsigned long long kk = lg_warp_nn(py, q.x, q.y, q.z, slots);
+            __syncwarp();
+            if (b0 + lane < npyr) { s_lq[li].x = __uint_as_float((unsigned)(kk >> 32)); s_lq[li].y = __uint_as_float((unsigned)kk); s_lq[li].w = __int_as_float(2); }
+        }
+    }
+    __syncthreads();
+    if (MODE == 1 && tid == 0) {
+        if (s_nleft) atomicAdd(&st->miss[1], (unsigned)s_nleft);
+        if (npyr) atomicAdd(&st->miss[2], (unsigned)npyr);
+        if (s_nglob) atomicAdd(&st->miss[3], (unsigned)s_nglob);
+        if (npass > 1) atomicAdd(&st->miss[4], 1u);
+    }
+
+    // ---- (6) results by ORIGINAL index
+#pragma unroll
+    for (int k = 0; k < NN_QPT; ++k) {
+        if (!valid[k]) continue;
+        if (left_at[k] >= 0) {
+            const float4 r = s_lq[left_at[k]];
+            key[k] = ((unsigned long long)__float_as_uint(r.x) << 32) | __float_as_uint(r.y);
+        }
+        const float d2 = __uint_as_float((unsigned)(key[k] >> 32));
+        const unsigned ti = (unsigned)(key[k] & 0xffffffffu);
+        if (MODE == 1) {
+            if (prev_s) prev_s[base + k * NN_THREADS + tid] = (int)ti;
+            const float4 t = __ldg(gv.t_orig + ti);
+            const int m = ((double)d2 > max_dist_sqr) ? -1 : (int)ti;                       // A.3
+            rec[2 * (size_t)qo[k]] = make_float4(qx[k], qy[k], qz[k], d2);
+            rec[2 * (size_t)qo[k] + 1] = make_float4(t.x, t.y, t.z, __int_as_float(m));
+        } else {
+            d2out[qo[k]] = d2;
+            if (MODE == 0) idx_out[qo[k]] = (int)ti;
+        }
+    }
 }
 
 // ------------------------------------------------------------------ canonical reductions, large n
@@ -740,10 +1066,10 @@ __device__ __forceinline__ bool lg_last_block(unsigned* ticket) {
     return last;
 }
 
-// pass A: per chunk sums of kept source xyz, matched target xyz (float), d2 (double), kept count
+// pass A: per chunk sums of kept source xyz, matched target xyz (float), d2 (double), kept count.
+// rec[2i] = {source xyz, d2}, rec[2i+1] = {target xyz, bits(index or -1)}: a lane's 8 records are two coalesced streams
 __global__ void __launch_bounds__(256)
-lg_passA_kernel(const float4* __restrict__ cur, const float4* __restrict__ t_orig, const int2* __restrict__ corr,
-                int n, int nchunks, float* __restrict__ partA /* [nchunks][6] */,
+lg_passA_kernel(const float4* __restrict__ rec, int n, int nchunks, float* __restrict__ partA /* [nchunks][6] */,
                 double* __restrict__ partD, int* __restrict__ partK, LgState* __restrict__ st) {
     if (st->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -753,25 +1079,19 @@ lg_passA_kernel(const float4* __restrict__ cur, const float4* __restrict__ t_ori
         double dsum = 0.0;
         int k = 0;
         const int i0 = (c << 8) + lane;
-        // all loads of the lane's 8 slots are issued before the (ordered) accumulation
-        int m[8]; float4 sv[8], tv[8]; float dv[8];
+        float4 sv[8], tv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + 32 * u;
-            m[u] = -1;
-            if (i < n) { const int2 cr = corr[i]; m[u] = cr.x; dv[u] = __int_as_float(cr.y); }
+            tv[u].w = __int_as_float(-1);
+            if (i < n) { sv[u] = rec[2 * (size_t)i]; tv[u] = rec[2 * (size_t)i + 1]; }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int i = i0 + 32 * u;
-            if (m[u] >= 0) { sv[u] = cur[i]; tv[u] = __ldg(t_orig + m[u]); }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (m[u] < 0) continue;
+            if (__float_as_int(tv[u].w) < 0) continue;
             a[0] = __fadd_rn(a[0], sv[u].x); a[1] = __fadd_rn(a[1], sv[u].y); a[2] = __fadd_rn(a[2], sv[u].z);
             a[3] = __fadd_rn(a[3], tv[u].x); a[4] = __fadd_rn(a[4], tv[u].y); a[5] = __fadd_rn(a[5], tv[u].z);
-            dsum = __dadd_rn(dsum, (double)dv[u]);
+            dsum = __dadd_rn(dsum, (double)sv[u].w);
             ++k;
         }
 #pragma unroll
@@ -815,9 +1135,8 @@ lg_passA_kernel(const float4* __restrict__ cur, const float4* __restrict__ t_ori
 
 // pass B: sigma partials, then (last CTA) umeyama + accumulate + convergence
 __global__ void __launch_bounds__(256)
-lg_passB_kernel(const float4* __restrict__ cur, const float4* __restrict__ t_orig, const int2* __restrict__ corr,
-                int n, int nchunks, float* __restrict__ partB /* [nchunks][9] */, LgState* __restrict__ st,
-                int max_iter, double rot_thr, double trans_thr, double mse_rel, double mse_abs) {
+lg_passB_kernel(const float4* __restrict__ rec, int n, int nchunks, float* __restrict__ partB /* [nchunks][9] */,
+                LgState* __restrict__ st, int max_iter, double rot_thr, double trans_thr, double mse_rel, double mse_abs) {
     if (st->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * 8 + warp;
@@ -827,17 +1146,16 @@ lg_passB_kernel(const float4* __restrict__ cur, const float4* __restrict__ t_ori
         const float dm0 = st->dmean[0], dm1 = st->dmean[1], dm2 = st->dmean[2];
         float a[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const int i0 = (c << 8) + lane;
-        int m[8]; float4 sv[8], tv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { const int i = i0 + 32 * u; m[u] = i < n ? corr[i].x : -1; }
+        float4 sv[8], tv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + 32 * u;
-            if (m[u] >= 0) { sv[u] = cur[i]; tv[u] = __ldg(t_orig + m[u]); }
+            tv[u].w = __int_as_float(-1);
+            if (i < n) { sv[u] = rec[2 * (size_t)i]; tv[u] = rec[2 * (size_t)i + 1]; }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            if (m[u] < 0) continue;
+            if (__float_as_int(tv[u].w) < 0) continue;
             const float4 s = sv[u], t = tv[u];
             const float sx = sub_(s.x, sm0), sy = sub_(s.y, sm1), sz = sub_(s.z, sm2);
             const float dx = sub_(t.x, dm0), dy = sub_(t.y, dm1), dz = sub_(t.z, dm2);
@@ -936,10 +1254,11 @@ __global__ void lg_state_init_kernel(LgState* st) {
 namespace {
 
 struct Ctx {
-    cudaStream_t st; long long* launches; const DevAlloc& alloc; int err = 0;
+    cudaStream_t st; long long* launches; const DevAlloc& alloc; const char* pfx; int err = 0;
     template <class T> T* get(const char* name, size_t count) {
         void* p = nullptr;
-        int r = alloc(name, count * sizeof(T), &p);
+        char nm[96]; snprintf(nm, sizeof(nm), "%s%s", pfx, name);
+        int r = alloc(nm, count * sizeof(T), &p);
         if (r != KSS_OK) { err = r; return nullptr; }
         return reinterpret_cast<T*>(p);
     }
@@ -947,42 +1266,86 @@ struct Ctx {
     void launched(int k = 1) { *launches += k; }
 };
 
-inline int cell_bits(int n) {
-    int b = (int)std::ceil(std::log2((double)std::max(n, 2)) / 3.0) + 1;
-    return std::min(7, std::max(2, b));
+float grid_hc() {                       // cell size in units of the estimated point spacing (A/B switch)
+    const char* e = getenv("KSS_LG_HC");
+    const float v = e ? (float)atof(e) : 0.0f;
+    return v > 0.0f ? v : 1.3f;
 }
 
-// Morton-cell bucket order of a cloud.  target: tp (padded) + t_orig ; source: perm only.
-int order_cloud(Ctx& c, const char* tag, const double* d_pts, int n, float4* p4, float4* tp, int npad, int* perm) {
-    char nm[64];
-    const int bits = cell_bits(n);
-    const int m = 1 << (3 * bits);
-    snprintf(nm, sizeof(nm), "%s_bb", tag);   unsigned* bb = c.get<unsigned>(nm, 8);
-    snprintf(nm, sizeof(nm), "%s_cell", tag); unsigned* cellid = c.get<unsigned>(nm, n);
-    snprintf(nm, sizeof(nm), "%s_hist", tag); unsigned* hist = c.get<unsigned>(nm, m);
-    snprintf(nm, sizeof(nm), "%s_tot", tag);  unsigned* tot = c.get<unsigned>(nm, 4096);
+// counting sort of a cloud by (Morton block, fine cell) of the grid `geom`: scratch is shared between the target and
+// the query cloud (stream order), only blk_rank / fine_start / n_occ are per cloud
+struct GridScratch {
+    size_t nbmax; int max_bits;
+    unsigned *pkey, *blk_cnt, *blk_base, *fine_cnt;
+    unsigned long long *blk_scan, *blk_tot;
+};
+int grid_scratch(Ctx& c, int n_max, int max_bits, GridScratch* s) {
+    s->max_bits = max_bits; s->nbmax = (size_t)1 << max_bits;
+    const size_t occ_max = std::min((size_t)n_max, s->nbmax);
+    s->pkey = c.get<unsigned>("lg_pkey", n_max);
+    s->blk_cnt = c.get<unsigned>("lg_blk_cnt", s->nbmax);
+    s->blk_scan = c.get<unsigned long long>("lg_blk_scan", s->nbmax);
+    s->blk_tot = c.get<unsigned long long>("lg_blk_tot", s->nbmax / 1024 + 1);
+    s->blk_base = c.get<unsigned>("lg_blk_base", occ_max + 1);
+    s->fine_cnt = c.get<unsigned>("lg_fine_cnt", occ_max * 64);
+    return c.err;
+}
+void grid_sort(Ctx& c, const GridScratch& s, const LgGeom* geom, const float4* p4, int n, unsigned* blk_rank, unsigned* fine_start,
+               int* n_occ, float4* sorted) {
+    const int gp = (n + 255) / 256;
+    const int nsb = (int)(s.nbmax / 1024);
+    cudaMemsetAsync(s.blk_cnt, 0, sizeof(unsigned) * s.nbmax, c.st);
+    lg_bin_kernel<<<gp, 256, 0, c.st>>>(p4, n, geom, s.pkey, s.blk_cnt);
+    lg_bscan1_kernel<<<nsb, 1024, 0, c.st>>>(s.blk_cnt, geom, s.blk_scan, s.blk_tot);
+    lg_bscan2_kernel<<<1, 1024, 0, c.st>>>(s.blk_tot, geom, n_occ);
+    lg_bscan3_kernel<<<nsb, 1024, 0, c.st>>>(s.blk_cnt, s.blk_scan, s.blk_tot, geom, blk_rank, s.blk_base);
+    lg_zero_fine_kernel<<<148 * 4, 256, 0, c.st>>>(n_occ, reinterpret_cast<uint4*>(s.fine_cnt));
+    lg_fine_hist_kernel<<<gp, 256, 0, c.st>>>(s.pkey, n, blk_rank, s.fine_cnt);
+    lg_fine_scan_kernel<<<148 * 4, 256, 0, c.st>>>(n_occ, s.blk_base, s.fine_cnt, fine_start, n);
+    lg_grid_scatter_kernel<<<gp, 256, 0, c.st>>>(p4, n, s.pkey, blk_rank, fine_start, s.fine_cnt, sorted);
+    c.launched(8);
+}
+inline int grid_max_bits(int n_t) { return std::min(22, std::max(12, lg_ceil_log2(std::max(1, n_t)) + 2)); }
+
+// a query cloud in the order of the TARGET's grid (clamped into it): a CTA's 512 consecutive queries then touch a
+// handful of blocks.  p4 = by original index, sorted: w = original index.  Order never affects results.
+int order_queries(Ctx& c, const GridScratch& s, const LgGridView& gv, const double* d_pts, int n, float4* p4, float4* sorted) {
+    const size_t occ_max = std::min((size_t)n, s.nbmax);
+    unsigned* bb = c.get<unsigned>("lg_q_bb", 8);
+    unsigned* blk_rank = c.get<unsigned>("lg_q_blk_rank", s.nbmax);
+    unsigned* fine_start = c.get<unsigned>("lg_q_fine_start", occ_max * 64 + 68);
+    int* n_occ = c.get<int>("lg_q_nocc", 1);
     if (c.err) return c.err;
-    const int nb = (m + 1023) / 1024;
-    cudaMemsetAsync(hist, 0, sizeof(unsigned) * m, c.st);
-    lg_init_bbox_kernel<<<1, 32, 0, c.st>>>(bb);
+    lg_init_bbox_kernel<<<1, 32, 0, c.st>>>(bb, nullptr);
     lg_convert_bbox_kernel<<<(n + 255) / 256, 256, 0, c.st>>>(d_pts, n, p4, bb);
-    lg_hist_kernel<<<(n + 255) / 256, 256, 0, c.st>>>(p4, n, bb, bits, cellid, hist);
-    lg_scan1_kernel<<<nb, 1024, 0, c.st>>>(hist, m, tot);
-    lg_scan2_kernel<<<1, 1024, 0, c.st>>>(tot, nb);
-    lg_scan3_kernel<<<nb, 1024, 0, c.st>>>(hist, m, tot);
-    lg_scatter_kernel<<<(n + 255) / 256, 256, 0, c.st>>>(p4, n, cellid, hist, tp, perm);
-    c.launched(7);
-    if (tp && npad > n) { lg_pad_kernel<<<1, 32, 0, c.st>>>(tp, n, npad); c.launched(); }
+    c.launched(2);
+    grid_sort(c, s, gv.geom, p4, n, blk_rank, fine_start, n_occ, sorted);
     return c.ok() ? KSS_OK : c.err;
 }
 
-int build_pyramid(Ctx& c, const double* d_t, int n_t, Pyramid* py, float4** t_orig_out) {
+// block grid + pyramid of the target, everything enqueued, no host synchronisation
+int build_target(Ctx& c, const double* d_t, int n_t, int n_q_max, Pyramid* py, LgGridView* gv, GridScratch* scr) {
     const int npad = (n_t + 31) / 32 * 32;
+    const int max_bits = grid_max_bits(n_t);
+    if (grid_scratch(c, std::max(n_t, n_q_max), max_bits, scr)) return c.err;
+    const size_t occ_max = std::min((size_t)n_t, scr->nbmax);
     float4* t_orig = c.get<float4>("lg_t_orig", n_t);
     float4* tp = c.get<float4>("lg_tp", npad);
+    unsigned* bb = c.get<unsigned>("lg_t_bb", 8);
+    float* sample = c.get<float>("lg_sample", LG_SAMPLES);
+    LgGeom* geom = c.get<LgGeom>("lg_geom", 1);
+    unsigned* blk_rank = c.get<unsigned>("lg_blk_rank", scr->nbmax);
+    unsigned* fine_start = c.get<unsigned>("lg_fine_start", occ_max * 64 + 68);
+    int* n_occ = c.get<int>("lg_t_nocc", 1);
     if (c.err) return c.err;
-    int r = order_cloud(c, "lg_t", d_t, n_t, t_orig, tp, npad, nullptr);
-    if (r) return r;
+    lg_init_bbox_kernel<<<1, 256, 0, c.st>>>(bb, sample);
+    lg_convert_bbox_kernel<<<(n_t + 255) / 256, 256, 0, c.st>>>(d_t, n_t, t_orig, bb);
+    lg_probe_kernel<<<(n_t + 1023) / 1024, LG_SAMPLES, 0, c.st>>>(t_orig, n_t, sample);
+    lg_geom_kernel<<<1, LG_SAMPLES, 0, c.st>>>(bb, sample, n_t, grid_hc(), max_bits, geom);
+    c.launched(4);
+    grid_sort(c, *scr, geom, t_orig, n_t, blk_rank, fine_start, n_occ, tp);
+    if (npad > n_t) { lg_pad_kernel<<<1, 32, 0, c.st>>>(tp, n_t, npad); c.launched(); }
+    // box pyramid over 32-point tiles of the sorted array
     py->tp = tp;
     int cnt = npad / 32, lev = 0;
     float* boxes[LG_MAX_LEVELS];
@@ -1002,173 +1365,48 @@ int build_pyramid(Ctx& c, const double* d_t, int n_t, Pyramid* py, float4** t_or
     }
     py->nlev = lev;
     for (int l = lev; l < LG_MAX_LEVELS; ++l) { py->cnt[l] = 0; py->pad[l] = 0; py->box[l] = nullptr; }
-    if (t_orig_out) *t_orig_out = t_orig;
+    gv->geom = geom; gv->blk_rank = blk_rank; gv->fine_start = fine_start; gv->tp = tp; gv->t_orig = t_orig; gv->n_t = n_t;
+    if (getenv("KSS_LG_VERBOSE")) {
+        LgGeom h; int no = 0;
+        cudaMemcpyAsync(&h, geom, sizeof(h), cudaMemcpyDeviceToHost, c.st);
+        cudaMemcpyAsync(&no, n_occ, sizeof(int), cudaMemcpyDeviceToHost, c.st);
+        cudaStreamSynchronize(c.st);
+        fprintf(stderr, "[lg] n_t=%d h=%g fine %d,%d,%d blocks %d,%d,%d (table %d) occupied %d -> %.1f points / block\n", n_t, h.h,
+                h.nf[0], h.nf[1], h.nf[2], h.nb[0], h.nb[1], h.nb[2], h.nbp, no, no ? (double)n_t / no : 0.0);
+    }
     return c.ok() ? KSS_OK : c.err;
 }
 
-bool lcg_enabled() { const char* e = getenv("KSS_NO_LCG"); return !(e && e[0] == '1'); }
+inline int nn_grid(int n_q) { return (n_q + NN_QPC - 1) / NN_QPC; }
 
-// large candidate grid over the target's bounding box (device bbox from order_cloud's "<tag>_bb")
-int build_lcg(Ctx& c, const float4* t_orig, int n_t, LcgView* view) {
-    memset(view, 0, sizeof(*view));
-    if (!lcg_enabled()) return KSS_OK;
-    unsigned* bb = c.get<unsigned>("lg_t_bb", 8);
-    if (c.err) return c.err;
-    unsigned hb[6];
-    if (cudaMemcpyAsync(hb, bb, sizeof(hb), cudaMemcpyDeviceToHost, c.st) != cudaSuccess) return KSS_ERR_CUDA;
-    if (cudaStreamSynchronize(c.st) != cudaSuccess) return KSS_ERR_CUDA;
-    auto o2f = [](unsigned u) { unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; memcpy(&f, &v, 4); return f; };
-    float lo[3], ext[3], emax = 0.f;
-    for (int a = 0; a < 3; ++a) { lo[a] = o2f(hb[a]); ext[a] = o2f(hb[3 + a]) - lo[a]; emax = std::max(emax, ext[a]); }
-    if (!(emax > 0.f)) return KSS_OK;                                   // degenerate cloud: pyramid only
-    const float margin = 0.02f * emax + 1e-6f;
-    double vol = 1.0;
-    for (int a = 0; a < 3; ++a) { lo[a] -= margin; ext[a] += 2.f * margin; vol *= std::max(ext[a], 1e-3f * emax); }
-    const double cells_target = std::min(67108864.0, std::max(4096.0, 32.0 * (double)n_t));
-    const double h = std::cbrt(vol / cells_target);
-    LcgGeom g;
-    int L = 0;
-    for (int a = 0; a < 3; ++a) {
-        int b = (int)std::lround(std::log2(std::max(ext[a], 1e-3f * emax) / h));
-        b = std::min(10, std::max(0, b));
-        g.bits[a] = b; L = std::max(L, b);
-        g.lo[a] = lo[a]; g.h[a] = ext[a] / (float)(1 << b); g.inv_h[a] = (float)(1 << b) / ext[a];
-    }
-    g.levels = L + 1;
-    size_t hdr_total = 0;
-    std::vector<size_t> hdr_off(g.levels);
-    for (int l = 0; l < g.levels; ++l) {
-        hdr_off[l] = hdr_total;
-        hdr_total += (size_t)1 << (lcg_bits(g, l, 0) + lcg_bits(g, l, 1) + lcg_bits(g, l, 2));
-    }
-    const size_t finest = (size_t)1 << (g.bits[0] + g.bits[1] + g.bits[2]);
-    // list storage: two ping-pong scratch regions for the intermediate levels (a level only reads its
-    // parent level) and one region for the finest level, which is the only one queries use
-    const unsigned long long cap_s = 112ull * (unsigned long long)n_t + 65536ull;
-    const unsigned long long cap_f = 4ull * finest + 32ull * (unsigned long long)n_t + 65536ull;
-    unsigned long long* hdr = c.get<unsigned long long>("lcg_hdr", hdr_total);
-    // u32 arena: [scratch A | scratch B | persistent far lists of intermediate levels]; float4 arena: finest level
-    unsigned* arena = c.get<unsigned>("lcg_arena", 2 * cap_s);
-    float4* arena4 = c.get<float4>("lcg_arena4", cap_f);
-    unsigned long long* cursor = c.get<unsigned long long>("lcg_cursor", 2);
-    int* ok = c.get<int>("lcg_ok", 2);
-    if (c.err) { c.err = 0; return KSS_OK; }                             // not enough memory: pyramid only
-    const int one = 1;
-    cudaMemcpyAsync(ok, &one, sizeof(int), cudaMemcpyHostToDevice, c.st);
-    unsigned long long prev_cursor = 0;
-    double mean_parent = (double)n_t;
-    // the hierarchy starts at the last level with <= 256 cells, built directly from all targets (one block per cell)
-    int l_start = 0;
-    for (int l = 0; l < g.levels; ++l)
-        if ((lcg_bits(g, l, 0) + lcg_bits(g, l, 1) + lcg_bits(g, l, 2)) <= 8) l_start = l;
-    unsigned* worklist = nullptr; unsigned* nwork = nullptr;
-    for (int l = l_start; l < g.levels; ++l) {
-        LcgLevelArgs a;
-        memset(&a, 0, sizeof(a));
-        a.level = l;
-        for (int k = 0; k < 3; ++k) {
-            a.bits[k] = lcg_bits(g, l, k); a.pbits[k] = l ? lcg_bits(g, l - 1, k) : 0;
-            a.lo[k] = g.lo[k]; a.h[k] = ext[k] / (float)(1 << a.bits[k]);
-        }
-        a.tgt = t_orig; a.n_t = n_t;
-        a.hdr_prev = l ? hdr + hdr_off[l - 1] : nullptr; a.hdr_cur = hdr + hdr_off[l];
-        a.from_all = l == l_start ? 1 : 0;
-        const bool last = l == g.levels - 1;
-        const unsigned long long region = (unsigned long long)(l & 1) * cap_s;
-        a.arena = arena; a.cursor = cursor; a.cap = region + cap_s; a.persist_all = last ? 1 : 0;
-        a.cap_persist = cap_f; a.arena4 = last ? arena4 : nullptr;
-        a.ok = ok;
-        const unsigned long long init2[2] = {region, 0ull};                 // scratch cursor, float4-arena cursor
-        cudaMemcpyAsync(cursor, init2, sizeof(init2), cudaMemcpyHostToDevice, c.st);
-        if (cudaStreamSynchronize(c.st) != cudaSuccess) return KSS_ERR_CUDA;
-        prev_cursor = region;
-        const long long ncells = 1ll << (a.bits[0] + a.bits[1] + a.bits[2]);
-        const int gs_used = (a.from_all || (mean_parent > 1024.0 && ncells <= (1 << 20))) ? 256 : (mean_parent > 40.0 ? 32 : 1);
-        if (gs_used == 256) lcg_level_kernel<256><<<(unsigned)ncells, 256, 0, c.st>>>(a);
-        else if (gs_used == 32) lcg_level_kernel<32><<<(unsigned)((ncells * 32 + 255) / 256), 256, 0, c.st>>>(a);
-        else if (!last) lcg_level_kernel<1><<<(unsigned)((ncells + 255) / 256), 256, 0, c.st>>>(a);
-        else {
-            // finest level, two passes: (1) inherit or enqueue, (2) build the enqueued cells with dense warps
-            if (!worklist) { worklist = c.get<unsigned>("lcg_work", (size_t)ncells * 2); nwork = c.get<unsigned>("lcg_nwork", 2); }
-            if (c.err) { c.err = 0; return KSS_OK; }
-            cudaMemsetAsync(nwork, 0, 8, c.st);
-            LcgLevelArgs p1 = a; p1.worklist_out = worklist; p1.worklist_long = worklist + ncells; p1.nwork_out = nwork;
-            lcg_level_kernel<1><<<(unsigned)((ncells + 255) / 256), 256, 0, c.st>>>(p1);
-            unsigned hn[2] = {0, 0};
-            if (cudaMemcpyAsync(hn, nwork, sizeof(hn), cudaMemcpyDeviceToHost, c.st) != cudaSuccess) return KSS_ERR_CUDA;
-            if (cudaStreamSynchronize(c.st) != cudaSuccess) return KSS_ERR_CUDA;
-            if (getenv("KSS_LCG_VERBOSE"))
-                fprintf(stderr, "[lcg] finest level: %u short + %u long of %lld cells are built, the rest inherit\n", hn[0], hn[1], ncells);
-            if (hn[0]) {
-                LcgLevelArgs p2 = a; p2.worklist = worklist; p2.nwork = hn[0];
-                lcg_level_kernel<1><<<(hn[0] + 255) / 256, 256, 0, c.st>>>(p2);
-            }
-            if (hn[1]) {
-                LcgLevelArgs p3 = a; p3.worklist = worklist + ncells; p3.nwork = hn[1];
-                lcg_level_kernel<32><<<(unsigned)(((unsigned long long)hn[1] * 32 + 255) / 256), 256, 0, c.st>>>(p3);
-            }
-            c.launched(2);
-        }
-        c.launched();
-        unsigned long long cur2[2] = {0, 0};
-        if (cudaMemcpyAsync(cur2, cursor, sizeof(cur2), cudaMemcpyDeviceToHost, c.st) != cudaSuccess) return KSS_ERR_CUDA;
-        if (cudaStreamSynchronize(c.st) != cudaSuccess) return KSS_ERR_CUDA;
-        const unsigned long long cur = last ? cur2[1] + region : cur2[0];
-        mean_parent = (double)(cur - prev_cursor) / (double)ncells;
-        if (getenv("KSS_LCG_VERBOSE")) {
-            static double t_prev = 0; struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
-            const double t_now = ts.tv_sec + 1e-9 * ts.tv_nsec;
-            fprintf(stderr, "[lcg] level %d GS %d bits %d,%d,%d cells %lld entries %llu mean %.2f  (+%.3f ms)\n", l, gs_used, a.bits[0], a.bits[1],
-                    a.bits[2], ncells, cur - prev_cursor, mean_parent, l > l_start ? (t_now - t_prev) * 1e3 : 0.0);
-            t_prev = t_now;
-        }
-        prev_cursor = cur;
-    }
-    int hok = 0;
-    if (cudaMemcpyAsync(&hok, ok, sizeof(int), cudaMemcpyDeviceToHost, c.st) != cudaSuccess) return KSS_ERR_CUDA;
-    if (cudaStreamSynchronize(c.st) != cudaSuccess) return KSS_ERR_CUDA;
-    view->hdr = hdr + hdr_off[g.levels - 1];
-    view->arena4 = arena4;
-    view->arena = arena;
-    view->tgt = t_orig;
-    view->g = g;
-    view->ok = hok;
-    if (getenv("KSS_LCG_VERBOSE"))
-        fprintf(stderr, "[lcg] n_t=%d bits=%d,%d,%d levels=%d cells=%zu caps %llu/%llu finest mean list %.2f ok=%d\n", n_t,
-                g.bits[0], g.bits[1], g.bits[2], g.levels, finest, cap_s, cap_f, mean_parent, hok);
-    return c.ok() ? KSS_OK : c.err;
+template <int MODE>
+void launch_nn(cudaStream_t st, const Pyramid& py, const LgGridView& gv, int n_q, float4* cur_s, const float4* inp_s, int* idx,
+               float* d2, float4* rec, int* prev, LgState* state, double max2) {
+    cudaFuncSetAttribute(lg_nn_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM);
+    lg_nn_kernel<MODE><<<nn_grid(n_q), NN_THREADS, NN_SMEM, st>>>(py, gv, n_q, cur_s, inp_s, idx, d2, rec, prev, state, max2);
 }
-
-inline int nn_grid(int n_q) { return (n_q + LG_WARPS * 32 - 1) / (LG_WARPS * 32); }
 
 }  // namespace
 
 int large_nn_device(cudaStream_t st, long long* launches, const double* d_q, int n_q, const double* d_t, int n_t,
                     int* d_idx, float* d_d2, const DevAlloc& alloc) {
-    Ctx c{st, launches, alloc};
-    Pyramid py;
-    float4* t_orig = nullptr;
-    int r = build_pyramid(c, d_t, n_t, &py, &t_orig);
-    if (r) return r;
-    LcgView lcg;
-    r = build_lcg(c, t_orig, n_t, &lcg);
+    Ctx c{st, launches, alloc, ""};
+    Pyramid py; LgGridView gv; GridScratch scr;
+    int r = build_target(c, d_t, n_t, n_q, &py, &gv, &scr);
     if (r) return r;
     float4* q4 = c.get<float4>("lg_q4", n_q);
-    int* perm = c.get<int>("lg_perm", n_q);
+    float4* qs = c.get<float4>("lg_qs", n_q);
     if (c.err) return c.err;
-    r = order_cloud(c, "lg_q", d_q, n_q, q4, nullptr, 0, perm);
+    r = order_queries(c, scr, gv, d_q, n_q, q4, qs);
     if (r) return r;
-    lg_nn_kernel<0><<<nn_grid(n_q), LG_WARPS * 32, 0, st>>>(py, lcg, t_orig, perm, n_q, q4, nullptr, d_idx, d_d2, nullptr, nullptr, 0.0);
+    launch_nn<0>(st, py, gv, n_q, qs, nullptr, d_idx, d_d2, nullptr, nullptr, nullptr, 0.0);
     c.launched();
     return c.ok() ? KSS_OK : c.err;
 }
 
-int large_metrics_device(cudaStream_t st, long long* launches, const double* d_q, const int* d_cnt_q, int cap_q,
-                         const double* d_t, const int* d_cnt_t, int cap_t, double* d_out3, const DevAlloc& alloc) {
-    // ragged large clouds would need the counts on the host: the batch API passes full capacity here
-    (void)d_cnt_q; (void)d_cnt_t;
-    Ctx c{st, launches, alloc};
-    const int n_q = cap_q, n_t = cap_t;
+int large_metrics_device(cudaStream_t st, long long* launches, const double* d_q, int n_q, const double* d_t, int n_t,
+                         double* d_out3, const DevAlloc& alloc) {
+    Ctx c{st, launches, alloc, ""};
     int* idx = c.get<int>("lg_idx", n_q);
     float* d2 = c.get<float>("lg_d2", n_q);
     if (c.err) return c.err;
@@ -1188,14 +1426,14 @@ int large_metrics_device(cudaStream_t st, long long* launches, const double* d_q
 int large_icp_host(cudaStream_t st, long long* launches, const double* src, int n_s, const double* tgt, int n_t,
                    const kss_icp_params* prm, float T[16], double* fitness, int* iters, int* converged,
                    const DevAlloc& alloc) {
-    Ctx c{st, launches, alloc};
+    Ctx c{st, launches, alloc, ""};
     double* d_s = c.get<double>("lg_in_s", (size_t)n_s * 3);
     double* d_t = c.get<double>("lg_in_t", (size_t)n_t * 3);
     if (c.err) return c.err;
     cudaMemcpyAsync(d_s, src, sizeof(double) * 3 * (size_t)n_s, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_t, tgt, sizeof(double) * 3 * (size_t)n_t, cudaMemcpyHostToDevice, st);
     LargeIcp run;
-    int r = large_icp_prepare(st, launches, d_s, n_s, d_t, n_t, alloc, &run);
+    int r = large_icp_prepare(st, launches, d_s, n_s, d_t, n_t, alloc, &run, "");
     if (r) return r;
     r = large_icp_run(st, launches, &run, prm, 0);
     if (r) return r;
@@ -1204,22 +1442,19 @@ int large_icp_host(cudaStream_t st, long long* launches, const double* src, int 
 
 // ---- reusable pieces (bench.py times large_icp_iterations on a prepared run)
 int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, int n_s, const double* d_t, int n_t,
-                      const DevAlloc& alloc, LargeIcp* run) {
-    Ctx c{st, launches, alloc};
-    Pyramid py;
-    float4* t_orig = nullptr;
-    int r = build_pyramid(c, d_t, n_t, &py, &t_orig);
+                      const DevAlloc& alloc, LargeIcp* run, const char* prefix) {
+    Ctx c{st, launches, alloc, prefix ? prefix : ""};
+    Pyramid py; LgGridView gv; GridScratch scr;
+    int r = build_target(c, d_t, n_t, n_s, &py, &gv, &scr);
     if (r) return r;
-    LcgView lcg;
-    r = build_lcg(c, t_orig, n_t, &lcg);
-    if (r) return r;
-    static_assert(sizeof(LcgView) <= sizeof(run->lcg), "LargeIcp::lcg too small");
-    memcpy(run->lcg, &lcg, sizeof(lcg));
-    float4* inp = c.get<float4>("lg_inp", n_s);
-    float4* cur = c.get<float4>("lg_cur", n_s);
-    int* perm = c.get<int>("lg_perm", n_s);
-    int* idx = c.get<int>("lg_corr", (size_t)n_s * 2);      // int2 {index, d2 bits} per source point
+    static_assert(sizeof(LgGridView) <= sizeof(run->grid), "LargeIcp::grid too small");
+    memcpy(run->grid, &gv, sizeof(gv));
+    float4* q4 = c.get<float4>("lg_q4", n_s);                 // by original index (scratch of the sort)
+    float4* inp = c.get<float4>("lg_inp", n_s);               // sorted input (fitness pass)
+    float4* cur = c.get<float4>("lg_cur", n_s);               // sorted, transformed in place every iteration
+    float4* rec = c.get<float4>("lg_rec", (size_t)n_s * 2);   // per-point records by original index
     float* d2 = c.get<float>("lg_d2", n_s);
+    int* prev = c.get<int>("lg_prev", n_s);                   // last iteration's match per sorted position (-1: none yet)
     const int nchunks = (n_s + 255) / 256;
     float* pA = c.get<float>("lg_partA", (size_t)nchunks * 6);
     float* pB = c.get<float>("lg_partB", (size_t)nchunks * 9);
@@ -1228,15 +1463,16 @@ int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, i
     LgState* state = c.get<LgState>("lg_state", 1);
     double* out3 = c.get<double>("lg_out3", 4);
     if (c.err) return c.err;
-    r = order_cloud(c, "lg_q", d_s, n_s, inp, nullptr, 0, perm);
+    r = order_queries(c, scr, gv, d_s, n_s, q4, inp);
     if (r) return r;
     cudaMemcpyAsync(cur, inp, sizeof(float4) * (size_t)n_s, cudaMemcpyDeviceToDevice, st);
+    cudaMemsetAsync(prev, 0xff, sizeof(int) * (size_t)n_s, st);
     lg_state_init_kernel<<<1, 32, 0, st>>>(state);
     c.launched();
     static_assert(sizeof(Pyramid) <= sizeof(run->pyramid), "LargeIcp::pyramid too small");
     memcpy(run->pyramid, &py, sizeof(py));
     run->n_s = n_s; run->n_t = n_t; run->nchunks = nchunks;
-    run->t_orig = t_orig; run->inp = inp; run->cur = cur; run->perm = perm; run->idx = idx; run->d2 = d2;
+    run->inp = inp; run->cur = cur; run->rec = rec; run->d2 = d2; run->prev = prev;
     run->partA = pA; run->partB = pB; run->partD = pD; run->partK = pK; run->state = state; run->out3 = out3;
     return c.ok() ? KSS_OK : c.err;
 }
@@ -1244,20 +1480,17 @@ int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, i
 // enqueue `count` ICP iterations (each = NN + pass A + pass B); kernels are no-ops once the run is done
 int large_icp_iterations(cudaStream_t st, long long* launches, LargeIcp* run, const kss_icp_params* prm, int count) {
     Pyramid py; memcpy(&py, run->pyramid, sizeof(py));
-    LcgView lcg; memcpy(&lcg, run->lcg, sizeof(lcg));
+    LgGridView gv; memcpy(&gv, run->grid, sizeof(gv));
     LgState* state = (LgState*)run->state;
     const double max2 = prm->max_corr_dist * prm->max_corr_dist;
     const int n = run->n_s, nch = run->nchunks;
     const double mse_abs = prm->fitness_eps < 0.0 ? -1.0 : 1e-12;   // fitness_eps < 0: never converge (steady-state timing)
     for (int k = 0; k < count; ++k) {
         if (run->mark) run->mark(run->mark_user, KSS_STAGE_LARGE_NN, 1);
-        lg_nn_kernel<1><<<nn_grid(n), LG_WARPS * 32, 0, st>>>(py, lcg, (const float4*)run->t_orig, run->perm, n, (float4*)run->cur, nullptr, nullptr,
-                                                              nullptr, (int2*)run->idx, state, max2);
+        launch_nn<1>(st, py, gv, n, (float4*)run->cur, nullptr, nullptr, nullptr, (float4*)run->rec, run->prev, state, max2);
         if (run->mark) { run->mark(run->mark_user, KSS_STAGE_LARGE_NN, 0); run->mark(run->mark_user, KSS_STAGE_LARGE_REDUCE, 1); }
-        lg_passA_kernel<<<(nch + 7) / 8, 256, 0, st>>>((const float4*)run->cur, (const float4*)run->t_orig, (const int2*)run->idx,
-                                                       n, nch, run->partA, run->partD, run->partK, state);
-        lg_passB_kernel<<<(nch + 7) / 8, 256, 0, st>>>((const float4*)run->cur, (const float4*)run->t_orig, (const int2*)run->idx, n,
-                                                       nch, run->partB, state, prm->max_iterations,
+        lg_passA_kernel<<<(nch + 7) / 8, 256, 0, st>>>((const float4*)run->rec, n, nch, run->partA, run->partD, run->partK, state);
+        lg_passB_kernel<<<(nch + 7) / 8, 256, 0, st>>>((const float4*)run->rec, n, nch, run->partB, state, prm->max_iterations,
                                                        1.0 - prm->transformation_eps, prm->transformation_eps,
                                                        prm->fitness_eps, mse_abs);
         if (run->mark) run->mark(run->mark_user, KSS_STAGE_LARGE_REDUCE, 0);
@@ -1280,9 +1513,8 @@ int large_icp_run(cudaStream_t st, long long* launches, LargeIcp* run, const kss
     }
     // getFitnessScore: final * ORIGINAL input, NN, mean d2 in double (A.7)
     Pyramid py; memcpy(&py, run->pyramid, sizeof(py));
-    LcgView lcg; memcpy(&lcg, run->lcg, sizeof(lcg));
-    lg_nn_kernel<2><<<nn_grid(run->n_s), LG_WARPS * 32, 0, st>>>(py, lcg, (const float4*)run->t_orig, run->perm, run->n_s, nullptr, (const float4*)run->inp,
-                                                               nullptr, run->d2, nullptr, state, 0.0);
+    LgGridView gv; memcpy(&gv, run->grid, sizeof(gv));
+    launch_nn<2>(st, py, gv, run->n_s, nullptr, (const float4*)run->inp, nullptr, run->d2, nullptr, nullptr, state, 0.0);
     lg_passF_kernel<<<(run->nchunks + 7) / 8, 256, 0, st>>>(run->d2, run->n_s, run->nchunks, run->partD, nullptr,
                                                             &state->ticketF, run->out3);
     *launches += 2;
@@ -1295,8 +1527,20 @@ int large_icp_result(cudaStream_t st, LargeIcp* run, float T[16], double* fitnes
     if (cudaMemcpyAsync(&h, run->state, sizeof(LgState), cudaMemcpyDeviceToHost, st) != cudaSuccess) return KSS_ERR_CUDA;
     if (cudaMemcpyAsync(o3, run->out3, sizeof(o3), cudaMemcpyDeviceToHost, st) != cudaSuccess) return KSS_ERR_CUDA;
     if (cudaStreamSynchronize(st) != cudaSuccess) return KSS_ERR_CUDA;
-    if (getenv("KSS_LCG_VERBOSE"))
-        fprintf(stderr, "[lcg] grid misses over the run: outside box %u, empty %u, far/long %u, grid off %u (iterations %d)\n", h.miss[1], h.miss[2], h.miss[3], h.miss[4], h.iters);
+    if (getenv("KSS_LG_VERBOSE")) {
+        unsigned d[8]; cudaMemcpyFromSymbol(d, lg_dbg, sizeof(d));
+        unsigned d2[4]; cudaMemcpyFromSymbol(d2, lg_dbg2, sizeof(d2));
+        fprintf(stderr, "[lg] third stage: no bound %u, cube too large %u, failed %u, resolved %u\n", d2[0], d2[1], d2[2], d2[3]);
+        fprintf(stderr, "[lg] unstaged half-passes by reason: box %u, touched blocks %u, points %u, occupied %u; sums: points %u occupied %u touched %u box %u\n",
+                d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
+    }
+#ifdef KSS_LG_COUNT
+    { unsigned long long c4[4]; cudaMemcpyFromSymbol(c4, lg_cnt, sizeof(c4));
+      fprintf(stderr, "[lg] first stage: %.2f candidates per query, %.2f lane slots per query (over %llu query slots)\n", (double)c4[0] / c4[2], (double)c4[1] / c4[2], c4[2]); }
+#endif
+    if (getenv("KSS_LG_VERBOSE"))
+        fprintf(stderr, "[lg] over the run: %u second-stage searches, %u pyramid fallbacks, %u CTAs on global tables (iterations %d)\n",
+                h.miss[1], h.miss[2], h.miss[3], h.iters);
     if (T) for (int i = 0; i < 16; ++i) T[i] = h.fin[i];
     if (fitness) *fitness = o3[0];
     if (iters) *iters = h.iters;

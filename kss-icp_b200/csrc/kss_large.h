@@ -1,6 +1,7 @@
-// kss_large.h -- clouds beyond one CTA's shared memory (> 2048 points): hierarchical
-// Morton-tile NN, canonical-order reductions and the full-resolution ICP loop
+// kss_large.h -- clouds beyond one CTA's shared memory (> 2048 points): block-grid NN with TMA-staged
+// target tiles (box pyramid as exact fallback), canonical-order reductions and the full-resolution ICP loop
 // (shapeRegistration_ICP(int iter), KSS_ICP.hpp:133-183; PCR_QM at full resolution).
+// Nothing here synchronises with the host except large_icp_run's convergence poll and large_icp_result.
 #pragma once
 #include <cuda_runtime.h>
 #include <functional>
@@ -15,25 +16,27 @@ typedef std::function<int(const char* name, size_t bytes, void** out)> DevAlloc;
 int large_nn_device(cudaStream_t st, long long* launches, const double* d_q, int n_q, const double* d_t, int n_t,
                     int* d_idx, float* d_d2, const DevAlloc& alloc);
 
-// PCR_QM (registrationMeasure.hpp:47-98) for one pair; counts are device ints, caps host ints
-int large_metrics_device(cudaStream_t st, long long* launches, const double* d_q, const int* d_cnt_q, int cap_q,
-                         const double* d_t, const int* d_cnt_t, int cap_t, double* d_out3, const DevAlloc& alloc);
+// PCR_QM (registrationMeasure.hpp:47-98) for one pair of n_q / n_t points (device pointers, host counts)
+int large_metrics_device(cudaStream_t st, long long* launches, const double* d_q, int n_q, const double* d_t, int n_t,
+                         double* d_out3, const DevAlloc& alloc);
 
 // a prepared full-resolution ICP run (device buffers owned by the context's allocator)
 struct LargeIcp {
     alignas(8) unsigned char pyramid[160];
-    alignas(8) unsigned char lcg[160];
+    alignas(8) unsigned char grid[64];
     int n_s = 0, n_t = 0, nchunks = 0;
-    void *t_orig = nullptr, *inp = nullptr, *cur = nullptr, *state = nullptr;
-    int *perm = nullptr, *idx = nullptr, *partK = nullptr;
+    void *inp = nullptr, *cur = nullptr, *rec = nullptr, *state = nullptr;
+    int *partK = nullptr, *prev = nullptr;
     float *d2 = nullptr, *partA = nullptr, *partB = nullptr;
     double *partD = nullptr, *out3 = nullptr;
     // optional stage marks (CUDA-event timing by the context): mark(user, KSS_STAGE_*, begin?1:0)
     void (*mark)(void* user, int stage, int begin) = nullptr;
     void* mark_user = nullptr;
 };
+// `prefix` names the run's buffers: a prepared run that outlives the call (kss_icp_large_begin / _iterate / _end) gets
+// its own, so that other large-path calls on the same context cannot regrow them underneath it
 int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, int n_s, const double* d_t, int n_t,
-                      const DevAlloc& alloc, LargeIcp* run);
+                      const DevAlloc& alloc, LargeIcp* run, const char* prefix);
 int large_icp_iterations(cudaStream_t st, long long* launches, LargeIcp* run, const kss_icp_params* prm, int count);
 int large_icp_run(cudaStream_t st, long long* launches, LargeIcp* run, const kss_icp_params* prm, int poll);
 int large_icp_result(cudaStream_t st, LargeIcp* run, float T[16], double* fitness, int* iters, int* converged);

@@ -76,3 +76,61 @@ def test_register_with_large_full_clouds(ctx, okss, pkg):
     assert np.array_equal(np.asarray(r["T"]).reshape(4, 4), o["T"])
     assert int(r["winner"]) == o["winner"]
     assert np.allclose([r["mse"], r["rmse"], r["mae"]], [o["mse"], o["rmse"], o["mae"]], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("case", ["identical", "line", "two_clusters", "plane_dup", "tiny_spread", "outside"])
+def test_large_nn_degenerate_geometry(ctx, okss, case):
+    """the block grid's cell size comes from a nearest-neighbour probe of the target: degenerate targets (zero extent,
+    collinear, clusters far apart, duplicated sheets) and queries outside the target's box must stay exact"""
+    rng = np.random.default_rng(abs(hash(case)) % 1000)
+    n = 6000
+    if case == "identical":
+        t = np.tile(np.array([[0.25, -1.5, 3.0]]), (n, 1)); q = _cloud(rng, 3000) + t[0]
+    elif case == "line":
+        t = np.zeros((n, 3)); t[:, 0] = rng.uniform(-2, 2, n); q = _cloud(rng, 3000, 0.3); q[:, 0] *= 8
+    elif case == "two_clusters":
+        t = np.concatenate([_cloud(rng, n // 2, 0.01), _cloud(rng, n // 2, 0.01) + 50.0]); q = np.concatenate([_cloud(rng, 1500, 0.02), _cloud(rng, 1500, 20.0) + 25.0])
+    elif case == "plane_dup":
+        a = rng.uniform(-1, 1, (n // 2, 3)); a[:, 2] = 0.0
+        t = np.concatenate([a, a]); q = a[:3000] + rng.normal(size=(3000, 3)) * 0.002
+    elif case == "tiny_spread":
+        t = _cloud(rng, n, 1e-6) + 1000.0; q = _cloud(rng, 3000, 2e-6) + 1000.0
+    else:
+        t = rng.uniform(0, 1, (n, 3)); q = rng.uniform(-3, 4, (3000, 3))
+    t = t.astype(np.float32).astype(np.float64); q = q.astype(np.float32).astype(np.float64)
+    idx, d2 = ctx.nn_search(q, t)
+    oi, od = okss.nn(q, t, okss.NN_KDTREE)
+    assert np.array_equal(d2, od)
+    assert np.array_equal(idx, oi)
+
+
+def test_large_nn_grid_ties(ctx, okss):
+    """a lattice target with queries on cell centres: 8-way fp32 ties across fine cells and blocks of the grid"""
+    g = np.stack(np.meshgrid(np.arange(20.0), np.arange(20.0), np.arange(20.0)), -1).reshape(-1, 3) / 16.0
+    rng = np.random.default_rng(5)
+    t = g[rng.permutation(len(g))]
+    q = g[::2] + 1.0 / 32.0
+    idx, d2 = ctx.nn_search(q, t)
+    oi, od = okss.nn(q, t, okss.NN_BRUTE)
+    assert np.array_equal(d2, od) and np.array_equal(idx, oi)
+
+
+def test_register_batch_ragged_large_full_clouds(ctx, okss, pkg):
+    """ragged batch whose FULL clouds take the large path (> 2048 points): final apply + PCR_QM must honour the per-pair
+    counts (rows beyond a pair's count are padding)"""
+    rng = np.random.default_rng(11)
+    P, cap = 3, 5000
+    cS = np.array([5000, 3100, 2500], np.int32); cT = np.array([4200, 5000, 2050], np.int32)
+    fs = np.zeros((P, cap, 3)); ft = np.zeros((P, cap, 3)); ss = []; st = []
+    for p in range(P):
+        pr = pkg.synth.modelnet_pair(60 + p, n_full=cap)
+        fs[p, :cS[p]] = pr["full_s"][:cS[p]]; ft[p, :cT[p]] = pr["full_t"][:cT[p]]
+        fs[p, cS[p]:] = 1e3; ft[p, cT[p]:] = -1e3                       # padding that would wreck the metrics if it were used
+        ss.append(pkg.synth.simplify(fs[p, :cS[p]], 1000, rng)); st.append(pkg.synth.simplify(ft[p, :cT[p]], 1000, rng))
+    ss = np.stack(ss); st = np.stack(st)
+    res, pa = ctx.register_batch(ss, st, fs, ft, counts=(None, None, cS, cT), want_points=True)
+    for p in range(P):
+        o = okss.register(ss[p], st[p], fs[p, :cS[p]], ft[p, :cT[p]], sum_order=okss.SUM_CANON256, want_points=True)
+        assert np.array_equal(np.asarray(res[p]["T"]).reshape(4, 4), o["T"]) and int(res[p]["winner"]) == o["winner"]
+        assert np.array_equal(pa[p, :cS[p]], o["point_align"])
+        assert np.allclose([res[p]["mse"], res[p]["rmse"], res[p]["mae"]], [o["mse"], o["rmse"], o["mae"]], rtol=1e-12, atol=0)
