@@ -57,8 +57,10 @@ struct LgGridView {
     const unsigned* fine_start;      // [n_occ * 64 + 68] absolute start offset of every fine cell (ends with n_t)
     const float4* tp;                // sorted targets
     const float4* t_orig;            // targets by original index
+    const unsigned* lut;             // [3][1024] per-axis bit spreads of the Morton-compact block code: code = x | y | z
     int n_t;
 };
+constexpr int LG_LUT = 1024;         // blocks per axis are at most ~1001 (lg_geom_kernel)
 
 // ------------------------------------------------------------------ build kernels
 __global__ void lg_init_bbox_kernel(unsigned* bb, float* sample_d2) {
@@ -161,6 +163,19 @@ __device__ __forceinline__ unsigned lg_block_code(int bx, int by, int bz, const 
         if (k < bbits[2]) { code |= (unsigned)((bz >> k) & 1) << sh; ++sh; }
     }
     return code;
+}
+
+// per-axis tables so that the block code is three loads and two ORs in the search kernels
+__global__ void __launch_bounds__(256)
+lg_lut_kernel(const LgGeom* __restrict__ gp, unsigned* __restrict__ lut) {
+    const LgGeom g = *gp;
+    for (int i = threadIdx.x; i < 3 * LG_LUT; i += blockDim.x) {
+        const int a = i / LG_LUT, v = i % LG_LUT;
+        lut[i] = lg_block_code(a == 0 ? v : 0, a == 1 ? v : 0, a == 2 ? v : 0, g.bbits);
+    }
+}
+__device__ __forceinline__ unsigned lg_code(const unsigned* __restrict__ lut, int bx, int by, int bz) {
+    return __ldg(lut + bx) | __ldg(lut + LG_LUT + by) | __ldg(lut + 2 * LG_LUT + bz);
 }
 
 __global__ void __launch_bounds__(256)
@@ -415,6 +430,8 @@ struct LgState {
     int iters, done, converged, kept, apply_T;
     unsigned ticketA, ticketB, ticketF;
     unsigned miss[5];            // diagnostics: [1] second-stage searches, [2] pyramid fallbacks, [3] passes on global tables, [4] CTAs split in two passes
+    unsigned n_unres;            // queries of this iteration the refine kernel left to the general kernels
+    unsigned pad_;
 };
 
 // ------------------------------------------------------------------ staged grid search
@@ -478,9 +495,9 @@ struct SmemAcc {
     }
 };
 struct GlobAcc {
-    const unsigned* blk_rank; const unsigned* fine_start; const float4* tp; const int* bbits;
+    const unsigned* blk_rank; const unsigned* fine_start; const float4* tp; const unsigned* lut;
     __device__ __forceinline__ bool block(int bx, int by, int bz, const unsigned*& t, const float4*& p) const {
-        const unsigned r = __ldg(blk_rank + lg_block_code(bx, by, bz, bbits));
+        const unsigned r = __ldg(blk_rank + lg_code(lut, bx, by, bz));
         if (r == LG_EMPTY) return false;
         t = fine_start + (size_t)r * 64;
         p = tp;
@@ -561,6 +578,7 @@ template <int MODE>
 __global__ void __launch_bounds__(NN_THREADS, KSS_NN_CTAS)
 lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s, const float4* __restrict__ inp_s,
              int* __restrict__ idx_out, float* __restrict__ d2out, float4* __restrict__ rec, int* __restrict__ prev_s,
+             const unsigned char* __restrict__ flag /* MODE 1 after lg_refine_kernel: 1 = still to do (already transformed) */,
              LgState* __restrict__ st, double max_dist_sqr) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     float4* s_pts = reinterpret_cast<float4*>(dyn_smem);
@@ -582,6 +600,7 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s, con
     __shared__ int s_nleft, s_npyr, s_n2, s_nglob, s_nreg;
 
     if (MODE == 1 && st->done) return;
+    if (MODE == 1 && flag && st->n_unres <= (unsigned)n_q / 8u) return;       // few left: lg_left_kernel takes them one warp each
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < (int)(sizeof(LgGeom) / 4)) reinterpret_cast<int*>(&g)[tid] = reinterpret_cast<const int*>(gv.geom)[tid];
     if (MODE != 0 && tid < 16) T[tid] = MODE == 1 ? st->Tk[tid] : st->fin[tid];
@@ -596,11 +615,11 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s, con
                                                  // its distance bounds the search before a single cell is read
     unsigned long long key[NN_QPT];
     int left_at[NN_QPT];
-    const bool applyT = MODE == 1 && st->apply_T;
+    const bool applyT = MODE == 1 && st->apply_T && !flag;
 #pragma unroll
     for (int k = 0; k < NN_QPT; ++k) {
         const int pos = base + k * NN_THREADS + tid;
-        valid[k] = pos < n_q;
+        valid[k] = pos < n_q && (!(MODE == 1 && flag) || flag[pos]);
         qx[k] = qy[k] = qz[k] = 0.0f; qo[k] = 0u;
         qc[k].inside = false; qc[k].cx = qc[k].cy = qc[k].cz = 0; qc[k].m = 1.0f;
         key[k] = 0xffffffffffffffffull; left_at[k] = -1;
@@ -703,7 +722,7 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s, con
         const int nreg = s_nreg;
         if (tid < nreg) {                                        // ranks and point ranges of the touched blocks, one thread each
             const int li = s_list[tid];
-            const unsigned r = __ldg(gv.blk_rank + lg_block_code(bx0 + li % rx, by0 + (li / rx) % ry, bz0 + li / (rx * ry), g.bbits));
+            const unsigned r = __ldg(gv.blk_rank + lg_code(gv.lut, bx0 + li % rx, by0 + (li / rx) % ry, bz0 + li / (rx * ry)));
             unsigned q0 = 0u, cnt = 0u;
             if (r != LG_EMPTY) { q0 = __ldg(gv.fine_start + (size_t)r * 64); cnt = __ldg(gv.fine_start + (size_t)r * 64 + 64) - q0; }
             s_rank[tid] = r; s_p0[tid] = q0; s_cnt[tid] = cnt;
@@ -765,7 +784,7 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s, con
         //      the rest go to a per-thread list and ONE flat loop walks them, so that a warp iterates max-over-lanes of the
         //      candidate TOTALS instead of the sum over cells of per-cell maxima
         SmemAcc sacc{s_pts, s_tab, s_slot, s_delta, bx0, by0, bz0, rx, ry};
-        GlobAcc gacc{gv.blk_rank, gv.fine_start, gv.tp, g.bbits};
+        GlobAcc gacc{gv.blk_rank, gv.fine_start, gv.tp, gv.lut};
         unsigned* rng = s_rng + tid * NN_RNG_STRIDE;
 #pragma unroll
         for (int k = 0; k < NN_QPT; ++k) {
@@ -884,7 +903,7 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s, con
         __syncthreads();
         if (tid == 0) s_npyr = 0;
         __syncthreads();
-        GlobAcc gacc{gv.blk_rank, gv.fine_start, gv.tp, g.bbits};
+        GlobAcc gacc{gv.blk_rank, gv.fine_start, gv.tp, gv.lut};
         for (int e3 = warp; e3 < n3; e3 += NN_THREADS / 32) {
             const int li = s_pyr[e3];
             const float4 q = s_lq[li];
@@ -963,6 +982,146 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s, con
             if (MODE == 0) idx_out[qo[k]] = (int)ti;
         }
     }
+}
+
+// Steady-state fast path of the ICP iteration: nothing is staged.  A query that carries last iteration's match holds a
+// bound before a single cell is read; when the cube q +- sqrt(bound) meets at most 3 x 3 rows of cells, the thread reads
+// exactly those cells from the grid in global memory (the working set is L2-resident: points 16 B, tables, ranks) and is
+// done -- exact without proof (every target that can beat or tie the bound lies in the cube).  Everything else is
+// flagged, counted and queued for the general kernels (lg_nn_kernel<1> when many, lg_left_kernel when few).
+__global__ void __launch_bounds__(256)
+lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur_s, float4* __restrict__ rec, int* __restrict__ prev_s,
+                 unsigned char* __restrict__ flag, int* __restrict__ worklist, LgState* __restrict__ st, double max_dist_sqr) {
+    __shared__ LgGeom g;
+    __shared__ float T[16];
+    if (st->done) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < (int)(sizeof(LgGeom) / 4)) reinterpret_cast<int*>(&g)[tid] = reinterpret_cast<const int*>(gv.geom)[tid];
+    if (tid < 16) T[tid] = st->Tk[tid];
+    __syncthreads();
+    const int pos = blockIdx.x * blockDim.x + tid;
+    const bool valid = pos < n_q;
+    bool unres = false;
+    if (valid) {
+        const int pv = prev_s[pos];
+        float4 tprev = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pv >= 0) tprev = __ldg(gv.t_orig + pv);
+        const float4 p = cur_s[pos];
+        float x = p.x, y = p.y, z = p.z;
+        if (st->apply_T) {
+            xform_point(T, p.x, p.y, p.z, x, y, z);                  // transformCloud of the previous iteration (A.5)
+            cur_s[pos] = make_float4(x, y, z, p.w);
+        }
+        unres = true;
+        if (pv >= 0) {
+            Best b; b.d = d2_rn(x, y, z, tprev.x, tprev.y, tprev.z); b.idx = (unsigned)pv;
+            const float ubd = b.d;
+            const float rc = sqrtf(ubd) * g.inv_h * 1.00001f + 0.003f;
+            if (rc <= 1.6f) {                                        // (false for NaN too)
+                const float fx = (x - g.lo[0]) * g.inv_h, fy = (y - g.lo[1]) * g.inv_h, fz = (z - g.lo[2]) * g.inv_h;
+                // the previous match is a target inside the grid and at most 1.6 cells away: no integer overflow
+                const int xl = max((int)floorf(fx - rc), 0), xh = min((int)floorf(fx + rc), g.nf[0] - 1);
+                const int yl = max((int)floorf(fy - rc), 0), yh = min((int)floorf(fy + rc), g.nf[1] - 1);
+                const int zl = max((int)floorf(fz - rc), 0), zh = min((int)floorf(fz + rc), g.nf[2] - 1);
+                auto gap1 = [](float f, int i) { return fmaxf(fmaxf((float)i - f, f - (float)(i + 1)) - 0.002f, 0.0f); };
+                const float h2 = g.h * g.h;
+                GlobAcc gacc{gv.blk_rank, gv.fine_start, gv.tp, gv.lut};
+                for (int iz = zl; iz <= zh; ++iz) {
+                    const float gz = gap1(fz, iz);
+                    for (int iy = yl; iy <= yh; ++iy) {
+                        const float gy = gap1(fy, iy);
+                        const float lb = (gy * gy + gz * gz) * h2;
+                        if (lb > ubd) continue;                              // everything in this row is strictly farther
+                        int xa = xl, xb = xh;
+                        while (xa < xb && lb + gap1(fx, xa) * gap1(fx, xa) * h2 > ubd) ++xa;
+                        while (xb > xa && lb + gap1(fx, xb) * gap1(fx, xb) * h2 > ubd) --xb;
+                        lg_scan_cells(gacc, xa, xb, iy, iy, iz, iz, x, y, z, b);
+                    }
+                }
+                unres = false;
+                const float4 t = b.idx == (unsigned)pv ? tprev : __ldg(gv.t_orig + b.idx);
+                const unsigned orig = __float_as_uint(p.w);
+                const int m = ((double)b.d > max_dist_sqr) ? -1 : (int)b.idx;                // A.3
+                prev_s[pos] = (int)b.idx;
+                rec[2 * (size_t)orig] = make_float4(x, y, z, b.d);
+                rec[2 * (size_t)orig + 1] = make_float4(t.x, t.y, t.z, __int_as_float(m));
+            }
+        }
+        flag[pos] = unres ? 1 : 0;
+    }
+    const unsigned bal = __ballot_sync(KSS_FULL, valid && unres);
+    if (bal) {
+        unsigned at = 0u;
+        if (lane == 0) at = atomicAdd(&st->n_unres, (unsigned)__popc(bal));
+        at = __shfl_sync(KSS_FULL, at, 0);
+        if (valid && unres) worklist[at + __popc(bal & ((1u << lane) - 1u))] = pos;
+    }
+}
+
+// The few queries lg_refine_kernel could not finish, one WARP each (persistent grid over the work list): a query with a
+// bound reads the cells meeting the cube q +- sqrt(bound) (lane = row, up to 17 x 17 rows); the rest goes to the pyramid.
+__global__ void __launch_bounds__(256)
+lg_left_kernel(Pyramid py, LgGridView gv, int n_q, const float4* __restrict__ cur_s, float4* __restrict__ rec,
+               int* __restrict__ prev_s, const int* __restrict__ worklist, LgState* __restrict__ st, double max_dist_sqr) {
+    __shared__ LgGeom g;
+    __shared__ float4 slots[8][TILE];
+    if (st->done) return;
+    const unsigned nu = st->n_unres;
+    if (nu > (unsigned)n_q / 8u) return;                             // many: lg_nn_kernel<1> staged them
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < (int)(sizeof(LgGeom) / 4)) reinterpret_cast<int*>(&g)[tid] = reinterpret_cast<const int*>(gv.geom)[tid];
+    __syncthreads();
+    GlobAcc gacc{gv.blk_rank, gv.fine_start, gv.tp, gv.lut};
+    const unsigned nw = gridDim.x * (blockDim.x >> 5);
+    unsigned n_pyr = 0u;
+    for (unsigned e = blockIdx.x * (blockDim.x >> 5) + warp; e < nu; e += nw) {
+        const int pos = worklist[e];
+        const float4 q = cur_s[pos];
+        const int pv = prev_s[pos];
+        unsigned long long kk = 0xffffffffffffffffull;
+        bool done = false;
+        if (pv >= 0) {
+            const float4 tp0 = __ldg(gv.t_orig + pv);
+            const float ubd = d2_rn(q.x, q.y, q.z, tp0.x, tp0.y, tp0.z);
+            const float rc = sqrtf(ubd) * g.inv_h * 1.00001f + 0.003f;
+            if (rc <= 8.0f) {
+                const float fx = (q.x - g.lo[0]) * g.inv_h, fy = (q.y - g.lo[1]) * g.inv_h, fz = (q.z - g.lo[2]) * g.inv_h;
+                const int xl = max((int)floorf(fx - rc), 0), xh = min((int)floorf(fx + rc), g.nf[0] - 1);
+                const int yl = max((int)floorf(fy - rc), 0), yh = min((int)floorf(fy + rc), g.nf[1] - 1);
+                const int zl = max((int)floorf(fz - rc), 0), zh = min((int)floorf(fz + rc), g.nf[2] - 1);
+                const int ny = yh - yl + 1, nrows = ny * (zh - zl + 1);
+                auto gap1 = [](float f, int i) { return fmaxf(fmaxf((float)i - f, f - (float)(i + 1)) - 0.002f, 0.0f); };
+                const float h2 = g.h * g.h;
+                Best b; b.d = ubd; b.idx = (unsigned)pv;
+                for (int rw = lane; rw < nrows; rw += 32) {
+                    const int iy = yl + rw % ny, iz = zl + rw / ny;
+                    const float gy = gap1(fy, iy), gz = gap1(fz, iz);
+                    const float lb = (gy * gy + gz * gz) * h2;
+                    if (lb > ubd) continue;
+                    int xa = xl, xb = xh;
+                    while (xa < xb && lb + gap1(fx, xa) * gap1(fx, xa) * h2 > ubd) ++xa;
+                    while (xb > xa && lb + gap1(fx, xb) * gap1(fx, xb) * h2 > ubd) --xb;
+                    lg_scan_cells(gacc, xa, xb, iy, iy, iz, iz, q.x, q.y, q.z, b);
+                }
+                kk = ((unsigned long long)__float_as_uint(b.d) << 32) | b.idx;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(KSS_FULL, kk, off); kk = o < kk ? o : kk; }
+                done = true;
+            }
+        }
+        if (!done) { kk = lg_warp_nn(py, q.x, q.y, q.z, slots[warp]); ++n_pyr; }       // every lane carries the same query
+        if (lane == 0) {
+            const float d2 = __uint_as_float((unsigned)(kk >> 32));
+            const unsigned ti = (unsigned)kk;
+            const float4 t = __ldg(gv.t_orig + ti);
+            const unsigned orig = __float_as_uint(q.w);
+            const int m = ((double)d2 > max_dist_sqr) ? -1 : (int)ti;                       // A.3
+            prev_s[pos] = (int)ti;
+            rec[2 * (size_t)orig] = make_float4(q.x, q.y, q.z, d2);
+            rec[2 * (size_t)orig + 1] = make_float4(t.x, t.y, t.z, __int_as_float(m));
+        }
+    }
+    if (lane == 0 && n_pyr) atomicAdd(&st->miss[2], n_pyr);
 }
 
 // ------------------------------------------------------------------ canonical reductions, large n
@@ -1122,6 +1281,7 @@ lg_passA_kernel(const float4* __restrict__ rec, int n, int nchunks, float* __res
     if ((threadIdx.x & 31) == 0 && k) atomicAdd(&kept_s, k);
     __syncthreads();
     if (threadIdx.x == 0) {
+        st->n_unres = 0u;                                            // (all search kernels of this iteration are done)
         const int cnt = kept_s;
         st->kept = cnt;
         if (cnt >= 3) {
@@ -1247,6 +1407,7 @@ __global__ void lg_state_init_kernel(LgState* st) {
         st->prev_mse = DBL_MAX; st->mse = 0; st->fitness = 0; st->iters = 0; st->done = 0; st->converged = 0;
         st->kept = 0; st->apply_T = 0; st->ticketA = st->ticketB = st->ticketF = 0u; st->one_over_n = 0.f;
         for (int i = 0; i < 5; ++i) st->miss[i] = 0u;
+        st->n_unres = 0u; st->pad_ = 0u;
     }
 }
 
@@ -1337,12 +1498,14 @@ int build_target(Ctx& c, const double* d_t, int n_t, int n_q_max, Pyramid* py, L
     unsigned* blk_rank = c.get<unsigned>("lg_blk_rank", scr->nbmax);
     unsigned* fine_start = c.get<unsigned>("lg_fine_start", occ_max * 64 + 68);
     int* n_occ = c.get<int>("lg_t_nocc", 1);
+    unsigned* lut = c.get<unsigned>("lg_lut", 3 * LG_LUT);
     if (c.err) return c.err;
     lg_init_bbox_kernel<<<1, 256, 0, c.st>>>(bb, sample);
     lg_convert_bbox_kernel<<<(n_t + 255) / 256, 256, 0, c.st>>>(d_t, n_t, t_orig, bb);
     lg_probe_kernel<<<(n_t + 1023) / 1024, LG_SAMPLES, 0, c.st>>>(t_orig, n_t, sample);
     lg_geom_kernel<<<1, LG_SAMPLES, 0, c.st>>>(bb, sample, n_t, grid_hc(), max_bits, geom);
-    c.launched(4);
+    lg_lut_kernel<<<1, 256, 0, c.st>>>(geom, lut);
+    c.launched(5);
     grid_sort(c, *scr, geom, t_orig, n_t, blk_rank, fine_start, n_occ, tp);
     if (npad > n_t) { lg_pad_kernel<<<1, 32, 0, c.st>>>(tp, n_t, npad); c.launched(); }
     // box pyramid over 32-point tiles of the sorted array
@@ -1365,7 +1528,7 @@ int build_target(Ctx& c, const double* d_t, int n_t, int n_q_max, Pyramid* py, L
     }
     py->nlev = lev;
     for (int l = lev; l < LG_MAX_LEVELS; ++l) { py->cnt[l] = 0; py->pad[l] = 0; py->box[l] = nullptr; }
-    gv->geom = geom; gv->blk_rank = blk_rank; gv->fine_start = fine_start; gv->tp = tp; gv->t_orig = t_orig; gv->n_t = n_t;
+    gv->geom = geom; gv->blk_rank = blk_rank; gv->fine_start = fine_start; gv->tp = tp; gv->t_orig = t_orig; gv->lut = lut; gv->n_t = n_t;
     if (getenv("KSS_LG_VERBOSE")) {
         LgGeom h; int no = 0;
         cudaMemcpyAsync(&h, geom, sizeof(h), cudaMemcpyDeviceToHost, c.st);
@@ -1381,9 +1544,9 @@ inline int nn_grid(int n_q) { return (n_q + NN_QPC - 1) / NN_QPC; }
 
 template <int MODE>
 void launch_nn(cudaStream_t st, const Pyramid& py, const LgGridView& gv, int n_q, float4* cur_s, const float4* inp_s, int* idx,
-               float* d2, float4* rec, int* prev, LgState* state, double max2) {
+               float* d2, float4* rec, int* prev, const unsigned char* flag, LgState* state, double max2) {
     cudaFuncSetAttribute(lg_nn_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM);
-    lg_nn_kernel<MODE><<<nn_grid(n_q), NN_THREADS, NN_SMEM, st>>>(py, gv, n_q, cur_s, inp_s, idx, d2, rec, prev, state, max2);
+    lg_nn_kernel<MODE><<<nn_grid(n_q), NN_THREADS, NN_SMEM, st>>>(py, gv, n_q, cur_s, inp_s, idx, d2, rec, prev, flag, state, max2);
 }
 
 }  // namespace
@@ -1399,7 +1562,7 @@ int large_nn_device(cudaStream_t st, long long* launches, const double* d_q, int
     if (c.err) return c.err;
     r = order_queries(c, scr, gv, d_q, n_q, q4, qs);
     if (r) return r;
-    launch_nn<0>(st, py, gv, n_q, qs, nullptr, d_idx, d_d2, nullptr, nullptr, nullptr, 0.0);
+    launch_nn<0>(st, py, gv, n_q, qs, nullptr, d_idx, d_d2, nullptr, nullptr, nullptr, nullptr, 0.0);
     c.launched();
     return c.ok() ? KSS_OK : c.err;
 }
@@ -1455,6 +1618,8 @@ int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, i
     float4* rec = c.get<float4>("lg_rec", (size_t)n_s * 2);   // per-point records by original index
     float* d2 = c.get<float>("lg_d2", n_s);
     int* prev = c.get<int>("lg_prev", n_s);                   // last iteration's match per sorted position (-1: none yet)
+    unsigned char* flag = c.get<unsigned char>("lg_flag", n_s);
+    int* worklist = c.get<int>("lg_worklist", n_s);
     const int nchunks = (n_s + 255) / 256;
     float* pA = c.get<float>("lg_partA", (size_t)nchunks * 6);
     float* pB = c.get<float>("lg_partB", (size_t)nchunks * 9);
@@ -1472,7 +1637,7 @@ int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, i
     static_assert(sizeof(Pyramid) <= sizeof(run->pyramid), "LargeIcp::pyramid too small");
     memcpy(run->pyramid, &py, sizeof(py));
     run->n_s = n_s; run->n_t = n_t; run->nchunks = nchunks;
-    run->inp = inp; run->cur = cur; run->rec = rec; run->d2 = d2; run->prev = prev;
+    run->inp = inp; run->cur = cur; run->rec = rec; run->d2 = d2; run->prev = prev; run->flag = flag; run->worklist = worklist;
     run->partA = pA; run->partB = pB; run->partD = pD; run->partK = pK; run->state = state; run->out3 = out3;
     return c.ok() ? KSS_OK : c.err;
 }
@@ -1487,14 +1652,18 @@ int large_icp_iterations(cudaStream_t st, long long* launches, LargeIcp* run, co
     const double mse_abs = prm->fitness_eps < 0.0 ? -1.0 : 1e-12;   // fitness_eps < 0: never converge (steady-state timing)
     for (int k = 0; k < count; ++k) {
         if (run->mark) run->mark(run->mark_user, KSS_STAGE_LARGE_NN, 1);
-        launch_nn<1>(st, py, gv, n, (float4*)run->cur, nullptr, nullptr, nullptr, (float4*)run->rec, run->prev, state, max2);
+        // correspondences: the refine kernel finishes every query whose last match bounds the search to a few cells;
+        // the general kernels take what it flags (staged CTAs when many, one warp per query when few)
+        lg_refine_kernel<<<(n + 255) / 256, 256, 0, st>>>(gv, n, (float4*)run->cur, (float4*)run->rec, run->prev, run->flag, run->worklist, state, max2);
+        launch_nn<1>(st, py, gv, n, (float4*)run->cur, nullptr, nullptr, nullptr, (float4*)run->rec, run->prev, run->flag, state, max2);
+        lg_left_kernel<<<148, 256, 0, st>>>(py, gv, n, (const float4*)run->cur, (float4*)run->rec, run->prev, run->worklist, state, max2);
         if (run->mark) { run->mark(run->mark_user, KSS_STAGE_LARGE_NN, 0); run->mark(run->mark_user, KSS_STAGE_LARGE_REDUCE, 1); }
         lg_passA_kernel<<<(nch + 7) / 8, 256, 0, st>>>((const float4*)run->rec, n, nch, run->partA, run->partD, run->partK, state);
         lg_passB_kernel<<<(nch + 7) / 8, 256, 0, st>>>((const float4*)run->rec, n, nch, run->partB, state, prm->max_iterations,
                                                        1.0 - prm->transformation_eps, prm->transformation_eps,
                                                        prm->fitness_eps, mse_abs);
         if (run->mark) run->mark(run->mark_user, KSS_STAGE_LARGE_REDUCE, 0);
-        *launches += 3;
+        *launches += 5;
     }
     return cudaGetLastError() == cudaSuccess ? KSS_OK : KSS_ERR_CUDA;
 }
@@ -1514,7 +1683,7 @@ int large_icp_run(cudaStream_t st, long long* launches, LargeIcp* run, const kss
     // getFitnessScore: final * ORIGINAL input, NN, mean d2 in double (A.7)
     Pyramid py; memcpy(&py, run->pyramid, sizeof(py));
     LgGridView gv; memcpy(&gv, run->grid, sizeof(gv));
-    launch_nn<2>(st, py, gv, run->n_s, nullptr, (const float4*)run->inp, nullptr, run->d2, nullptr, nullptr, state, 0.0);
+    launch_nn<2>(st, py, gv, run->n_s, nullptr, (const float4*)run->inp, nullptr, run->d2, nullptr, nullptr, nullptr, state, 0.0);
     lg_passF_kernel<<<(run->nchunks + 7) / 8, 256, 0, st>>>(run->d2, run->n_s, run->nchunks, run->partD, nullptr,
                                                             &state->ticketF, run->out3);
     *launches += 2;

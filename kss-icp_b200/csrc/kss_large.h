@@ -26,7 +26,8 @@ struct LargeIcp {
     alignas(8) unsigned char grid[64];
     int n_s = 0, n_t = 0, nchunks = 0;
     void *inp = nullptr, *cur = nullptr, *rec = nullptr, *state = nullptr;
-    int *partK = nullptr, *prev = nullptr;
+    int *partK = nullptr, *prev = nullptr, *worklist = nullptr;
+    unsigned char* flag = nullptr;
     float *d2 = nullptr, *partA = nullptr, *partB = nullptr;
     double *partD = nullptr, *out3 = nullptr;
     // optional stage marks (CUDA-event timing by the context): mark(user, KSS_STAGE_*, begin?1:0)
