@@ -213,6 +213,27 @@ int kss_register_batch(kss_ctx* ctx, const kss_batch* b, kss_pair_result* result
 int kss_register_batch_device(kss_ctx* ctx, const kss_batch* b, kss_pair_result* d_results,
                               double* d_point_align);
 
+/* ---- multi-GPU (one ctx per GPU; a single pair / ICP run is never split) ----------------- */
+
+/* registration pairs are independent (Main_KSS_List.cpp:132-167 is a plain loop): contiguous blocks of the batch on
+ * n_ctx contexts (one per GPU, this process), one host thread each, host buffers, no data-path collective */
+int kss_register_batch_multi(kss_ctx** ctxs, int n_ctx, const kss_batch* b, kss_pair_result* results, double* point_align);
+
+/* NCCL plumbing for hypothesis sharding.  One process per GPU: rank 0 calls kss_nccl_get_unique_id, hands the 128 bytes to
+ * the other ranks (torch.distributed / MPI / a file), every rank calls kss_ctx_nccl_init.  One process, several GPUs:
+ * kss_ctx_nccl_init_all on the array of contexts.  libnccl.so.2 is resolved at run time. */
+int kss_nccl_get_unique_id(void* id128);
+int kss_ctx_nccl_init(kss_ctx* ctx, const void* id128, int rank, int world);
+int kss_ctx_nccl_init_all(kss_ctx** ctxs, int n);
+
+/* KSSICP_Registration + PCR_QM with the rotation hypotheses of every pair sharded over the ranks of ctx's communicator
+ * (every rank passes the SAME batch and receives the SAME results): the 729-hypothesis sweep is slabbed over the ranks and
+ * completed by one ncclAllGather of the score grid (initRegistrationKSS.hpp:245-268); the ICP runs over angleList
+ * (KSS_ICP.hpp:102-118) are dealt round-robin and their fp64 fitness vector is completed by ONE ncclAllReduce(min); every
+ * rank then applies the reference's selection rule (KSS_ICP.hpp:113) and repeats the winner's run (KSS_ICP.hpp:130).
+ * Host buffers; the collectives run on ctx's stream.  world == 1 (no kss_ctx_nccl_init) is the unsharded path. */
+int kss_register_batch_hyp_sharded(kss_ctx* ctx, const kss_batch* b, kss_pair_result* results, double* point_align);
+
 /* one pair, the exact flow of KSSICP_Registration (KSS_ICP.hpp:86-130); sim_s = sim_t = NULL: raw clouds,
  * simplified by the library first (KSS_ICP.hpp:53-82), n_s / n_t ignored */
 int kss_register(kss_ctx* ctx, const double* sim_s, int n_s, const double* sim_t, int n_t,

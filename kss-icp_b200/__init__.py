@@ -273,12 +273,73 @@ class Context:
         self._ck(self.lib.kss_register_batch_device(self.h, C.byref(b), C.c_void_p(d_results),
                                                     C.c_void_p(d_point_align or 0)))
 
+    # ---- multi-GPU ---------------------------------------------------------------
+    def nccl_init(self, unique_id, rank, world):
+        """join the communicator of `unique_id` (128 bytes from nccl_unique_id() on rank 0) as `rank` of `world`"""
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.lib.kss_ctx_nccl_init(self.h, buf, C.c_int(rank), C.c_int(world)))
+
+    def register_batch_hyp_sharded(self, sim_s, sim_t, full_s, full_t, step=8.0, max_iter=1000, counts=None,
+                                   want_points=False, judge_threshold=0.0005):
+        """register_batch with the rotation hypotheses of every pair sharded over the ranks of this context's
+        communicator (every rank passes the same batch and gets the same results)"""
+        fs = _f64(full_s); ft = _f64(full_t)
+        raw = sim_s is None
+        ss = None if raw else _f64(sim_s); st = None if raw else _f64(sim_t)
+        P = fs.shape[0]
+        cn = [None] * 4
+        if counts is not None:
+            cn = [np.ascontiguousarray(c, np.int32) if c is not None else None for c in counts]
+        b = self._batch(P, (0 if raw else ss.shape[1], 0 if raw else st.shape[1], fs.shape[1], ft.shape[1]),
+                        (None if raw else _p(ss).value, None if raw else _p(st).value, _p(fs).value, _p(ft).value),
+                        tuple((_p(c).value if c is not None else None) for c in cn), step, max_iter, judge_threshold)
+        res = np.zeros(P, RESULT_DTYPE)
+        pa = np.empty_like(fs) if want_points else None
+        self._ck(self.lib.kss_register_batch_hyp_sharded(self.h, C.byref(b), _p(res), _p(pa)))
+        return (res, pa) if want_points else res
+
     def register(self, sim_s, sim_t, full_s, full_t, step=8.0, max_iter=1000, want_points=False):
         out = self.register_batch(_f64(sim_s)[None], _f64(sim_t)[None], _f64(full_s)[None], _f64(full_t)[None],
                                   step=step, max_iter=max_iter, want_points=want_points)
         if want_points:
             return out[0][0], out[1][0]
         return out[0]
+
+
+def nccl_unique_id():
+    """128 bytes identifying a new NCCL communicator (call on rank 0, hand to every rank's Context.nccl_init)"""
+    buf = (C.c_ubyte * 128)()
+    rc = load_library().kss_nccl_get_unique_id(buf)
+    if rc != KSS_OK:
+        raise KssError("kss_nccl_get_unique_id failed with %d (libnccl.so.2 not loadable?)" % rc)
+    return bytes(buf)
+
+
+def nccl_init_all(contexts):
+    """one process, several GPUs: a communicator over `contexts` (rank = position)"""
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    rc = load_library().kss_ctx_nccl_init_all(arr, C.c_int(len(contexts)))
+    if rc != KSS_OK:
+        raise KssError("kss_ctx_nccl_init_all failed with %d: %s" % (rc, load_library().kss_last_error(contexts[0].h).decode()))
+
+
+def register_batch_multi(contexts, sim_s, sim_t, full_s, full_t, step=8.0, max_iter=1000, want_points=False,
+                         judge_threshold=0.0005):
+    """pairs in contiguous blocks over `contexts` (one per GPU), one host thread each inside the library"""
+    fs = _f64(full_s); ft = _f64(full_t)
+    raw = sim_s is None
+    ss = None if raw else _f64(sim_s); st = None if raw else _f64(sim_t)
+    P = fs.shape[0]
+    b = Context._batch(P, (0 if raw else ss.shape[1], 0 if raw else st.shape[1], fs.shape[1], ft.shape[1]),
+                       (None if raw else _p(ss).value, None if raw else _p(st).value, _p(fs).value, _p(ft).value),
+                       (None,) * 4, step, max_iter, judge_threshold)
+    res = np.zeros(P, RESULT_DTYPE)
+    pa = np.empty_like(fs) if want_points else None
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    rc = load_library().kss_register_batch_multi(arr, C.c_int(len(contexts)), C.byref(b), _p(res), _p(pa))
+    if rc != KSS_OK:
+        raise KssError("kss_register_batch_multi failed with %d: %s" % (rc, load_library().kss_last_error(contexts[0].h).decode()))
+    return (res, pa) if want_points else res
 
 
 def exported_symbols():

@@ -8,7 +8,11 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <dlfcn.h>
+#include <nccl.h>            // types only: the library is resolved at run time (kss_nccl below), never linked
 
 #include "kss_kernels.h"
 #include "kss_large.h"
@@ -32,6 +36,9 @@ struct kss_ctx {
     struct Buf { void* p = nullptr; size_t cap = 0; };
     std::map<std::string, Buf> bufs;
     size_t ws_budget = (size_t)48 << 30;
+    // hypothesis sharding (kss_ctx_nccl_init): this ctx is rank `rank` of `world`, one ctx per GPU
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
     int hyp_slots = 32;               // hypothesis CTAs per pair in the batched ICP launch (kss_ctx_set_hyp_slots)
     int* aivs_bad = nullptr;          // device flag written by the last raw-cloud batch (kss_aivs.h)
     // batch lanes: chunks of a batch alternate between a few internal streams, so that one chunk's copies and the
@@ -55,6 +62,38 @@ struct kss_ctx {
 
 namespace {
 
+// NCCL entry points, resolved from the copy already loaded in the process (torch's) or from libnccl.so.2
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi* kss_nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.ok ? &api : nullptr;
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return nullptr;
+#define KSS_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name))
+    KSS_SYM(GetUniqueId, "ncclGetUniqueId"); KSS_SYM(CommInitRank, "ncclCommInitRank"); KSS_SYM(CommInitAll, "ncclCommInitAll");
+    KSS_SYM(CommDestroy, "ncclCommDestroy"); KSS_SYM(AllGather, "ncclAllGather"); KSS_SYM(AllReduce, "ncclAllReduce");
+    KSS_SYM(GroupStart, "ncclGroupStart"); KSS_SYM(GroupEnd, "ncclGroupEnd"); KSS_SYM(GetErrorString, "ncclGetErrorString");
+#undef KSS_SYM
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommInitAll && api.CommDestroy && api.AllGather && api.AllReduce &&
+             api.GroupStart && api.GroupEnd && api.GetErrorString;
+    return api.ok ? &api : nullptr;
+}
+
 int fail(kss_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
     return code;
@@ -68,6 +107,17 @@ int fail(kss_ctx* c, int code, const std::string& msg) {
             snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
                      __FILE__, __LINE__);                                                     \
             return fail(ctx, KSS_ERR_CUDA, b_);                                               \
+        }                                                                                     \
+    } while (0)
+
+#define NC(call)                                                                              \
+    do {                                                                                      \
+        ncclResult_t e_ = (call);                                                             \
+        if (e_ != ncclSuccess) {                                                              \
+            char b_[512];                                                                     \
+            snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #call, kss_nccl()->GetErrorString(e_), \
+                     __FILE__, __LINE__);                                                     \
+            return fail(ctx, KSS_ERR_NCCL, b_);                                               \
         }                                                                                     \
     } while (0)
 
@@ -133,6 +183,19 @@ int dev_buf(kss_ctx* ctx, const char* name, size_t count, T** out) {
         if (r_ != KSS_OK) return r_;                       \
     } while (0)
 
+__global__ void fill_f64_kernel(double* p, size_t n, double v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// hypothesis slabs of the score grid: value [P][hpad] <-> vg [world][P][slab] (equal counts for ncclAllGather)
+__global__ void slab_pack_kernel(const double* value, int P, int hpad, int h_lo, int h_hi, int slab, double* vg_mine) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (i < slab) vg_mine[(size_t)p * slab + i] = h_lo + i < h_hi ? value[(size_t)p * hpad + h_lo + i] : 0.0;
+}
+__global__ void slab_unpack_kernel(const double* vg, int P, int hpad, int H, int slab, int world, double* value) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (h < H) { const int r = h / slab; value[(size_t)p * hpad + h] = vg[((size_t)r * P + p) * slab + (h - r * slab)]; }
+}
 __global__ void fill_int_kernel(int* p, int n, int v) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -210,7 +273,7 @@ void icp_fill(IcpArgs& a, const kss_icp_params& prm) {
 int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s, const double* sim_t,
                     const double* full_s, const double* full_t, const int* cnt_s, const int* cnt_t,
                     const int* cnt_S, const int* cnt_T, const int* h_cnt_S, const int* h_cnt_T, int slots,
-                    kss_pair_result* d_out, double* d_point_align) {
+                    kss_pair_result* d_out, double* d_point_align, bool shard) {
     cudaStream_t st = ctx->stream;
     const int G = ctx->G, H = G * G * G, hpad = H;
     const int cap_s = b.cap_s, cap_t = b.cap_t, cap_S = b.cap_S, cap_T = b.cap_T;
@@ -254,14 +317,39 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
         ctx->launches += nl;
         cg = &cgb;
     }
-    {
-        StageTimer tm(ctx, KSS_STAGE_SWEEP);
-        KL(launch_sweep(st, P, s_al, cnt_s, cap_s, s_perm, t_sorted, t_box, cnt_t, cap_tpad, ctx->d_trig_accum, G,
-                        KSS_SCORE_AVE, rbuf, hpad, cg));
-    }
-    {
+    const bool sharded = shard && ctx->comm && ctx->world > 1;
+    if (!sharded) {
+        {
+            StageTimer tm(ctx, KSS_STAGE_SWEEP);
+            KL(launch_sweep(st, P, s_al, cnt_s, cap_s, s_perm, t_sorted, t_box, cnt_t, cap_tpad, ctx->d_trig_accum, G,
+                            KSS_SCORE_AVE, rbuf, hpad, cg, 0, G * G));
+        }
+        {
+            StageTimer tm(ctx, KSS_STAGE_SWEEP_FINALIZE);
+            KL(launch_sweep_finalize(st, P, rbuf, cnt_s, cap_s, hpad, G, KSS_SCORE_AVE, value, best_h, minima, n_minima, 0, H, 3));
+        }
+    } else {
+        // rotation hypotheses slabbed over the ranks (initRegistrationKSS.hpp:245-268 scores every (i, j, k) independently):
+        // this rank sweeps the (i, j) pairs [ij_lo, ij_hi), sums its slab, ONE all-gather completes the grid everywhere,
+        // then argmin + local minima (initRegistration_kernel needs the whole grid) run identically on every rank
+        const int per = (G * G + ctx->world - 1) / ctx->world, slab = per * G;
+        const int ij_lo = std::min(G * G, ctx->rank * per), ij_hi = std::min(G * G, ij_lo + per);
+        double* vg;
+        BUF("hyp_vg", (size_t)ctx->world * P * slab, &vg);
+        {
+            StageTimer tm(ctx, KSS_STAGE_SWEEP);
+            KL(launch_sweep(st, P, s_al, cnt_s, cap_s, s_perm, t_sorted, t_box, cnt_t, cap_tpad, ctx->d_trig_accum, G,
+                            KSS_SCORE_AVE, rbuf, hpad, cg, ij_lo, ij_hi));
+        }
         StageTimer tm(ctx, KSS_STAGE_SWEEP_FINALIZE);
-        KL(launch_sweep_finalize(st, P, rbuf, cnt_s, cap_s, hpad, G, KSS_SCORE_AVE, value, best_h, minima, n_minima));
+        KL(launch_sweep_finalize(st, P, rbuf, cnt_s, cap_s, hpad, G, KSS_SCORE_AVE, value, best_h, minima, n_minima, ij_lo * G, ij_hi * G, 1));
+        double* mine = vg + (size_t)ctx->rank * P * slab;
+        slab_pack_kernel<<<dim3((slab + 127) / 128, P), 128, 0, st>>>(value, P, hpad, ij_lo * G, ij_hi * G, slab, mine);
+        KL(cudaGetLastError());
+        NC(kss_nccl()->AllGather(mine, vg, (size_t)P * slab, ncclDouble, ctx->comm, st));
+        slab_unpack_kernel<<<dim3((H + 127) / 128, P), 128, 0, st>>>(vg, P, hpad, H, slab, ctx->world, value);
+        KL(cudaGetLastError());
+        KL(launch_sweep_finalize(st, P, rbuf, cnt_s, cap_s, hpad, G, KSS_SCORE_AVE, value, best_h, minima, n_minima, 0, H, 2));
     }
 
     IcpArgs a{};
@@ -279,18 +367,47 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
     if (cg) { a.cg_geom = cg->geom; a.cg_hdr = cg->hdr; a.cg_arena = cg->arena; a.cg_ok = cg->ok; }
     icp_fill(a, b.icp);
     a.run_T = run_T; a.run_fit = run_fit; a.run_iters = run_iters; a.run_conv = run_conv;
-    a.run_hyp = run_hyp; a.run_tot = run_tot;
+    a.run_hyp = run_hyp; a.run_tot = run_tot; a.hyp_rank = 0; a.hyp_world = 1;
     a.mode = 3;                                                // judge (KSS_ICP.hpp:93) + hypothesis runs (:102-118), one launch
-    {
-        StageTimer tm(ctx, KSS_STAGE_ICP_HYP);
-        KL(launch_icp(st, P, 1 + slots, a));
-    }
     double* pa = d_point_align;
     if (!pa) BUF("point_align", (size_t)P * cap_S * 3, &pa);
-    {
+    if (!sharded) {
+        {
+            StageTimer tm(ctx, KSS_STAGE_ICP_HYP);
+            KL(launch_icp(st, P, 1 + slots, a));
+        }
         StageTimer tm(ctx, KSS_STAGE_SELECT_APPLY);
         KL(launch_select(st, P, R, hpad, G, b.judge_threshold, align8, run_fit, run_iters, run_T, run_conv, run_hyp,
                          run_tot, best_h, minima, n_minima, d_out));
+        KL(launch_final_apply(st, P, full_s, cnt_S, cap_S, align8, d_out, ctx->d_trig_accum, ctx->d_trig_list, G, pa));
+    } else {
+        // ICP runs over angleList dealt round-robin to the ranks (KSS_ICP.hpp:102-118 is a serial loop over independent
+        // runs); the kernel writes every run's fitness (and iteration count) at its l into a vector pre-filled with +inf,
+        // and ONE all-reduce(MIN, double) on this ctx's stream completes it on every rank
+        double* hyp_fit; double* run2_fit; float* run2_T; int *run2_iters, *run2_conv, *win_minima, *n_win;
+        BUF("hyp_fit", (size_t)P * 2 * hpad, &hyp_fit);
+        BUF("run2_T", (size_t)P * 2 * 16, &run2_T); BUF("run2_fit", (size_t)P * 2, &run2_fit);
+        BUF("run2_iters", (size_t)P * 2, &run2_iters); BUF("run2_conv", (size_t)P * 2, &run2_conv);
+        BUF("win_minima", (size_t)P * hpad, &win_minima); BUF("n_win", (size_t)P, &n_win);
+        const size_t nfit = (size_t)P * 2 * hpad;
+        fill_f64_kernel<<<(unsigned)((nfit + 255) / 256), 256, 0, st>>>(hyp_fit, nfit, (double)INFINITY);
+        KL(cudaGetLastError());
+        a.hyp_rank = ctx->rank; a.hyp_world = ctx->world; a.hyp_fit = hyp_fit;
+        {
+            StageTimer tm(ctx, KSS_STAGE_ICP_HYP);
+            KL(launch_icp(st, P, 1 + slots, a));
+            NC(kss_nccl()->AllReduce(hyp_fit, hyp_fit, nfit, ncclDouble, ncclMin, ctx->comm, st));
+        }
+        StageTimer tm(ctx, KSS_STAGE_SELECT_APPLY);
+        KL(launch_select_sharded(st, P, R, hpad, G, b.judge_threshold, align8, run_fit, run_iters, hyp_fit, best_h, minima, n_minima,
+                                 d_out, win_minima, n_win));
+        // KSS_ICP.hpp:130: the final ICP repeats the winner's run -- on every rank, from the same start, hence identical
+        IcpArgs f = a;
+        f.mode = 1; f.runs_per_pair = 2; f.judge_thr = -1.0; f.minima = win_minima; f.n_minima = n_win;
+        f.hyp_rank = 0; f.hyp_world = 1; f.hyp_fit = nullptr; f.run_hyp = nullptr; f.run_tot = nullptr;
+        f.run_T = run2_T; f.run_fit = run2_fit; f.run_iters = run2_iters; f.run_conv = run2_conv;
+        KL(launch_icp(st, P, 1, f));
+        KL(launch_finish_sharded(st, P, R, run_fit, run_iters, run_conv, run_T, run2_fit, run2_iters, run2_conv, run2_T, d_out));
         KL(launch_final_apply(st, P, full_s, cnt_S, cap_S, align8, d_out, ctx->d_trig_accum, ctx->d_trig_list, G, pa));
     }
     StageTimer tm_metrics(ctx, KSS_STAGE_METRICS);
@@ -386,6 +503,7 @@ void kss_ctx_destroy(kss_ctx* ctx) {
         if (ctx->lane_done[l]) cudaEventDestroy(ctx->lane_done[l]);
     }
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    if (ctx->comm && kss_nccl()) kss_nccl()->CommDestroy(ctx->comm);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -527,8 +645,8 @@ int kss_rotation_sweep(kss_ctx* ctx, const double* src_aligned, int n_s, const d
         ctx->launches += nl;
         cg = &cgb;
     }
-    KL(launch_sweep(ctx->stream, 1, d_s, c_s, n_s, s_perm, t_sorted, t_box, c_t, tpad, ctx->d_trig_accum, G, score_mode, rbuf, H, cg));
-    KL(launch_sweep_finalize(ctx->stream, 1, rbuf, c_s, n_s, H, G, score_mode, d_val, d_best, d_min, d_nmin));
+    KL(launch_sweep(ctx->stream, 1, d_s, c_s, n_s, s_perm, t_sorted, t_box, c_t, tpad, ctx->d_trig_accum, G, score_mode, rbuf, H, cg, 0, G * G));
+    KL(launch_sweep_finalize(ctx->stream, 1, rbuf, c_s, n_s, H, G, score_mode, d_val, d_best, d_min, d_nmin, 0, H, 3));
     std::vector<int> hmin(H);
     int hbest = 0, nmin = 0;
     if (value) CU(cudaMemcpyAsync(value, d_val, sizeof(double) * H, cudaMemcpyDeviceToHost, ctx->stream));
@@ -613,7 +731,7 @@ int kss_icp(kss_ctx* ctx, const double* src, int n_s, const double* tgt, int n_t
     IcpArgs a{};
     a.src_f64 = d_s; a.cnt_s = c_s; a.cap_s = n_s; a.s_perm = s_perm;
     a.t_sorted = t_sorted; a.t_box = t_box; a.t_inv = t_inv; a.cnt_t = c_t; a.cap_t = n_t; a.cap_tpad = tpad;
-    a.mode = 2; a.runs_per_pair = 1; a.judge_thr = -1.0;
+    a.mode = 2; a.runs_per_pair = 1; a.judge_thr = -1.0; a.hyp_world = 1;
     CgBuffers cgb{};
     if (cg_enabled()) {
         r = cg_buffers(ctx, 1, &cgb); if (r) return r;
@@ -724,7 +842,7 @@ int ensure_lanes(kss_ctx* ctx, int n) {
 // The batch in chunks; `host` = b's clouds/counts and results/point_align are host memory (copied per chunk on the
 // chunk's lane), else device memory.  Everything is ordered after the work already on ctx->stream, and ctx->stream
 // waits for all lanes at the end.
-int batch_core(kss_ctx* ctx, const kss_batch* b_in, bool host, kss_pair_result* results, double* point_align) {
+int batch_core(kss_ctx* ctx, const kss_batch* b_in, bool host, kss_pair_result* results, double* point_align, bool shard = false) {
     kss_batch bb = *b_in;
     const bool raw = !bb.sim_s;
     if (raw) {   // pNumber (KSS_ICP.hpp:53-67) plus room for a trim step that stops early on its stale neighbour lists
@@ -756,6 +874,10 @@ int batch_core(kss_ctx* ctx, const kss_batch* b_in, bool host, kss_pair_result* 
         int nchunks = std::max((NP + chunk - 1) / chunk, want);
         if (nchunks < 1) nchunks = 1;
         chunk = (NP + nchunks - 1) / nchunks;
+    }
+    if (shard) {     // collectives must be issued in the same order on every rank: one lane, chunks in sequence
+        lanes = 1;
+        chunk = (int)std::min<size_t>((size_t)NP, std::max<size_t>(1, ctx->ws_budget / per));
     }
     if (chunk >= NP) lanes = 1;
     r = ensure_lanes(ctx, lanes); if (r) return r;
@@ -842,7 +964,7 @@ int batch_core(kss_ctx* ctx, const kss_batch* b_in, bool host, kss_pair_result* 
                     if ((hS && (hS[i] < 1 || hS[i] > bb.cap_S)) || (hT && (hT[i] < 1 || hT[i] > bb.cap_T)))
                         return fail(ctx, KSS_ERR_ARG, "kss_batch: a full-resolution count is outside 1..capacity");
             }
-            q = pipeline_device(ctx, P, bb, sim_s, sim_t, full_s, full_t, c_s, c_t, c_S, c_T, hS, hT, slots, d_res, d_pa);
+            q = pipeline_device(ctx, P, bb, sim_s, sim_t, full_s, full_t, c_s, c_t, c_S, c_T, hS, hT, slots, d_res, d_pa, shard);
             if (q) return q;
             if (host) {
                 CU(cudaMemcpyAsync(results + p0, d_res, sizeof(kss_pair_result) * (size_t)P, cudaMemcpyDeviceToHost, st));
@@ -882,6 +1004,89 @@ int kss_register_batch(kss_ctx* ctx, const kss_batch* b, kss_pair_result* result
     if (raw) CU(cudaMemcpyAsync(&bad, ctx->aivs_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (bad) return aivs_status(ctx, bad);
+    return KSS_OK;
+}
+
+// ---- multi-GPU -----------------------------------------------------------------------
+int kss_nccl_get_unique_id(void* id128) {
+    if (!id128) return KSS_ERR_ARG;
+    NcclApi* n = kss_nccl();
+    if (!n) return KSS_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    if (n->GetUniqueId(&id) != ncclSuccess) return KSS_ERR_NCCL;
+    std::memcpy(id128, &id, sizeof(id));
+    return KSS_OK;
+}
+
+int kss_ctx_nccl_init(kss_ctx* ctx, const void* id128, int rank, int world) {
+    if (!ctx) return KSS_ERR_ARG;
+    if (!id128 || world < 1 || rank < 0 || rank >= world) return fail(ctx, KSS_ERR_ARG, "kss_ctx_nccl_init: bad argument");
+    if (!kss_nccl()) return fail(ctx, KSS_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->comm) { kss_nccl()->CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    NC(kss_nccl()->CommInitRank(&ctx->comm, world, id, rank));
+    ctx->rank = rank; ctx->world = world;
+    return KSS_OK;
+}
+
+int kss_ctx_nccl_init_all(kss_ctx** ctxs, int n) {
+    if (!ctxs || n < 1) return KSS_ERR_ARG;
+    kss_ctx* ctx = ctxs[0];
+    if (!ctx) return KSS_ERR_ARG;
+    if (!kss_nccl()) return fail(ctx, KSS_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    std::vector<int> devs(n);
+    std::vector<ncclComm_t> comms(n);
+    for (int i = 0; i < n; ++i) { if (!ctxs[i]) return fail(ctx, KSS_ERR_ARG, "kss_ctx_nccl_init_all: null ctx"); devs[i] = ctxs[i]->device; }
+    NC(kss_nccl()->CommInitAll(comms.data(), n, devs.data()));
+    for (int i = 0; i < n; ++i) {
+        if (ctxs[i]->comm) kss_nccl()->CommDestroy(ctxs[i]->comm);
+        ctxs[i]->comm = comms[i]; ctxs[i]->rank = i; ctxs[i]->world = n;
+    }
+    return KSS_OK;
+}
+
+int kss_register_batch_hyp_sharded(kss_ctx* ctx, const kss_batch* b, kss_pair_result* results, double* point_align) {
+    int r = check_batch(ctx, b); if (r) return r;
+    if (!results) return fail(ctx, KSS_ERR_ARG, "kss_register_batch_hyp_sharded: null results");
+    if (ctx->world > 1 && !ctx->comm) return fail(ctx, KSS_ERR_NCCL, "kss_register_batch_hyp_sharded: call kss_ctx_nccl_init first");
+    CU(cudaSetDevice(ctx->device));
+    const bool raw = !b->sim_s;
+    r = batch_core(ctx, b, true, results, point_align, true); if (r) return r;
+    int bad = 0;
+    if (raw) CU(cudaMemcpyAsync(&bad, ctx->aivs_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (bad) return aivs_status(ctx, bad);
+    return KSS_OK;
+}
+
+int kss_register_batch_multi(kss_ctx** ctxs, int n_ctx, const kss_batch* b, kss_pair_result* results, double* point_align) {
+    if (!ctxs || n_ctx < 1 || !ctxs[0]) return KSS_ERR_ARG;
+    int r = check_batch(ctxs[0], b); if (r) return r;
+    if (!results) return fail(ctxs[0], KSS_ERR_ARG, "kss_register_batch_multi: null results");
+    // pairs are independent (Main_KSS_List.cpp:132-167 is a plain loop): contiguous blocks, one host thread per context, no
+    // data-path collective
+    const int NP = b->n_pairs, per = (NP + n_ctx - 1) / n_ctx;
+    std::vector<int> rc(n_ctx, KSS_OK);
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_ctx; ++i) {
+        const int p0 = std::min(NP, i * per), p1 = std::min(NP, p0 + per);
+        if (p1 <= p0) continue;
+        th.emplace_back([=, &rc]() {
+            kss_batch one = *b;
+            one.n_pairs = p1 - p0;
+            one.full_s = b->full_s + (size_t)p0 * b->cap_S * 3; one.full_t = b->full_t + (size_t)p0 * b->cap_T * 3;
+            if (b->sim_s) { one.sim_s = b->sim_s + (size_t)p0 * b->cap_s * 3; one.sim_t = b->sim_t + (size_t)p0 * b->cap_t * 3; }
+            one.cnt_s = b->cnt_s ? b->cnt_s + p0 : nullptr; one.cnt_t = b->cnt_t ? b->cnt_t + p0 : nullptr;
+            one.cnt_S = b->cnt_S ? b->cnt_S + p0 : nullptr; one.cnt_T = b->cnt_T ? b->cnt_T + p0 : nullptr;
+            rc[i] = kss_register_batch(ctxs[i], &one, results + p0, point_align ? point_align + (size_t)p0 * b->cap_S * 3 : nullptr);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n_ctx; ++i)
+        if (rc[i] != KSS_OK) { if (i) ctxs[0]->err = "context " + std::to_string(i) + ": " + ctxs[i]->err; return rc[i]; }
     return KSS_OK;
 }
 

@@ -44,6 +44,10 @@ struct IcpArgs {
     // hypothesis slots that serve several hypotheses (more local minima than slots): run_hyp = 2 * l + qualifies of the
     // run the slot ended up holding, run_tot = {sum of iterations, number of runs} of the slot (both may be null)
     int* run_hyp; int* run_tot;
+    // hypothesis sharding over ranks (KSS_ICP.hpp:102-118 is a serial loop over independent runs): the CTA of slot s runs
+    // l = s * world + rank, then strides by slots * world; hyp_fit [P][2][hpad] (null: off) receives fitness and iteration
+    // count of EVERY run at its l -- the vector one all-reduce(MIN) completes on every rank
+    int hyp_rank, hyp_world; double* hyp_fit;
     // optional trace
     unsigned long long* phase_cycles;      // diagnostics (tools/): per-phase clock64 sums of thread 0, or null
     int trace_cap; int32_t* trace_idx; float* trace_T; double* trace_mse; float* trace_src;
@@ -60,18 +64,25 @@ cudaError_t launch_middle_align(cudaStream_t st, int P, const double* sim_s, con
 cudaError_t launch_sweep(cudaStream_t st, int P, const double* s_al, const int* cnt_s, int cap_s,
                          const unsigned short* s_perm, const float4* t_sorted, const float* t_box,
                          const int* cnt_t, int cap_tpad, const double* trig_accum, int G, int score_mode,
-                         float* rbuf, int hpad, const CgBuffers* cg);
+                         float* rbuf, int hpad, const CgBuffers* cg, int ij_lo, int ij_hi);
 cudaError_t launch_cg_build(cudaStream_t st, int P, int geom_mode, const double* a, const int* cnt_a, int cap_a,
                             const double* b, const int* cnt_b, int cap_b, const float4* t_sorted,
                             const unsigned short* t_inv, int cap_t, const int* cnt_t,
                             int cap_tpad, const CgBuffers& cg, int* launches);
 cudaError_t launch_sweep_finalize(cudaStream_t st, int P, const float* rbuf, const int* cnt_s, int cap_s, int hpad,
-                                  int G, int score_mode, double* value, int* best_h, int* minima, int* n_minima);
+                                  int G, int score_mode, double* value, int* best_h, int* minima, int* n_minima,
+                                  int h_lo, int h_hi, int phases);
 cudaError_t launch_icp(cudaStream_t st, int P, int slots, const IcpArgs& a);
 cudaError_t launch_select(cudaStream_t st, int P, int runs_per_pair, int hpad, int G, double judge_thr,
                           const double* align8, const double* run_fit, const int* run_iters, const float* run_T,
                           const int* run_conv, const int* run_hyp, const int* run_tot,
                           const int* best_h, const int* minima, const int* n_minima, PairOut* out);
+cudaError_t launch_select_sharded(cudaStream_t st, int P, int runs_per_pair, int hpad, int G, double judge_thr, const double* align8,
+                                  const double* run_fit, const int* run_iters, const double* hyp_fit, const int* best_h,
+                                  const int* minima, const int* n_minima, PairOut* out, int* win_minima, int* n_win);
+cudaError_t launch_finish_sharded(cudaStream_t st, int P, int runs_per_pair, const double* run_fit, const int* run_iters,
+                                  const int* run_conv, const float* run_T, const double* run2_fit, const int* run2_iters,
+                                  const int* run2_conv, const float* run2_T, PairOut* out);
 cudaError_t launch_final_apply(cudaStream_t st, int P, const double* full_s, const int* cnt_S, int cap_S,
                                const double* align8, const PairOut* out, const double* trig_accum,
                                const double* trig_list, int G, double* point_align);

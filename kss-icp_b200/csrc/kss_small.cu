@@ -781,7 +781,7 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
              const float4* __restrict__ t_sorted, const float* __restrict__ t_box,
              const int* __restrict__ cnt_t, int cap_tpad,
              const double* __restrict__ trig_accum /* [G][2] cos,sin */, int G, int score_mode,
-             float* __restrict__ rbuf, int hpad,
+             float* __restrict__ rbuf, int hpad, int ij_lo /* first (i, j) pair of this launch: hypothesis slabs */,
              const float* __restrict__ cg_geom, const cg_hdr_t* __restrict__ cg_hdr,
              const unsigned short* __restrict__ cg_arena, const int* __restrict__ cg_ok) {
     extern __shared__ unsigned char smem_raw[];
@@ -800,7 +800,7 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
     CgView cg{};
     if (use_cg) cg = cg_view(cg_geom, cg_hdr, cg_arena, cg_ok, p);
 
-    const int gi = blockIdx.x / G, gj = blockIdx.x % G;
+    const int gi = (blockIdx.x + ij_lo) / G, gj = (blockIdx.x + ij_lo) % G;
     const double ci = trig_accum[2 * gi], si = trig_accum[2 * gi + 1];
     const double cj = trig_accum[2 * gj], sj = trig_accum[2 * gj + 1];
     const int n_s = cnt_s[p];
@@ -862,7 +862,8 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
 // errorT = 9999) and the clamped 5x5x5 local-minimum test in (i,j,k) loop order.
 __global__ void __launch_bounds__(1024)
 sweep_finalize_kernel(const float* __restrict__ rbuf, const int* __restrict__ cnt_s, int cap_s, int hpad,
-                      int G, int score_mode,
+                      int G, int score_mode, int h_lo, int h_hi /* hypotheses this launch sums */,
+                      int phases /* 1: the sums, 2: argmin + local minima over the full grid in `value`, 3: both */,
                       double* __restrict__ value /* [P][hpad] */, int* __restrict__ best_h /* [P] */,
                       int* __restrict__ minima /* [P][hpad] */, int* __restrict__ n_minima /* [P] */) {
     extern __shared__ unsigned char smem_raw[];
@@ -874,7 +875,7 @@ sweep_finalize_kernel(const float* __restrict__ rbuf, const int* __restrict__ cn
     const int n = cnt_s[p];
     const float* rb = rbuf + (size_t)p * cap_s * hpad;
     if (threadIdx.x == 0) bestkey = 0xffffffffffffffffull;
-    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    for (int h = h_lo + threadIdx.x; (phases & 1) && h < h_hi; h += blockDim.x) {
         double sum = 0.0, dmax = -9999.0;
         // 16 independent loads in flight per thread, then the strictly ordered adds
         int i = 0;
@@ -901,6 +902,9 @@ sweep_finalize_kernel(const float* __restrict__ rbuf, const int* __restrict__ cn
         val[h] = v;
         value[(size_t)p * hpad + h] = v;
     }
+    if (!(phases & 2)) return;
+    if (phases == 2)                         // the grid was summed elsewhere (hypothesis slabs gathered from all ranks)
+        for (int h = threadIdx.x; h < H; h += blockDim.x) val[h] = value[(size_t)p * hpad + h];
     __syncthreads();
     // first strict minimum below 9999 in loop order == smallest (value, h) pair
     for (int h = threadIdx.x; h < H; h += blockDim.x) {
@@ -1007,7 +1011,8 @@ icp_small_kernel(IcpArgs a) {
     __syncthreads();
     if (mode == 1) {
         const bool active = a.mode == 3 || a.judge_thr < 0.0 || a.run_fit[p * a.runs_per_pair] > a.judge_thr;
-        if (!active || hslot >= a.n_minima[p] || hslot >= a.runs_per_pair - 1) return;
+        hs = hslot * max(a.hyp_world, 1) + a.hyp_rank; // hypothesis-sharded: this rank runs l = rank (mod world)
+        if (!active || hs >= a.n_minima[p] || hslot >= a.runs_per_pair - 1) return;
     } else if (mode == 0) {
         if (threadIdx.x < 3) {
             const int h = a.best_h[p], k = threadIdx.x;
@@ -1290,6 +1295,10 @@ icp_small_kernel(IcpArgs a) {
             tot_iters += iters; ++tot_runs;
             // the first run is always stored (it is what the reference uses when nothing qualifies: angleIndex = 0);
             // later runs (increasing l) replace it only by a strictly smaller qualifying fitness
+            if (a.hyp_fit) {                          // the full fitness / iteration vectors of a hypothesis-sharded pair
+                a.hyp_fit[(size_t)p * 2 * a.hpad + hs] = fit;
+                a.hyp_fit[(size_t)p * 2 * a.hpad + a.hpad + hs] = (double)iters;
+            }
             take = !stored || (qual && (!have_best || fit < best_fit));
             if (take) {
                 a.run_fit[run] = fit;
@@ -1304,7 +1313,7 @@ icp_small_kernel(IcpArgs a) {
         if (take && lane < 16) a.run_T[(size_t)run * 16 + lane] = fin[lane];
     }
     if (mode != 1) break;
-    hs += a.runs_per_pair - 1;
+    hs += (a.runs_per_pair - 1) * max(a.hyp_world, 1);
     if (hs >= a.n_minima[p]) break;
   }
     if (threadIdx.x == 0 && a.run_tot) { a.run_tot[2 * run] = tot_iters; a.run_tot[2 * run + 1] = tot_runs; }
@@ -1364,6 +1373,79 @@ __global__ void select_kernel(int P, int runs_per_pair, int hpad, int G, double 
     o.n_icp_runs = nruns + 1;
     o.overflow = overflow;
     for (int i = 0; i < 16; ++i) o.T[i] = run_T[((size_t)p * runs_per_pair + use_run) * 16 + i];
+}
+
+// =============================================================== hypothesis-sharded selection
+// The fitness vector is complete on every rank after ONE all-reduce(MIN) (entries a rank did not run were +inf):
+// every rank applies KSS_ICP.hpp:100-116 to it -- Q = 9999, first l with ri < Q && ri >= 0 -- and queues the winner's
+// start for the final ICP (KSS_ICP.hpp:130), which every rank repeats (deterministic, so identical).
+// hyp_fit [P][2][hpad]: fitness | iteration count (as double) per hypothesis l.
+__global__ void select_sharded_kernel(int P, int runs_per_pair, int hpad, int G, double judge_thr,
+                                      const double* __restrict__ align8, const double* __restrict__ run_fit,
+                                      const int* __restrict__ run_iters, const double* __restrict__ hyp_fit,
+                                      const int* __restrict__ best_h, const int* __restrict__ minima,
+                                      const int* __restrict__ n_minima, PairOut* __restrict__ out,
+                                      int* __restrict__ win_minima /* [P][hpad], entry 0 */, int* __restrict__ n_win /* [P] */) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    PairOut& o = out[p];
+    for (int i = 0; i < 8; ++i) o.align[i] = align8[(size_t)p * 8 + i];
+    const double E = run_fit[p * runs_per_pair];
+    o.judge_fitness = E;
+    o.judge_iters = run_iters[p * runs_per_pair];
+    o.n_minima = n_minima[p];
+    o.best_h = best_h[p];
+    o.G = G;
+    int total = o.judge_iters, nruns = 1, used_h = best_h[p], winner = -1, multi = 0;
+    if (E > judge_thr) {
+        multi = 1;
+        double Q = 9999.0;
+        int angleIndex = 0;
+        const int L = n_minima[p];
+        const double* fit = hyp_fit + (size_t)p * 2 * hpad;
+        for (int l = 0; l < L; ++l) {
+            const double ri = fit[l];
+            total += (int)fit[hpad + l]; ++nruns;
+            if (ri < Q && ri >= 0.0) { Q = ri; angleIndex = l; }
+        }
+        winner = angleIndex;
+        used_h = minima[(size_t)p * hpad + angleIndex];
+    }
+    o.branch_multi = multi; o.winner = winner; o.used_h = used_h; o.use_list = multi;
+    o.total_icp_iters = total; o.n_icp_runs = nruns + 1;          // (+ the final run, whose iterations are added below)
+    o.overflow = 0; o.reserved_[0] = 0; o.reserved_[1] = 0;
+    win_minima[(size_t)p * hpad] = used_h;
+    n_win[p] = multi;
+}
+// after the final run: run2_* has two slots per pair, slot 1 = the winner's repeated run (multi pairs only)
+__global__ void finish_sharded_kernel(int P, int runs_per_pair, const double* __restrict__ run_fit, const int* __restrict__ run_iters,
+                                      const int* __restrict__ run_conv, const float* __restrict__ run_T,
+                                      const double* __restrict__ run2_fit, const int* __restrict__ run2_iters,
+                                      const int* __restrict__ run2_conv, const float* __restrict__ run2_T, PairOut* __restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    PairOut& o = out[p];
+    const bool m = o.branch_multi != 0;
+    const size_t r1 = (size_t)p * runs_per_pair, r2 = (size_t)p * 2 + 1;
+    o.final_fitness = m ? run2_fit[r2] : run_fit[r1];
+    o.final_iters = m ? run2_iters[r2] : run_iters[r1];
+    o.final_converged = m ? run2_conv[r2] : run_conv[r1];
+    o.total_icp_iters += o.final_iters;
+    for (int i = 0; i < 16; ++i) o.T[i] = m ? run2_T[r2 * 16 + i] : run_T[r1 * 16 + i];
+}
+cudaError_t launch_select_sharded(cudaStream_t st, int P, int runs_per_pair, int hpad, int G, double judge_thr, const double* align8,
+                                  const double* run_fit, const int* run_iters, const double* hyp_fit, const int* best_h,
+                                  const int* minima, const int* n_minima, PairOut* out, int* win_minima, int* n_win) {
+    select_sharded_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, runs_per_pair, hpad, G, judge_thr, align8, run_fit, run_iters, hyp_fit,
+                                                          best_h, minima, n_minima, out, win_minima, n_win);
+    return cudaGetLastError();
+}
+cudaError_t launch_finish_sharded(cudaStream_t st, int P, int runs_per_pair, const double* run_fit, const int* run_iters,
+                                  const int* run_conv, const float* run_T, const double* run2_fit, const int* run2_iters,
+                                  const int* run2_conv, const float* run2_T, PairOut* out) {
+    finish_sharded_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, runs_per_pair, run_fit, run_iters, run_conv, run_T, run2_fit, run2_iters,
+                                                          run2_conv, run2_T, out);
+    return cudaGetLastError();
 }
 
 // =============================================================== final_apply_kernel
@@ -1520,11 +1602,12 @@ cudaError_t launch_middle_align(cudaStream_t st, int P, const double* sim_s, con
 cudaError_t launch_sweep(cudaStream_t st, int P, const double* s_al, const int* cnt_s, int cap_s,
                          const unsigned short* s_perm, const float4* t_sorted, const float* t_box,
                          const int* cnt_t, int cap_tpad, const double* trig_accum, int G, int score_mode,
-                         float* rbuf, int hpad, const CgBuffers* cg) {
+                         float* rbuf, int hpad, const CgBuffers* cg, int ij_lo, int ij_hi) {
     const size_t smem = (size_t)cap_tpad * sizeof(float4) + 6 * MAX_TILES * sizeof(float);
     cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sweep_kernel<<<dim3(G * G, P), 256, smem, st>>>(s_al, cnt_s, cap_s, s_perm, t_sorted, t_box, cnt_t, cap_tpad,
-                                                   trig_accum, G, score_mode, rbuf, hpad,
+    if (ij_hi <= ij_lo) return cudaSuccess;
+    sweep_kernel<<<dim3(ij_hi - ij_lo, P), 256, smem, st>>>(s_al, cnt_s, cap_s, s_perm, t_sorted, t_box, cnt_t, cap_tpad,
+                                                   trig_accum, G, score_mode, rbuf, hpad, ij_lo,
                                                    cg ? cg->geom : nullptr, cg ? cg->hdr : nullptr,
                                                    cg ? cg->arena : nullptr, cg ? cg->ok : nullptr);
     return cudaGetLastError();
@@ -1574,11 +1657,13 @@ size_t cg_worklist_entries_per_pair() { return CG_WL_CAP; }
 size_t cg_worklist2_entries_per_pair() { return CG_WL2_CAP; }
 
 cudaError_t launch_sweep_finalize(cudaStream_t st, int P, const float* rbuf, const int* cnt_s, int cap_s, int hpad,
-                                  int G, int score_mode, double* value, int* best_h, int* minima, int* n_minima) {
+                                  int G, int score_mode, double* value, int* best_h, int* minima, int* n_minima,
+                                  int h_lo, int h_hi, int phases) {
     const int H = G * G * G;
     const size_t smem = (size_t)H * sizeof(double) + H;
     int threads = H < 1024 ? (H + 31) / 32 * 32 : 1024;
-    sweep_finalize_kernel<<<P, threads, smem, st>>>(rbuf, cnt_s, cap_s, hpad, G, score_mode, value, best_h, minima, n_minima);
+    sweep_finalize_kernel<<<P, threads, smem, st>>>(rbuf, cnt_s, cap_s, hpad, G, score_mode, h_lo, h_hi, phases, value, best_h,
+                                                    minima, n_minima);
     return cudaGetLastError();
 }
 size_t icp_smem_bytes(int cap_s, int cap_t, int cap_tpad) {
