@@ -113,3 +113,27 @@ def test_released_command_line(ctx, okss, pkg, tmp_path):
     assert np.allclose([float(x) for x in m.groups()], [exp["mse"], exp["rmse"], exp["mae"]], rtol=2e-5)
     xyz = (tmp_path / "r.xyz").read_text().split()
     assert int(xyz[0]) == 800 and len(xyz) == 1 + 3 * 800
+
+
+@pytest.mark.parametrize("mode", ["pairs", "hyp"])
+def test_batch_driver_multi_gpu(ctx, okss, pkg, tmp_path, mode):
+    """Main_KSS_List_b200 --gpus 2: the C++ host drives the loop of Main_KSS_List.cpp:128-179 on several GPUs, pairs in
+    contiguous blocks (kss_register_batch_multi) or hypotheses sharded (NCCL inside the library): same output as one GPU"""
+    import torch
+    exe = os.path.join(BIN, "Main_KSS_List_b200")
+    if not os.path.exists(exe) or torch.cuda.device_count() < 2:
+        pytest.skip("needs the batch driver and 2 GPUs")
+    lines = []
+    for i, n in enumerate((700, 1100, 400, 900, 650)):
+        p = pkg.synth.modelnet_pair(170 + i, n_full=n)
+        a, b = tmp_path / ("s%d.ply" % i), tmp_path / ("t%d.ply" % i)
+        _write_ply(a, p["full_s"]); _write_ply(b, p["full_t"])
+        lines.append("%s %s" % (a, b))
+    (tmp_path / "list.txt").write_text("\n".join(lines) + "\n")
+    one = subprocess.run([exe, str(tmp_path / "list.txt")], capture_output=True, text=True, timeout=300)
+    two = subprocess.run([exe, "--gpus", "2"] + (["--hyp-shard"] if mode == "hyp" else []) + [str(tmp_path / "list.txt")],
+                         capture_output=True, text=True, timeout=300)
+    assert one.returncode == 0 and two.returncode == 0, (one.stderr[-1000:], two.stderr[-1000:])
+    pat = r"pair \d+ MSE: .*"
+    assert re.findall(pat, one.stdout) == re.findall(pat, two.stdout) and len(re.findall(pat, one.stdout)) == 5
+    assert "2 GPUs" in two.stdout
