@@ -6,9 +6,8 @@ uniform and Box-Muller built on uniform; no np.random.normal).  Coordinates are 
 float32-representable doubles, because the reference's PLY loader delivers floats
 (PlyLoad.cpp:93-101).
 
-`simplify` is a seeded-subset STAND-IN for the reference's AIVS simplification
-(Method_AIVS_SimPro.hpp), which sits before the hot path and is out of scope this round
-(SURVEY.md 8 f1): the hot path only needs clouds of the size AIVS would hand it
+`simplify` is a seeded subset used only where a test wants GIVEN simplified clouds (the sim_s / sim_t mode of the
+batch API); the registration path itself runs the real AIVS simplification (Method_AIVS_SimPro.hpp) on the device
 (pNumber = min(|S|,|T|)/2 capped at 2000, KSS_ICP.hpp:57-66).
 """
 import numpy as np
@@ -228,6 +227,28 @@ def scan_pair(index, n, config=4, angle_deg=5.0, shift=0.02):
     c = t.mean(0)
     s = (s - c) @ R.T + c + shift * axis
     return dict(full_t=f32r(t), full_s=f32r(s), R=R, t=shift * axis)
+
+
+def c1_pair(model_points, n=10000, index=1, config=1):
+    """config 1 (BASELINE.json configs[0]): source = `model_points` (the reference's Armadillo.gird,
+    43 871 points; tests/golden/fullsize_pairs.npz) decimated to n points by a seeded shuffle; target = a random
+    similarity of an INDEPENDENT n-point subsample of the same file"""
+    rng = _rng(config, index)
+    pts = np.asarray(model_points, np.float64)
+    src = pts[rng.permutation(len(pts))[:n]]
+    tgt0 = pts[rng.permutation(len(pts))[:n]]
+    R, sc, tr = random_similarity(rng)
+    return dict(full_s=f32r(src), full_t=apply_similarity(tgt0, R, sc, tr), R=R, scale=sc, t=tr)
+
+
+def c5_pair(model_points, keep_frac, index=0, n=10000, config=5):
+    """config 5: a C1-style pair whose SOURCE is cropped by a random half-space to keep_frac of its points
+    (partial / defective overlap)"""
+    p = c1_pair(model_points, n=n, index=100 + index, config=config)
+    rng = _rng(config, 1000 + index)
+    p["full_s"] = crop_halfspace(p["full_s"], keep_frac, rng)
+    p["keep_frac"] = keep_frac
+    return p
 
 
 def crop_halfspace(points, keep_frac, rng):

@@ -24,24 +24,28 @@ def _check(r, o, metrics_rtol=0.0):
     assert np.allclose(got, exp, rtol=metrics_rtol, atol=0) if metrics_rtol else np.array_equal(got, exp)
 
 
+def _raw_oracle(okss, full_s, full_t, want_points=False):
+    """the oracle through the raw path: pNumber rule (KSS_ICP.hpp:57-66) and AIVS of both clouds, then the registration"""
+    pn = min(min(len(full_s), len(full_t)) // 2, 2000)
+    ss = okss.aivs_simplify(full_s, pn)[0]; st = okss.aivs_simplify(full_t, pn)[0]
+    return okss.register(ss, st, full_s, full_t, sum_order=okss.SUM_CANON256, want_points=want_points)
+
+
 def test_c1_10k_pair(ctx, okss, pkg):
-    """configs[0]: ~10k-point pair with a random similarity; pNumber = 2000, 729 hypotheses, iter 1000.
-    Simplified clouds run on the small path, the 10k full clouds on the large path (PCR_QM: 1e-12)."""
-    rng = np.random.default_rng(101)
+    """configs[0]: ~10k-point pair with a random similarity, RAW path (AIVS to pNumber = 2000 inside the library),
+    729 hypotheses, iter 1000; the 10k full clouds take the large path (PCR_QM: 1e-12).  The Armadillo pair of the
+    reference's own data is in tests/test_gpu_refdata.py; this one is a synthetic CAD shape."""
     p = pkg.synth.modelnet_pair(900, n_full=10000, config=1)
-    sim_s = pkg.synth.simplify(p["full_s"], 2000, rng); sim_t = pkg.synth.simplify(p["full_t"], 2000, rng)
-    r = ctx.register(sim_s, sim_t, p["full_s"], p["full_t"])
-    o = okss.register(sim_s, sim_t, p["full_s"], p["full_t"], sum_order=okss.SUM_CANON256)
-    _check(r, o, metrics_rtol=1e-12)
+    r = ctx.register_batch(None, None, p["full_s"][None], p["full_t"][None])[0]
+    _check(r, _raw_oracle(okss, p["full_s"], p["full_t"]), metrics_rtol=1e-12)
 
 
 def test_c2_100k_noisy_nonuniform(ctx, okss, pkg):
     """configs[1]: 100k-point procedural surface, density ~ exp(2x), Gaussian noise on the source"""
-    rng = np.random.default_rng(102)
     p = pkg.synth.surface_pair(0, 100000)
-    sim_s = pkg.synth.simplify(p["full_s"], 2000, rng); sim_t = pkg.synth.simplify(p["full_t"], 2000, rng)
-    r, pa = ctx.register(sim_s, sim_t, p["full_s"], p["full_t"], want_points=True)
-    o = okss.register(sim_s, sim_t, p["full_s"], p["full_t"], sum_order=okss.SUM_CANON256, want_points=True)
+    res, pa = ctx.register_batch(None, None, p["full_s"][None], p["full_t"][None], want_points=True)    # raw: AIVS of 100k points inside
+    r, pa = res[0], pa[0]
+    o = _raw_oracle(okss, p["full_s"], p["full_t"], want_points=True)
     _check(r, o, metrics_rtol=1e-12)
     assert np.array_equal(pa, o["point_align"])
     # correspondences of the full-resolution aligned cloud against the full target: all identical
@@ -68,11 +72,14 @@ def test_c5_partial_overlap(ctx, okss, pkg, keep):
     rng = np.random.default_rng(int(keep * 100))
     p = pkg.synth.modelnet_pair(950 + int(keep * 10), n_full=4000, config=5)
     full_s = pkg.synth.crop_halfspace(p["full_s"], keep, rng)
-    pn = min(min(len(full_s), len(p["full_t"])) // 2, 2000)
-    sim_s = pkg.synth.simplify(full_s, pn, rng); sim_t = pkg.synth.simplify(p["full_t"], pn, rng)
-    r = ctx.register(sim_s, sim_t, full_s, p["full_t"])
-    o = okss.register(sim_s, sim_t, full_s, p["full_t"], sum_order=okss.SUM_CANON256)
+    r = ctx.register_batch(None, None, full_s[None], p["full_t"][None])[0]                     # raw path
+    o = _raw_oracle(okss, full_s, p["full_t"])
     _check(r, o, metrics_rtol=1e-12)
-    # and through the hypothesis-sharded driver (what 8 GPUs run, here world = 1)
-    d = pkg.dist.register_hypothesis_sharded(ctx, sim_s, sim_t, full_s, p["full_t"], list_angles=pkg.sweep_angles(8.0)[1])
-    assert d["winner"] == o["winner"] and np.array_equal(d["T"], o["T"])
+    # and through the hypothesis-sharded entry of the library (what 8 GPUs run; here world = 1) ...
+    d = ctx.register_batch_hyp_sharded(None, None, full_s[None], p["full_t"][None])[0]
+    _check(d, o, metrics_rtol=1e-12)
+    # ... and the Python driver over the single-object calls, on the oracle-simplified clouds
+    pn = min(min(len(full_s), len(p["full_t"])) // 2, 2000)
+    sim_s = okss.aivs_simplify(full_s, pn)[0]; sim_t = okss.aivs_simplify(p["full_t"], pn)[0]
+    e = pkg.dist.register_hypothesis_sharded(ctx, sim_s, sim_t, full_s, p["full_t"])
+    assert e["winner"] == o["winner"] and np.array_equal(e["T"], o["T"])
