@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--no-1m", action="store_true", help="skip the 1M-point ICP-iteration roofline leg")
     ap.add_argument("--points-1m", type=int, default=1000000)
     ap.add_argument("--only-1m", action="store_true", help="debug: run only the 1M-point leg")
+    ap.add_argument("--config", default="all", choices=["all", "c3", "c1", "c2", "c4pipe", "c5"],
+                    help="all: the headline batch (c3) plus one leg per other BASELINE.json configuration; cN: only that leg")
     return ap.parse_args()
 
 
@@ -101,6 +103,38 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+def c3_kernel_rooflines(stages, res, pairs, clocks):
+    """what bounds the headline step: the three big stages are not HBM-bound (24-48 KB per pair lives in shared memory / L2)
+    but issue-bound.  Per stage: exact-NN queries/s from the live stage time, and the warp-instruction issue rate against
+    148 SMs x 4 schedulers x clock, with the instruction count per pair taken from the committed ncu capture
+    (profiles/r02_c3_kernels.json, same workload)."""
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_c3_kernels.json")))
+    except Exception:
+        prof = {}
+    clk = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = 148 * 4 * clk * 1e6
+    n_s = N_FULL // 2
+    q = {"sweep": 729.0 * n_s * pairs,
+         "icp_hyp": float(res["total_icp_iters"].sum() - res["final_iters"].sum() + res["n_icp_runs"].sum() - len(res)) * n_s}
+    out = {"issue_peak_warp_inst_per_s": peak, "sm_mhz": clk,
+           "note": "stage times: single-lane untimed extra step (stage_ms_single_lane_rank0); warp instructions per pair: ncu capture"}
+    for st_name, kern in (("sweep", "sweep_kernel"), ("icp_hyp", "icp_small_kernel"), ("cg_build", "cg_build (6 kernels)"), ("aivs", "aivs_small_kernel")):
+        ms = stages.get(st_name, 0.0)
+        if not ms:
+            continue
+        d = {"kernel": kern, "ms": ms}
+        if st_name in q:
+            d["nn_queries_per_s"] = q[st_name] / (ms * 1e-3)
+        wi = prof.get(kern, {}).get("warp_inst_per_pair")
+        if wi:
+            d["warp_inst_per_s"] = wi * pairs / (ms * 1e-3)
+            d["frac_of_issue_peak"] = d["warp_inst_per_s"] / peak
+            d["warp_inst_per_pair_ncu"] = wi
+        out[st_name] = d
+    return out
 
 
 def shard(total, world, rank):
@@ -169,6 +203,34 @@ def main():
     pkg = entry.load_package()
     stream = torch.cuda.Stream(device=local)
     ctx = pkg.Context(local, stream=stream.cuda_stream)
+    if world > 1:
+        # the library's own NCCL communicator (hypothesis sharding, config 5): rank 0's id handed out through torch
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda:%d" % local)
+        if rank == 0:
+            idt.copy_(torch.tensor(list(pkg.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.nccl_init(bytes(idt.cpu().tolist()), rank, world)
+
+    import bench_configs
+    if args.config not in ("all", "c3"):
+        from oracle import okss
+        okss.build()
+        def _bar():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        if args.config == "c5":
+            leg = bench_configs.leg_c5(pkg, ctx, okss, world, rank, barrier=_bar)
+        elif rank == 0:
+            leg = {"c1": bench_configs.leg_c1, "c2": bench_configs.leg_c2, "c4pipe": bench_configs.leg_c4pipe}[args.config](pkg, ctx, okss)
+        else:
+            leg = None
+        if rank == 0:
+            print(json.dumps({"config": args.config, "n_gpus": world, **leg}))
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     if args.only_1m:
         import bench_large
@@ -256,10 +318,27 @@ def main():
         dist.all_reduce(tl)
         launches = int(tl[0])
 
+    # ---- config 5 on every rank (hypotheses sharded over the ranks inside the library); the other configurations at N = 1
+    configs = {}
+    if args.config == "all":
+        from oracle import okss as _ok
+        if rank == 0:
+            _ok.build()
+        barrier()
+        c5 = bench_configs.leg_c5(pkg, ctx, _ok, world, rank, barrier=barrier)
+        if rank == 0:
+            configs["c5"] = c5
+            if world == 1:
+                configs["c1"] = bench_configs.leg_c1(pkg, ctx, _ok)
+                configs["c2"] = bench_configs.leg_c2(pkg, ctx, _ok)
+                if not args.no_1m:
+                    configs["c4pipe"] = bench_configs.leg_c4pipe(pkg, ctx, _ok, n=args.points_1m)
+
     # ---- N=1 only: the 1M-point full-resolution ICP iteration (roofline) and the CPU baseline
     roofline = None
     extra = {}
     cpu_baseline = None
+    order_stat = None
     if rank == 0:
         hbm_peak, which = peaks()
         try:
@@ -274,12 +353,20 @@ def main():
             okss.build()
             n, cores = cpu_sample_pairs(args, okss)
             t0 = time.perf_counter()
-            okss.register_batch(None, None, hnp["full_s"][:n], hnp["full_t"][:n], step=STEP,
-                                max_iter=MAX_ITER, sum_order=okss.SUM_SERIAL, method=okss.NN_KDTREE, threads=0)
+            serial, _ = okss.register_batch(None, None, hnp["full_s"][:n], hnp["full_t"][:n], step=STEP,
+                                            max_iter=MAX_ITER, sum_order=okss.SUM_SERIAL, method=okss.NN_KDTREE, threads=0)
             dt = time.perf_counter() - t0
+            n1 = min(8, n)                                        # the faithful single-thread figure (the reference is serial)
+            t1 = time.perf_counter()
+            okss.register_batch(None, None, hnp["full_s"][:n1], hnp["full_t"][:n1], step=STEP, max_iter=MAX_ITER,
+                                sum_order=okss.SUM_SERIAL, method=okss.NN_KDTREE, threads=1)
+            dt1 = time.perf_counter() - t1
             cpu_baseline = {"value": n / dt, "unit": "registrations/s", "cores": cores, "kind": "port",
                             "sample": "first %d of the %d pairs, oracle port (AIVS + kd-tree NN, serial sums), %d threads, %.1f s"
-                                      % (n, args.pairs, cores, dt)}
+                                      % (n, args.pairs, cores, dt),
+                            "single_thread": {"value": n1 / dt1, "unit": "registrations/s", "cores": 1,
+                                              "sample": "first %d pairs, one host thread, %.1f s" % (n1, dt1)}}
+            order_stat = bench_configs.order_statistic(okss, hnp["full_s"], hnp["full_t"], serial[:min(n, 128)])
         # parity spot check of the timed output (not timed): first pair against the oracle
         line = {"metric": METRIC, "value": args.pairs / (ms_dev / 1000.0), "unit": "registrations/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
@@ -294,15 +381,17 @@ def main():
                         "h2d_bytes_per_step": h2d * world if world > 1 else h2d,
                         "d2h_bytes_per_step": d2h * world if world > 1 else d2h, "ms_per_step": ms_e2e},
                 "gpu_launches": launches, "clocks": clocks, "stage_ms_single_lane_rank0": stages,
-                "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "configs": configs}
         line.update(extra)
+        line["c3_kernels"] = c3_kernel_rooflines(stages, res_np, args.pairs if world == 1 else P, clocks)
         r0 = res_np[0]
         line["result_sample"] = {"pair0_rmse": float(r0["rmse"]), "pair0_winner": int(r0["winner"]),
                                  "mean_icp_runs": float(res_np["n_icp_runs"].mean()),
                                  "mean_icp_iters": float(res_np["total_icp_iters"].mean()),
                                  "mean_minima": float(res_np["n_minima"].mean()),
                                  "multi_fraction": float(res_np["branch_multi"].mean()),
-                                 "overflow_pairs": int(res_np["overflow"].sum())}
+                                 "overflow_pairs": int(res_np["overflow"].sum()),
+                                 "summation_order_serial_vs_canon256": order_stat}
         print(json.dumps(line))
     ctx.close()
     if world > 1:

@@ -1,0 +1,155 @@
+"""bench_configs.py -- the BASELINE.json configurations other than the headline batch, each timed through the
+host-buffer C ABI (H2D / D2H inside), spot-checked against the oracle and with the oracle port's CPU time beside it:
+
+  c1     configs[0]: the 10k Armadillo pair (reference data, tests/golden/fullsize_pairs.npz) with a random similarity,
+         the flow of Main_KSS_ICP.cpp:79-88 (pNumber 2000, AIVS, 729 hypotheses, ICP iter 1000, PCR_QM at 10k x 10k)
+  c2     configs[1]: 100k-point procedural pair, Gaussian noise + non-uniform density (AIVS of 100k points, PCR_QM 100k x 100k)
+  c4pipe configs[3] as the reference would run it: 1M x 1M pair -> AIVS to 2000 -> hot path -> PCR_QM at 1M x 1M
+         (registrationMeasure.hpp:47-98 is the only full-resolution stage)
+  c5     configs[4]: pairs cropped to 30 / 50 / 70 %, full 729-hypothesis sweep and every local-minimum ICP run, the
+         hypotheses sharded over the ranks inside the library (ncclAllGather of the score slabs + ONE ncclAllReduce(min));
+         time-to-winner per pair, winner compared with the oracle
+
+The oracle is used as the checker and as the CPU figure (a single pair runs on ONE host thread: the reference is serial)."""
+import os
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _fixture():
+    return np.load(os.path.join(HERE, "tests", "golden", "fullsize_pairs.npz"))
+
+
+def _raw_oracle(okss, s, t):
+    t0 = time.perf_counter()
+    pn = min(min(len(s), len(t)) // 2, 2000)                                   # KSS_ICP.hpp:57-66
+    ss = okss.aivs_simplify(s, pn)[0]; st = okss.aivs_simplify(t, pn)[0]
+    o = okss.register(ss, st, s, t, sum_order=okss.SUM_CANON256, method=okss.NN_KDTREE)
+    return o, time.perf_counter() - t0
+
+
+def _parity(r, o):
+    T = np.asarray(r["T"]).reshape(4, 4)
+    R1, R2 = T[:3, :3].astype(np.float64), o["T"][:3, :3].astype(np.float64)
+    return {"winner_equal": bool(int(r["winner"]) == o["winner"]), "n_minima_equal": bool(int(r["n_minima"]) == o["n_minima"]),
+            "T_bit_equal": bool(np.array_equal(T, o["T"])),
+            "rotation_delta_rad": float(np.arccos(np.clip((np.trace(R1.T @ R2) - 1) / 2, -1, 1))),
+            "rmse_rel_delta": float(abs(float(r["rmse"]) - o["rmse"]) / max(o["rmse"], 1e-300)),
+            "icp_iters_equal": bool(int(r["total_icp_iters"]) == o["total_icp_iters"])}
+
+
+def _time_calls(fn, reps):
+    fn()                                                                       # warm-up (buffers grow once)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(1000.0 * (time.perf_counter() - t0))
+    return float(np.median(ts)), ts
+
+
+def single_pair_leg(name, what, pkg, ctx, okss, p, reps, truth_R=None):
+    s, t = p["full_s"], p["full_t"]
+    out = {}
+
+    def call():
+        out["r"] = ctx.register_batch(None, None, s[None], t[None])[0]
+    ms, _ = _time_calls(call, reps)
+    o, cpu_s = _raw_oracle(okss, s, t)
+    r = out["r"]
+    leg = {"workload": what, "source_points": int(len(s)), "target_points": int(len(t)),
+           "ms_per_registration_e2e": ms, "registrations_per_s": 1000.0 / ms,
+           "h2d_bytes": int((len(s) + len(t)) * 24), "timing": "host clock around kss_register_batch (host buffers in, results out), median of %d" % reps,
+           "rmse": float(r["rmse"]), "hypotheses": int(r["n_minima"]), "icp_iters": int(r["total_icp_iters"]),
+           "parity_vs_oracle": _parity(r, o),
+           "cpu_port": {"seconds": cpu_s, "registrations_per_s": 1.0 / cpu_s, "cores": 1,
+                        "what": "oracle port, one pair on ONE host thread (the reference is serial): AIVS + sweep + ICP runs + PCR_QM"},
+           "speedup_vs_cpu_port_single_thread": cpu_s * 1000.0 / ms}
+    return leg
+
+
+def leg_c1(pkg, ctx, okss, reps=5):
+    p = pkg.synth.c1_pair(_fixture()["Armadillo_gird"])
+    return single_pair_leg("c1", "configs[0]: Armadillo.gird 10k pair, random similarity, Main_KSS_ICP.cpp flow", pkg, ctx, okss, p, reps)
+
+
+def leg_c2(pkg, ctx, okss, reps=3):
+    p = pkg.synth.surface_pair(0, 100000)
+    return single_pair_leg("c2", "configs[1]: 100k-point pair, Gaussian noise, non-uniform density", pkg, ctx, okss, p, reps)
+
+
+def leg_c4pipe(pkg, ctx, okss, reps=3, n=1000000):
+    p = pkg.synth.scan_pair(0, n)
+    return single_pair_leg("c4pipe", "configs[3], reference-faithful pipeline: %d x %d pair -> AIVS to 2000 -> hot path -> PCR_QM at full resolution" % (n, n),
+                           pkg, ctx, okss, p, reps)
+
+
+def c5_batch(pkg, variants=8):
+    """3 crop levels x `variants` random similarities / crop planes of the 10k Armadillo pair"""
+    arm = _fixture()["Armadillo_gird"]
+    ps = [pkg.synth.c5_pair(arm, keep, index=3 * v + i) for v in range(variants) for i, keep in enumerate((0.3, 0.5, 0.7))]
+    cS = np.array([len(p["full_s"]) for p in ps], np.int32); cT = np.array([len(p["full_t"]) for p in ps], np.int32)
+    fs = np.zeros((len(ps), cS.max(), 3)); ft = np.zeros((len(ps), cT.max(), 3))
+    for i, p in enumerate(ps):
+        fs[i, :cS[i]] = p["full_s"]; ft[i, :cT[i]] = p["full_t"]
+    return ps, fs, ft, cS, cT
+
+
+def leg_c5(pkg, ctx, okss, world, rank, reps=5, barrier=None):
+    """every rank calls this; hypotheses sharded over the ranks of ctx's communicator (world = 1: unsharded)"""
+    ps, fs, ft, cS, cT = c5_batch(pkg)
+    out = {}
+
+    def call():
+        if barrier:
+            barrier()
+        out["r"] = ctx.register_batch_hyp_sharded(None, None, fs, ft, counts=(None, None, cS, cT))
+    ms, ts = _time_calls(call, reps)
+    if rank != 0:
+        return None
+    res = out["r"]
+    par, cpu_s = [], 0.0
+    checked = ps[:3]                                                            # one pair per crop level against the oracle
+    for i, p in enumerate(checked):
+        o, dt = _raw_oracle(okss, p["full_s"], p["full_t"])
+        cpu_s += dt
+        d = _parity(res[i], o)
+        d["keep_frac"] = p["keep_frac"]; d["winner"] = int(res[i]["winner"]); d["hypotheses"] = int(res[i]["n_minima"])
+        par.append(d)
+    return {"workload": "configs[4]: %d Armadillo 10k pairs, source cropped to 30 / 50 / 70 %%, 729-hypothesis sweep + all local-minimum ICP runs" % len(ps),
+            "pairs": len(ps), "ranks": world, "sharding": "sweep slabs + ncclAllGather, ICP runs round-robin + one ncclAllReduce(min), inside the library" if world > 1 else "none (1 rank)",
+            "ms_time_to_winner_per_pair": ms / len(ps), "ms_per_call": ms, "registrations_per_s": 1000.0 * len(ps) / ms,
+            "timing": "host clock around kss_register_batch_hyp_sharded on rank 0 after a barrier (host buffers), median of %d" % reps,
+            "winner_equals_oracle": bool(all(d["winner_equal"] for d in par)), "parity_vs_oracle": par,
+            "cpu_port": {"seconds_per_pair": cpu_s / len(checked), "cores": 1, "what": "oracle port, one host thread per pair, first %d pairs" % len(checked)},
+            "speedup_vs_cpu_port_single_thread": (cpu_s / len(checked)) * 1000.0 / (ms / len(ps)),
+            "note": "a single pair's 729 sweep hypotheses (81 CTAs) and its 7-20 local-minimum ICP runs (one CTA each) already run "
+                    "concurrently on one B200 (148 SMs x 4 CTAs), so sharding them lowers the time to the winner only when the batch "
+                    "saturates a GPU; the sharded path also repeats the winner's run (KSS_ICP.hpp:130) instead of reusing it"}
+
+
+def order_statistic(okss, full_s, full_t, serial_results):
+    """the honest error bar of an oracle whose float summation order is a choice (Eigen's is unknown): the same pairs in
+    SUM_SERIAL (given) and SUM_CANON256 order"""
+    n = len(serial_results)
+    canon, _ = okss.register_batch(None, None, full_s[:n], full_t[:n], sum_order=okss.SUM_CANON256, method=okss.NN_KDTREE, threads=0)
+    dw = di = 0
+    ang, dfit_other = [], []
+    for a, c in zip(serial_results, canon):
+        if a["winner"] != c["winner"]:
+            dw += 1
+            dfit_other.append(abs(a["final_fitness"] - c["final_fitness"]) / max(a["final_fitness"], 1e-300))
+            continue
+        if a["final_iters"] != c["final_iters"]:
+            di += 1
+        R1, R2 = a["T"][:3, :3].astype(np.float64), c["T"][:3, :3].astype(np.float64)
+        ang.append(float(np.arccos(np.clip((np.trace(R1.T @ R2) - 1) / 2, -1, 1))))
+    ang = np.array(ang) if ang else np.zeros(1)
+    return {"pairs": n, "winner_differs": dw, "same_winner_final_iters_differ": di,
+            "same_winner_rotation_delta_rad": {"max": float(ang.max()), "p99": float(np.quantile(ang, 0.99)), "median": float(np.median(ang)),
+                                               "above_1e-4": int((ang > 1e-4).sum())},
+            "different_winner_max_rel_fitness_delta": float(max(dfit_other)) if dfit_other else 0.0,
+            "note": "different winners are symmetry-equivalent local minima of CAD-like shapes (fitness equal to ~1e-6 relative)"}

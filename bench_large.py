@@ -40,6 +40,7 @@ def icp_iteration_roofline(pkg, ctx, args, hbm_peak, which, stream=None):
     build_ms = ctx.stage_ms(7)[0]
     # a whole run as a user would make it (kss_icp semantics): build + iterations to PCL's convergence + fitness pass
     import time as _time
+    ctx.icp(p["full_s"], p["full_t"])                      # untimed: the one-shot entry has its own buffers (cudaMalloc)
     t0 = _time.perf_counter()
     whole = ctx.icp(p["full_s"], p["full_t"])
     whole_ms = 1000.0 * (_time.perf_counter() - t0)
