@@ -498,6 +498,7 @@ void kss_ctx_destroy(kss_ctx* ctx) {
     collect_spans(ctx);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto& kv : ctx->bufs) if (kv.second.p) cudaFree(kv.second.p);
+    if (ctx->large_run.h_unres) cudaFreeHost(ctx->large_run.h_unres);
     for (int l = 0; l < kss_ctx::MAX_LANES; ++l) {
         if (ctx->lane_stream[l]) cudaStreamDestroy(ctx->lane_stream[l]);
         if (ctx->lane_done[l]) cudaEventDestroy(ctx->lane_done[l]);

@@ -1018,9 +1018,9 @@ lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur_s, float4* __r
             Best b; b.d = d2_rn(x, y, z, tprev.x, tprev.y, tprev.z); b.idx = (unsigned)pv;
             const float ubd = b.d;
             const float rc = sqrtf(ubd) * g.inv_h * 1.00001f + 0.003f;
-            if (rc <= 1.6f) {                                        // (false for NaN too)
+            if (rc <= 2.6f) {                                        // (false for NaN too)
                 const float fx = (x - g.lo[0]) * g.inv_h, fy = (y - g.lo[1]) * g.inv_h, fz = (z - g.lo[2]) * g.inv_h;
-                // the previous match is a target inside the grid and at most 1.6 cells away: no integer overflow
+                // the previous match is a target inside the grid and at most 2.6 cells away: no integer overflow
                 const int xl = max((int)floorf(fx - rc), 0), xh = min((int)floorf(fx + rc), g.nf[0] - 1);
                 const int yl = max((int)floorf(fy - rc), 0), yh = min((int)floorf(fy + rc), g.nf[1] - 1);
                 const int zl = max((int)floorf(fz - rc), 0), zh = min((int)floorf(fz + rc), g.nf[2] - 1);
@@ -1063,12 +1063,13 @@ lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur_s, float4* __r
 // bound reads the cells meeting the cube q +- sqrt(bound) (lane = row, up to 17 x 17 rows); the rest goes to the pyramid.
 __global__ void __launch_bounds__(256)
 lg_left_kernel(Pyramid py, LgGridView gv, int n_q, const float4* __restrict__ cur_s, float4* __restrict__ rec,
-               int* __restrict__ prev_s, const int* __restrict__ worklist, LgState* __restrict__ st, double max_dist_sqr) {
+               int* __restrict__ prev_s, const int* __restrict__ worklist, LgState* __restrict__ st, double max_dist_sqr,
+               int staged_launched) {
     __shared__ LgGeom g;
     __shared__ float4 slots[8][TILE];
     if (st->done) return;
     const unsigned nu = st->n_unres;
-    if (nu > (unsigned)n_q / 8u) return;                             // many: lg_nn_kernel<1> staged them
+    if (staged_launched && nu > (unsigned)n_q / 8u) return;          // many: lg_nn_kernel<1> staged them
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < (int)(sizeof(LgGeom) / 4)) reinterpret_cast<int*>(&g)[tid] = reinterpret_cast<const int*>(gv.geom)[tid];
     __syncthreads();
@@ -1230,7 +1231,8 @@ __device__ __forceinline__ bool lg_last_block(unsigned* ticket) {
 // rec[2i] = {source xyz, d2}, rec[2i+1] = {target xyz, bits(index or -1)}: a lane's 8 records are two coalesced streams
 __global__ void __launch_bounds__(256)
 lg_passA_kernel(const float4* __restrict__ rec, int n, int nchunks, float* __restrict__ partA /* [nchunks][6] */,
-                double* __restrict__ partD, int* __restrict__ partK, LgState* __restrict__ st) {
+                double* __restrict__ partD, int* __restrict__ partK, LgState* __restrict__ st,
+                volatile int* __restrict__ h_unres /* pinned host word: how many queries the refine kernel left over */) {
     if (st->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * 8 + warp;
@@ -1282,6 +1284,7 @@ lg_passA_kernel(const float4* __restrict__ rec, int n, int nchunks, float* __res
     if ((threadIdx.x & 31) == 0 && k) atomicAdd(&kept_s, k);
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (h_unres) *h_unres = (int)min(st->n_unres, 0x7fffffffu);  // the host reads it, stale, to decide which general kernel to enqueue
         st->n_unres = 0u;                                            // (all search kernels of this iteration are done)
         const int cnt = kept_s;
         st->kept = cnt;
@@ -1600,8 +1603,9 @@ int large_icp_host(cudaStream_t st, long long* launches, const double* src, int 
     int r = large_icp_prepare(st, launches, d_s, n_s, d_t, n_t, alloc, &run, "");
     if (r) return r;
     r = large_icp_run(st, launches, &run, prm, 0);
-    if (r) return r;
-    return large_icp_result(st, &run, T, fitness, iters, converged);
+    if (!r) r = large_icp_result(st, &run, T, fitness, iters, converged);
+    if (run.h_unres) { cudaStreamSynchronize(st); cudaFreeHost(run.h_unres); }
+    return r;
 }
 
 // ---- reusable pieces (bench.py times large_icp_iterations on a prepared run)
@@ -1633,6 +1637,8 @@ int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, i
     if (r) return r;
     cudaMemcpyAsync(cur, inp, sizeof(float4) * (size_t)n_s, cudaMemcpyDeviceToDevice, st);
     cudaMemsetAsync(prev, 0xff, sizeof(int) * (size_t)n_s, st);
+    if (!run->h_unres && cudaHostAlloc((void**)&run->h_unres, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); run->h_unres = nullptr; }
+    if (run->h_unres) *run->h_unres = 0x7fffffff;             // nothing known yet: the first iterations stage
     lg_state_init_kernel<<<1, 32, 0, st>>>(state);
     c.launched();
     static_assert(sizeof(Pyramid) <= sizeof(run->pyramid), "LargeIcp::pyramid too small");
@@ -1655,16 +1661,20 @@ int large_icp_iterations(cudaStream_t st, long long* launches, LargeIcp* run, co
         if (run->mark) run->mark(run->mark_user, KSS_STAGE_LARGE_NN, 1);
         // correspondences: the refine kernel finishes every query whose last match bounds the search to a few cells;
         // the general kernels take what it flags (staged CTAs when many, one warp per query when few)
+        // (the host knows the left-over count of an EARLIER iteration from a pinned word passA writes: it only decides
+        // whether the staged kernel is worth a launch; the one-warp-per-query kernel always runs and takes any count)
+        const int known = run->h_unres ? *(volatile int*)run->h_unres : 0x7fffffff;
+        const bool staged = known > n / 8;
         lg_refine_kernel<<<(n + 255) / 256, 256, 0, st>>>(gv, n, (float4*)run->cur, (float4*)run->rec, run->prev, run->flag, run->worklist, state, max2);
-        launch_nn<1>(st, py, gv, n, (float4*)run->cur, nullptr, nullptr, nullptr, (float4*)run->rec, run->prev, run->flag, state, max2);
-        lg_left_kernel<<<148, 256, 0, st>>>(py, gv, n, (const float4*)run->cur, (float4*)run->rec, run->prev, run->worklist, state, max2);
+        if (staged) launch_nn<1>(st, py, gv, n, (float4*)run->cur, nullptr, nullptr, nullptr, (float4*)run->rec, run->prev, run->flag, state, max2);
+        lg_left_kernel<<<148, 256, 0, st>>>(py, gv, n, (const float4*)run->cur, (float4*)run->rec, run->prev, run->worklist, state, max2, staged ? 1 : 0);
         if (run->mark) { run->mark(run->mark_user, KSS_STAGE_LARGE_NN, 0); run->mark(run->mark_user, KSS_STAGE_LARGE_REDUCE, 1); }
-        lg_passA_kernel<<<(nch + 7) / 8, 256, 0, st>>>((const float4*)run->rec, n, nch, run->partA, run->partD, run->partK, state);
+        lg_passA_kernel<<<(nch + 7) / 8, 256, 0, st>>>((const float4*)run->rec, n, nch, run->partA, run->partD, run->partK, state, run->h_unres);
         lg_passB_kernel<<<(nch + 7) / 8, 256, 0, st>>>((const float4*)run->rec, n, nch, run->partB, state, prm->max_iterations,
                                                        1.0 - prm->transformation_eps, prm->transformation_eps,
                                                        prm->fitness_eps, mse_abs);
         if (run->mark) run->mark(run->mark_user, KSS_STAGE_LARGE_REDUCE, 0);
-        *launches += 5;
+        *launches += staged ? 5 : 4;
     }
     return cudaGetLastError() == cudaSuccess ? KSS_OK : KSS_ERR_CUDA;
 }

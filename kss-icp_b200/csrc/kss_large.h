@@ -28,6 +28,7 @@ struct LargeIcp {
     void *inp = nullptr, *cur = nullptr, *rec = nullptr, *state = nullptr;
     int *partK = nullptr, *prev = nullptr, *worklist = nullptr;
     unsigned char* flag = nullptr;
+    int* h_unres = nullptr;             // pinned host word (mapped): left-over count of an earlier iteration
     float *d2 = nullptr, *partA = nullptr, *partB = nullptr;
     double *partD = nullptr, *out3 = nullptr;
     // optional stage marks (CUDA-event timing by the context): mark(user, KSS_STAGE_*, begin?1:0)
