@@ -229,6 +229,26 @@ def scan_pair(index, n, config=4, angle_deg=5.0, shift=0.02):
     return dict(full_t=f32r(t), full_s=f32r(s), R=R, t=shift * axis)
 
 
+def transfer_pc(points, cord, angle, rate=1.0, dis=0.0):
+    """the reference's TransferPC (transferPC.hpp:66-130): rotate about axis `cord` (1 x, 2 y, else z; the convention of
+    initRegistration_Transfer), scale about the centroid, translate all three coordinates by `dis` -- in that order"""
+    p = np.array(points, np.float64)
+    c, s_ = np.cos(angle), np.sin(angle)
+    x, y, z = p[:, 0].copy(), p[:, 1].copy(), p[:, 2].copy()
+    if cord == 1:
+        p[:, 1] = y * c - z * s_; p[:, 2] = y * s_ + z * c
+    elif cord == 2:
+        p[:, 0] = z * s_ + x * c; p[:, 2] = z * c - x * s_
+    else:
+        p[:, 0] = x * c - y * s_; p[:, 1] = x * s_ + y * c
+    if rate != 1.0:
+        m = np.array([np.add.reduce(p[:, a]) / len(p) for a in range(3)])
+        p = (p - m) * rate + m
+    if dis != 0.0:
+        p = p + dis
+    return p
+
+
 def c1_pair(model_points, n=10000, index=1, config=1):
     """config 1 (BASELINE.json configs[0]): source = `model_points` (the reference's Armadillo.gird,
     43 871 points; tests/golden/fullsize_pairs.npz) decimated to n points by a seeded shuffle; target = a random
