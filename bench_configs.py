@@ -19,6 +19,12 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def rot_delta(R1, R2):
+    """angle between two rotations from the chord |R1 - R2|_F = 2 sqrt(2) sin(angle / 2) (well conditioned near zero,
+    unlike arccos of the trace: fp32 rotation matrices are orthonormal only to 1e-7, which arccos turns into 1e-3)"""
+    return 2.0 * float(np.arcsin(min(1.0, float(np.linalg.norm(np.asarray(R1, np.float64) - np.asarray(R2, np.float64))) / (2.0 * np.sqrt(2.0)))))
+
+
 def _fixture():
     return np.load(os.path.join(HERE, "tests", "golden", "fullsize_pairs.npz"))
 
@@ -36,7 +42,7 @@ def _parity(r, o):
     R1, R2 = T[:3, :3].astype(np.float64), o["T"][:3, :3].astype(np.float64)
     return {"winner_equal": bool(int(r["winner"]) == o["winner"]), "n_minima_equal": bool(int(r["n_minima"]) == o["n_minima"]),
             "T_bit_equal": bool(np.array_equal(T, o["T"])),
-            "rotation_delta_rad": float(np.arccos(np.clip((np.trace(R1.T @ R2) - 1) / 2, -1, 1))),
+            "rotation_delta_rad": rot_delta(R1, R2),
             "rmse_rel_delta": float(abs(float(r["rmse"]) - o["rmse"]) / max(o["rmse"], 1e-300)),
             "icp_iters_equal": bool(int(r["total_icp_iters"]) == o["total_icp_iters"])}
 
@@ -146,7 +152,7 @@ def order_statistic(okss, full_s, full_t, serial_results):
         if a["final_iters"] != c["final_iters"]:
             di += 1
         R1, R2 = a["T"][:3, :3].astype(np.float64), c["T"][:3, :3].astype(np.float64)
-        ang.append(float(np.arccos(np.clip((np.trace(R1.T @ R2) - 1) / 2, -1, 1))))
+        ang.append(rot_delta(R1, R2))
     ang = np.array(ang) if ang else np.zeros(1)
     return {"pairs": n, "winner_differs": dw, "same_winner_final_iters_differ": di,
             "same_winner_rotation_delta_rad": {"max": float(ang.max()), "p99": float(np.quantile(ang, 0.99)), "median": float(np.median(ang)),

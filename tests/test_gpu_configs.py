@@ -9,7 +9,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _rot_err(A, B):
-    return float(np.arccos(np.clip((np.trace(A[:3, :3].astype(np.float64).T @ B[:3, :3].astype(np.float64)) - 1) / 2, -1, 1)))
+    """angle between two rotations from the chord |A - B|_F = 2 sqrt(2) sin(angle / 2): unlike arccos of the trace it is
+    well conditioned near zero (fp32 rotation matrices are orthonormal only to 1e-7, which arccos turns into 1e-3)"""
+    d = float(np.linalg.norm(A[:3, :3].astype(np.float64) - B[:3, :3].astype(np.float64)))
+    return 2.0 * float(np.arcsin(min(1.0, d / (2.0 * np.sqrt(2.0)))))
 
 
 def _check(r, o, metrics_rtol=0.0):

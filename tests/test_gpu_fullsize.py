@@ -7,7 +7,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _rot_angle(R1, R2):
-    return float(np.arccos(np.clip((np.trace(R1.T @ R2) - 1) / 2, -1, 1)))
+    """chord formula: well conditioned near zero, unlike arccos of the trace"""
+    return 2.0 * float(np.arcsin(min(1.0, np.linalg.norm(R1 - R2) / (2.0 * np.sqrt(2.0)))))
 
 
 def test_c3_full_batch_properties(ctx, okss, pkg):

@@ -127,7 +127,7 @@ def test_icp_free_running_bit_exact(ctx, okss, pkg, index, n_full, hyp):
     # reduction order of the reference's Eigen sums is unknown: the serial order agrees to fp32 rounding
     s = okss.icp(src, tgt, sum_order=okss.SUM_SERIAL, method=okss.NN_KDTREE)
     R1, R2 = s["T"][:3, :3].astype(np.float64), g["T"][:3, :3].astype(np.float64)
-    ang = np.arccos(np.clip((np.trace(R1.T @ R2) - 1) / 2, -1, 1))
+    ang = 2.0 * np.arcsin(min(1.0, np.linalg.norm(R1 - R2) / (2.0 * np.sqrt(2.0))))   # chord: well conditioned near zero
     dt = np.abs(s["T"][:3, 3] - g["T"][:3, 3]).max()
     if s["iters"] == o["iters"]:
         assert ang < 1e-4                               # north_star: rotation error < 1e-4 rad
