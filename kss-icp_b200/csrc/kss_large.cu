@@ -26,8 +26,13 @@
 #include "kss_device.cuh"
 #include "kss_large.h"
 
+#ifndef KSS_SCAN_UNROLL
+#define KSS_SCAN_UNROLL 4
+#endif
+
 namespace kss {
 
+constexpr int SCAN_UNROLL = KSS_SCAN_UNROLL;
 constexpr int LG_MAX_LEVELS = 4;     // 32^4 tiles * 32 points = 33.5 M points
 constexpr int LG_SAMPLES = 256;      // nearest-neighbour probe of the build
 
@@ -523,6 +528,9 @@ __device__ __forceinline__ void lg_scan_cells(const Acc& acc, int x0, int x1, in
                     // d2 >= 0: float bits order as integers, so (d2 bits, index) compares as ONE 64-bit key -- smallest
                     // distance, lowest original index among equals
                     unsigned long long bk = ((unsigned long long)__float_as_uint(b.d) << 32) | b.idx;
+                    // (lanes of a warp hold segments of different lengths: a deep unroll makes every lane pay the remainder
+                    // blocks of the longest -- 4 measured best: 0.112 ms vs 0.125 ms with 8 for the 1M-point search)
+#pragma unroll SCAN_UNROLL
                     for (unsigned j = s; j < e; ++j) {
                         const float4 c = p[j];
                         const unsigned long long ck = ((unsigned long long)__float_as_uint(d2_rn(qx, qy, qz, c.x, c.y, c.z)) << 32) | __float_as_uint(c.w);
