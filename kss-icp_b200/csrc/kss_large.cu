@@ -1152,7 +1152,7 @@ __device__ __forceinline__ void lg_finish_f32(const float* __restrict__ part, in
             const int i = (c << 8) + lane + 32 * u;
             have[u] = i < nchunks;
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) v[u][q] = have[u] ? part[(size_t)i * NQ + q] : 0.0f;
+            for (int q = 0; q < NQ; ++q) v[u][q] = have[u] ? __ldcg(part + (size_t)i * NQ + q) : 0.0f;      // (L2: written by other CTAs)
         }
         float p[NQ];
 #pragma unroll
@@ -1196,7 +1196,7 @@ __device__ __forceinline__ double lg_finish_f64(const double* __restrict__ part,
         double v[8];
         bool have[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int i = (c << 8) + lane + 32 * u; have[u] = i < nchunks; v[u] = have[u] ? part[i] : 0.0; }
+        for (int u = 0; u < 8; ++u) { const int i = (c << 8) + lane + 32 * u; have[u] = i < nchunks; v[u] = have[u] ? __ldcg(part + i) : 0.0; }
         double p = 0.0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) if (have[u]) p = __dadd_rn(p, v[u]);
@@ -1235,59 +1235,56 @@ __device__ __forceinline__ bool lg_last_block(unsigned* ticket) {
     return last;
 }
 
-// pass A: per chunk sums of kept source xyz, matched target xyz (float), d2 (double), kept count.
+// ---- the two reduction passes of an iteration (pcl::umeyama demeans before it multiplies: the means first, then sigma)
 // rec[2i] = {source xyz, d2}, rec[2i+1] = {target xyz, bits(index or -1)}: a lane's 8 records are two coalesced streams
-__global__ void __launch_bounds__(256)
-lg_passA_kernel(const float4* __restrict__ rec, int n, int nchunks, float* __restrict__ partA /* [nchunks][6] */,
-                double* __restrict__ partD, int* __restrict__ partK, LgState* __restrict__ st,
-                volatile int* __restrict__ h_unres /* pinned host word: how many queries the refine kernel left over */) {
-    if (st->done) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * 8 + warp;
-    if (c < nchunks) {
-        float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        double dsum = 0.0;
-        int k = 0;
-        const int i0 = (c << 8) + lane;
-        float4 sv[8], tv[8];
+__device__ __forceinline__ void lg_load_chunk(const float4* __restrict__ rec, int n, int c, float4 (&sv)[8], float4 (&tv)[8]) {
+    const int i0 = (c << 8) + (threadIdx.x & 31);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + 32 * u;
-            tv[u].w = __int_as_float(-1);
-            if (i < n) { sv[u] = rec[2 * (size_t)i]; tv[u] = rec[2 * (size_t)i + 1]; }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (__float_as_int(tv[u].w) < 0) continue;
-            a[0] = __fadd_rn(a[0], sv[u].x); a[1] = __fadd_rn(a[1], sv[u].y); a[2] = __fadd_rn(a[2], sv[u].z);
-            a[3] = __fadd_rn(a[3], tv[u].x); a[4] = __fadd_rn(a[4], tv[u].y); a[5] = __fadd_rn(a[5], tv[u].z);
-            dsum = __dadd_rn(dsum, (double)sv[u].w);
-            ++k;
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-#pragma unroll
-            for (int q = 0; q < 6; ++q) a[q] = __fadd_rn(a[q], __shfl_xor_sync(KSS_FULL, a[q], off));
-            dsum = __dadd_rn(dsum, __shfl_xor_sync(KSS_FULL, dsum, off));
-        }
-        k = __reduce_add_sync(KSS_FULL, k);
-        if (lane == 0) {
-#pragma unroll
-            for (int q = 0; q < 6; ++q) partA[(size_t)c * 6 + q] = a[q];
-            partD[c] = dsum; partK[c] = k;
-        }
+    for (int u = 0; u < 8; ++u) {
+        const int i = i0 + 32 * u;
+        tv[u].w = __int_as_float(-1);
+        if (i < n) { sv[u] = rec[2 * (size_t)i]; tv[u] = rec[2 * (size_t)i + 1]; }
     }
-    if (!lg_last_block(&st->ticketA)) return;
-    // ---- last CTA: upper levels, means, mse
+}
+// pass A of one 256-element chunk (one warp): sums of kept source xyz, matched target xyz (float), d2 (double), kept count
+__device__ __forceinline__ void lg_chunk_A(const float4 (&sv)[8], const float4 (&tv)[8], int c, float* __restrict__ partA,
+                                           double* __restrict__ partD, int* __restrict__ partK) {
+    float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    double dsum = 0.0;
+    int k = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        if (__float_as_int(tv[u].w) < 0) continue;
+        a[0] = __fadd_rn(a[0], sv[u].x); a[1] = __fadd_rn(a[1], sv[u].y); a[2] = __fadd_rn(a[2], sv[u].z);
+        a[3] = __fadd_rn(a[3], tv[u].x); a[4] = __fadd_rn(a[4], tv[u].y); a[5] = __fadd_rn(a[5], tv[u].z);
+        dsum = __dadd_rn(dsum, (double)sv[u].w);
+        ++k;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) a[q] = __fadd_rn(a[q], __shfl_xor_sync(KSS_FULL, a[q], off));
+        dsum = __dadd_rn(dsum, __shfl_xor_sync(KSS_FULL, dsum, off));
+    }
+    k = __reduce_add_sync(KSS_FULL, k);
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) partA[(size_t)c * 6 + q] = a[q];
+        partD[c] = dsum; partK[c] = k;
+    }
+}
+// one whole CTA: upper reduction levels of pass A, the means, the mse
+__device__ __forceinline__ void lg_finish_A(int nchunks, const float* __restrict__ partA, const double* __restrict__ partD,
+                                            const int* __restrict__ partK, LgState* __restrict__ st, volatile int* __restrict__ h_unres) {
     __shared__ float tot[16];
     __shared__ int kept_s;
-    if (nchunks == 1) { if (threadIdx.x < 6) tot[threadIdx.x] = partA[threadIdx.x]; __syncthreads(); }
+    if (nchunks == 1) { if (threadIdx.x < 6) tot[threadIdx.x] = __ldcg(partA + threadIdx.x); __syncthreads(); }
     else lg_finish_f32<6>(partA, nchunks, tot);
-    const double dtot = nchunks == 1 ? partD[0] : lg_finish_f64(partD, nchunks);
+    const double dtot = nchunks == 1 ? __ldcg(partD) : lg_finish_f64(partD, nchunks);
     if (threadIdx.x == 0) kept_s = 0;
     __syncthreads();
     int k = 0;
-    for (int i = threadIdx.x; i < nchunks; i += blockDim.x) k += partK[i];
+    for (int i = threadIdx.x; i < nchunks; i += blockDim.x) k += __ldcg(partK + i);
     k = __reduce_add_sync(KSS_FULL, k);
     if ((threadIdx.x & 31) == 0 && k) atomicAdd(&kept_s, k);
     __syncthreads();
@@ -1304,49 +1301,34 @@ lg_passA_kernel(const float4* __restrict__ rec, int n, int nchunks, float* __res
         }
     }
 }
-
-// pass B: sigma partials, then (last CTA) umeyama + accumulate + convergence
-__global__ void __launch_bounds__(256)
-lg_passB_kernel(const float4* __restrict__ rec, int n, int nchunks, float* __restrict__ partB /* [nchunks][9] */,
-                LgState* __restrict__ st, int max_iter, double rot_thr, double trans_thr, double mse_rel, double mse_abs) {
-    if (st->done) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * 8 + warp;
-    const bool enough = st->kept >= 3;
-    if (c < nchunks && enough) {
-        const float sm0 = st->smean[0], sm1 = st->smean[1], sm2 = st->smean[2];
-        const float dm0 = st->dmean[0], dm1 = st->dmean[1], dm2 = st->dmean[2];
-        float a[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        const int i0 = (c << 8) + lane;
-        float4 sv[8], tv[8];
+// pass B of one chunk: sigma(a, b) partials = sum (d_a - dmean_a) * (s_b - smean_b)
+__device__ __forceinline__ void lg_chunk_B(const float4 (&sv)[8], const float4 (&tv)[8], int c, float sm0, float sm1, float sm2,
+                                           float dm0, float dm1, float dm2, float* __restrict__ partB) {
+    float a[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + 32 * u;
-            tv[u].w = __int_as_float(-1);
-            if (i < n) { sv[u] = rec[2 * (size_t)i]; tv[u] = rec[2 * (size_t)i + 1]; }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (__float_as_int(tv[u].w) < 0) continue;
-            const float4 s = sv[u], t = tv[u];
-            const float sx = sub_(s.x, sm0), sy = sub_(s.y, sm1), sz = sub_(s.z, sm2);
-            const float dx = sub_(t.x, dm0), dy = sub_(t.y, dm1), dz = sub_(t.z, dm2);
-            a[0] = add_(a[0], mul_(dx, sx)); a[1] = add_(a[1], mul_(dx, sy)); a[2] = add_(a[2], mul_(dx, sz));
-            a[3] = add_(a[3], mul_(dy, sx)); a[4] = add_(a[4], mul_(dy, sy)); a[5] = add_(a[5], mul_(dy, sz));
-            a[6] = add_(a[6], mul_(dz, sx)); a[7] = add_(a[7], mul_(dz, sy)); a[8] = add_(a[8], mul_(dz, sz));
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1)
-#pragma unroll
-            for (int q = 0; q < 9; ++q) a[q] = __fadd_rn(a[q], __shfl_xor_sync(KSS_FULL, a[q], off));
-        if (lane == 0)
-#pragma unroll
-            for (int q = 0; q < 9; ++q) partB[(size_t)c * 9 + q] = a[q];
+    for (int u = 0; u < 8; ++u) {
+        if (__float_as_int(tv[u].w) < 0) continue;
+        const float4 s = sv[u], t = tv[u];
+        const float sx = sub_(s.x, sm0), sy = sub_(s.y, sm1), sz = sub_(s.z, sm2);
+        const float dx = sub_(t.x, dm0), dy = sub_(t.y, dm1), dz = sub_(t.z, dm2);
+        a[0] = add_(a[0], mul_(dx, sx)); a[1] = add_(a[1], mul_(dx, sy)); a[2] = add_(a[2], mul_(dx, sz));
+        a[3] = add_(a[3], mul_(dy, sx)); a[4] = add_(a[4], mul_(dy, sy)); a[5] = add_(a[5], mul_(dy, sz));
+        a[6] = add_(a[6], mul_(dz, sx)); a[7] = add_(a[7], mul_(dz, sy)); a[8] = add_(a[8], mul_(dz, sz));
     }
-    if (!lg_last_block(&st->ticketB)) return;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+        for (int q = 0; q < 9; ++q) a[q] = __fadd_rn(a[q], __shfl_xor_sync(KSS_FULL, a[q], off));
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int q = 0; q < 9; ++q) partB[(size_t)c * 9 + q] = a[q];
+}
+// one whole CTA: upper levels of pass B, then umeyama + accumulate + convergence on one thread
+__device__ __forceinline__ void lg_finish_B(int nchunks, const float* __restrict__ partB, LgState* __restrict__ st, bool enough,
+                                            int max_iter, double rot_thr, double trans_thr, double mse_rel, double mse_abs) {
     __shared__ float tot[16];
     if (enough) {
-        if (nchunks == 1) { if (threadIdx.x < 9) tot[threadIdx.x] = partB[threadIdx.x]; __syncthreads(); }
+        if (nchunks == 1) { if (threadIdx.x < 9) tot[threadIdx.x] = __ldcg(partB + threadIdx.x); __syncthreads(); }
         else lg_finish_f32<9>(partB, nchunks, tot);
     }
     if (threadIdx.x == 0) {
@@ -1378,6 +1360,36 @@ lg_passB_kernel(const float4* __restrict__ rec, int n, int nchunks, float* __res
         }
         if (dn) { st->done = 1; st->converged = 1; }
     }
+}
+
+// two launches, one warp per chunk, the last CTA to finish does the upper levels
+__global__ void __launch_bounds__(256)
+lg_passA_kernel(const float4* __restrict__ rec, int n, int nchunks, float* __restrict__ partA /* [nchunks][6] */,
+                double* __restrict__ partD, int* __restrict__ partK, LgState* __restrict__ st,
+                volatile int* __restrict__ h_unres /* pinned host word: how many queries the refine kernel left over */) {
+    if (st->done) return;
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c < nchunks) {
+        float4 sv[8], tv[8];
+        lg_load_chunk(rec, n, c, sv, tv);
+        lg_chunk_A(sv, tv, c, partA, partD, partK);
+    }
+    if (!lg_last_block(&st->ticketA)) return;
+    lg_finish_A(nchunks, partA, partD, partK, st, h_unres);
+}
+__global__ void __launch_bounds__(256)
+lg_passB_kernel(const float4* __restrict__ rec, int n, int nchunks, float* __restrict__ partB /* [nchunks][9] */,
+                LgState* __restrict__ st, int max_iter, double rot_thr, double trans_thr, double mse_rel, double mse_abs) {
+    if (st->done) return;
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const bool enough = st->kept >= 3;
+    if (c < nchunks && enough) {
+        float4 sv[8], tv[8];
+        lg_load_chunk(rec, n, c, sv, tv);
+        lg_chunk_B(sv, tv, c, st->smean[0], st->smean[1], st->smean[2], st->dmean[0], st->dmean[1], st->dmean[2], partB);
+    }
+    if (!lg_last_block(&st->ticketB)) return;
+    lg_finish_B(nchunks, partB, st, enough, max_iter, rot_thr, trans_thr, mse_rel, mse_abs);
 }
 
 // double sums of d2 (and sqrt d2) by original index: fitness (A.7) / PCR_QM (large clouds)
