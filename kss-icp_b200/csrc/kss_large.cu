@@ -63,6 +63,7 @@ struct LgGridView {
     const float4* tp;                // sorted targets
     const float4* t_orig;            // targets by original index
     const unsigned* lut;             // [3][1024] per-axis bit spreads of the Morton-compact block code: code = x | y | z
+    const float4* knn;               // neighbour lists by ORIGINAL target index (ICP runs only), see lg_knn_kernel
     int n_t;
 };
 constexpr int LG_LUT = 1024;         // blocks per axis are at most ~1001 (lg_geom_kernel)
@@ -434,10 +435,15 @@ struct LgState {
     double prev_mse, mse, fitness;
     int iters, done, converged, kept, apply_T;
     unsigned ticketA, ticketB, ticketF;
-    unsigned miss[5];            // diagnostics: [1] second-stage searches, [2] pyramid fallbacks, [3] passes on global tables, [4] CTAs split in two passes
+    unsigned miss[5];            // diagnostics: [0] certificates re-established from the neighbour lists, [1] queries sent to the search kernels, [2] pyramid fallbacks, [3] passes on global tables, [4] CTAs split in two passes
     unsigned n_unres;            // queries of this iteration the refine kernel left to the general kernels
-    unsigned pad_;
+    unsigned n_fail;             // queries of this iteration whose certificate did not hold (lg_track_kernel)
 };
+
+// Programmatic dependent launch: the kernels of an iteration are launched so that one may be scheduled while its
+// predecessor drains (launch latency and independent loads overlap the predecessor's serial tail); nothing the
+// predecessor writes may be read, and nothing written, before this returns.  A no-op in an ordinary launch.
+__device__ __forceinline__ void lg_wait_prior() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ------------------------------------------------------------------ staged grid search
 constexpr int NN_THREADS = 256;
@@ -576,8 +582,8 @@ __device__ __forceinline__ bool lg_proven(const LgGeom& g, const QCell& q, int r
 }
 
 // NN kernel.  MODE 0: plain queries (sorted, w = original index) -> idx/d2 by original index
-//             MODE 1: ICP iteration: apply st->Tk to the sorted source in place, correspondences with rejection,
-//                     one 32-byte record {source xyz, d2 | target xyz, index or -1} per point by ORIGINAL index
+//             MODE 1: ICP iteration: the queries lg_track_kernel / lg_refine_kernel left flagged (flagS, by sorted
+//                     position; state by ORIGINAL index through perm): match -> tg[i], no certificate (cur[i].w = 0)
 //             MODE 2: fitness pass: query = st->fin * input, d2 by original index
 // One CTA = NN_QPC consecutive queries.  A pass = region of blocks around the pass's queries -> TMA bulk copies of the
 // blocks' points and offset tables into shared memory -> 2x2x2 search per thread -> warp-cooperative 4x4x4 search of the
@@ -585,10 +591,10 @@ __device__ __forceinline__ bool lg_proven(const LgGeom& g, const QCell& q, int r
 // that still does not fit reads the grid from global memory.  What neither stage proves goes to the box pyramid.
 template <int MODE>
 __global__ void __launch_bounds__(NN_THREADS, KSS_NN_CTAS)
-lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s, const float4* __restrict__ inp_s,
-             int* __restrict__ idx_out, float* __restrict__ d2out, float4* __restrict__ rec, int* __restrict__ prev_s,
-             const unsigned char* __restrict__ flag /* MODE 1 after lg_refine_kernel: 1 = still to do (already transformed) */,
-             LgState* __restrict__ st, double max_dist_sqr) {
+lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s /* MODE 1: by original index */,
+             const float4* __restrict__ inp_s, int* __restrict__ idx_out, float* __restrict__ d2out,
+             float4* __restrict__ tg /* MODE 1: matches by original index */, const int* __restrict__ perm,
+             unsigned char* __restrict__ flagS /* MODE 1: 1 = still to do */, LgState* __restrict__ st) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     float4* s_pts = reinterpret_cast<float4*>(dyn_smem);
     unsigned* s_tab = reinterpret_cast<unsigned*>(s_pts + NN_PTS_CAP);
@@ -608,8 +614,9 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s, con
     __shared__ unsigned s_p0[NN_MAXREG], s_cnt[NN_MAXREG], s_rank[NN_MAXREG];
     __shared__ int s_nleft, s_npyr, s_n2, s_nglob, s_nreg;
 
+    if (MODE == 1) lg_wait_prior();
     if (MODE == 1 && st->done) return;
-    if (MODE == 1 && flag && st->n_unres <= (unsigned)n_q / 8u) return;       // few left: lg_left_kernel takes them one warp each
+    if (MODE == 1 && st->n_unres <= (unsigned)n_q / 8u) return;       // few left: lg_left_kernel takes them one warp each
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < (int)(sizeof(LgGeom) / 4)) reinterpret_cast<int*>(&g)[tid] = reinterpret_cast<const int*>(gv.geom)[tid];
     if (MODE != 0 && tid < 16) T[tid] = MODE == 1 ? st->Tk[tid] : st->fin[tid];
@@ -624,25 +631,22 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s, con
                                                  // its distance bounds the search before a single cell is read
     unsigned long long key[NN_QPT];
     int left_at[NN_QPT];
-    const bool applyT = MODE == 1 && st->apply_T && !flag;
 #pragma unroll
     for (int k = 0; k < NN_QPT; ++k) {
         const int pos = base + k * NN_THREADS + tid;
-        valid[k] = pos < n_q && (!(MODE == 1 && flag) || flag[pos]);
+        valid[k] = pos < n_q && (MODE != 1 || flagS[pos]);
         qx[k] = qy[k] = qz[k] = 0.0f; qo[k] = 0u;
         qc[k].inside = false; qc[k].cx = qc[k].cy = qc[k].cz = 0; qc[k].m = 1.0f;
         key[k] = 0xffffffffffffffffull; left_at[k] = -1;
         ub[k].d = __int_as_float(0x7f800000); ub[k].idx = 0xffffffffu; box[k] = 0;
         if (valid[k]) {
-            const int pv = (MODE == 1 && prev_s) ? prev_s[pos] : -1;
-            float4 tprev = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pv >= 0) tprev = __ldg(gv.t_orig + pv);
-            const float4 p = MODE == 2 ? inp_s[pos] : cur_s[pos];
-            qo[k] = __float_as_uint(p.w);
-            if (MODE == 2 || applyT) {
-                xform_point(T, p.x, p.y, p.z, qx[k], qy[k], qz[k]);      // transformCloud of the previous iteration (A.5) / final * input (A.7)
-                if (MODE == 1) cur_s[pos] = make_float4(qx[k], qy[k], qz[k], p.w);
-            } else { qx[k] = p.x; qy[k] = p.y; qz[k] = p.z; }
+            const int oi = MODE == 1 ? perm[pos] : 0;
+            const float4 tprev = MODE == 1 ? tg[oi] : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+            const int pv = __float_as_int(tprev.w);                          // last iteration's match (-1: none yet)
+            const float4 p = MODE == 2 ? inp_s[pos] : MODE == 1 ? cur_s[oi] : cur_s[pos];
+            qo[k] = MODE == 1 ? (unsigned)oi : __float_as_uint(p.w);
+            if (MODE == 2) xform_point(T, p.x, p.y, p.z, qx[k], qy[k], qz[k]);      // final * input (A.7)
+            else { qx[k] = p.x; qy[k] = p.y; qz[k] = p.z; }                   // (MODE 1: lg_track_kernel applied T_k already)
             qc[k] = lg_qcell(g, qx[k], qy[k], qz[k]);
             if (pv >= 0) { ub[k].d = d2_rn(qx[k], qy[k], qz[k], tprev.x, tprev.y, tprev.z); ub[k].idx = (unsigned)pv; }
             // the cells a search has to read.  With a bound: the cells meeting the cube q +- sqrt(bound) -- every target that
@@ -964,7 +968,6 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s, con
     }
     __syncthreads();
     if (MODE == 1 && tid == 0) {
-        if (s_nleft) atomicAdd(&st->miss[1], (unsigned)s_nleft);
         if (npyr) atomicAdd(&st->miss[2], (unsigned)npyr);
         if (s_nglob) atomicAdd(&st->miss[3], (unsigned)s_nglob);
         if (npass > 1) atomicAdd(&st->miss[4], 1u);
@@ -981,11 +984,10 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s, con
         const float d2 = __uint_as_float((unsigned)(key[k] >> 32));
         const unsigned ti = (unsigned)(key[k] & 0xffffffffu);
         if (MODE == 1) {
-            if (prev_s) prev_s[base + k * NN_THREADS + tid] = (int)ti;
             const float4 t = __ldg(gv.t_orig + ti);
-            const int m = ((double)d2 > max_dist_sqr) ? -1 : (int)ti;                       // A.3
-            rec[2 * (size_t)qo[k]] = make_float4(qx[k], qy[k], qz[k], d2);
-            rec[2 * (size_t)qo[k] + 1] = make_float4(t.x, t.y, t.z, __int_as_float(m));
+            tg[qo[k]] = make_float4(t.x, t.y, t.z, __int_as_float((int)ti));
+            cur_s[qo[k]] = make_float4(qx[k], qy[k], qz[k], 0.0f);                          // no certificate from this kernel
+            flagS[base + k * NN_THREADS + tid] = 0;
         } else {
             d2out[qo[k]] = d2;
             if (MODE == 0) idx_out[qo[k]] = (int)ti;
@@ -993,91 +995,286 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s, con
     }
 }
 
-// Steady-state fast path of the ICP iteration: nothing is staged.  A query that carries last iteration's match holds a
-// bound before a single cell is read; when the cube q +- sqrt(bound) meets at most 3 x 3 rows of cells, the thread reads
-// exactly those cells from the grid in global memory (the working set is L2-resident: points 16 B, tables, ranks) and is
-// done -- exact without proof (every target that can beat or tie the bound lies in the cube).  Everything else is
-// flagged, counted and queued for the general kernels (lg_nn_kernel<1> when many, lg_left_kernel when few).
+// ---- certificates.  Per source point (by ORIGINAL index) the run keeps cur[i] = {current position, lb} and
+// tg[i] = {matched target, its index}: lb is a strict lower bound of the distance from the current position to every
+// target OTHER than the match.  lg_track_kernel moves the point by T_k, lowers lb by the length of the move and keeps the
+// match whenever its distance is still below lb (then it is the unique nearest neighbour: nothing to search, the pass
+// streams).  The search kernels below establish lb = min(distance to the second-nearest target scanned, distance to the
+// unscanned region).  Both bounds are kept 1e-5 (relative) apart from the values they are compared with, four orders of
+// magnitude above the fp32 rounding of d2_rn, so a kept match is also the search's answer bit for bit (no tie possible).
+constexpr float LG_CERT_UP = 1.00001f, LG_CERT_DOWN = 0.99999f;
+
+// best (d2 bits << 32 | original index) and the second-smallest d2 among the scanned targets
+struct Best2 { unsigned long long key; float second; };
+
+template <class Acc>
+__device__ __forceinline__ void lg_scan_cells2(const Acc& acc, int x0, int x1, int iy, int iz, float qx, float qy, float qz, Best2& b) {
+    const int f = ((iz & 3) << 4) | ((iy & 3) << 2);
+    for (int ix = x0; ix <= x1;) {
+        const int bx = ix >> 2;
+        const int xe = min(x1, (bx << 2) | 3);                        // cells of one block along x are contiguous
+        const unsigned* t; const float4* p;
+        if (acc.block(bx, iy >> 2, iz >> 2, t, p)) {
+            const unsigned s = t[f + (ix & 3)], e = t[f + (xe & 3) + 1];
+#pragma unroll SCAN_UNROLL
+            for (unsigned j = s; j < e; ++j) {
+                const float4 c = p[j];
+                const unsigned long long ck = ((unsigned long long)__float_as_uint(d2_rn(qx, qy, qz, c.x, c.y, c.z)) << 32) | __float_as_uint(c.w);
+                const unsigned long long hi = ck < b.key ? b.key : ck;          // the loser of (candidate, best) bounds the second
+                b.key = ck < b.key ? ck : b.key;
+                b.second = fminf(b.second, __uint_as_float((unsigned)(hi >> 32)));
+            }
+        }
+        ix = xe + 1;
+    }
+}
+
+// the cells meeting the cube q +- rho, rows and row ends farther than min(second so far, rho) skipped: exact best, and
+// every target that is not the best is at least min(sqrt(second), rho) away (gaps are 0.002 cells short, the cube 0.003
+// cells wide of the rounding of the binning).  rows_per_thread: lanes of a warp share one query when nl > 1.
+template <class Acc>
+__device__ __forceinline__ void lg_cube_search(const Acc& acc, const LgGeom& g, float x, float y, float z, float rho, int lane, int nl, Best2& b) {
+    const float rc = rho * g.inv_h * 1.00001f + 0.003f;
+    const float fx = (x - g.lo[0]) * g.inv_h, fy = (y - g.lo[1]) * g.inv_h, fz = (z - g.lo[2]) * g.inv_h;
+    const int xl = max((int)floorf(fx - rc), 0), xh = min((int)floorf(fx + rc), g.nf[0] - 1);
+    const int yl = max((int)floorf(fy - rc), 0), yh = min((int)floorf(fy + rc), g.nf[1] - 1);
+    const int zl = max((int)floorf(fz - rc), 0), zh = min((int)floorf(fz + rc), g.nf[2] - 1);
+    const int ny = yh - yl + 1, nrows = ny * (zh - zl + 1);
+    auto gap1 = [](float f, int i) { return fmaxf(fmaxf((float)i - f, f - (float)(i + 1)) - 0.002f, 0.0f); };
+    const float h2 = g.h * g.h, rho2 = rho * rho;
+    // the query's own row first: it usually holds the two nearest targets, whose distances then prune the other rows
+    const int r0 = (min(max((int)floorf(fz), zl), zh) - zl) * ny + (min(max((int)floorf(fy), yl), yh) - yl);
+    for (int k = lane; k < nrows; k += nl) {
+        const int rw = k == 0 ? r0 : (k <= r0 ? k - 1 : k);
+        const int iy = yl + rw % ny, iz = zl + rw / ny;
+        const float gy = gap1(fy, iy), gz = gap1(fz, iz);
+        const float lb = (gy * gy + gz * gz) * h2;
+        const float thr = fminf(b.second, rho2);
+        if (lb > thr) continue;                                      // everything in this row is strictly farther
+        int xa = xl, xb = xh;
+        while (xa < xb && lb + gap1(fx, xa) * gap1(fx, xa) * h2 > thr) ++xa;
+        while (xb > xa && lb + gap1(fx, xb) * gap1(fx, xb) * h2 > thr) --xb;
+        lg_scan_cells2(acc, xa, xb, iy, iz, x, y, z, b);
+    }
+}
+
+// ---- neighbour lists of the target (built once per pair): knn[p * LG_KSLOTS] = {R, count, -, -}, then LG_KNN targets
+// {x, y, z, bits(index)} (pads far away) such that EVERY target closer to p than R is listed.  A query q matched to p
+// then has every target within R - |q p| of itself in {p} + list(p): one 128-byte line replaces a walk over grid cells.
+#ifndef KSS_LG_KSLOTS
+#define KSS_LG_KSLOTS 8
+#endif
+constexpr int LG_KSLOTS = KSS_LG_KSLOTS;         // float4 slots per target (8 = one 128-byte line)
+constexpr int LG_KNN = LG_KSLOTS - 1;
+
+__global__ void __launch_bounds__(128)
+lg_knn_kernel(LgGridView gv, float4* __restrict__ knn) {
+    __shared__ LgGeom g;
+    if (threadIdx.x < (int)(sizeof(LgGeom) / 4)) reinterpret_cast<int*>(&g)[threadIdx.x] = reinterpret_cast<const int*>(gv.geom)[threadIdx.x];
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= gv.n_t) return;
+    const float4 p = gv.tp[j];                                    // sorted order: neighbouring threads share cells
+    const unsigned self = __float_as_uint(p.w);
+    const int cx = lg_fine(p.x, g.lo[0], g.inv_h, g.nf[0]), cy = lg_fine(p.y, g.lo[1], g.inv_h, g.nf[1]), cz = lg_fine(p.z, g.lo[2], g.inv_h, g.nf[2]);
+    const float fx = (p.x - g.lo[0]) * g.inv_h, fy = (p.y - g.lo[1]) * g.inv_h, fz = (p.z - g.lo[2]) * g.inv_h;
+    GlobAcc acc{gv.blk_rank, gv.fine_start, gv.tp, gv.lut};
+    float dd[LG_KNN]; float4 ee[LG_KNN];
+    int cnt = 0; float maxd = 0.0f; int maxj = 0; float cover = 0.0f;
+    for (int r = 1; r <= 2; ++r) {
+        cnt = 0; maxd = 0.0f; maxj = 0;
+#pragma unroll
+        for (int k = 0; k < LG_KNN; ++k) { dd[k] = __int_as_float(0x7f800000); ee[k] = make_float4(PAD_COORD, PAD_COORD, PAD_COORD, __int_as_float(0x7fffffff)); }
+        const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nf[0] - 1);
+        const int y0 = max(cy - r, 0), y1 = min(cy + r, g.nf[1] - 1);
+        const int z0 = max(cz - r, 0), z1 = min(cz + r, g.nf[2] - 1);
+        for (int iz = z0; iz <= z1; ++iz)
+            for (int iy = y0; iy <= y1; ++iy) {
+                const int f = ((iz & 3) << 4) | ((iy & 3) << 2);
+                for (int ix = x0; ix <= x1;) {
+                    const int bx = ix >> 2, xe = min(x1, (bx << 2) | 3);
+                    const unsigned* t; const float4* pts;
+                    if (acc.block(bx, iy >> 2, iz >> 2, t, pts)) {
+                        const unsigned s0 = t[f + (ix & 3)], e0 = t[f + (xe & 3) + 1];
+                        for (unsigned q = s0; q < e0; ++q) {
+                            const float4 c = pts[q];
+                            if (__float_as_uint(c.w) == self) continue;
+                            const float d = d2_rn(p.x, p.y, p.z, c.x, c.y, c.z);
+                            if (cnt < LG_KNN) {                      // fill
+#pragma unroll
+                                for (int k = 0; k < LG_KNN; ++k) if (k == cnt) { dd[k] = d; ee[k] = c; }
+                                ++cnt;
+                                if (cnt == LG_KNN) {
+                                    maxd = dd[0]; maxj = 0;
+#pragma unroll
+                                    for (int k = 1; k < LG_KNN; ++k) if (dd[k] > maxd) { maxd = dd[k]; maxj = k; }
+                                }
+                            } else if (d < maxd) {                   // replace the farthest
+#pragma unroll
+                                for (int k = 0; k < LG_KNN; ++k) if (k == maxj) { dd[k] = d; ee[k] = c; }
+                                maxd = dd[0]; maxj = 0;
+#pragma unroll
+                                for (int k = 1; k < LG_KNN; ++k) if (dd[k] > maxd) { maxd = dd[k]; maxj = k; }
+                            }
+                        }
+                    }
+                    ix = xe + 1;
+                }
+            }
+        // every target outside the scanned cells is at least `cover` away (no targets beyond the grid; the binning is
+        // exact to < 1e-4 cells, 0.002 allowed)
+        float cv = __int_as_float(0x7f800000);
+        if (cx - r > 0) cv = fminf(cv, fx - (float)(cx - r));
+        if (cx + r < g.nf[0] - 1) cv = fminf(cv, (float)(cx + r + 1) - fx);
+        if (cy - r > 0) cv = fminf(cv, fy - (float)(cy - r));
+        if (cy + r < g.nf[1] - 1) cv = fminf(cv, (float)(cy + r + 1) - fy);
+        if (cz - r > 0) cv = fminf(cv, fz - (float)(cz - r));
+        if (cz + r < g.nf[2] - 1) cv = fminf(cv, (float)(cz + r + 1) - fz);
+        cover = fmaxf(cv - 0.002f, 0.0f) * g.h;
+        if (cnt == LG_KNN) break;
+    }
+    // full list: everything closer than its farthest entry is listed (equal distances may be missing: strict bound)
+    float R = cover;
+    if (cnt == LG_KNN) R = fminf(R, sqrtf(maxd));
+    R = fminf(R, 1.0e30f) * LG_CERT_DOWN;
+    float4* out = knn + (size_t)self * LG_KSLOTS;
+    out[0] = make_float4(R, (float)cnt, 0.0f, 0.0f);
+#pragma unroll
+    for (int k = 0; k < LG_KNN; ++k) out[1 + k] = ee[k];
+}
+
+// The flagged queries (by sorted position, so that a warp's searches share cache lines), one thread each: a query that
+// carries a match holds a bound before a single cell is read.  It scans the cube q +- (bound + margin) from the grid in
+// global memory (L2-resident: points 16 B, tables, ranks) when that is at most 3 x 3 rows of cells -- exact without
+// proof, and the margin is what the certificate lives on.  The margin is dropped while T_k still moves the point
+// farther than a certificate could survive.  Everything else is counted and queued for the general kernels.
+constexpr int RF_SEG = 2048;                     // sorted positions per CTA of lg_refine_kernel
 __global__ void __launch_bounds__(256)
-lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur_s, float4* __restrict__ rec, int* __restrict__ prev_s,
-                 unsigned char* __restrict__ flag, int* __restrict__ worklist, LgState* __restrict__ st, double max_dist_sqr) {
+lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur, float4* __restrict__ tg, const int* __restrict__ perm,
+                 unsigned char* __restrict__ flagS, int* __restrict__ worklist, LgState* __restrict__ st, float margin_cells) {
     __shared__ LgGeom g;
     __shared__ float T[16];
-    if (st->done) return;
+    __shared__ int s_list[RF_SEG];               // flagged positions of the segment, compacted: every lane of a warp searches
+    __shared__ int s_n;
+    lg_wait_prior();
+    if (st->done || st->n_fail == 0u) return;
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid < (int)(sizeof(LgGeom) / 4)) reinterpret_cast<int*>(&g)[tid] = reinterpret_cast<const int*>(gv.geom)[tid];
     if (tid < 16) T[tid] = st->Tk[tid];
+    if (tid == 0) s_n = 0;
     __syncthreads();
-    const int pos = blockIdx.x * blockDim.x + tid;
-    const bool valid = pos < n_q;
-    bool unres = false;
-    if (valid) {
-        const int pv = prev_s[pos];
-        float4 tprev = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pv >= 0) tprev = __ldg(gv.t_orig + pv);
-        const float4 p = cur_s[pos];
-        float x = p.x, y = p.y, z = p.z;
-        if (st->apply_T) {
-            xform_point(T, p.x, p.y, p.z, x, y, z);                  // transformCloud of the previous iteration (A.5)
-            cur_s[pos] = make_float4(x, y, z, p.w);
-        }
-        unres = true;
-        if (pv >= 0) {
-            Best b; b.d = d2_rn(x, y, z, tprev.x, tprev.y, tprev.z); b.idx = (unsigned)pv;
-            const float ubd = b.d;
-            const float rc = sqrtf(ubd) * g.inv_h * 1.00001f + 0.003f;
-            if (rc <= 2.6f) {                                        // (false for NaN too)
-                const float fx = (x - g.lo[0]) * g.inv_h, fy = (y - g.lo[1]) * g.inv_h, fz = (z - g.lo[2]) * g.inv_h;
-                // the previous match is a target inside the grid and at most 2.6 cells away: no integer overflow
-                const int xl = max((int)floorf(fx - rc), 0), xh = min((int)floorf(fx + rc), g.nf[0] - 1);
-                const int yl = max((int)floorf(fy - rc), 0), yh = min((int)floorf(fy + rc), g.nf[1] - 1);
-                const int zl = max((int)floorf(fz - rc), 0), zh = min((int)floorf(fz + rc), g.nf[2] - 1);
-                auto gap1 = [](float f, int i) { return fmaxf(fmaxf((float)i - f, f - (float)(i + 1)) - 0.002f, 0.0f); };
-                const float h2 = g.h * g.h;
-                GlobAcc gacc{gv.blk_rank, gv.fine_start, gv.tp, gv.lut};
-                for (int iz = zl; iz <= zh; ++iz) {
-                    const float gz = gap1(fz, iz);
-                    for (int iy = yl; iy <= yh; ++iy) {
-                        const float gy = gap1(fy, iy);
-                        const float lb = (gy * gy + gz * gz) * h2;
-                        if (lb > ubd) continue;                              // everything in this row is strictly farther
-                        int xa = xl, xb = xh;
-                        while (xa < xb && lb + gap1(fx, xa) * gap1(fx, xa) * h2 > ubd) ++xa;
-                        while (xb > xa && lb + gap1(fx, xb) * gap1(fx, xb) * h2 > ubd) --xb;
-                        lg_scan_cells(gacc, xa, xb, iy, iy, iz, iz, x, y, z, b);
+    {   // 8 flags per thread (one 8-byte load), ballot-free compaction: order within the segment does not matter
+        const int p0 = blockIdx.x * RF_SEG + tid * 8;
+        unsigned long long f8 = 0ull;
+        if (p0 + 8 <= n_q) f8 = *reinterpret_cast<const unsigned long long*>(flagS + p0);
+        else for (int j = 0; j < 8; ++j) if (p0 + j < n_q && flagS[p0 + j]) f8 |= 1ull << (8 * j);
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cnt += (int)((f8 >> (8 * j)) & 1ull);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(KSS_FULL, incl, o); if (lane >= o) incl += y; }
+        int wbase = 0;
+        if (lane == 31 && incl) wbase = atomicAdd(&s_n, incl);
+        wbase = __shfl_sync(KSS_FULL, wbase, 31);
+        int at = wbase + incl - cnt;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if ((f8 >> (8 * j)) & 1ull) s_list[at++] = p0 + j;
+    }
+    __syncthreads();
+    const int nl = s_n;
+    const float m = margin_cells * g.h;
+    GlobAcc gacc{gv.blk_rank, gv.fine_start, gv.tp, gv.lut};
+    if (nl <= 8) {
+        // a handful (the steady state: points beyond the target's rim, whose second-nearest target is as far as the
+        // nearest, keep failing): one WARP per query, lane = row of cells, so that nobody waits for a long serial search
+        const int w = tid >> 5;
+        if (w >= nl) return;
+        const int pos = s_list[w];
+        const int i = perm[pos];
+        const float4 q = cur[i], t0 = tg[i];
+        bool unres = true;
+        if (__float_as_int(t0.w) >= 0) {
+            const float sd = sqrtf(d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z));
+            float nx, ny, nz;
+            xform_point(T, q.x, q.y, q.z, nx, ny, nz);
+            const float mv = sqrtf((nx - q.x) * (nx - q.x) + (ny - q.y) * (ny - q.y) + (nz - q.z) * (nz - q.z));
+            const float rho = fmaxf(sd * LG_CERT_UP + (2.0f * mv < m ? m : 0.0f), sd * 1.001f);
+            if (rho * g.inv_h * 1.00001f + 0.003f <= 8.0f) {
+                Best2 b; b.key = 0xffffffffffffffffull; b.second = __int_as_float(0x7f800000);
+                lg_cube_search(gacc, g, q.x, q.y, q.z, rho, lane, 32, b);
+                unsigned long long kk = b.key;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(KSS_FULL, kk, off); kk = o < kk ? o : kk; }
+                float s2 = b.key == kk ? b.second : __uint_as_float((unsigned)(b.key >> 32));
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) s2 = fminf(s2, __shfl_xor_sync(KSS_FULL, s2, off));
+                if (kk != 0xffffffffffffffffull) {
+                    unres = false;
+                    if (lane == 0) {
+                        const unsigned ti = (unsigned)kk;
+                        const float4 t = ti == (unsigned)__float_as_int(t0.w) ? t0 : __ldg(gv.t_orig + ti);
+                        tg[i] = make_float4(t.x, t.y, t.z, __int_as_float((int)ti));
+                        cur[i] = make_float4(q.x, q.y, q.z, sqrtf(fminf(s2, rho * rho)) * LG_CERT_DOWN);
+                        flagS[pos] = 0;
                     }
                 }
-                unres = false;
-                const float4 t = b.idx == (unsigned)pv ? tprev : __ldg(gv.t_orig + b.idx);
-                const unsigned orig = __float_as_uint(p.w);
-                const int m = ((double)b.d > max_dist_sqr) ? -1 : (int)b.idx;                // A.3
-                prev_s[pos] = (int)b.idx;
-                rec[2 * (size_t)orig] = make_float4(x, y, z, b.d);
-                rec[2 * (size_t)orig + 1] = make_float4(t.x, t.y, t.z, __int_as_float(m));
             }
         }
-        flag[pos] = unres ? 1 : 0;
+        if (unres && lane == 0) worklist[atomicAdd(&st->n_unres, 1u)] = pos;
+        return;
     }
-    const unsigned bal = __ballot_sync(KSS_FULL, valid && unres);
-    if (bal) {
-        unsigned at = 0u;
-        if (lane == 0) at = atomicAdd(&st->n_unres, (unsigned)__popc(bal));
-        at = __shfl_sync(KSS_FULL, at, 0);
-        if (valid && unres) worklist[at + __popc(bal & ((1u << lane) - 1u))] = pos;
+    for (int e0 = 0; e0 < nl; e0 += 256) {
+        const int e = e0 + tid;
+        const bool valid = e < nl;
+        bool unres = false;
+        int pos = 0;
+        if (valid) {
+            pos = s_list[e];
+            const int i = perm[pos];
+            const float4 q = cur[i], t0 = tg[i];
+            unres = true;
+            if (__float_as_int(t0.w) >= 0) {
+                const float sd = sqrtf(d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z));
+                float nx, ny, nz;
+                xform_point(T, q.x, q.y, q.z, nx, ny, nz);                // how far T_k would move the point once more
+                const float mv = sqrtf((nx - q.x) * (nx - q.x) + (ny - q.y) * (ny - q.y) + (nz - q.z) * (nz - q.z));
+                const float rho = sd * LG_CERT_UP + (2.0f * mv < m ? m : 0.0f);
+                if (rho * g.inv_h * 1.00001f + 0.003f <= 2.6f) {          // (false for NaN too)
+                    Best2 b; b.key = 0xffffffffffffffffull; b.second = __int_as_float(0x7f800000);
+                    lg_cube_search(gacc, g, q.x, q.y, q.z, rho, 0, 1, b);
+                    if (b.key != 0xffffffffffffffffull) {                 // (the match itself lies in the cube)
+                        unres = false;
+                        const unsigned ti = (unsigned)b.key;
+                        const float4 t = ti == (unsigned)__float_as_int(t0.w) ? t0 : __ldg(gv.t_orig + ti);
+                        tg[i] = make_float4(t.x, t.y, t.z, __int_as_float((int)ti));
+                        cur[i] = make_float4(q.x, q.y, q.z, sqrtf(fminf(b.second, rho * rho)) * LG_CERT_DOWN);
+                        flagS[pos] = 0;
+                    }
+                }
+            }
+        }
+        const unsigned bal = __ballot_sync(KSS_FULL, valid && unres);
+        if (bal) {
+            unsigned at = 0u;
+            if (lane == 0) at = atomicAdd(&st->n_unres, (unsigned)__popc(bal));
+            at = __shfl_sync(KSS_FULL, at, 0);
+            if (valid && unres) worklist[at + __popc(bal & ((1u << lane) - 1u))] = pos;
+        }
     }
 }
 
 // The few queries lg_refine_kernel could not finish, one WARP each (persistent grid over the work list): a query with a
-// bound reads the cells meeting the cube q +- sqrt(bound) (lane = row, up to 17 x 17 rows); the rest goes to the pyramid.
+// match reads the cells meeting the cube q +- bound (lane = row, up to 17 x 17 rows); the rest goes to the pyramid.
 __global__ void __launch_bounds__(256)
-lg_left_kernel(Pyramid py, LgGridView gv, int n_q, const float4* __restrict__ cur_s, float4* __restrict__ rec,
-               int* __restrict__ prev_s, const int* __restrict__ worklist, LgState* __restrict__ st, double max_dist_sqr,
-               int staged_launched) {
+lg_left_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur, float4* __restrict__ tg, const int* __restrict__ perm,
+               unsigned char* __restrict__ flagS, const int* __restrict__ worklist, LgState* __restrict__ st, int staged_launched) {
     __shared__ LgGeom g;
     __shared__ float4 slots[8][TILE];
+    lg_wait_prior();
     if (st->done) return;
     const unsigned nu = st->n_unres;
-    if (staged_launched && nu > (unsigned)n_q / 8u) return;          // many: lg_nn_kernel<1> staged them
+    if (nu == 0u || (staged_launched && nu > (unsigned)n_q / 8u)) return;          // many: lg_nn_kernel<1> staged them
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < (int)(sizeof(LgGeom) / 4)) reinterpret_cast<int*>(&g)[tid] = reinterpret_cast<const int*>(gv.geom)[tid];
     __syncthreads();
@@ -1086,49 +1283,34 @@ lg_left_kernel(Pyramid py, LgGridView gv, int n_q, const float4* __restrict__ cu
     unsigned n_pyr = 0u;
     for (unsigned e = blockIdx.x * (blockDim.x >> 5) + warp; e < nu; e += nw) {
         const int pos = worklist[e];
-        const float4 q = cur_s[pos];
-        const int pv = prev_s[pos];
+        const int i = perm[pos];
+        const float4 q = cur[i], t0 = tg[i];
         unsigned long long kk = 0xffffffffffffffffull;
-        bool done = false;
-        if (pv >= 0) {
-            const float4 tp0 = __ldg(gv.t_orig + pv);
-            const float ubd = d2_rn(q.x, q.y, q.z, tp0.x, tp0.y, tp0.z);
-            const float rc = sqrtf(ubd) * g.inv_h * 1.00001f + 0.003f;
-            if (rc <= 8.0f) {
-                const float fx = (q.x - g.lo[0]) * g.inv_h, fy = (q.y - g.lo[1]) * g.inv_h, fz = (q.z - g.lo[2]) * g.inv_h;
-                const int xl = max((int)floorf(fx - rc), 0), xh = min((int)floorf(fx + rc), g.nf[0] - 1);
-                const int yl = max((int)floorf(fy - rc), 0), yh = min((int)floorf(fy + rc), g.nf[1] - 1);
-                const int zl = max((int)floorf(fz - rc), 0), zh = min((int)floorf(fz + rc), g.nf[2] - 1);
-                const int ny = yh - yl + 1, nrows = ny * (zh - zl + 1);
-                auto gap1 = [](float f, int i) { return fmaxf(fmaxf((float)i - f, f - (float)(i + 1)) - 0.002f, 0.0f); };
-                const float h2 = g.h * g.h;
-                Best b; b.d = ubd; b.idx = (unsigned)pv;
-                for (int rw = lane; rw < nrows; rw += 32) {
-                    const int iy = yl + rw % ny, iz = zl + rw / ny;
-                    const float gy = gap1(fy, iy), gz = gap1(fz, iz);
-                    const float lb = (gy * gy + gz * gz) * h2;
-                    if (lb > ubd) continue;
-                    int xa = xl, xb = xh;
-                    while (xa < xb && lb + gap1(fx, xa) * gap1(fx, xa) * h2 > ubd) ++xa;
-                    while (xb > xa && lb + gap1(fx, xb) * gap1(fx, xb) * h2 > ubd) --xb;
-                    lg_scan_cells(gacc, xa, xb, iy, iy, iz, iz, q.x, q.y, q.z, b);
-                }
-                kk = ((unsigned long long)__float_as_uint(b.d) << 32) | b.idx;
+        float lbq = 0.0f;
+        if (__float_as_int(t0.w) >= 0) {
+            // (0.1 % beyond the match: far from the target the second-nearest is about as far as the nearest, and that is
+            // all the certificate can live on)
+            const float rho = sqrtf(d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z)) * 1.001f;
+            if (rho * g.inv_h * 1.00001f + 0.003f <= 8.0f) {
+                Best2 b; b.key = 0xffffffffffffffffull; b.second = __int_as_float(0x7f800000);
+                lg_cube_search(gacc, g, q.x, q.y, q.z, rho, lane, 32, b);
+                kk = b.key;
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(KSS_FULL, kk, off); kk = o < kk ? o : kk; }
-                done = true;
+                // second-nearest over the lanes: a lane's two nearest are (key, second)
+                float s2 = b.key == kk ? b.second : __uint_as_float((unsigned)(b.key >> 32));
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) s2 = fminf(s2, __shfl_xor_sync(KSS_FULL, s2, off));
+                lbq = sqrtf(fminf(s2, rho * rho)) * LG_CERT_DOWN;
             }
         }
-        if (!done) { kk = lg_warp_nn(py, q.x, q.y, q.z, slots[warp]); ++n_pyr; }       // every lane carries the same query
+        if (kk == 0xffffffffffffffffull) { kk = lg_warp_nn(py, q.x, q.y, q.z, slots[warp]); ++n_pyr; lbq = 0.0f; }       // every lane carries the same query
         if (lane == 0) {
-            const float d2 = __uint_as_float((unsigned)(kk >> 32));
             const unsigned ti = (unsigned)kk;
             const float4 t = __ldg(gv.t_orig + ti);
-            const unsigned orig = __float_as_uint(q.w);
-            const int m = ((double)d2 > max_dist_sqr) ? -1 : (int)ti;                       // A.3
-            prev_s[pos] = (int)ti;
-            rec[2 * (size_t)orig] = make_float4(q.x, q.y, q.z, d2);
-            rec[2 * (size_t)orig + 1] = make_float4(t.x, t.y, t.z, __int_as_float(m));
+            tg[i] = make_float4(t.x, t.y, t.z, __int_as_float((int)ti));
+            cur[i] = make_float4(q.x, q.y, q.z, lbq);
+            flagS[pos] = 0;
         }
     }
     if (lane == 0 && n_pyr) atomicAdd(&st->miss[2], n_pyr);
@@ -1221,6 +1403,15 @@ __device__ __forceinline__ double lg_finish_f64(const double* __restrict__ part,
     return res;
 }
 
+#ifdef KSS_LG_TIMELINE
+__device__ unsigned long long lg_tl[16];
+__device__ __forceinline__ unsigned long long lg_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define LG_TL_MIN(i) do { if (threadIdx.x == 0) atomicMin(&lg_tl[i], lg_now()); } while (0)
+#define LG_TL_SET(i) do { if (threadIdx.x == 0) lg_tl[i] = lg_now(); } while (0)
+#else
+#define LG_TL_MIN(i) do {} while (0)
+#define LG_TL_SET(i) do {} while (0)
+#endif
 __device__ __forceinline__ bool lg_last_block(unsigned* ticket) {
     __shared__ bool last;
     __threadfence();
@@ -1236,18 +1427,31 @@ __device__ __forceinline__ bool lg_last_block(unsigned* ticket) {
 }
 
 // ---- the two reduction passes of an iteration (pcl::umeyama demeans before it multiplies: the means first, then sigma)
-// rec[2i] = {source xyz, d2}, rec[2i+1] = {target xyz, bits(index or -1)}: a lane's 8 records are two coalesced streams
-__device__ __forceinline__ void lg_load_chunk(const float4* __restrict__ rec, int n, int c, float4 (&sv)[8], float4 (&tv)[8]) {
+// A lane's 8 points of a 256-chunk of ORIGINAL indices, as the reductions want them: sv = {source xyz, d2},
+// tv = {target xyz, bits(index, or -1 when rejected: d2 > max_dist^2, A.3)} -- two coalesced streams (cur, tg)
+__device__ __forceinline__ void lg_pair(const float4& c, const float4& t, double max2, float4& sv, float4& tv) {
+    const float d2 = d2_rn(c.x, c.y, c.z, t.x, t.y, t.z);
+    const int ti = __float_as_int(t.w);
+    sv = make_float4(c.x, c.y, c.z, d2);
+    tv = make_float4(t.x, t.y, t.z, __int_as_float((ti < 0 || (double)d2 > max2) ? -1 : ti));
+}
+__device__ __forceinline__ void lg_load_chunk(const float4* __restrict__ cur, const float4* __restrict__ tg, double max2, int n, int c,
+                                              float4 (&sv)[8], float4 (&tv)[8]) {
     const int i0 = (c << 8) + (threadIdx.x & 31);
+    float4 cv[8], gv[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
         const int i = i0 + 32 * u;
+        if (i < n) { cv[u] = cur[i]; gv[u] = tg[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
         tv[u].w = __int_as_float(-1);
-        if (i < n) { sv[u] = rec[2 * (size_t)i]; tv[u] = rec[2 * (size_t)i + 1]; }
+        if (i0 + 32 * u < n) lg_pair(cv[u], gv[u], max2, sv[u], tv[u]);
     }
 }
 // pass A of one 256-element chunk (one warp): sums of kept source xyz, matched target xyz (float), d2 (double), kept count
-__device__ __forceinline__ void lg_chunk_A(const float4 (&sv)[8], const float4 (&tv)[8], int c, float* __restrict__ partA,
+__device__ __forceinline__ void lg_chunk_A(const float4 (&sv)[8], const float4 (&tv)[8], int c, int S, float* __restrict__ partA,
                                            double* __restrict__ partD, int* __restrict__ partK) {
     float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     double dsum = 0.0;
@@ -1269,29 +1473,157 @@ __device__ __forceinline__ void lg_chunk_A(const float4 (&sv)[8], const float4 (
     k = __reduce_add_sync(KSS_FULL, k);
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int q = 0; q < 6; ++q) partA[(size_t)c * 6 + q] = a[q];
+        for (int q = 0; q < 6; ++q) partA[(size_t)q * S + c] = a[q];
         partD[c] = dsum; partK[c] = k;
     }
 }
-// one whole CTA: upper reduction levels of pass A, the means, the mse
-__device__ __forceinline__ void lg_finish_A(int nchunks, const float* __restrict__ partA, const double* __restrict__ partD,
-                                            const int* __restrict__ partK, LgState* __restrict__ st, volatile int* __restrict__ h_unres) {
-    __shared__ float tot[16];
-    __shared__ int kept_s;
-    if (nchunks == 1) { if (threadIdx.x < 6) tot[threadIdx.x] = __ldcg(partA + threadIdx.x); __syncthreads(); }
-    else lg_finish_f32<6>(partA, nchunks, tot);
-    const double dtot = nchunks == 1 ? __ldcg(partD) : lg_finish_f64(partD, nchunks);
-    if (threadIdx.x == 0) kept_s = 0;
-    __syncthreads();
-    int k = 0;
-    for (int i = threadIdx.x; i < nchunks; i += blockDim.x) k += __ldcg(partK + i);
-    k = __reduce_add_sync(KSS_FULL, k);
-    if ((threadIdx.x & 31) == 0 && k) atomicAdd(&kept_s, k);
+// ---- upper levels of the canonical sums, spread over the grid: partials are SoA [quantity][S] (S = padded chunk
+// count).  The CTA that completes a group of 256 chunks (per-group counters) reduces the group with ONE warp (level 2,
+// lane-strided + butterfly as everywhere); the warp that completes the last group does level 3 and the finish.  Nothing
+// waits: the serial tail of a pass is one group's level 2 + level 3 + the scalar finish.
+struct LgTree {
+    unsigned* grpcnt;                // [S2] chunks of each group that have arrived (reset by the last warp)
+    float* l2f;                      // [9][S2] level-2 results
+    double* l2d;                     // [S2]
+    int* l2k;                        // [S2]
+    int S, S2;                       // padded chunk / group counts
+};
+template <int NQ>
+__device__ __forceinline__ void lg_group_f32(const float* __restrict__ part, int S, int nchunks, int g, float* __restrict__ l2, int S2) {
+    const int lane = threadIdx.x & 31;
+    float v[NQ][8];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = (g << 8) + lane + 32 * u;
+            v[q][u] = i < nchunks ? __ldcg(part + (size_t)q * S + i) : 0.0f;          // (L2: written by other CTAs)
+        }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        float p = 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if ((g << 8) + lane + 32 * u < nchunks) p = __fadd_rn(p, v[q][u]);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) p = __fadd_rn(p, __shfl_xor_sync(KSS_FULL, p, off));
+        if (nchunks == 1) p = __shfl_sync(KSS_FULL, v[q][0], 0);                       // a single chunk is its own total
+        if (lane == 0) l2[(size_t)q * S2 + g] = p;
+    }
+}
+__device__ __forceinline__ void lg_group_f64(const double* __restrict__ part, int nchunks, int g, double* __restrict__ l2) {
+    const int lane = threadIdx.x & 31;
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = (g << 8) + lane + 32 * u; v[u] = i < nchunks ? __ldcg(part + i) : 0.0; }
+    double p = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) if ((g << 8) + lane + 32 * u < nchunks) p = __dadd_rn(p, v[u]);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) p = __dadd_rn(p, __shfl_xor_sync(KSS_FULL, p, off));
+    if (nchunks == 1) p = __shfl_sync(KSS_FULL, v[0], 0);
+    if (lane == 0) l2[g] = p;
+}
+// level 3 (one warp): every lane ends up with the totals.  All loads are issued before the first add (n2 <= 256: up to
+// 8 values per lane and quantity), the adds keep the canonical order (lane-strided, then the butterfly).
+template <int NQ>
+__device__ __forceinline__ void lg_top_f32(const float* __restrict__ l2, int S2, int n2, float (&tot)[NQ]) {
+    const int lane = threadIdx.x & 31;
+    if (n2 <= 32) {
+        float v[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) v[q] = lane < n2 ? __ldcg(l2 + (size_t)q * S2 + lane) : 0.0f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            if (n2 == 1) { tot[q] = __shfl_sync(KSS_FULL, v[q], 0); continue; }
+            float p = lane < n2 ? __fadd_rn(0.0f, v[q]) : 0.0f;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) p = __fadd_rn(p, __shfl_xor_sync(KSS_FULL, p, off));
+            tot[q] = p;
+        }
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = lane + 32 * u < n2 ? __ldcg(l2 + (size_t)q * S2 + lane + 32 * u) : 0.0f;
+        float p = 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (lane + 32 * u < n2) p = __fadd_rn(p, v[u]);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) p = __fadd_rn(p, __shfl_xor_sync(KSS_FULL, p, off));
+        tot[q] = p;
+    }
+}
+__device__ __forceinline__ double lg_top_f64(const double* __restrict__ l2, int n2) {
+    const int lane = threadIdx.x & 31;
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = lane + 32 * u < n2 ? __ldcg(l2 + lane + 32 * u) : 0.0;
+    if (n2 == 1) return __shfl_sync(KSS_FULL, v[0], 0);
+    double p = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) if (lane + 32 * u < n2) p = __dadd_rn(p, v[u]);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) p = __dadd_rn(p, __shfl_xor_sync(KSS_FULL, p, off));
+    return p;
+}
+// CTA b holds the chunks 8b .. 8b+7 (all of group b >> 5) and brings `mine` of them (thread 0's value counts; 0: no
+// arrival).  Returns the group to reduce in warp 0 of the CTA that completed it, -1 everywhere else.
+__device__ __forceinline__ int lg_group_arrive(unsigned* __restrict__ grpcnt, int nchunks, unsigned mine) {
+    __shared__ int s_g;
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (h_unres) *h_unres = (int)min(st->n_unres, 0x7fffffffu);  // the host reads it, stale, to decide which general kernel to enqueue
-        st->n_unres = 0u;                                            // (all search kernels of this iteration are done)
-        const int cnt = kept_s;
+        const int g = blockIdx.x >> 5;
+        const unsigned all = (unsigned)min(256, nchunks - (g << 8));
+        s_g = (mine && atomicAdd(&grpcnt[g], mine) + mine == all) ? g : -1;
+    }
+    __syncthreads();
+    const int g = s_g;
+    if (g < 0 || threadIdx.x >= 32) return -1;
+    __threadfence();
+    return g;
+}
+// after the group's level 2 is written: true in the warp that completed the last group (counters reset for the next pass)
+__device__ __forceinline__ bool lg_groups_done(unsigned* __restrict__ grpcnt, unsigned* __restrict__ ticket, int n2) {
+    const int lane = threadIdx.x & 31;
+    __threadfence();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = atomicAdd(ticket, 1u) == (unsigned)(n2 - 1);
+    last = __shfl_sync(KSS_FULL, last, 0);
+    if (!last) return false;
+    __threadfence();
+    for (int i = lane; i < n2; i += 32) grpcnt[i] = 0u;
+    if (lane == 0) *ticket = 0u;
+    return true;
+}
+
+__device__ __forceinline__ void lg_group_A(const float* __restrict__ partA, const double* __restrict__ partD, const int* __restrict__ partK,
+                                           const LgTree& tr, int nchunks, int g) {
+    lg_group_f32<6>(partA, tr.S, nchunks, g, tr.l2f, tr.S2);
+    lg_group_f64(partD, nchunks, g, tr.l2d);
+    int k = 0;                                   // kept counts: integer, any order
+    for (int i = (g << 8) + (threadIdx.x & 31); i < min(nchunks, (g + 1) << 8); i += 32) k += __ldcg(partK + i);
+    k = __reduce_add_sync(KSS_FULL, k);
+    if ((threadIdx.x & 31) == 0) tr.l2k[g] = k;
+}
+// one warp: level 3 of pass A, the means, the mse
+__device__ __forceinline__ void lg_finish_A(int nchunks, const LgTree& tr, LgState* __restrict__ st, volatile int* __restrict__ h_unres) {
+    const int n2 = (nchunks + 255) >> 8;
+    float tot[6];
+    int k = 0;
+    for (int i = threadIdx.x & 31; i < n2; i += 32) k += __ldcg(tr.l2k + i);
+    const unsigned nu = st->n_unres, nf = st->n_fail, m1 = st->miss[1];      // (loads before the first store to *st)
+    const double dtot = lg_top_f64(tr.l2d, n2);
+    lg_top_f32<6>(tr.l2f, tr.S2, n2, tot);
+    k = __reduce_add_sync(KSS_FULL, k);
+    if ((threadIdx.x & 31) == 0) {
+        if (h_unres) *h_unres = (int)min(nu, 0x7fffffffu);           // the host reads it, stale, to decide which general kernel to enqueue
+        st->miss[1] = m1 + nf;
+        st->n_unres = 0u; st->n_fail = 0u;                           // (all search kernels of this iteration are done)
+        const int cnt = k;
         st->kept = cnt;
         if (cnt >= 3) {
             const float oon = div_(1.0f, (float)cnt);
@@ -1302,7 +1634,7 @@ __device__ __forceinline__ void lg_finish_A(int nchunks, const float* __restrict
     }
 }
 // pass B of one chunk: sigma(a, b) partials = sum (d_a - dmean_a) * (s_b - smean_b)
-__device__ __forceinline__ void lg_chunk_B(const float4 (&sv)[8], const float4 (&tv)[8], int c, float sm0, float sm1, float sm2,
+__device__ __forceinline__ void lg_chunk_B(const float4 (&sv)[8], const float4 (&tv)[8], int c, int S, float sm0, float sm1, float sm2,
                                            float dm0, float dm1, float dm2, float* __restrict__ partB) {
     float a[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -1321,33 +1653,40 @@ __device__ __forceinline__ void lg_chunk_B(const float4 (&sv)[8], const float4 (
         for (int q = 0; q < 9; ++q) a[q] = __fadd_rn(a[q], __shfl_xor_sync(KSS_FULL, a[q], off));
     if ((threadIdx.x & 31) == 0)
 #pragma unroll
-        for (int q = 0; q < 9; ++q) partB[(size_t)c * 9 + q] = a[q];
+        for (int q = 0; q < 9; ++q) partB[(size_t)q * S + c] = a[q];
 }
-// one whole CTA: upper levels of pass B, then umeyama + accumulate + convergence on one thread
-__device__ __forceinline__ void lg_finish_B(int nchunks, const float* __restrict__ partB, LgState* __restrict__ st, bool enough,
+// one warp: level 3 of pass B, then umeyama + accumulate + convergence on one thread
+__device__ __forceinline__ void lg_finish_B(int nchunks, const LgTree& tr, LgState* __restrict__ st, bool enough,
                                             int max_iter, double rot_thr, double trans_thr, double mse_rel, double mse_abs) {
-    __shared__ float tot[16];
-    if (enough) {
-        if (nchunks == 1) { if (threadIdx.x < 9) tot[threadIdx.x] = __ldcg(partB + threadIdx.x); __syncthreads(); }
-        else lg_finish_f32<9>(partB, nchunks, tot);
-    }
+    const int n2 = (nchunks + 255) >> 8;
+    float tot[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) tot[q] = 0.0f;
+    // everything the scalar finish reads from *st, before anything is stored to it (one round trip to L2)
+    const int lane = threadIdx.x & 31;
+    const float stv = lane < 16 ? st->fin[lane] : lane < 19 ? st->smean[lane - 16] : lane < 22 ? st->dmean[lane - 19] : lane == 22 ? st->one_over_n : 0.0f;
+    const int it0 = st->iters;
+    const double mse = st->mse, prev = st->prev_mse;
+    if (enough) lg_top_f32<9>(tr.l2f, tr.S2, n2, tot);
+    float F[16], sm[3], dm[3];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) F[i] = __shfl_sync(KSS_FULL, stv, i);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { sm[i] = __shfl_sync(KSS_FULL, stv, 16 + i); dm[i] = __shfl_sync(KSS_FULL, stv, 19 + i); }
+    const float oon = __shfl_sync(KSS_FULL, stv, 22);
+    LG_TL_SET(2);
     if (threadIdx.x == 0) {
         if (!enough) { st->done = 1; st->converged = 0; return; }      // min_number_correspondences_
-        float sigma[9], T[16], F[16], sm[3], dm[3];
+        float sigma[9], T[16];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) sigma[i] = mul_(st->one_over_n, tot[i]);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { sm[i] = st->smean[i]; dm[i] = st->dmean[i]; }
+        for (int i = 0; i < 9; ++i) sigma[i] = mul_(oon, tot[i]);
         umeyama_finish(sigma, sm, dm, T);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) F[i] = st->fin[i];
         mat4_mul(T, F, F);
 #pragma unroll
         for (int i = 0; i < 16; ++i) { st->Tk[i] = T[i]; st->fin[i] = F[i]; }
         st->apply_T = 1;
-        const int it = st->iters + 1;
+        const int it = it0 + 1;
         st->iters = it;
-        const double mse = st->mse, prev = st->prev_mse;
         int dn = 0;
         if (it >= max_iter) dn = 1;
         else {
@@ -1362,34 +1701,236 @@ __device__ __forceinline__ void lg_finish_B(int nchunks, const float* __restrict
     }
 }
 
-// two launches, one warp per chunk, the last CTA to finish does the upper levels
-__global__ void __launch_bounds__(256)
-lg_passA_kernel(const float4* __restrict__ rec, int n, int nchunks, float* __restrict__ partA /* [nchunks][6] */,
-                double* __restrict__ partD, int* __restrict__ partK, LgState* __restrict__ st,
-                volatile int* __restrict__ h_unres /* pinned host word: how many queries the refine kernel left over */) {
-    if (st->done) return;
-    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (c < nchunks) {
-        float4 sv[8], tv[8];
-        lg_load_chunk(rec, n, c, sv, tv);
-        lg_chunk_A(sv, tv, c, partA, partD, partK);
+// The streaming pass of an iteration, by ORIGINAL index (one warp per 256-chunk, 8 points per lane -- the order of the
+// canonical sums): transformCloud of the previous iteration (A.5) and the certificate test.  Failed certificates are
+// queued per warp and re-established 32 at a time from the neighbour list of the match (every target within
+// R(p) - |q p| of q is in {p} + list(p): best and second-best are exact whenever the best is that close).  Chunks in
+// which every match was settled here get pass A right away.  Points that stay open are flagged at their SORTED
+// position for the search kernels; their chunks are marked dirty for lg_passA_kernel.
+constexpr int TK_QCAP = 64;                      // queue entries per warp (a round of 32 is processed whenever it holds >= 32)
+
+// one round: lane e < cnt takes queue entry e.  Returns 1 if the entry stays open.
+__device__ __forceinline__ unsigned lg_list_round(const float4* __restrict__ qa, const float4* __restrict__ qb, int cnt, int lane,
+                                                  const float4* __restrict__ knn, float4* __restrict__ cur, float4* __restrict__ tg,
+                                                  const int* __restrict__ inv, unsigned char* __restrict__ flagS, unsigned& nlist) {
+    if (lane >= cnt) return 0u;
+    const float4 q = qa[lane];                   // {x, y, z, bits(i)}
+    const float4 p = qb[lane];                   // the match {x, y, z, bits(index)}
+    const int i = __float_as_int(q.w);
+    const float4* L = knn + (size_t)__float_as_int(p.w) * LG_KSLOTS;
+    float4 e[LG_KSLOTS];
+#pragma unroll
+    for (int k = 0; k < LG_KSLOTS; ++k) e[k] = __ldg(L + k);
+    unsigned long long bk = ((unsigned long long)__float_as_uint(d2_rn(q.x, q.y, q.z, p.x, p.y, p.z)) << 32) | __float_as_uint(p.w);
+    const float rho = e[0].x - sqrtf(__uint_as_float((unsigned)(bk >> 32))) * LG_CERT_UP;      // everything within rho of q is in {p} + list(p)
+    float second = __int_as_float(0x7f800000);
+    int kb = 0;
+#pragma unroll
+    for (int k = 1; k < LG_KSLOTS; ++k) {
+        const unsigned long long ck = ((unsigned long long)__float_as_uint(d2_rn(q.x, q.y, q.z, e[k].x, e[k].y, e[k].z)) << 32) | __float_as_uint(e[k].w);
+        const bool better = ck < bk;
+        const unsigned long long hi = better ? bk : ck;
+        second = fminf(second, __uint_as_float((unsigned)(hi >> 32)));
+        bk = better ? ck : bk;
+        kb = better ? k : kb;
     }
-    if (!lg_last_block(&st->ticketA)) return;
-    lg_finish_A(nchunks, partA, partD, partK, st, h_unres);
+    const float db = sqrtf(__uint_as_float((unsigned)(bk >> 32)));
+    if (db * LG_CERT_UP < rho) {                 // (false for NaN and for rho <= 0)
+        cur[i] = make_float4(q.x, q.y, q.z, fminf(sqrtf(second), rho) * LG_CERT_DOWN);
+        if (kb) {
+            float4 t = e[1];
+#pragma unroll
+            for (int k = 2; k < LG_KSLOTS; ++k) if (k == kb) t = e[k];
+            tg[i] = t;
+        }
+        ++nlist;
+        return 0u;
+    }
+    cur[i] = make_float4(q.x, q.y, q.z, 0.0f);
+    flagS[inv[i]] = 1;
+    return 1u;
+}
+
+__device__ __forceinline__ float lg_sqrt_approx(float x) {      // relative error 2^-22, far inside the certificate margins
+    float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+__global__ void __launch_bounds__(256, 2)
+lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict__ tg, const int* __restrict__ inv,
+                const float4* __restrict__ knn, unsigned char* __restrict__ flagS, unsigned char* __restrict__ dirty,
+                float* __restrict__ partA, double* __restrict__ partD, int* __restrict__ partK, LgTree tr,
+                LgState* __restrict__ st, double max2, volatile int* __restrict__ h_unres) {
+    __shared__ float T[16];
+    __shared__ float4 s_qa[8][TK_QCAP], s_qb[8][TK_QCAP];
+    __shared__ unsigned s_clean;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 8 + warp;
+    const int i0 = (c << 8) + lane;
+    float4 sv[8], tv[8];                             // {position, d2}, {match, index}: what the sums need
+    if (c < nchunks) {                               // (pass B only reads them: before the wait)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + 32 * u;
+            if (i < n) { sv[u] = cur[i]; tv[u] = tg[i]; }
+        }
+    }
+    lg_wait_prior();
+    if (st->done) return;
+    if (threadIdx.x < 16) T[threadIdx.x] = st->Tk[threadIdx.x];
+    if (threadIdx.x == 0) s_clean = 0u;
+    __syncthreads();
+    const bool applyT = st->apply_T != 0;
+    if (c < nchunks) {
+        float4* qa = s_qa[warp]; float4* qb = s_qb[warp];
+        unsigned nfail = 0u, nlist = 0u, redo = 0u;  // redo: bit u = this lane's point u went through the queue
+        int qn = 0;                                  // queue fill (warp-uniform)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + 32 * u;
+            bool push = false, open = false;
+            if (i < n) {
+                const float4 cv = sv[u];
+                float x = cv.x, y = cv.y, z = cv.z, lb = cv.w;
+                if (applyT) {
+                    xform_point(T, cv.x, cv.y, cv.z, x, y, z);
+                    const float mx = x - cv.x, my = y - cv.y, mz = z - cv.z;
+                    lb = (lb - lg_sqrt_approx(mx * mx + my * my + mz * mz) * LG_CERT_UP) * LG_CERT_DOWN;
+                }
+                const float d2 = d2_rn(x, y, z, tv[u].x, tv[u].y, tv[u].z);
+                sv[u] = make_float4(x, y, z, d2);
+                const bool has = __float_as_int(tv[u].w) >= 0;
+                // sqrt(d2) * UP < lb, squared (lb > 0)
+                if (has && lb > 0.0f && d2 * (LG_CERT_UP * LG_CERT_UP) < lb * lb) cur[i] = make_float4(x, y, z, lb);
+                else if (has) push = true;
+                else { open = true; cur[i] = make_float4(x, y, z, 0.0f); flagS[inv[i]] = 1; }
+            }
+            if (open) ++nfail;
+            const unsigned pb = __ballot_sync(KSS_FULL, push);
+            if (pb) {                                                     // (warp-uniform)
+                if (push) {
+                    const int at = qn + __popc(pb & ((1u << lane) - 1u));
+                    qa[at] = make_float4(sv[u].x, sv[u].y, sv[u].z, __int_as_float(i));
+                    qb[at] = tv[u];
+                    redo |= 1u << u;
+                }
+                qn += __popc(pb);
+                __syncwarp();
+                if (qn >= 32) {
+                    nfail += lg_list_round(qa, qb, 32, lane, knn, cur, tg, inv, flagS, nlist);
+                    __syncwarp();
+                    if (lane + 32 < qn) { const float4 a = qa[lane + 32], b2 = qb[lane + 32]; __syncwarp(); qa[lane] = a; qb[lane] = b2; }
+                    else __syncwarp();
+                    qn -= 32;
+                    __syncwarp();
+                }
+            }
+        }
+        if (qn > 0) nfail += lg_list_round(qa, qb, qn, lane, knn, cur, tg, inv, flagS, nlist);
+        nfail = __reduce_add_sync(KSS_FULL, nfail);
+        nlist = __reduce_add_sync(KSS_FULL, nlist);
+        if (lane == 0) {
+            dirty[c] = nfail ? 1 : 0;
+            if (nfail) atomicAdd(&st->n_fail, nfail);
+            if (nlist) atomicAdd(&st->miss[0], nlist);
+            if (!nfail) atomicAdd(&s_clean, 1u);
+        }
+        if (!nfail) {
+            // pass A of the chunk: matches that went through the queue may have changed
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + 32 * u;
+                if (i >= n) { tv[u].w = __int_as_float(-1); continue; }
+                if ((redo >> u) & 1u) tv[u] = __ldcg(tg + i);
+                lg_pair(sv[u], tv[u], max2, sv[u], tv[u]);
+            }
+            lg_chunk_A(sv, tv, c, tr.S, partA, partD, partK);
+        }
+    }
+    // the clean chunks arrive at their group; a group (and, with nothing open anywhere, the whole of pass A) that
+    // completes here is reduced here
+    __syncthreads();
+    const int g = lg_group_arrive(tr.grpcnt, nchunks, s_clean);
+    if (g < 0) return;
+    lg_group_A(partA, partD, partK, tr, nchunks, g);
+    if (!lg_groups_done(tr.grpcnt, &st->ticketA, (nchunks + 255) >> 8)) return;
+    lg_finish_A(nchunks, tr, st, h_unres);
+}
+
+// pass A of the dirty chunks (their searches are done by now), then the upper levels and the means
+__global__ void __launch_bounds__(256)
+lg_passA_kernel(const float4* __restrict__ cur, const float4* __restrict__ tg, const unsigned char* __restrict__ dirty, double max2,
+                int n, int nchunks, float* __restrict__ partA /* [6][S] */, double* __restrict__ partD, int* __restrict__ partK,
+                LgTree tr, LgState* __restrict__ st,
+                volatile int* __restrict__ h_unres /* pinned host word: how many queries the refine kernel left over */) {
+    lg_wait_prior();
+    if (st->done) return;
+    __shared__ unsigned s_mine;
+    if (threadIdx.x == 0) s_mine = 0u;
+    __syncthreads();
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c < nchunks && dirty[c]) {               // (the clean chunks arrived in lg_track_kernel)
+        float4 sv[8], tv[8];
+        lg_load_chunk(cur, tg, max2, n, c, sv, tv);
+        lg_chunk_A(sv, tv, c, tr.S, partA, partD, partK);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_mine, 1u);
+    }
+    __syncthreads();
+    const int g = lg_group_arrive(tr.grpcnt, nchunks, s_mine);
+    if (g < 0) return;
+    lg_group_A(partA, partD, partK, tr, nchunks, g);
+    if (!lg_groups_done(tr.grpcnt, &st->ticketA, (nchunks + 255) >> 8)) return;
+    lg_finish_A(nchunks, tr, st, h_unres);
 }
 __global__ void __launch_bounds__(256)
-lg_passB_kernel(const float4* __restrict__ rec, int n, int nchunks, float* __restrict__ partB /* [nchunks][9] */,
+lg_passB_kernel(const float4* __restrict__ cur, const float4* __restrict__ tg, double max2, int n, int nchunks,
+                float* __restrict__ partB /* [9][S] */, LgTree tr,
                 LgState* __restrict__ st, int max_iter, double rot_thr, double trans_thr, double mse_rel, double mse_abs) {
-    if (st->done) return;
+    LG_TL_MIN(0);
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    float4 sv[8], tv[8];
+    if (c < nchunks) lg_load_chunk(cur, tg, max2, n, c, sv, tv);      // (pass A does not write them: before the wait)
+    lg_wait_prior();
+    if (st->done) return;
     const bool enough = st->kept >= 3;
+#ifdef KSS_LG_TIMELINE
+    const unsigned long long tl0 = lg_now();
+    unsigned long long tl1 = tl0, tl2 = tl0;
+#endif
     if (c < nchunks && enough) {
-        float4 sv[8], tv[8];
-        lg_load_chunk(rec, n, c, sv, tv);
-        lg_chunk_B(sv, tv, c, st->smean[0], st->smean[1], st->smean[2], st->dmean[0], st->dmean[1], st->dmean[2], partB);
+#ifdef KSS_LG_TIMELINE
+        if (__float_as_int(tv[0].w) != 0x12345678) tl1 = lg_now();
+#endif
+        lg_chunk_B(sv, tv, c, tr.S, st->smean[0], st->smean[1], st->smean[2], st->dmean[0], st->dmean[1], st->dmean[2], partB);
+#ifdef KSS_LG_TIMELINE
+        tl2 = lg_now();
+#endif
     }
-    if (!lg_last_block(&st->ticketB)) return;
-    lg_finish_B(nchunks, partB, st, enough, max_iter, rot_thr, trans_thr, mse_rel, mse_abs);
+    const int g = lg_group_arrive(tr.grpcnt, nchunks, (unsigned)min(8, nchunks - (int)blockIdx.x * 8));
+#ifdef KSS_LG_TIMELINE
+    if (threadIdx.x == 0) {
+        const unsigned long long tl3 = lg_now();
+        atomicAdd(&lg_tl[8], tl1 - tl0); atomicAdd(&lg_tl[9], tl2 - tl1); atomicAdd(&lg_tl[10], tl3 - tl2); atomicAdd(&lg_tl[11], 1ull);
+        atomicMax(&lg_tl[12], tl3); atomicMin(&lg_tl[13], tl0 + (blockIdx.x >= 296 ? 0ull : ~0ull >> 1));
+    }
+#endif
+    if (g < 0) return;
+    if (enough) lg_group_f32<9>(partB, tr.S, nchunks, g, tr.l2f, tr.S2);
+    if (!lg_groups_done(tr.grpcnt, &st->ticketB, (nchunks + 255) >> 8)) return;
+    LG_TL_SET(1);
+    lg_finish_B(nchunks, tr, st, enough, max_iter, rot_thr, trans_thr, mse_rel, mse_abs);
+    LG_TL_SET(3);
+}
+
+// state of a run from the sorted source: positions by original index without a certificate, no matches, the two maps
+__global__ void __launch_bounds__(256)
+lg_run_init_kernel(const float4* __restrict__ inp_s, int n, float4* __restrict__ cur, float4* __restrict__ tg,
+                   int* __restrict__ perm, int* __restrict__ inv, unsigned char* __restrict__ flagS) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n) return;
+    const float4 p = inp_s[pos];
+    const int i = __float_as_int(p.w);
+    perm[pos] = i; inv[i] = pos; flagS[pos] = 0;
+    cur[i] = make_float4(p.x, p.y, p.z, 0.0f);
+    tg[i] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
 }
 
 // double sums of d2 (and sqrt d2) by original index: fitness (A.7) / PCR_QM (large clouds)
@@ -1431,7 +1972,7 @@ __global__ void lg_state_init_kernel(LgState* st) {
         st->prev_mse = DBL_MAX; st->mse = 0; st->fitness = 0; st->iters = 0; st->done = 0; st->converged = 0;
         st->kept = 0; st->apply_T = 0; st->ticketA = st->ticketB = st->ticketF = 0u; st->one_over_n = 0.f;
         for (int i = 0; i < 5; ++i) st->miss[i] = 0u;
-        st->n_unres = 0u; st->pad_ = 0u;
+        st->n_unres = 0u; st->n_fail = 0u;
     }
 }
 
@@ -1552,7 +2093,7 @@ int build_target(Ctx& c, const double* d_t, int n_t, int n_q_max, Pyramid* py, L
     }
     py->nlev = lev;
     for (int l = lev; l < LG_MAX_LEVELS; ++l) { py->cnt[l] = 0; py->pad[l] = 0; py->box[l] = nullptr; }
-    gv->geom = geom; gv->blk_rank = blk_rank; gv->fine_start = fine_start; gv->tp = tp; gv->t_orig = t_orig; gv->lut = lut; gv->n_t = n_t;
+    gv->geom = geom; gv->blk_rank = blk_rank; gv->fine_start = fine_start; gv->tp = tp; gv->t_orig = t_orig; gv->lut = lut; gv->knn = nullptr; gv->n_t = n_t;
     if (getenv("KSS_LG_VERBOSE")) {
         LgGeom h; int no = 0;
         cudaMemcpyAsync(&h, geom, sizeof(h), cudaMemcpyDeviceToHost, c.st);
@@ -1566,11 +2107,23 @@ int build_target(Ctx& c, const double* d_t, int n_t, int n_q_max, Pyramid* py, L
 
 inline int nn_grid(int n_q) { return (n_q + NN_QPC - 1) / NN_QPC; }
 
+// launch with programmatic stream serialisation (see lg_wait_prior)
+template <class... KArgs, class... Args>
+void launch_pdl(bool pdl, void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int MODE>
 void launch_nn(cudaStream_t st, const Pyramid& py, const LgGridView& gv, int n_q, float4* cur_s, const float4* inp_s, int* idx,
-               float* d2, float4* rec, int* prev, const unsigned char* flag, LgState* state, double max2) {
+               float* d2, float4* tg, const int* perm, unsigned char* flagS, LgState* state) {
     cudaFuncSetAttribute(lg_nn_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM);
-    lg_nn_kernel<MODE><<<nn_grid(n_q), NN_THREADS, NN_SMEM, st>>>(py, gv, n_q, cur_s, inp_s, idx, d2, rec, prev, flag, state, max2);
+    lg_nn_kernel<MODE><<<nn_grid(n_q), NN_THREADS, NN_SMEM, st>>>(py, gv, n_q, cur_s, inp_s, idx, d2, tg, perm, flagS, state);
 }
 
 }  // namespace
@@ -1586,7 +2139,7 @@ int large_nn_device(cudaStream_t st, long long* launches, const double* d_q, int
     if (c.err) return c.err;
     r = order_queries(c, scr, gv, d_q, n_q, q4, qs);
     if (r) return r;
-    launch_nn<0>(st, py, gv, n_q, qs, nullptr, d_idx, d_d2, nullptr, nullptr, nullptr, nullptr, 0.0);
+    launch_nn<0>(st, py, gv, n_q, qs, nullptr, d_idx, d_d2, nullptr, nullptr, nullptr, nullptr);
     c.launched();
     return c.ok() ? KSS_OK : c.err;
 }
@@ -1638,25 +2191,41 @@ int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, i
     static_assert(sizeof(LgGridView) <= sizeof(run->grid), "LargeIcp::grid too small");
     memcpy(run->grid, &gv, sizeof(gv));
     float4* q4 = c.get<float4>("lg_q4", n_s);                 // by original index (scratch of the sort)
-    float4* inp = c.get<float4>("lg_inp", n_s);               // sorted input (fitness pass)
-    float4* cur = c.get<float4>("lg_cur", n_s);               // sorted, transformed in place every iteration
-    float4* rec = c.get<float4>("lg_rec", (size_t)n_s * 2);   // per-point records by original index
+    float4* inp = c.get<float4>("lg_inp", n_s);               // sorted input (fitness pass), w = original index
+    float4* cur = c.get<float4>("lg_cur", n_s);               // by original index: position (transformed in place every iteration), certificate
+    float4* tg = c.get<float4>("lg_tg", n_s);                 // by original index: matched target, its index (-1: none yet)
     float* d2 = c.get<float>("lg_d2", n_s);
-    int* prev = c.get<int>("lg_prev", n_s);                   // last iteration's match per sorted position (-1: none yet)
-    unsigned char* flag = c.get<unsigned char>("lg_flag", n_s);
+    int* perm = c.get<int>("lg_perm", n_s);                   // sorted position -> original index
+    int* inv = c.get<int>("lg_inv", n_s);                     // original index -> sorted position
+    unsigned char* flagS = c.get<unsigned char>("lg_flagS", n_s);     // by sorted position: to be searched
     int* worklist = c.get<int>("lg_worklist", n_s);
     const int nchunks = (n_s + 255) / 256;
-    float* pA = c.get<float>("lg_partA", (size_t)nchunks * 6);
-    float* pB = c.get<float>("lg_partB", (size_t)nchunks * 9);
-    double* pD = c.get<double>("lg_partD", nchunks);
-    int* pK = c.get<int>("lg_partK", nchunks);
+    unsigned char* dirty = c.get<unsigned char>("lg_dirty", nchunks);
+    float4* knn = c.get<float4>("lg_knn", (size_t)n_t * LG_KSLOTS);  // neighbour lists of the target, by original index
+    const int S = (nchunks + 31) / 32 * 32, n2 = (nchunks + 255) / 256, S2 = (n2 + 31) / 32 * 32;
+    float* pA = c.get<float>("lg_partA", (size_t)S * 6);
+    float* pB = c.get<float>("lg_partB", (size_t)S * 9);
+    double* pD = c.get<double>("lg_partD", S);
+    int* pK = c.get<int>("lg_partK", S);
+    float* l2f = c.get<float>("lg_l2f", (size_t)S2 * 9);
+    double* l2d = c.get<double>("lg_l2d", S2);
+    int* l2k = c.get<int>("lg_l2k", S2);
+    unsigned* grpcnt = c.get<unsigned>("lg_grpcnt", S2);
     LgState* state = c.get<LgState>("lg_state", 1);
     double* out3 = c.get<double>("lg_out3", 4);
     if (c.err) return c.err;
     r = order_queries(c, scr, gv, d_s, n_s, q4, inp);
     if (r) return r;
-    cudaMemcpyAsync(cur, inp, sizeof(float4) * (size_t)n_s, cudaMemcpyDeviceToDevice, st);
-    cudaMemsetAsync(prev, 0xff, sizeof(int) * (size_t)n_s, st);
+    if (n2 > 256) return KSS_ERR_UNSUPPORTED;                     // three reduction levels: n <= 16.7 M source points
+#ifdef KSS_LG_TIMELINE
+    { unsigned long long z[16]; for (int i = 0; i < 16; ++i) z[i] = (i >= 8 && i <= 12) ? 0ull : ~0ull; cudaMemcpyToSymbol(lg_tl, z, sizeof(z)); }
+#endif
+    cudaMemsetAsync(grpcnt, 0, sizeof(unsigned) * S2, st);
+    lg_run_init_kernel<<<(n_s + 255) / 256, 256, 0, st>>>(inp, n_s, cur, tg, perm, inv, flagS);
+    lg_knn_kernel<<<(n_t + 127) / 128, 128, 0, st>>>(gv, knn);
+    gv.knn = knn;
+    memcpy(run->grid, &gv, sizeof(gv));
+    c.launched(2);
     if (!run->h_unres && cudaHostAlloc((void**)&run->h_unres, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); run->h_unres = nullptr; }
     if (run->h_unres) *run->h_unres = 0x7fffffff;             // nothing known yet: the first iterations stage
     lg_state_init_kernel<<<1, 32, 0, st>>>(state);
@@ -1664,8 +2233,10 @@ int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, i
     static_assert(sizeof(Pyramid) <= sizeof(run->pyramid), "LargeIcp::pyramid too small");
     memcpy(run->pyramid, &py, sizeof(py));
     run->n_s = n_s; run->n_t = n_t; run->nchunks = nchunks;
-    run->inp = inp; run->cur = cur; run->rec = rec; run->d2 = d2; run->prev = prev; run->flag = flag; run->worklist = worklist;
+    run->inp = inp; run->cur = cur; run->tg = tg; run->d2 = d2; run->perm = perm; run->inv = inv; run->flagS = flagS;
+    run->dirty = dirty; run->worklist = worklist;
     run->partA = pA; run->partB = pB; run->partD = pD; run->partK = pK; run->state = state; run->out3 = out3;
+    run->l2f = l2f; run->l2d = l2d; run->l2k = l2k; run->grpcnt = grpcnt; run->S = S; run->S2 = S2;
     return c.ok() ? KSS_OK : c.err;
 }
 
@@ -1677,24 +2248,34 @@ int large_icp_iterations(cudaStream_t st, long long* launches, LargeIcp* run, co
     const double max2 = prm->max_corr_dist * prm->max_corr_dist;
     const int n = run->n_s, nch = run->nchunks;
     const double mse_abs = prm->fitness_eps < 0.0 ? -1.0 : 1e-12;   // fitness_eps < 0: never converge (steady-state timing)
+    static const float margin = [] { const char* e = getenv("KSS_LG_MARGIN"); return e ? (float)atof(e) : 0.5f; }();   // certificate margin, in cells
+    float4 *cur = (float4*)run->cur, *tg = (float4*)run->tg;
+    const LgTree tr{run->grpcnt, run->l2f, run->l2d, run->l2k, run->S, run->S2};
+    static const bool pdl = !getenv("KSS_LG_NO_PDL");
     for (int k = 0; k < count; ++k) {
         if (run->mark) run->mark(run->mark_user, KSS_STAGE_LARGE_NN, 1);
-        // correspondences: the refine kernel finishes every query whose last match bounds the search to a few cells;
-        // the general kernels take what it flags (staged CTAs when many, one warp per query when few)
-        // (the host knows the left-over count of an EARLIER iteration from a pinned word passA writes: it only decides
-        // whether the staged kernel is worth a launch; the one-warp-per-query kernel always runs and takes any count)
+        // correspondences: the streaming pass keeps every match whose certificate holds; the refine kernel searches the
+        // rest around their last match; the general kernels take what it leaves (staged CTAs when many, one warp per
+        // query when few).  (The host knows the left-over count of an EARLIER iteration from a pinned word passA writes:
+        // it only decides whether the staged kernel is worth a launch; the one-warp-per-query kernel takes any count.)
         const int known = run->h_unres ? *(volatile int*)run->h_unres : 0x7fffffff;
         const bool staged = known > n / 8;
-        lg_refine_kernel<<<(n + 255) / 256, 256, 0, st>>>(gv, n, (float4*)run->cur, (float4*)run->rec, run->prev, run->flag, run->worklist, state, max2);
-        if (staged) launch_nn<1>(st, py, gv, n, (float4*)run->cur, nullptr, nullptr, nullptr, (float4*)run->rec, run->prev, run->flag, state, max2);
-        lg_left_kernel<<<148, 256, 0, st>>>(py, gv, n, (const float4*)run->cur, (float4*)run->rec, run->prev, run->worklist, state, max2, staged ? 1 : 0);
+        launch_pdl(pdl, lg_track_kernel, (nch + 7) / 8, 256, 0, st, n, nch, cur, tg, run->inv, gv.knn, run->flagS, run->dirty, run->partA,
+                   run->partD, run->partK, tr, state, max2, (volatile int*)run->h_unres);
+        launch_pdl(pdl, lg_refine_kernel, (n + RF_SEG - 1) / RF_SEG, 256, 0, st, gv, n, cur, tg, run->perm, run->flagS, run->worklist, state, margin);
+        if (staged) {
+            cudaFuncSetAttribute(lg_nn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM);
+            launch_pdl(pdl, lg_nn_kernel<1>, nn_grid(n), NN_THREADS, NN_SMEM, st, py, gv, n, cur, (const float4*)nullptr, (int*)nullptr,
+                       (float*)nullptr, tg, run->perm, run->flagS, state);
+        }
+        launch_pdl(pdl, lg_left_kernel, 148 * 4, 256, 0, st, py, gv, n, cur, tg, run->perm, run->flagS, run->worklist, state, staged ? 1 : 0);
         if (run->mark) { run->mark(run->mark_user, KSS_STAGE_LARGE_NN, 0); run->mark(run->mark_user, KSS_STAGE_LARGE_REDUCE, 1); }
-        lg_passA_kernel<<<(nch + 7) / 8, 256, 0, st>>>((const float4*)run->rec, n, nch, run->partA, run->partD, run->partK, state, run->h_unres);
-        lg_passB_kernel<<<(nch + 7) / 8, 256, 0, st>>>((const float4*)run->rec, n, nch, run->partB, state, prm->max_iterations,
-                                                       1.0 - prm->transformation_eps, prm->transformation_eps,
-                                                       prm->fitness_eps, mse_abs);
+        launch_pdl(pdl, lg_passA_kernel, (nch + 7) / 8, 256, 0, st, (const float4*)cur, (const float4*)tg, run->dirty, max2, n, nch, run->partA,
+                   run->partD, run->partK, tr, state, (volatile int*)run->h_unres);
+        launch_pdl(pdl, lg_passB_kernel, (nch + 7) / 8, 256, 0, st, (const float4*)cur, (const float4*)tg, max2, n, nch, run->partB, tr, state,
+                   prm->max_iterations, 1.0 - prm->transformation_eps, prm->transformation_eps, prm->fitness_eps, mse_abs);
         if (run->mark) run->mark(run->mark_user, KSS_STAGE_LARGE_REDUCE, 0);
-        *launches += staged ? 5 : 4;
+        *launches += staged ? 6 : 5;
     }
     return cudaGetLastError() == cudaSuccess ? KSS_OK : KSS_ERR_CUDA;
 }
@@ -1714,7 +2295,7 @@ int large_icp_run(cudaStream_t st, long long* launches, LargeIcp* run, const kss
     // getFitnessScore: final * ORIGINAL input, NN, mean d2 in double (A.7)
     Pyramid py; memcpy(&py, run->pyramid, sizeof(py));
     LgGridView gv; memcpy(&gv, run->grid, sizeof(gv));
-    launch_nn<2>(st, py, gv, run->n_s, nullptr, (const float4*)run->inp, nullptr, run->d2, nullptr, nullptr, nullptr, state, 0.0);
+    launch_nn<2>(st, py, gv, run->n_s, nullptr, (const float4*)run->inp, nullptr, run->d2, nullptr, nullptr, nullptr, state);
     lg_passF_kernel<<<(run->nchunks + 7) / 8, 256, 0, st>>>(run->d2, run->n_s, run->nchunks, run->partD, nullptr,
                                                             &state->ticketF, run->out3);
     *launches += 2;
@@ -1734,6 +2315,14 @@ int large_icp_result(cudaStream_t st, LargeIcp* run, float T[16], double* fitnes
         fprintf(stderr, "[lg] unstaged half-passes by reason: box %u, touched blocks %u, points %u, occupied %u; sums: points %u occupied %u touched %u box %u\n",
                 d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
     }
+#ifdef KSS_LG_TIMELINE
+    { unsigned long long t[16]; cudaMemcpyFromSymbol(t, lg_tl, sizeof(t));
+      fprintf(stderr, "[lg] passB timeline (first CTA start of ANY launch is the min; use a 1-iteration run): first CTA -> last group %.2f us, level 3 %.2f us, SVD etc. %.2f us\n",
+              (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3);
+      fprintf(stderr, "[lg] passB per CTA (thread 0): load %.2f us, chunk %.2f us, arrive %.2f us (%llu CTAs); first start -> last arrive %.2f us; first start of a CTA >= 296: +%.2f us\n",
+              t[8] * 1e-3 / t[11], t[9] * 1e-3 / t[11], t[10] * 1e-3 / t[11], t[11], (t[12] - t[0]) * 1e-3, (t[13] - t[0]) * 1e-3);
+      unsigned long long z[16]; for (int i = 0; i < 16; ++i) z[i] = ~0ull; cudaMemcpyToSymbol(lg_tl, z, sizeof(z)); }
+#endif
 #ifdef KSS_LG_COUNT
     { unsigned long long c4[4]; cudaMemcpyFromSymbol(c4, lg_cnt, sizeof(c4));
       fprintf(stderr, "[lg] first stage: %.2f candidates per query, %.2f lane slots per query (over %llu query slots)\n", (double)c4[0] / c4[2], (double)c4[1] / c4[2], c4[2]); }

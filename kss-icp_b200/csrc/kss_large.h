@@ -23,14 +23,16 @@ int large_metrics_device(cudaStream_t st, long long* launches, const double* d_q
 // a prepared full-resolution ICP run (device buffers owned by the context's allocator)
 struct LargeIcp {
     alignas(8) unsigned char pyramid[160];
-    alignas(8) unsigned char grid[64];
+    alignas(8) unsigned char grid[72];
     int n_s = 0, n_t = 0, nchunks = 0;
-    void *inp = nullptr, *cur = nullptr, *rec = nullptr, *state = nullptr;
-    int *partK = nullptr, *prev = nullptr, *worklist = nullptr;
-    unsigned char* flag = nullptr;
+    void *inp = nullptr, *cur = nullptr, *tg = nullptr, *state = nullptr;   // inp: sorted input; cur / tg: by original index
+    int *partK = nullptr, *perm = nullptr, *inv = nullptr, *worklist = nullptr;
+    unsigned char *flagS = nullptr, *dirty = nullptr;
     int* h_unres = nullptr;             // pinned host word (mapped): left-over count of an earlier iteration
-    float *d2 = nullptr, *partA = nullptr, *partB = nullptr;
-    double *partD = nullptr, *out3 = nullptr;
+    float *d2 = nullptr, *partA = nullptr, *partB = nullptr, *l2f = nullptr;     // partials [quantity][S], level-2 results [9][S2]
+    double *partD = nullptr, *l2d = nullptr, *out3 = nullptr;
+    int* l2k = nullptr; unsigned* grpcnt = nullptr;
+    int S = 0, S2 = 0;                  // padded chunk / 256-chunk-group counts
     // optional stage marks (CUDA-event timing by the context): mark(user, KSS_STAGE_*, begin?1:0)
     void (*mark)(void* user, int stage, int begin) = nullptr;
     void* mark_user = nullptr;

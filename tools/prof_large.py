@@ -11,6 +11,6 @@ p = pkg.synth.scan_pair(0, N)
 ctx = pkg.Context(0)
 never = dict(max_iter=1 << 30, fit_eps=-1.0, trans_eps=-1.0)
 ctx.icp_large_begin(p["full_s"], p["full_t"])
-ctx.icp_large_iterate(36, **never)
+ctx.icp_large_iterate(int(sys.argv[2]) if len(sys.argv) > 2 else 36, **never)
 ctx.synchronize()
 print(ctx.icp_large_end(**never)["fitness"])
