@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-1m", action="store_true", help="skip the 1M-point ICP-iteration roofline leg")
     ap.add_argument("--points-1m", type=int, default=1000000)
+    ap.add_argument("--settle-1m", type=int, default=400, help="iterations past PCL's convergence before the steady-state iteration is timed")
     ap.add_argument("--only-1m", action="store_true", help="debug: run only the 1M-point leg")
     ap.add_argument("--config", default="all", choices=["all", "c3", "c1", "c2", "c4pipe", "c5"],
                     help="all: the headline batch (c3) plus one leg per other BASELINE.json configuration; cN: only that leg")

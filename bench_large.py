@@ -6,6 +6,13 @@ Algorithmic bytes: fp32 12 B/point, 4 B index, 4 B d2
   Sigma / MSE  : 12 N_s + 8 N_s + 12 N_s (gather)
   transform    : 12 N_s + 12 N_s
   iteration    : 76 N_s + 12 N_t  (= 88 MB at N_s = N_t = 1e6)
+
+What an iteration costs depends on how far T_k still moves the cloud (a match is kept without a search
+while its certificate holds), so three regimes are timed and all are reported:
+  steady state        : the fixed point the iteration settles into (SURVEY.md 8d: "time one steady-state iteration");
+                        `roofline` and the icp_iter_1m headline are this one, L2 flushed before every timed iteration
+  at PCL convergence  : the 100 iterations right after the one at which PCL's own criteria stop this pair
+  real run            : every iteration of the run to PCL's convergence (first iterations search from scratch)
 """
 import json
 import os
@@ -14,13 +21,30 @@ import numpy as np
 
 
 def _ncu_traffic():
-    """DRAM bytes per launch of the NN kernel from the committed ncu capture (profiles/), or None"""
+    """DRAM bytes per launch of the streaming kernel from the committed ncu capture (profiles/), or None"""
     p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic.json")
     try:
-        k = json.load(open(p))["lg_refine_kernel"]
+        k = json.load(open(p))["lg_track_kernel"]
         return float(k["dram_bytes_read"] + k["dram_bytes_write"])
     except Exception:
         return None
+
+
+def _timed_iterations(ctx, st, never, count, flush=None):
+    """CUDA-event time of `count` single iterations on the launching stream (ms each)"""
+    import torch
+    out = []
+    with torch.cuda.stream(st):
+        for _ in range(count):
+            if flush is not None:
+                flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            ctx.icp_large_iterate(1, **never)
+            e1.record(st)
+            e1.synchronize()
+            out.append(e0.elapsed_time(e1))
+    return out
 
 
 def icp_iteration_roofline(pkg, ctx, args, hbm_peak, which, stream=None):
@@ -30,77 +54,83 @@ def icp_iteration_roofline(pkg, ctx, args, hbm_peak, which, stream=None):
     dev = torch.cuda.current_device()
     st = torch.cuda.current_stream() if stream is None else stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % dev)     # > 126 MB L2
-    never = dict(max_iter=1 << 30, fit_eps=-1.0, trans_eps=-1.0)                  # steady state: no convergence exit
+    never = dict(max_iter=1 << 30, fit_eps=-1.0, trans_eps=-1.0)                  # no convergence exit
 
     ctx.icp_large_begin(p["full_s"], p["full_t"])          # first call also pays cudaMalloc of the work buffers
     ctx.synchronize()
     ctx.set_timing(True)
-    ctx.icp_large_begin(p["full_s"], p["full_t"])          # timed: H2D (pageable) + block grid of the target + box pyramid + query sort
+    ctx.icp_large_begin(p["full_s"], p["full_t"])          # timed: H2D (pageable) + block grid + box pyramid + neighbour lists + query sort
     ctx.synchronize()
     build_ms = ctx.stage_ms(7)[0]
+    ctx.set_timing(False)
     # a whole run as a user would make it (kss_icp semantics): build + iterations to PCL's convergence + fitness pass
     import time as _time
     ctx.icp(p["full_s"], p["full_t"])                      # untimed: the one-shot entry has its own buffers (cudaMalloc)
     t0 = _time.perf_counter()
     whole = ctx.icp(p["full_s"], p["full_t"])
     whole_ms = 1000.0 * (_time.perf_counter() - t0)
+    n_pcl = int(whole["iters"])
+
+    # (a) the real run, iteration by iteration (same trajectory: the convergence exit is only disabled)
     ctx.icp_large_begin(p["full_s"], p["full_t"])
     ctx.synchronize()
-    ctx.icp_large_iterate(30, **never)                                            # warm-up, reaches the fixed point
+    run_ms = _timed_iterations(ctx, st, never, n_pcl)
+    # (b) right after PCL's criteria would have stopped
+    after = _timed_iterations(ctx, st, never, 100)
+    # (c) steady state: the fixed point
+    ctx.icp_large_iterate(max(0, args.settle_1m - 100), **never)
     ctx.synchronize()
-    ctx.set_timing(True)                                                          # reset accumulators
-
-    # (a) cold: L2 flushed before every timed iteration
-    cold = []
-    with torch.cuda.stream(st):
-        for _ in range(40):
-            flush.zero_()
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(st)
-            ctx.icp_large_iterate(1, **never)
-            e1.record(st)
-            e1.synchronize()
-            cold.append(e0.elapsed_time(e1))
+    cold = _timed_iterations(ctx, st, never, 100, flush=flush)                    # L2 flushed before every iteration
+    K = 200
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    ctx.icp_large_iterate(K, **never)                                             # back to back (the pair lives in L2)
+    e1.record(st)
+    e1.synchronize()
+    warm_ms = e0.elapsed_time(e1) / K
+    # per-stage split of the cold iteration (the stage events sit between the kernels and cost a little overlap)
+    ctx.set_timing(True)
+    _timed_iterations(ctx, st, never, 40, flush=flush)
     nn_ms_cold, nn_calls = ctx.stage_ms(8)
     red_ms_cold, _ = ctx.stage_ms(9)
     nn_cold = nn_ms_cold / max(1, nn_calls)
     red_cold = red_ms_cold / max(1, nn_calls)
-    ctx.set_timing(True)
-
-    # (b) warm: back-to-back iterations (what a real ICP run sees: the pair lives in L2)
-    K = 200
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(st)
-    ctx.icp_large_iterate(K, **never)
-    e1.record(st)
-    e1.synchronize()
-    warm_ms = e0.elapsed_time(e1) / K
-    nn_ms_warm, c2 = ctx.stage_ms(8)
-    red_ms_warm, _ = ctx.stage_ms(9)
     ctx.set_timing(False)
     res = ctx.icp_large_end(**never)
 
     iter_bytes = 76.0 * N + 12.0 * N
     nn_bytes = 12.0 * N + 12.0 * N + 8.0 * N
     cold_ms = float(np.median(cold))
-    roofline = {"bound": "hbm", "kernel": "lg_refine_kernel (+ the general kernels for what it flags): 1M-point correspondence search + fused transform",
-                "achieved": nn_bytes / (nn_cold * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": nn_bytes / (nn_cold * 1e-3) / 1e9 / hbm_peak, "traffic": _ncu_traffic(),
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch of lg_refine_kernel, ncu capture summarised in profiles/r02_large_path_1m.md",
+    after_ms = float(np.median(after))
+    gbs = lambda b, ms: b / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm",
+                "kernel": "lg_track_kernel (+ lg_refine_kernel / lg_left_kernel for the points whose certificate failed): "
+                          "1M-point correspondences + fused transform + fused pass A, steady state",
+                "achieved": gbs(nn_bytes, nn_cold), "peak": hbm_peak, "unit": "GB/s",
+                "frac": gbs(nn_bytes, nn_cold) / hbm_peak, "traffic": _ncu_traffic(),
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch of lg_track_kernel, ncu capture summarised in profiles/r02_large_path_1m.md",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % which,
                 "algorithmic_bytes_per_launch": nn_bytes, "ms_per_launch": nn_cold,
-                "timing": "CUDA events on the launching stream around every launch, L2 flushed (256 MB write) before each iteration, 40 launches"}
-    extra = {"icp_iter_1m": {"points": N, "ms_cold_l2_flushed": cold_ms, "ms_warm_back_to_back": warm_ms,
+                "timing": "CUDA events on the launching stream around the correspondence kernels of every iteration, "
+                          "L2 flushed (256 MB write) before each iteration, 40 iterations at the fixed point"}
+    extra = {"icp_iter_1m": {"points": N,
+                             "regime": "steady state (fixed point after %d iterations)" % (n_pcl + args.settle_1m),
+                             "ms_cold_l2_flushed": cold_ms, "ms_warm_back_to_back": warm_ms,
                              "algorithmic_bytes": iter_bytes,
-                             "achieved_gbs_cold": iter_bytes / (cold_ms * 1e-3) / 1e9,
-                             "achieved_gbs_warm": iter_bytes / (warm_ms * 1e-3) / 1e9,
-                             "frac_of_hbm_cold": iter_bytes / (cold_ms * 1e-3) / 1e9 / hbm_peak,
-                             "frac_of_hbm_warm": iter_bytes / (warm_ms * 1e-3) / 1e9 / hbm_peak,
+                             "achieved_gbs_cold": gbs(iter_bytes, cold_ms), "achieved_gbs_warm": gbs(iter_bytes, warm_ms),
+                             "frac_of_hbm_cold": gbs(iter_bytes, cold_ms) / hbm_peak,
+                             "frac_of_hbm_warm": gbs(iter_bytes, warm_ms) / hbm_peak,
                              "nn_ms_cold": nn_cold, "reduce_svd_ms_cold": red_cold,
-                             "nn_ms_warm": nn_ms_warm / max(1, c2), "reduce_svd_ms_warm": red_ms_warm / max(1, c2),
                              "build_ms_once_per_pair": build_ms, "kernels_per_iteration": 5,
                              "final_fitness": res["fitness"],
-                             "whole_run": {"ms_host_clock": whole_ms, "iterations": int(whole["iters"]), "converged": int(whole["converged"]),
+                             "at_pcl_convergence": {"iterations": "%d..%d" % (n_pcl + 1, n_pcl + 100), "ms_median_warm": after_ms,
+                                                    "frac_of_hbm": gbs(iter_bytes, after_ms) / hbm_peak},
+                             "real_run": {"iterations_to_pcl_convergence": n_pcl,
+                                          "ms_per_iteration": [round(x, 4) for x in run_ms],
+                                          "ms_sum": float(np.sum(run_ms)), "ms_mean": float(np.mean(run_ms)),
+                                          "what": "every iteration of the run (CUDA events, back to back): the first ones "
+                                                  "search from scratch far from the target, later ones keep certified matches"},
+                             "whole_run": {"ms_host_clock": whole_ms, "iterations": n_pcl, "converged": int(whole["converged"]),
                                            "fitness": float(whole["fitness"]),
                                            "what": "kss_icp from host clouds: H2D + build + iterations to PCL's convergence + fitness pass + D2H"}}}
     return roofline, extra

@@ -33,6 +33,10 @@
 namespace kss {
 
 constexpr int SCAN_UNROLL = KSS_SCAN_UNROLL;
+#ifndef KSS_LG_CUBE3
+#define KSS_LG_CUBE3 3.0f
+#endif
+constexpr float cube3 = KSS_LG_CUBE3;  // a warp scans the cube q +- bound cell by cell up to this many cells of reach; beyond, the (seeded) box pyramid
 constexpr int LG_MAX_LEVELS = 4;     // 32^4 tiles * 32 points = 33.5 M points
 constexpr int LG_SAMPLES = 256;      // nearest-neighbour probe of the build
 
@@ -410,13 +414,17 @@ __device__ __forceinline__ void lg_descend(const Pyramid& py, int node, NNState&
 }
 
 // all 32 lanes carry a query (idle lanes repeat a neighbour's); returns (d2 bits << 32) | original index
-__device__ __forceinline__ unsigned long long lg_warp_nn(const Pyramid& py, float qx, float qy, float qz, float4* slot) {
+// seed_d2: an upper bound of the lane's answer (the distance to ANY target, e.g. last iteration's match; +inf: none).
+// Boxes and tiles are skipped only when strictly farther (with slack), so the seeding target itself is met again and
+// returned with its index if nothing beats it.
+__device__ __forceinline__ unsigned long long lg_warp_nn(const Pyramid& py, float qx, float qy, float qz, float4* slot,
+                                                         float seed_d2 = __builtin_inff()) {
     NNState s;
     s.qx = qx; s.qy = qy; s.qz = qz;
     s.lx = warp_min_f(qx); s.ly = warp_min_f(qy); s.lz = warp_min_f(qz);
     s.hx = warp_max_f(qx); s.hy = warp_max_f(qy); s.hz = warp_max_f(qz);
-    s.best = __int_as_float(0x7f800000);
-    s.bestkey = 0xffffffffffffffffull;
+    s.best = seed_d2;
+    s.bestkey = ((unsigned long long)__float_as_uint(seed_d2) << 32) | 0xffffffffull;
     s.slot = slot;
     switch (py.nlev) {      // virtual root above the top level
         case 1: lg_descend<1>(py, 0, s); break;
@@ -923,7 +931,7 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s /* M
             const float ubd = s_lub[li];
             const float rc = sqrtf(ubd) * g.inv_h * 1.00001f + 0.003f;
             bool done3 = false;
-            if (rc <= 8.0f) {
+            if (rc <= cube3) {
                 const float fx = (q.x - g.lo[0]) * g.inv_h, fy = (q.y - g.lo[1]) * g.inv_h, fz = (q.z - g.lo[2]) * g.inv_h;
                 // (a query with a bound this small is within 8 cells of a target, hence of the grid: no overflow)
                 const int xl = max((int)floorf(fx - rc), 0), xh = min((int)floorf(fx + rc), g.nf[0] - 1);
@@ -950,7 +958,7 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s /* M
                 if (done3 && lane == 0) { s_lq[li].x = __uint_as_float((unsigned)(kk >> 32)); s_lq[li].y = __uint_as_float((unsigned)kk); s_lq[li].w = __int_as_float(2); }
             }
             if (!done3 && lane == 0) s_pyr[NN_QPC + atomicAdd(&s_npyr, 1)] = (unsigned short)li;
-            if (lane == 0) atomicAdd(&lg_dbg2[done3 ? 3 : !(ubd < 3.0e38f) ? 0 : rc > 8.0f ? 1 : 2], 1u);
+            if (lane == 0) atomicAdd(&lg_dbg2[done3 ? 3 : !(ubd < 3.0e38f) ? 0 : rc > cube3 ? 1 : 2], 1u);
         }
         __syncthreads();
     }
@@ -961,7 +969,7 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s /* M
         for (int b0 = warp * 32; b0 < npyr; b0 += NN_THREADS) {
             const int li = s_pyr[NN_QPC + min(b0 + lane, npyr - 1)];      // idle lanes repeat the last query
             const float4 q = s_lq[li];
-            const unsigned long long kk = lg_warp_nn(py, q.x, q.y, q.z, slots);
+            const unsigned long long kk = lg_warp_nn(py, q.x, q.y, q.z, slots, s_lub[li]);
             __syncwarp();
             if (b0 + lane < npyr) { s_lq[li].x = __uint_as_float((unsigned)(kk >> 32)); s_lq[li].y = __uint_as_float((unsigned)kk); s_lq[li].w = __int_as_float(2); }
         }
@@ -1004,11 +1012,35 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s /* M
 // magnitude above the fp32 rounding of d2_rn, so a kept match is also the search's answer bit for bit (no tie possible).
 constexpr float LG_CERT_UP = 1.00001f, LG_CERT_DOWN = 0.99999f;
 
-// best (d2 bits << 32 | original index) and the second-smallest d2 among the scanned targets
-struct Best2 { unsigned long long key; float second; };
+// trackers of a scan.  Best2: best (d2 bits << 32 | original index) and the second-smallest d2 among the scanned targets;
+// Best3: the two best keys and the third-smallest d2 (for points whose two nearest targets are about equally far: the
+// certificate then names both and bounds the third)
+constexpr unsigned long long LG_KEY_NONE = (0x7f800000ull << 32) | 0xffffffffull;       // d2 = +inf
+struct Best2 {
+    unsigned long long key; float second;
+    __device__ __forceinline__ void init() { key = 0xffffffffffffffffull; second = __int_as_float(0x7f800000); }
+    __device__ __forceinline__ void update(unsigned long long ck) {
+        const unsigned long long hi = ck < key ? key : ck;              // the loser of (candidate, best) bounds the second
+        key = ck < key ? ck : key;
+        second = fminf(second, __uint_as_float((unsigned)(hi >> 32)));
+    }
+    __device__ __forceinline__ float thr() const { return second; }
+};
+struct Best3 {
+    unsigned long long k1, k2; float third;
+    __device__ __forceinline__ void init() { k1 = k2 = LG_KEY_NONE; third = __int_as_float(0x7f800000); }
+    __device__ __forceinline__ void update(unsigned long long ck) {
+        const unsigned long long h1 = ck < k1 ? k1 : ck;
+        k1 = ck < k1 ? ck : k1;
+        const unsigned long long h2 = h1 < k2 ? k2 : h1;
+        k2 = h1 < k2 ? h1 : k2;
+        third = fminf(third, __uint_as_float((unsigned)(h2 >> 32)));
+    }
+    __device__ __forceinline__ float thr() const { return third; }
+};
 
-template <class Acc>
-__device__ __forceinline__ void lg_scan_cells2(const Acc& acc, int x0, int x1, int iy, int iz, float qx, float qy, float qz, Best2& b) {
+template <class Acc, class Trk>
+__device__ __forceinline__ void lg_scan_cells2(const Acc& acc, int x0, int x1, int iy, int iz, float qx, float qy, float qz, Trk& b) {
     const int f = ((iz & 3) << 4) | ((iy & 3) << 2);
     for (int ix = x0; ix <= x1;) {
         const int bx = ix >> 2;
@@ -1019,10 +1051,7 @@ __device__ __forceinline__ void lg_scan_cells2(const Acc& acc, int x0, int x1, i
 #pragma unroll SCAN_UNROLL
             for (unsigned j = s; j < e; ++j) {
                 const float4 c = p[j];
-                const unsigned long long ck = ((unsigned long long)__float_as_uint(d2_rn(qx, qy, qz, c.x, c.y, c.z)) << 32) | __float_as_uint(c.w);
-                const unsigned long long hi = ck < b.key ? b.key : ck;          // the loser of (candidate, best) bounds the second
-                b.key = ck < b.key ? ck : b.key;
-                b.second = fminf(b.second, __uint_as_float((unsigned)(hi >> 32)));
+                b.update(((unsigned long long)__float_as_uint(d2_rn(qx, qy, qz, c.x, c.y, c.z)) << 32) | __float_as_uint(c.w));
             }
         }
         ix = xe + 1;
@@ -1032,8 +1061,8 @@ __device__ __forceinline__ void lg_scan_cells2(const Acc& acc, int x0, int x1, i
 // the cells meeting the cube q +- rho, rows and row ends farther than min(second so far, rho) skipped: exact best, and
 // every target that is not the best is at least min(sqrt(second), rho) away (gaps are 0.002 cells short, the cube 0.003
 // cells wide of the rounding of the binning).  rows_per_thread: lanes of a warp share one query when nl > 1.
-template <class Acc>
-__device__ __forceinline__ void lg_cube_search(const Acc& acc, const LgGeom& g, float x, float y, float z, float rho, int lane, int nl, Best2& b) {
+template <class Acc, class Trk>
+__device__ __forceinline__ void lg_cube_search(const Acc& acc, const LgGeom& g, float x, float y, float z, float rho, int lane, int nl, Trk& b) {
     const float rc = rho * g.inv_h * 1.00001f + 0.003f;
     const float fx = (x - g.lo[0]) * g.inv_h, fy = (y - g.lo[1]) * g.inv_h, fz = (z - g.lo[2]) * g.inv_h;
     const int xl = max((int)floorf(fx - rc), 0), xh = min((int)floorf(fx + rc), g.nf[0] - 1);
@@ -1049,7 +1078,7 @@ __device__ __forceinline__ void lg_cube_search(const Acc& acc, const LgGeom& g, 
         const int iy = yl + rw % ny, iz = zl + rw / ny;
         const float gy = gap1(fy, iy), gz = gap1(fz, iz);
         const float lb = (gy * gy + gz * gz) * h2;
-        const float thr = fminf(b.second, rho2);
+        const float thr = fminf(b.thr(), rho2);
         if (lb > thr) continue;                                      // everything in this row is strictly farther
         int xa = xl, xb = xh;
         while (xa < xb && lb + gap1(fx, xa) * gap1(fx, xa) * h2 > thr) ++xa;
@@ -1143,6 +1172,43 @@ lg_knn_kernel(LgGridView gv, float4* __restrict__ knn) {
     for (int k = 0; k < LG_KNN; ++k) out[1 + k] = ee[k];
 }
 
+
+// One WARP, one query (lane = row of cells): exact best over the cube q +- rho, written with the strongest certificate
+// the scan supports -- the runner-up by name when it is inside the cube (cur.w = -lb3, tg2 = runner-up: lg_track_kernel
+// then compares the two every iteration and needs a search only when the THIRD target comes close).  False if the cube
+// holds nothing (the caller falls back).
+__device__ __forceinline__ bool lg_warp_search_store(const GlobAcc& gacc, const LgGeom& g, const float4* __restrict__ t_orig, const float4& q,
+                                                     const float4& t0, float rho, int lane, int i, float4* __restrict__ cur,
+                                                     float4* __restrict__ tg, float4* __restrict__ tg2) {
+    Best3 b; b.init();
+    lg_cube_search(gacc, g, q.x, q.y, q.z, rho, lane, 32, b);
+    unsigned long long K1 = b.k1;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(KSS_FULL, K1, off); K1 = o < K1 ? o : K1; }
+    if (K1 == LG_KEY_NONE) return false;
+    unsigned long long K2 = b.k1 == K1 ? b.k2 : b.k1;                 // (the lanes scan disjoint rows: K1 lives in one lane)
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(KSS_FULL, K2, off); K2 = o < K2 ? o : K2; }
+    float rest = b.k1 == K1 ? (b.k2 == K2 ? b.third : __uint_as_float((unsigned)(b.k2 >> 32)))
+               : b.k1 == K2 ? __uint_as_float((unsigned)(b.k2 >> 32)) : __uint_as_float((unsigned)(b.k1 >> 32));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) rest = fminf(rest, __shfl_xor_sync(KSS_FULL, rest, off));
+    if (lane == 0) {
+        const float rho2 = rho * rho;
+        const unsigned ti = (unsigned)K1;
+        const float4 t = ti == (unsigned)__float_as_int(t0.w) ? t0 : __ldg(t_orig + ti);
+        tg[i] = make_float4(t.x, t.y, t.z, __int_as_float((int)ti));
+        const float d2nd = __uint_as_float((unsigned)(K2 >> 32));
+        if (d2nd < rho2) {                                            // the runner-up is known by name
+            const unsigned t2i = (unsigned)K2;
+            const float4 t2 = __ldg(t_orig + t2i);
+            tg2[i] = make_float4(t2.x, t2.y, t2.z, __int_as_float((int)t2i));
+            cur[i] = make_float4(q.x, q.y, q.z, -(sqrtf(fminf(rest, rho2)) * LG_CERT_DOWN));
+        } else cur[i] = make_float4(q.x, q.y, q.z, sqrtf(rho2) * LG_CERT_DOWN);
+    }
+    return true;
+}
+
 // The flagged queries (by sorted position, so that a warp's searches share cache lines), one thread each: a query that
 // carries a match holds a bound before a single cell is read.  It scans the cube q +- (bound + margin) from the grid in
 // global memory (L2-resident: points 16 B, tables, ranks) when that is at most 3 x 3 rows of cells -- exact without
@@ -1150,7 +1216,7 @@ lg_knn_kernel(LgGridView gv, float4* __restrict__ knn) {
 // farther than a certificate could survive.  Everything else is counted and queued for the general kernels.
 constexpr int RF_SEG = 2048;                     // sorted positions per CTA of lg_refine_kernel
 __global__ void __launch_bounds__(256)
-lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur, float4* __restrict__ tg, const int* __restrict__ perm,
+lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur, float4* __restrict__ tg, float4* __restrict__ tg2, const int* __restrict__ perm,
                  unsigned char* __restrict__ flagS, int* __restrict__ worklist, LgState* __restrict__ st, float margin_cells) {
     __shared__ LgGeom g;
     __shared__ float T[16];
@@ -1195,30 +1261,10 @@ lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur, float4* __res
         const float4 q = cur[i], t0 = tg[i];
         bool unres = true;
         if (__float_as_int(t0.w) >= 0) {
-            const float sd = sqrtf(d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z));
-            float nx, ny, nz;
-            xform_point(T, q.x, q.y, q.z, nx, ny, nz);
-            const float mv = sqrtf((nx - q.x) * (nx - q.x) + (ny - q.y) * (ny - q.y) + (nz - q.z) * (nz - q.z));
-            const float rho = fmaxf(sd * LG_CERT_UP + (2.0f * mv < m ? m : 0.0f), sd * 1.001f);
-            if (rho * g.inv_h * 1.00001f + 0.003f <= 8.0f) {
-                Best2 b; b.key = 0xffffffffffffffffull; b.second = __int_as_float(0x7f800000);
-                lg_cube_search(gacc, g, q.x, q.y, q.z, rho, lane, 32, b);
-                unsigned long long kk = b.key;
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(KSS_FULL, kk, off); kk = o < kk ? o : kk; }
-                float s2 = b.key == kk ? b.second : __uint_as_float((unsigned)(b.key >> 32));
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) s2 = fminf(s2, __shfl_xor_sync(KSS_FULL, s2, off));
-                if (kk != 0xffffffffffffffffull) {
-                    unres = false;
-                    if (lane == 0) {
-                        const unsigned ti = (unsigned)kk;
-                        const float4 t = ti == (unsigned)__float_as_int(t0.w) ? t0 : __ldg(gv.t_orig + ti);
-                        tg[i] = make_float4(t.x, t.y, t.z, __int_as_float((int)ti));
-                        cur[i] = make_float4(q.x, q.y, q.z, sqrtf(fminf(s2, rho * rho)) * LG_CERT_DOWN);
-                        flagS[pos] = 0;
-                    }
-                }
+            const float rho = sqrtf(d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z)) * 1.001f + m;
+            if (rho * g.inv_h * 1.00001f + 0.003f <= cube3 && lg_warp_search_store(gacc, g, gv.t_orig, q, t0, rho, lane, i, cur, tg, tg2)) {
+                unres = false;
+                if (lane == 0) flagS[pos] = 0;
             }
         }
         if (unres && lane == 0) worklist[atomicAdd(&st->n_unres, 1u)] = pos;
@@ -1241,7 +1287,7 @@ lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur, float4* __res
                 const float mv = sqrtf((nx - q.x) * (nx - q.x) + (ny - q.y) * (ny - q.y) + (nz - q.z) * (nz - q.z));
                 const float rho = sd * LG_CERT_UP + (2.0f * mv < m ? m : 0.0f);
                 if (rho * g.inv_h * 1.00001f + 0.003f <= 2.6f) {          // (false for NaN too)
-                    Best2 b; b.key = 0xffffffffffffffffull; b.second = __int_as_float(0x7f800000);
+                    Best2 b; b.init();
                     lg_cube_search(gacc, g, q.x, q.y, q.z, rho, 0, 1, b);
                     if (b.key != 0xffffffffffffffffull) {                 // (the match itself lies in the cube)
                         unres = false;
@@ -1267,7 +1313,7 @@ lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur, float4* __res
 // The few queries lg_refine_kernel could not finish, one WARP each (persistent grid over the work list): a query with a
 // match reads the cells meeting the cube q +- bound (lane = row, up to 17 x 17 rows); the rest goes to the pyramid.
 __global__ void __launch_bounds__(256)
-lg_left_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur, float4* __restrict__ tg, const int* __restrict__ perm,
+lg_left_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur, float4* __restrict__ tg, float4* __restrict__ tg2, const int* __restrict__ perm,
                unsigned char* __restrict__ flagS, const int* __restrict__ worklist, LgState* __restrict__ st, int staged_launched) {
     __shared__ LgGeom g;
     __shared__ float4 slots[8][TILE];
@@ -1285,33 +1331,23 @@ lg_left_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur, flo
         const int pos = worklist[e];
         const int i = perm[pos];
         const float4 q = cur[i], t0 = tg[i];
-        unsigned long long kk = 0xffffffffffffffffull;
-        float lbq = 0.0f;
+        bool found = false;
         if (__float_as_int(t0.w) >= 0) {
-            // (0.1 % beyond the match: far from the target the second-nearest is about as far as the nearest, and that is
-            // all the certificate can live on)
-            const float rho = sqrtf(d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z)) * 1.001f;
-            if (rho * g.inv_h * 1.00001f + 0.003f <= 8.0f) {
-                Best2 b; b.key = 0xffffffffffffffffull; b.second = __int_as_float(0x7f800000);
-                lg_cube_search(gacc, g, q.x, q.y, q.z, rho, lane, 32, b);
-                kk = b.key;
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) { const unsigned long long o = __shfl_xor_sync(KSS_FULL, kk, off); kk = o < kk ? o : kk; }
-                // second-nearest over the lanes: a lane's two nearest are (key, second)
-                float s2 = b.key == kk ? b.second : __uint_as_float((unsigned)(b.key >> 32));
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) s2 = fminf(s2, __shfl_xor_sync(KSS_FULL, s2, off));
-                lbq = sqrtf(fminf(s2, rho * rho)) * LG_CERT_DOWN;
+            // (0.1 % beyond the match: far from the target the second-nearest is about as far as the nearest)
+            const float rho = sqrtf(d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z)) * 1.001f + 0.25f * g.h;
+            if (rho * g.inv_h * 1.00001f + 0.003f <= cube3) found = lg_warp_search_store(gacc, g, gv.t_orig, q, t0, rho, lane, i, cur, tg, tg2);
+        }
+        if (!found) {
+            const float seed = __float_as_int(t0.w) >= 0 ? d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z) : __int_as_float(0x7f800000);
+            const unsigned long long kk = lg_warp_nn(py, q.x, q.y, q.z, slots[warp], seed); ++n_pyr;       // every lane carries the same query
+            if (lane == 0) {
+                const unsigned ti = (unsigned)kk;
+                const float4 t = __ldg(gv.t_orig + ti);
+                tg[i] = make_float4(t.x, t.y, t.z, __int_as_float((int)ti));
+                cur[i] = make_float4(q.x, q.y, q.z, 0.0f);
             }
         }
-        if (kk == 0xffffffffffffffffull) { kk = lg_warp_nn(py, q.x, q.y, q.z, slots[warp]); ++n_pyr; lbq = 0.0f; }       // every lane carries the same query
-        if (lane == 0) {
-            const unsigned ti = (unsigned)kk;
-            const float4 t = __ldg(gv.t_orig + ti);
-            tg[i] = make_float4(t.x, t.y, t.z, __int_as_float((int)ti));
-            cur[i] = make_float4(q.x, q.y, q.z, lbq);
-            flagS[pos] = 0;
-        }
+        if (lane == 0) flagS[pos] = 0;
     }
     if (lane == 0 && n_pyr) atomicAdd(&st->miss[2], n_pyr);
 }
@@ -1755,7 +1791,7 @@ __device__ __forceinline__ float lg_sqrt_approx(float x) {      // relative erro
     float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
 }
 __global__ void __launch_bounds__(256, 2)
-lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict__ tg, const int* __restrict__ inv,
+lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict__ tg, float4* __restrict__ tg2, const int* __restrict__ inv,
                 const float4* __restrict__ knn, unsigned char* __restrict__ flagS, unsigned char* __restrict__ dirty,
                 float* __restrict__ partA, double* __restrict__ partD, int* __restrict__ partK, LgTree tr,
                 LgState* __restrict__ st, double max2, volatile int* __restrict__ h_unres) {
@@ -1789,17 +1825,25 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
             bool push = false, open = false;
             if (i < n) {
                 const float4 cv = sv[u];
-                float x = cv.x, y = cv.y, z = cv.z, lb = cv.w;
+                float x = cv.x, y = cv.y, z = cv.z, lb = fabsf(cv.w);
+                const bool two = cv.w < 0.0f;                               // the certificate names the runner-up (tg2)
                 if (applyT) {
                     xform_point(T, cv.x, cv.y, cv.z, x, y, z);
                     const float mx = x - cv.x, my = y - cv.y, mz = z - cv.z;
                     lb = (lb - lg_sqrt_approx(mx * mx + my * my + mz * mz) * LG_CERT_UP) * LG_CERT_DOWN;
                 }
-                const float d2 = d2_rn(x, y, z, tv[u].x, tv[u].y, tv[u].z);
+                float d2 = d2_rn(x, y, z, tv[u].x, tv[u].y, tv[u].z);
+                if (two) {                                                  // (rare: points about equally far from two targets)
+                    const float4 t2 = tg2[i];
+                    const float d2b = d2_rn(x, y, z, t2.x, t2.y, t2.z);
+                    const unsigned long long ka = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(tv[u].w);
+                    const unsigned long long kb = ((unsigned long long)__float_as_uint(d2b) << 32) | __float_as_uint(t2.w);
+                    if (kb < ka) { tg2[i] = tv[u]; tg[i] = t2; tv[u] = t2; d2 = d2b; }
+                }
                 sv[u] = make_float4(x, y, z, d2);
                 const bool has = __float_as_int(tv[u].w) >= 0;
                 // sqrt(d2) * UP < lb, squared (lb > 0)
-                if (has && lb > 0.0f && d2 * (LG_CERT_UP * LG_CERT_UP) < lb * lb) cur[i] = make_float4(x, y, z, lb);
+                if (has && lb > 0.0f && d2 * (LG_CERT_UP * LG_CERT_UP) < lb * lb) cur[i] = make_float4(x, y, z, two ? -lb : lb);
                 else if (has) push = true;
                 else { open = true; cur[i] = make_float4(x, y, z, 0.0f); flagS[inv[i]] = 1; }
             }
@@ -2194,6 +2238,7 @@ int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, i
     float4* inp = c.get<float4>("lg_inp", n_s);               // sorted input (fitness pass), w = original index
     float4* cur = c.get<float4>("lg_cur", n_s);               // by original index: position (transformed in place every iteration), certificate
     float4* tg = c.get<float4>("lg_tg", n_s);                 // by original index: matched target, its index (-1: none yet)
+    float4* tg2 = c.get<float4>("lg_tg2", n_s);               // by original index: the runner-up, where the certificate names it (cur.w < 0)
     float* d2 = c.get<float>("lg_d2", n_s);
     int* perm = c.get<int>("lg_perm", n_s);                   // sorted position -> original index
     int* inv = c.get<int>("lg_inv", n_s);                     // original index -> sorted position
@@ -2233,7 +2278,7 @@ int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, i
     static_assert(sizeof(Pyramid) <= sizeof(run->pyramid), "LargeIcp::pyramid too small");
     memcpy(run->pyramid, &py, sizeof(py));
     run->n_s = n_s; run->n_t = n_t; run->nchunks = nchunks;
-    run->inp = inp; run->cur = cur; run->tg = tg; run->d2 = d2; run->perm = perm; run->inv = inv; run->flagS = flagS;
+    run->inp = inp; run->cur = cur; run->tg = tg; run->tg2 = tg2; run->d2 = d2; run->perm = perm; run->inv = inv; run->flagS = flagS;
     run->dirty = dirty; run->worklist = worklist;
     run->partA = pA; run->partB = pB; run->partD = pD; run->partK = pK; run->state = state; run->out3 = out3;
     run->l2f = l2f; run->l2d = l2d; run->l2k = l2k; run->grpcnt = grpcnt; run->S = S; run->S2 = S2;
@@ -2260,15 +2305,15 @@ int large_icp_iterations(cudaStream_t st, long long* launches, LargeIcp* run, co
         // it only decides whether the staged kernel is worth a launch; the one-warp-per-query kernel takes any count.)
         const int known = run->h_unres ? *(volatile int*)run->h_unres : 0x7fffffff;
         const bool staged = known > n / 8;
-        launch_pdl(pdl, lg_track_kernel, (nch + 7) / 8, 256, 0, st, n, nch, cur, tg, run->inv, gv.knn, run->flagS, run->dirty, run->partA,
+        launch_pdl(pdl, lg_track_kernel, (nch + 7) / 8, 256, 0, st, n, nch, cur, tg, (float4*)run->tg2, run->inv, gv.knn, run->flagS, run->dirty, run->partA,
                    run->partD, run->partK, tr, state, max2, (volatile int*)run->h_unres);
-        launch_pdl(pdl, lg_refine_kernel, (n + RF_SEG - 1) / RF_SEG, 256, 0, st, gv, n, cur, tg, run->perm, run->flagS, run->worklist, state, margin);
+        launch_pdl(pdl, lg_refine_kernel, (n + RF_SEG - 1) / RF_SEG, 256, 0, st, gv, n, cur, tg, (float4*)run->tg2, run->perm, run->flagS, run->worklist, state, margin);
         if (staged) {
             cudaFuncSetAttribute(lg_nn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM);
             launch_pdl(pdl, lg_nn_kernel<1>, nn_grid(n), NN_THREADS, NN_SMEM, st, py, gv, n, cur, (const float4*)nullptr, (int*)nullptr,
                        (float*)nullptr, tg, run->perm, run->flagS, state);
         }
-        launch_pdl(pdl, lg_left_kernel, 148 * 4, 256, 0, st, py, gv, n, cur, tg, run->perm, run->flagS, run->worklist, state, staged ? 1 : 0);
+        launch_pdl(pdl, lg_left_kernel, 148 * 4, 256, 0, st, py, gv, n, cur, tg, (float4*)run->tg2, run->perm, run->flagS, run->worklist, state, staged ? 1 : 0);
         if (run->mark) { run->mark(run->mark_user, KSS_STAGE_LARGE_NN, 0); run->mark(run->mark_user, KSS_STAGE_LARGE_REDUCE, 1); }
         launch_pdl(pdl, lg_passA_kernel, (nch + 7) / 8, 256, 0, st, (const float4*)cur, (const float4*)tg, run->dirty, max2, n, nch, run->partA,
                    run->partD, run->partK, tr, state, (volatile int*)run->h_unres);

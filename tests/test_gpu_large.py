@@ -134,3 +134,32 @@ def test_register_batch_ragged_large_full_clouds(ctx, okss, pkg):
         assert np.array_equal(np.asarray(res[p]["T"]).reshape(4, 4), o["T"]) and int(res[p]["winner"]) == o["winner"]
         assert np.array_equal(pa[p, :cS[p]], o["point_align"])
         assert np.allclose([res[p]["mse"], res[p]["rmse"], res[p]["mae"]], [o["mse"], o["rmse"], o["mae"]], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("n,index,iters", [(20000, 4, 60), (70000, 5, 45)])
+def test_large_icp_long_run_bit_exact(ctx, okss, pkg, n, index, iters):
+    """far past PCL's convergence (rotation/translation and relative-MSE exits disabled, fixed iteration count): late
+    iterations keep certified matches, re-certify from the target's neighbour lists or search only a few points -- every
+    one of them has to leave the same correspondences as the oracle's kd-tree, or T and the fitness drift apart"""
+    p = pkg.synth.scan_pair(index, n)
+    kw = dict(max_iter=iters, trans_eps=-1.0, fit_eps=0.0)
+    o = okss.icp(p["full_s"], p["full_t"], sum_order=okss.SUM_CANON256, method=okss.NN_KDTREE, **kw)
+    g = ctx.icp(p["full_s"], p["full_t"], **kw)
+    assert g["iters"] == o["iters"] and g["iters"] > 30
+    assert np.array_equal(g["T"], o["T"])
+    assert g["fitness"] == o["fitness"]
+
+
+def test_large_icp_duplicate_targets_and_rim(ctx, okss, pkg):
+    """targets that coincide (fp32-equal distances: the lowest index has to win in every iteration, certificates can
+    never hold for them) and a source that reaches beyond the target's footprint (two targets about equally far)"""
+    p = pkg.synth.scan_pair(6, 30000)
+    t = p["full_t"].copy()
+    t[15000:15400] = t[100:500]                            # 400 coincident pairs
+    s = np.concatenate([p["full_s"], p["full_s"][:2000] * np.array([1.0, 1.0, 1.0]) + np.array([0.35, 0.0, 0.0])])
+    kw = dict(max_iter=40, trans_eps=-1.0, fit_eps=0.0, max_corr_dist=0.2)
+    o = okss.icp(s, t, sum_order=okss.SUM_CANON256, method=okss.NN_KDTREE, **kw)
+    g = ctx.icp(s, t, **kw)
+    assert g["iters"] == o["iters"]
+    assert np.array_equal(g["T"], o["T"])
+    assert g["fitness"] == o["fitness"]
