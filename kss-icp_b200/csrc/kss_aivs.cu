@@ -58,63 +58,65 @@ __device__ __forceinline__ void aivs_center(const AivsGrid& g, int box, double c
     c[2] = __ddiv_rn(__dadd_rn(__dadd_rn(__dadd_rn(g.mn[2], __dmul_rn((double)(z_num - 1), g.unit)), g.mn[2]), __dmul_rn((double)z_num, g.unit)), 2.0);
 }
 
-// ---------------------------------------------------------------- 1. border, grid geometry (one CTA per cloud)
+// ---------------------------------------------------------------- 1. border (many CTAs per cloud), grid geometry
+__device__ __forceinline__ unsigned long long aivs_ord(double v) {          // monotone map double -> u64
+    unsigned long long a = (unsigned long long)__double_as_longlong(v);
+    return (a >> 63) ? ~a : (a | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double aivs_unord(unsigned long long a) {
+    a = (a >> 63) ? (a & 0x7fffffffffffffffull) : ~a;
+    return __longlong_as_double((long long)a);
+}
+// ext[p][0..2] = min keys (initialised to all ones), ext[p][3..5] = max keys (initialised to zero)
 __global__ void __launch_bounds__(256)
-aivs_grid_kernel(const double* __restrict__ pts, const int* __restrict__ cnt, int cap, const int* __restrict__ point_num,
-                 int point_num_all, int bcap, AivsGrid* __restrict__ grids, int* __restrict__ bad) {
-    __shared__ unsigned long long kmin[3], kmax[3];      // (ordered double bits, index) packed: value high bits not enough ->
-    __shared__ double vmin[3], vmax[3];
-    __shared__ int imin[3], imax[3];
-    const int p = blockIdx.x;
+aivs_extent_kernel(const double* __restrict__ pts, const int* __restrict__ cnt, int cap, unsigned long long* __restrict__ ext) {
+    const int p = blockIdx.y;
     const int n = cnt ? cnt[p] : cap;
     const double* P = pts + (size_t)p * cap * 3;
-    // two steps: extreme values, then the lowest index attaining them (= first strict extreme in a forward scan)
     double lmin[3] = {INFINITY, INFINITY, INFINITY}, lmax[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+#pragma unroll
         for (int d = 0; d < 3; ++d) { const double v = P[3 * (size_t)i + d]; lmin[d] = fmin(lmin[d], v); lmax[d] = fmax(lmax[d], v); }
-    if (threadIdx.x < 3) { kmin[threadIdx.x] = 0xffffffffffffffffull; kmax[threadIdx.x] = 0ull; imin[threadIdx.x] = 0x7fffffff; imax[threadIdx.x] = 0x7fffffff; }
-    __syncthreads();
+#pragma unroll
     for (int d = 0; d < 3; ++d) {
-        unsigned long long a = (unsigned long long)__double_as_longlong(lmin[d]); a = (a >> 63) ? ~a : (a | 0x8000000000000000ull);
-        unsigned long long b = (unsigned long long)__double_as_longlong(lmax[d]); b = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-        atomicMin(&kmin[d], a); atomicMax(&kmax[d], b);
-    }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        unsigned long long a = kmin[threadIdx.x]; a = (a >> 63) ? (a & 0x7fffffffffffffffull) : ~a;
-        unsigned long long b = kmax[threadIdx.x]; b = (b >> 63) ? (b & 0x7fffffffffffffffull) : ~b;
-        vmin[threadIdx.x] = __longlong_as_double((long long)a); vmax[threadIdx.x] = __longlong_as_double((long long)b);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-        for (int d = 0; d < 3; ++d) {
-            const double v = P[3 * (size_t)i + d];
-            if (v == vmin[d]) atomicMin(&imin[d], i);
-            if (v == vmax[d]) atomicMin(&imax[d], i);
+        unsigned long long a = aivs_ord(lmin[d]), b = aivs_ord(lmax[d]);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const unsigned long long oa = __shfl_xor_sync(KSS_FULL, a, off), ob = __shfl_xor_sync(KSS_FULL, b, off);
+            a = oa < a ? oa : a; b = ob > b ? ob : b;
         }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        AivsGrid g;
-        g.n = n; g.point_num = point_num ? point_num[p] : point_num_all;
-        const int boxNum = aivs_box_scale(n);
-        double dis[3];
-        for (int d = 0; d < 3; ++d) { g.mn[d] = vmin[d]; dis[d] = fabs(__dsub_rn(vmax[d], vmin[d])); }
-        double large = dis[0];
-        if (large < dis[1]) large = dis[1];
-        if (large < dis[2]) large = dis[2];
-        g.unit = __ddiv_rn(large, (double)boxNum);
-        int num[3];
-        for (int d = 0; d < 3; ++d) {
-            const double nd = __ddiv_rn(dis[d], g.unit);
-            num[d] = (int)nd;
-            if (nd > (double)num[d]) num[d]++;
-        }
-        g.nx = num[0]; g.ny = num[1]; g.nz = num[2];
-        const long long nb = (long long)g.nx * g.ny * g.nz + 1;
-        g.nbox = (int)nb; g.n_samples = 0; g.pad = 0;
-        if (!(large > 0.0) || nb > bcap || g.nx < 1 || g.ny < 1 || g.nz < 1) { g.nbox = 0; atomicExch(bad, 1); }   // degenerate cloud
-        grids[p] = g;
+        if ((threadIdx.x & 31) == 0) { atomicMin(&ext[(size_t)p * 6 + d], a); atomicMax(&ext[(size_t)p * 6 + 3 + d], b); }
     }
+}
+__global__ void __launch_bounds__(128)
+aivs_grid_kernel(const unsigned long long* __restrict__ ext, const int* __restrict__ cnt, int cap, const int* __restrict__ point_num,
+                 int point_num_all, int bcap, int P, AivsGrid* __restrict__ grids, int* __restrict__ bad) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int n = cnt ? cnt[p] : cap;
+    AivsGrid g;
+    g.n = n; g.point_num = point_num ? point_num[p] : point_num_all;
+    const int boxNum = aivs_box_scale(n);
+    double dis[3];
+    for (int d = 0; d < 3; ++d) {
+        const double vmin = aivs_unord(ext[(size_t)p * 6 + d]), vmax = aivs_unord(ext[(size_t)p * 6 + 3 + d]);
+        g.mn[d] = vmin; dis[d] = fabs(__dsub_rn(vmax, vmin));
+    }
+    double large = dis[0];
+    if (large < dis[1]) large = dis[1];
+    if (large < dis[2]) large = dis[2];
+    g.unit = __ddiv_rn(large, (double)boxNum);
+    int num[3];
+    for (int d = 0; d < 3; ++d) {
+        const double nd = __ddiv_rn(dis[d], g.unit);
+        num[d] = (int)nd;
+        if (nd > (double)num[d]) num[d]++;
+    }
+    g.nx = num[0]; g.ny = num[1]; g.nz = num[2];
+    const long long nb = (long long)g.nx * g.ny * g.nz + 1;
+    g.nbox = (int)nb; g.n_samples = 0; g.pad = 0;
+    if (!(large > 0.0) || nb > bcap || g.nx < 1 || g.ny < 1 || g.nz < 1) { g.nbox = 0; atomicExch(bad, 1); }   // degenerate cloud
+    grids[p] = g;
 }
 
 __device__ __forceinline__ int aivs_box_of(const AivsGrid& g, const double* q) {
@@ -190,39 +192,54 @@ aivs_fill_kernel(int cap, const AivsGrid* __restrict__ grids, int bcap, const in
     members[(size_t)p * cap + atomicAdd(&cursor[(size_t)p * bcap + b], 1)] = i;
 }
 
-// per box: ascending original index (the reference's push_back order), the centre-nearest member, the quota
+// per box (one WARP): ascending original index (the reference's push_back order) by rank sort through `tmp`, the
+// centre-nearest member, the quota
 __global__ void __launch_bounds__(256)
 aivs_box_kernel(const double* __restrict__ pts, int cap, const AivsGrid* __restrict__ grids, int bcap,
-                const int* __restrict__ box_start, int* __restrict__ members, int* __restrict__ center_pos,
+                const int* __restrict__ box_start, int* __restrict__ members, int* __restrict__ tmp, int* __restrict__ center_pos,
                 int* __restrict__ quota) {
     const int p = blockIdx.y;
     const AivsGrid g = grids[p];
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= g.nbox) return;
     const int* st = box_start + (size_t)p * (bcap + 1);
     const int s = st[b], m = st[b + 1] - s;
     int* mem = members + (size_t)p * cap + s;
-    for (int i = 1; i < m; ++i) {                              // insertion sort (lists are short)
-        const int v = mem[i];
-        int j = i - 1;
-        while (j >= 0 && mem[j] > v) { mem[j + 1] = mem[j]; --j; }
-        mem[j + 1] = v;
+    int* tm = tmp + (size_t)p * cap + s;
+    if (m > 1) {                                               // all indices are distinct: rank = number of smaller ones
+        for (int i = lane; i < m; i += 32) {
+            const int v = mem[i];
+            int r = 0;
+            for (int j = 0; j < m; ++j) r += mem[j] < v;
+            tm[r] = v;
+        }
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) mem[i] = tm[i];
+        __syncwarp();
     }
     double c[3];
     aivs_center(g, b, c);
     double best = 9999.0; int bi = -1;
     const double* P = pts + (size_t)p * cap * 3;
-    for (int i = 0; i < m; ++i) {                              // BoxInput: first strict minimum of the distance to the centre
+    for (int i = lane; i < m; i += 32) {                       // BoxInput: first strict minimum of the distance to the centre
         const double* q = P + 3 * (size_t)mem[i];
         const double dx = __dsub_rn(c[0], q[0]), dy = __dsub_rn(c[1], q[1]), dz = __dsub_rn(c[2], q[2]);
         const double dm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
         if (best > dm) { best = dm; bi = i; }
     }
-    center_pos[(size_t)p * bcap + b] = bi;
-    const double rate = __ddiv_rn((double)g.point_num, (double)g.n);
-    const double sb = __dmul_rn((double)m, rate);
-    const int t = (int)sb;
-    quota[(size_t)p * bcap + b] = (__dsub_rn(sb, (double)t) > 0.2) ? t + 1 : t;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {                  // smaller distance, the lower position among equals
+        const double ob = __shfl_xor_sync(KSS_FULL, best, off);
+        const int oi = __shfl_xor_sync(KSS_FULL, bi, off);
+        if (oi >= 0 && (bi < 0 || ob < best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+        center_pos[(size_t)p * bcap + b] = bi;
+        const double rate = __ddiv_rn((double)g.point_num, (double)g.n);
+        const double sb = __dmul_rn((double)m, rate);
+        const int t = (int)sb;
+        quota[(size_t)p * bcap + b] = (__dsub_rn(sb, (double)t) > 0.2) ? t + 1 : t;
+    }
 }
 
 // ---------------------------------------------------------------- 3. farthest point sampling, one colour per launch
@@ -238,12 +255,15 @@ __device__ __forceinline__ int aivs_colour(int i, int j, int k) {
     return 7;
 }
 
-// one box of AIVS_Voroni_OpenMP_KNN, run by one thread
+// one box of AIVS_Voroni_OpenMP_KNN, run by one WARP: lane l owns the members t = l (mod 32) of the box (their running
+// minimum distances md[t] live in global memory); seeds are found 32 candidates at a time and applied one after the other
+// (a minimum does not care about the order); the arg-max keeps the reference's first strict maximum
 __device__ void aivs_fps_box(int p, int b, const AivsGrid& g, const double* __restrict__ pts, int cap, int bcap,
                              const int* __restrict__ box_start, const int* __restrict__ members,
                              const int* __restrict__ center_pos, const int* __restrict__ quota,
                              unsigned char* __restrict__ selected /* labelG == 0 */, double* __restrict__ mind,
                              int* __restrict__ sel, int* __restrict__ sel_cnt) {
+    const int lane = threadIdx.x & 31;
     const int* st = box_start + (size_t)p * (bcap + 1);
     const int s = st[b], m = st[b + 1] - s;
     const int simNum = quota[(size_t)p * bcap + b];
@@ -256,6 +276,8 @@ __device__ void aivs_fps_box(int p, int b, const AivsGrid& g, const double* __re
     double pc[3];
     aivs_center(g, b, pc);
     const double radius = __ddiv_rn(__dmul_rn(g.unit, 3.0), 4.0);
+    const double cl[3] = {__dsub_rn(pc[0], radius), __dsub_rn(pc[1], radius), __dsub_rn(pc[2], radius)};
+    const double ch[3] = {__dadd_rn(pc[0], radius), __dadd_rn(pc[1], radius), __dadd_rn(pc[2], radius)};
     // neighbour boxes through the reference's decode (no x wrap, B10)
     const int z_num = b / (g.nx * g.ny) + 1;
     const int leveZ = b % (g.nx * g.ny);
@@ -271,65 +293,81 @@ __device__ void aivs_fps_box(int p, int b, const AivsGrid& g, const double* __re
     if (z_num > 1) zs[nzs++] = z_num - 1;
     zs[nzs++] = z_num;
     if (z_num < g.nz) zs[nzs++] = z_num + 1;
+    auto relax = [&](float sx, float sy, float sz, bool assign) {     // md[t] = min(md[t], |member t - s|) over the lane's members
+        for (int t = lane; t < m; t += 32) {
+            const double* w = P + 3 * (size_t)mem[s + t];
+            const double d = (double)__fsqrt_rn(d2_rn((float)w[0], (float)w[1], (float)w[2], sx, sy, sz));
+            if (assign || d < md[t]) md[t] = d;
+        }
+    };
     // initial distances: to the nearest already-selected point of the neighbour boxes inside the seed cube,
     // or (if there is none) to the box's centre-nearest member, which then becomes the first sample
-    for (int t = 0; t < m; ++t) md[t] = INFINITY;
+    for (int t = lane; t < m; t += 32) md[t] = INFINITY;
     bool any_seed = false;
     for (int a = 0; a < nxs; ++a) for (int c = 0; c < nys; ++c) for (int e = 0; e < nzs; ++e) {
         if (xs[a] == x_num && ys[c] == y_num && zs[e] == z_num) continue;
         const int nb = xs[a] + (ys[c] - 1) * g.nx + (zs[e] - 1) * g.nx * g.ny;
         if (nb >= g.nbox || nb < 0) continue;
         const int ns = st[nb], nm = st[nb + 1] - ns;
-        for (int l = 0; l < nm; ++l) {
-            const int pt = mem[ns + l];
-            if (!lab[pt]) continue;
-            const double* q = P + 3 * (size_t)pt;
-            if (!(q[0] <= __dadd_rn(pc[0], radius) && q[0] >= __dsub_rn(pc[0], radius) && q[1] <= __dadd_rn(pc[1], radius) &&
-                  q[1] >= __dsub_rn(pc[1], radius) && q[2] <= __dadd_rn(pc[2], radius) && q[2] >= __dsub_rn(pc[2], radius))) continue;
-            any_seed = true;
-            const float sx = (float)q[0], sy = (float)q[1], sz = (float)q[2];
-            for (int t = 0; t < m; ++t) {
-                const double* w = P + 3 * (size_t)mem[s + t];
-                const double d = (double)__fsqrt_rn(d2_rn((float)w[0], (float)w[1], (float)w[2], sx, sy, sz));
-                if (d < md[t]) md[t] = d;
+        for (int l0 = 0; l0 < nm; l0 += 32) {
+            const int l = l0 + lane;
+            bool seed = false;
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            if (l < nm) {
+                const int pt = mem[ns + l];
+                if (lab[pt]) {
+                    const double* q = P + 3 * (size_t)pt;
+                    seed = q[0] <= ch[0] && q[0] >= cl[0] && q[1] <= ch[1] && q[1] >= cl[1] && q[2] <= ch[2] && q[2] >= cl[2];
+                    sx = (float)q[0]; sy = (float)q[1]; sz = (float)q[2];
+                }
+            }
+            unsigned bal = __ballot_sync(KSS_FULL, seed);
+            any_seed |= bal != 0u;
+            while (bal) {
+                const int src = __ffs(bal) - 1; bal &= bal - 1u;
+                relax(__shfl_sync(KSS_FULL, sx, src), __shfl_sync(KSS_FULL, sy, src), __shfl_sync(KSS_FULL, sz, src), false);
             }
         }
     }
-    for (int t = 0; t < m; ++t) if (md[t] == INFINITY) md[t] = 9999.0;
+    for (int t = lane; t < m; t += 32) if (md[t] == INFINITY) md[t] = 9999.0;
     int sampled = 0;
     if (!any_seed) {
         const int ci = center_pos[(size_t)p * bcap + b];
         if (ci >= 0 && ci < m) {
             const double* q = P + 3 * (size_t)mem[s + ci];
-            const float sx = (float)q[0], sy = (float)q[1], sz = (float)q[2];
-            for (int t = 0; t < m; ++t) {
-                const double* w = P + 3 * (size_t)mem[s + t];
-                md[t] = (double)__fsqrt_rn(d2_rn((float)w[0], (float)w[1], (float)w[2], sx, sy, sz));
-            }
-            md[ci] = 0.0; out[sampled++] = mem[s + ci]; lab[mem[s + ci]] = 1;
+            relax((float)q[0], (float)q[1], (float)q[2], true);
+            __syncwarp();
+            if (lane == 0) { md[ci] = 0.0; out[sampled] = mem[s + ci]; lab[mem[s + ci]] = 1; }
+            ++sampled;
+            __syncwarp();
         }
     }
     while (sampled < simNum) {
         int pick = -1; double mx = 0.0;
-        for (int t = 0; t < m; ++t) if (md[t] > mx) { pick = t; mx = md[t]; }     // first strict maximum
-        if (pick == -1) break;
-        md[pick] = 0.0; lab[mem[s + pick]] = 1; out[sampled++] = mem[s + pick];
-        const double* q = P + 3 * (size_t)mem[s + pick];
-        const float sx = (float)q[0], sy = (float)q[1], sz = (float)q[2];
-        for (int t = 0; t < m; ++t) {
-            const double* w = P + 3 * (size_t)mem[s + t];
-            const double d = (double)__fsqrt_rn(d2_rn(sx, sy, sz, (float)w[0], (float)w[1], (float)w[2]));
-            if (d < md[t]) md[t] = d;
+        for (int t = lane; t < m; t += 32) if (md[t] > mx) { pick = t; mx = md[t]; }     // the lane's first strict maximum
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {              // larger value, the lower position among equals
+            const double om = __shfl_xor_sync(KSS_FULL, mx, off);
+            const int op = __shfl_xor_sync(KSS_FULL, pick, off);
+            if (op >= 0 && (pick < 0 || om > mx || (om == mx && op < pick))) { mx = om; pick = op; }
         }
+        if (pick == -1) break;
+        const int pp = mem[s + pick];
+        if (lane == 0) { md[pick] = 0.0; lab[pp] = 1; out[sampled] = pp; }
+        ++sampled;
+        __syncwarp();
+        const double* q = P + 3 * (size_t)pp;
+        relax((float)q[0], (float)q[1], (float)q[2], false);
+        __syncwarp();
     }
-    sel_cnt[(size_t)p * bcap + b] = sampled;
+    if (lane == 0) sel_cnt[(size_t)p * bcap + b] = sampled;
 }
 
 // Same-colour boxes never see each other's points -- except the boxes whose index is a multiple of nx * ny: the
 // reference's centre decode misplaces their centre (B10), so their seed cube can reach same-colour boxes, including
 // each other.  In the reference's loop order they are the last boxes of their colour, in ascending index.  So a colour
-// is two phases: 2c = all other boxes, one thread each; 2c + 1 = the misplaced ones, one after the other.
-__global__ void __launch_bounds__(128)
+// is two phases: 2c = all other boxes, one warp each; 2c + 1 = the misplaced ones, one after the other (one warp).
+__global__ void __launch_bounds__(256)
 aivs_fps_kernel(int phase, const double* __restrict__ pts, int cap, const AivsGrid* __restrict__ grids, int bcap,
                 const int* __restrict__ box_start, const int* __restrict__ members, const int* __restrict__ center_pos,
                 const int* __restrict__ quota, unsigned char* __restrict__ selected, double* __restrict__ mind,
@@ -338,15 +376,17 @@ aivs_fps_kernel(int phase, const double* __restrict__ pts, int cap, const AivsGr
     const AivsGrid g = grids[p];
     const int colour = phase >> 1;
     if (phase & 1) {
-        if (blockIdx.x != 0 || threadIdx.x != 0) return;
+        if (blockIdx.x != 0 || threadIdx.x >= 32) return;
         for (int k = 1; k <= g.nz; ++k) {
             const int b = g.nx * g.ny * k;
             if (b >= g.nbox || aivs_colour(g.nx, g.ny, k) != colour) continue;
             aivs_fps_box(p, b, g, pts, cap, bcap, box_start, members, center_pos, quota, selected, mind, sel, sel_cnt);
+            __threadfence();                                   // (the next misplaced box may read this one's labels)
+            __syncwarp();
         }
         return;
     }
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b < 1 || b >= g.nbox || (b % (g.nx * g.ny)) == 0) return;
     // true (i,j,k) of the box, as the colouring loop enumerates them (Method_AIVS_SimPro.hpp:598-602)
     const int b0 = b - 1;
@@ -986,8 +1026,9 @@ int aivs_simplify_device(cudaStream_t st, long long* launches, int P, const doub
         return alloc(nm, bytes, out);
     };
     AivsGrid* grids; int *box_of, *box_cnt, *box_start, *cursor, *members, *center_pos, *quota, *sel, *sel_cnt, *sel_start, *sample;
-    unsigned char* selected; double* mind; unsigned long long* key1; float* dis2;
+    unsigned char* selected; double* mind; unsigned long long *key1, *ext; float* dis2;
     int r = 0;
+    r |= get("ext", sizeof(unsigned long long) * (size_t)P * 6, (void**)&ext);
     r |= get("grids", sizeof(AivsGrid) * (size_t)P, (void**)&grids);
     r |= get("box_of", sizeof(int) * (size_t)P * cap, (void**)&box_of);
     r |= get("box_cnt", sizeof(int) * (size_t)P * bcap, (void**)&box_cnt);
@@ -1009,15 +1050,18 @@ int aivs_simplify_device(cudaStream_t st, long long* launches, int P, const doub
     cudaMemsetAsync(box_cnt, 0, sizeof(int) * (size_t)P * bcap, st);
     cudaMemsetAsync(sel_cnt, 0, sizeof(int) * (size_t)P * bcap, st);
     cudaMemsetAsync(selected, 0, (size_t)P * cap, st);
-    aivs_grid_kernel<<<P, 256, 0, st>>>(d_pts, d_cnt, cap, d_point_num, point_num_all, bcap, grids, d_bad);
-    const dim3 gp((cap + 255) / 256, P), gb((bcap + 255) / 256, P);
+    cudaMemset2DAsync(ext, 48, 0xff, 24, P, st);                      // min keys: all ones
+    cudaMemset2DAsync(ext + 3, 48, 0x00, 24, P, st);                  // max keys: zero
+    aivs_extent_kernel<<<dim3(std::max(1, std::min((cap + 2047) / 2048, 1184 / std::max(P, 1) + 1)), P), 256, 0, st>>>(d_pts, d_cnt, cap, ext);
+    aivs_grid_kernel<<<(P + 127) / 128, 128, 0, st>>>(ext, d_cnt, cap, d_point_num, point_num_all, bcap, P, grids, d_bad);
+    const dim3 gp((cap + 255) / 256, P), gb((bcap + 255) / 256, P), gw((bcap + 7) / 8, P);
     aivs_count_kernel<<<gp, 256, 0, st>>>(d_pts, cap, grids, bcap, box_of, box_cnt);
     aivs_scan_kernel<<<P, 1024, 0, st>>>(grids, bcap, box_cnt, box_start, cursor);
     aivs_fill_kernel<<<gp, 256, 0, st>>>(cap, grids, bcap, box_of, cursor, members);
-    aivs_box_kernel<<<gb, 256, 0, st>>>(d_pts, cap, grids, bcap, box_start, members, center_pos, quota);
+    aivs_box_kernel<<<gw, 256, 0, st>>>(d_pts, cap, grids, bcap, box_start, members, sel, center_pos, quota);
     for (int c = 0; c < 16; ++c)
-        aivs_fps_kernel<<<dim3((bcap + 127) / 128, P), 128, 0, st>>>(c, d_pts, cap, grids, bcap, box_start, members, center_pos,
-                                                                  quota, selected, mind, sel, sel_cnt);
+        aivs_fps_kernel<<<(c & 1) ? dim3(1, P) : gw, (c & 1) ? 32 : 256, 0, st>>>(c, d_pts, cap, grids, bcap, box_start, members, center_pos,
+                                                                               quota, selected, mind, sel, sel_cnt);
     aivs_scan_kernel<<<P, 1024, 0, st>>>(grids, bcap, sel_cnt, sel_start, nullptr);
     aivs_gather_kernel<<<gb, 256, 0, st>>>(cap, grids, bcap, box_start, sel, sel_cnt, sel_start, sample);
     aivs_k3_kernel<<<dim3((smax + 255) / 256, P), 256, 0, st>>>(d_pts, cap, grids, bcap, sel_start, sample, key1, dis2);
@@ -1026,7 +1070,7 @@ int aivs_simplify_device(cudaStream_t st, long long* launches, int P, const doub
     if (cudaFuncSetAttribute(aivs_cut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return KSS_ERR_CUDA;
     aivs_cut_kernel<<<P, 512, smem, st>>>(d_pts, cap, grids, bcap, sel_start, sample, key1, dis2, np2, d_out, out_cap, d_out_cnt,
                                           d_out_idx, d_bad);
-    *launches += 25;
+    *launches += 26;
     return cudaGetLastError() == cudaSuccess ? KSS_OK : KSS_ERR_CUDA;
 }
 
