@@ -1179,7 +1179,7 @@ lg_knn_kernel(LgGridView gv, float4* __restrict__ knn) {
 // holds nothing (the caller falls back).
 __device__ __forceinline__ bool lg_warp_search_store(const GlobAcc& gacc, const LgGeom& g, const float4* __restrict__ t_orig, const float4& q,
                                                      const float4& t0, float rho, int lane, int i, float4* __restrict__ cur,
-                                                     float4* __restrict__ tg, float4* __restrict__ tg2) {
+                                                     float4* __restrict__ tg, float4* __restrict__ tg2, float4* __restrict__ cert) {
     Best3 b; b.init();
     lg_cube_search(gacc, g, q.x, q.y, q.z, rho, lane, 32, b);
     unsigned long long K1 = b.k1;
@@ -1203,8 +1203,8 @@ __device__ __forceinline__ bool lg_warp_search_store(const GlobAcc& gacc, const 
             const unsigned t2i = (unsigned)K2;
             const float4 t2 = __ldg(t_orig + t2i);
             tg2[i] = make_float4(t2.x, t2.y, t2.z, __int_as_float((int)t2i));
-            cur[i] = make_float4(q.x, q.y, q.z, -(sqrtf(fminf(rest, rho2)) * LG_CERT_DOWN));
-        } else cur[i] = make_float4(q.x, q.y, q.z, sqrtf(rho2) * LG_CERT_DOWN);
+            cur[i] = cert[i] = make_float4(q.x, q.y, q.z, -(sqrtf(fminf(rest, rho2)) * LG_CERT_DOWN));
+        } else cur[i] = cert[i] = make_float4(q.x, q.y, q.z, sqrtf(rho2) * LG_CERT_DOWN);
     }
     return true;
 }
@@ -1216,7 +1216,7 @@ __device__ __forceinline__ bool lg_warp_search_store(const GlobAcc& gacc, const 
 // farther than a certificate could survive.  Everything else is counted and queued for the general kernels.
 constexpr int RF_SEG = 2048;                     // sorted positions per CTA of lg_refine_kernel
 __global__ void __launch_bounds__(256)
-lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur, float4* __restrict__ tg, float4* __restrict__ tg2, const int* __restrict__ perm,
+lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur, float4* __restrict__ tg, float4* __restrict__ tg2, float4* __restrict__ cert, const int* __restrict__ perm,
                  unsigned char* __restrict__ flagS, int* __restrict__ worklist, LgState* __restrict__ st, float margin_cells) {
     __shared__ LgGeom g;
     __shared__ float T[16];
@@ -1262,9 +1262,19 @@ lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur, float4* __res
         bool unres = true;
         if (__float_as_int(t0.w) >= 0) {
             const float rho = sqrtf(d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z)) * 1.001f + m;
-            if (rho * g.inv_h * 1.00001f + 0.003f <= cube3 && lg_warp_search_store(gacc, g, gv.t_orig, q, t0, rho, lane, i, cur, tg, tg2)) {
+            if (rho * g.inv_h * 1.00001f + 0.003f <= cube3 && lg_warp_search_store(gacc, g, gv.t_orig, q, t0, rho, lane, i, cur, tg, tg2, cert)) {
                 unres = false;
                 if (lane == 0) flagS[pos] = 0;
+#ifdef KSS_LG_DEBUG
+                if (lane == 0 && st->iters > 400 && st->iters < 404) {
+                    const float4 c2 = cur[i], n1 = tg[i], n2 = tg2[i];
+                    const float4 L0 = __ldg(gv.knn + (size_t)__float_as_int(t0.w) * LG_KSLOTS);
+                    printf("it %d i %d: sd %.6g (cells %.3f) old match %d -> %d, new cert %.6g (gap %.3g), runner-up %d at %.6g, list R %.6g, rho %.6g\n", st->iters, i,
+                           sqrtf(d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z)), sqrtf(d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z)) * g.inv_h, __float_as_int(t0.w), __float_as_int(n1.w), c2.w,
+                           fabsf(c2.w) - sqrtf(d2_rn(q.x, q.y, q.z, n1.x, n1.y, n1.z)), c2.w < 0 ? __float_as_int(n2.w) : -1,
+                           c2.w < 0 ? sqrtf(d2_rn(q.x, q.y, q.z, n2.x, n2.y, n2.z)) : 0.f, L0.x, rho);
+                }
+#endif
             }
         }
         if (unres && lane == 0) worklist[atomicAdd(&st->n_unres, 1u)] = pos;
@@ -1294,7 +1304,7 @@ lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur, float4* __res
                         const unsigned ti = (unsigned)b.key;
                         const float4 t = ti == (unsigned)__float_as_int(t0.w) ? t0 : __ldg(gv.t_orig + ti);
                         tg[i] = make_float4(t.x, t.y, t.z, __int_as_float((int)ti));
-                        cur[i] = make_float4(q.x, q.y, q.z, sqrtf(fminf(b.second, rho * rho)) * LG_CERT_DOWN);
+                        cur[i] = cert[i] = make_float4(q.x, q.y, q.z, sqrtf(fminf(b.second, rho * rho)) * LG_CERT_DOWN);
                         flagS[pos] = 0;
                     }
                 }
@@ -1313,7 +1323,7 @@ lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur, float4* __res
 // The few queries lg_refine_kernel could not finish, one WARP each (persistent grid over the work list): a query with a
 // match reads the cells meeting the cube q +- bound (lane = row, up to 17 x 17 rows); the rest goes to the pyramid.
 __global__ void __launch_bounds__(256)
-lg_left_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur, float4* __restrict__ tg, float4* __restrict__ tg2, const int* __restrict__ perm,
+lg_left_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur, float4* __restrict__ tg, float4* __restrict__ tg2, float4* __restrict__ cert, const int* __restrict__ perm,
                unsigned char* __restrict__ flagS, const int* __restrict__ worklist, LgState* __restrict__ st, int staged_launched) {
     __shared__ LgGeom g;
     __shared__ float4 slots[8][TILE];
@@ -1335,7 +1345,7 @@ lg_left_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur, flo
         if (__float_as_int(t0.w) >= 0) {
             // (0.1 % beyond the match: far from the target the second-nearest is about as far as the nearest)
             const float rho = sqrtf(d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z)) * 1.001f + 0.25f * g.h;
-            if (rho * g.inv_h * 1.00001f + 0.003f <= cube3) found = lg_warp_search_store(gacc, g, gv.t_orig, q, t0, rho, lane, i, cur, tg, tg2);
+            if (rho * g.inv_h * 1.00001f + 0.003f <= cube3) found = lg_warp_search_store(gacc, g, gv.t_orig, q, t0, rho, lane, i, cur, tg, tg2, cert);
         }
         if (!found) {
             const float seed = __float_as_int(t0.w) >= 0 ? d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z) : __int_as_float(0x7f800000);
@@ -1748,7 +1758,7 @@ constexpr int TK_QCAP = 64;                      // queue entries per warp (a ro
 // one round: lane e < cnt takes queue entry e.  Returns 1 if the entry stays open.
 __device__ __forceinline__ unsigned lg_list_round(const float4* __restrict__ qa, const float4* __restrict__ qb, int cnt, int lane,
                                                   const float4* __restrict__ knn, float4* __restrict__ cur, float4* __restrict__ tg,
-                                                  const int* __restrict__ inv, unsigned char* __restrict__ flagS, unsigned& nlist) {
+                                                  float4* __restrict__ cert, unsigned& nlist) {
     if (lane >= cnt) return 0u;
     const float4 q = qa[lane];                   // {x, y, z, bits(i)}
     const float4 p = qb[lane];                   // the match {x, y, z, bits(index)}
@@ -1772,7 +1782,7 @@ __device__ __forceinline__ unsigned lg_list_round(const float4* __restrict__ qa,
     }
     const float db = sqrtf(__uint_as_float((unsigned)(bk >> 32)));
     if (db * LG_CERT_UP < rho) {                 // (false for NaN and for rho <= 0)
-        cur[i] = make_float4(q.x, q.y, q.z, fminf(sqrtf(second), rho) * LG_CERT_DOWN);
+        cur[i] = cert[i] = make_float4(q.x, q.y, q.z, fminf(sqrtf(second), rho) * LG_CERT_DOWN);
         if (kb) {
             float4 t = e[1];
 #pragma unroll
@@ -1782,16 +1792,14 @@ __device__ __forceinline__ unsigned lg_list_round(const float4* __restrict__ qa,
         ++nlist;
         return 0u;
     }
-    cur[i] = make_float4(q.x, q.y, q.z, 0.0f);
-    flagS[inv[i]] = 1;
-    return 1u;
+    return 1u;                                   // stays open: the caller decides who searches it
 }
 
 __device__ __forceinline__ float lg_sqrt_approx(float x) {      // relative error 2^-22, far inside the certificate margins
     float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
 }
 __global__ void __launch_bounds__(256, 2)
-lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict__ tg, float4* __restrict__ tg2, const int* __restrict__ inv,
+lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict__ tg, float4* __restrict__ tg2, float4* __restrict__ cert, const int* __restrict__ inv,
                 const float4* __restrict__ knn, unsigned char* __restrict__ flagS, unsigned char* __restrict__ dirty,
                 float* __restrict__ partA, double* __restrict__ partD, int* __restrict__ partK, LgTree tr,
                 LgState* __restrict__ st, double max2, volatile int* __restrict__ h_unres) {
@@ -1817,6 +1825,11 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
     const bool applyT = st->apply_T != 0;
     if (c < nchunks) {
         float4* qa = s_qa[warp]; float4* qb = s_qb[warp];
+        // entries a list round left open go to the search kernels
+        auto leftover = [&](unsigned open, int) -> unsigned {
+            if (open) { const float4 q = qa[lane]; const int i = __float_as_int(q.w); cur[i] = make_float4(q.x, q.y, q.z, 0.0f); flagS[inv[i]] = 1; }
+            return open;
+        };
         unsigned nfail = 0u, nlist = 0u, redo = 0u;  // redo: bit u = this lane's point u went through the queue
         int qn = 0;                                  // queue fill (warp-uniform)
 #pragma unroll
@@ -1843,7 +1856,17 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
                 sv[u] = make_float4(x, y, z, d2);
                 const bool has = __float_as_int(tv[u].w) >= 0;
                 // sqrt(d2) * UP < lb, squared (lb > 0)
-                if (has && lb > 0.0f && d2 * (LG_CERT_UP * LG_CERT_UP) < lb * lb) cur[i] = make_float4(x, y, z, two ? -lb : lb);
+                bool ok = has && lb > 0.0f && d2 * (LG_CERT_UP * LG_CERT_UP) < lb * lb;
+                if (!ok && has && cv.w != 0.0f) {
+                    // lb lost the length of the whole PATH since the certificate was established; what counts is the
+                    // DISPLACEMENT from where it was established (at a fixed point the cloud jitters by an fp32 ulp per
+                    // iteration and goes nowhere): second chance from the recorded position, and a fresh start for lb
+                    const float4 c0 = cert[i];
+                    const float ex = x - c0.x, ey = y - c0.y, ez = z - c0.z;
+                    lb = (fabsf(c0.w) - sqrtf(ex * ex + ey * ey + ez * ez) * LG_CERT_UP) * LG_CERT_DOWN;
+                    ok = lb > 0.0f && d2 * (LG_CERT_UP * LG_CERT_UP) < lb * lb;
+                }
+                if (ok) cur[i] = make_float4(x, y, z, two ? -lb : lb);
                 else if (has) push = true;
                 else { open = true; cur[i] = make_float4(x, y, z, 0.0f); flagS[inv[i]] = 1; }
             }
@@ -1859,7 +1882,7 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
                 qn += __popc(pb);
                 __syncwarp();
                 if (qn >= 32) {
-                    nfail += lg_list_round(qa, qb, 32, lane, knn, cur, tg, inv, flagS, nlist);
+                    nfail += leftover(lg_list_round(qa, qb, 32, lane, knn, cur, tg, cert, nlist), 32);
                     __syncwarp();
                     if (lane + 32 < qn) { const float4 a = qa[lane + 32], b2 = qb[lane + 32]; __syncwarp(); qa[lane] = a; qb[lane] = b2; }
                     else __syncwarp();
@@ -1868,7 +1891,7 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
                 }
             }
         }
-        if (qn > 0) nfail += lg_list_round(qa, qb, qn, lane, knn, cur, tg, inv, flagS, nlist);
+        if (qn > 0) nfail += leftover(lg_list_round(qa, qb, qn, lane, knn, cur, tg, cert, nlist), qn);
         nfail = __reduce_add_sync(KSS_FULL, nfail);
         nlist = __reduce_add_sync(KSS_FULL, nlist);
         if (lane == 0) {
@@ -1892,9 +1915,9 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
     // the clean chunks arrive at their group; a group (and, with nothing open anywhere, the whole of pass A) that
     // completes here is reduced here
     __syncthreads();
-    const int g = lg_group_arrive(tr.grpcnt, nchunks, s_clean);
-    if (g < 0) return;
-    lg_group_A(partA, partD, partK, tr, nchunks, g);
+    const int grp = lg_group_arrive(tr.grpcnt, nchunks, s_clean);
+    if (grp < 0) return;
+    lg_group_A(partA, partD, partK, tr, nchunks, grp);
     if (!lg_groups_done(tr.grpcnt, &st->ticketA, (nchunks + 255) >> 8)) return;
     lg_finish_A(nchunks, tr, st, h_unres);
 }
@@ -2238,6 +2261,7 @@ int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, i
     float4* inp = c.get<float4>("lg_inp", n_s);               // sorted input (fitness pass), w = original index
     float4* cur = c.get<float4>("lg_cur", n_s);               // by original index: position (transformed in place every iteration), certificate
     float4* tg = c.get<float4>("lg_tg", n_s);                 // by original index: matched target, its index (-1: none yet)
+    float4* cert = c.get<float4>("lg_cert", n_s);             // by original index: where and with which bound the certificate was established
     float4* tg2 = c.get<float4>("lg_tg2", n_s);               // by original index: the runner-up, where the certificate names it (cur.w < 0)
     float* d2 = c.get<float>("lg_d2", n_s);
     int* perm = c.get<int>("lg_perm", n_s);                   // sorted position -> original index
@@ -2278,7 +2302,7 @@ int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, i
     static_assert(sizeof(Pyramid) <= sizeof(run->pyramid), "LargeIcp::pyramid too small");
     memcpy(run->pyramid, &py, sizeof(py));
     run->n_s = n_s; run->n_t = n_t; run->nchunks = nchunks;
-    run->inp = inp; run->cur = cur; run->tg = tg; run->tg2 = tg2; run->d2 = d2; run->perm = perm; run->inv = inv; run->flagS = flagS;
+    run->inp = inp; run->cur = cur; run->tg = tg; run->tg2 = tg2; run->cert = cert; run->d2 = d2; run->perm = perm; run->inv = inv; run->flagS = flagS;
     run->dirty = dirty; run->worklist = worklist;
     run->partA = pA; run->partB = pB; run->partD = pD; run->partK = pK; run->state = state; run->out3 = out3;
     run->l2f = l2f; run->l2d = l2d; run->l2k = l2k; run->grpcnt = grpcnt; run->S = S; run->S2 = S2;
@@ -2305,15 +2329,15 @@ int large_icp_iterations(cudaStream_t st, long long* launches, LargeIcp* run, co
         // it only decides whether the staged kernel is worth a launch; the one-warp-per-query kernel takes any count.)
         const int known = run->h_unres ? *(volatile int*)run->h_unres : 0x7fffffff;
         const bool staged = known > n / 8;
-        launch_pdl(pdl, lg_track_kernel, (nch + 7) / 8, 256, 0, st, n, nch, cur, tg, (float4*)run->tg2, run->inv, gv.knn, run->flagS, run->dirty, run->partA,
+        launch_pdl(pdl, lg_track_kernel, (nch + 7) / 8, 256, 0, st, n, nch, cur, tg, (float4*)run->tg2, (float4*)run->cert, run->inv, gv.knn, run->flagS, run->dirty, run->partA,
                    run->partD, run->partK, tr, state, max2, (volatile int*)run->h_unres);
-        launch_pdl(pdl, lg_refine_kernel, (n + RF_SEG - 1) / RF_SEG, 256, 0, st, gv, n, cur, tg, (float4*)run->tg2, run->perm, run->flagS, run->worklist, state, margin);
+        launch_pdl(pdl, lg_refine_kernel, (n + RF_SEG - 1) / RF_SEG, 256, 0, st, gv, n, cur, tg, (float4*)run->tg2, (float4*)run->cert, run->perm, run->flagS, run->worklist, state, margin);
         if (staged) {
             cudaFuncSetAttribute(lg_nn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM);
             launch_pdl(pdl, lg_nn_kernel<1>, nn_grid(n), NN_THREADS, NN_SMEM, st, py, gv, n, cur, (const float4*)nullptr, (int*)nullptr,
                        (float*)nullptr, tg, run->perm, run->flagS, state);
         }
-        launch_pdl(pdl, lg_left_kernel, 148 * 4, 256, 0, st, py, gv, n, cur, tg, (float4*)run->tg2, run->perm, run->flagS, run->worklist, state, staged ? 1 : 0);
+        launch_pdl(pdl, lg_left_kernel, 148 * 4, 256, 0, st, py, gv, n, cur, tg, (float4*)run->tg2, (float4*)run->cert, run->perm, run->flagS, run->worklist, state, staged ? 1 : 0);
         if (run->mark) { run->mark(run->mark_user, KSS_STAGE_LARGE_NN, 0); run->mark(run->mark_user, KSS_STAGE_LARGE_REDUCE, 1); }
         launch_pdl(pdl, lg_passA_kernel, (nch + 7) / 8, 256, 0, st, (const float4*)cur, (const float4*)tg, run->dirty, max2, n, nch, run->partA,
                    run->partD, run->partK, tr, state, (volatile int*)run->h_unres);

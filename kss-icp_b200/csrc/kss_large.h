@@ -25,7 +25,7 @@ struct LargeIcp {
     alignas(8) unsigned char pyramid[160];
     alignas(8) unsigned char grid[72];
     int n_s = 0, n_t = 0, nchunks = 0;
-    void *inp = nullptr, *cur = nullptr, *tg = nullptr, *tg2 = nullptr, *state = nullptr;   // inp: sorted input; cur / tg: by original index
+    void *inp = nullptr, *cur = nullptr, *tg = nullptr, *tg2 = nullptr, *cert = nullptr, *state = nullptr;   // inp: sorted input; cur / tg: by original index
     int *partK = nullptr, *perm = nullptr, *inv = nullptr, *worklist = nullptr;
     unsigned char *flagS = nullptr, *dirty = nullptr;
     int* h_unres = nullptr;             // pinned host word (mapped): left-over count of an earlier iteration
