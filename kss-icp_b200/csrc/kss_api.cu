@@ -46,6 +46,12 @@ struct kss_ctx {
     static constexpr int MAX_LANES = 4;
     cudaStream_t lane_stream[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t lane_done[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+    // full-resolution PCR_QM of a batch of large pairs: the pairs of a chunk go round-robin over a few side streams (each
+    // with its own large-path buffers), so that the many small launches of one pair overlap those of its neighbours
+    static constexpr int MQ = 4;
+    cudaStream_t mq_stream[MQ] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t mq_done[MQ] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t mq_fork = nullptr;
     cudaEvent_t fork_ev = nullptr;
     std::string buf_suffix;           // appended to buffer names while a lane is active
     // optional per-stage CUDA-event timing (bench.py roofline): events on the launching stream
@@ -421,14 +427,31 @@ int pipeline_device(kss_ctx* ctx, int P, const kss_batch& b, const double* sim_s
         KL(launch_nn_small(st, P, 1, pa, cnt_S, cap_S, S_perm, T_sorted, T_box, cnt_T, cap_Tpad, nullptr, nullptr,
                            &d_out[0].mse, (int)(sizeof(kss_pair_result) / sizeof(double))));
     } else {
-        // full-resolution clouds beyond the shared-memory path: block-grid NN, pair by pair (every launch is enqueued
-        // without a host synchronisation; h_cnt_* are the per-pair sizes on the host, null = capacity)
+        // full-resolution clouds beyond the shared-memory path: block-grid NN per pair (every launch is enqueued without a
+        // host synchronisation; h_cnt_* are the per-pair sizes on the host, null = capacity).  One pair: on this stream.
+        // Several: round-robin over MQ side streams with their own buffers, forked from and joined to this stream.
+        const int nq = P > 1 ? std::min(P, (int)kss_ctx::MQ) : 0;
+        if (nq) {
+            if (!ctx->mq_fork) CU(cudaEventCreateWithFlags(&ctx->mq_fork, cudaEventDisableTiming));
+            for (int k = 0; k < nq; ++k) {
+                if (!ctx->mq_stream[k]) CU(cudaStreamCreateWithFlags(&ctx->mq_stream[k], cudaStreamNonBlocking));
+                if (!ctx->mq_done[k]) CU(cudaEventCreateWithFlags(&ctx->mq_done[k], cudaEventDisableTiming));
+            }
+            CU(cudaEventRecord(ctx->mq_fork, st));
+            for (int k = 0; k < nq; ++k) CU(cudaStreamWaitEvent(ctx->mq_stream[k], ctx->mq_fork, 0));
+        }
         for (int p = 0; p < P; ++p) {
-            int r = large_metrics_device(ctx->stream, &ctx->launches, pa + (size_t)p * cap_S * 3, h_cnt_S ? h_cnt_S[p] : cap_S,
+            const int k = nq ? p % nq : 0;
+            char pfx[16]; snprintf(pfx, sizeof(pfx), nq ? "pq%d:" : "", k);
+            int r = large_metrics_device(nq ? ctx->mq_stream[k] : st, &ctx->launches, pa + (size_t)p * cap_S * 3, h_cnt_S ? h_cnt_S[p] : cap_S,
                                          full_t + (size_t)p * cap_T * 3, h_cnt_T ? h_cnt_T[p] : cap_T, &d_out[p].mse,
                                          [&](const char* name, size_t bytes, void** out) {
-                                             unsigned char* q; int rr = dev_buf(ctx, name, bytes, &q); *out = q; return rr; });
+                                             unsigned char* q; int rr = dev_buf(ctx, (std::string(pfx) + name).c_str(), bytes, &q); *out = q; return rr; });
             if (r != KSS_OK) return fail(ctx, r, "large-cloud metrics failed");
+        }
+        for (int k = 0; k < nq; ++k) {
+            CU(cudaEventRecord(ctx->mq_done[k], ctx->mq_stream[k]));
+            CU(cudaStreamWaitEvent(st, ctx->mq_done[k], 0));
         }
     }
     return KSS_OK;
@@ -504,6 +527,11 @@ void kss_ctx_destroy(kss_ctx* ctx) {
         if (ctx->lane_done[l]) cudaEventDestroy(ctx->lane_done[l]);
     }
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    for (int k = 0; k < kss_ctx::MQ; ++k) {
+        if (ctx->mq_stream[k]) cudaStreamDestroy(ctx->mq_stream[k]);
+        if (ctx->mq_done[k]) cudaEventDestroy(ctx->mq_done[k]);
+    }
+    if (ctx->mq_fork) cudaEventDestroy(ctx->mq_fork);
     if (ctx->comm && kss_nccl()) kss_nccl()->CommDestroy(ctx->comm);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
