@@ -1,6 +1,7 @@
 /*
  * kss_oracle.cpp -- CPU restatement of the KSS-ICP registration hot path.
- * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (see kss_oracle.h header comment).
+ * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED except the nearest-neighbour stage, which is checked against real FLANN
+ * code (see kss_oracle.h header comment).
  *
  * Build:  g++ -O2 -std=c++17 -ffp-contract=off -pthread -fPIC -shared
  * (-ffp-contract=off is REQUIRED: every expression below is meant to round once
