@@ -37,7 +37,9 @@ def _timed_iterations(ctx, st, never, count, flush=None):
     with torch.cuda.stream(st):
         for _ in range(count):
             if flush is not None:
-                flush.zero_()
+                flush[0].zero_()                 # > L2 written: nothing of the pair is left in L2 ...
+                flush[1].sum()                   # ... and > L2 read: no dirty lines either, whose write-back would be billed to
+                                                 # the first kernel of the iteration
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(st)
             ctx.icp_large_iterate(1, **never)
@@ -53,7 +55,8 @@ def icp_iteration_roofline(pkg, ctx, args, hbm_peak, which, stream=None):
     p = pkg.synth.scan_pair(0, N)
     dev = torch.cuda.current_device()
     st = torch.cuda.current_stream() if stream is None else stream
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % dev)     # > 126 MB L2
+    flush = (torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % dev),      # > 126 MB L2, twice
+             torch.zeros(64 << 20, dtype=torch.float32, device="cuda:%d" % dev))
     never = dict(max_iter=1 << 30, fit_eps=-1.0, trans_eps=-1.0)                  # no convergence exit
 
     ctx.icp_large_begin(p["full_s"], p["full_t"])          # first call also pays cudaMalloc of the work buffers
@@ -93,10 +96,29 @@ def icp_iteration_roofline(pkg, ctx, args, hbm_peak, which, stream=None):
     _timed_iterations(ctx, st, never, 40, flush=flush)
     nn_ms_cold, nn_calls = ctx.stage_ms(8)
     red_ms_cold, _ = ctx.stage_ms(9)
+    track_ms_cold, track_calls = ctx.stage_ms(12)
     nn_cold = nn_ms_cold / max(1, nn_calls)
     red_cold = red_ms_cold / max(1, nn_calls)
+    track_cold = track_ms_cold / max(1, track_calls)
     ctx.set_timing(False)
     res = ctx.icp_large_end(**never)
+
+    # the reference's own correspondence engine beside it: real FLANN code (OpenCV's bundled copy, exact single kd-tree
+    # as in pcl::KdTreeFLANN) on one host core, for the NN stage of ONE iteration
+    flann_cpu = None
+    try:
+        import cv2
+        t32 = np.ascontiguousarray(p["full_t"], np.float32); q32 = np.ascontiguousarray(p["full_s"][:min(N, 200000)], np.float32)
+        t0 = _time.perf_counter()
+        fidx = cv2.flann_Index(t32, dict(algorithm=4, leaf_max_size=10, reorder=True, dim=3))
+        t1 = _time.perf_counter()
+        fidx.knnSearch(q32, 1, params=dict(checks=-1, eps=0.0, sorted=True))
+        t2 = _time.perf_counter()
+        flann_cpu = {"what": "cv2.flann_Index algorithm 4 (FLANN KDTreeSingleIndex), exact 1-NN, one host thread",
+                     "kd_tree_build_s": t1 - t0, "queries": int(len(q32)), "query_s": t2 - t1,
+                     "nn_stage_ms_per_iteration_extrapolated": 1000.0 * (t2 - t1) * N / len(q32)}
+    except Exception as e:      # noqa: BLE001
+        flann_cpu = {"unavailable": str(e)[:80]}
 
     iter_bytes = 76.0 * N + 12.0 * N
     nn_bytes = 12.0 * N + 12.0 * N + 8.0 * N
@@ -104,15 +126,17 @@ def icp_iteration_roofline(pkg, ctx, args, hbm_peak, which, stream=None):
     after_ms = float(np.median(after))
     gbs = lambda b, ms: b / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm",
-                "kernel": "lg_track_kernel (+ lg_refine_kernel / lg_left_kernel for the points whose certificate failed): "
-                          "1M-point correspondences + fused transform + fused pass A, steady state",
-                "achieved": gbs(nn_bytes, nn_cold), "peak": hbm_peak, "unit": "GB/s",
-                "frac": gbs(nn_bytes, nn_cold) / hbm_peak, "traffic": _ncu_traffic(),
+                "kernel": "lg_track_kernel: 1M-point correspondences (certificate test, neighbour-list re-certification) + fused "
+                          "transform + fused pass A, steady state; the whole correspondence stage (with lg_refine_kernel / "
+                          "lg_left_kernel for the points left open) is icp_iter_1m.nn_ms_cold",
+                "achieved": gbs(nn_bytes, track_cold), "peak": hbm_peak, "unit": "GB/s",
+                "frac": gbs(nn_bytes, track_cold) / hbm_peak, "traffic": _ncu_traffic(),
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch of lg_track_kernel, ncu capture summarised in profiles/r02_large_path_1m.md",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % which,
-                "algorithmic_bytes_per_launch": nn_bytes, "ms_per_launch": nn_cold,
-                "timing": "CUDA events on the launching stream around the correspondence kernels of every iteration, "
-                          "L2 flushed (256 MB write) before each iteration, 40 iterations at the fixed point"}
+                "algorithmic_bytes_per_launch": nn_bytes, "ms_per_launch": track_cold,
+                "timing": "CUDA events on the launching stream around every launch of the kernel, "
+                          "L2 flushed (256 MB written, then 256 MB of another buffer read so that no dirty lines are left) before each "
+                          "iteration, 40 iterations at the fixed point"}
     extra = {"icp_iter_1m": {"points": N,
                              "regime": "steady state (fixed point after %d iterations)" % (n_pcl + args.settle_1m),
                              "ms_cold_l2_flushed": cold_ms, "ms_warm_back_to_back": warm_ms,
@@ -130,6 +154,7 @@ def icp_iteration_roofline(pkg, ctx, args, hbm_peak, which, stream=None):
                                           "ms_sum": float(np.sum(run_ms)), "ms_mean": float(np.mean(run_ms)),
                                           "what": "every iteration of the run (CUDA events, back to back): the first ones "
                                                   "search from scratch far from the target, later ones keep certified matches"},
+                             "flann_cpu": flann_cpu,
                              "whole_run": {"ms_host_clock": whole_ms, "iterations": n_pcl, "converged": int(whole["converged"]),
                                            "fitness": float(whole["fitness"]),
                                            "what": "kss_icp from host clouds: H2D + build + iterations to PCL's convergence + fitness pass + D2H"}}}

@@ -127,7 +127,8 @@ int kss_ctx_set_hyp_slots(kss_ctx* ctx, int slots);
 #define KSS_STAGE_LARGE_REDUCE    9   /* large path: canonical reductions + SVD       */
 #define KSS_STAGE_CG_BUILD       10   /* candidate grid build (per pair, once)         */
 #define KSS_STAGE_AIVS           11   /* AIVS simplification of raw clouds             */
-#define KSS_STAGE_COUNT          12
+#define KSS_STAGE_LARGE_TRACK    12   /* large path: the streaming kernel of an ICP iteration alone (inside LARGE_NN) */
+#define KSS_STAGE_COUNT          13
 int kss_ctx_set_timing(kss_ctx* ctx, int enable);      /* also resets the accumulators */
 int kss_ctx_stage_ms(kss_ctx* ctx, int stage, double* ms, long long* calls);
 

@@ -2329,8 +2329,10 @@ int large_icp_iterations(cudaStream_t st, long long* launches, LargeIcp* run, co
         // it only decides whether the staged kernel is worth a launch; the one-warp-per-query kernel takes any count.)
         const int known = run->h_unres ? *(volatile int*)run->h_unres : 0x7fffffff;
         const bool staged = known > n / 8;
+        if (run->mark) run->mark(run->mark_user, KSS_STAGE_LARGE_TRACK, 1);
         launch_pdl(pdl, lg_track_kernel, (nch + 7) / 8, 256, 0, st, n, nch, cur, tg, (float4*)run->tg2, (float4*)run->cert, run->inv, gv.knn, run->flagS, run->dirty, run->partA,
                    run->partD, run->partK, tr, state, max2, (volatile int*)run->h_unres);
+        if (run->mark) run->mark(run->mark_user, KSS_STAGE_LARGE_TRACK, 0);
         launch_pdl(pdl, lg_refine_kernel, (n + RF_SEG - 1) / RF_SEG, 256, 0, st, gv, n, cur, tg, (float4*)run->tg2, (float4*)run->cert, run->perm, run->flagS, run->worklist, state, margin);
         if (staged) {
             cudaFuncSetAttribute(lg_nn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM);
