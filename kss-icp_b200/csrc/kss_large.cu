@@ -11,10 +11,15 @@
 //           completing on an mbarrier), then every thread searches 2x2x2 fine cells around its query (4x4x4 if the
 //           first stage cannot prove exactness) from shared memory.  A search is accepted only when the best distance
 //           is below the distance to the unsearched region, so the result is the exact minimum over ALL targets
-//           (ties: lowest ORIGINAL index); anything else falls back to the box pyramid.
-//   reduce: CANON256 sums by ORIGINAL source index over 32-byte per-point records the NN kernel scatters
-//           (one warp per 256-element chunk, last CTA finishes the upper levels), umeyama/SVD on one thread,
-//           device-side convergence
+//           (ties: lowest ORIGINAL index); anything else falls back to the box pyramid (seeded with the distance to
+//           the previous match when there is one).
+//   icp   : per source point, by ORIGINAL index, {position, certificate} and {match}: the certificate is a lower bound
+//           of the distance to every target other than the match.  lg_track_kernel streams the state once per
+//           iteration (transform, certificate test, re-certification from the 7-neighbour list of the match, pass A of
+//           the canonical sums for chunks without open points); lg_refine_kernel / lg_nn_kernel<1> / lg_left_kernel
+//           search what stays open; see the comment above LG_CERT_UP.
+//   reduce: CANON256 sums by ORIGINAL source index (one warp per 256-element chunk, SoA partials, the upper levels by
+//           whichever warp completes a group of 256 chunks), umeyama/SVD on one thread, device-side convergence
 #include <algorithm>
 #include <climits>
 #include <cmath>
