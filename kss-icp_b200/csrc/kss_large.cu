@@ -662,6 +662,9 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s /* M
             else { qx[k] = p.x; qy[k] = p.y; qz[k] = p.z; }                   // (MODE 1: lg_track_kernel applied T_k already)
             qc[k] = lg_qcell(g, qx[k], qy[k], qz[k]);
             if (pv >= 0) { ub[k].d = d2_rn(qx[k], qy[k], qz[k], tprev.x, tprev.y, tprev.z); ub[k].idx = (unsigned)pv; }
+            // a bound beyond the reach of the cell-by-cell stages: nothing here can prove the answer, the query goes
+            // straight to the seeded pyramid (and does not stretch the region this CTA stages)
+            if (MODE == 1 && pv >= 0 && sqrtf(ub[k].d) * g.inv_h > cube3) qc[k].inside = false;
             // the cells a search has to read.  With a bound: the cells meeting the cube q +- sqrt(bound) -- every target that
             // can beat or tie the bound lies inside (0.003 cells of slack for the rounding of the binning), so scanning them
             // is exact without any further proof.  Without (or when the cube leaves the 4x4x4 cells around the nearest corner,
@@ -883,7 +886,10 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s /* M
             if (ok) key[k] = ((unsigned long long)__float_as_uint(b.d) << 32) | b.idx;
             else {
                 left_at[k] = atomicAdd(&s_nleft, 1);
-                s_lq[left_at[k]] = make_float4(qx[k], qy[k], qz[k], __int_as_float(staged4 ? 1 : 0));
+                // (an unbounded query with nothing at all in its 2x2x2 cells is far from the target: the 4x4x4 stage would
+                //  most likely come back empty-handed too -- to the pyramid)
+                const bool try4 = staged4 && (b.d < __int_as_float(0x7f800000) || ub[k].d < __int_as_float(0x7f800000));
+                s_lq[left_at[k]] = make_float4(qx[k], qy[k], qz[k], __int_as_float(try4 ? 1 : 0));
                 s_lub[left_at[k]] = ub[k].d;
             }
         }
@@ -1255,6 +1261,7 @@ lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur, float4* __res
     __syncthreads();
     const int nl = s_n;
     const float m = margin_cells * g.h;
+    const bool walk = gv.knn != nullptr;
     GlobAcc gacc{gv.blk_rank, gv.fine_start, gv.tp, gv.lut};
     if (nl <= 8) {
         // a handful (the steady state: points beyond the target's rim, whose second-nearest target is as far as the
@@ -1293,10 +1300,31 @@ lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur, float4* __res
         if (valid) {
             pos = s_list[e];
             const int i = perm[pos];
-            const float4 q = cur[i], t0 = tg[i];
+            const float4 q = cur[i];
+            float4 t0 = tg[i];
             unres = true;
             if (__float_as_int(t0.w) >= 0) {
-                const float sd = sqrtf(d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z));
+                float sd = sqrtf(d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z));
+                // a match that T_k left far behind (beyond the radius its neighbour list covers) bounds the search badly:
+                // walk downhill over the neighbour lists first -- ANY target is a valid bound, and a better one makes
+                // the cube (or, for the general kernels, the seeded pyramid descent) small
+                if (walk) {
+                    float d0 = sd * sd;
+                    for (int step = 0; step < 64; ++step) {
+                        const float4* L = gv.knn + (size_t)__float_as_int(t0.w) * LG_KSLOTS;
+                        if (!(sd > __ldg(L).x)) break;
+                        float4 nb = t0; float dn = d0;
+#pragma unroll
+                        for (int k = 1; k < LG_KSLOTS; ++k) {
+                            const float4 c = __ldg(L + k);
+                            const float d = d2_rn(q.x, q.y, q.z, c.x, c.y, c.z);
+                            if (d < dn) { dn = d; nb = c; }
+                        }
+                        if (!(dn < d0)) break;
+                        t0 = nb; d0 = dn; sd = sqrtf(dn);
+                    }
+                    if (__float_as_int(t0.w) != __float_as_int(tg[i].w)) tg[i] = t0;     // (the general kernels seed from it)
+                }
                 float nx, ny, nz;
                 xform_point(T, q.x, q.y, q.z, nx, ny, nz);                // how far T_k would move the point once more
                 const float mv = sqrtf((nx - q.x) * (nx - q.x) + (ny - q.y) * (ny - q.y) + (nz - q.z) * (nz - q.z));

@@ -8,8 +8,8 @@
 //   icp_small_kernel       one whole PCL-1.8.1 ICP run per CTA      (KSS_ICP.hpp:323-356 + SURVEY.md A.2-A.7)
 //   select_kernel          hypothesis choice                        (KSS_ICP.hpp:99-125)
 //   final_apply_kernel     similarity + final 4x4 on the full cloud (KSS_ICP.hpp:119-124, 222-230)
-//   metrics_small_kernel   PCR_QM                                   (registrationMeasure.hpp:47-98)
-//   nn_small_kernel        bare exact 1-NN (tests, kss_nn_search)
+//   nn_small_kernel        bare exact 1-NN (kss_nn_search) and, with serial sums per cloud, PCR_QM (registrationMeasure.hpp:47-98)
+//   cg_* kernels           the per-pair candidate grid (kss_cg.cuh) the sweep and the ICP runs query
 #include "kss_device.cuh"
 #include "kss_cg.cuh"
 #include "kss_kernels.h"
