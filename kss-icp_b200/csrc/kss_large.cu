@@ -1529,20 +1529,22 @@ __device__ __forceinline__ void lg_load_chunk(const float4* __restrict__ cur, co
         if (i0 + 32 * u < n) lg_pair(cv[u], gv[u], max2, sv[u], tv[u]);
     }
 }
-// pass A of one 256-element chunk (one warp): sums of kept source xyz, matched target xyz (float), d2 (double), kept count
-__device__ __forceinline__ void lg_chunk_A(const float4 (&sv)[8], const float4 (&tv)[8], int c, int S, float* __restrict__ partA,
-                                           double* __restrict__ partD, int* __restrict__ partK) {
-    float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    double dsum = 0.0;
-    int k = 0;
+// pass A of one 256-element chunk (one warp): sums of kept source xyz, matched target xyz (float), d2 (double), kept count.
+// A lane adds ITS points in increasing index (the canonical order): lg_accum_A can be called for the first four and then the
+// last four; lg_store_A is the butterfly + the partials.
+template <int N>
+__device__ __forceinline__ void lg_accum_A(const float4 (&sv)[N], const float4 (&tv)[N], float (&a)[6], double& dsum, int& k) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < N; ++u) {
         if (__float_as_int(tv[u].w) < 0) continue;
         a[0] = __fadd_rn(a[0], sv[u].x); a[1] = __fadd_rn(a[1], sv[u].y); a[2] = __fadd_rn(a[2], sv[u].z);
         a[3] = __fadd_rn(a[3], tv[u].x); a[4] = __fadd_rn(a[4], tv[u].y); a[5] = __fadd_rn(a[5], tv[u].z);
         dsum = __dadd_rn(dsum, (double)sv[u].w);
         ++k;
     }
+}
+__device__ __forceinline__ void lg_store_A(float (&a)[6], double dsum, int k, int c, int S, float* __restrict__ partA,
+                                           double* __restrict__ partD, int* __restrict__ partK) {
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
 #pragma unroll
@@ -1555,6 +1557,14 @@ __device__ __forceinline__ void lg_chunk_A(const float4 (&sv)[8], const float4 (
         for (int q = 0; q < 6; ++q) partA[(size_t)q * S + c] = a[q];
         partD[c] = dsum; partK[c] = k;
     }
+}
+__device__ __forceinline__ void lg_chunk_A(const float4 (&sv)[8], const float4 (&tv)[8], int c, int S, float* __restrict__ partA,
+                                           double* __restrict__ partD, int* __restrict__ partK) {
+    float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    double dsum = 0.0;
+    int k = 0;
+    lg_accum_A<8>(sv, tv, a, dsum, k);
+    lg_store_A(a, dsum, k, c, S, partA, partD, partK);
 }
 // ---- upper levels of the canonical sums, spread over the grid: partials are SoA [quantity][S] (S = padded chunk
 // count).  The CTA that completes a group of 256 chunks (per-group counters) reduces the group with ONE warp (level 2,
@@ -1733,6 +1743,33 @@ __device__ __forceinline__ void lg_chunk_B(const float4 (&sv)[8], const float4 (
     if ((threadIdx.x & 31) == 0)
 #pragma unroll
         for (int q = 0; q < 9; ++q) partB[(size_t)q * S + c] = a[q];
+}
+// the same in two halves of four points per lane (fewer live registers: every CTA of the pass is resident at once); the
+// first half may be loaded before the means are known
+__device__ __forceinline__ void lg_load_half(const float4* __restrict__ cur, const float4* __restrict__ tg, int n, int c, int half,
+                                             float4 (&cv)[4], float4 (&gv)[4]) {
+    const int i0 = (c << 8) + (threadIdx.x & 31) + 128 * half;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = i0 + 32 * u;
+        gv[u].w = __int_as_float(-1);
+        if (i < n) { cv[u] = cur[i]; gv[u] = tg[i]; }
+    }
+}
+__device__ __forceinline__ void lg_accum_B(const float4 (&cv)[4], const float4 (&gv)[4], double max2, float sm0, float sm1, float sm2,
+                                           float dm0, float dm1, float dm2, float (&a)[9]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int ti = __float_as_int(gv[u].w);
+        if (ti < 0) continue;                                       // (beyond n, or no match)
+        const float4 s = cv[u], t = gv[u];
+        if ((double)d2_rn(s.x, s.y, s.z, t.x, t.y, t.z) > max2) continue;       // rejected (A.3), as lg_pair decides
+        const float sx = sub_(s.x, sm0), sy = sub_(s.y, sm1), sz = sub_(s.z, sm2);
+        const float dx = sub_(t.x, dm0), dy = sub_(t.y, dm1), dz = sub_(t.z, dm2);
+        a[0] = add_(a[0], mul_(dx, sx)); a[1] = add_(a[1], mul_(dx, sy)); a[2] = add_(a[2], mul_(dx, sz));
+        a[3] = add_(a[3], mul_(dy, sx)); a[4] = add_(a[4], mul_(dy, sy)); a[5] = add_(a[5], mul_(dy, sz));
+        a[6] = add_(a[6], mul_(dz, sx)); a[7] = add_(a[7], mul_(dz, sy)); a[8] = add_(a[8], mul_(dz, sz));
+    }
 }
 // one warp: level 3 of pass B, then umeyama + accumulate + convergence on one thread
 __device__ __forceinline__ void lg_finish_B(int nchunks, const LgTree& tr, LgState* __restrict__ st, bool enough,
@@ -1956,7 +1993,7 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
 }
 
 // pass A of the dirty chunks (their searches are done by now), then the upper levels and the means
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 lg_passA_kernel(const float4* __restrict__ cur, const float4* __restrict__ tg, const unsigned char* __restrict__ dirty, double max2,
                 int n, int nchunks, float* __restrict__ partA /* [6][S] */, double* __restrict__ partD, int* __restrict__ partK,
                 LgTree tr, LgState* __restrict__ st,
@@ -1968,9 +2005,20 @@ lg_passA_kernel(const float4* __restrict__ cur, const float4* __restrict__ tg, c
     __syncthreads();
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (c < nchunks && dirty[c]) {               // (the clean chunks arrived in lg_track_kernel)
-        float4 sv[8], tv[8];
-        lg_load_chunk(cur, tg, max2, n, c, sv, tv);
-        lg_chunk_A(sv, tv, c, tr.S, partA, partD, partK);
+        float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        double dsum = 0.0; int k = 0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {   // two halves of four points per lane: every CTA of the pass is resident at once
+            float4 cv[4], gv[4], sv[4], tv[4];
+            lg_load_half(cur, tg, n, c, half, cv, gv);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                tv[u].w = __int_as_float(-1);
+                if (__float_as_int(gv[u].w) >= 0) lg_pair(cv[u], gv[u], max2, sv[u], tv[u]);
+            }
+            lg_accum_A<4>(sv, tv, a, dsum, k);
+        }
+        lg_store_A(a, dsum, k, c, tr.S, partA, partD, partK);
         if ((threadIdx.x & 31) == 0) atomicAdd(&s_mine, 1u);
     }
     __syncthreads();
@@ -1980,14 +2028,14 @@ lg_passA_kernel(const float4* __restrict__ cur, const float4* __restrict__ tg, c
     if (!lg_groups_done(tr.grpcnt, &st->ticketA, (nchunks + 255) >> 8)) return;
     lg_finish_A(nchunks, tr, st, h_unres);
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 lg_passB_kernel(const float4* __restrict__ cur, const float4* __restrict__ tg, double max2, int n, int nchunks,
                 float* __restrict__ partB /* [9][S] */, LgTree tr,
                 LgState* __restrict__ st, int max_iter, double rot_thr, double trans_thr, double mse_rel, double mse_abs) {
     LG_TL_MIN(0);
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-    float4 sv[8], tv[8];
-    if (c < nchunks) lg_load_chunk(cur, tg, max2, n, c, sv, tv);      // (pass A does not write them: before the wait)
+    float4 cv[4], gv[4];
+    if (c < nchunks) lg_load_half(cur, tg, n, c, 0, cv, gv);          // (pass A does not write them: before the wait)
     lg_wait_prior();
     if (st->done) return;
     const bool enough = st->kept >= 3;
@@ -1996,10 +2044,21 @@ lg_passB_kernel(const float4* __restrict__ cur, const float4* __restrict__ tg, d
     unsigned long long tl1 = tl0, tl2 = tl0;
 #endif
     if (c < nchunks && enough) {
+        const float sm0 = st->smean[0], sm1 = st->smean[1], sm2 = st->smean[2], dm0 = st->dmean[0], dm1 = st->dmean[1], dm2 = st->dmean[2];
+        float a[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        lg_accum_B(cv, gv, max2, sm0, sm1, sm2, dm0, dm1, dm2, a);
+        lg_load_half(cur, tg, n, c, 1, cv, gv);
+        lg_accum_B(cv, gv, max2, sm0, sm1, sm2, dm0, dm1, dm2, a);
 #ifdef KSS_LG_TIMELINE
-        if (__float_as_int(tv[0].w) != 0x12345678) tl1 = lg_now();
+        tl1 = lg_now();
 #endif
-        lg_chunk_B(sv, tv, c, tr.S, st->smean[0], st->smean[1], st->smean[2], st->dmean[0], st->dmean[1], st->dmean[2], partB);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+            for (int q = 0; q < 9; ++q) a[q] = __fadd_rn(a[q], __shfl_xor_sync(KSS_FULL, a[q], off));
+        if ((threadIdx.x & 31) == 0)
+#pragma unroll
+            for (int q = 0; q < 9; ++q) partB[(size_t)q * tr.S + c] = a[q];
 #ifdef KSS_LG_TIMELINE
         tl2 = lg_now();
 #endif
