@@ -163,3 +163,31 @@ def test_large_icp_duplicate_targets_and_rim(ctx, okss, pkg):
     assert g["iters"] == o["iters"]
     assert np.array_equal(g["T"], o["T"])
     assert g["fitness"] == o["fitness"]
+
+
+@pytest.mark.parametrize("case", ["tiny_target", "identical", "line_target", "far_apart", "few_source_many_target", "two_sheets"])
+def test_large_icp_degenerate_cases(ctx, okss, case):
+    """the certificate machinery on inputs it was not tuned for: targets with fewer points than a neighbour list holds,
+    coincident clouds (every distance 0), collinear targets, clouds that never meet (every match rejected by the
+    max-distance test from some iteration on), a handful of source points, two sheets closer than the cell size"""
+    rng = np.random.default_rng(abs(hash(case)) % 997)
+    f = lambda a: a.astype(np.float32).astype(np.float64)
+    kw = dict(max_iter=30, trans_eps=-1.0, fit_eps=0.0)
+    if case == "tiny_target":
+        t = f(rng.normal(size=(5, 3))); s = f(rng.normal(size=(3000, 3)) * 0.5)
+    elif case == "identical":
+        t = f(rng.uniform(-1, 1, (4000, 3))); s = t.copy()
+    elif case == "line_target":
+        t = np.zeros((3000, 3)); t[:, 0] = rng.uniform(-2, 2, 3000); t = f(t); s = f(rng.normal(size=(2500, 3)) * 0.2); s[:, 0] *= 8
+    elif case == "far_apart":
+        t = f(rng.uniform(0, 1, (3000, 3))); s = f(rng.uniform(0, 1, (3000, 3)) + 5.0); kw["max_corr_dist"] = 4.0
+    elif case == "few_source_many_target":
+        t = f(rng.uniform(-1, 1, (20000, 3))); s = f(rng.uniform(-0.8, 0.8, (7, 3)))
+    else:
+        a = rng.uniform(-1, 1, (3000, 3)); a[:, 2] = 0.0
+        t = f(np.concatenate([a, a + np.array([0.0, 0.0, 1e-4])])); s = f(a[:2500] + rng.normal(size=(2500, 3)) * 0.003 + np.array([0.01, 0.0, 0.0]))
+    o = okss.icp(s, t, sum_order=okss.SUM_CANON256, method=okss.NN_KDTREE, **kw)
+    g = ctx.icp(s, t, **kw)
+    assert g["iters"] == o["iters"] and g["converged"] == o["converged"]
+    assert np.array_equal(g["T"], o["T"], equal_nan=True)
+    assert g["fitness"] == o["fitness"] or (np.isnan(g["fitness"]) and np.isnan(o["fitness"]))
