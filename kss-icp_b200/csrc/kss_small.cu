@@ -1556,6 +1556,12 @@ nn_small_kernel(const double* __restrict__ q, const int* __restrict__ cnt_q, int
     if (MODE == 1) {
         __syncthreads();
         __shared__ double sums[2];
+        // the square roots by everybody (into the target tile, which is no longer needed), so that the two serial chains
+        // of the reference's loop (registrationMeasure.hpp:83-88) are additions only
+        double* sq = reinterpret_cast<double*>(tgt);
+        const bool par = (size_t)n_q * sizeof(double) <= (size_t)npad * sizeof(float4);
+        if (par) for (int i = threadIdx.x; i < n_q; i += blockDim.x) sq[i] = __dsqrt_rn((double)d2s[i]);
+        __syncthreads();
         if (threadIdx.x == 0) {
             double s = 0.0;
 #pragma unroll 8
@@ -1564,8 +1570,13 @@ nn_small_kernel(const double* __restrict__ q, const int* __restrict__ cnt_q, int
         }
         if (threadIdx.x == 32) {
             double s = 0.0;
+            if (par) {
+#pragma unroll 8
+                for (int i = 0; i < n_q; ++i) s = __dadd_rn(s, sq[i]);
+            } else {
 #pragma unroll 4
-            for (int i = 0; i < n_q; ++i) s = __dadd_rn(s, __dsqrt_rn((double)d2s[i]));
+                for (int i = 0; i < n_q; ++i) s = __dadd_rn(s, __dsqrt_rn((double)d2s[i]));
+            }
             sums[1] = s;
         }
         __syncthreads();
