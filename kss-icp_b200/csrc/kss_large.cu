@@ -42,6 +42,10 @@ constexpr int SCAN_UNROLL = KSS_SCAN_UNROLL;
 #define KSS_LG_CUBE3 3.0f
 #endif
 constexpr float cube3 = KSS_LG_CUBE3;  // a warp scans the cube q +- bound cell by cell up to this many cells of reach; beyond, the (seeded) box pyramid
+#ifndef KSS_LG_STAGED_DIV
+#define KSS_LG_STAGED_DIV 32u
+#endif
+constexpr unsigned LG_STAGED_DIV = KSS_LG_STAGED_DIV;   // more than n / this many points left open by the refine kernel: the staged kernel (512 per CTA) instead of one warp each
 constexpr int LG_MAX_LEVELS = 4;     // 32^4 tiles * 32 points = 33.5 M points
 constexpr int LG_SAMPLES = 256;      // nearest-neighbour probe of the build
 
@@ -629,7 +633,7 @@ lg_nn_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur_s /* M
 
     if (MODE == 1) lg_wait_prior();
     if (MODE == 1 && st->done) return;
-    if (MODE == 1 && st->n_unres <= (unsigned)n_q / 8u) return;       // few left: lg_left_kernel takes them one warp each
+    if (MODE == 1 && st->n_unres <= (unsigned)n_q / LG_STAGED_DIV) return;       // few left: lg_left_kernel takes them one warp each
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < (int)(sizeof(LgGeom) / 4)) reinterpret_cast<int*>(&g)[tid] = reinterpret_cast<const int*>(gv.geom)[tid];
     if (MODE != 0 && tid < 16) T[tid] = MODE == 1 ? st->Tk[tid] : st->fin[tid];
@@ -1363,7 +1367,7 @@ lg_left_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur, flo
     lg_wait_prior();
     if (st->done) return;
     const unsigned nu = st->n_unres;
-    if (nu == 0u || (staged_launched && nu > (unsigned)n_q / 8u)) return;          // many: lg_nn_kernel<1> staged them
+    if (nu == 0u || (staged_launched && nu > (unsigned)n_q / LG_STAGED_DIV)) return;          // many: lg_nn_kernel<1> staged them
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < (int)(sizeof(LgGeom) / 4)) reinterpret_cast<int*>(&g)[tid] = reinterpret_cast<const int*>(gv.geom)[tid];
     __syncthreads();
@@ -2420,7 +2424,7 @@ int large_icp_iterations(cudaStream_t st, long long* launches, LargeIcp* run, co
         // query when few).  (The host knows the left-over count of an EARLIER iteration from a pinned word passA writes:
         // it only decides whether the staged kernel is worth a launch; the one-warp-per-query kernel takes any count.)
         const int known = run->h_unres ? *(volatile int*)run->h_unres : 0x7fffffff;
-        const bool staged = known > n / 8;
+        const bool staged = known > n / (int)LG_STAGED_DIV;
         if (run->mark) run->mark(run->mark_user, KSS_STAGE_LARGE_TRACK, 1);
         launch_pdl(pdl, lg_track_kernel, (nch + 7) / 8, 256, 0, st, n, nch, cur, tg, (float4*)run->tg2, (float4*)run->cert, run->inv, gv.knn, run->flagS, run->dirty, run->partA,
                    run->partD, run->partK, tr, state, max2, (volatile int*)run->h_unres);
