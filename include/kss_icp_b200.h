@@ -41,6 +41,11 @@ extern "C" {
 #define KSS_SCORE_AVE  0
 #define KSS_SCORE_MAX  1
 #define KSS_SCORE_DIFF 2
+/* NOT a mode of the released sources: a reading of the authors' closed CUDA build (EXE/KSS-ICP-VCG-Cuda.exe, symbols
+ * voxelCudaBlock / pt_VoxelJudge): the target becomes an NV^3 voxel-occupancy grid (NV = sqrt(n_t / 16), 4..32) over the cube +-1.1 max|coordinate| and
+ * a hypothesis scores the share of source points that land in an empty voxel -- no nearest-neighbour search at all.
+ * Only kss_rotation_sweep takes it; the registration entry points always use KSS_SCORE_AVE like KSSICP_Registration. */
+#define KSS_SCORE_VOXEL 3
 
 typedef struct kss_ctx kss_ctx;
 

@@ -17,7 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_DIR), "include", "kss_icp_b200.h")
 
 KSS_OK = 0
 SMALL_MAX = 2048
-SCORE_AVE, SCORE_MAX, SCORE_DIFF = 0, 1, 2
+SCORE_AVE, SCORE_MAX, SCORE_DIFF, SCORE_VOXEL = 0, 1, 2, 3
 STAGES = ("prep", "sweep", "sweep_finalize", "icp_judge", "icp_hyp", "select_apply", "metrics",
           "large_build", "large_nn", "large_reduce", "cg_build", "aivs")
 

@@ -649,7 +649,7 @@ int kss_rotation_sweep(kss_ctx* ctx, const double* src_aligned, int n_s, const d
     if (!ctx) return KSS_ERR_ARG;
     if (!src_aligned || !tgt || n_s < 1 || n_t < 1) return fail(ctx, KSS_ERR_ARG, "kss_rotation_sweep: bad argument");
     if (n_s > SMALL_MAX || n_t > SMALL_MAX) return fail(ctx, KSS_ERR_UNSUPPORTED, "kss_rotation_sweep: > 2048 points");
-    if (score_mode < 0 || score_mode > 2) return fail(ctx, KSS_ERR_ARG, "kss_rotation_sweep: score_mode");
+    if (score_mode < 0 || score_mode > KSS_SCORE_VOXEL) return fail(ctx, KSS_ERR_ARG, "kss_rotation_sweep: score_mode");
     CU(cudaSetDevice(ctx->device));
     int r = ensure_trig(ctx, step); if (r) return r;
     const int G = ctx->G, H = G * G * G;

@@ -810,6 +810,47 @@ sweep_kernel(const double* __restrict__ s_al, const int* __restrict__ cnt_s, int
     const int hbase = (gi * G + gj) * G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
+    if (score_mode == KSS_SCORE_VOXEL) {
+        // voxel-occupancy score (see KSS_SCORE_VOXEL in the header): 1 for a source point in an empty voxel, else 0
+        constexpr int NVMAX = 32;
+        const int NV = min(NVMAX, max(4, (int)floor(sqrt((double)n_t / 16.0))));        // ~16 target points per occupied face voxel
+        __shared__ unsigned s_occ[NVMAX * NVMAX * NVMAX / 32];
+        __shared__ unsigned s_max;
+        for (int j = threadIdx.x; j < NVMAX * NVMAX * NVMAX / 32; j += blockDim.x) s_occ[j] = 0u;
+        if (threadIdx.x == 0) s_max = 0u;
+        __syncthreads();
+        float m = 0.0f;
+        for (int j = threadIdx.x; j < n_t; j += blockDim.x) m = fmaxf(m, fmaxf(fabsf(tgt[j].x), fmaxf(fabsf(tgt[j].y), fabsf(tgt[j].z))));
+        atomicMax(&s_max, __float_as_uint(m));                     // (non-negative floats order as their bits)
+        __syncthreads();
+        const float E = __fmul_rn(1.1f, __uint_as_float(s_max));
+        const float inv = __fdiv_rn((float)NV, __fmul_rn(2.0f, E));
+        auto vox = [&](float v) { return (int)floorf(__fmul_rn(__fadd_rn(v, E), inv)); };
+        if (E > 0.0f)
+            for (int j = threadIdx.x; j < n_t; j += blockDim.x) {
+                const int b = (vox(tgt[j].z) * NV + vox(tgt[j].y)) * NV + vox(tgt[j].x);
+                atomicOr(&s_occ[b >> 5], 1u << (b & 31));
+            }
+        __syncthreads();
+        for (int o = threadIdx.x; o < n_s; o += blockDim.x) {
+            double x = sa[3 * o], y = sa[3 * o + 1], z = sa[3 * o + 2];
+            rot_x(ci, si, y, z);
+            rot_y(cj, sj, x, z);
+            for (int k = 0; k < G; ++k) {
+                double xx = x, yy = y;
+                rot_z(trig_accum[2 * k], trig_accum[2 * k + 1], xx, yy);
+                const int ix = vox((float)xx), iy = vox((float)yy), iz = vox((float)z);
+                bool hit = false;
+                if (E > 0.0f && ix >= 0 && ix < NV && iy >= 0 && iy < NV && iz >= 0 && iz < NV) {
+                    const int b = (iz * NV + iy) * NV + ix;
+                    hit = (s_occ[b >> 5] >> (b & 31)) & 1u;
+                }
+                rb[(size_t)o * hpad + hbase + k] = hit ? 0.0f : 1.0f;
+            }
+        }
+        return;
+    }
+
     for (int base = warp * 32; base < n_s; base += nwarps * 32) {
         const int jpos = base + lane;
         const bool valid = jpos < n_s;

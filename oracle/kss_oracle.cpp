@@ -722,6 +722,40 @@ int okss_sweep_angles(double step, double* accum, double* list, int cap) {
     return g;
 }
 
+/* KSS_SCORE_VOXEL (a reading of the authors' closed CUDA build, not of the released sources): the target as an NV^3
+ * occupancy grid over the cube +-1.1 max|coordinate|; a hypothesis scores the share of source points in empty voxels */
+struct VoxelGrid {
+    int NV;                                     /* voxels per axis: ~16 target points per occupied face voxel, 4..32 */
+    std::vector<unsigned char> occ;
+    float E, inv;
+    VoxelGrid(const float* t, int n_t) {
+        NV = (int)std::floor(std::sqrt((double)n_t / 16.0));
+        NV = std::min(32, std::max(4, NV));
+        occ.assign((size_t)NV * NV * NV, 0);
+        float m = 0.0f;
+        for (int i = 0; i < 3 * n_t; ++i) m = std::max(m, std::fabs(t[i]));
+        E = 1.1f * m;
+        inv = (float)NV / (2.0f * E);
+        if (E > 0.0f)
+            for (int i = 0; i < n_t; ++i) occ[((size_t)vox(t[3 * i + 2]) * NV + vox(t[3 * i + 1])) * NV + vox(t[3 * i])] = 1;
+    }
+    int vox(float v) const { float f = v + E; f = f * inv; return (int)std::floor(f); }
+    bool hit(const float q[3]) const {
+        if (!(E > 0.0f)) return false;
+        const int ix = vox(q[0]), iy = vox(q[1]), iz = vox(q[2]);
+        if (ix < 0 || ix >= NV || iy < 0 || iy >= NV || iz < 0 || iz >= NV) return false;
+        return occ[((size_t)iz * NV + iy) * NV + ix] != 0;
+    }
+};
+static double score_voxel(const std::vector<double>& pts, int n_s, const VoxelGrid& vg) {
+    double sum = 0;
+    for (int i = 0; i < n_s; ++i) {
+        float q[3] = {(float)pts[3 * i], (float)pts[3 * i + 1], (float)pts[3 * i + 2]};
+        sum = sum + (vg.hit(q) ? 0.0 : 1.0);
+    }
+    return sum / n_s;
+}
+
 static double score_cloud(const std::vector<double>& pts, int n_s, const NNIndex& nn, int score_mode,
                           float* queries, int32_t* idx, float* d2out) {
     /* initRegistrationKSS.hpp:406-479 : K=2 search, neighbour [0] only */
@@ -771,6 +805,7 @@ int okss_sweep(const double* src_aligned, int n_s, const double* tgt, int n_t,
     std::vector<float> tf(3 * (size_t)n_t);
     for (int i = 0; i < 3 * n_t; ++i) tf[i] = (float)tgt[i];          /* :231-235 narrowing */
     NNIndex nn(tf.data(), n_t, nn_method);
+    VoxelGrid vg(tf.data(), score_mode == OKSS_SCORE_VOXEL ? n_t : 0);
     std::vector<double> ang(1024);
     int G = okss_sweep_angles(step, ang.data(), nullptr, 1024);
     double errorT = 9999;
@@ -789,7 +824,8 @@ int okss_sweep(const double* src_aligned, int n_s, const double* tgt, int n_t,
                 double ck = std::cos(ang[kk]), sk = std::sin(ang[kk]);
                 pxyz = pxy;
                 for (int k = 0; k < n_s; ++k) rotate_axis(3, ck, sk, &pxyz[3 * k]);
-                double e = score_cloud(pxyz, n_s, nn, score_mode, nullptr, nullptr, nullptr);
+                double e = score_mode == OKSS_SCORE_VOXEL ? score_voxel(pxyz, n_s, vg)
+                                                          : score_cloud(pxyz, n_s, nn, score_mode, nullptr, nullptr, nullptr);
                 value[((size_t)i * G + j) * G + kk] = e;
                 if (e < errorT) {                                       /* :258 first strict min */
                     errorT = e;

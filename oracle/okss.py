@@ -15,7 +15,7 @@ _SO = os.path.join(_DIR, "libkss_oracle.so")
 
 NN_BRUTE, NN_KDTREE = 0, 1
 SUM_SERIAL, SUM_CANON256 = 0, 1
-SCORE_AVE, SCORE_MAX, SCORE_DIFF = 0, 1, 2
+SCORE_AVE, SCORE_MAX, SCORE_DIFF, SCORE_VOXEL = 0, 1, 2, 3
 
 
 def build(force=False):

@@ -71,6 +71,23 @@ def test_sweep_bit_exact(ctx, okss, pkg, mode):
     assert np.array_equal(g["minima"], o["minima"])
 
 
+def test_sweep_voxel_score_mode(ctx, okss, pkg):
+    """KSS_SCORE_VOXEL (optional, NOT a mode of the released sources: a reading of the authors' closed CUDA build): the
+    occupancy-grid score of every hypothesis, its arg-min and its local minima equal the oracle's bit for bit"""
+    for seed, n in ((3, 600), (9, 2000)):
+        p = pkg.synth.modelnet_pair(seed, n_full=n)
+        _, al = okss.middle_align(p["sim_s"], p["sim_t"])
+        o = okss.sweep(al, p["sim_t"], 8.0, okss.SCORE_VOXEL, okss.NN_KDTREE)
+        g = ctx.rotation_sweep(al, p["sim_t"], 8.0, pkg.SCORE_VOXEL)
+        assert np.array_equal(g["value"], o["value"])
+        assert np.array_equal(g["best_index"], o["best_index"]) and np.array_equal(g["minima"], o["minima"])
+        assert 0.0 <= g["value"].min() and g["value"].max() <= 1.0
+    t = np.zeros((300, 3)); s_ = np.random.default_rng(1).normal(size=(300, 3))       # zero-extent target: every point misses
+    g = ctx.rotation_sweep(s_, t, 8.0, pkg.SCORE_VOXEL)
+    o = okss.sweep(s_, t, 8.0, okss.SCORE_VOXEL, okss.NN_KDTREE)
+    assert np.array_equal(g["value"], o["value"]) and np.all(g["value"] == 1.0)
+
+
 def test_sweep_other_steps(ctx, okss, pkg):
     p = pkg.synth.modelnet_pair(4, n_full=256)
     _, al = okss.middle_align(p["sim_s"], p["sim_t"])
