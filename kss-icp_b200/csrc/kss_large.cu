@@ -1401,57 +1401,8 @@ lg_left_kernel(Pyramid py, LgGridView gv, int n_q, float4* __restrict__ cur, flo
 
 // ------------------------------------------------------------------ canonical reductions, large n
 // level 1: one warp per 256-element chunk of ORIGINAL indices (lane-strided partials + butterfly)
-// upper levels: the last CTA to finish reduces the chunk partials by the same rule (<= 2 more levels)
-template <int NQ>
-__device__ __forceinline__ void lg_finish_f32(const float* __restrict__ part, int nchunks, float* out /* [NQ] smem */) {
-    // called by one full CTA (256 threads = 8 warps); part is [nchunks][NQ].  Level 2: one warp per 256 partials,
-    // all NQ quantities at once, the lane's 8 rows loaded up front (the accumulation order is unchanged).
-    __shared__ float lvl2[256 * 16];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int n2 = (nchunks + 255) >> 8;             // level-2 chunks (<= 256 supported -> n <= 16.7 M)
-    for (int c = warp; c < n2; c += nwarps) {
-        float v[8][NQ];
-        bool have[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = (c << 8) + lane + 32 * u;
-            have[u] = i < nchunks;
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) v[u][q] = have[u] ? __ldcg(part + (size_t)i * NQ + q) : 0.0f;      // (L2: written by other CTAs)
-        }
-        float p[NQ];
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) p[q] = 0.0f;
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (have[u])
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) p[q] = __fadd_rn(p[q], v[u][q]);
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1)
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) p[q] = __fadd_rn(p[q], __shfl_xor_sync(KSS_FULL, p[q], off));
-        if (lane == 0)
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) lvl2[c * 16 + q] = p[q];
-    }
-    __syncthreads();
-    if (warp == 0) {
-        for (int q = 0; q < NQ; ++q) {
-            float r;
-            if (n2 == 1) r = lvl2[q];
-            else {
-                float p = 0.0f;
-                for (int i = lane; i < n2; i += 32) p = __fadd_rn(p, lvl2[i * 16 + q]);
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) p = __fadd_rn(p, __shfl_xor_sync(KSS_FULL, p, off));
-                r = p;
-            }
-            if (lane == 0) out[q] = r;
-        }
-    }
-    __syncthreads();
-}
+// upper levels (<= 2 more, same rule): for the one-off double sums (fitness, PCR_QM: lg_passF_kernel) the last CTA to
+// finish reduces the chunk partials (lg_finish_f64); the ICP passes use the tree further down (LgTree)
 __device__ __forceinline__ double lg_finish_f64(const double* __restrict__ part, int nchunks) {
     __shared__ double lvl2d[256];
     __shared__ double res;
@@ -1517,21 +1468,6 @@ __device__ __forceinline__ void lg_pair(const float4& c, const float4& t, double
     const int ti = __float_as_int(t.w);
     sv = make_float4(c.x, c.y, c.z, d2);
     tv = make_float4(t.x, t.y, t.z, __int_as_float((ti < 0 || (double)d2 > max2) ? -1 : ti));
-}
-__device__ __forceinline__ void lg_load_chunk(const float4* __restrict__ cur, const float4* __restrict__ tg, double max2, int n, int c,
-                                              float4 (&sv)[8], float4 (&tv)[8]) {
-    const int i0 = (c << 8) + (threadIdx.x & 31);
-    float4 cv[8], gv[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int i = i0 + 32 * u;
-        if (i < n) { cv[u] = cur[i]; gv[u] = tg[i]; }
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        tv[u].w = __int_as_float(-1);
-        if (i0 + 32 * u < n) lg_pair(cv[u], gv[u], max2, sv[u], tv[u]);
-    }
 }
 // pass A of one 256-element chunk (one warp): sums of kept source xyz, matched target xyz (float), d2 (double), kept count.
 // A lane adds ITS points in increasing index (the canonical order): lg_accum_A can be called for the first four and then the
@@ -1726,30 +1662,8 @@ __device__ __forceinline__ void lg_finish_A(int nchunks, const LgTree& tr, LgSta
         }
     }
 }
-// pass B of one chunk: sigma(a, b) partials = sum (d_a - dmean_a) * (s_b - smean_b)
-__device__ __forceinline__ void lg_chunk_B(const float4 (&sv)[8], const float4 (&tv)[8], int c, int S, float sm0, float sm1, float sm2,
-                                           float dm0, float dm1, float dm2, float* __restrict__ partB) {
-    float a[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        if (__float_as_int(tv[u].w) < 0) continue;
-        const float4 s = sv[u], t = tv[u];
-        const float sx = sub_(s.x, sm0), sy = sub_(s.y, sm1), sz = sub_(s.z, sm2);
-        const float dx = sub_(t.x, dm0), dy = sub_(t.y, dm1), dz = sub_(t.z, dm2);
-        a[0] = add_(a[0], mul_(dx, sx)); a[1] = add_(a[1], mul_(dx, sy)); a[2] = add_(a[2], mul_(dx, sz));
-        a[3] = add_(a[3], mul_(dy, sx)); a[4] = add_(a[4], mul_(dy, sy)); a[5] = add_(a[5], mul_(dy, sz));
-        a[6] = add_(a[6], mul_(dz, sx)); a[7] = add_(a[7], mul_(dz, sy)); a[8] = add_(a[8], mul_(dz, sz));
-    }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1)
-#pragma unroll
-        for (int q = 0; q < 9; ++q) a[q] = __fadd_rn(a[q], __shfl_xor_sync(KSS_FULL, a[q], off));
-    if ((threadIdx.x & 31) == 0)
-#pragma unroll
-        for (int q = 0; q < 9; ++q) partB[(size_t)q * S + c] = a[q];
-}
-// the same in two halves of four points per lane (fewer live registers: every CTA of the pass is resident at once); the
-// first half may be loaded before the means are known
+// pass B of one chunk: sigma(a, b) partials = sum (d_a - dmean_a) * (s_b - smean_b), in two halves of four points per lane
+// (fewer live registers: every CTA of the pass is resident at once); the first half may be loaded before the means are known
 __device__ __forceinline__ void lg_load_half(const float4* __restrict__ cur, const float4* __restrict__ tg, int n, int c, int half,
                                              float4 (&cv)[4], float4 (&gv)[4]) {
     const int i0 = (c << 8) + (threadIdx.x & 31) + 128 * half;
