@@ -192,11 +192,12 @@ aivs_fill_kernel(int cap, const AivsGrid* __restrict__ grids, int bcap, const in
     members[(size_t)p * cap + atomicAdd(&cursor[(size_t)p * bcap + b], 1)] = i;
 }
 
-// per box (one WARP): ascending original index (the reference's push_back order) by rank sort through `tmp`, the
-// centre-nearest member, the quota
+// per box (one WARP): the centre-nearest member and the quota.  The reference keeps a box's members in ascending
+// original index (push_back order) and breaks every tie by position; the member lists here are in the arbitrary order
+// of the atomic fill, and every tie is broken by the ORIGINAL INDEX instead -- the same choice, without a sort.
 __global__ void __launch_bounds__(256)
 aivs_box_kernel(const double* __restrict__ pts, int cap, const AivsGrid* __restrict__ grids, int bcap,
-                const int* __restrict__ box_start, int* __restrict__ members, int* __restrict__ tmp, int* __restrict__ center_pos,
+                const int* __restrict__ box_start, const int* __restrict__ members, int* __restrict__ center_pos,
                 int* __restrict__ quota) {
     const int p = blockIdx.y;
     const AivsGrid g = grids[p];
@@ -204,34 +205,23 @@ aivs_box_kernel(const double* __restrict__ pts, int cap, const AivsGrid* __restr
     if (b >= g.nbox) return;
     const int* st = box_start + (size_t)p * (bcap + 1);
     const int s = st[b], m = st[b + 1] - s;
-    int* mem = members + (size_t)p * cap + s;
-    int* tm = tmp + (size_t)p * cap + s;
-    if (m > 1) {                                               // all indices are distinct: rank = number of smaller ones
-        for (int i = lane; i < m; i += 32) {
-            const int v = mem[i];
-            int r = 0;
-            for (int j = 0; j < m; ++j) r += mem[j] < v;
-            tm[r] = v;
-        }
-        __syncwarp();
-        for (int i = lane; i < m; i += 32) mem[i] = tm[i];
-        __syncwarp();
-    }
+    const int* mem = members + (size_t)p * cap + s;
     double c[3];
     aivs_center(g, b, c);
-    double best = 9999.0; int bi = -1;
+    double best = 9999.0; int bi = -1, bidx = 0x7fffffff;
     const double* P = pts + (size_t)p * cap * 3;
     for (int i = lane; i < m; i += 32) {                       // BoxInput: first strict minimum of the distance to the centre
-        const double* q = P + 3 * (size_t)mem[i];
+        const int pi = mem[i];
+        const double* q = P + 3 * (size_t)pi;
         const double dx = __dsub_rn(c[0], q[0]), dy = __dsub_rn(c[1], q[1]), dz = __dsub_rn(c[2], q[2]);
         const double dm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-        if (best > dm) { best = dm; bi = i; }
+        if (best > dm || (bi >= 0 && best == dm && pi < bidx)) { best = dm; bi = i; bidx = pi; }
     }
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {                  // smaller distance, the lower position among equals
+    for (int off = 16; off >= 1; off >>= 1) {                  // smaller distance, the lower original index among equals
         const double ob = __shfl_xor_sync(KSS_FULL, best, off);
-        const int oi = __shfl_xor_sync(KSS_FULL, bi, off);
-        if (oi >= 0 && (bi < 0 || ob < best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+        const int oi = __shfl_xor_sync(KSS_FULL, bi, off), ox = __shfl_xor_sync(KSS_FULL, bidx, off);
+        if (oi >= 0 && (bi < 0 || ob < best || (ob == best && ox < bidx))) { best = ob; bi = oi; bidx = ox; }
     }
     if (lane == 0) {
         center_pos[(size_t)p * bcap + b] = bi;
@@ -301,25 +291,28 @@ __device__ void aivs_fps_box(int p, int b, const AivsGrid& g, const double* __re
         }
     };
     // initial distances: to the nearest already-selected point of the neighbour boxes inside the seed cube,
-    // or (if there is none) to the box's centre-nearest member, which then becomes the first sample
+    // or (if there is none) to the box's centre-nearest member, which then becomes the first sample.  The selected
+    // points of a box are its sample list so far (sel / sel_cnt): lane k looks at neighbour box k.
     for (int t = lane; t < m; t += 32) md[t] = INFINITY;
     bool any_seed = false;
-    for (int a = 0; a < nxs; ++a) for (int c = 0; c < nys; ++c) for (int e = 0; e < nzs; ++e) {
-        if (xs[a] == x_num && ys[c] == y_num && zs[e] == z_num) continue;
-        const int nb = xs[a] + (ys[c] - 1) * g.nx + (zs[e] - 1) * g.nx * g.ny;
-        if (nb >= g.nbox || nb < 0) continue;
-        const int ns = st[nb], nm = st[nb + 1] - ns;
-        for (int l0 = 0; l0 < nm; l0 += 32) {
-            const int l = l0 + lane;
+    {
+        int nb = -1, ncnt = 0;
+        if (lane < 27) {
+            const int a = lane % 3, c = (lane / 3) % 3, e = lane / 9;
+            if (a < nxs && c < nys && e < nzs && !(xs[a] == x_num && ys[c] == y_num && zs[e] == z_num)) {
+                const int q = xs[a] + (ys[c] - 1) * g.nx + (zs[e] - 1) * g.nx * g.ny;
+                if (q < g.nbox && q >= 0) { nb = q; ncnt = sel_cnt[(size_t)p * bcap + q]; }
+            }
+        }
+        const int rounds = __reduce_max_sync(KSS_FULL, ncnt);
+        for (int l = 0; l < rounds; ++l) {
             bool seed = false;
             float sx = 0.f, sy = 0.f, sz = 0.f;
-            if (l < nm) {
-                const int pt = mem[ns + l];
-                if (lab[pt]) {
-                    const double* q = P + 3 * (size_t)pt;
-                    seed = q[0] <= ch[0] && q[0] >= cl[0] && q[1] <= ch[1] && q[1] >= cl[1] && q[2] <= ch[2] && q[2] >= cl[2];
-                    sx = (float)q[0]; sy = (float)q[1]; sz = (float)q[2];
-                }
+            if (l < ncnt) {
+                const int pt = sel[(size_t)p * cap + st[nb] + l];
+                const double* q = P + 3 * (size_t)pt;
+                seed = q[0] <= ch[0] && q[0] >= cl[0] && q[1] <= ch[1] && q[1] >= cl[1] && q[2] <= ch[2] && q[2] >= cl[2];
+                sx = (float)q[0]; sy = (float)q[1]; sz = (float)q[2];
             }
             unsigned bal = __ballot_sync(KSS_FULL, seed);
             any_seed |= bal != 0u;
@@ -343,13 +336,16 @@ __device__ void aivs_fps_box(int p, int b, const AivsGrid& g, const double* __re
         }
     }
     while (sampled < simNum) {
-        int pick = -1; double mx = 0.0;
-        for (int t = lane; t < m; t += 32) if (md[t] > mx) { pick = t; mx = md[t]; }     // the lane's first strict maximum
+        int pick = -1, pidx = 0x7fffffff; double mx = 0.0;
+        for (int t = lane; t < m; t += 32) {                   // the first strict maximum = largest value, lowest original index
+            const double v = md[t];
+            if (v > mx || (pick >= 0 && v == mx && mem[s + t] < pidx)) { pick = t; mx = v; pidx = mem[s + t]; }
+        }
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {              // larger value, the lower position among equals
+        for (int off = 16; off >= 1; off >>= 1) {
             const double om = __shfl_xor_sync(KSS_FULL, mx, off);
-            const int op = __shfl_xor_sync(KSS_FULL, pick, off);
-            if (op >= 0 && (pick < 0 || om > mx || (om == mx && op < pick))) { mx = om; pick = op; }
+            const int op = __shfl_xor_sync(KSS_FULL, pick, off), ox = __shfl_xor_sync(KSS_FULL, pidx, off);
+            if (op >= 0 && (pick < 0 || om > mx || (om == mx && ox < pidx))) { mx = om; pick = op; pidx = ox; }
         }
         if (pick == -1) break;
         const int pp = mem[s + pick];
@@ -1058,7 +1054,7 @@ int aivs_simplify_device(cudaStream_t st, long long* launches, int P, const doub
     aivs_count_kernel<<<gp, 256, 0, st>>>(d_pts, cap, grids, bcap, box_of, box_cnt);
     aivs_scan_kernel<<<P, 1024, 0, st>>>(grids, bcap, box_cnt, box_start, cursor);
     aivs_fill_kernel<<<gp, 256, 0, st>>>(cap, grids, bcap, box_of, cursor, members);
-    aivs_box_kernel<<<gw, 256, 0, st>>>(d_pts, cap, grids, bcap, box_start, members, sel, center_pos, quota);
+    aivs_box_kernel<<<gw, 256, 0, st>>>(d_pts, cap, grids, bcap, box_start, members, center_pos, quota);
     for (int c = 0; c < 16; ++c)
         aivs_fps_kernel<<<(c & 1) ? dim3(1, P) : gw, (c & 1) ? 32 : 256, 0, st>>>(c, d_pts, cap, grids, bcap, box_start, members, center_pos,
                                                                                quota, selected, mind, sel, sel_cnt);
