@@ -1708,7 +1708,6 @@ __device__ __forceinline__ void lg_finish_B(int nchunks, const LgTree& tr, LgSta
 #pragma unroll
     for (int i = 0; i < 3; ++i) { sm[i] = __shfl_sync(KSS_FULL, stv, 16 + i); dm[i] = __shfl_sync(KSS_FULL, stv, 19 + i); }
     const float oon = __shfl_sync(KSS_FULL, stv, 22);
-    LG_TL_SET(2);
     if (threadIdx.x == 0) {
         if (!enough) { st->done = 1; st->converged = 0; return; }      // min_number_correspondences_
         float sigma[9], T[16];
@@ -1805,11 +1804,17 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
             if (i < n) { sv[u] = cur[i]; tv[u] = tg[i]; }
         }
     }
+#ifdef KSS_LG_TIMELINE
+    const unsigned long long k0 = lg_now();
+#endif
     lg_wait_prior();
     if (st->done) return;
     if (threadIdx.x < 16) T[threadIdx.x] = st->Tk[threadIdx.x];
     if (threadIdx.x == 0) s_clean = 0u;
     __syncthreads();
+#ifdef KSS_LG_TIMELINE
+    const unsigned long long k1 = lg_now();
+#endif
     const bool applyT = st->apply_T != 0;
     if (c < nchunks) {
         float4* qa = s_qa[warp]; float4* qb = s_qb[warp];
@@ -1820,6 +1825,11 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
         };
         unsigned nfail = 0u, nlist = 0u, redo = 0u;  // redo: bit u = this lane's point u went through the queue
         int qn = 0;                                  // queue fill (warp-uniform)
+#ifdef KSS_LG_TIMELINE
+        const unsigned long long ka = lg_now();
+        if (__float_as_int(sv[0].w) == 0x7fc12345 || __float_as_int(tv[7].w) == 0x12345678) atomicAdd(&lg_tl[14], 1ull);   // (first use of the loaded data)
+        const unsigned long long kb = lg_now();
+#endif
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + 32 * u;
@@ -1880,6 +1890,10 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
             }
         }
         if (qn > 0) nfail += leftover(lg_list_round(qa, qb, qn, lane, knn, cur, tg, cert, nlist), qn);
+#ifdef KSS_LG_TIMELINE
+        const unsigned long long kc = lg_now();
+        if (threadIdx.x == 0 && st->iters > 400) { atomicAdd(&lg_tl[1], kb - ka); atomicAdd(&lg_tl[2], kc - kb); }
+#endif
         nfail = __reduce_add_sync(KSS_FULL, nfail);
         nlist = __reduce_add_sync(KSS_FULL, nlist);
         if (lane == 0) {
@@ -1899,11 +1913,23 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
             }
             lg_chunk_A(sv, tv, c, tr.S, partA, partD, partK);
         }
+#ifdef KSS_LG_TIMELINE
+        if (threadIdx.x == 0 && st->iters > 400) atomicAdd(&lg_tl[3], lg_now() - kc);
+#endif
     }
     // the clean chunks arrive at their group; a group (and, with nothing open anywhere, the whole of pass A) that
     // completes here is reduced here
+#ifdef KSS_LG_TIMELINE
+    const unsigned long long k2 = lg_now();
+#endif
     __syncthreads();
     const int grp = lg_group_arrive(tr.grpcnt, nchunks, s_clean);
+#ifdef KSS_LG_TIMELINE
+    if (threadIdx.x == 0 && st->iters > 400) {
+        const unsigned long long k3 = lg_now();
+        atomicAdd(&lg_tl[8], k1 - k0); atomicAdd(&lg_tl[9], k2 - k1); atomicAdd(&lg_tl[10], k3 - k2); atomicAdd(&lg_tl[11], 1ull);
+    }
+#endif
     if (grp < 0) return;
     lg_group_A(partA, partD, partK, tr, nchunks, grp);
     if (!lg_groups_done(tr.grpcnt, &st->ticketA, (nchunks + 255) >> 8)) return;
@@ -1950,7 +1976,6 @@ __global__ void __launch_bounds__(256, 4)
 lg_passB_kernel(const float4* __restrict__ cur, const float4* __restrict__ tg, double max2, int n, int nchunks,
                 float* __restrict__ partB /* [9][S] */, LgTree tr,
                 LgState* __restrict__ st, int max_iter, double rot_thr, double trans_thr, double mse_rel, double mse_abs) {
-    LG_TL_MIN(0);
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
     float4 cv[4], gv[4];
     if (c < nchunks) lg_load_half(cur, tg, n, c, 0, cv, gv);          // (pass A does not write them: before the wait)
@@ -1985,16 +2010,13 @@ lg_passB_kernel(const float4* __restrict__ cur, const float4* __restrict__ tg, d
 #ifdef KSS_LG_TIMELINE
     if (threadIdx.x == 0) {
         const unsigned long long tl3 = lg_now();
-        atomicAdd(&lg_tl[8], tl1 - tl0); atomicAdd(&lg_tl[9], tl2 - tl1); atomicAdd(&lg_tl[10], tl3 - tl2); atomicAdd(&lg_tl[11], 1ull);
-        atomicMax(&lg_tl[12], tl3); atomicMin(&lg_tl[13], tl0 + (blockIdx.x >= 296 ? 0ull : ~0ull >> 1));
+        (void)tl3;
     }
 #endif
     if (g < 0) return;
     if (enough) lg_group_f32<9>(partB, tr.S, nchunks, g, tr.l2f, tr.S2);
     if (!lg_groups_done(tr.grpcnt, &st->ticketB, (nchunks + 255) >> 8)) return;
-    LG_TL_SET(1);
     lg_finish_B(nchunks, tr, st, enough, max_iter, rot_thr, trans_thr, mse_rel, mse_abs);
-    LG_TL_SET(3);
 }
 
 // state of a run from the sorted source: positions by original index without a certificate, no matches, the two maps
@@ -2297,7 +2319,7 @@ int large_icp_prepare(cudaStream_t st, long long* launches, const double* d_s, i
     if (r) return r;
     if (n2 > 256) return KSS_ERR_UNSUPPORTED;                     // three reduction levels: n <= 16.7 M source points
 #ifdef KSS_LG_TIMELINE
-    { unsigned long long z[16]; for (int i = 0; i < 16; ++i) z[i] = (i >= 8 && i <= 12) ? 0ull : ~0ull; cudaMemcpyToSymbol(lg_tl, z, sizeof(z)); }
+    { unsigned long long z[16]; for (int i = 0; i < 16; ++i) z[i] = 0ull; cudaMemcpyToSymbol(lg_tl, z, sizeof(z)); }
 #endif
     cudaMemsetAsync(grpcnt, 0, sizeof(unsigned) * S2, st);
     lg_run_init_kernel<<<(n_s + 255) / 256, 256, 0, st>>>(inp, n_s, cur, tg, perm, inv, flagS);
@@ -2400,8 +2422,8 @@ int large_icp_result(cudaStream_t st, LargeIcp* run, float T[16], double* fitnes
     { unsigned long long t[16]; cudaMemcpyFromSymbol(t, lg_tl, sizeof(t));
       fprintf(stderr, "[lg] passB timeline (first CTA start of ANY launch is the min; use a 1-iteration run): first CTA -> last group %.2f us, level 3 %.2f us, SVD etc. %.2f us\n",
               (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3);
-      fprintf(stderr, "[lg] passB per CTA (thread 0): load %.2f us, chunk %.2f us, arrive %.2f us (%llu CTAs); first start -> last arrive %.2f us; first start of a CTA >= 296: +%.2f us\n",
-              t[8] * 1e-3 / t[11], t[9] * 1e-3 / t[11], t[10] * 1e-3 / t[11], t[11], (t[12] - t[0]) * 1e-3, (t[13] - t[0]) * 1e-3);
+      fprintf(stderr, "[lg] track per CTA after iteration 400 (thread 0): start->wait+T %.2f us, chunk work %.2f us [wait for loads %.2f, loop %.2f, sums %.2f], arrive %.2f us (%llu CTA-launches)\n",
+              t[8] * 1e-3 / t[11], t[9] * 1e-3 / t[11], (t[1] + 1) * 1e-3 / t[11], (t[2] + 1) * 1e-3 / t[11], (t[3] + 1) * 1e-3 / t[11], t[10] * 1e-3 / t[11], t[11]);
       unsigned long long z[16]; for (int i = 0; i < 16; ++i) z[i] = ~0ull; cudaMemcpyToSymbol(lg_tl, z, sizeof(z)); }
 #endif
 #ifdef KSS_LG_COUNT

@@ -6,6 +6,6 @@ p = pkg.synth.scan_pair(0, 1000000)
 ctx = pkg.Context(0)
 never = dict(max_iter=1 << 30, fit_eps=-1.0, trans_eps=-1.0)
 ctx.icp_large_begin(p["full_s"], p["full_t"])
-ctx.icp_large_iterate(1, **never)
+ctx.icp_large_iterate(430, **never)
 ctx.synchronize()
 print(ctx.icp_large_end(max_iter=1)["iters"])
