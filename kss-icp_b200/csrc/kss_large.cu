@@ -2349,7 +2349,7 @@ int large_icp_iterations(cudaStream_t st, long long* launches, LargeIcp* run, co
     const double max2 = prm->max_corr_dist * prm->max_corr_dist;
     const int n = run->n_s, nch = run->nchunks;
     const double mse_abs = prm->fitness_eps < 0.0 ? -1.0 : 1e-12;   // fitness_eps < 0: never converge (steady-state timing)
-    static const float margin = [] { const char* e = getenv("KSS_LG_MARGIN"); return e ? (float)atof(e) : 0.5f; }();   // certificate margin, in cells
+    static const float margin = [] { const char* e = getenv("KSS_LG_MARGIN"); return e ? (float)atof(e) : 0.25f; }();  // certificate margin, in cells
     float4 *cur = (float4*)run->cur, *tg = (float4*)run->tg;
     const LgTree tr{run->grpcnt, run->l2f, run->l2d, run->l2k, run->S, run->S2};
     static const bool pdl = !getenv("KSS_LG_NO_PDL");
