@@ -895,9 +895,9 @@ int batch_core(kss_ctx* ctx, const kss_batch* b_in, bool host, kss_pair_result* 
     // two chunks per lane when the batch is big enough for every chunk to give each SM a pair; equal chunk sizes
     if (lanes > 1) {
         // measured on B200 (2,468 / 1,234 / 617 / 309 pairs): two chunks hide one chunk's thin ICP tail behind the other's
-        // kernels (+8 % at 309-617 pairs, neutral at 2,468); with host buffers three chunks also hide most of the copies
+        // kernels (+8 % at 309-617 pairs, neutral at 2,468).  Host buffers: the second chunk's copies overlap the first
+        // chunk's kernels either way; 2,468 pairs end to end 78.4 ms with 2 chunks, 79.8 with 3, 79.6 with 4 (round 2 kernels)
         int want = NP >= 296 ? 2 : 1;
-        if (host && NP >= 3 * 296) want = 3;                         // 2,468 pairs, host buffers: 83.9 ms with 3 chunks, 85.3 with 4, 86.4 with 2
         const char* em = getenv("KSS_CHUNKS");
         if (em && atoi(em) > 0) want = atoi(em);
         int nchunks = std::max((NP + chunk - 1) / chunk, want);
