@@ -918,8 +918,18 @@ int batch_core(kss_ctx* ctx, const kss_batch* b_in, bool host, kss_pair_result* 
     auto alloc = [&](const char* name, size_t bytes, void** out) {
         unsigned char* q; int rr = dev_buf(ctx, name, bytes, &q); *out = q; return rr; };
     int rc = KSS_OK, ci = 0;
-    for (int p0 = 0; p0 < NP && rc == KSS_OK; p0 += chunk, ++ci) {
-        const int P = std::min(chunk, NP - p0);
+    // host buffers, two chunks: nothing runs until the first chunk's clouds are on the device, so the first chunk is the
+    // smaller one (KSS_CHUNK_SKEW = its share).  Measured on the 2,468-pair batch, end to end: 0.40 -> 76.8 ms, while 0.35,
+    // 0.45 and 0.50 all give 79.0 ms (three runs each): the gain is as much the two lanes falling out of step (one lane's
+    // thin ICP tail under the other's sweep) as the shorter first copy, and it is specific to this split
+    int first = chunk;
+    if (host && lanes == 2 && chunk < NP && 2 * chunk >= NP) {
+        static const double skew = [] { const char* e = getenv("KSS_CHUNK_SKEW"); const double v = e ? atof(e) : 0.0; return v > 0.0 && v < 1.0 ? v : 0.4; }();
+        first = std::max(1, (int)(NP * skew + 0.5));
+        chunk = std::max(first, NP - first);
+    }
+    for (int p0 = 0, P = 0; p0 < NP && rc == KSS_OK; p0 += P, ++ci) {
+        P = std::min(ci == 0 ? first : chunk, NP - p0);
         const int lane = ci % lanes;
         cudaStream_t st = ctx->lane_stream[lane];
         ctx->stream = st;
