@@ -1825,6 +1825,15 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
         };
         unsigned nfail = 0u, nlist = 0u, redo = 0u;  // redo: bit u = this lane's point u went through the queue
         int qn = 0;                                  // queue fill (warp-uniform)
+        // runner-ups of the two-candidate certificates (8 % of the points at a fixed point, so nearly every warp has one in
+        // every round of 32): all loads in flight at once -- fetched inside the loop they were eight serial round trips
+        float4 t2v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + 32 * u;
+            t2v[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (i < n && sv[u].w < 0.0f) t2v[u] = tg2[i];
+        }
 #ifdef KSS_LG_TIMELINE
         const unsigned long long ka = lg_now();
         if (__float_as_int(sv[0].w) == 0x7fc12345 || __float_as_int(tv[7].w) == 0x12345678) atomicAdd(&lg_tl[14], 1ull);   // (first use of the loaded data)
@@ -1845,7 +1854,7 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
                 }
                 float d2 = d2_rn(x, y, z, tv[u].x, tv[u].y, tv[u].z);
                 if (two) {                                                  // (rare: points about equally far from two targets)
-                    const float4 t2 = tg2[i];
+                    const float4 t2 = t2v[u];
                     const float d2b = d2_rn(x, y, z, t2.x, t2.y, t2.z);
                     const unsigned long long ka = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(tv[u].w);
                     const unsigned long long kb = ((unsigned long long)__float_as_uint(d2b) << 32) | __float_as_uint(t2.w);
@@ -1902,6 +1911,7 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
             if (nlist) atomicAdd(&st->miss[0], nlist);
             if (!nfail) atomicAdd(&s_clean, 1u);
         }
+        __syncwarp();                                // (without it lane 0 and the other 31 run the whole of pass A one after the other)
         if (!nfail) {
             // pass A of the chunk: matches that went through the queue may have changed
 #pragma unroll
