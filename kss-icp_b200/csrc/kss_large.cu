@@ -1796,12 +1796,21 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * 8 + warp;
     const int i0 = (c << 8) + lane;
-    float4 sv[8], tv[8];                             // {position, d2}, {match, index}: what the sums need
+    float4 sv[8], tv[8], t2v[8];                     // {position, d2}, {match, index}: what the sums need; runner-ups
     if (c < nchunks) {                               // (pass B only reads them: before the wait)
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + 32 * u;
             if (i < n) { sv[u] = cur[i]; tv[u] = tg[i]; }
+        }
+        // runner-ups of the two-candidate certificates (8 % of the points at a fixed point, so nearly every warp has one in
+        // every round of 32): all loads in flight at once -- fetched inside the loop they were eight serial round trips --
+        // and before the wait too (pass B does not write them either)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + 32 * u;
+            t2v[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (i < n && sv[u].w < 0.0f) t2v[u] = tg2[i];
         }
     }
 #ifdef KSS_LG_TIMELINE
@@ -1825,15 +1834,6 @@ lg_track_kernel(int n, int nchunks, float4* __restrict__ cur, float4* __restrict
         };
         unsigned nfail = 0u, nlist = 0u, redo = 0u;  // redo: bit u = this lane's point u went through the queue
         int qn = 0;                                  // queue fill (warp-uniform)
-        // runner-ups of the two-candidate certificates (8 % of the points at a fixed point, so nearly every warp has one in
-        // every round of 32): all loads in flight at once -- fetched inside the loop they were eight serial round trips
-        float4 t2v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + 32 * u;
-            t2v[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (i < n && sv[u].w < 0.0f) t2v[u] = tg2[i];
-        }
 #ifdef KSS_LG_TIMELINE
         const unsigned long long ka = lg_now();
         if (__float_as_int(sv[0].w) == 0x7fc12345 || __float_as_int(tv[7].w) == 0x12345678) atomicAdd(&lg_tl[14], 1ull);   // (first use of the loaded data)
