@@ -1229,10 +1229,93 @@ __device__ __forceinline__ bool lg_warp_search_store(const GlobAcc& gacc, const 
 // global memory (L2-resident: points 16 B, tables, ranks) when that is at most 3 x 3 rows of cells -- exact without
 // proof, and the margin is what the certificate lives on.  The margin is dropped while T_k still moves the point
 // farther than a certificate could survive.  Everything else is counted and queued for the general kernels.
+// the flagged queries of a segment, G lanes each (G = 1: one thread per query)
+template <int G>
+__device__ __forceinline__ void lg_refine_queries(const GlobAcc& gacc, const LgGeom& g, const LgGridView& gv, const float* T, float m, bool walk,
+                                                  const int* s_list, int nl, float4* __restrict__ cur, float4* __restrict__ tg, float4* __restrict__ cert,
+                                                  const int* __restrict__ perm, unsigned char* __restrict__ flagS, int* __restrict__ worklist,
+                                                  LgState* __restrict__ st) {
+    const int tid = threadIdx.x, lane = tid & 31, sub = tid % G;
+    constexpr int QP = 256 / G;                  // queries per pass of the CTA
+    const unsigned gmask = G == 1 ? 0u : (G == 32 ? KSS_FULL : ((1u << G) - 1u) << (lane & ~(G - 1)));
+    for (int e0 = 0; e0 < nl; e0 += QP) {
+        const int e = e0 + tid / G;
+        const bool valid = e < nl;
+        bool unres = false;
+        int pos = 0;
+        if (valid) {
+            pos = s_list[e];
+            const int i = perm[pos];
+            const float4 q = cur[i];
+            float4 t0 = tg[i];
+            const int t_first = __float_as_int(t0.w);
+            unres = true;
+            if (t_first >= 0) {
+                float sd = sqrtf(d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z));
+                // a match that T_k left far behind (beyond the radius its neighbour list covers) bounds the search badly:
+                // walk downhill over the neighbour lists first -- ANY target is a valid bound, and a better one makes
+                // the cube (or, for the general kernels, the seeded pyramid descent) small  (every lane of the group walks)
+                if (walk) {
+                    float d0 = sd * sd;
+                    for (int step = 0; step < 64; ++step) {
+                        const float4* L = gv.knn + (size_t)__float_as_int(t0.w) * LG_KSLOTS;
+                        if (!(sd > __ldg(L).x)) break;
+                        float4 nb = t0; float dn = d0;
+#pragma unroll
+                        for (int k = 1; k < LG_KSLOTS; ++k) {
+                            const float4 c = __ldg(L + k);
+                            const float d = d2_rn(q.x, q.y, q.z, c.x, c.y, c.z);
+                            if (d < dn) { dn = d; nb = c; }
+                        }
+                        if (!(dn < d0)) break;
+                        t0 = nb; d0 = dn; sd = sqrtf(dn);
+                    }
+                    if (sub == 0 && __float_as_int(t0.w) != t_first) tg[i] = t0;          // (the general kernels seed from it)
+                }
+                float nx, ny, nz;
+                xform_point(T, q.x, q.y, q.z, nx, ny, nz);                // how far T_k would move the point once more
+                const float mv = sqrtf((nx - q.x) * (nx - q.x) + (ny - q.y) * (ny - q.y) + (nz - q.z) * (nz - q.z));
+                const float rho = sd * LG_CERT_UP + (2.0f * mv < m ? m : 0.0f);
+                if (rho * g.inv_h * 1.00001f + 0.003f <= 2.6f) {          // (false for NaN too)
+                    Best2 b; b.init();
+                    lg_cube_search(gacc, g, q.x, q.y, q.z, rho, sub, G, b);
+                    if (G > 1) {                                          // the lanes scanned disjoint rows
+#pragma unroll
+                        for (int off = G / 2; off >= 1; off >>= 1) {
+                            const unsigned long long ok = __shfl_xor_sync(gmask, b.key, off);
+                            const float os = __shfl_xor_sync(gmask, b.second, off);
+                            b.update(ok);
+                            b.second = fminf(b.second, os);
+                        }
+                    }
+                    if (b.key != 0xffffffffffffffffull) {                 // (the match itself lies in the cube)
+                        unres = false;
+                        if (sub == 0) {
+                            const unsigned ti = (unsigned)b.key;
+                            const float4 t = ti == (unsigned)__float_as_int(t0.w) ? t0 : __ldg(gv.t_orig + ti);
+                            tg[i] = make_float4(t.x, t.y, t.z, __int_as_float((int)ti));
+                            cur[i] = cert[i] = make_float4(q.x, q.y, q.z, sqrtf(fminf(b.second, rho * rho)) * LG_CERT_DOWN);
+                            flagS[pos] = 0;
+                        }
+                    }
+                }
+            }
+        }
+        const bool mine = valid && unres && sub == 0;
+        const unsigned bal = __ballot_sync(KSS_FULL, mine);
+        if (bal) {
+            unsigned at = 0u;
+            if (lane == 0) at = atomicAdd(&st->n_unres, (unsigned)__popc(bal));
+            at = __shfl_sync(KSS_FULL, at, 0);
+            if (mine) worklist[at + __popc(bal & ((1u << lane) - 1u))] = pos;
+        }
+    }
+}
+
 constexpr int RF_SEG = 2048;                     // sorted positions per CTA of lg_refine_kernel
 __global__ void __launch_bounds__(256)
 lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur, float4* __restrict__ tg, float4* __restrict__ tg2, float4* __restrict__ cert, const int* __restrict__ perm,
-                 unsigned char* __restrict__ flagS, int* __restrict__ worklist, LgState* __restrict__ st, float margin_cells) {
+                 unsigned char* __restrict__ flagS, int* __restrict__ worklist, LgState* __restrict__ st, float margin_cells, int gsel /* lanes per query (1 or 4); 0 = by the count */) {
     __shared__ LgGeom g;
     __shared__ float T[16];
     __shared__ int s_list[RF_SEG];               // flagged positions of the segment, compacted: every lane of a warp searches
@@ -1296,65 +1379,13 @@ lg_refine_kernel(LgGridView gv, int n_q, float4* __restrict__ cur, float4* __res
         if (unres && lane == 0) worklist[atomicAdd(&st->n_unres, 1u)] = pos;
         return;
     }
-    for (int e0 = 0; e0 < nl; e0 += 256) {
-        const int e = e0 + tid;
-        const bool valid = e < nl;
-        bool unres = false;
-        int pos = 0;
-        if (valid) {
-            pos = s_list[e];
-            const int i = perm[pos];
-            const float4 q = cur[i];
-            float4 t0 = tg[i];
-            unres = true;
-            if (__float_as_int(t0.w) >= 0) {
-                float sd = sqrtf(d2_rn(q.x, q.y, q.z, t0.x, t0.y, t0.z));
-                // a match that T_k left far behind (beyond the radius its neighbour list covers) bounds the search badly:
-                // walk downhill over the neighbour lists first -- ANY target is a valid bound, and a better one makes
-                // the cube (or, for the general kernels, the seeded pyramid descent) small
-                if (walk) {
-                    float d0 = sd * sd;
-                    for (int step = 0; step < 64; ++step) {
-                        const float4* L = gv.knn + (size_t)__float_as_int(t0.w) * LG_KSLOTS;
-                        if (!(sd > __ldg(L).x)) break;
-                        float4 nb = t0; float dn = d0;
-#pragma unroll
-                        for (int k = 1; k < LG_KSLOTS; ++k) {
-                            const float4 c = __ldg(L + k);
-                            const float d = d2_rn(q.x, q.y, q.z, c.x, c.y, c.z);
-                            if (d < dn) { dn = d; nb = c; }
-                        }
-                        if (!(dn < d0)) break;
-                        t0 = nb; d0 = dn; sd = sqrtf(dn);
-                    }
-                    if (__float_as_int(t0.w) != __float_as_int(tg[i].w)) tg[i] = t0;     // (the general kernels seed from it)
-                }
-                float nx, ny, nz;
-                xform_point(T, q.x, q.y, q.z, nx, ny, nz);                // how far T_k would move the point once more
-                const float mv = sqrtf((nx - q.x) * (nx - q.x) + (ny - q.y) * (ny - q.y) + (nz - q.z) * (nz - q.z));
-                const float rho = sd * LG_CERT_UP + (2.0f * mv < m ? m : 0.0f);
-                if (rho * g.inv_h * 1.00001f + 0.003f <= 2.6f) {          // (false for NaN too)
-                    Best2 b; b.init();
-                    lg_cube_search(gacc, g, q.x, q.y, q.z, rho, 0, 1, b);
-                    if (b.key != 0xffffffffffffffffull) {                 // (the match itself lies in the cube)
-                        unres = false;
-                        const unsigned ti = (unsigned)b.key;
-                        const float4 t = ti == (unsigned)__float_as_int(t0.w) ? t0 : __ldg(gv.t_orig + ti);
-                        tg[i] = make_float4(t.x, t.y, t.z, __int_as_float((int)ti));
-                        cur[i] = cert[i] = make_float4(q.x, q.y, q.z, sqrtf(fminf(b.second, rho * rho)) * LG_CERT_DOWN);
-                        flagS[pos] = 0;
-                    }
-                }
-            }
-        }
-        const unsigned bal = __ballot_sync(KSS_FULL, valid && unres);
-        if (bal) {
-            unsigned at = 0u;
-            if (lane == 0) at = atomicAdd(&st->n_unres, (unsigned)__popc(bal));
-            at = __shfl_sync(KSS_FULL, at, 0);
-            if (valid && unres) worklist[at + __popc(bal & ((1u << lane) - 1u))] = pos;
-        }
-    }
+    // Up to 128 flagged points in the segment (the iterations around PCL's convergence): four lanes per query, lane = every
+    // fourth row of cells of the cube -- one thread each leaves most of the CTA idle and every search one serial chain of
+    // dependent loads.  Beyond that one thread per query is the cheaper order: the query's own row comes first and its two
+    // distances prune most other rows, which lanes that start elsewhere scan for nothing (measured: 2, 4, 8 lanes; 32 .. 512).
+    if (gsel == 0) gsel = nl <= 128 ? 4 : 1;
+    if (gsel >= 4) lg_refine_queries<4>(gacc, g, gv, T, m, walk, s_list, nl, cur, tg, cert, perm, flagS, worklist, st);
+    else lg_refine_queries<1>(gacc, g, gv, T, m, walk, s_list, nl, cur, tg, cert, perm, flagS, worklist, st);
 }
 
 // The few queries lg_refine_kernel could not finish, one WARP each (persistent grid over the work list): a query with a
@@ -2371,11 +2402,12 @@ int large_icp_iterations(cudaStream_t st, long long* launches, LargeIcp* run, co
         // it only decides whether the staged kernel is worth a launch; the one-warp-per-query kernel takes any count.)
         const int known = run->h_unres ? *(volatile int*)run->h_unres : 0x7fffffff;
         const bool staged = known > n / (int)LG_STAGED_DIV;
+        static const int refine_g = [] { const char* e = getenv("KSS_LG_REFINE_G"); return e ? atoi(e) : 0; }();    // A/B: lanes per query of lg_refine_kernel (1 or 4; default: by the count)
         if (run->mark) run->mark(run->mark_user, KSS_STAGE_LARGE_TRACK, 1);
         launch_pdl(pdl, lg_track_kernel, (nch + 7) / 8, 256, 0, st, n, nch, cur, tg, (float4*)run->tg2, (float4*)run->cert, run->inv, gv.knn, run->flagS, run->dirty, run->partA,
                    run->partD, run->partK, tr, state, max2, (volatile int*)run->h_unres);
         if (run->mark) run->mark(run->mark_user, KSS_STAGE_LARGE_TRACK, 0);
-        launch_pdl(pdl, lg_refine_kernel, (n + RF_SEG - 1) / RF_SEG, 256, 0, st, gv, n, cur, tg, (float4*)run->tg2, (float4*)run->cert, run->perm, run->flagS, run->worklist, state, margin);
+        launch_pdl(pdl, lg_refine_kernel, (n + RF_SEG - 1) / RF_SEG, 256, 0, st, gv, n, cur, tg, (float4*)run->tg2, (float4*)run->cert, run->perm, run->flagS, run->worklist, state, margin, refine_g);
         if (staged) {
             cudaFuncSetAttribute(lg_nn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM);
             launch_pdl(pdl, lg_nn_kernel<1>, nn_grid(n), NN_THREADS, NN_SMEM, st, py, gv, n, cur, (const float4*)nullptr, (int*)nullptr,
