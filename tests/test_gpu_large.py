@@ -191,3 +191,23 @@ def test_large_icp_degenerate_cases(ctx, okss, case):
     assert g["iters"] == o["iters"] and g["converged"] == o["converged"]
     assert np.array_equal(g["T"], o["T"], equal_nan=True)
     assert g["fitness"] == o["fitness"] or (np.isnan(g["fitness"]) and np.isnan(o["fitness"]))
+
+
+def test_large_icp_refine_lanes_switch(ctx, pkg):
+    """lg_refine_kernel searches a flagged point with one thread or with four lanes (every fourth row of cells each, merged
+    by shuffles), by the number of flagged points of the segment: both orders forced through KSS_LG_REFINE_G (read once per
+    process, hence the subprocesses) leave iteration count, transform and fitness bit-identical to the default"""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, json; sys.path.insert(0, %r); import __graft_entry__ as e; pkg = e.load_package(); c = pkg.Context(0); "
+            "p = pkg.synth.scan_pair(5, 40000); g = c.icp(p['full_s'], p['full_t'], max_iter=40, trans_eps=-1.0, fit_eps=0.0); "
+            "print('RES ' + json.dumps({'iters': int(g['iters']), 'T': [float(x).hex() for x in g['T'].ravel()], 'fitness': float(g['fitness']).hex()}))") % root
+    p = pkg.synth.scan_pair(5, 40000)
+    g = ctx.icp(p["full_s"], p["full_t"], max_iter=40, trans_eps=-1.0, fit_eps=0.0)
+    want = {"iters": int(g["iters"]), "T": [float(x).hex() for x in g["T"].ravel()], "fitness": float(g["fitness"]).hex()}
+    for lanes in ("1", "4"):
+        env = dict(os.environ, KSS_LG_REFINE_G=lanes)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        line = [l for l in out.stdout.splitlines() if l.startswith("RES ")][-1]
+        assert json.loads(line[4:]) == want, "KSS_LG_REFINE_G=%s changes the result" % lanes
