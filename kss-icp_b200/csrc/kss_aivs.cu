@@ -390,6 +390,313 @@ aivs_fps_kernel(int phase, const double* __restrict__ pts, int cap, const AivsGr
     aivs_fps_box(p, b, g, pts, cap, bcap, box_start, members, center_pos, quota, selected, mind, sel, sel_cnt);
 }
 
+// The even phases with the box staged in shared memory: the members of a warp's box (coordinates narrowed as the reference
+// narrows them, original indices, running minimum distances -- all of them floats: a distance is a widened float, 9999 and
+// 0 are floats too) are read once; every relax pass and every arg-max then runs over shared memory.  (aivs_fps_box walks
+// its members through global gathers and global minimum distances 10-30 times per box: a 1M-point cloud spent 0.13-0.33 ms
+// per colour there, one dependent chain per warp.)  The arg-max is the reference's first strict maximum = largest value,
+// lowest original index; the order in which seeds are applied does not matter to a minimum.  Boxes with more members than
+// fit take aivs_fps_box.
+constexpr int FPS_WCAP = 512;                // members staged per box by a warp (20 bytes each)
+constexpr int FPS_MCAP = 4096;               // ... by a CTA (aivs_fps_big_kernel)
+constexpr int FPS_BIGCAP = 1024;             // boxes per cloud and colour that can be handed to aivs_fps_big_kernel
+constexpr size_t FPS_SMEM = (size_t)8 * (FPS_WCAP * 20 + 27 * 3 * 4);
+__global__ void __launch_bounds__(256)
+aivs_fps_smem_kernel(int colour, const double* __restrict__ pts, int cap, const AivsGrid* __restrict__ grids, int bcap,
+                     const int* __restrict__ box_start, const int* __restrict__ members, const int* __restrict__ center_pos,
+                     const int* __restrict__ quota, unsigned char* __restrict__ selected, double* __restrict__ mind,
+                     int* __restrict__ sel, int* __restrict__ sel_cnt, int* __restrict__ biglist, int* __restrict__ bigcnt) {
+    extern __shared__ unsigned char fps_raw[];
+    const int p = blockIdx.y;
+    const AivsGrid g = grids[p];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * 8 + warp;
+    if (b < 1 || b >= g.nbox || (b % (g.nx * g.ny)) == 0) return;
+    const int b0 = b - 1;
+    if (aivs_colour(b0 % g.nx + 1, (b0 / g.nx) % g.ny + 1, b0 / (g.nx * g.ny) + 1) != colour) return;
+    const int* st = box_start + (size_t)p * (bcap + 1);
+    const int s = st[b], m = st[b + 1] - s;
+    const int simNum = quota[(size_t)p * bcap + b];
+    if (m == 0 || simNum == 0) return;
+    if (m > FPS_WCAP) {
+        // a big box would be the long pole of the launch on one warp: aivs_fps_big_kernel gives it a CTA (same colour, so
+        // nobody here reads its samples)
+        int slot = FPS_BIGCAP;                                   // (no list: small clouds, where eight more launches cost more than the pole)
+        if (biglist && lane == 0) slot = atomicAdd(&bigcnt[p * 8 + colour], 1);
+        slot = __shfl_sync(KSS_FULL, slot, 0);
+        if (slot < FPS_BIGCAP) { if (lane == 0) biglist[((size_t)p * 8 + colour) * FPS_BIGCAP + slot] = b; }
+        else aivs_fps_box(p, b, g, pts, cap, bcap, box_start, members, center_pos, quota, selected, mind, sel, sel_cnt);
+        return;
+    }
+    float* X = reinterpret_cast<float*>(fps_raw + (size_t)warp * (FPS_WCAP * 20 + 27 * 3 * 4));
+    float* Y = X + FPS_WCAP;
+    float* Z = Y + FPS_WCAP;
+    float* MD = Z + FPS_WCAP;
+    int* IDX = reinterpret_cast<int*>(MD + FPS_WCAP);
+    float* sd = reinterpret_cast<float*>(IDX + FPS_WCAP);        // [27][3] seeds of one round
+    const int* mem = members + (size_t)p * cap;
+    const double* P = pts + (size_t)p * cap * 3;
+    unsigned char* lab = selected + (size_t)p * cap;
+    int* out = sel + (size_t)p * cap + s;
+    for (int t = lane; t < m; t += 32) {
+        const int i = mem[s + t];
+        const double* w = P + 3 * (size_t)i;
+        X[t] = (float)w[0]; Y[t] = (float)w[1]; Z[t] = (float)w[2];
+        IDX[t] = i;
+        MD[t] = INFINITY;
+    }
+    // seeds: the already-selected points of the neighbour boxes inside the seed cube (lane k looks at neighbour box k)
+    double pc[3];
+    aivs_center(g, b, pc);
+    const double radius = __ddiv_rn(__dmul_rn(g.unit, 3.0), 4.0);
+    const double cl[3] = {__dsub_rn(pc[0], radius), __dsub_rn(pc[1], radius), __dsub_rn(pc[2], radius)};
+    const double ch[3] = {__dadd_rn(pc[0], radius), __dadd_rn(pc[1], radius), __dadd_rn(pc[2], radius)};
+    const int z_num = b / (g.nx * g.ny) + 1;
+    const int leveZ = b % (g.nx * g.ny);
+    const int y_num = leveZ / g.nx + 1;
+    const int x_num = leveZ % g.nx;
+    int xs[3], ys[3], zs[3], nxs = 0, nys = 0, nzs = 0;
+    if (x_num > 1) xs[nxs++] = x_num - 1;
+    xs[nxs++] = x_num;
+    if (x_num < g.nx) xs[nxs++] = x_num + 1;
+    if (y_num > 1) ys[nys++] = y_num - 1;
+    ys[nys++] = y_num;
+    if (y_num < g.ny) ys[nys++] = y_num + 1;
+    if (z_num > 1) zs[nzs++] = z_num - 1;
+    zs[nzs++] = z_num;
+    if (z_num < g.nz) zs[nzs++] = z_num + 1;
+    int nb = -1, ncnt = 0;
+    if (lane < 27) {
+        const int a = lane % 3, c = (lane / 3) % 3, e = lane / 9;
+        if (a < nxs && c < nys && e < nzs && !(xs[a] == x_num && ys[c] == y_num && zs[e] == z_num)) {
+            const int q = xs[a] + (ys[c] - 1) * g.nx + (zs[e] - 1) * g.nx * g.ny;
+            if (q < g.nbox && q >= 0) { nb = q; ncnt = sel_cnt[(size_t)p * bcap + q]; }
+        }
+    }
+    const int rounds = __reduce_max_sync(KSS_FULL, ncnt);
+    bool any_seed = false;
+    __syncwarp();
+    for (int l = 0; l < rounds; ++l) {
+        bool seed = false;
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        if (l < ncnt) {
+            const int pt = sel[(size_t)p * cap + st[nb] + l];
+            const double* q = P + 3 * (size_t)pt;
+            seed = q[0] <= ch[0] && q[0] >= cl[0] && q[1] <= ch[1] && q[1] >= cl[1] && q[2] <= ch[2] && q[2] >= cl[2];
+            sx = (float)q[0]; sy = (float)q[1]; sz = (float)q[2];
+        }
+        const unsigned bal = __ballot_sync(KSS_FULL, seed);
+        if (!bal) continue;
+        any_seed = true;
+        if (seed) { const int k = __popc(bal & ((1u << lane) - 1u)); sd[3 * k] = sx; sd[3 * k + 1] = sy; sd[3 * k + 2] = sz; }
+        __syncwarp();
+        const int ns = __popc(bal);
+        for (int t = lane; t < m; t += 32) {
+            float md = MD[t];
+            const float x = X[t], y = Y[t], z = Z[t];
+            for (int k = 0; k < ns; ++k) {
+                const float d = __fsqrt_rn(d2_rn(x, y, z, sd[3 * k], sd[3 * k + 1], sd[3 * k + 2]));
+                if (d < md) md = d;
+            }
+            MD[t] = md;
+        }
+        __syncwarp();
+    }
+    for (int t = lane; t < m; t += 32) if (MD[t] == INFINITY) MD[t] = 9999.0f;
+    __syncwarp();
+    int sampled = 0;
+    if (!any_seed) {
+        const int ci = center_pos[(size_t)p * bcap + b];
+        if (ci >= 0 && ci < m) {
+            const float sx = X[ci], sy = Y[ci], sz = Z[ci];
+            for (int t = lane; t < m; t += 32) MD[t] = __fsqrt_rn(d2_rn(X[t], Y[t], Z[t], sx, sy, sz));
+            __syncwarp();
+            if (lane == 0) { MD[ci] = 0.0f; out[0] = IDX[ci]; lab[IDX[ci]] = 1; }
+            sampled = 1;
+            __syncwarp();
+        }
+    }
+    while (sampled < simNum) {
+        int pick = -1, pidx = 0x7fffffff; float mx = 0.0f;
+        for (int t = lane; t < m; t += 32) {                   // the first strict maximum = largest value, lowest original index
+            const float v = MD[t];
+            if (v > mx || (pick >= 0 && v == mx && IDX[t] < pidx)) { pick = t; mx = v; pidx = IDX[t]; }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const float om = __shfl_xor_sync(KSS_FULL, mx, off);
+            const int op = __shfl_xor_sync(KSS_FULL, pick, off), ox = __shfl_xor_sync(KSS_FULL, pidx, off);
+            if (op >= 0 && (pick < 0 || om > mx || (om == mx && ox < pidx))) { mx = om; pick = op; pidx = ox; }
+        }
+        if (pick == -1) break;
+        if (lane == 0) { MD[pick] = 0.0f; lab[pidx] = 1; out[sampled] = pidx; }
+        ++sampled;
+        __syncwarp();
+        const float sx = X[pick], sy = Y[pick], sz = Z[pick];
+        for (int t = lane; t < m; t += 32) {
+            const float d = __fsqrt_rn(d2_rn(X[t], Y[t], Z[t], sx, sy, sz));
+            if (d < MD[t]) MD[t] = d;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) sel_cnt[(size_t)p * bcap + b] = sampled;
+}
+
+// The boxes aivs_fps_smem_kernel set aside (more than FPS_WCAP members), one CTA each: the same algorithm with 256 threads
+// over the staged members, the arg-max reduced over the CTA with the same rule.
+__global__ void __launch_bounds__(256)
+aivs_fps_big_kernel(int colour, const double* __restrict__ pts, int cap, const AivsGrid* __restrict__ grids, int bcap,
+                    const int* __restrict__ box_start, const int* __restrict__ members, const int* __restrict__ center_pos,
+                    const int* __restrict__ quota, unsigned char* __restrict__ selected, double* __restrict__ mind,
+                    int* __restrict__ sel, int* __restrict__ sel_cnt, const int* __restrict__ biglist, const int* __restrict__ bigcnt) {
+    extern __shared__ unsigned char fps_raw[];
+    __shared__ float sd[27][3];
+    __shared__ int s_nseed, s_any, s_rounds, s_pick;
+    __shared__ float r_v[8];
+    __shared__ int r_t[8], r_i[8];
+    const int p = blockIdx.y;
+    const AivsGrid g = grids[p];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nbig = min(bigcnt[p * 8 + colour], FPS_BIGCAP);
+    float* X = reinterpret_cast<float*>(fps_raw);
+    float* Y = X + FPS_MCAP;
+    float* Z = Y + FPS_MCAP;
+    float* MD = Z + FPS_MCAP;
+    int* IDX = reinterpret_cast<int*>(MD + FPS_MCAP);
+    const int* st = box_start + (size_t)p * (bcap + 1);
+    const int* mem = members + (size_t)p * cap;
+    const double* P = pts + (size_t)p * cap * 3;
+    unsigned char* lab = selected + (size_t)p * cap;
+    for (int e = blockIdx.x; e < nbig; e += gridDim.x) {
+        __syncthreads();                                         // (the previous box of this CTA is done with the shared arrays)
+        const int b = biglist[((size_t)p * 8 + colour) * FPS_BIGCAP + e];
+        const int s = st[b], m = st[b + 1] - s;
+        const int simNum = quota[(size_t)p * bcap + b];
+        if (m > FPS_MCAP) {
+            if (tid < 32) aivs_fps_box(p, b, g, pts, cap, bcap, box_start, members, center_pos, quota, selected, mind, sel, sel_cnt);
+            continue;
+        }
+        int* out = sel + (size_t)p * cap + s;
+        for (int t = tid; t < m; t += 256) {
+            const int i = mem[s + t];
+            const double* w = P + 3 * (size_t)i;
+            X[t] = (float)w[0]; Y[t] = (float)w[1]; Z[t] = (float)w[2];
+            IDX[t] = i;
+            MD[t] = INFINITY;
+        }
+        // seeds: warp 0 finds them, 27 neighbour boxes at a time
+        int nb = -1, ncnt = 0;
+        double cl[3] = {0.0, 0.0, 0.0}, ch[3] = {0.0, 0.0, 0.0};
+        if (warp == 0) {
+            double pc[3];
+            aivs_center(g, b, pc);
+            const double radius = __ddiv_rn(__dmul_rn(g.unit, 3.0), 4.0);
+            for (int a = 0; a < 3; ++a) { cl[a] = __dsub_rn(pc[a], radius); ch[a] = __dadd_rn(pc[a], radius); }
+            const int z_num = b / (g.nx * g.ny) + 1;
+            const int leveZ = b % (g.nx * g.ny);
+            const int y_num = leveZ / g.nx + 1;
+            const int x_num = leveZ % g.nx;
+            int xs[3], ys[3], zs[3], nxs = 0, nys = 0, nzs = 0;
+            if (x_num > 1) xs[nxs++] = x_num - 1;
+            xs[nxs++] = x_num;
+            if (x_num < g.nx) xs[nxs++] = x_num + 1;
+            if (y_num > 1) ys[nys++] = y_num - 1;
+            ys[nys++] = y_num;
+            if (y_num < g.ny) ys[nys++] = y_num + 1;
+            if (z_num > 1) zs[nzs++] = z_num - 1;
+            zs[nzs++] = z_num;
+            if (z_num < g.nz) zs[nzs++] = z_num + 1;
+            if (lane < 27) {
+                const int a = lane % 3, c = (lane / 3) % 3, e2 = lane / 9;
+                if (a < nxs && c < nys && e2 < nzs && !(xs[a] == x_num && ys[c] == y_num && zs[e2] == z_num)) {
+                    const int q = xs[a] + (ys[c] - 1) * g.nx + (zs[e2] - 1) * g.nx * g.ny;
+                    if (q < g.nbox && q >= 0) { nb = q; ncnt = sel_cnt[(size_t)p * bcap + q]; }
+                }
+            }
+            const int rounds = __reduce_max_sync(KSS_FULL, ncnt);
+            if (lane == 0) { s_rounds = rounds; s_any = 0; }
+        }
+        __syncthreads();
+        const int rounds = s_rounds;
+        for (int l = 0; l < rounds; ++l) {
+            if (warp == 0) {
+                bool seed = false;
+                float sx = 0.f, sy = 0.f, sz = 0.f;
+                if (l < ncnt) {
+                    const int pt = sel[(size_t)p * cap + st[nb] + l];
+                    const double* q = P + 3 * (size_t)pt;
+                    seed = q[0] <= ch[0] && q[0] >= cl[0] && q[1] <= ch[1] && q[1] >= cl[1] && q[2] <= ch[2] && q[2] >= cl[2];
+                    sx = (float)q[0]; sy = (float)q[1]; sz = (float)q[2];
+                }
+                const unsigned bal = __ballot_sync(KSS_FULL, seed);
+                if (seed) { const int k = __popc(bal & ((1u << lane) - 1u)); sd[k][0] = sx; sd[k][1] = sy; sd[k][2] = sz; }
+                if (lane == 0) { s_nseed = __popc(bal); if (bal) s_any = 1; }
+            }
+            __syncthreads();
+            const int ns = s_nseed;
+            if (ns)
+                for (int t = tid; t < m; t += 256) {
+                    float md = MD[t];
+                    const float x = X[t], y = Y[t], z = Z[t];
+                    for (int k = 0; k < ns; ++k) {
+                        const float d = __fsqrt_rn(d2_rn(x, y, z, sd[k][0], sd[k][1], sd[k][2]));
+                        if (d < md) md = d;
+                    }
+                    MD[t] = md;
+                }
+            __syncthreads();
+        }
+        for (int t = tid; t < m; t += 256) if (MD[t] == INFINITY) MD[t] = 9999.0f;
+        __syncthreads();
+        int sampled = 0;
+        if (!s_any) {
+            const int ci = center_pos[(size_t)p * bcap + b];
+            if (ci >= 0 && ci < m) {
+                const float sx = X[ci], sy = Y[ci], sz = Z[ci];
+                for (int t = tid; t < m; t += 256) MD[t] = __fsqrt_rn(d2_rn(X[t], Y[t], Z[t], sx, sy, sz));
+                __syncthreads();
+                if (tid == 0) { MD[ci] = 0.0f; out[0] = IDX[ci]; lab[IDX[ci]] = 1; }
+                sampled = 1;
+                __syncthreads();
+            }
+        }
+        while (sampled < simNum) {
+            int pick = -1, pidx = 0x7fffffff; float mx = 0.0f;
+            for (int t = tid; t < m; t += 256) {
+                const float v = MD[t];
+                if (v > mx || (pick >= 0 && v == mx && IDX[t] < pidx)) { pick = t; mx = v; pidx = IDX[t]; }
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const float om = __shfl_xor_sync(KSS_FULL, mx, off);
+                const int op = __shfl_xor_sync(KSS_FULL, pick, off), ox = __shfl_xor_sync(KSS_FULL, pidx, off);
+                if (op >= 0 && (pick < 0 || om > mx || (om == mx && ox < pidx))) { mx = om; pick = op; pidx = ox; }
+            }
+            if (lane == 0) { r_v[warp] = mx; r_t[warp] = pick; r_i[warp] = pidx; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < 8; ++w) {
+                    const float om = r_v[w]; const int op = r_t[w], ox = r_i[w];
+                    if (op >= 0 && (pick < 0 || om > mx || (om == mx && ox < pidx))) { mx = om; pick = op; pidx = ox; }
+                }
+                s_pick = pick;
+                if (pick >= 0) { MD[pick] = 0.0f; lab[pidx] = 1; out[sampled] = pidx; }
+            }
+            __syncthreads();
+            pick = s_pick;
+            if (pick == -1) break;
+            ++sampled;
+            const float sx = X[pick], sy = Y[pick], sz = Z[pick];
+            for (int t = tid; t < m; t += 256) {
+                const float d = __fsqrt_rn(d2_rn(X[t], Y[t], Z[t], sx, sy, sz));
+                if (d < MD[t]) MD[t] = d;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) sel_cnt[(size_t)p * bcap + b] = sampled;
+    }
+}
+
 // ---------------------------------------------------------------- 4. samples in box order, K = 3 lists, greedy trim
 constexpr int AIVS_MAX_SAMPLES = 16384;      // trim works on at most this many samples per cloud (14-bit ids in the sort key)
 
@@ -1023,7 +1330,10 @@ int aivs_simplify_device(cudaStream_t st, long long* launches, int P, const doub
     };
     AivsGrid* grids; int *box_of, *box_cnt, *box_start, *cursor, *members, *center_pos, *quota, *sel, *sel_cnt, *sel_start, *sample;
     unsigned char* selected; double* mind; unsigned long long *key1, *ext; float* dis2;
+    int *biglist, *bigcnt;
     int r = 0;
+    r |= get("biglist", sizeof(int) * (size_t)P * 8 * FPS_BIGCAP, (void**)&biglist);
+    r |= get("bigcnt", sizeof(int) * (size_t)P * 8, (void**)&bigcnt);
     r |= get("ext", sizeof(unsigned long long) * (size_t)P * 6, (void**)&ext);
     r |= get("grids", sizeof(AivsGrid) * (size_t)P, (void**)&grids);
     r |= get("box_of", sizeof(int) * (size_t)P * cap, (void**)&box_of);
@@ -1046,6 +1356,7 @@ int aivs_simplify_device(cudaStream_t st, long long* launches, int P, const doub
     cudaMemsetAsync(box_cnt, 0, sizeof(int) * (size_t)P * bcap, st);
     cudaMemsetAsync(sel_cnt, 0, sizeof(int) * (size_t)P * bcap, st);
     cudaMemsetAsync(selected, 0, (size_t)P * cap, st);
+    cudaMemsetAsync(bigcnt, 0, sizeof(int) * (size_t)P * 8, st);
     cudaMemset2DAsync(ext, 48, 0xff, 24, P, st);                      // min keys: all ones
     cudaMemset2DAsync(ext + 3, 48, 0x00, 24, P, st);                  // max keys: zero
     aivs_extent_kernel<<<dim3(std::max(1, std::min((cap + 2047) / 2048, 1184 / std::max(P, 1) + 1)), P), 256, 0, st>>>(d_pts, d_cnt, cap, ext);
@@ -1055,9 +1366,19 @@ int aivs_simplify_device(cudaStream_t st, long long* launches, int P, const doub
     aivs_scan_kernel<<<P, 1024, 0, st>>>(grids, bcap, box_cnt, box_start, cursor);
     aivs_fill_kernel<<<gp, 256, 0, st>>>(cap, grids, bcap, box_of, cursor, members);
     aivs_box_kernel<<<gw, 256, 0, st>>>(d_pts, cap, grids, bcap, box_start, members, center_pos, quota);
+    static const bool fps_warp = getenv("KSS_AIVS_FPS_WARP") != nullptr;          // A/B: the even phases through global memory too (aivs_fps_box)
+    if (!fps_warp && (cudaFuncSetAttribute(aivs_fps_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FPS_SMEM) != cudaSuccess ||
+                      cudaFuncSetAttribute(aivs_fps_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FPS_MCAP * 20) != cudaSuccess)) return KSS_ERR_CUDA;
+    const bool use_big = cap >= 250000;                                            // (boxes beyond FPS_WCAP members are the rule there)
     for (int c = 0; c < 16; ++c)
-        aivs_fps_kernel<<<(c & 1) ? dim3(1, P) : gw, (c & 1) ? 32 : 256, 0, st>>>(c, d_pts, cap, grids, bcap, box_start, members, center_pos,
-                                                                               quota, selected, mind, sel, sel_cnt);
+        if (!(c & 1) && !fps_warp) {
+            aivs_fps_smem_kernel<<<gw, 256, FPS_SMEM, st>>>(c >> 1, d_pts, cap, grids, bcap, box_start, members, center_pos,
+                                                            quota, selected, mind, sel, sel_cnt, use_big ? biglist : nullptr, bigcnt);
+            if (use_big) aivs_fps_big_kernel<<<dim3(std::max(1, 296 / std::max(P, 1)), P), 256, FPS_MCAP * 20, st>>>(c >> 1, d_pts, cap, grids, bcap, box_start, members, center_pos,
+                                                                                   quota, selected, mind, sel, sel_cnt, biglist, bigcnt);
+        } else
+            aivs_fps_kernel<<<(c & 1) ? dim3(1, P) : gw, (c & 1) ? 32 : 256, 0, st>>>(c, d_pts, cap, grids, bcap, box_start, members, center_pos,
+                                                                                   quota, selected, mind, sel, sel_cnt);
     aivs_scan_kernel<<<P, 1024, 0, st>>>(grids, bcap, sel_cnt, sel_start, nullptr);
     aivs_gather_kernel<<<gb, 256, 0, st>>>(cap, grids, bcap, box_start, sel, sel_cnt, sel_start, sample);
     aivs_k3_kernel<<<dim3((smax + 255) / 256, P), 256, 0, st>>>(d_pts, cap, grids, bcap, sel_start, sample, key1, dis2);
@@ -1066,7 +1387,7 @@ int aivs_simplify_device(cudaStream_t st, long long* launches, int P, const doub
     if (cudaFuncSetAttribute(aivs_cut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return KSS_ERR_CUDA;
     aivs_cut_kernel<<<P, 512, smem, st>>>(d_pts, cap, grids, bcap, sel_start, sample, key1, dis2, np2, d_out, out_cap, d_out_cnt,
                                           d_out_idx, d_bad);
-    *launches += 26;
+    *launches += (fps_warp || !use_big) ? 26 : 34;
     return cudaGetLastError() == cudaSuccess ? KSS_OK : KSS_ERR_CUDA;
 }
 

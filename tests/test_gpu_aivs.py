@@ -226,3 +226,12 @@ def test_register_raw_large_clouds(ctx, okss, pkg):
     assert np.array_equal(raw["T"], one["T"])
     for k in ("mse", "rmse", "mae"):
         assert abs(raw[k] - one[k]) <= 1e-12 * max(1.0, abs(one[k])), k
+
+
+def test_aivs_big_boxes_take_the_cta_path(ctx, okss, pkg):
+    """clouds from 250,000 points on hand the boxes with more than 512 members to aivs_fps_big_kernel (one CTA per box,
+    members staged in shared memory) and stage the others per warp: a non-uniform 300k-point scan has both kinds -- the
+    kept points are still the oracle's, index for index"""
+    p = pkg.synth.scan_pair(7, 300000)
+    idx = _check(ctx, okss, p["full_t"], 2000)
+    assert len(np.unique(idx)) == len(idx)
