@@ -981,8 +981,25 @@ int batch_core(kss_ctx* ctx, const kss_batch* b_in, bool host, kss_pair_result* 
                 BUF("aivs_sim_s", (size_t)P * bb.cap_s * 3, &d_ss); BUF("aivs_sim_t", (size_t)P * bb.cap_t * 3, &d_st);
                 BUF("aivs_pn", P, &d_pn); BUF("aivs_cnt_s", P, &d_cs); BUF("aivs_cnt_t", P, &d_ct);
                 q = aivs_pnumber_device(st, &ctx->launches, P, c_S, bb.cap_S, c_T, bb.cap_T, d_pn);
+                // Clouds beyond one CTA (the any-size kernels: ~30 small launches per cloud, a chain of latencies for a pair or two):
+                // the source on a side stream next to the target (separate scratch, tags "s" / "t").  Batches of small clouds are
+                // throughput-bound, one stream.
+                const bool side = (bb.cap_S > SMALL_MAX || bb.cap_T > SMALL_MAX) && P <= 4 && !getenv("KSS_AIVS_ONE_STREAM");
+                cudaStream_t st_s = st;
+                if (side) {
+                    if (!ctx->mq_fork) CU(cudaEventCreateWithFlags(&ctx->mq_fork, cudaEventDisableTiming));
+                    if (!ctx->mq_stream[0]) CU(cudaStreamCreateWithFlags(&ctx->mq_stream[0], cudaStreamNonBlocking));
+                    if (!ctx->mq_done[0]) CU(cudaEventCreateWithFlags(&ctx->mq_done[0], cudaEventDisableTiming));
+                    CU(cudaEventRecord(ctx->mq_fork, st));
+                    CU(cudaStreamWaitEvent(ctx->mq_stream[0], ctx->mq_fork, 0));
+                    st_s = ctx->mq_stream[0];
+                }
                 if (!q) q = aivs_simplify_device(st, &ctx->launches, P, full_t, c_T, bb.cap_T, d_pn, 0, d_st, bb.cap_t, d_ct, nullptr, d_bad, alloc, "t");
-                if (!q) q = aivs_simplify_device(st, &ctx->launches, P, full_s, c_S, bb.cap_S, d_pn, 0, d_ss, bb.cap_s, d_cs, nullptr, d_bad, alloc, "s");
+                if (!q) q = aivs_simplify_device(st_s, &ctx->launches, P, full_s, c_S, bb.cap_S, d_pn, 0, d_ss, bb.cap_s, d_cs, nullptr, d_bad, alloc, "s");
+                if (side) {
+                    CU(cudaEventRecord(ctx->mq_done[0], st_s));
+                    CU(cudaStreamWaitEvent(st, ctx->mq_done[0], 0));
+                }
                 if (q) return fail(ctx, q, "AIVS simplification failed to launch");
                 sim_s = d_ss; sim_t = d_st; c_s = d_cs; c_t = d_ct;
             } else {
