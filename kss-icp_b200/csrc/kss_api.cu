@@ -981,10 +981,10 @@ int batch_core(kss_ctx* ctx, const kss_batch* b_in, bool host, kss_pair_result* 
                 BUF("aivs_sim_s", (size_t)P * bb.cap_s * 3, &d_ss); BUF("aivs_sim_t", (size_t)P * bb.cap_t * 3, &d_st);
                 BUF("aivs_pn", P, &d_pn); BUF("aivs_cnt_s", P, &d_cs); BUF("aivs_cnt_t", P, &d_ct);
                 q = aivs_pnumber_device(st, &ctx->launches, P, c_S, bb.cap_S, c_T, bb.cap_T, d_pn);
-                // Clouds beyond one CTA (the any-size kernels: ~30 small launches per cloud, a chain of latencies for a pair or two):
-                // the source on a side stream next to the target (separate scratch, tags "s" / "t").  Batches of small clouds are
-                // throughput-bound, one stream.
-                const bool side = (bb.cap_S > SMALL_MAX || bb.cap_T > SMALL_MAX) && P <= 4 && !getenv("KSS_AIVS_ONE_STREAM");
+                // Clouds beyond one CTA (the any-size kernels: ~30 small launches per batch of clouds, mostly chains of latencies):
+                // the sources on a side stream next to the targets (separate scratch, tags "s" / "t"; one pair of 10k points
+                // 3.5 -> 3.1 ms, 64 of them: AIVS 6.3 -> 5.3 ms).  Batches of small clouds are throughput-bound, one stream.
+                const bool side = (bb.cap_S > SMALL_MAX || bb.cap_T > SMALL_MAX) && !getenv("KSS_AIVS_ONE_STREAM");
                 cudaStream_t st_s = st;
                 if (side) {
                     if (!ctx->mq_fork) CU(cudaEventCreateWithFlags(&ctx->mq_fork, cudaEventDisableTiming));
